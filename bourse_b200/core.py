@@ -1,0 +1,424 @@
+"""Drop-in mirror of the reference's Python extension module ``bourse.core``.
+
+Same class names, constructor/method signatures, return layouts and error behaviour as the PyO3
+classes (reference: ``rust/src/order_book.rs:35-398``, ``rust/src/step_sim.rs:55-608``,
+``rust/src/step_sim_numpy.rs:66-517``, tuples ``rust/src/types.rs:4-40``), backed by the CUDA library
+through the C ABI (``include/bourse_b200.h``) — every book lives on the GPU and every mutation is a
+kernel launch.  There is no CPU implementation behind these classes.
+
+``BatchedEnv`` is the native shape of the new framework: thousands of independent envs advanced in
+lockstep, with the same per-env semantics.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import typing
+
+import numpy as np
+
+from . import abi
+
+MAX_PRICE = 2**32 - 1
+
+
+class PanicException(Exception):
+    """Raised where the reference would panic (e.g. an unknown order id, orderbook.rs:642)."""
+
+
+def _check(lib, h, rc):
+    if rc == abi.BB_OK:
+        return
+    msg = lib.bb_last_error(h)
+    msg = msg.decode() if msg else f"bourse_b200 error {rc}"
+    if rc == abi.BB_EPRICE:
+        raise ValueError(msg)
+    if rc == abi.BB_EBADID:
+        raise PanicException(msg)
+    if rc == abi.BB_ECAP:
+        raise MemoryError(msg)
+    if rc == abi.BB_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+class BatchedEnv:
+    """`n_envs` independent Env instances (crates/step_sim/src/env.rs:58-71) on one GPU."""
+
+    def __init__(self, n_envs: int, seed: int, start_time: int, tick_size: int, step_size: int, trading: bool = True, *,
+                 device: int = 0, env_id_base: int = 0, obs_words: int = abi.OBS_L2, max_orders: int = 1 << 16,
+                 max_trades: int = 1 << 16, max_steps: int = 1 << 12, max_queue: int = 256, pages_smem: int = 0,
+                 pages_total: int = 0, price_granule: int = 0):
+        self._lib = abi.load()
+        cfg = abi.Config()
+        cfg.struct_size = C.sizeof(abi.Config)
+        cfg.device, cfg.n_envs, cfg.env_id_base = device, n_envs, env_id_base
+        cfg.start_time, cfg.step_size, cfg.seed = start_time, step_size, seed
+        cfg.tick_size, cfg.price_granule, cfg.trading = tick_size, price_granule, int(trading)
+        cfg.obs_words, cfg.max_orders, cfg.max_trades = obs_words, max_orders, max_trades
+        cfg.max_steps, cfg.max_queue = max_steps, max_queue
+        cfg.pages_smem, cfg.pages_total = pages_smem, pages_total
+        self._h = C.c_void_p()
+        self.n_envs, self.obs_words, self.tick_size = n_envs, obs_words, tick_size
+        rc = self._lib.bb_create(C.byref(cfg), C.byref(self._h))
+        if rc != abi.BB_OK:
+            msg = self._lib.bb_last_error(None)
+            self._h = C.c_void_p()
+            raise RuntimeError(f"bb_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.bb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _check(self._lib, self._h, rc)
+
+    # ------------------------------------------------------------------ control
+    def reset(self): self._ck(self._lib.bb_reset(self._h))
+    def synchronize(self): self._ck(self._lib.bb_synchronize(self._h))
+    def set_stream(self, cuda_stream: int): self._ck(self._lib.bb_set_stream(self._h, C.c_void_p(cuda_stream)))
+    def set_trading(self, on: bool, env: int = abi.ALL_ENVS): self._ck(self._lib.bb_set_trading(self._h, env, int(on)))
+    def set_time(self, env: int, t: int): self._ck(self._lib.bb_set_time(self._h, env, t))
+
+    def time(self, env: int = 0) -> int:
+        t = C.c_uint64()
+        self._ck(self._lib.bb_time(self._h, env, C.byref(t)))
+        return t.value
+
+    # ------------------------------------------------------------------ Env mode
+    def submit(self, action, side=None, vol=None, trader=None, price=None, order_id=None, env=None, flags=None):
+        """Batched Env::place_order / cancel_order / modify_order; returns u64 ids (NO_ID where none)."""
+        action = np.ascontiguousarray(action, dtype=np.uint32)
+        n = len(action)
+
+        def arr(x, dt):
+            if x is None:
+                return None
+            x = np.ascontiguousarray(x, dtype=dt)
+            if len(x) != n:
+                raise ValueError("instruction arrays must have equal length")
+            return x
+
+        if side is not None:
+            side = arr(np.asarray(side).astype(np.uint8), np.uint8)
+        vol, trader, price = arr(vol, np.uint32), arr(trader, np.uint32), arr(price, np.uint32)
+        order_id, env, flags = arr(order_id, np.uint64), arr(env, np.uint32), arr(flags, np.uint32)
+        out = np.empty(n, dtype=np.uint64)
+        done = C.c_uint64()
+        rc = self._lib.bb_submit(self._h, n, abi.ptr(env), abi.ptr(action), abi.ptr(side), abi.ptr(vol), abi.ptr(trader),
+                                 abi.ptr(price), abi.ptr(order_id), abi.ptr(flags), abi.ptr(out), C.byref(done))
+        self._ck(rc)
+        return out
+
+    def step(self, n_steps: int = 1): self._ck(self._lib.bb_step(self._h, n_steps))
+
+    # ------------------------------------------------------------------ immediate mode / replay
+    def replay(self, instrs: np.ndarray, env_offsets=None):
+        instrs = np.ascontiguousarray(instrs, dtype=abi.INSTR_DTYPE)
+        if env_offsets is None:
+            if self.n_envs != 1:
+                raise ValueError("env_offsets required when n_envs > 1")
+            env_offsets = np.array([0, len(instrs)], dtype=np.uint64)
+        env_offsets = np.ascontiguousarray(env_offsets, dtype=np.uint64)
+        if len(env_offsets) != self.n_envs + 1 or env_offsets[-1] != len(instrs):
+            raise ValueError("env_offsets must have n_envs + 1 entries ending at len(instrs)")
+        self._ck(self._lib.bb_replay(self._h, abi.ptr(instrs), abi.ptr(env_offsets)))
+
+    def replay_device(self, d_instrs_ptr: int, d_offsets_ptr: int):
+        self._ck(self._lib.bb_replay_device(self._h, C.c_void_p(d_instrs_ptr), C.c_void_p(d_offsets_ptr)))
+
+    # ------------------------------------------------------------------ in-kernel agents
+    def set_agents(self, groups):
+        arr = np.zeros(len(groups), dtype=abi.GROUP_DTYPE)
+        for i, g in enumerate(groups):
+            arr[i] = g
+        self._ck(self._lib.bb_set_agents(self._h, abi.ptr(arr), len(arr)))
+
+    def run_agents(self, n_steps: int, seed: int, sync: bool = True):
+        self._ck(self._lib.bb_run_agents(self._h, seed, n_steps))
+        if sync:
+            self.synchronize()
+
+    # ------------------------------------------------------------------ reads
+    def level_1_data(self) -> np.ndarray:
+        out = np.empty((self.n_envs, 9), dtype=np.uint32)
+        self._ck(self._lib.bb_level1(self._h, abi.ptr(out)))
+        return out
+
+    def level_2_data(self) -> np.ndarray:
+        out = np.empty((self.n_envs, 45), dtype=np.uint32)
+        self._ck(self._lib.bb_level2(self._h, abi.ptr(out)))
+        return out
+
+    def book_level_1(self, env: int = 0) -> np.ndarray:
+        out = np.empty(8, dtype=np.uint32)
+        self._ck(self._lib.bb_book_level1(self._h, env, abi.ptr(out)))
+        return out
+
+    def book_level_2(self, env: int = 0) -> np.ndarray:
+        out = np.empty(45, dtype=np.uint32)
+        self._ck(self._lib.bb_book_level2(self._h, env, abi.ptr(out)))
+        return out
+
+    def n_steps(self, env: int = 0) -> int:
+        n = C.c_uint32()
+        self._ck(self._lib.bb_n_steps(self._h, env, C.byref(n)))
+        return n.value
+
+    def history(self, env: int = 0, first: int = 0, n: typing.Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self.n_steps(env) - first
+        out = np.empty((n, self.obs_words), dtype=np.uint32)
+        self._ck(self._lib.bb_history(self._h, env, first, n, abi.ptr(out)))
+        return out
+
+    def history_all(self, n_steps: int, out: typing.Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n_envs, n_steps, self.obs_words), dtype=np.uint32)
+        self._ck(self._lib.bb_history_all(self._h, n_steps, abi.ptr(out)))
+        return out
+
+    def n_orders(self, env: int = 0) -> int:
+        n = C.c_uint64()
+        self._ck(self._lib.bb_n_orders(self._h, env, C.byref(n)))
+        return n.value
+
+    def n_trades(self, env: int = 0) -> int:
+        n = C.c_uint64()
+        self._ck(self._lib.bb_n_trades(self._h, env, C.byref(n)))
+        return n.value
+
+    def orders_arrays(self, env: int = 0):
+        n = self.n_orders(env)
+        cols = dict(side=np.empty(n, np.uint8), status=np.empty(n, np.uint8), arr_time=np.empty(n, np.uint64),
+                    end_time=np.empty(n, np.uint64), vol=np.empty(n, np.uint32), start_vol=np.empty(n, np.uint32),
+                    price=np.empty(n, np.uint32), trader=np.empty(n, np.uint32))
+        self._ck(self._lib.bb_orders(self._h, env, 0, n, *[abi.ptr(c) for c in cols.values()]))
+        return cols
+
+    def trades_arrays(self, env: int = 0):
+        n = self.n_trades(env)
+        cols = dict(t=np.empty(n, np.uint64), side=np.empty(n, np.uint8), price=np.empty(n, np.uint32),
+                    vol=np.empty(n, np.uint32), active=np.empty(n, np.uint64), passive=np.empty(n, np.uint64))
+        self._ck(self._lib.bb_trades(self._h, env, 0, n, *[abi.ptr(c) for c in cols.values()]))
+        return cols
+
+    def get_orders(self, env: int = 0):
+        """list[PyOrder] = (side, status, arr, end, vol, start_vol, price, trader, id) — rust/src/types.rs:19-31"""
+        c = self.orders_arrays(env)
+        return [(bool(c["side"][i]), int(c["status"][i]), int(c["arr_time"][i]), int(c["end_time"][i]), int(c["vol"][i]),
+                 int(c["start_vol"][i]), int(c["price"][i]), int(c["trader"][i]), i) for i in range(len(c["side"]))]
+
+    def get_trades(self, env: int = 0):
+        """list[PyTrade] = (t, side, price, vol, active_id, passive_id) — rust/src/types.rs:4-17"""
+        c = self.trades_arrays(env)
+        return [(int(c["t"][i]), bool(c["side"][i]), int(c["price"][i]), int(c["vol"][i]), int(c["active"][i]),
+                 int(c["passive"][i])) for i in range(len(c["t"]))]
+
+    def order_status(self, order_id: int, env: int = 0) -> int:
+        s = C.c_uint8()
+        self._ck(self._lib.bb_order_status(self._h, env, order_id, C.byref(s)))
+        return s.value
+
+    def env_errors(self) -> np.ndarray:
+        out = np.empty(self.n_envs, dtype=np.uint32)
+        self._ck(self._lib.bb_env_errors(self._h, abi.ptr(out)))
+        return out
+
+    def stats(self) -> dict:
+        s = abi.Stats()
+        self._ck(self._lib.bb_stats(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in abi.Stats._fields_}
+
+
+def random_group(n_agents, tick_range, vol_range, tick_size, activity_rate):
+    """RandomAgents::new argument order (crates/step_sim/src/agents/random_agent.rs:66-81)."""
+    g = np.zeros(1, dtype=abi.GROUP_DTYPE)[0]
+    g["kind"], g["n_agents"] = abi.GROUP_RANDOM, n_agents
+    g["tick_lo"], g["tick_hi"] = tick_range
+    g["vol_lo"], g["vol_hi"] = vol_range
+    g["tick_size"], g["rate"] = tick_size, activity_rate
+    return g
+
+
+def momentum_group(agent_id_start, n_agents, tick_size, p_cancel, trade_vol, decay, demand, scale, order_ratio,
+                   price_dist_mu, price_dist_sigma):
+    """MomentumAgent::new + MomentumParams (crates/step_sim/src/agents/momentum_agent.rs:16-35, 118-134)."""
+    g = np.zeros(1, dtype=abi.GROUP_DTYPE)[0]
+    g["kind"], g["n_agents"] = abi.GROUP_MOMENTUM, n_agents
+    g["tick_lo"], g["vol_lo"] = agent_id_start, trade_vol
+    g["tick_size"], g["rate"] = tick_size, p_cancel
+    g["decay"], g["demand"], g["scale"], g["order_ratio"] = decay, demand, scale, order_ratio
+    g["mu"], g["sigma"] = price_dist_mu, price_dist_sigma
+    return g
+
+
+class OrderBook:
+    """``bourse.core.OrderBook`` (rust/src/order_book.rs:35-375): immediate-mode book on the GPU."""
+
+    def __init__(self, start_time: int, tick_size: int, trading: bool = True, *, max_orders: int = 1 << 18,
+                 max_trades: int = 1 << 18, **kw):
+        self._env = BatchedEnv(1, 0, start_time, tick_size, 1, trading, max_orders=max_orders, max_trades=max_trades,
+                               max_steps=kw.pop("max_steps", 1 << 10), **kw)
+        self._t = start_time
+        self._one = np.zeros(1, dtype=abi.INSTR_DTYPE)
+
+    def _apply(self, op_flags, order_id=0, price=0, vol=0, trader=0):
+        x = self._one
+        x["t"], x["op_flags"], x["order_id"] = self._t, op_flags, order_id
+        x["price"], x["vol"], x["trader"] = price, vol, trader
+        self._env.replay(x)
+
+    def set_time(self, t: int): self._t = t; self._env.set_time(0, t)
+    def enable_trading(self): self._env.set_trading(True, 0)
+    def disable_trading(self): self._env.set_trading(False, 0)
+
+    def _l1(self): return [int(x) for x in self._env.book_level_1(0)]
+    def bid_ask(self): l = self._l1(); return (l[0], l[1])
+    def bid_vol(self): return self._l1()[2]
+    def ask_vol(self): return self._l1()[3]
+    def best_bid_vol(self): return self._l1()[4]
+    def best_ask_vol(self): return self._l1()[5]
+    def best_bid_vol_and_orders(self): l = self._l1(); return (l[4], l[6])
+    def best_ask_vol_and_orders(self): l = self._l1(); return (l[5], l[7])
+    def level_2_data(self) -> np.ndarray: return self._env.book_level_2(0)
+    def trade_vol(self) -> int: return int(self._env.book_level_2(0)[0])
+
+    def order_status(self, order_id: int) -> int: return self._env.order_status(order_id, 0)
+
+    def place_order(self, bid: bool, vol: int, trader_id: int, price: typing.Optional[int] = None) -> int:
+        if price is not None and price % self._env.tick_size != 0:  # orderbook.rs:367-383
+            raise ValueError(f"Price {price} was not a multiple of tick-size {self._env.tick_size}")
+        oid = self._env.n_orders(0)
+        f = abi.OP_NEW | (abi.F_BID if bid else 0) | (abi.F_MARKET if price is None else 0)
+        self._apply(f, 0, price or 0, vol, trader_id)
+        return oid
+
+    def cancel_order(self, order_id: int): self._apply(abi.OP_CANCEL, order_id)
+
+    def modify_order(self, order_id: int, new_price: typing.Optional[int] = None, new_vol: typing.Optional[int] = None):
+        f = abi.OP_MODIFY | (abi.F_HAS_PRICE if new_price is not None else 0) | (abi.F_HAS_VOL if new_vol is not None else 0)
+        self._apply(f, order_id, new_price or 0, new_vol or 0)
+
+    def replay(self, instrs: np.ndarray) -> np.ndarray:
+        """Apply a packed instruction stream (config C2); returns the [n_emit, 45] records of F_EMIT rows."""
+        first = self._env.n_steps(0)
+        self._env.replay(instrs)
+        if len(instrs):
+            self._t = int(instrs["t"][-1])
+        return self._env.history(0, first)
+
+    def get_trades(self): return self._env.get_trades(0)
+    def get_orders(self): return self._env.get_orders(0)
+
+    def save_json_snapshot(self, path: str, pretty: bool = False):
+        from .snapshot import save_json
+        save_json(self, path, pretty)
+
+
+class _StepEnvBase:
+    def __init__(self, seed: int, start_time: int, tick_size: int, step_size: int, trading: bool = True, *,
+                 max_orders: int = 1 << 18, max_trades: int = 1 << 18, max_steps: int = 1 << 14, max_queue: int = 4096, **kw):
+        self._env = BatchedEnv(1, seed, start_time, tick_size, step_size, trading, obs_words=abi.OBS_L2,
+                               max_orders=max_orders, max_trades=max_trades, max_steps=max_steps, max_queue=max_queue, **kw)
+        self._one_u32 = np.zeros(1, np.uint32)
+
+    def enable_trading(self): self._env.set_trading(True, 0)
+    def disable_trading(self): self._env.set_trading(False, 0)
+    def step(self): self._env.step(1)
+    def get_orders(self): return self._env.get_orders(0)
+    def get_trades(self): return self._env.get_trades(0)
+    def order_status(self, order_id: int) -> int: return self._env.order_status(order_id, 0)
+
+    def _l2(self) -> np.ndarray:
+        return self._env.level_2_data()[0]
+
+    def get_market_data(self) -> typing.Dict[str, np.ndarray]:
+        """45 u32 arrays keyed as rust/src/step_sim.rs:562-607."""
+        h = self._env.history(0)
+        d = {"trade_vol": h[:, 0].copy(), "bid_price": h[:, 1].copy(), "ask_price": h[:, 2].copy(),
+             "ask_vol": h[:, 3].copy(), "bid_vol": h[:, 4].copy()}
+        for i in range(10):
+            d[f"bid_vol_{i}"] = h[:, 5 + 4 * i].copy()
+            d[f"n_bid_{i}"] = h[:, 6 + 4 * i].copy()
+            d[f"ask_vol_{i}"] = h[:, 7 + 4 * i].copy()
+            d[f"n_ask_{i}"] = h[:, 8 + 4 * i].copy()
+        return d
+
+
+class StepEnv(_StepEnvBase):
+    """``bourse.core.StepEnv`` (rust/src/step_sim.rs:55-608)."""
+
+    @property
+    def time(self): return self._env.time(0)
+    @property
+    def bid_ask(self): l = self._l2(); return (int(l[1]), int(l[2]))
+    @property
+    def ask_vol(self): return int(self._l2()[3])
+    @property
+    def bid_vol(self): return int(self._l2()[4])
+    @property
+    def best_bid_vol(self): return int(self._l2()[5])
+    @property
+    def best_bid_vol_and_orders(self): l = self._l2(); return (int(l[5]), int(l[6]))
+    @property
+    def best_ask_vol(self): return int(self._l2()[7])
+    @property
+    def best_ask_vol_and_orders(self): l = self._l2(); return (int(l[7]), int(l[8]))
+    @property
+    def trade_vol(self): return int(self._l2()[0])
+
+    def place_order(self, bid: bool, vol: int, trader_id: int, price: typing.Optional[int] = None) -> int:
+        flags = None if price is not None else np.array([abi.F_MARKET], np.uint32)
+        ids = self._env.submit([abi.ACT_NEW], [1 if bid else 0], [vol], [trader_id], [price or 0], None, None, flags)
+        return int(ids[0])
+
+    def cancel_order(self, order_id: int):
+        self._env.submit([abi.ACT_CANCEL], order_id=[order_id])
+
+    def modify_order(self, order_id: int, new_price: typing.Optional[int] = None, new_vol: typing.Optional[int] = None):
+        f = (abi.F_HAS_PRICE if new_price is not None else 0) | (abi.F_HAS_VOL if new_vol is not None else 0)
+        self._env.submit([abi.ACT_MODIFY], vol=[new_vol or 0], price=[new_price or 0], order_id=[order_id],
+                         flags=np.array([f], np.uint32))
+
+    def get_prices(self): h = self._env.history(0); return h[:, 1].copy(), h[:, 2].copy()
+    def get_volumes(self): h = self._env.history(0); return h[:, 4].copy(), h[:, 3].copy()
+    def get_touch_volumes(self): h = self._env.history(0); return h[:, 5].copy(), h[:, 7].copy()
+    def get_touch_order_counts(self): h = self._env.history(0); return h[:, 6].copy(), h[:, 8].copy()
+    def get_trade_volumes(self): return self._env.history(0)[:, 0].copy()
+    def level_1_data_array(self): return self._l2()[1:9].copy()   # 8 values, no trade_vol (step_sim.rs:381-395)
+    def level_2_data_array(self): return self._l2().copy()
+
+
+class StepEnvNumpy(_StepEnvBase):
+    """``bourse.core.StepEnvNumpy`` (rust/src/step_sim_numpy.rs:66-517)."""
+
+    def submit_limit_orders(self, orders):
+        sides, vols, traders, prices = orders
+        n = len(sides)
+        return self._env.submit(np.full(n, abi.ACT_NEW, np.uint32), np.asarray(sides), vols, traders, prices)
+
+    def submit_cancellations(self, order_ids):
+        order_ids = np.asarray(order_ids, dtype=np.uint64)
+        self._env.submit(np.full(len(order_ids), abi.ACT_CANCEL, np.uint32), order_id=order_ids)
+
+    def submit_instructions(self, instructions):
+        action, sides, vols, traders, prices, order_ids = instructions
+        action = np.asarray(action, dtype=np.uint32)
+        # the reference treats every code other than 1 / 2 as a no-op (step_sim_numpy.rs:254-268)
+        action = np.where((action == 1) | (action == 2), action, 0).astype(np.uint32)
+        return self._env.submit(action, np.asarray(sides), vols, traders, prices, order_ids)
+
+    def level_1_data(self): return self._l2()[:9].copy()
+    def level_2_data(self): return self._l2().copy()
+
+
+def order_book_from_json(path: str) -> OrderBook:
+    from .snapshot import load_json
+    return load_json(path)

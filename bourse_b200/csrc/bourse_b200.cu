@@ -1,0 +1,812 @@
+// Host side of the C ABI declared in include/bourse_b200.h: handle lifetime, the per-env transaction
+// queues of Env mode (crates/step_sim/src/env.rs:166-219), launches, and the read-back calls that
+// feed the Python `bourse.core` mirror.  All compute happens in kernels.cuh; nothing here touches
+// book state on the CPU, and there is no fallback when CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace bb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct SmemLayout {
+    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar;
+};
+
+constexpr u32 WPB = 4;  // warps (books) per CTA
+
+inline u32 align_up(u32 x, u32 a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct bb_handle {
+    bb_config cfg;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device
+    unsigned char* blobs = nullptr;
+    OrderHot* oh = nullptr;
+    OrderCold* oc = nullptr;
+    TradeRec* tr = nullptr;
+    u32* hist = nullptr;
+    u32* err_flag = nullptr;
+    u64* d_offsets = nullptr;
+    u64* d_seeds = nullptr;
+    bb_instr* d_instrs = nullptr;
+    size_t d_instrs_cap = 0;
+    u32* d_snap = nullptr;  // [n_envs][45]
+    unsigned long long* d_stats = nullptr;
+    u32* rslot = nullptr;
+    MomState* mom = nullptr;
+    uint4* scratch = nullptr;
+    size_t scratch_warps = 0;
+    // pinned host staging
+    bb_instr* h_instrs = nullptr;
+    size_t h_instrs_cap = 0;
+    u64* h_offsets = nullptr;
+    // layout
+    u64 blob_stride = 0;
+    u32 blob_smem_bytes = 0, p_total = 0, p_smem = 0, granule = 0, max_steps_padded = 0;
+    u64 hist_env_stride = 0;
+    SmemLayout lay_apply{}, lay_sim{}, lay_snap{};
+    // agents
+    std::vector<bb_agent_group> groups;
+    u32 agents_per_env = 0, mom_groups = 0;
+    // host mirrors for Env mode
+    std::vector<std::vector<bb_instr>> queue;
+    std::vector<u64> n_orders_host;  // ids handed out so far (includes queued NEW)
+    bool mirror_dirty = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(bb_handle* h, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (h) h->err = msg;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(h, BB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+u64 splitmix_next(u64& x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    u64 z = x;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr) {
+    SmemLayout l{};
+    u32 off = align_up(h->blob_smem_bytes, 16);
+    l.off_perm = off;
+    off += align_up(4u * h->cfg.max_queue, 16);  // perm + jarr (u16 each)
+    l.off_obs = off;
+    if (with_obs) off += align_up(2u * OBS_STAGE_STEPS * h->cfg.obs_words * 4u, 16);
+    l.off_instr = off;
+    if (with_instr) off += 2048;
+    l.off_bar = off;
+    off += 32;
+    l.warp_bytes = align_up(off, 128);
+    return l;
+}
+
+void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.blobs = h->blobs;
+    p.blob_stride = h->blob_stride;
+    p.oh = h->oh;
+    p.oc = h->oc;
+    p.tr = h->tr;
+    p.hist = h->hist;
+    p.err_flag = h->err_flag;
+    p.step_size = h->cfg.step_size;
+    p.hist_env_stride = h->hist_env_stride;
+    p.blob_smem_bytes = h->blob_smem_bytes;
+    p.n_envs = h->cfg.n_envs;
+    p.env_id_base = h->cfg.env_id_base;
+    p.p_total = h->p_total;
+    p.p_smem = h->p_smem;
+    p.granule = h->granule;
+    p.tick = h->cfg.tick_size;
+    p.max_orders = h->cfg.max_orders;
+    p.max_trades = h->cfg.max_trades;
+    p.max_steps = h->max_steps_padded;
+    p.max_queue = h->cfg.max_queue;
+    p.obs_words = h->cfg.obs_words;
+    p.warp_smem_bytes = l.warp_bytes;
+    p.off_perm = l.off_perm;
+    p.off_obs = l.off_obs;
+    p.off_instr = l.off_instr;
+    p.off_bar = l.off_bar;
+}
+
+template <class K> int grid_for(bb_handle* h, K kernel, const SmemLayout& l, u32 n_items, int* grid_out) {
+    const size_t smem = (size_t)l.warp_bytes * WPB;
+    CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WPB * 32, smem));
+    if (per_sm < 1) return fail(h, BB_EINVAL, "configuration does not fit in shared memory (reduce pages_smem / max_queue)");
+    const u32 want = (n_items + WPB - 1) / WPB;
+    const u32 cap = (u32)per_sm * (u32)h->sm_count;
+    *grid_out = (int)(want < cap ? want : cap);
+    if (*grid_out < 1) *grid_out = 1;
+    return BB_OK;
+}
+
+int init_books(bb_handle* h) {
+    const bb_config& c = h->cfg;
+    std::vector<u64> seeds(2 * (size_t)c.n_envs);
+    for (u32 e = 0; e < c.n_envs; ++e) {  // Xoroshiro128StarStar::seed_from_u64 (rand_xoshiro 0.6.0)
+        u64 x = c.seed + c.env_id_base + e;
+        seeds[2 * e] = splitmix_next(x);
+        seeds[2 * e + 1] = splitmix_next(x);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_seeds, seeds.data(), seeds.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    k_init<<<c.n_envs, 64, 0, h->stream>>>(h->blobs, h->blob_stride, c.n_envs, h->p_total, c.start_time, c.trading ? 1u : 0u,
+                                           h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (auto& q : h->queue) q.clear();
+    std::fill(h->n_orders_host.begin(), h->n_orders_host.end(), 0);
+    h->mirror_dirty = false;
+    return BB_OK;
+}
+
+int refresh_mirror(bb_handle* h) {
+    if (!h->mirror_dirty) return BB_OK;
+    std::vector<u32> n(h->cfg.n_envs);
+    CUDA_TRY(h, cudaMemcpy2DAsync(n.data(), 4, h->blobs + offsetof(BookHdr, n_orders), h->blob_stride, 4, h->cfg.n_envs,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (u32 e = 0; e < h->cfg.n_envs; ++e) h->n_orders_host[e] = n[e] + [&] {
+        u64 k = 0;
+        for (auto& x : h->queue[e]) k += (x.op_flags & BB_OP_MASK) == BB_OP_NEW;
+        return k;
+    }();
+    h->mirror_dirty = false;
+    return BB_OK;
+}
+
+int check_device_errors(bb_handle* h) {
+    u32 flag = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&flag, h->err_flag, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
+        char buf[160];
+        snprintf(buf, sizeof buf, "device flagged env errors 0x%x (bad order id / capacity); see bb_env_errors", flag);
+        return fail(h, (flag & ERR_BAD_ID) ? BB_EBADID : (flag & 0x80000000u) ? BB_ECUDA : BB_ECAP, buf);
+    }
+    return BB_OK;
+}
+
+int ensure_instr_capacity(bb_handle* h, size_t n) {
+    if (n > h->d_instrs_cap) {
+        if (h->d_instrs) cudaFree(h->d_instrs);
+        h->d_instrs = nullptr;
+        const size_t cap = n + n / 2 + 1024;
+        CUDA_TRY(h, cudaMalloc(&h->d_instrs, cap * sizeof(bb_instr)));
+        h->d_instrs_cap = cap;
+    }
+    if (n > h->h_instrs_cap) {
+        if (h->h_instrs) cudaFreeHost(h->h_instrs);
+        h->h_instrs = nullptr;
+        const size_t cap = n + n / 2 + 1024;
+        CUDA_TRY(h, cudaMallocHost(&h->h_instrs, cap * sizeof(bb_instr)));
+        h->h_instrs_cap = cap;
+    }
+    return BB_OK;
+}
+
+int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_offsets, u32 n_steps) {
+    KParams p;
+    fill_params(h, h->lay_apply, p);
+    p.instrs = d_instrs;
+    p.offsets = d_offsets;
+    p.n_steps = n_steps;
+    int grid = 0, rc;
+    const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
+    if (mode == MODE_REPLAY) {
+        if ((rc = grid_for(h, k_apply<MODE_REPLAY>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;
+        k_apply<MODE_REPLAY><<<grid, WPB * 32, smem, h->stream>>>(p);
+    } else {
+        if ((rc = grid_for(h, k_apply<MODE_ENV>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;
+        k_apply<MODE_ENV><<<grid, WPB * 32, smem, h->stream>>>(p);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return BB_OK;
+}
+
+int snapshot(bb_handle* h, u32 first_env, u32 n, u32* d45, u32* d8) {
+    KParams p;
+    fill_params(h, h->lay_snap, p);
+    int grid = 0, rc;
+    if ((rc = grid_for(h, k_snapshot, h->lay_snap, n, &grid))) return rc;
+    k_snapshot<<<grid, WPB * 32, (size_t)h->lay_snap.warp_bytes * WPB, h->stream>>>(p, d45, d8, first_env, n);
+    CUDA_TRY(h, cudaGetLastError());
+    return BB_OK;
+}
+
+#define CHECK_H(h) \
+    if (!(h)) return fail(nullptr, BB_EINVAL, "null handle")
+#define CHECK_ENV(h, env) \
+    if ((env) >= (h)->cfg.n_envs) return fail(h, BB_EINVAL, "env index out of range")
+
+}  // namespace
+
+extern "C" {
+
+int bb_abi_version(void) { return BB_ABI_VERSION; }
+
+const char* bb_last_error(const bb_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int bb_create(const bb_config* cfg, bb_handle** out) {
+    if (!cfg || !out) return fail(nullptr, BB_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(bb_config)) return fail(nullptr, BB_EINVAL, "bb_config.struct_size mismatch");
+    if (cfg->tick_size == 0 || cfg->n_envs == 0) return fail(nullptr, BB_EINVAL, "tick_size and n_envs must be > 0");
+    if (cfg->obs_words != BB_OBS_L1 && cfg->obs_words != BB_OBS_L2) return fail(nullptr, BB_EINVAL, "obs_words must be 9 or 45");
+    if (cfg->max_orders == 0 || cfg->max_queue == 0 || cfg->max_queue > 65535 || cfg->max_steps == 0)
+        return fail(nullptr, BB_EINVAL, "max_orders, max_steps must be > 0 and 0 < max_queue <= 65535");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(nullptr, BB_ECUDA, "no CUDA device available: bourse_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, BB_EINVAL, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(nullptr, BB_ECUDA, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
+                                           std::to_string(prop.minor) + "); this library is built for sm_100a only");
+    CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
+
+    bb_handle* h = new bb_handle();
+    h->cfg = *cfg;
+    h->sm_count = prop.multiProcessorCount;
+    h->granule = cfg->price_granule ? cfg->price_granule : cfg->tick_size;
+    h->p_total = align_up(cfg->pages_total ? cfg->pages_total : 32u, 32);
+    h->p_smem = cfg->pages_smem ? cfg->pages_smem : 10u;
+    if (h->p_smem > h->p_total) h->p_smem = h->p_total;
+    h->blob_smem_bytes = 128u + 12u * h->p_total + 512u * h->p_smem;
+    h->blob_stride = 128ull + 12ull * h->p_total + 512ull * h->p_total;
+    h->max_steps_padded = align_up(cfg->max_steps, 4);
+    h->hist_env_stride = (u64)h->max_steps_padded * cfg->obs_words;
+    h->lay_apply = make_layout(h, false, true);
+    h->lay_sim = make_layout(h, true, false);
+    h->lay_snap = make_layout(h, false, false);
+    h->queue.resize(cfg->n_envs);
+    h->n_orders_host.assign(cfg->n_envs, 0);
+
+    auto bail = [&](int rc) {
+        bb_destroy(h);
+        return rc;
+    };
+#define TRY_ALLOC(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) return bail(fail(nullptr, BB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__))); \
+    } while (0)
+    const size_t ne = cfg->n_envs;
+    TRY_ALLOC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    TRY_ALLOC(cudaMalloc(&h->blobs, ne * h->blob_stride));
+    TRY_ALLOC(cudaMalloc(&h->oh, ne * cfg->max_orders * sizeof(OrderHot)));
+    TRY_ALLOC(cudaMalloc(&h->oc, ne * cfg->max_orders * sizeof(OrderCold)));
+    if (cfg->max_trades) TRY_ALLOC(cudaMalloc(&h->tr, ne * cfg->max_trades * sizeof(TradeRec)));
+    TRY_ALLOC(cudaMalloc(&h->hist, ne * h->hist_env_stride * 4));
+    TRY_ALLOC(cudaMalloc(&h->err_flag, 4));
+    TRY_ALLOC(cudaMalloc(&h->d_offsets, (ne + 1) * 8));
+    TRY_ALLOC(cudaMalloc(&h->d_seeds, ne * 16));
+    TRY_ALLOC(cudaMalloc(&h->d_snap, ne * 45 * 4));
+    TRY_ALLOC(cudaMalloc(&h->d_stats, 8 * 8));
+    TRY_ALLOC(cudaMallocHost(&h->h_offsets, (ne + 1) * 8));
+#undef TRY_ALLOC
+    int rc = init_books(h);
+    if (rc) return bail(rc);
+    *out = h;
+    return BB_OK;
+}
+
+int bb_destroy(bb_handle* h) {
+    if (!h) return BB_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->blobs); cudaFree(h->oh); cudaFree(h->oc); cudaFree(h->tr); cudaFree(h->hist); cudaFree(h->err_flag);
+    cudaFree(h->d_offsets); cudaFree(h->d_seeds); cudaFree(h->d_instrs); cudaFree(h->d_snap); cudaFree(h->d_stats);
+    cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch);
+    if (h->h_instrs) cudaFreeHost(h->h_instrs);
+    if (h->h_offsets) cudaFreeHost(h->h_offsets);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return BB_OK;
+}
+
+int bb_reset(bb_handle* h) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    return init_books(h);
+}
+
+int bb_set_stream(bb_handle* h, void* cuda_stream) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return BB_OK;
+}
+
+int bb_synchronize(bb_handle* h) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_submit(bb_handle* h, uint64_t n, const uint32_t* env, const uint32_t* action, const uint8_t* side_is_bid,
+              const uint32_t* vol, const uint32_t* trader, const uint32_t* price, const uint64_t* order_id,
+              const uint32_t* flags, uint64_t* out_ids, uint64_t* n_done) {
+    CHECK_H(h);
+    if (n_done) *n_done = 0;
+    if (!action) return fail(h, BB_EINVAL, "action array is required");
+    if (!env && h->cfg.n_envs != 1) return fail(h, BB_EINVAL, "env array is required when n_envs > 1");
+    int rc = refresh_mirror(h);
+    if (rc) return rc;
+    for (uint64_t r = 0; r < n; ++r) {
+        const u32 e = env ? env[r] : 0u;
+        if (e >= h->cfg.n_envs) return fail(h, BB_EINVAL, "env index out of range at row " + std::to_string(r));
+        const u32 f = flags ? flags[r] : (BB_F_HAS_PRICE | BB_F_HAS_VOL);
+        bb_instr x{};
+        uint64_t id_out = BB_NO_ID;
+        switch (action[r]) {
+            case BB_ACT_NEW: {
+                const bool market = flags && (f & BB_F_MARKET);
+                const u32 p = price ? price[r] : 0u;
+                if (!market && p % h->cfg.tick_size != 0) {  // create_order tick check, orderbook.rs:367-383
+                    if (n_done) *n_done = r;
+                    return fail(h, BB_EPRICE, "Price " + std::to_string(p) + " was not a multiple of tick-size " +
+                                                  std::to_string(h->cfg.tick_size));
+                }
+                if (h->n_orders_host[e] >= h->cfg.max_orders) {
+                    if (n_done) *n_done = r;
+                    return fail(h, BB_ECAP, "max_orders exceeded for env " + std::to_string(e));
+                }
+                id_out = h->n_orders_host[e]++;
+                x.op_flags = BB_OP_NEW | ((side_is_bid && side_is_bid[r]) ? BB_F_BID : 0u) | (market ? BB_F_MARKET : 0u);
+                x.order_id = (u32)id_out;
+                x.price = p;
+                x.vol = vol ? vol[r] : 0u;
+                x.trader = trader ? trader[r] : 0u;
+                break;
+            }
+            case BB_ACT_CANCEL:
+            case BB_ACT_MODIFY: {
+                const uint64_t id = order_id ? order_id[r] : 0;
+                x.op_flags = action[r] == BB_ACT_CANCEL ? BB_OP_CANCEL : (BB_OP_MODIFY | (f & (BB_F_HAS_PRICE | BB_F_HAS_VOL)));
+                // ids that do not fit 32 bits cannot exist; keep them out of range so the step flags BB_EBADID
+                x.order_id = id > 0xFFFFFFFEull ? 0xFFFFFFFFu : (u32)id;
+                x.price = price ? price[r] : 0u;
+                x.vol = vol ? vol[r] : 0u;
+                break;
+            }
+            default:  // BB_ACT_NOOP and unknown codes are no-ops (step_sim_numpy.rs:256, 267)
+                if (out_ids) out_ids[r] = BB_NO_ID;
+                if (n_done) *n_done = r + 1;
+                continue;
+        }
+        h->queue[e].push_back(x);
+        if (out_ids) out_ids[r] = id_out;
+        if (n_done) *n_done = r + 1;
+    }
+    return BB_OK;
+}
+
+int bb_step(bb_handle* h, uint32_t n_steps) {
+    CHECK_H(h);
+    if (n_steps == 0) return BB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const u32 ne = h->cfg.n_envs;
+    size_t total = 0;
+    for (u32 e = 0; e < ne; ++e) {
+        h->h_offsets[e] = total;
+        total += h->queue[e].size();
+    }
+    h->h_offsets[ne] = total;
+    int rc = ensure_instr_capacity(h, total + 1);
+    if (rc) return rc;
+    for (u32 e = 0; e < ne; ++e) {
+        if (!h->queue[e].empty())
+            memcpy(h->h_instrs + h->h_offsets[e], h->queue[e].data(), h->queue[e].size() * sizeof(bb_instr));
+        h->queue[e].clear();
+    }
+    if (total) CUDA_TRY(h, cudaMemcpyAsync(h->d_instrs, h->h_instrs, total * sizeof(bb_instr), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_offsets, h->h_offsets, (ne + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_apply(h, MODE_ENV, h->d_instrs, h->d_offsets, n_steps))) return rc;
+    return check_device_errors(h);
+}
+
+int bb_replay(bb_handle* h, const bb_instr* instrs, const uint64_t* env_offsets) {
+    CHECK_H(h);
+    if (!env_offsets) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const u32 ne = h->cfg.n_envs;
+    const size_t total = env_offsets[ne];
+    if (total && !instrs) return fail(h, BB_EINVAL, "null instruction array");
+    int rc = refresh_mirror(h);
+    if (rc) return rc;
+    if ((rc = ensure_instr_capacity(h, total + 1))) return rc;
+    if (total) memcpy(h->h_instrs, instrs, total * sizeof(bb_instr));
+    memcpy(h->h_offsets, env_offsets, (ne + 1) * 8);
+    if (total) CUDA_TRY(h, cudaMemcpyAsync(h->d_instrs, h->h_instrs, total * sizeof(bb_instr), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_offsets, h->h_offsets, (ne + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_apply(h, MODE_REPLAY, h->d_instrs, h->d_offsets, 0))) return rc;
+    for (u32 e = 0; e < ne; ++e)
+        for (size_t i = env_offsets[e]; i < env_offsets[e + 1]; ++i)
+            h->n_orders_host[e] += (instrs[i].op_flags & BB_OP_MASK) == BB_OP_NEW;
+    return check_device_errors(h);
+}
+
+int bb_replay_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets) {
+    CHECK_H(h);
+    if (!d_env_offsets) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    h->mirror_dirty = true;
+    return launch_apply(h, MODE_REPLAY, d_instrs, d_env_offsets, 0);
+}
+
+int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups) {
+    CHECK_H(h);
+    if (n_groups > MAX_GROUPS) return fail(h, BB_EINVAL, "at most 8 agent groups");
+    if (n_groups && !groups) return fail(h, BB_EINVAL, "null groups");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    u32 total = 0, mom = 0;
+    for (u32 i = 0; i < n_groups; ++i) {
+        const bb_agent_group& g = groups[i];
+        if (g.kind == BB_GROUP_RANDOM) {
+            if (g.tick_hi <= g.tick_lo || g.vol_hi <= g.vol_lo) return fail(h, BB_EINVAL, "empty tick/vol range");
+            if (g.n_agents >= (1u << 19)) return fail(h, BB_EINVAL, "too many agents in a group");
+        } else if (g.kind == BB_GROUP_MOMENTUM) {
+            if ((u64)g.tick_lo + g.n_agents >= (1u << 19)) return fail(h, BB_EINVAL, "momentum trader ids must stay below 2^19");
+            if (g.tick_size == 0 || g.n_agents == 0) return fail(h, BB_EINVAL, "momentum group needs tick_size and n_agents > 0");
+            ++mom;
+        } else {
+            return fail(h, BB_EINVAL, "unknown agent group kind");
+        }
+        total += g.n_agents;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->rslot); h->rslot = nullptr;
+    cudaFree(h->mom); h->mom = nullptr;
+    h->groups.assign(groups, groups + n_groups);
+    h->agents_per_env = total;
+    h->mom_groups = mom;
+    const size_t ne = h->cfg.n_envs;
+    if (total) {
+        CUDA_TRY(h, cudaMalloc(&h->rslot, ne * total * 4));
+        CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
+    }
+    if (mom) {
+        CUDA_TRY(h, cudaMalloc(&h->mom, ne * mom * sizeof(MomState)));
+        CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * sizeof(MomState), h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
+    CHECK_H(h);
+    if (h->groups.empty()) return fail(h, BB_EINVAL, "bb_set_agents has not been called");
+    if (n_steps == 0) return BB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    for (auto& q : h->queue)
+        if (!q.empty()) return fail(h, BB_EINVAL, "host-queued instructions pending: call bb_step first");
+    // history capacity is validated up front so the kernel can stage records without per-step checks
+    u32 recorded = 0;
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->h_offsets, 8, h->blobs + offsetof(BookHdr, n_steps), h->blob_stride, 4, 1,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    recorded = *(u32*)h->h_offsets;
+    if ((u64)recorded + n_steps > h->max_steps_padded) return fail(h, BB_ECAP, "max_steps exceeded");
+    KParams p;
+    fill_params(h, h->lay_sim, p);
+    p.n_steps = n_steps;
+    p.n_groups = (u32)h->groups.size();
+    p.agents_per_env = h->agents_per_env;
+    p.mom_groups_per_env = h->mom_groups;
+    p.rslot = h->rslot;
+    p.mom = h->mom;
+    p.seed_lo = (u32)seed;
+    p.seed_hi = (u32)(seed >> 32);
+    for (size_t i = 0; i < h->groups.size(); ++i) p.groups[i] = h->groups[i];
+    int grid = 0, rc;
+    if ((rc = grid_for(h, k_sim, h->lay_sim, h->cfg.n_envs, &grid))) return rc;
+    const size_t warps = (size_t)grid * WPB;
+    if (warps > h->scratch_warps) {
+        cudaFree(h->scratch);
+        h->scratch = nullptr;
+        CUDA_TRY(h, cudaMalloc(&h->scratch, warps * h->cfg.max_queue * sizeof(uint4)));
+        h->scratch_warps = warps;
+    }
+    p.scratch = h->scratch;
+    k_sim<<<grid, WPB * 32, (size_t)h->lay_sim.warp_bytes * WPB, h->stream>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    h->mirror_dirty = true;
+    return BB_OK;
+}
+
+int bb_level2(bb_handle* h, uint32_t* out) {
+    CHECK_H(h);
+    if (!out) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = snapshot(h, 0, h->cfg.n_envs, h->d_snap, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_snap, (size_t)h->cfg.n_envs * 45 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_level1(bb_handle* h, uint32_t* out) {
+    CHECK_H(h);
+    if (!out) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = snapshot(h, 0, h->cfg.n_envs, h->d_snap, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpy2DAsync(out, 36, h->d_snap, 180, 36, h->cfg.n_envs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_book_level1(bb_handle* h, uint32_t env, uint32_t* out8) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = snapshot(h, env, 1, nullptr, h->d_snap);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out8, h->d_snap, 32, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_book_level2(bb_handle* h, uint32_t env, uint32_t* out45) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = snapshot(h, env, 1, h->d_snap, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out45, h->d_snap, 180, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+static int read_hdr_u32(bb_handle* h, u32 env, size_t off, u32* v) {
+    CUDA_TRY(h, cudaMemcpyAsync(v, h->blobs + (size_t)env * h->blob_stride + off, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_n_steps(bb_handle* h, uint32_t env, uint32_t* n) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    return read_hdr_u32(h, env, offsetof(BookHdr, n_steps), n);
+}
+
+int bb_history(bb_handle* h, uint32_t env, uint32_t first, uint32_t n, uint32_t* out) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    if ((u64)first + n > h->max_steps_padded) return fail(h, BB_EINVAL, "history range out of bounds");
+    if (n == 0) return BB_OK;
+    const u32 w = h->cfg.obs_words;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->hist + (size_t)env * h->hist_env_stride + (size_t)first * w, (size_t)n * w * 4,
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_history_all(bb_handle* h, uint32_t n_steps, uint32_t* out) {
+    CHECK_H(h);
+    if (n_steps > h->max_steps_padded) return fail(h, BB_EINVAL, "history range out of bounds");
+    if (n_steps == 0) return BB_OK;
+    const size_t row = (size_t)n_steps * h->cfg.obs_words * 4;
+    CUDA_TRY(h, cudaMemcpy2DAsync(out, row, h->hist, h->hist_env_stride * 4, row, h->cfg.n_envs, cudaMemcpyDeviceToHost,
+                                  h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_history_device(bb_handle* h, void** d_ptr, uint64_t* env_stride_words, uint32_t* obs_words) {
+    CHECK_H(h);
+    if (d_ptr) *d_ptr = h->hist;
+    if (env_stride_words) *env_stride_words = h->hist_env_stride;
+    if (obs_words) *obs_words = h->cfg.obs_words;
+    return BB_OK;
+}
+
+int bb_n_orders(bb_handle* h, uint32_t env, uint64_t* n) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    int rc = refresh_mirror(h);
+    if (rc) return rc;
+    *n = h->n_orders_host[env];
+    return BB_OK;
+}
+
+int bb_n_trades(bb_handle* h, uint32_t env, uint64_t* n) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    u32 v = 0;
+    int rc = read_hdr_u32(h, env, offsetof(BookHdr, n_trades), &v);
+    *n = v;
+    return rc;
+}
+
+int bb_orders(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint8_t* side_is_bid, uint8_t* status,
+              uint64_t* arr_time, uint64_t* end_time, uint32_t* vol, uint32_t* start_vol, uint32_t* price,
+              uint32_t* trader) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    int rc = refresh_mirror(h);
+    if (rc) return rc;
+    if (first + n > h->n_orders_host[env]) return fail(h, BB_EBADID, "order range out of bounds");
+    if (n == 0) return BB_OK;
+    // ids below the device count are materialised records; the rest are still New in the host queue
+    u64 n_queued_new = 0;
+    for (auto& x : h->queue[env]) n_queued_new += (x.op_flags & BB_OP_MASK) == BB_OP_NEW;
+    const u64 n_dev = h->n_orders_host[env] - n_queued_new;
+    const u64 dev_n = first < n_dev ? std::min(n, n_dev - first) : 0;
+    std::vector<OrderHot> hot(dev_n);
+    std::vector<OrderCold> cold(dev_n);
+    if (dev_n) {
+        CUDA_TRY(h, cudaMemcpyAsync(hot.data(), h->oh + (size_t)env * h->cfg.max_orders + first, dev_n * sizeof(OrderHot),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(cold.data(), h->oc + (size_t)env * h->cfg.max_orders + first, dev_n * sizeof(OrderCold),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    }
+    u64 t_now = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&t_now, h->blobs + (size_t)env * h->blob_stride, 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (u64 i = 0; i < dev_n; ++i) {
+        if (side_is_bid) side_is_bid[i] = (hot[i].meta & META_BID) ? 1 : 0;
+        if (status) status[i] = (uint8_t)(hot[i].meta & META_STATUS_MASK);
+        if (arr_time) arr_time[i] = cold[i].arr_time;
+        if (end_time) end_time[i] = cold[i].end_time;
+        if (vol) vol[i] = hot[i].vol;
+        if (start_vol) start_vol[i] = hot[i].start_vol;
+        if (price) price[i] = hot[i].price;
+        if (trader) trader[i] = cold[i].trader;
+    }
+    for (auto& x : h->queue[env]) {
+        if ((x.op_flags & BB_OP_MASK) != BB_OP_NEW) continue;
+        if (x.order_id < first || x.order_id >= first + n) continue;
+        const u64 i = x.order_id - first;
+        const bool bid = x.op_flags & BB_F_BID;
+        if (side_is_bid) side_is_bid[i] = bid;
+        if (status) status[i] = ST_NEW;
+        if (arr_time) arr_time[i] = t_now;  // create_order stamps the current book time (orderbook.rs:373)
+        if (end_time) end_time[i] = ~0ULL;
+        const u32 p = (x.op_flags & BB_F_MARKET) ? (bid ? 0xFFFFFFFFu : 0u) : x.price;
+        if (vol) vol[i] = x.vol;
+        if (start_vol) start_vol[i] = x.vol;
+        if (price) price[i] = p;
+        if (trader) trader[i] = x.trader;
+    }
+    return BB_OK;
+}
+
+int bb_trades(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* t, uint8_t* side_is_bid, uint32_t* price,
+              uint32_t* vol, uint64_t* active_id, uint64_t* passive_id) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    u32 have = 0;
+    int rc = read_hdr_u32(h, env, offsetof(BookHdr, n_trades), &have);
+    if (rc) return rc;
+    if (first + n > have) return fail(h, BB_EINVAL, "trade range out of bounds");
+    if (n == 0) return BB_OK;
+    std::vector<TradeRec> rec(n);
+    CUDA_TRY(h, cudaMemcpyAsync(rec.data(), h->tr + (size_t)env * h->cfg.max_trades + first, n * sizeof(TradeRec),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (u64 i = 0; i < n; ++i) {
+        if (t) t[i] = rec[i].t;
+        if (side_is_bid) side_is_bid[i] = (uint8_t)rec[i].side_bid;
+        if (price) price[i] = rec[i].price;
+        if (vol) vol[i] = rec[i].vol;
+        if (active_id) active_id[i] = rec[i].active;
+        if (passive_id) passive_id[i] = rec[i].passive;
+    }
+    return BB_OK;
+}
+
+int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* status) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    int rc = refresh_mirror(h);
+    if (rc) return rc;
+    if (order_id >= h->n_orders_host[env])
+        return fail(h, BB_EBADID, "No order with id " + std::to_string(order_id) + " exists");
+    for (auto& x : h->queue[env])
+        if ((x.op_flags & BB_OP_MASK) == BB_OP_NEW && x.order_id == order_id) {
+            *status = ST_NEW;
+            return BB_OK;
+        }
+    u32 meta = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&meta, &h->oh[(size_t)env * h->cfg.max_orders + order_id].meta, 4, cudaMemcpyDeviceToHost,
+                                h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *status = (uint8_t)(meta & META_STATUS_MASK);
+    return BB_OK;
+}
+
+int bb_time(bb_handle* h, uint32_t env, uint64_t* t) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    CUDA_TRY(h, cudaMemcpyAsync(t, h->blobs + (size_t)env * h->blob_stride, 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_set_time(bb_handle* h, uint32_t env, uint64_t t) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    CUDA_TRY(h, cudaMemcpyAsync(h->blobs + (size_t)env * h->blob_stride, &t, 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_set_trading(bb_handle* h, uint32_t env, int on) {
+    CHECK_H(h);
+    const u32 first = env == BB_ALL_ENVS ? 0 : env, cnt = env == BB_ALL_ENVS ? h->cfg.n_envs : 1;
+    if (env != BB_ALL_ENVS) CHECK_ENV(h, env);
+    std::vector<u32> v(cnt, on ? 1u : 0u);
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->blobs + (size_t)first * h->blob_stride + offsetof(BookHdr, trading), h->blob_stride,
+                                  v.data(), 4, 4, cnt, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_env_errors(bb_handle* h, uint32_t* out) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaMemcpy2DAsync(out, 4, h->blobs + offsetof(BookHdr, err), h->blob_stride, 4, h->cfg.n_envs,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_stats(bb_handle* h, bb_stats_t* out) {
+    CHECK_H(h);
+    if (!out) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, 64, h->stream));
+    k_stats<<<(h->cfg.n_envs + 255) / 256, 256, 0, h->stream>>>(h->blobs, h->blob_stride, h->cfg.n_envs, h->d_stats);
+    CUDA_TRY(h, cudaGetLastError());
+    unsigned long long v[8];
+    CUDA_TRY(h, cudaMemcpyAsync(v, h->d_stats, 64, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<u32> l1((size_t)h->cfg.n_envs * 9);
+    int rc = bb_level1(h, l1.data());
+    if (rc) return rc;
+    u64 fnv = 0xcbf29ce484222325ULL;
+    const unsigned char* b = (const unsigned char*)l1.data();
+    for (size_t i = 0; i < l1.size() * 4; ++i) fnv = (fnv ^ b[i]) * 0x100000001b3ULL;
+    out->instructions = v[0];
+    out->orders_created = v[1];
+    out->trades = v[2];
+    out->traded_volume = v[3];
+    out->env_steps = v[4];
+    out->transitions = v[5];
+    out->error_envs = v[6];
+    out->l1_checksum = fnv;
+    return BB_OK;
+}
+
+}  // extern "C"

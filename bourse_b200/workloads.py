@@ -1,0 +1,86 @@
+"""Synthetic workloads of BASELINE.json (made concrete in SURVEY.md 8d).
+
+`replay_stream` builds config C2: a place/cancel/modify mix for ONE book as a packed ``bb_instr``
+array (immediate-mode semantics, explicit time per instruction).  `c3_groups` / `c4_groups` are the
+agent populations of configs C3 / C4.  Host-side generation only; nothing here touches book state.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import abi
+from .core import momentum_group, random_group
+
+
+def replay_stream(n: int, seed: int, tick_size: int = 1, mid_ticks: int = 1000, half_width: int = 64,
+                  step_size: int = 100_000, emit_every: int = 64, max_vol: int = 100, trading_windows: bool = True,
+                  time_mode: str = "strict", min_vol: int = 1) -> np.ndarray:
+    """C2 stream: 55% limit, 5% market, 25% cancel, 15% modify (1/3 vol-only, 1/3 price-only, 1/3 both).
+
+    time_mode: "strict" (t strictly increasing: +1 per event, +step_size every `emit_every`),
+               "flat" (time never advances: exercises the reference's equal-key collisions, N1),
+               "jitter" (time may move backwards: exercises sorted queue insertion).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.random(n)
+    op = np.full(n, abi.OP_MODIFY, dtype=np.uint32)
+    op[u < 0.85] = abi.OP_CANCEL
+    op[u < 0.60] = abi.OP_NEW
+    market = (u >= 0.55) & (u < 0.60)
+    flags = np.zeros(n, dtype=np.uint32)
+    vol = rng.integers(min_vol, max_vol + 1, size=n, dtype=np.uint32)
+    if trading_windows and n >= 2000:  # trading switched off for ~1% of the stream
+        n_win = max(1, n // 5000)
+        starts = rng.integers(0, n - 60, size=n_win)
+        for s in starts:
+            op[s], vol[s], market[s] = abi.OP_SET_TRADING, 0, False
+            op[s + 50], vol[s + 50], market[s + 50] = abi.OP_SET_TRADING, 1, False
+    is_new = op == abi.OP_NEW
+    issued_before = np.cumsum(is_new) - is_new
+    target = np.floor(rng.random(n) * np.maximum(issued_before, 1)).astype(np.uint32)
+    needs_target = (op == abi.OP_CANCEL) | (op == abi.OP_MODIFY)
+    op[needs_target & (issued_before == 0)] = abi.OP_NOOP
+    side = rng.random(n) < 0.5
+    price = (rng.integers(mid_ticks - half_width, mid_ticks + half_width + 1, size=n).astype(np.uint32) * tick_size).astype(np.uint32)
+    kind = rng.integers(0, 3, size=n)
+    is_mod = op == abi.OP_MODIFY
+    flags[is_new & side] |= abi.F_BID
+    flags[is_new & market] |= abi.F_MARKET
+    flags[is_mod & (kind != 1)] |= abi.F_HAS_VOL
+    flags[is_mod & (kind != 0)] |= abi.F_HAS_PRICE
+    idx = np.arange(n, dtype=np.uint64)
+    if emit_every:
+        flags[(idx % emit_every) == emit_every - 1] |= abi.F_EMIT
+    if time_mode == "strict":
+        t = idx + 1 + (idx // max(emit_every, 1)) * step_size
+    elif time_mode == "flat":
+        t = np.zeros(n, dtype=np.uint64) + 5
+    elif time_mode == "jitter":
+        t = (rng.integers(0, 50, size=n) + (idx // 8)).astype(np.uint64)
+    else:
+        raise ValueError(time_mode)
+    out = np.zeros(n, dtype=abi.INSTR_DTYPE)
+    out["t"] = t
+    out["op_flags"] = op | flags
+    out["order_id"] = np.where(needs_target, target, 0)
+    out["price"] = np.where(is_new & market, 0, price)
+    out["vol"] = vol
+    out["trader"] = rng.integers(0, 1000, size=n, dtype=np.uint32)
+    return out
+
+
+def c3_groups():
+    """crates/step_sim/examples/random_agents/main.rs:10-19 — 50 + 50 RandomAgents."""
+    return [random_group(50, (40, 60), (10, 20), 2, 0.8), random_group(50, (10, 90), (50, 70), 2, 0.2)]
+
+
+def c4_groups():
+    """40 + 40 RandomAgents and a 20-trader MomentumAgent."""
+    return [random_group(40, (40, 60), (10, 20), 2, 0.8), random_group(40, (10, 90), (50, 70), 2, 0.2),
+            momentum_group(80, 20, 1, 0.1, 10, 1.0, 5.0, 0.5, 1.0, 0.0, 1.0)]
+
+
+def algorithmic_bytes(stats: dict, obs_words: int, ext_instructions: int = 0) -> int:
+    """25*I_ext + 42*N_created + 26*N_transitions + 33*N_trades + OBS*E."""
+    return (25 * ext_instructions + 42 * stats["orders_created"] + 26 * stats["transitions"] + 33 * stats["trades"]
+            + 4 * obs_words * stats["env_steps"])

@@ -1,0 +1,217 @@
+/* bourse_b200 — C ABI of the B200-native batched limit-order-book simulator.
+ *
+ * This is the drop-in boundary for the reference's hot path: the calls
+ * below are what a binding for `bourse.core` (PyO3 module, /root/reference/rust/src/lib.rs:7-15)
+ * or a Rust `extern "C"` host would bind instead of `bourse_book::OrderBook` /
+ * `bourse_de::{Env, sim_runner}`.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * One handle owns `n_envs` independent books ("envs") on ONE CUDA device plus everything the
+ * reference keeps per `Env`: order table, trade log, transaction queue, per-step level-2 history.
+ * All pointer arguments are HOST pointers unless the function name ends in `_device`.
+ * Every function returns BB_OK (0) or a negative bb_status; bb_last_error() gives the text.
+ * A handle is not thread-safe.  Calls are synchronous unless stated otherwise.
+ *
+ * There is no CPU fallback: bb_create fails with BB_ECUDA when no sm_100 device is usable.
+ */
+#ifndef BOURSE_B200_H
+#define BOURSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+typedef struct bb_handle bb_handle;
+
+typedef enum {
+    BB_OK = 0,
+    BB_EPRICE = -1,   /* price not a multiple of tick size: OrderError::PriceError, orderbook.rs:127-142 */
+    BB_EBADID = -2,   /* order id does not exist: the reference panics, orderbook.rs:642 / :749 */
+    BB_ECAP = -3,     /* a configured capacity (orders / trades / queue / pages / steps) was exceeded */
+    BB_ECUDA = -4,    /* CUDA runtime error or no usable device */
+    BB_EINVAL = -5,   /* bad argument */
+    BB_EDEVICE = -6   /* the device flagged an env error during the call; see bb_env_errors */
+} bb_status;
+
+/* per-env sticky error bits reported by bb_env_errors */
+#define BB_ERR_CAP_ORDERS 0x01u
+#define BB_ERR_CAP_TRADES 0x02u
+#define BB_ERR_CAP_PAGES  0x04u
+#define BB_ERR_CAP_QUEUE  0x08u
+#define BB_ERR_BAD_ID     0x10u
+#define BB_ERR_GRANULE    0x20u  /* a resting price was not a multiple of price_granule */
+#define BB_ERR_CAP_STEPS  0x40u
+#define BB_ERR_CAP_LIVE   0x80u  /* MomentumAgent live-order list overflow */
+
+#define BB_OBS_L1 9u   /* StepEnvNumpy.level_1_data layout, rust/src/step_sim_numpy.rs:300-318 */
+#define BB_OBS_L2 45u  /* StepEnvNumpy.level_2_data layout, rust/src/step_sim_numpy.rs:351-368 */
+#define BB_LEVELS 10u  /* hard-wired in the reference's Python surface, rust/src/step_sim.rs:438 */
+
+#define BB_NO_ID UINT64_MAX  /* id returned for rows that create nothing, step_sim_numpy.rs:256-267 */
+#define BB_ALL_ENVS 0xFFFFFFFFu
+
+/* Replaces the constructor arguments of OrderBook::new (orderbook.rs:158-171), Env::new
+ * (crates/step_sim/src/env.rs:84-95) and StepEnv/StepEnvNumpy::new (rust/src/step_sim.rs:63-75),
+ * batched over n_envs, plus the capacities a preallocating device implementation needs. */
+typedef struct {
+    uint32_t struct_size;   /* sizeof(bb_config) */
+    int32_t device;         /* CUDA device ordinal */
+    uint32_t n_envs;        /* books owned by this handle (this rank's shard) */
+    uint32_t env_id_base;   /* global id of env 0: keeps agent RNG invariant to the sharding */
+    uint64_t start_time;    /* Nanos */
+    uint64_t step_size;     /* Nanos advanced per Env::step */
+    uint64_t seed;          /* env e shuffles with Xoroshiro128**(seed + env_id_base + e) (step_sim.rs:73) */
+    uint32_t tick_size;     /* > 0 */
+    uint32_t price_granule; /* ladder granularity; 0 => tick_size.  Every resting price must be a multiple */
+    uint32_t trading;       /* initial trading flag */
+    uint32_t obs_words;     /* BB_OBS_L1 or BB_OBS_L2: record written to the history each step */
+    uint32_t max_orders;    /* per env */
+    uint32_t max_trades;    /* per env; 0 disables the trade log (trade_vol is still tracked) */
+    uint32_t max_steps;     /* per env history records (steps, or emitted snapshots in replay mode) */
+    uint32_t max_queue;     /* per env instructions per step */
+    uint32_t pages_smem;    /* 32-level price pages per book resident in shared memory; 0 => default */
+    uint32_t pages_total;   /* total pages per book (the rest live in HBM); 0 => default */
+    uint32_t reserved[4];
+} bb_config;
+
+/* One instruction, 32 bytes; replaces Event<OrderId> (crates/order_book/src/types.rs:229-249) plus
+ * the creation arguments of create_order (orderbook.rs:356-396).  Streams of these are what the
+ * replay kernel bulk-copies from HBM. */
+typedef struct {
+    uint64_t t;        /* replay mode: book time this instruction executes at (OrderBook::set_time) */
+    uint32_t op_flags; /* BB_OP_* | BB_F_* */
+    uint32_t order_id; /* CANCEL / MODIFY target */
+    uint32_t price;    /* NEW: limit price; MODIFY: new price when BB_F_HAS_PRICE */
+    uint32_t vol;      /* NEW: volume; MODIFY: new volume when BB_F_HAS_VOL; SET_TRADING: 0 / 1 */
+    uint32_t trader;   /* NEW: trader id */
+    uint32_t aux;      /* reserved, 0 */
+} bb_instr;
+
+#define BB_OP_NOOP 0u
+#define BB_OP_NEW 1u          /* create_and_place_order, orderbook.rs:411-421 */
+#define BB_OP_CANCEL 2u       /* cancel_order, orderbook.rs:622-644 */
+#define BB_OP_MODIFY 3u       /* modify_order, orderbook.rs:743-772 */
+#define BB_OP_SET_TRADING 4u  /* enable/disable_trading, orderbook.rs:188-198 */
+#define BB_OP_MASK 0xFFu
+#define BB_F_BID (1u << 8)
+#define BB_F_MARKET (1u << 9)     /* price == None */
+#define BB_F_HAS_PRICE (1u << 10)
+#define BB_F_HAS_VOL (1u << 11)
+#define BB_F_EMIT (1u << 12)      /* replay mode: append a level-2 record to the history afterwards */
+
+/* Actions of StepEnvNumpy.submit_instructions (rust/src/step_sim_numpy.rs:254-268) */
+#define BB_ACT_NOOP 0u
+#define BB_ACT_NEW 1u
+#define BB_ACT_CANCEL 2u
+#define BB_ACT_MODIFY 3u /* extension: Env::modify_order (env.rs:208-219) through the array call */
+
+/* One built-in agent group, 80 bytes; groups are updated in array order each step, as the fields
+ * of a #[derive(AgentSet)] struct are (crates/macros/src/lib.rs:57-72).
+ *  kind 0 RandomAgents::new(n_agents, (tick_lo,tick_hi), (vol_lo,vol_hi), tick_size, rate)
+ *         crates/step_sim/src/agents/random_agent.rs:66-81
+ *  kind 1 MomentumAgent::new(agent_id_start = tick_lo, n_agents, MomentumParams{tick_size,
+ *         p_cancel = rate, trade_vol = vol_lo, decay, demand, scale, order_ratio, mu, sigma})
+ *         crates/step_sim/src/agents/momentum_agent.rs:16-35, 118-134 */
+typedef struct {
+    uint32_t kind;
+    uint32_t n_agents;
+    uint32_t tick_lo, tick_hi;
+    uint32_t vol_lo, vol_hi;
+    uint32_t tick_size;
+    float rate;
+    double decay, demand, scale, order_ratio, mu, sigma;
+} bb_agent_group;
+
+#define BB_GROUP_RANDOM 0u
+#define BB_GROUP_MOMENTUM 1u
+
+typedef struct {
+    uint64_t instructions;   /* events that reached process_event (New + Cancel + Modify) */
+    uint64_t orders_created;
+    uint64_t trades;
+    uint64_t traded_volume;
+    uint64_t env_steps;
+    uint64_t transitions;    /* order state changes after creation (place, fill, cancel, modify) */
+    uint64_t error_envs;     /* envs with a non-zero error word */
+    uint64_t l1_checksum;    /* FNV-1a over every env's current 9-word level-1 record */
+} bb_stats_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int bb_abi_version(void);
+int bb_create(const bb_config* cfg, bb_handle** out);
+int bb_destroy(bb_handle* h);
+int bb_reset(bb_handle* h); /* back to the freshly created state (same config) */
+const char* bb_last_error(const bb_handle* h /* may be NULL */);
+/* run on a caller-owned CUDA stream (cudaStream_t); NULL restores the handle's own stream */
+int bb_set_stream(bb_handle* h, void* cuda_stream);
+int bb_synchronize(bb_handle* h);
+
+/* ---- Env mode: queued instructions + step (crates/step_sim/src/env.rs:116-219) ---------------- */
+/* Replaces Env::place_order / cancel_order / modify_order and StepEnvNumpy.submit_limit_orders /
+ * submit_cancellations / submit_instructions (rust/src/step_sim_numpy.rs:147-275) for a batch of
+ * rows over many envs.  Rows are processed in order; ids are assigned per env in row order.
+ * On a tick error at row r the call returns BB_EPRICE, *n_done = r, rows < r stay queued (the
+ * reference's lazy map short-circuits the same way) and bb_last_error() holds the reference's
+ * message.  `flags` may be NULL (=> limit orders, BB_F_HAS_PRICE|BB_F_HAS_VOL for modifies);
+ * otherwise BB_F_MARKET / BB_F_HAS_PRICE / BB_F_HAS_VOL per row.  `env` may be NULL when n_envs==1.
+ * out_ids[r] = new order id, or BB_NO_ID for rows that create nothing. */
+int bb_submit(bb_handle* h, uint64_t n, const uint32_t* env, const uint32_t* action, const uint8_t* side_is_bid,
+              const uint32_t* vol, const uint32_t* trader, const uint32_t* price, const uint64_t* order_id,
+              const uint32_t* flags, uint64_t* out_ids, uint64_t* n_done);
+/* Env::step for every env, n_steps times (queued instructions are consumed by the first). */
+int bb_step(bb_handle* h, uint32_t n_steps);
+
+/* ---- immediate mode: OrderBook API / replayed streams (orderbook.rs:411-792) ------------------ */
+/* env_offsets[n_envs + 1] delimits each env's slice of `instrs`.  Every instruction executes at its
+ * own `t`.  NEW rows get ids in stream order.  Rows flagged BB_F_EMIT append a level-2 record. */
+int bb_replay(bb_handle* h, const bb_instr* instrs, const uint64_t* env_offsets);
+/* same with both arrays already resident in device memory (asynchronous on the handle's stream) */
+int bb_replay_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets);
+
+/* ---- built-in agents: sim_runner (crates/step_sim/src/runner.rs:46-69) ------------------------ */
+/* Defines the agent set (resets agent state).  Groups run in array order. */
+int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups);
+/* n_steps of { agents.update(env); env.step() } for every env inside one persistent kernel.
+ * Draws are Philox4x32-10 keyed (seed; global env id, step, agent) — DESIGN.md "RNG contract".
+ * Asynchronous on the handle's stream; pair with bb_synchronize or any read call. */
+int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps);
+
+/* ---- reads ---------------------------------------------------------------------------------- */
+/* cached end-of-step data of every env + live trade_vol in slot 0 (N7/N8 of SURVEY.md):
+ * out[n_envs][9] / out[n_envs][45] */
+int bb_level1(bb_handle* h, uint32_t* out);
+int bb_level2(bb_handle* h, uint32_t* out);
+/* live book of one env, OrderBook::level_1_data field order (types.rs:252-269): 8 words */
+int bb_book_level1(bb_handle* h, uint32_t env, uint32_t* out8);
+/* live book of one env in the 45-word layout */
+int bb_book_level2(bb_handle* h, uint32_t env, uint32_t* out45);
+int bb_n_steps(bb_handle* h, uint32_t env, uint32_t* n);
+/* history records [first, first+n) of one env: out[n][obs_words] (Level2DataRecords, data.rs:9-57) */
+int bb_history(bb_handle* h, uint32_t env, uint32_t first, uint32_t n, uint32_t* out);
+/* first n_steps records of every env: out[n_envs][n_steps][obs_words]; one strided D2H copy */
+int bb_history_all(bb_handle* h, uint32_t n_steps, uint32_t* out);
+int bb_n_orders(bb_handle* h, uint32_t env, uint64_t* n);
+int bb_n_trades(bb_handle* h, uint32_t env, uint64_t* n);
+/* PyOrder columns (rust/src/types.rs:19-31); order_id == row index.  Any column may be NULL. */
+int bb_orders(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint8_t* side_is_bid, uint8_t* status,
+              uint64_t* arr_time, uint64_t* end_time, uint32_t* vol, uint32_t* start_vol, uint32_t* price,
+              uint32_t* trader);
+/* PyTrade columns (rust/src/types.rs:4-17) */
+int bb_trades(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* t, uint8_t* side_is_bid,
+              uint32_t* price, uint32_t* vol, uint64_t* active_id, uint64_t* passive_id);
+int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* status);
+int bb_time(bb_handle* h, uint32_t env, uint64_t* t);
+int bb_set_time(bb_handle* h, uint32_t env, uint64_t t);
+int bb_set_trading(bb_handle* h, uint32_t env /* or BB_ALL_ENVS */, int on);
+int bb_env_errors(bb_handle* h, uint32_t* out /* [n_envs] */);
+int bb_stats(bb_handle* h, bb_stats_t* out);
+/* device pointer + strides of the history ring, for zero-copy consumers (DLPack at the Python edge) */
+int bb_history_device(bb_handle* h, void** d_ptr, uint64_t* env_stride_words, uint32_t* obs_words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOURSE_B200_H */

@@ -1,0 +1,95 @@
+"""GPU suite: the persistent agents+step kernel against the oracle driven by the same Philox contract.
+RandomAgents involve only integer and f32-compare arithmetic, so the whole market history, order
+table and trade log must match bit for bit.  MomentumAgent goes through f64 tanh/exp/log/cos whose
+last-ulp behaviour may differ between CUDA and glibc; tolerance: identical results on at least 90% of
+envs, and summary statistics within 5% (stated per assertion below)."""
+import numpy as np
+import pytest
+
+from bourse_b200 import abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_run(oracle, groups, seed, env_id, n_steps, tick=1, step_size=1_000_000):
+    env = oracle.StepEnvNumpy(0, 0, tick, step_size)
+    env.set_groups(groups)
+    env.run_agents(n_steps, seed, env_id=env_id, keyed=True)
+    return env
+
+
+@pytest.mark.parametrize("obs_words", [abi.OBS_L1, abi.OBS_L2])
+def test_random_agents_bit_exact(core, oracle, obs_words):
+    n_envs, n_steps, seed = 48, 64, 101
+    groups = workloads.c3_groups()
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=obs_words, env_id_base=1000, max_orders=8192,
+                          max_trades=16384, max_steps=n_steps, max_queue=128)
+    env.set_agents(groups)
+    env.run_agents(n_steps, seed)
+    assert not env.env_errors().any()
+    hist = env.history_all(n_steps)
+    total_instr = 0
+    for e in range(n_envs):
+        ce = oracle_run(oracle, groups, seed, 1000 + e, n_steps)
+        h = ce._history()
+        assert np.array_equal(hist[e], h[:, :obs_words]), e
+        assert env.get_trades(e) == ce.get_trades(), e
+        assert env.get_orders(e) == ce.get_orders(), e
+        total_instr += ce.n_instructions()
+    st = env.stats()
+    assert st["instructions"] == total_instr and st["env_steps"] == n_envs * n_steps
+    assert st["trades"] > 1000
+
+
+def test_run_in_pieces_equals_one_run(core):
+    """Idempotence of the launch boundary: 3 launches of 8/5/19 steps == one launch of 32 (state fully
+    round-trips through HBM, unaligned history offsets take the direct-store path)."""
+    groups = workloads.c3_groups()
+    def make():
+        e = core.BatchedEnv(16, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=4096, max_trades=8192, max_steps=32,
+                            max_queue=128)
+        e.set_agents(groups)
+        return e
+    a, b = make(), make()
+    a.run_agents(32, 9)
+    for k in (8, 5, 19):
+        b.run_agents(k, 9)
+    assert np.array_equal(a.history_all(32), b.history_all(32))
+    for e in range(16):
+        assert a.get_trades(e) == b.get_trades(e) and a.get_orders(e) == b.get_orders(e)
+    assert a.stats() == b.stats()
+
+
+def test_sharding_invariance(core):
+    """Envs keyed by GLOBAL id: 2 shards of 8 envs == 1 handle of 16."""
+    groups = workloads.c3_groups()
+    def make(n, base):
+        e = core.BatchedEnv(n, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1, env_id_base=base, max_orders=2048, max_trades=4096,
+                            max_steps=16, max_queue=128)
+        e.set_agents(groups)
+        e.run_agents(16, 4)
+        return e.history_all(16)
+    whole = make(16, 0)
+    assert np.array_equal(whole[:8], make(8, 0)) and np.array_equal(whole[8:], make(8, 8))
+
+
+def test_momentum_agents_match_oracle(core, oracle):
+    n_envs, n_steps, seed = 40, 80, 7
+    groups = workloads.c4_groups()
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=16384, max_trades=32768,
+                          max_steps=n_steps, max_queue=256)
+    env.set_agents(groups)
+    env.run_agents(n_steps, seed)
+    assert not env.env_errors().any()
+    hist = env.history_all(n_steps)
+    same = 0
+    tv_gpu, tv_cpu, n_mom = 0, 0, 0
+    for e in range(n_envs):
+        ce = oracle_run(oracle, groups, seed, e, n_steps)
+        h = ce._history()
+        same += int(np.array_equal(hist[e], h) and env.get_orders(e) == ce.get_orders())
+        tv_gpu += int(hist[e][:, 0].sum()); tv_cpu += int(h[:, 0].sum())
+        n_mom += sum(1 for o in ce.get_orders() if o[7] >= 80)
+    assert n_mom > 100, "momentum traders must actually trade in this config"
+    assert same >= int(0.9 * n_envs), f"only {same}/{n_envs} envs identical"          # tolerance: >= 90% identical
+    assert abs(tv_gpu - tv_cpu) <= 0.05 * tv_cpu                                       # tolerance: 5% on total traded volume

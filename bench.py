@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: lockstep order-book matching + Env step + in-kernel
+agents + observation emission.
+
+Workload (config C3 of BASELINE.json / SURVEY.md 8d, per GPU): 4096 envs x (50+50) RandomAgents
+(crates/step_sim/examples/random_agents/main.rs:10-19) x 1000 env-steps, level-1 observation per
+env-step, Env(0, tick 1, step 1_000_000).  One bench "step" = one full pass of that workload
+(reset + 1000 env-steps for every env).  Weak scaling: every rank runs its own 4096 envs, keyed by
+global env id; no per-step collective, one NCCL all-gather of the statistics at the end.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference's CPU algorithm (oracle) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "orders_per_sec"
+UNIT = "orders/s"
+N_ENVS_PER_GPU = 4096
+N_SIM_STEPS = 1000
+SEED = 101
+CPU_SAMPLE_ENVS = 1024
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx, self.proc, self.lines = device_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, m in zip(sm, mx) if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(n_envs: int, n_steps: int, threads: int) -> dict:
+    """The reference's algorithm on the host cores: C++ oracle, one env per core at a time, reference-style
+    shared Xoroshiro stream per env (crates/step_sim/src/runner.rs:46-69).  kind "port": the Rust
+    reference cannot be built in this image (no cargo/rustc)."""
+    from bourse_b200 import workloads
+    from oracle import oracle as orc
+
+    orc.build()
+    r = orc.bench_agents(n_envs, threads, n_steps, SEED, workloads.c3_groups(), keyed=False, start_time=0, tick_size=1,
+                         step_size=1_000_000)
+    return {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_envs} envs x {n_steps} env-steps of the C3 workload ({r['instructions']} instructions, "
+                      f"{r['seconds']:.2f} s wall), oracle/ C++ restatement, reference-style Xoroshiro stream per env",
+            "env_steps_per_sec": r["env_steps"] / r["seconds"], "seconds": r["seconds"], "instructions": r["instructions"]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(CPU_SAMPLE_ENVS, N_SIM_STEPS, cores)
+        if i >= args.warmup:
+            vals.append(r)
+            secs.append(r["seconds"])
+    tot_i = sum(r["instructions"] for r in vals)
+    tot_s = sum(secs)
+    v = tot_i / tot_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args.gpus, sample=f"each step = {CPU_SAMPLE_ENVS} envs x {N_SIM_STEPS} env-steps (bounded sample)"),
+        "env_steps_per_sec": sum(r["env_steps_per_sec"] * r["seconds"] for r in vals) / tot_s,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": vals[-1]["sample"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus: int, sample: str | None = None) -> dict:
+    c = {"workload": "C3: 4096 envs/GPU x (50+50) RandomAgents x 1000 env-steps, level-1 obs per env-step, "
+                     "Env(start 0, tick 1, step 1_000_000), agents tick_size 2 (crates/step_sim/examples/random_agents/main.rs)",
+         "n_envs_per_gpu": N_ENVS_PER_GPU, "n_envs_total": N_ENVS_PER_GPU * n_gpus, "env_steps_per_bench_step": N_SIM_STEPS,
+         "agents_per_env": 100, "obs": "level-1 (9 x u32) per env-step", "seed": SEED,
+         "parallelism": f"envs sharded over {n_gpus} GPU(s), no per-step collective",
+         "l2_policy": "working set (order + history slabs, ~7 GB touched per pass) far exceeds the 126 MB L2; "
+                      "a 512 MB buffer is also written between timed passes"}
+    if sample:
+        c["sample"] = sample
+    return c
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from bourse_b200 import abi, core, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bourse_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_envs = args.envs
+    groups = workloads.c3_groups()
+    stream = torch.cuda.current_stream()
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=rank * n_envs, obs_words=abi.OBS_L1,
+                          max_orders=args.max_orders, max_trades=args.max_trades, max_steps=args.sim_steps, max_queue=128)
+    env.set_agents(groups)
+    env.set_stream(stream.cuda_stream)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    n_steps = args.sim_steps
+
+    def one_pass():
+        env.reset()
+        env.run_agents(n_steps, SEED, sync=False)
+
+    # ---- device-resident timing: reset + persistent kernel, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        one_pass()
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    for a, m, b in ev:
+        a.record(stream)
+        env.reset()
+        m.record(stream)
+        env.run_agents(n_steps, SEED, sync=False)
+        b.record(stream)
+        flush.fill_(1)  # untimed L2 flush between passes
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, _, b in ev]
+    kern_ms = [m.elapsed_time(b) for _, m, b in ev]
+    clocks = sampler.stop() if rank == 0 else None
+    stats = env.stats()
+    if stats["error_envs"]:
+        raise SystemExit(f"device flagged errors in {stats['error_envs']} envs: {np.unique(env.env_errors())}")
+    total_ms = sum(step_ms)
+
+    # ---- end-to-end through the public API with HOST buffers: agent table up, full obs history + stats down
+    hist_host = torch.empty((n_envs, n_steps, abi.OBS_L1), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    h2d = len(groups) * abi.GROUP_DTYPE.itemsize
+    d2h = hist_host.nbytes + 64 + n_envs * 36
+    for _ in range(1):
+        env.reset(); env.set_agents(groups); env.run_agents(n_steps, SEED); env.history_all(n_steps, hist_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.reset()
+        env.set_agents(groups)            # host -> device: the agent population
+        env.run_agents(n_steps, SEED)     # synchronous
+        env.history_all(n_steps, hist_host)  # device -> host: every env-step's observation
+        st = env.stats()                  # device -> host: aggregate statistics (+ final level-1 of every env)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    checksum = int(hist_host[:, -1, :].astype(np.uint64).sum())
+
+    # ---- aggregate over ranks: max time, summed work; stats all-gathered over NCCL
+    vec = torch.tensor([total_ms, e2e_s, float(stats["instructions"]), float(stats["env_steps"]), float(stats["trades"]),
+                        float(stats["orders_created"]), float(stats["transitions"]), sum(kern_ms)], dtype=torch.float64,
+                       device="cuda")
+    if world > 1:
+        allv = [torch.empty_like(vec) for _ in range(world)]
+        dist.all_gather(allv, vec)
+        allv = torch.stack(allv).cpu().numpy()
+    else:
+        allv = vec.cpu().numpy()[None]
+    if rank == 0:
+        max_ms, max_e2e = allv[:, 0].max(), allv[:, 1].max()
+        instr_per_pass = allv[:, 2].sum()     # stats are per pass (reset each pass)
+        env_steps_per_pass = allv[:, 3].sum()
+        value = instr_per_pass * args.steps / (max_ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        alg_bytes = workloads.algorithmic_bytes(stats, abi.OBS_L1)          # this rank's k_sim launch
+        k_ms = sum(kern_ms) / len(kern_ms)
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k_sim_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cores = host_cores()
+        cpu = cpu_baseline(CPU_SAMPLE_ENVS, N_SIM_STEPS, cores) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": workload_config(world),
+            "env_steps_per_sec": env_steps_per_pass * args.steps / (max_ms * 1e-3),
+            "orders_per_pass": instr_per_pass, "trades_per_pass": allv[:, 4].sum(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_sim", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_source": peak_src},
+            "e2e": {"value": instr_per_pass * args.steps / max_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * max_e2e / args.steps,
+                    "api": "BatchedEnv.reset/set_agents/run_agents/history_all/stats (C ABI bb_*)", "obs_checksum": checksum},
+            "gpu_launches": 2 * args.steps, "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU)
+    ap.add_argument("--sim-steps", type=int, default=N_SIM_STEPS)
+    ap.add_argument("--max-orders", type=int, default=65536)
+    ap.add_argument("--max-trades", type=int, default=65536)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

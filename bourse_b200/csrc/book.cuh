@@ -472,7 +472,7 @@ __device__ __forceinline__ void book_place(const Ctx& c, u32 id, u32 side, u32 p
 
 // orderbook.rs:622-644
 __device__ __forceinline__ void book_cancel(const Ctx& c, u32 id, u64 t) {
-    if (id >= c.h->n_orders) {
+    if (id >= c.h->n_orders || id >= c.max_orders) {
         c.h->err |= ERR_BAD_ID;
         return;
     }
@@ -487,7 +487,7 @@ __device__ __forceinline__ void book_cancel(const Ctx& c, u32 id, u64 t) {
 
 // orderbook.rs:743-772 (+ reduce_order_vol :656-667, replace_order :679-723)
 __device__ __forceinline__ void book_modify(const Ctx& c, u32 id, bool has_p, u32 new_p, bool has_v, u32 new_v, u64 t) {
-    if (id >= c.h->n_orders) {
+    if (id >= c.h->n_orders || id >= c.max_orders) {
         c.h->err |= ERR_BAD_ID;
         return;
     }

@@ -148,7 +148,7 @@ template <class K> int grid_for(bb_handle* h, K kernel, const SmemLayout& l, u32
     return BB_OK;
 }
 
-int init_books(bb_handle* h) {
+int upload_seeds(bb_handle* h) {
     const bb_config& c = h->cfg;
     std::vector<u64> seeds(2 * (size_t)c.n_envs);
     for (u32 e = 0; e < c.n_envs; ++e) {  // Xoroshiro128StarStar::seed_from_u64 (rand_xoshiro 0.6.0)
@@ -157,11 +157,17 @@ int init_books(bb_handle* h) {
         seeds[2 * e + 1] = splitmix_next(x);
     }
     CUDA_TRY(h, cudaMemcpyAsync(h->d_seeds, seeds.data(), seeds.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+// asynchronous on the handle's stream: one small kernel rewrites every book header and page directory
+int init_books(bb_handle* h) {
+    const bb_config& c = h->cfg;
     k_init<<<c.n_envs, 64, 0, h->stream>>>(h->blobs, h->blob_stride, c.n_envs, h->p_total, c.start_time, c.trading ? 1u : 0u,
                                            h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (auto& q : h->queue) q.clear();
     std::fill(h->n_orders_host.begin(), h->n_orders_host.end(), 0);
     h->mirror_dirty = false;
@@ -316,7 +322,9 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     TRY_ALLOC(cudaMalloc(&h->d_stats, 8 * 8));
     TRY_ALLOC(cudaMallocHost(&h->h_offsets, (ne + 1) * 8));
 #undef TRY_ALLOC
-    int rc = init_books(h);
+    int rc = upload_seeds(h);
+    if (!rc) rc = init_books(h);
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(nullptr, BB_ECUDA, "init kernel failed");
     if (rc) return bail(rc);
     *out = h;
     return BB_OK;

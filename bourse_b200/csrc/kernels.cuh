@@ -284,7 +284,7 @@ __device__ __forceinline__ void random_agents_update(const KParams& p, const bb_
         u32 held = BB_NIL;
         if (valid) held = slots[slot_base + a];
         bool live = false;
-        if (active && held != BB_NIL) live = (c.oh[held].meta & META_STATUS_MASK) == ST_ACTIVE;
+        if (active && held < c.max_orders) live = (c.oh[held].meta & META_STATUS_MASK) == ST_ACTIVE;
         const bool do_cancel = active && live;
         const bool do_new = active && !live;
         const u32 new_mask = __ballot_sync(BB_FULL, do_new);
@@ -330,7 +330,7 @@ __device__ __forceinline__ void momentum_agent_update(const KParams& p, const bb
         bool active = false;
         if (valid) {
             id = ms->live[k];
-            active = (c.oh[id].meta & META_STATUS_MASK) == ST_ACTIVE;
+            active = id < c.max_orders && (c.oh[id].meta & META_STATUS_MASK) == ST_ACTIVE;
         }
         const uint4 r = philox4x32_10(env_g, step, PHILOX_SLOT_CANCEL | gi, k >> 2, p.seed_lo, p.seed_hi);
         const u32 word = (k & 3u) == 0 ? r.x : (k & 3u) == 1 ? r.y : (k & 3u) == 2 ? r.z : r.w;

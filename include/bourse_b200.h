@@ -143,7 +143,7 @@ typedef struct {
 int bb_abi_version(void);
 int bb_create(const bb_config* cfg, bb_handle** out);
 int bb_destroy(bb_handle* h);
-int bb_reset(bb_handle* h); /* back to the freshly created state (same config) */
+int bb_reset(bb_handle* h); /* back to the freshly created state (same config, same agents); asynchronous */
 const char* bb_last_error(const bb_handle* h /* may be NULL */);
 /* run on a caller-owned CUDA stream (cudaStream_t); NULL restores the handle's own stream */
 int bb_set_stream(bb_handle* h, void* cuda_stream);

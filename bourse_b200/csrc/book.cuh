@@ -17,6 +17,9 @@
 //   * price-time queue per level = intrusive doubly linked list through the 32-byte hot order
 //     records in HBM, kept sorted by key time; the common case (time moved forward) appends without
 //     reading the tail record.
+//   * the book header (time, counters, side totals, cached touch) lives in REGISTERS for the whole
+//     launch; shared memory and global memory are addressed with explicit ld/st.shared / ld/st.global
+//     so no generic-address or stack traffic is generated (profiles/r01_v1_summary.md).
 // All book code is warp-uniform: every lane executes it with identical values (loads broadcast, stores
 // coalesce to one transaction); lanes diverge only in the explicitly lane-parallel helpers.
 #pragma once
@@ -75,167 +78,250 @@ struct __align__(16) BookHdr {  // 128 bytes, head of every book blob
 static_assert(sizeof(BookHdr) == 128, "BookHdr must stay 128 bytes");
 static_assert(sizeof(OrderHot) == 32 && sizeof(OrderCold) == 32 && sizeof(TradeRec) == 32, "record sizes");
 
-// Everything a warp needs to operate on its book.
-struct Ctx {
-    BookHdr* h;     // shared memory
-    u32* tag;       // [p_total] shared
-    u32* vmap;      // [p_total] shared
-    u32* qmap;      // [p_total] shared
-    u32* pg_smem;   // [p_smem][128] shared
-    u32* pg_glob;   // [p_total][128] global (slots >= p_smem are live there)
-    OrderHot* oh;   // [max_orders] global
-    OrderCold* oc;  // [max_orders] global
-    TradeRec* tr;   // [max_trades] global
-    u32 p_total, p_smem;
-    u32 granule, tick;
-    u32 max_orders, max_trades;
+// ---- address-space-explicit memory operations ---------------------------------------------------------
+__device__ __forceinline__ u32 lds(u32 a) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ u64 lds64(u32 a) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ u32 ldg32(u64 a) {
+    u32 v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(a));
+    return v;
+}
+__device__ __forceinline__ u64 ldg64(u64 a) {
+    u64 v;
+    asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg128(u64 a) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a));
+    return v;
+}
+__device__ __forceinline__ void stg32(u64 a, u32 v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void stg64(u64 a, u64 v) { asm volatile("st.global.u64 [%0], %1;" ::"l"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void stg128(u64 a, u32 x, u32 y, u32 z, u32 w) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// byte offsets inside records
+#define OH_PRICE 0u
+#define OH_VOL 4u
+#define OH_NEXT 8u
+#define OH_PREV 12u
+#define OH_KEYT 16u
+#define OH_META 24u
+#define OH_SVOL 28u
+#define OC_ARR 0u
+#define OC_END 8u
+// byte offsets inside a 512-byte page
+#define PG_VOL 0u
+#define PG_CNT 128u
+#define PG_HEAD 256u
+#define PG_TAIL 384u
+
+#define FL_TRADING 1u
+#define FL_HAS_ASK 2u  // FL_HAS_ASK << side
+#define FL_HAS_BID 4u
+
+// Launch-invariant geometry (lives in the constant bank through the kernel parameter block).
+struct Geo {
+    u32 p_total, p_smem, granule, tick, max_orders, max_trades;
+};
+
+// Register-resident state of the warp's book.
+struct Book {
+    u64 t, max_key_time;
+    u32 n_orders, n_trades, trade_vol;  // n_trades counts every trade, logged or not
+    u32 vol_ask, vol_bid;  // side totals (side.rs:38)
+    u32 bq_ask, bq_bid;    // cached touch level index by queue
+    u32 flags, err;
+    u32 d_instr, d_trans, d_volume;  // per-launch deltas of the u64 header counters
+    u32 sb;                // shared-space address of the blob image
+    u64 oh, oc, tr, pg;    // global addresses of this env's slabs / page array
     u32 lane;
 };
 
-__device__ __forceinline__ u32* page_ptr(const Ctx& c, u32 slot) {
-    return slot < c.p_smem ? c.pg_smem + slot * 128u : c.pg_glob + (size_t)slot * 128u;
+__device__ __forceinline__ u32 tag_addr(const Book& b, u32 i) { return b.sb + 128u + 4u * i; }
+__device__ __forceinline__ u32 vmap_addr(const Geo& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (g.p_total + i); }
+__device__ __forceinline__ u32 qmap_addr(const Geo& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (2u * g.p_total + i); }
+
+struct PageRef {
+    u64 g;
+    u32 s;
+    bool smem;
+};
+__device__ __forceinline__ PageRef page_ref(const Geo& g, const Book& b, u32 slot) {
+    PageRef r;
+    r.smem = slot < g.p_smem;
+    r.s = b.sb + 128u + 12u * g.p_total + slot * 512u;
+    r.g = b.pg + (u64)slot * 512u;
+    return r;
+}
+__device__ __forceinline__ u32 pld(const PageRef& r, u32 off) { return r.smem ? lds(r.s + off) : ldg32(r.g + off); }
+__device__ __forceinline__ void pst(const PageRef& r, u32 off, u32 v) {
+    if (r.smem) sts(r.s + off, v); else stg32(r.g + off, v);
+}
+
+__device__ __forceinline__ bool has_best(const Book& b, u32 side) { return (b.flags >> (1u + side)) & 1u; }
+__device__ __forceinline__ u32 best_q(const Book& b, u32 side) { return side ? b.bq_bid : b.bq_ask; }
+__device__ __forceinline__ void set_best(Book& b, u32 side, u32 q) {
+    if (side) b.bq_bid = q; else b.bq_ask = q;
+    b.flags |= FL_HAS_ASK << side;
+}
+__device__ __forceinline__ void add_side_vol(Book& b, u32 side, u32 dv) {
+    if (side) b.vol_bid += dv; else b.vol_ask += dv;
+}
+
+// price -> level index; false when the price is not a multiple of the ladder granule
+__device__ __forceinline__ bool to_level(const Geo& g, u32 price, u32* q) {
+    if (g.granule == 1u) {
+        *q = price;
+        return true;
+    }
+    const u32 x = price / g.granule;
+    *q = x;
+    return x * g.granule == price;
 }
 
 // ---- page directory -----------------------------------------------------------------------------
-__device__ __forceinline__ u32 find_page(const Ctx& c, u32 side, u32 pkey) {
+__device__ __forceinline__ u32 find_page(const Geo& g, const Book& b, u32 side, u32 pkey) {
     const u32 want = (pkey << 1) | side;
-    for (u32 b = 0; b < c.p_total; b += 32) {
-        const u32 m = __ballot_sync(BB_FULL, c.tag[b + c.lane] == want);
-        if (m) return b + __ffs(m) - 1;
+    for (u32 base = 0; base < g.p_total; base += 32) {
+        const u32 m = __ballot_sync(BB_FULL, lds(tag_addr(b, base + b.lane)) == want);
+        if (m) return base + __ffs(m) - 1;
     }
     return BB_NIL;
 }
 
-__device__ __forceinline__ u32 alloc_page(const Ctx& c, u32 side, u32 pkey) {
-    for (u32 b = 0; b < c.p_total; b += 32) {
-        const u32 m = __ballot_sync(BB_FULL, c.tag[b + c.lane] == BB_TAG_FREE);
+__device__ __forceinline__ u32 alloc_page(const Geo& g, Book& b, u32 side, u32 pkey) {
+    for (u32 base = 0; base < g.p_total; base += 32) {
+        const u32 m = __ballot_sync(BB_FULL, lds(tag_addr(b, base + b.lane)) == BB_TAG_FREE);
         if (m) {
-            const u32 slot = b + __ffs(m) - 1;
-            c.tag[slot] = (pkey << 1) | side;
-            c.vmap[slot] = 0;
-            c.qmap[slot] = 0;
+            const u32 slot = base + __ffs(m) - 1;
+            sts(tag_addr(b, slot), (pkey << 1) | side);
+            sts(vmap_addr(g, b, slot), 0);
+            sts(qmap_addr(g, b, slot), 0);
             __syncwarp();
             return slot;
         }
     }
-    c.h->err |= ERR_CAP_PAGES;
+    b.err |= ERR_CAP_PAGES;
     return BB_NIL;
 }
 
-// best level by queue (== first key of the reference's `orders` map, side.rs:99-104 / 128-130)
-__device__ __forceinline__ void recompute_best(const Ctx& c, u32 side) {
+// best level by the given bitmap family (qmap: first key of `orders`, side.rs:99-104; vmap: first key
+// of `volumes`, side.rs:107-120).  Returns false when the side is empty.
+__device__ __forceinline__ bool scan_best(const Geo& g, const Book& b, u32 side, bool by_queue, u32* out_q) {
     u32 best = side ? 0u : 0xFFFFFFFFu;
     u32 any = 0;
-    for (u32 b = 0; b < c.p_total; b += 32) {
-        const u32 tg = c.tag[b + c.lane];
-        const u32 qm = c.qmap[b + c.lane];
-        const bool ok = (tg != BB_TAG_FREE) && ((tg & 1u) == side) && (qm != 0);
+    for (u32 base = 0; base < g.p_total; base += 32) {
+        const u32 tg = lds(tag_addr(b, base + b.lane));
+        const u32 bm = lds(by_queue ? qmap_addr(g, b, base + b.lane) : vmap_addr(g, b, base + b.lane));
+        const bool ok = (tg != BB_TAG_FREE) && ((tg & 1u) == side) && (bm != 0);
         any |= __ballot_sync(BB_FULL, ok);
         if (side) {
-            const u32 v = ok ? (((tg >> 1) << 5) + (31u - __clz(qm))) : 0u;
+            const u32 v = ok ? (((tg >> 1) << 5) + (31u - __clz(bm))) : 0u;
             best = max(best, __reduce_max_sync(BB_FULL, v));
         } else {
-            const u32 v = ok ? (((tg >> 1) << 5) + (__ffs(qm) - 1u)) : 0xFFFFFFFFu;
+            const u32 v = ok ? (((tg >> 1) << 5) + (__ffs(bm) - 1u)) : 0xFFFFFFFFu;
             best = min(best, __reduce_min_sync(BB_FULL, v));
         }
     }
-    c.h->best_q[side] = best;
-    c.h->has_best[side] = any != 0;
+    *out_q = best;
+    return any != 0;
 }
 
-// first level of the reference's `volumes` map (side.rs:107-120): (vol, count) at the best price by
-// count>0, which can differ from the queue's best only under N1
-__device__ __forceinline__ void best_by_volumes(const Ctx& c, u32 side, u32* vol, u32* cnt) {
-    u32 best = side ? 0u : 0xFFFFFFFFu;
-    u32 any = 0;
-    for (u32 b = 0; b < c.p_total; b += 32) {
-        const u32 tg = c.tag[b + c.lane];
-        const u32 vm = c.vmap[b + c.lane];
-        const bool ok = (tg != BB_TAG_FREE) && ((tg & 1u) == side) && (vm != 0);
-        any |= __ballot_sync(BB_FULL, ok);
-        if (side) {
-            const u32 v = ok ? (((tg >> 1) << 5) + (31u - __clz(vm))) : 0u;
-            best = max(best, __reduce_max_sync(BB_FULL, v));
-        } else {
-            const u32 v = ok ? (((tg >> 1) << 5) + (__ffs(vm) - 1u)) : 0xFFFFFFFFu;
-            best = min(best, __reduce_min_sync(BB_FULL, v));
-        }
-    }
-    *vol = 0;
-    *cnt = 0;
-    if (any) {
-        const u32 slot = find_page(c, side, best >> 5);
-        const u32* pg = page_ptr(c, slot);
-        *vol = pg[best & 31u];
-        *cnt = pg[32u + (best & 31u)];
-    }
+__device__ __forceinline__ void recompute_best(const Geo& g, Book& b, u32 side) {
+    u32 q;
+    if (scan_best(g, b, side, true, &q)) set_best(b, side, q);
+    else b.flags &= ~(FL_HAS_ASK << side);
 }
 
 // side.rs:99-104 + 194-196: empty ask => u32::MAX, empty bid => 0
-__device__ __forceinline__ u32 best_price(const Ctx& c, u32 side) {
-    if (!c.h->has_best[side]) return side ? 0u : 0xFFFFFFFFu;
-    return c.h->best_q[side] * c.granule;
+__device__ __forceinline__ u32 best_price(const Geo& g, const Book& b, u32 side) {
+    if (!has_best(b, side)) return side ? 0u : 0xFFFFFFFFu;
+    return best_q(b, side) * g.granule;
 }
 
 // side.rs:138-143 through the bid/ask wrappers: (vol, count) at an arbitrary price; warp-cooperative
-__device__ __forceinline__ void level_at(const Ctx& c, u32 side, u32 price, u32* vol, u32* cnt) {
+__device__ __forceinline__ void level_at(const Geo& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
     *vol = 0;
     *cnt = 0;
-    const u32 q = price / c.granule;
-    if (q * c.granule != price) return;
-    const u32 slot = find_page(c, side, q >> 5);
+    u32 q;
+    if (!to_level(g, price, &q)) return;
+    const u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) return;
-    if (!((c.vmap[slot] >> (q & 31u)) & 1u)) return;
-    const u32* pg = page_ptr(c, slot);
-    *vol = pg[q & 31u];
-    *cnt = pg[32u + (q & 31u)];
+    if (!((lds(vmap_addr(g, b, slot)) >> (q & 31u)) & 1u)) return;
+    const PageRef pr = page_ref(g, b, slot);
+    *vol = pld(pr, PG_VOL + 4u * (q & 31u));
+    *cnt = pld(pr, PG_CNT + 4u * (q & 31u));
 }
 
 // same lookup done independently by each lane (divergent prices) — used by the level-2 emitter
-__device__ __forceinline__ void level_at_lane(const Ctx& c, u32 side, u32 price, u32* vol, u32* cnt) {
+__device__ __forceinline__ void level_at_lane(const Geo& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
     *vol = 0;
     *cnt = 0;
-    const u32 q = price / c.granule;
-    if (q * c.granule != price) return;
+    u32 q;
+    if (!to_level(g, price, &q)) return;
     const u32 want = ((q >> 5) << 1) | side;
     u32 slot = BB_NIL;
-    for (u32 j = 0; j < c.p_total; ++j)
-        if (c.tag[j] == want) slot = j;
+    for (u32 j = 0; j < g.p_total; ++j)
+        if (lds(tag_addr(b, j)) == want) slot = j;
     if (slot == BB_NIL) return;
-    if (!((c.vmap[slot] >> (q & 31u)) & 1u)) return;
-    const u32* pg = page_ptr(c, slot);
-    *vol = pg[q & 31u];
-    *cnt = pg[32u + (q & 31u)];
+    if (!((lds(vmap_addr(g, b, slot)) >> (q & 31u)) & 1u)) return;
+    const PageRef pr = page_ref(g, b, slot);
+    *vol = pld(pr, PG_VOL + 4u * (q & 31u));
+    *cnt = pld(pr, PG_CNT + 4u * (q & 31u));
+}
+
+// first level of the reference's `volumes` map (side.rs:107-120)
+__device__ __forceinline__ void best_by_volumes(const Geo& g, const Book& b, u32 side, u32* vol, u32* cnt) {
+    *vol = 0;
+    *cnt = 0;
+    u32 q;
+    if (!scan_best(g, b, side, false, &q)) return;
+    const u32 slot = find_page(g, b, side, q >> 5);
+    const PageRef pr = page_ref(g, b, slot);
+    *vol = pld(pr, PG_VOL + 4u * (q & 31u));
+    *cnt = pld(pr, PG_CNT + 4u * (q & 31u));
 }
 
 // ---- volumes-map half of insert_order / remove_order / remove_vol (side.rs:54-96) ------------------
-__device__ __forceinline__ void level_add(const Ctx& c, u32 side, u32 slot, u32 l, u32 vol) {
-    u32* pg = page_ptr(c, slot);
+__device__ __forceinline__ void level_add(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
     const u32 bit = 1u << l;
-    if (c.vmap[slot] & bit) {
-        pg[l] += vol;
-        pg[32u + l] += 1u;
+    const u32 vm = lds(vmap_addr(g, b, slot));
+    if (vm & bit) {
+        pst(pr, PG_VOL + 4u * l, pld(pr, PG_VOL + 4u * l) + vol);
+        pst(pr, PG_CNT + 4u * l, pld(pr, PG_CNT + 4u * l) + 1u);
     } else {
-        pg[l] = vol;
-        pg[32u + l] = 1u;
-        c.vmap[slot] |= bit;
+        pst(pr, PG_VOL + 4u * l, vol);
+        pst(pr, PG_CNT + 4u * l, 1u);
+        sts(vmap_addr(g, b, slot), vm | bit);
     }
-    c.h->side_vol[side] += vol;
+    add_side_vol(b, side, vol);
 }
 
 // returns true when the page was released
-__device__ __forceinline__ bool level_remove(const Ctx& c, u32 side, u32 slot, u32 l, u32 vol) {
-    u32* pg = page_ptr(c, slot);
+__device__ __forceinline__ bool level_remove(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
     const u32 bit = 1u << l;
-    pg[l] -= vol;
-    const u32 cnt = pg[32u + l] - 1u;
-    pg[32u + l] = cnt;
-    c.h->side_vol[side] -= vol;
+    pst(pr, PG_VOL + 4u * l, pld(pr, PG_VOL + 4u * l) - vol);
+    const u32 cnt = pld(pr, PG_CNT + 4u * l) - 1u;
+    pst(pr, PG_CNT + 4u * l, cnt);
+    add_side_vol(b, side, 0u - vol);
     if (cnt == 0) {
-        const u32 vm = c.vmap[slot] & ~bit;
-        c.vmap[slot] = vm;
-        if (vm == 0 && c.qmap[slot] == 0) {
-            c.tag[slot] = BB_TAG_FREE;
+        const u32 vm = lds(vmap_addr(g, b, slot)) & ~bit;
+        sts(vmap_addr(g, b, slot), vm);
+        if (vm == 0 && lds(qmap_addr(g, b, slot)) == 0) {
+            sts(tag_addr(b, slot), BB_TAG_FREE);
             __syncwarp();
             return true;
         }
@@ -244,199 +330,211 @@ __device__ __forceinline__ bool level_remove(const Ctx& c, u32 side, u32 slot, u
 }
 
 // ---- orders-map half: the price-time queue ----------------------------------------------------------
-// unlink record `id` (with links prev/next) from level (slot,l); maintains qmap and the cached best
-__device__ __forceinline__ void queue_unlink(const Ctx& c, u32 side, u32 slot, u32 l, u32 q, u32 prev, u32 next) {
-    u32* pg = page_ptr(c, slot);
-    if (prev == BB_NIL) pg[64u + l] = next; else c.oh[prev].next = next;
-    if (next == BB_NIL) pg[96u + l] = prev; else c.oh[next].prev = prev;
+// unlink a record with links (prev,next) from level (slot,l); maintains qmap and the cached touch
+__device__ __forceinline__ void queue_unlink(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 q,
+                                             u32 prev, u32 next) {
+    if (prev == BB_NIL) pst(pr, PG_HEAD + 4u * l, next); else stg32(b.oh + (u64)prev * 32u + OH_NEXT, next);
+    if (next == BB_NIL) pst(pr, PG_TAIL + 4u * l, prev); else stg32(b.oh + (u64)next * 32u + OH_PREV, prev);
     if (prev == BB_NIL && next == BB_NIL) {
-        c.qmap[slot] &= ~(1u << l);
+        sts(qmap_addr(g, b, slot), lds(qmap_addr(g, b, slot)) & ~(1u << l));
         __syncwarp();
-        if (c.h->has_best[side] && c.h->best_q[side] == q) recompute_best(c, side);
+        if (has_best(b, side) && best_q(b, side) == q) recompute_best(g, b, side);
     }
 }
 
 // orders.remove(&(price', key_time)) for an order that does NOT own its key any more (N1 ghost):
 // whoever owns that key now loses it and becomes a ghost itself.
-__device__ __noinline__ void queue_remove_key_slow(const Ctx& c, u32 side, u32 slot, u32 l, u32 q, u64 key_time) {
-    const u32* pg = page_ptr(c, slot);
-    if (!((c.qmap[slot] >> l) & 1u)) return;
-    u32 cur = pg[64u + l];
+__device__ __forceinline__ void queue_remove_key_slow(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l,
+                                                      u32 q, u64 key_time) {
+    if (!((lds(qmap_addr(g, b, slot)) >> l) & 1u)) return;
+    u32 cur = pld(pr, PG_HEAD + 4u * l);
     while (cur != BB_NIL) {
-        const OrderHot r = c.oh[cur];
-        if (r.key_time == key_time) {
-            c.oh[cur].meta = r.meta | META_GHOST;
-            queue_unlink(c, side, slot, l, q, r.prev, r.next);
+        const u64 ra = b.oh + (u64)cur * 32u;
+        const uint4 a = ldg128(ra);
+        const u64 kt = ldg64(ra + OH_KEYT);
+        if (kt == key_time) {
+            stg32(ra + OH_META, ldg32(ra + OH_META) | META_GHOST);
+            queue_unlink(g, b, side, slot, pr, l, q, a.w, a.z);
             return;
         }
-        if (r.key_time > key_time) return;
-        cur = r.next;
+        if (kt > key_time) return;
+        cur = a.z;
     }
 }
 
 // orders.insert((price', t), id) when time did not move strictly forward: sorted position, or take
 // over an existing equal key.  Returns the (prev,next) links the new record must carry.
-__device__ __noinline__ void queue_insert_slow(const Ctx& c, u32 slot, u32 l, u32 id, u64 t, u32* out_prev, u32* out_next) {
-    u32* pg = page_ptr(c, slot);
-    u32 cur = pg[96u + l];  // walk back from the tail
-    u32 after = BB_NIL;     // node that will follow the new one
+__device__ __forceinline__ void queue_insert_slow(const Book& b, const PageRef& pr, u32 l, u32 id, u64 t, u32* out_prev,
+                                                  u32* out_next) {
+    u32 cur = pld(pr, PG_TAIL + 4u * l);  // walk back from the tail
+    u32 after = BB_NIL;                   // node that will follow the new one
     while (cur != BB_NIL) {
-        const OrderHot r = c.oh[cur];
-        if (r.key_time < t) break;
-        if (r.key_time == t) {
+        const u64 ra = b.oh + (u64)cur * 32u;
+        const uint4 a = ldg128(ra);
+        const u64 kt = ldg64(ra + OH_KEYT);
+        if (kt < t) break;
+        if (kt == t) {
             // BTreeMap::insert on an existing key: value replaced, position kept (side.rs:55)
-            c.oh[cur].meta = r.meta | META_GHOST;
-            if (r.prev == BB_NIL) pg[64u + l] = id; else c.oh[r.prev].next = id;
-            if (r.next == BB_NIL) pg[96u + l] = id; else c.oh[r.next].prev = id;
-            *out_prev = r.prev;
-            *out_next = r.next;
+            stg32(ra + OH_META, ldg32(ra + OH_META) | META_GHOST);
+            if (a.w == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)a.w * 32u + OH_NEXT, id);
+            if (a.z == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)a.z * 32u + OH_PREV, id);
+            *out_prev = a.w;
+            *out_next = a.z;
             return;
         }
         after = cur;
-        cur = r.prev;
+        cur = a.w;
     }
     // insert between cur (may be NIL => new head) and after (may be NIL => new tail)
-    if (cur == BB_NIL) pg[64u + l] = id; else c.oh[cur].next = id;
-    if (after == BB_NIL) pg[96u + l] = id; else c.oh[after].prev = id;
+    if (cur == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)cur * 32u + OH_NEXT, id);
+    if (after == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)after * 32u + OH_PREV, id);
     *out_prev = cur;
     *out_next = after;
 }
 
 // side.rs:54-66 insert_order for a resting order.  Returns false when the order could not rest.
-__device__ __forceinline__ bool book_insert(const Ctx& c, u32 side, u32 price, u64 t, u32 id, u32 vol, u32* out_prev,
+__device__ __forceinline__ bool book_insert(const Geo& g, Book& b, u32 side, u32 price, u64 t, u32 id, u32 vol, u32* out_prev,
                                             u32* out_next) {
     *out_prev = BB_NIL;
     *out_next = BB_NIL;
-    const u32 q = price / c.granule;
-    if (q * c.granule != price) {
-        c.h->err |= ERR_GRANULE;
+    u32 q;
+    if (!to_level(g, price, &q)) {
+        b.err |= ERR_GRANULE;
         return false;
     }
-    u32 slot = find_page(c, side, q >> 5);
+    u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) {
-        slot = alloc_page(c, side, q >> 5);
+        slot = alloc_page(g, b, side, q >> 5);
         if (slot == BB_NIL) return false;
     }
     const u32 l = q & 31u;
-    level_add(c, side, slot, l, vol);
-    u32* pg = page_ptr(c, slot);
+    const PageRef pr = page_ref(g, b, slot);
+    level_add(g, b, side, slot, pr, l, vol);
     const u32 bit = 1u << l;
-    if (!(c.qmap[slot] & bit)) {
-        pg[64u + l] = id;
-        pg[96u + l] = id;
-        c.qmap[slot] |= bit;
-        const bool better = !c.h->has_best[side] || (side ? q > c.h->best_q[side] : q < c.h->best_q[side]);
-        if (better) {
-            c.h->best_q[side] = q;
-            c.h->has_best[side] = 1;
-        }
-    } else if (t > c.h->max_key_time) {
-        const u32 tail = pg[96u + l];
-        c.oh[tail].next = id;
-        pg[96u + l] = id;
+    const u32 qm = lds(qmap_addr(g, b, slot));
+    if (!(qm & bit)) {
+        pst(pr, PG_HEAD + 4u * l, id);
+        pst(pr, PG_TAIL + 4u * l, id);
+        sts(qmap_addr(g, b, slot), qm | bit);
+        const bool better = !has_best(b, side) || (side ? q > b.bq_bid : q < b.bq_ask);
+        if (better) set_best(b, side, q);
+    } else if (t > b.max_key_time) {
+        const u32 tail = pld(pr, PG_TAIL + 4u * l);
+        stg32(b.oh + (u64)tail * 32u + OH_NEXT, id);
+        pst(pr, PG_TAIL + 4u * l, id);
         *out_prev = tail;
     } else {
-        queue_insert_slow(c, slot, l, id, t, out_prev, out_next);
+        queue_insert_slow(b, pr, l, id, t, out_prev, out_next);
     }
-    if (t > c.h->max_key_time) c.h->max_key_time = t;
+    if (t > b.max_key_time) b.max_key_time = t;
     __syncwarp();
     return true;
 }
 
-// side.rs:75-84 remove_order(key, vol) for the order described by `r`
-__device__ __forceinline__ void book_remove(const Ctx& c, u32 side, const OrderHot& r, u32 vol) {
-    const u32 q = r.price / c.granule;
-    const u32 slot = find_page(c, side, q >> 5);
+// side.rs:75-84 remove_order(key, vol) for an order with the given record fields
+__device__ __forceinline__ void book_remove(const Geo& g, Book& b, u32 side, u32 price, u32 prev, u32 next, u64 key_time,
+                                            bool ghost, u32 vol) {
+    u32 q;
+    to_level(g, price, &q);
+    const u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) return;  // unreachable for Active orders
     const u32 l = q & 31u;
-    if (r.meta & META_GHOST) queue_remove_key_slow(c, side, slot, l, q, r.key_time);
-    else queue_unlink(c, side, slot, l, q, r.prev, r.next);
-    level_remove(c, side, slot, l, vol);
+    const PageRef pr = page_ref(g, b, slot);
+    if (ghost) queue_remove_key_slow(g, b, side, slot, pr, l, q, key_time);
+    else queue_unlink(g, b, side, slot, pr, l, q, prev, next);
+    level_remove(g, b, side, slot, pr, l, vol);
 }
 
-__device__ __forceinline__ void log_trade(const Ctx& c, u64 t, u32 passive_bid, u32 price, u32 vol, u32 active, u32 passive) {
-    const u32 n = c.h->n_trades;
-    if (n < c.max_trades) {
-        TradeRec rec;
-        rec.t = t; rec.price = price; rec.vol = vol; rec.active = active; rec.passive = passive;
-        rec.side_bid = passive_bid; rec.pad = 0;
-        c.tr[n] = rec;
-        c.h->n_trades = n + 1;
-    } else if (c.max_trades) {
-        c.h->err |= ERR_CAP_TRADES;
+__device__ __forceinline__ void log_trade(const Geo& g, Book& b, u64 t, u32 passive_bid, u32 price, u32 vol, u32 active,
+                                          u32 passive) {
+    const u32 n = b.n_trades;
+    if (n < g.max_trades) {
+        const u64 a = b.tr + (u64)n * 32u;
+        stg128(a, (u32)t, (u32)(t >> 32), price, vol);
+        stg128(a + 16u, active, passive, passive_bid, 0u);
+    } else if (g.max_trades) {
+        b.err |= ERR_CAP_TRADES;
     }
-    c.h->n_trades_total += 1;
+    b.n_trades = n + 1;
 }
 
 // orderbook.rs:429-487 match_bid / match_ask + :843-870 match_orders.  Sweeps the opposite side in
 // price-time order; returns the aggressor's remaining volume, *filled as the reference's Status::Filled.
-__device__ __forceinline__ u32 book_match(const Ctx& c, u32 side, u32 price, u32 vol, u32 id, u64 t, bool* filled) {
+__device__ __forceinline__ u32 book_match(const Geo& g, Book& b, u32 side, u32 price, u32 vol, u32 id, u64 t, bool* filled) {
     const u32 o = side ^ 1u;
     *filled = false;
     u32 slot = BB_NIL, slot_key = BB_NIL;
-    while (vol > 0 && c.h->has_best[o]) {
-        const u32 bq = c.h->best_q[o];
-        const u32 bprice = bq * c.granule;
+    PageRef pr = page_ref(g, b, 0);
+    while (vol > 0 && has_best(b, o)) {
+        const u32 bq = best_q(b, o);
+        const u32 bprice = bq * g.granule;
         if (side ? (price < bprice) : (price > bprice)) break;
         if (slot_key != (bq >> 5)) {
-            slot = find_page(c, o, bq >> 5);
+            slot = find_page(g, b, o, bq >> 5);
             slot_key = bq >> 5;
-        }
-        if (slot == BB_NIL) {  // only reachable after a capacity error left the book inconsistent
-            c.h->err |= ERR_CAP_PAGES;
-            break;
+            if (slot == BB_NIL) {  // only reachable after a capacity error left the book inconsistent
+                b.err |= ERR_CAP_PAGES;
+                break;
+            }
+            pr = page_ref(g, b, slot);
         }
         const u32 l = bq & 31u;
-        u32* pg = page_ptr(c, slot);
-        const u32 hid = pg[64u + l];
-        if (hid >= c.max_orders) {
-            c.h->err |= ERR_BAD_ID;
+        const u32 hid = pld(pr, PG_HEAD + 4u * l);
+        if (hid >= g.max_orders) {
+            b.err |= ERR_BAD_ID;
             break;
         }
-        const uint4 ph = *reinterpret_cast<const uint4*>(&c.oh[hid]);  // price, vol, next, prev
+        const u64 ha = b.oh + (u64)hid * 32u;
+        const uint4 ph = ldg128(ha);  // price, vol, next, prev
         const u32 tv = min(vol, ph.y);
         vol -= tv;
         const u32 pvol = ph.y - tv;
-        log_trade(c, t, o, ph.x, tv, id, hid);
-        c.h->trade_vol += tv;
-        c.h->traded_volume += tv;
-        c.h->n_transitions += 1;
+        log_trade(g, b, t, o, ph.x, tv, id, hid);
+        b.trade_vol += tv;
+        b.d_volume += tv;
+        b.d_trans += 1;
         if (pvol == 0) {
-            c.oh[hid].vol = 0;
-            c.oh[hid].meta = ST_FILLED | (o ? META_BID : 0u);
-            c.oc[hid].end_time = t;
+            stg32(ha + OH_VOL, 0u);
+            stg32(ha + OH_META, ST_FILLED | (o ? META_BID : 0u));
+            stg64(b.oc + (u64)hid * 32u + OC_END, t);
             // side.remove_order(match.key, tv): the head always owns its key
             const u32 nxt = ph.z;
-            pg[64u + l] = nxt;
+            pst(pr, PG_HEAD + 4u * l, nxt);
             bool emptied = false;
             if (nxt == BB_NIL) {
-                pg[96u + l] = BB_NIL;
-                c.qmap[slot] &= ~(1u << l);
+                pst(pr, PG_TAIL + 4u * l, BB_NIL);
+                sts(qmap_addr(g, b, slot), lds(qmap_addr(g, b, slot)) & ~(1u << l));
                 emptied = true;
             } else {
-                c.oh[nxt].prev = BB_NIL;
+                stg32(b.oh + (u64)nxt * 32u + OH_PREV, BB_NIL);
             }
-            const bool released = level_remove(c, o, slot, l, tv);
-            if (released) slot_key = BB_NIL;
+            if (level_remove(g, b, o, slot, pr, l, tv)) slot_key = BB_NIL;
             if (emptied) {
                 __syncwarp();
-                recompute_best(c, o);
+                recompute_best(g, b, o);
             }
         } else {
-            c.oh[hid].vol = pvol;
-            pg[l] -= tv;  // side.remove_vol(price, tv)
-            c.h->side_vol[o] -= tv;
+            stg32(ha + OH_VOL, pvol);
+            pst(pr, PG_VOL + 4u * l, pld(pr, PG_VOL + 4u * l) - tv);  // side.remove_vol(price, tv)
+            add_side_vol(b, o, 0u - tv);
         }
         if (vol == 0) *filled = true;
     }
     return vol;
 }
 
+__device__ __forceinline__ void write_order(const Book& b, u32 id, u32 price, u32 vol, u32 next, u32 prev, u64 key_time, u32 meta,
+                                            u32 start_vol) {
+    const u64 a = b.oh + (u64)id * 32u;
+    stg128(a, price, vol, next, prev);
+    stg128(a + 16u, (u32)key_time, (u32)(key_time >> 32), meta, start_vol);
+}
+
 // orderbook.rs:583-611 place_order for a freshly created order whose fields are all known to the
 // caller (create_order :356-396 happened at submission).  Writes the complete record.
-__device__ __forceinline__ void book_place(const Ctx& c, u32 id, u32 side, u32 price, u32 vol, u32 trader, u64 t) {
-    if (id >= c.max_orders) {
-        c.h->err |= ERR_CAP_ORDERS;
+__device__ __forceinline__ void book_place(const Geo& g, Book& b, u32 id, u32 side, u32 price, u32 vol, u32 trader, u64 t) {
+    if (id >= g.max_orders) {
+        b.err |= ERR_CAP_ORDERS;
         return;
     }
     const bool market = side ? (price == 0xFFFFFFFFu) : (price == 0u);  // N3: decided by the price value
@@ -444,89 +542,87 @@ __device__ __forceinline__ void book_place(const Ctx& c, u32 id, u32 side, u32 p
     u64 end_time = ~0ULL;
     bool filled = false;
     if (market) {
-        if (c.h->trading) {
-            rem = book_match(c, side, price, vol, id, t, &filled);
+        if (b.flags & FL_TRADING) {
+            rem = book_match(g, b, side, price, vol, id, t, &filled);
             status = filled ? ST_FILLED : ST_CANCELLED;  // orderbook.rs:517-531
         } else {
             status = ST_REJECTED;
         }
         end_time = t;
     } else {
-        if (c.h->trading) rem = book_match(c, side, price, vol, id, t, &filled);
+        if (b.flags & FL_TRADING) rem = book_match(g, b, side, price, vol, id, t, &filled);
         if (filled) {
             status = ST_FILLED;
             end_time = t;
         } else {
-            book_insert(c, side, price, t, id, rem, &prev, &next);  // orderbook.rs:499-504
+            book_insert(g, b, side, price, t, id, rem, &prev, &next);  // orderbook.rs:499-504
         }
     }
-    OrderHot r;
-    r.price = price; r.vol = rem; r.next = next; r.prev = prev;
-    r.key_time = t; r.meta = status | (side ? META_BID : 0u); r.start_vol = vol;
-    OrderCold cr;
-    cr.arr_time = t; cr.end_time = end_time; cr.trader = trader; cr.pad0 = cr.pad1 = cr.pad2 = 0;
-    c.oh[id] = r;
-    c.oc[id] = cr;
-    c.h->n_transitions += 1;
+    write_order(b, id, price, rem, next, prev, t, status | (side ? META_BID : 0u), vol);
+    const u64 ca = b.oc + (u64)id * 32u;
+    stg128(ca, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));
+    stg128(ca + 16u, trader, 0u, 0u, 0u);
+    b.d_trans += 1;
 }
 
 // orderbook.rs:622-644
-__device__ __forceinline__ void book_cancel(const Ctx& c, u32 id, u64 t) {
-    if (id >= c.h->n_orders || id >= c.max_orders) {
-        c.h->err |= ERR_BAD_ID;
+__device__ __forceinline__ void book_cancel(const Geo& g, Book& b, u32 id, u64 t) {
+    if (id >= b.n_orders || id >= g.max_orders) {
+        b.err |= ERR_BAD_ID;
         return;
     }
-    const OrderHot r = c.oh[id];
-    if ((r.meta & META_STATUS_MASK) != ST_ACTIVE) return;
-    const u32 side = (r.meta & META_BID) ? 1u : 0u;
-    c.oh[id].meta = ST_CANCELLED | (r.meta & META_BID);
-    c.oc[id].end_time = t;
-    book_remove(c, side, r, r.vol);
-    c.h->n_transitions += 1;
+    const u64 ra = b.oh + (u64)id * 32u;
+    const uint4 a = ldg128(ra);        // price, vol, next, prev
+    const uint4 c = ldg128(ra + 16u);  // key_time lo, hi, meta, start_vol
+    if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
+    const u32 side = (c.z & META_BID) ? 1u : 0u;
+    stg32(ra + OH_META, ST_CANCELLED | (c.z & META_BID));
+    stg64(b.oc + (u64)id * 32u + OC_END, t);
+    book_remove(g, b, side, a.x, a.w, a.z, ((u64)c.y << 32) | c.x, (c.z & META_GHOST) != 0, a.y);
+    b.d_trans += 1;
 }
 
 // orderbook.rs:743-772 (+ reduce_order_vol :656-667, replace_order :679-723)
-__device__ __forceinline__ void book_modify(const Ctx& c, u32 id, bool has_p, u32 new_p, bool has_v, u32 new_v, u64 t) {
-    if (id >= c.h->n_orders || id >= c.max_orders) {
-        c.h->err |= ERR_BAD_ID;
+__device__ __forceinline__ void book_modify(const Geo& g, Book& b, u32 id, bool has_p, u32 new_p, bool has_v, u32 new_v, u64 t) {
+    if (id >= b.n_orders || id >= g.max_orders) {
+        b.err |= ERR_BAD_ID;
         return;
     }
-    const OrderHot r = c.oh[id];
-    if ((r.meta & META_STATUS_MASK) != ST_ACTIVE) return;
+    const u64 ra = b.oh + (u64)id * 32u;
+    const uint4 a = ldg128(ra);
+    const uint4 c = ldg128(ra + 16u);
+    if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
     if (!has_p && !has_v) return;
-    const u32 side = (r.meta & META_BID) ? 1u : 0u;
-    if (!has_p && new_v < r.vol) {
-        const u32 d = r.vol - new_v;
-        c.oh[id].vol = new_v;
-        const u32 q = r.price / c.granule;
-        const u32 slot = find_page(c, side, q >> 5);
+    const u32 side = (c.z & META_BID) ? 1u : 0u;
+    if (!has_p && new_v < a.y) {
+        const u32 d = a.y - new_v;
+        stg32(ra + OH_VOL, new_v);
+        u32 q;
+        to_level(g, a.x, &q);
+        const u32 slot = find_page(g, b, side, q >> 5);
         if (slot != BB_NIL) {
-            page_ptr(c, slot)[q & 31u] -= d;
-            c.h->side_vol[side] -= d;
+            const PageRef pr = page_ref(g, b, slot);
+            pst(pr, PG_VOL + 4u * (q & 31u), pld(pr, PG_VOL + 4u * (q & 31u)) - d);
+            add_side_vol(b, side, 0u - d);
         }
-        c.h->n_transitions += 1;
+        b.d_trans += 1;
         return;
     }
-    const u32 price = has_p ? new_p : r.price;
-    const u32 vol = has_v ? new_v : r.vol;
-    book_remove(c, side, r, r.vol);
+    const u32 price = has_p ? new_p : a.x;
+    const u32 vol = has_v ? new_v : a.y;
+    const u64 old_kt = ((u64)c.y << 32) | c.x;
+    book_remove(g, b, side, a.x, a.w, a.z, old_kt, (c.z & META_GHOST) != 0, a.y);
     u32 rem = vol, prev = BB_NIL, next = BB_NIL;
     bool filled = false;
-    if (c.h->trading) rem = book_match(c, side, price, vol, id, t, &filled);
-    OrderHot w;
-    w.price = price; w.vol = rem; w.start_vol = r.start_vol;
+    if (b.flags & FL_TRADING) rem = book_match(g, b, side, price, vol, id, t, &filled);
     if (filled) {
-        w.meta = ST_FILLED | (r.meta & META_BID);
-        w.key_time = r.key_time;
-        c.oc[id].end_time = t;
+        write_order(b, id, price, rem, BB_NIL, BB_NIL, old_kt, ST_FILLED | (c.z & META_BID), c.w);
+        stg64(b.oc + (u64)id * 32u + OC_END, t);
     } else {
-        book_insert(c, side, price, t, id, rem, &prev, &next);
-        w.meta = ST_ACTIVE | (r.meta & META_BID);
-        w.key_time = t;
+        book_insert(g, b, side, price, t, id, rem, &prev, &next);
+        write_order(b, id, price, rem, next, prev, t, ST_ACTIVE | (c.z & META_BID), c.w);
     }
-    w.next = next; w.prev = prev;
-    c.oh[id] = w;
-    c.h->n_transitions += 1;
+    b.d_trans += 1;
 }
 
 // ---- observation emission ------------------------------------------------------------------------
@@ -534,36 +630,97 @@ __device__ __forceinline__ void book_modify(const Ctx& c, u32 id, bool has_p, u3
 // [trade_vol, bid_price, ask_price, ask_vol, bid_vol, then per level i: bid_vol_i, n_bid_i, ask_vol_i, n_ask_i]
 // Levels sit at FIXED tick offsets from the touch with wrapping arithmetic (orderbook.rs:229-264).
 // Each lane returns the word(s) it owns: word index = lane (and lane + 32 for the 45-word record).
-__device__ __forceinline__ void book_obs(const Ctx& c, u32 n_words, u32* w0, u32* w1) {
-    const u32 bid = best_price(c, 1), ask = best_price(c, 0);
-    u32 a = 0, b = 0;
+__device__ __forceinline__ void book_obs(const Geo& g, const Book& b, u32 n_words, u32* w0, u32* w1) {
+    const u32 bid = best_price(g, b, 1), ask = best_price(g, b, 0);
+    u32 x = 0, y = 0;
     if (n_words <= 9u) {
         u32 bv, bc, av, ac;
-        level_at(c, 1, bid, &bv, &bc);
-        level_at(c, 0, ask, &av, &ac);
-        const u32 l = c.lane;
-        a = l == 0 ? c.h->trade_vol : l == 1 ? bid : l == 2 ? ask : l == 3 ? c.h->side_vol[0] : l == 4 ? c.h->side_vol[1]
+        level_at(g, b, 1, bid, &bv, &bc);
+        level_at(g, b, 0, ask, &av, &ac);
+        const u32 l = b.lane;
+        x = l == 0 ? b.trade_vol : l == 1 ? bid : l == 2 ? ask : l == 3 ? b.vol_ask : l == 4 ? b.vol_bid
           : l == 5 ? bv : l == 6 ? bc : l == 7 ? av : l == 8 ? ac : 0u;
     } else {
         // words 5..44: level i = (w-5)/4, field f = (w-5)%4 -> f<2 bid (vol,cnt), else ask (vol,cnt)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const u32 w = c.lane + 32u * half;
+            const u32 w = b.lane + 32u * half;
             u32 val = 0;
             if (w >= 5u && w < 45u) {
                 const u32 i = (w - 5u) >> 2, f = (w - 5u) & 3u;
                 u32 v, n;
-                if (f < 2u) level_at_lane(c, 1, bid - i * c.tick, &v, &n);
-                else level_at_lane(c, 0, ask + i * c.tick, &v, &n);
+                if (f < 2u) level_at_lane(g, b, 1, bid - i * g.tick, &v, &n);
+                else level_at_lane(g, b, 0, ask + i * g.tick, &v, &n);
                 val = (f & 1u) ? n : v;
             } else if (w < 5u) {
-                val = w == 0 ? c.h->trade_vol : w == 1 ? bid : w == 2 ? ask : w == 3 ? c.h->side_vol[0] : c.h->side_vol[1];
+                val = w == 0 ? b.trade_vol : w == 1 ? bid : w == 2 ? ask : w == 3 ? b.vol_ask : b.vol_bid;
             }
-            if (half == 0) a = val; else b = val;
+            if (half == 0) x = val; else y = val;
         }
     }
-    *w0 = a;
-    *w1 = b;
+    *w0 = x;
+    *w1 = y;
+}
+
+// ---- header <-> registers ---------------------------------------------------------------------------
+// n_steps, step_counter and the xoroshiro state stay in the shared-memory header (touched once per step).
+#define HDR_T 0u
+#define HDR_MAXKT 8u
+#define HDR_RNG0 16u
+#define HDR_RNG1 24u
+#define HDR_NORDERS 32u
+#define HDR_NTRADES 36u
+#define HDR_TRADEVOL 40u
+#define HDR_TRADING 44u
+#define HDR_SIDEVOL 48u
+#define HDR_BESTQ 56u
+#define HDR_HASBEST 64u
+#define HDR_ERR 72u
+#define HDR_NSTEPS 76u
+#define HDR_STEPCTR 80u
+#define HDR_NINSTR 88u
+#define HDR_NTRANS 96u
+#define HDR_VOLUME 104u
+#define HDR_NTRADES_TOTAL 112u
+#define HDR_NCREATED 120u
+
+__device__ __forceinline__ void book_from_header(Book& b) {
+    b.t = lds64(b.sb + HDR_T);
+    b.max_key_time = lds64(b.sb + HDR_MAXKT);
+    b.n_orders = lds(b.sb + HDR_NORDERS);
+    b.n_trades = (u32)lds64(b.sb + HDR_NTRADES_TOTAL);
+    b.trade_vol = lds(b.sb + HDR_TRADEVOL);
+    b.vol_ask = lds(b.sb + HDR_SIDEVOL);
+    b.vol_bid = lds(b.sb + HDR_SIDEVOL + 4u);
+    b.bq_ask = lds(b.sb + HDR_BESTQ);
+    b.bq_bid = lds(b.sb + HDR_BESTQ + 4u);
+    b.flags = (lds(b.sb + HDR_TRADING) ? FL_TRADING : 0u) | (lds(b.sb + HDR_HASBEST) ? FL_HAS_ASK : 0u) |
+              (lds(b.sb + HDR_HASBEST + 4u) ? FL_HAS_BID : 0u);
+    b.err = lds(b.sb + HDR_ERR);
+    b.d_instr = b.d_trans = b.d_volume = 0;
+}
+
+__device__ __forceinline__ void book_to_header(const Geo& g, const Book& b) {
+    sts64(b.sb + HDR_T, b.t);
+    sts64(b.sb + HDR_MAXKT, b.max_key_time);
+    sts64(b.sb + HDR_NCREATED, lds64(b.sb + HDR_NCREATED) + (b.n_orders - lds(b.sb + HDR_NORDERS)));
+    sts(b.sb + HDR_NORDERS, b.n_orders);
+    sts(b.sb + HDR_TRADEVOL, b.trade_vol);
+    sts(b.sb + HDR_SIDEVOL, b.vol_ask);
+    sts(b.sb + HDR_SIDEVOL + 4u, b.vol_bid);
+    sts(b.sb + HDR_BESTQ, b.bq_ask);
+    sts(b.sb + HDR_BESTQ + 4u, b.bq_bid);
+    sts(b.sb + HDR_TRADING, (b.flags & FL_TRADING) ? 1u : 0u);
+    sts(b.sb + HDR_HASBEST, (b.flags & FL_HAS_ASK) ? 1u : 0u);
+    sts(b.sb + HDR_HASBEST + 4u, (b.flags & FL_HAS_BID) ? 1u : 0u);
+    sts(b.sb + HDR_ERR, b.err);
+    sts64(b.sb + HDR_NINSTR, lds64(b.sb + HDR_NINSTR) + b.d_instr);
+    sts64(b.sb + HDR_NTRANS, lds64(b.sb + HDR_NTRANS) + b.d_trans);
+    sts64(b.sb + HDR_VOLUME, lds64(b.sb + HDR_VOLUME) + b.d_volume);
+    const u64 tt = lds64(b.sb + HDR_NTRADES_TOTAL);
+    sts64(b.sb + HDR_NTRADES_TOTAL, tt + (u32)(b.n_trades - (u32)tt));
+    sts(b.sb + HDR_NTRADES, min(b.n_trades, g.max_trades));  // records actually present in the trade log
+    __syncwarp();
 }
 
 }  // namespace bb

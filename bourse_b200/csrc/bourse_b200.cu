@@ -119,12 +119,12 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.blob_smem_bytes = h->blob_smem_bytes;
     p.n_envs = h->cfg.n_envs;
     p.env_id_base = h->cfg.env_id_base;
-    p.p_total = h->p_total;
-    p.p_smem = h->p_smem;
-    p.granule = h->granule;
-    p.tick = h->cfg.tick_size;
-    p.max_orders = h->cfg.max_orders;
-    p.max_trades = h->cfg.max_trades;
+    p.geo.p_total = h->p_total;
+    p.geo.p_smem = h->p_smem;
+    p.geo.granule = h->granule;
+    p.geo.tick = h->cfg.tick_size;
+    p.geo.max_orders = h->cfg.max_orders;
+    p.geo.max_trades = h->cfg.max_trades;
     p.max_steps = h->max_steps_padded;
     p.max_queue = h->cfg.max_queue;
     p.obs_words = h->cfg.obs_words;

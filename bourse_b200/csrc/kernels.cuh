@@ -40,8 +40,8 @@ struct KParams {
     u64 hist_env_stride;  // words
     u32 blob_smem_bytes;
     u32 n_envs, env_id_base;
-    u32 p_total, p_smem, granule, tick;
-    u32 max_orders, max_trades, max_steps, max_queue, obs_words;
+    Geo geo;  // p_total, p_smem, granule, tick, max_orders, max_trades
+    u32 max_steps, max_queue, obs_words;
     u32 warp_smem_bytes, off_perm, off_obs, off_instr, off_bar;
     // k_apply
     const bb_instr* instrs;
@@ -56,20 +56,13 @@ struct KParams {
     bb_agent_group groups[MAX_GROUPS];
 };
 
-__device__ __forceinline__ void make_ctx(Ctx& c, const KParams& p, unsigned char* ws, u32 env, u32 lane) {
-    c.h = reinterpret_cast<BookHdr*>(ws);
-    c.tag = reinterpret_cast<u32*>(ws + 128);
-    c.vmap = c.tag + p.p_total;
-    c.qmap = c.vmap + p.p_total;
-    c.pg_smem = c.qmap + p.p_total;
-    c.pg_glob = reinterpret_cast<u32*>(p.blobs + (size_t)env * p.blob_stride + 128 + 12u * p.p_total);
-    c.oh = p.oh + (size_t)env * p.max_orders;
-    c.oc = p.oc + (size_t)env * p.max_orders;
-    c.tr = p.tr + (size_t)env * p.max_trades;
-    c.p_total = p.p_total; c.p_smem = p.p_smem;
-    c.granule = p.granule; c.tick = p.tick;
-    c.max_orders = p.max_orders; c.max_trades = p.max_trades;
-    c.lane = lane;
+__device__ __forceinline__ void make_book(Book& b, const KParams& p, unsigned char* ws, u32 env, u32 lane) {
+    b.sb = smem_u32(ws);
+    b.pg = (u64)(p.blobs + (size_t)env * p.blob_stride + 128 + 12u * p.geo.p_total);
+    b.oh = (u64)(p.oh + (size_t)env * p.geo.max_orders);
+    b.oc = (u64)(p.oc + (size_t)env * p.geo.max_orders);
+    b.tr = (u64)(p.tr + (size_t)env * p.geo.max_trades);
+    b.lane = lane;
 }
 
 // bulk-load the shared-memory image of a book (header, page directory, resident pages)
@@ -97,44 +90,43 @@ __device__ __forceinline__ void blob_store(const KParams& p, unsigned char* ws, 
 }
 
 // append one observation record to the env's history (Level2DataRecords::append_record, data.rs:44-56)
-__device__ __forceinline__ void emit_obs_direct(const Ctx& c, const KParams& p, u32 env) {
+__device__ __forceinline__ void emit_obs_direct(Book& b, const KParams& p, u32 env) {
     u32 w0, w1;
-    book_obs(c, p.obs_words, &w0, &w1);
-    const u32 n = c.h->n_steps;
+    book_obs(p.geo, b, p.obs_words, &w0, &w1);
+    const u32 n = lds(b.sb + HDR_NSTEPS);
     if (n < p.max_steps) {
-        u32* dst = p.hist + (size_t)env * p.hist_env_stride + (size_t)n * p.obs_words;
-        if (c.lane < p.obs_words) dst[c.lane] = w0;
-        if (c.lane + 32u < p.obs_words) dst[c.lane + 32u] = w1;
-        c.h->n_steps = n + 1;
+        const u64 dst = (u64)(p.hist + (size_t)env * p.hist_env_stride + (size_t)n * p.obs_words);
+        if (b.lane < p.obs_words) stg32(dst + 4u * b.lane, w0);
+        if (b.lane + 32u < p.obs_words) stg32(dst + 4u * (b.lane + 32u), w1);
+        sts(b.sb + HDR_NSTEPS, n + 1);
     } else {
-        c.h->err |= ERR_CAP_STEPS;
+        b.err |= ERR_CAP_STEPS;
     }
     __syncwarp();
 }
 
 // one decoded instruction against the book (process_event, orderbook.rs:782-792)
-__device__ __forceinline__ void apply_instr(const Ctx& c, u32 op_flags, u32 order_id, u32 price, u32 vol, u32 trader, u64 t,
-                                            bool assign_id) {
+__device__ __forceinline__ void apply_instr(const Geo& g, Book& b, u32 op_flags, u32 order_id, u32 price, u32 vol, u32 trader,
+                                            u64 t, bool assign_id) {
     const u32 op = op_flags & BB_OP_MASK;
     if (op == BB_OP_NEW) {
         const u32 side = (op_flags & BB_F_BID) ? 1u : 0u;
         if (op_flags & BB_F_MARKET) price = side ? 0xFFFFFFFFu : 0u;  // types.rs:160-172, 213-225
         u32 id = order_id;
         if (assign_id) {
-            id = c.h->n_orders;
-            c.h->n_orders = id + 1;
+            id = b.n_orders;
+            b.n_orders = id + 1;
         }
-        c.h->n_created += 1;
-        c.h->n_instr += 1;
-        book_place(c, id, side, price, vol, trader, t);
+        b.d_instr += 1;
+        book_place(g, b, id, side, price, vol, trader, t);
     } else if (op == BB_OP_CANCEL) {
-        c.h->n_instr += 1;
-        book_cancel(c, order_id, t);
+        b.d_instr += 1;
+        book_cancel(g, b, order_id, t);
     } else if (op == BB_OP_MODIFY) {
-        c.h->n_instr += 1;
-        book_modify(c, order_id, (op_flags & BB_F_HAS_PRICE) != 0, price, (op_flags & BB_F_HAS_VOL) != 0, vol, t);
+        b.d_instr += 1;
+        book_modify(g, b, order_id, (op_flags & BB_F_HAS_PRICE) != 0, price, (op_flags & BB_F_HAS_VOL) != 0, vol, t);
     } else if (op == BB_OP_SET_TRADING) {
-        c.h->trading = vol ? 1u : 0u;
+        b.flags = vol ? (b.flags | FL_TRADING) : (b.flags & ~FL_TRADING);
     }
 }
 
@@ -145,6 +137,7 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
     u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
     uint16_t* perm = reinterpret_cast<uint16_t*>(ws + p.off_perm);
     uint4* chunk = reinterpret_cast<uint4*>(ws + p.off_instr);  // [2][32][2] uint4 = two 1 KB instruction batches
+    const Geo& g = p.geo;
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -156,12 +149,13 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
     u32 ph_blob = 0, ph_c0 = 0, ph_c1 = 0;
 
     for (u32 env = blockIdx.x * wpb + warp; env < p.n_envs; env += gridDim.x * wpb) {
-        Ctx c;
-        make_ctx(c, p, ws, env, lane);
+        Book b;
+        make_book(b, p, ws, env, lane);
         if (!blob_load(p, ws, env, &bar[0], ph_blob, lane)) {
             if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
             return;
         }
+        book_from_header(b);
         const u64 off = p.offsets[env];
         const u32 n = (u32)(p.offsets[env + 1] - off);
         const bb_instr* ins = p.instrs + off;
@@ -188,45 +182,45 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
                 ph ^= 1u;
                 const u32 cnt = min(32u, n - i0);
                 for (u32 k = 0; k < cnt; ++k) {
-                    const uint4 a = chunk[buf * 64u + 2u * k], b = chunk[buf * 64u + 2u * k + 1u];
-                    const u64 t = ((u64)a.y << 32) | a.x;
-                    c.h->t = t;
-                    apply_instr(c, a.z, a.w, b.x, b.y, b.z, t, true);
-                    if (a.z & BB_F_EMIT) emit_obs_direct(c, p, env);
+                    const uint4 x = chunk[buf * 64u + 2u * k], y = chunk[buf * 64u + 2u * k + 1u];
+                    const u64 t = ((u64)x.y << 32) | x.x;
+                    b.t = t;
+                    apply_instr(g, b, x.z, x.w, y.x, y.y, y.z, t, true);
+                    if (x.z & BB_F_EMIT) emit_obs_direct(b, p, env);
                 }
                 __syncwarp();
             }
         } else {
             for (u32 s = 0; s < p.n_steps; ++s) {
-                const u64 start = c.h->t;
-                c.h->trade_vol = 0;  // env.rs:117-118
+                const u64 start = b.t;
+                b.trade_vol = 0;  // env.rs:117-118
                 const u32 m = (s == 0) ? n : 0u;
-                if (m > p.max_queue) c.h->err |= ERR_CAP_QUEUE;
+                if (m > p.max_queue) b.err |= ERR_CAP_QUEUE;
                 const u32 mm = min(m, p.max_queue);
                 // (a) create_order happened at submission (env.rs:173): publish status New for the new ids
                 u32 max_id = 0;
                 for (u32 j = lane; j < mm; j += 32) {
                     const u32 of = ins[j].op_flags, id = ins[j].order_id;
-                    if ((of & BB_OP_MASK) == BB_OP_NEW && id < p.max_orders) {
-                        c.oh[id].meta = ST_NEW | ((of & BB_F_BID) ? META_BID : 0u);
+                    if ((of & BB_OP_MASK) == BB_OP_NEW && id < g.max_orders) {
+                        stg32(b.oh + (u64)id * 32u + OH_META, ST_NEW | ((of & BB_F_BID) ? META_BID : 0u));
                         max_id = max(max_id, id + 1);
                     }
                     perm[j] = (uint16_t)j;
                 }
                 max_id = __reduce_max_sync(BB_FULL, max_id);
-                if (max_id > c.h->n_orders) c.h->n_orders = max_id;
+                if (max_id > b.n_orders) b.n_orders = max_id;
                 __syncwarp();
                 // (b) transactions.shuffle(rng) (env.rs:121): Fisher-Yates from the back
                 {
-                    u64 s0 = c.h->rng_s0, s1 = c.h->rng_s1;
+                    u64 s0 = lds64(b.sb + HDR_RNG0), s1 = lds64(b.sb + HDR_RNG1);
                     for (u32 i = mm; i > 1; --i) {
                         const u32 j = xoroshiro_range(s0, s1, i);
-                        const uint16_t a = perm[i - 1], b = perm[j];
-                        perm[i - 1] = b;
-                        perm[j] = a;
+                        const uint16_t x = perm[i - 1], y = perm[j];
+                        perm[i - 1] = y;
+                        perm[j] = x;
                     }
-                    c.h->rng_s0 = s0;
-                    c.h->rng_s1 = s1;
+                    sts64(b.sb + HDR_RNG0, s0);
+                    sts64(b.sb + HDR_RNG1, s1);
                 }
                 __syncwarp();
                 // (c) process in shuffled order at t = start + i (env.rs:123-127)
@@ -239,19 +233,20 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
                     }
                     __syncwarp();
                     for (u32 k = 0; k < cnt; ++k) {
-                        const uint4 a = chunk[2u * k], b = chunk[2u * k + 1u];
+                        const uint4 x = chunk[2u * k], y = chunk[2u * k + 1u];
                         const u64 t = start + i0 + k;
-                        c.h->t = t;
-                        apply_instr(c, a.z, a.w, b.x, b.y, b.z, t, false);
+                        b.t = t;
+                        apply_instr(g, b, x.z, x.w, y.x, y.y, y.z, t, false);
                     }
                     __syncwarp();
                 }
-                c.h->t = start + p.step_size;  // env.rs:129
-                c.h->step_counter += 1;
-                emit_obs_direct(c, p, env);    // env.rs:132-134
+                b.t = start + p.step_size;  // env.rs:129
+                sts(b.sb + HDR_STEPCTR, lds(b.sb + HDR_STEPCTR) + 1u);
+                emit_obs_direct(b, p, env);  // env.rs:132-134
             }
         }
-        if (c.h->err && lane == 0) atomicOr(p.err_flag, c.h->err);
+        if (b.err && lane == 0) atomicOr(p.err_flag, b.err);
+        book_to_header(g, b);
         blob_store(p, ws, env, lane);
     }
 }
@@ -264,36 +259,40 @@ struct Emit {  // running state of one env-step's transaction queue
 };
 
 __device__ __forceinline__ void queue_push(const KParams& p, uint4* q, Emit& e, bool has, u32 op_flags, u32 id, u32 price,
-                                           u32 vol, Ctx& c) {
+                                           u32 vol, u32 lane) {
     const u32 m = __ballot_sync(BB_FULL, has);
-    const u32 pos = e.n + __popc(m & ((1u << c.lane) - 1u));
+    const u32 pos = e.n + __popc(m & ((1u << lane) - 1u));
     if (has) {
         if (pos < p.max_queue) q[pos] = make_uint4(op_flags, id, price, vol);
     }
     e.n += __popc(m);
 }
 
+__device__ __forceinline__ bool order_is_active(const Geo& g, const Book& b, u32 id) {
+    return id < g.max_orders && (ldg32(b.oh + (u64)id * 32u + OH_META) & META_STATUS_MASK) == ST_ACTIVE;
+}
+
 // RandomAgents::update (crates/step_sim/src/agents/random_agent.rs:85-119), one lane per agent
-__device__ __forceinline__ void random_agents_update(const KParams& p, const bb_agent_group& g, Ctx& c, uint4* q, Emit& e,
-                                                     u32* slots, u32 env_g, u32 step, u32 slot_base) {
-    for (u32 a0 = 0; a0 < g.n_agents; a0 += 32) {
-        const u32 a = a0 + c.lane;
-        const bool valid = a < g.n_agents;
+__device__ __forceinline__ void random_agents_update(const KParams& p, const bb_agent_group& ag, const Book& b, uint4* q,
+                                                     Emit& e, u32* slots, u32 env_g, u32 step, u32 slot_base) {
+    for (u32 a0 = 0; a0 < ag.n_agents; a0 += 32) {
+        const u32 a = a0 + b.lane;
+        const bool valid = a < ag.n_agents;
         const uint4 r = philox4x32_10(env_g, step, slot_base + a, 0, p.seed_lo, p.seed_hi);
-        const bool active = valid && (u32_to_f32_unit(r.x) < g.rate);
+        const bool active = valid && (u32_to_f32_unit(r.x) < ag.rate);
         u32 held = BB_NIL;
         if (valid) held = slots[slot_base + a];
         bool live = false;
-        if (active && held < c.max_orders) live = (c.oh[held].meta & META_STATUS_MASK) == ST_ACTIVE;
+        if (active) live = order_is_active(p.geo, b, held);
         const bool do_cancel = active && live;
         const bool do_new = active && !live;
         const u32 new_mask = __ballot_sync(BB_FULL, do_new);
-        const u32 id = e.next_id + __popc(new_mask & ((1u << c.lane) - 1u));
+        const u32 id = e.next_id + __popc(new_mask & ((1u << b.lane) - 1u));
         const u32 side_bid = r.y >> 31;
-        const u32 tick = g.tick_lo + mulhi_range(r.z, g.tick_hi - g.tick_lo);
-        const u32 vol = g.vol_lo + mulhi_range(r.w, g.vol_hi - g.vol_lo);
+        const u32 tick = ag.tick_lo + mulhi_range(r.z, ag.tick_hi - ag.tick_lo);
+        const u32 vol = ag.vol_lo + mulhi_range(r.w, ag.vol_hi - ag.vol_lo);
         const u32 of = do_cancel ? BB_OP_CANCEL : (BB_OP_NEW | (side_bid ? BB_F_BID : 0u) | (a << 13));
-        queue_push(p, q, e, active, of, do_cancel ? held : id, tick * g.tick_size, vol, c);
+        queue_push(p, q, e, active, of, do_cancel ? held : id, tick * ag.tick_size, vol, b.lane);
         e.next_id += __popc(new_mask);
         if (active) slots[slot_base + a] = do_cancel ? BB_NIL : id;
     }
@@ -318,46 +317,53 @@ __device__ __forceinline__ u32 round_price(double x, double tick, bool up) {
 }
 
 // MomentumAgent::update (crates/step_sim/src/agents/momentum_agent.rs:145-209)
-__device__ __forceinline__ void momentum_agent_update(const KParams& p, const bb_agent_group& g, Ctx& c, uint4* q, Emit& e,
-                                                      MomState* ms, u32 env_g, u32 step, u32 gi, u32 slot_base) {
+struct MomOut {
+    u32 n, next_id, err;
+};
+__device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_agent_group& ag, u64 oh, u32 lane, u32 bid,
+                                                     u32 ask, uint4* q, u32 e_n, u32 e_next_id, MomState* ms, u32 env_g,
+                                                     u32 step, u32 gi, u32 slot_base) {
+    Emit e;
+    e.n = e_n;
+    e.next_id = e_next_id;
+    u32 err = 0;
     // (1) cancel_live_orders (common.rs:56-75): position-indexed draws, survivors compacted in place
     const u32 n_live = ms->n_live;
     u32 n_keep = 0;
     for (u32 k0 = 0; k0 < n_live; k0 += 32) {
-        const u32 k = k0 + c.lane;
+        const u32 k = k0 + lane;
         const bool valid = k < n_live;
         u32 id = BB_NIL;
         bool active = false;
         if (valid) {
             id = ms->live[k];
-            active = id < c.max_orders && (c.oh[id].meta & META_STATUS_MASK) == ST_ACTIVE;
+            active = id < p.geo.max_orders && (ldg32(oh + (u64)id * 32u + OH_META) & META_STATUS_MASK) == ST_ACTIVE;
         }
         const uint4 r = philox4x32_10(env_g, step, PHILOX_SLOT_CANCEL | gi, k >> 2, p.seed_lo, p.seed_hi);
         const u32 word = (k & 3u) == 0 ? r.x : (k & 3u) == 1 ? r.y : (k & 3u) == 2 ? r.z : r.w;
-        const bool keep = active && (u32_to_f32_unit(word) > g.rate);
+        const bool keep = active && (u32_to_f32_unit(word) > ag.rate);
         const bool cancel = active && !keep;
-        queue_push(p, q, e, cancel, BB_OP_CANCEL, id, 0, 0, c);
+        queue_push(p, q, e, cancel, BB_OP_CANCEL, id, 0, 0, lane);
         const u32 km = __ballot_sync(BB_FULL, keep);
         __syncwarp();
-        if (keep) ms->live[n_keep + __popc(km & ((1u << c.lane) - 1u))] = id;
+        if (keep) ms->live[n_keep + __popc(km & ((1u << lane) - 1u))] = id;
         n_keep += __popc(km);
         __syncwarp();
     }
     // (2) mid price of the live book (orderbook.rs:272-276; u32 spread wraps as in a release build)
-    const u32 bid = best_price(c, 1), ask = best_price(c, 0);
     const double mid = (double)bid + 0.5 * (double)(u32)(ask - bid);
     // (3) momentum and order probabilities
     double m = 0.0, p_market = 0.0;
     if (ms->has_last) {
-        m = ms->momentum * (1.0 - g.decay) + g.decay * (mid - ms->last_price);
-        p_market = g.demand * tanh(g.scale * m) / (double)g.n_agents;
+        m = ms->momentum * (1.0 - ag.decay) + ag.decay * (mid - ms->last_price);
+        p_market = ag.demand * tanh(ag.scale * m) / (double)ag.n_agents;
     }
-    const double p_limit = g.order_ratio * p_market;
-    const double tick = (double)g.tick_size;
+    const double p_limit = ag.order_ratio * p_market;
+    const double tick = (double)ag.tick_size;
     // (4) per trader: limit order then market order
-    for (u32 j0 = 0; j0 < g.n_agents; j0 += 32) {
-        const u32 j = j0 + c.lane;
-        const bool valid = j < g.n_agents;
+    for (u32 j0 = 0; j0 < ag.n_agents; j0 += 32) {
+        const u32 j = j0 + lane;
+        const bool valid = j < ag.n_agents;
         const uint4 ra = philox4x32_10(env_g, step, slot_base + j, 0, p.seed_lo, p.seed_hi);
         const uint4 rb = philox4x32_10(env_g, step, slot_base + j, 1, p.seed_lo, p.seed_hi);
         const bool dir = (m > 0.0) || (m < 0.0);
@@ -369,40 +375,45 @@ __device__ __forceinline__ void momentum_agent_update(const KParams& p, const bb
             const double u2 = u64_to_f64_unit(rb.z, rb.w);
             if (u1 < 1e-300) u1 = 1e-300;
             const double nrm = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
-            const double dist = fabs(exp(g.mu + g.sigma * nrm));
+            const double dist = fabs(exp(ag.mu + ag.sigma * nrm));
             price = (m > 0.0) ? round_price(mid - dist, tick, false) : round_price(mid + dist, tick, true);
-            if (price % p.tick != 0) c.h->err |= ERR_GRANULE;  // the reference unwraps a PriceError here
+            if (price % p.geo.tick != 0) err |= ERR_GRANULE;  // the reference unwraps a PriceError here
         }
         u32 total;
         const u32 cnt = (do_limit ? 1u : 0u) + (do_market ? 1u : 0u);
-        const u32 before = warp_excl_scan(cnt, c.lane, &total);
+        const u32 before = warp_excl_scan(cnt, lane, &total);
         const u32 bidf = (m > 0.0) ? BB_F_BID : 0u;
-        const u32 trader = g.tick_lo + j;
+        const u32 trader = ag.tick_lo + j;
         const u32 lm = __ballot_sync(BB_FULL, do_limit);
         const u32 id_l = e.next_id + before;
         const u32 id_m = id_l + (do_limit ? 1u : 0u);
         if (do_limit) {
             const u32 pos = e.n + before;
-            if (pos < p.max_queue) q[pos] = make_uint4(BB_OP_NEW | bidf | (trader << 13), id_l, price, g.vol_lo);
-            const u32 lpos = n_keep + __popc(lm & ((1u << c.lane) - 1u));
-            if (lpos < LIVE_CAP) ms->live[lpos] = id_l; else c.h->err |= ERR_CAP_LIVE;
+            if (pos < p.max_queue) q[pos] = make_uint4(BB_OP_NEW | bidf | (trader << 13), id_l, price, ag.vol_lo);
+            const u32 lpos = n_keep + __popc(lm & ((1u << lane) - 1u));
+            if (lpos < LIVE_CAP) ms->live[lpos] = id_l; else err |= ERR_CAP_LIVE;
         }
         if (do_market) {
             const u32 pos = e.n + before + (do_limit ? 1u : 0u);
-            if (pos < p.max_queue) q[pos] = make_uint4(BB_OP_NEW | BB_F_MARKET | bidf | (trader << 13), id_m, 0, g.vol_lo);
+            if (pos < p.max_queue) q[pos] = make_uint4(BB_OP_NEW | BB_F_MARKET | bidf | (trader << 13), id_m, 0, ag.vol_lo);
         }
         n_keep = min(n_keep + __popc(lm), (u32)LIVE_CAP);
         e.n += total;
         e.next_id += total;
     }
     __syncwarp();
-    if (c.lane == 0) {
+    if (lane == 0) {
         ms->momentum = m;
         ms->last_price = mid;
         ms->has_last = 1;
         ms->n_live = n_keep;
     }
     __syncwarp();
+    MomOut out;
+    out.n = e.n;
+    out.next_id = e.next_id;
+    out.err = err;
+    return out;
 }
 
 __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
@@ -414,6 +425,7 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
     uint16_t* jarr = perm + p.max_queue;
     u32* stage = reinterpret_cast<u32*>(ws + p.off_obs);  // [2][OBS_STAGE_STEPS * obs_words]
     uint4* q = p.scratch + (size_t)(blockIdx.x * wpb + warp) * p.max_queue;
+    const Geo& g = p.geo;
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -424,45 +436,50 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
     const u32 stage_words = OBS_STAGE_STEPS * p.obs_words;
 
     for (u32 env = blockIdx.x * wpb + warp; env < p.n_envs; env += gridDim.x * wpb) {
-        Ctx c;
-        make_ctx(c, p, ws, env, lane);
+        Book b;
+        make_book(b, p, ws, env, lane);
         if (!blob_load(p, ws, env, &bar[0], ph_blob, lane)) {
             if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
             return;
         }
+        book_from_header(b);
         const u32 env_g = p.env_id_base + env;
         u32* slots = p.rslot + (size_t)env * p.agents_per_env;
         u32* hist_env = p.hist + (size_t)env * p.hist_env_stride;
-        const u32 hist0 = c.h->n_steps;
+        const u32 hist0 = lds(b.sb + HDR_NSTEPS);
         const bool staged = (hist0 & 3u) == 0;  // bulk stores need 16-byte aligned record groups
         u32 sbuf = 0, sfill = 0, sbase = hist0;
+        u32 step = lds(b.sb + HDR_STEPCTR);
 
-        for (u32 s = 0; s < p.n_steps; ++s) {
-            const u32 step = c.h->step_counter;
+        for (u32 s = 0; s < p.n_steps; ++s, ++step) {
             // ---- agents.update(env, rng) in declaration order (crates/macros/src/lib.rs:57-72)
             Emit e;
             e.n = 0;
-            e.next_id = c.h->n_orders;
+            e.next_id = b.n_orders;
             u32 slot_base = 0, mi = 0;
             for (u32 gi = 0; gi < p.n_groups; ++gi) {
-                const bb_agent_group& g = p.groups[gi];
-                if (g.kind == BB_GROUP_RANDOM) {
-                    random_agents_update(p, g, c, q, e, slots, env_g, step, slot_base);
+                const bb_agent_group& ag = p.groups[gi];
+                if (ag.kind == BB_GROUP_RANDOM) {
+                    random_agents_update(p, ag, b, q, e, slots, env_g, step, slot_base);
                 } else {
-                    momentum_agent_update(p, g, c, q, e, p.mom + (size_t)env * p.mom_groups_per_env + mi, env_g, step, gi,
-                                          slot_base);
+                    const MomOut mo = momentum_agent_update(p, ag, b.oh, lane, best_price(g, b, 1), best_price(g, b, 0), q, e.n,
+                                                            e.next_id, p.mom + (size_t)env * p.mom_groups_per_env + mi, env_g,
+                                                            step, gi, slot_base);
+                    e.n = mo.n;
+                    e.next_id = mo.next_id;
+                    b.err |= mo.err;
                     ++mi;
                 }
-                slot_base += g.n_agents;
+                slot_base += ag.n_agents;
             }
-            if (e.n > p.max_queue) c.h->err |= ERR_CAP_QUEUE;
+            if (e.n > p.max_queue) b.err |= ERR_CAP_QUEUE;
             const u32 n = min(e.n, p.max_queue);
-            c.h->n_orders = e.next_id;  // create_order at submission (env.rs:173)
+            b.n_orders = e.next_id;  // create_order at submission (env.rs:173)
             __syncwarp();
 
             // ---- Env::step (env.rs:116-135)
-            const u64 start = c.h->t;
-            c.h->trade_vol = 0;
+            const u64 start = b.t;
+            b.trade_vol = 0;
             // shuffle: Fisher-Yates from the back, one Philox word per position, draws made lane-parallel
             for (u32 i = lane; i < n; i += 32) perm[i] = (uint16_t)i;
             for (u32 b0 = 0; b0 * 4u < n; b0 += 32) {
@@ -479,9 +496,9 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
             __syncwarp();
             for (u32 i = n; i > 1; --i) {
                 const u32 j = jarr[i - 1];
-                const uint16_t a = perm[i - 1], b = perm[j];
-                perm[i - 1] = b;
-                perm[j] = a;
+                const uint16_t x = perm[i - 1], y = perm[j];
+                perm[i - 1] = y;
+                perm[j] = x;
             }
             __syncwarp();
             // process in shuffled order at t = start + i
@@ -493,22 +510,20 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
                     const u32 of = __shfl_sync(BB_FULL, mine.x, k), id = __shfl_sync(BB_FULL, mine.y, k);
                     const u32 price = __shfl_sync(BB_FULL, mine.z, k), vol = __shfl_sync(BB_FULL, mine.w, k);
                     const u64 t = start + i0 + k;
-                    c.h->t = t;
-                    apply_instr(c, of & 0x1FFFu, id, price, vol, of >> 13, t, false);
+                    b.t = t;
+                    apply_instr(g, b, of & 0x1FFFu, id, price, vol, of >> 13, t, false);
                 }
             }
-            c.h->t = start + p.step_size;
-            c.h->step_counter = step + 1;
+            b.t = start + p.step_size;
             __syncwarp();
 
             // ---- observation record: staged in shared memory, flushed with bulk stores
             if (staged) {
                 u32 w0, w1;
-                book_obs(c, p.obs_words, &w0, &w1);
+                book_obs(g, b, p.obs_words, &w0, &w1);
                 u32* dst = stage + sbuf * stage_words + sfill * p.obs_words;
                 if (lane < p.obs_words) dst[lane] = w0;
                 if (lane + 32u < p.obs_words) dst[lane + 32u] = w1;
-                c.h->n_steps += 1;
                 if (++sfill == OBS_STAGE_STEPS) {
                     __syncwarp();
                     fence_proxy_async();
@@ -524,19 +539,22 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
                     sbuf ^= 1u;
                 }
             } else {
-                emit_obs_direct(c, p, env);
+                emit_obs_direct(b, p, env);
             }
         }
         // tail of the staging buffer
-        if (staged && sfill) {
+        if (staged) {
             __syncwarp();
             const u32 words = sfill * p.obs_words;
             u32* dst = hist_env + (size_t)sbase * p.obs_words;
             const u32* src = stage + sbuf * stage_words;
             for (u32 i = lane; i < words; i += 32) dst[i] = src[i];
+            sts(b.sb + HDR_NSTEPS, hist0 + p.n_steps);
         }
+        sts(b.sb + HDR_STEPCTR, step);
         if (lane == 0) bulk_wait_all<0>();
-        if (c.h->err && lane == 0) atomicOr(p.err_flag, c.h->err);
+        if (b.err && lane == 0) atomicOr(p.err_flag, b.err);
+        book_to_header(g, b);
         blob_store(p, ws, env, lane);
     }
 }
@@ -550,6 +568,7 @@ __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParam
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned char* ws = smem + (size_t)warp * p.warp_smem_bytes;
     u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
+    const Geo& g = p.geo;
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -559,21 +578,22 @@ __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParam
     u32 ph = 0;
     for (u32 i = blockIdx.x * wpb + warp; i < n_out; i += gridDim.x * wpb) {
         const u32 env = first_env + i;
-        Ctx c;
-        make_ctx(c, p, ws, env, lane);
+        Book b;
+        make_book(b, p, ws, env, lane);
         if (!blob_load(p, ws, env, &bar[0], ph, lane)) return;
+        book_from_header(b);
         u32 w0, w1;
-        book_obs(c, 45u, &w0, &w1);
+        book_obs(g, b, 45u, &w0, &w1);
         if (out45) {
             out45[(size_t)i * 45u + lane] = w0;
             if (lane + 32u < 45u) out45[(size_t)i * 45u + 32u + lane] = w1;
         }
         if (out8) {
             u32 bv, bc, av, ac;
-            best_by_volumes(c, 1, &bv, &bc);
-            best_by_volumes(c, 0, &av, &ac);
-            const u32 bid = best_price(c, 1), ask = best_price(c, 0);
-            const u32 v = lane == 0 ? bid : lane == 1 ? ask : lane == 2 ? c.h->side_vol[1] : lane == 3 ? c.h->side_vol[0]
+            best_by_volumes(g, b, 1, &bv, &bc);
+            best_by_volumes(g, b, 0, &av, &ac);
+            const u32 bid = best_price(g, b, 1), ask = best_price(g, b, 0);
+            const u32 v = lane == 0 ? bid : lane == 1 ? ask : lane == 2 ? b.vol_bid : lane == 3 ? b.vol_ask
                         : lane == 4 ? bv : lane == 5 ? av : lane == 6 ? bc : ac;
             if (lane < 8) out8[(size_t)i * 8u + lane] = v;
         }

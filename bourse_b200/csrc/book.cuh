@@ -49,17 +49,17 @@ enum { ST_NEW = 0, ST_ACTIVE = 1, ST_FILLED = 2, ST_CANCELLED = 3, ST_REJECTED =
 #define ERR_CAP_STEPS 0x40u
 #define ERR_CAP_LIVE 0x80u
 
-// Order record split by access pattern (types.rs:79-101 `Order` + orderbook.rs:36-44 key):
-// hot = what matching / cancel / modify read; cold = write-only timestamps and the trader id.
-struct __align__(16) OrderHot {
+// Order record (types.rs:79-101 `Order` + orderbook.rs:36-44 key), 64 bytes = two 32-byte sectors split
+// by access pattern: the first sector is what matching / cancel / modify read and update, the second
+// holds the write-only timestamps and the trader id.
+struct __align__(16) OrderRec {
     u32 price, vol, next, prev;
     u64 key_time;  // time component of the queue key (arrival, or the last replace)
     u32 meta, start_vol;
-};
-struct __align__(16) OrderCold {
     u64 arr_time, end_time;
     u32 trader, pad0, pad1, pad2;
 };
+#define ORD_STRIDE 64u
 struct __align__(16) TradeRec {  // types.rs:105-118
     u64 t;
     u32 price, vol, active, passive, side_bid, pad;
@@ -76,7 +76,7 @@ struct __align__(16) BookHdr {  // 128 bytes, head of every book blob
     u64 n_instr, n_transitions, traded_volume, n_trades_total, n_created;
 };
 static_assert(sizeof(BookHdr) == 128, "BookHdr must stay 128 bytes");
-static_assert(sizeof(OrderHot) == 32 && sizeof(OrderCold) == 32 && sizeof(TradeRec) == 32, "record sizes");
+static_assert(sizeof(OrderRec) == 64 && sizeof(TradeRec) == 32, "record sizes");
 
 // ---- address-space-explicit memory operations ---------------------------------------------------------
 __device__ __forceinline__ u32 lds(u32 a) {
@@ -120,8 +120,9 @@ __device__ __forceinline__ void stg128(u64 a, u32 x, u32 y, u32 z, u32 w) {
 #define OH_KEYT 16u
 #define OH_META 24u
 #define OH_SVOL 28u
-#define OC_ARR 0u
-#define OC_END 8u
+#define OC_ARR 32u
+#define OC_END 40u
+#define OC_TRADER 48u
 // byte offsets inside a 512-byte page
 #define PG_VOL 0u
 #define PG_CNT 128u
@@ -136,6 +137,13 @@ __device__ __forceinline__ void stg128(u64 a, u32 x, u32 y, u32 z, u32 w) {
 struct Geo {
     u32 p_total, p_smem, granule, tick, max_orders, max_trades;
 };
+// Compile-time specialisation of the common geometry: FAST <=> granule == 1 && p_total == 32, which
+// removes the price division and turns every page-directory loop into a single ballot.
+template <bool FAST_> struct GeoT : Geo {
+    static constexpr bool FAST = FAST_;
+};
+template <class G> __device__ __forceinline__ u32 ptot(const G& g) { return G::FAST ? 32u : g.p_total; }
+template <class G> __device__ __forceinline__ u32 gran(const G& g) { return G::FAST ? 1u : g.granule; }
 
 // Register-resident state of the warp's book.
 struct Book {
@@ -146,23 +154,25 @@ struct Book {
     u32 flags, err;
     u32 d_instr, d_trans, d_volume;  // per-launch deltas of the u64 header counters
     u32 sb;                // shared-space address of the blob image
-    u64 oh, oc, tr, pg;    // global addresses of this env's slabs / page array
+    u64 oh;                // global address of this env's order slab
+    u64 tr;                // global address of this env's trade slab
+    u64 pg;                // global address of this env's page array (slots >= p_smem live there)
     u32 lane;
 };
 
 __device__ __forceinline__ u32 tag_addr(const Book& b, u32 i) { return b.sb + 128u + 4u * i; }
-__device__ __forceinline__ u32 vmap_addr(const Geo& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (g.p_total + i); }
-__device__ __forceinline__ u32 qmap_addr(const Geo& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (2u * g.p_total + i); }
+template <class G> __device__ __forceinline__ u32 vmap_addr(const G& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (ptot(g) + i); }
+template <class G> __device__ __forceinline__ u32 qmap_addr(const G& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (2u * ptot(g) + i); }
 
 struct PageRef {
     u64 g;
     u32 s;
     bool smem;
 };
-__device__ __forceinline__ PageRef page_ref(const Geo& g, const Book& b, u32 slot) {
+template <class G> __device__ __forceinline__ PageRef page_ref(const G& g, const Book& b, u32 slot) {
     PageRef r;
     r.smem = slot < g.p_smem;
-    r.s = b.sb + 128u + 12u * g.p_total + slot * 512u;
+    r.s = b.sb + 128u + 12u * ptot(g) + slot * 512u;
     r.g = b.pg + (u64)slot * 512u;
     return r;
 }
@@ -182,28 +192,28 @@ __device__ __forceinline__ void add_side_vol(Book& b, u32 side, u32 dv) {
 }
 
 // price -> level index; false when the price is not a multiple of the ladder granule
-__device__ __forceinline__ bool to_level(const Geo& g, u32 price, u32* q) {
-    if (g.granule == 1u) {
+template <class G> __device__ __forceinline__ bool to_level(const G& g, u32 price, u32* q) {
+    if (G::FAST || gran(g) == 1u) {
         *q = price;
         return true;
     }
-    const u32 x = price / g.granule;
+    const u32 x = price / gran(g);
     *q = x;
-    return x * g.granule == price;
+    return x * gran(g) == price;
 }
 
 // ---- page directory -----------------------------------------------------------------------------
-__device__ __forceinline__ u32 find_page(const Geo& g, const Book& b, u32 side, u32 pkey) {
+template <class G> __device__ __forceinline__ u32 find_page(const G& g, const Book& b, u32 side, u32 pkey) {
     const u32 want = (pkey << 1) | side;
-    for (u32 base = 0; base < g.p_total; base += 32) {
+    for (u32 base = 0; base < ptot(g); base += 32) {
         const u32 m = __ballot_sync(BB_FULL, lds(tag_addr(b, base + b.lane)) == want);
         if (m) return base + __ffs(m) - 1;
     }
     return BB_NIL;
 }
 
-__device__ __forceinline__ u32 alloc_page(const Geo& g, Book& b, u32 side, u32 pkey) {
-    for (u32 base = 0; base < g.p_total; base += 32) {
+template <class G> __device__ __forceinline__ u32 alloc_page(const G& g, Book& b, u32 side, u32 pkey) {
+    for (u32 base = 0; base < ptot(g); base += 32) {
         const u32 m = __ballot_sync(BB_FULL, lds(tag_addr(b, base + b.lane)) == BB_TAG_FREE);
         if (m) {
             const u32 slot = base + __ffs(m) - 1;
@@ -220,10 +230,10 @@ __device__ __forceinline__ u32 alloc_page(const Geo& g, Book& b, u32 side, u32 p
 
 // best level by the given bitmap family (qmap: first key of `orders`, side.rs:99-104; vmap: first key
 // of `volumes`, side.rs:107-120).  Returns false when the side is empty.
-__device__ __forceinline__ bool scan_best(const Geo& g, const Book& b, u32 side, bool by_queue, u32* out_q) {
+template <class G> __device__ __forceinline__ bool scan_best(const G& g, const Book& b, u32 side, bool by_queue, u32* out_q) {
     u32 best = side ? 0u : 0xFFFFFFFFu;
     u32 any = 0;
-    for (u32 base = 0; base < g.p_total; base += 32) {
+    for (u32 base = 0; base < ptot(g); base += 32) {
         const u32 tg = lds(tag_addr(b, base + b.lane));
         const u32 bm = lds(by_queue ? qmap_addr(g, b, base + b.lane) : vmap_addr(g, b, base + b.lane));
         const bool ok = (tg != BB_TAG_FREE) && ((tg & 1u) == side) && (bm != 0);
@@ -240,20 +250,32 @@ __device__ __forceinline__ bool scan_best(const Geo& g, const Book& b, u32 side,
     return any != 0;
 }
 
-__device__ __forceinline__ void recompute_best(const Geo& g, Book& b, u32 side) {
+template <class G> __device__ __forceinline__ void recompute_best(const G& g, Book& b, u32 side) {
     u32 q;
     if (scan_best(g, b, side, true, &q)) set_best(b, side, q);
     else b.flags &= ~(FL_HAS_ASK << side);
 }
 
+// The touch level (page `slot`, page key `pkey`) just lost its last queued order and `qm` is that page's
+// remaining queue bitmap.  Pages of one side never overlap in price, so when the page that held the best
+// level still has a queued level, the new best is in the same page: one bit scan instead of a directory scan.
+template <class G> __device__ __forceinline__ void next_best_after(const G& g, Book& b, u32 side, u32 pkey, u32 qm) {
+    if (qm) {
+        const u32 l = side ? (31u - __clz(qm)) : (__ffs(qm) - 1u);
+        set_best(b, side, (pkey << 5) + l);
+    } else {
+        recompute_best(g, b, side);
+    }
+}
+
 // side.rs:99-104 + 194-196: empty ask => u32::MAX, empty bid => 0
-__device__ __forceinline__ u32 best_price(const Geo& g, const Book& b, u32 side) {
+template <class G> __device__ __forceinline__ u32 best_price(const G& g, const Book& b, u32 side) {
     if (!has_best(b, side)) return side ? 0u : 0xFFFFFFFFu;
-    return best_q(b, side) * g.granule;
+    return best_q(b, side) * gran(g);
 }
 
 // side.rs:138-143 through the bid/ask wrappers: (vol, count) at an arbitrary price; warp-cooperative
-__device__ __forceinline__ void level_at(const Geo& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
+template <class G> __device__ __forceinline__ void level_at(const G& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
     *vol = 0;
     *cnt = 0;
     u32 q;
@@ -267,14 +289,14 @@ __device__ __forceinline__ void level_at(const Geo& g, const Book& b, u32 side, 
 }
 
 // same lookup done independently by each lane (divergent prices) — used by the level-2 emitter
-__device__ __forceinline__ void level_at_lane(const Geo& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
+template <class G> __device__ __forceinline__ void level_at_lane(const G& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
     *vol = 0;
     *cnt = 0;
     u32 q;
     if (!to_level(g, price, &q)) return;
     const u32 want = ((q >> 5) << 1) | side;
     u32 slot = BB_NIL;
-    for (u32 j = 0; j < g.p_total; ++j)
+    for (u32 j = 0; j < ptot(g); ++j)
         if (lds(tag_addr(b, j)) == want) slot = j;
     if (slot == BB_NIL) return;
     if (!((lds(vmap_addr(g, b, slot)) >> (q & 31u)) & 1u)) return;
@@ -284,7 +306,7 @@ __device__ __forceinline__ void level_at_lane(const Geo& g, const Book& b, u32 s
 }
 
 // first level of the reference's `volumes` map (side.rs:107-120)
-__device__ __forceinline__ void best_by_volumes(const Geo& g, const Book& b, u32 side, u32* vol, u32* cnt) {
+template <class G> __device__ __forceinline__ void best_by_volumes(const G& g, const Book& b, u32 side, u32* vol, u32* cnt) {
     *vol = 0;
     *cnt = 0;
     u32 q;
@@ -296,7 +318,7 @@ __device__ __forceinline__ void best_by_volumes(const Geo& g, const Book& b, u32
 }
 
 // ---- volumes-map half of insert_order / remove_order / remove_vol (side.rs:54-96) ------------------
-__device__ __forceinline__ void level_add(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
+template <class G> __device__ __forceinline__ void level_add(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
     const u32 bit = 1u << l;
     const u32 vm = lds(vmap_addr(g, b, slot));
     if (vm & bit) {
@@ -311,7 +333,7 @@ __device__ __forceinline__ void level_add(const Geo& g, Book& b, u32 side, u32 s
 }
 
 // returns true when the page was released
-__device__ __forceinline__ bool level_remove(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
+template <class G> __device__ __forceinline__ bool level_remove(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
     const u32 bit = 1u << l;
     pst(pr, PG_VOL + 4u * l, pld(pr, PG_VOL + 4u * l) - vol);
     const u32 cnt = pld(pr, PG_CNT + 4u * l) - 1u;
@@ -331,25 +353,26 @@ __device__ __forceinline__ bool level_remove(const Geo& g, Book& b, u32 side, u3
 
 // ---- orders-map half: the price-time queue ----------------------------------------------------------
 // unlink a record with links (prev,next) from level (slot,l); maintains qmap and the cached touch
-__device__ __forceinline__ void queue_unlink(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 q,
+template <class G> __device__ __forceinline__ void queue_unlink(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 q,
                                              u32 prev, u32 next) {
-    if (prev == BB_NIL) pst(pr, PG_HEAD + 4u * l, next); else stg32(b.oh + (u64)prev * 32u + OH_NEXT, next);
-    if (next == BB_NIL) pst(pr, PG_TAIL + 4u * l, prev); else stg32(b.oh + (u64)next * 32u + OH_PREV, prev);
+    if (prev == BB_NIL) pst(pr, PG_HEAD + 4u * l, next); else stg32(b.oh + (u64)prev * ORD_STRIDE + OH_NEXT, next);
+    if (next == BB_NIL) pst(pr, PG_TAIL + 4u * l, prev); else stg32(b.oh + (u64)next * ORD_STRIDE + OH_PREV, prev);
     if (prev == BB_NIL && next == BB_NIL) {
-        sts(qmap_addr(g, b, slot), lds(qmap_addr(g, b, slot)) & ~(1u << l));
+        const u32 qm = lds(qmap_addr(g, b, slot)) & ~(1u << l);
+        sts(qmap_addr(g, b, slot), qm);
         __syncwarp();
-        if (has_best(b, side) && best_q(b, side) == q) recompute_best(g, b, side);
+        if (has_best(b, side) && best_q(b, side) == q) next_best_after(g, b, side, q >> 5, qm);
     }
 }
 
 // orders.remove(&(price', key_time)) for an order that does NOT own its key any more (N1 ghost):
 // whoever owns that key now loses it and becomes a ghost itself.
-__device__ __forceinline__ void queue_remove_key_slow(const Geo& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l,
+template <class G> __device__ __forceinline__ void queue_remove_key_slow(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l,
                                                       u32 q, u64 key_time) {
     if (!((lds(qmap_addr(g, b, slot)) >> l) & 1u)) return;
     u32 cur = pld(pr, PG_HEAD + 4u * l);
     while (cur != BB_NIL) {
-        const u64 ra = b.oh + (u64)cur * 32u;
+        const u64 ra = b.oh + (u64)cur * ORD_STRIDE;
         const uint4 a = ldg128(ra);
         const u64 kt = ldg64(ra + OH_KEYT);
         if (kt == key_time) {
@@ -369,15 +392,15 @@ __device__ __forceinline__ void queue_insert_slow(const Book& b, const PageRef& 
     u32 cur = pld(pr, PG_TAIL + 4u * l);  // walk back from the tail
     u32 after = BB_NIL;                   // node that will follow the new one
     while (cur != BB_NIL) {
-        const u64 ra = b.oh + (u64)cur * 32u;
+        const u64 ra = b.oh + (u64)cur * ORD_STRIDE;
         const uint4 a = ldg128(ra);
         const u64 kt = ldg64(ra + OH_KEYT);
         if (kt < t) break;
         if (kt == t) {
             // BTreeMap::insert on an existing key: value replaced, position kept (side.rs:55)
             stg32(ra + OH_META, ldg32(ra + OH_META) | META_GHOST);
-            if (a.w == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)a.w * 32u + OH_NEXT, id);
-            if (a.z == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)a.z * 32u + OH_PREV, id);
+            if (a.w == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)a.w * ORD_STRIDE + OH_NEXT, id);
+            if (a.z == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)a.z * ORD_STRIDE + OH_PREV, id);
             *out_prev = a.w;
             *out_next = a.z;
             return;
@@ -386,14 +409,14 @@ __device__ __forceinline__ void queue_insert_slow(const Book& b, const PageRef& 
         cur = a.w;
     }
     // insert between cur (may be NIL => new head) and after (may be NIL => new tail)
-    if (cur == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)cur * 32u + OH_NEXT, id);
-    if (after == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)after * 32u + OH_PREV, id);
+    if (cur == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)cur * ORD_STRIDE + OH_NEXT, id);
+    if (after == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)after * ORD_STRIDE + OH_PREV, id);
     *out_prev = cur;
     *out_next = after;
 }
 
 // side.rs:54-66 insert_order for a resting order.  Returns false when the order could not rest.
-__device__ __forceinline__ bool book_insert(const Geo& g, Book& b, u32 side, u32 price, u64 t, u32 id, u32 vol, u32* out_prev,
+template <class G> __device__ __forceinline__ bool book_insert(const G& g, Book& b, u32 side, u32 price, u64 t, u32 id, u32 vol, u32* out_prev,
                                             u32* out_next) {
     *out_prev = BB_NIL;
     *out_next = BB_NIL;
@@ -420,7 +443,7 @@ __device__ __forceinline__ bool book_insert(const Geo& g, Book& b, u32 side, u32
         if (better) set_best(b, side, q);
     } else if (t > b.max_key_time) {
         const u32 tail = pld(pr, PG_TAIL + 4u * l);
-        stg32(b.oh + (u64)tail * 32u + OH_NEXT, id);
+        stg32(b.oh + (u64)tail * ORD_STRIDE + OH_NEXT, id);
         pst(pr, PG_TAIL + 4u * l, id);
         *out_prev = tail;
     } else {
@@ -432,7 +455,7 @@ __device__ __forceinline__ bool book_insert(const Geo& g, Book& b, u32 side, u32
 }
 
 // side.rs:75-84 remove_order(key, vol) for an order with the given record fields
-__device__ __forceinline__ void book_remove(const Geo& g, Book& b, u32 side, u32 price, u32 prev, u32 next, u64 key_time,
+template <class G> __device__ __forceinline__ void book_remove(const G& g, Book& b, u32 side, u32 price, u32 prev, u32 next, u64 key_time,
                                             bool ghost, u32 vol) {
     u32 q;
     to_level(g, price, &q);
@@ -445,7 +468,7 @@ __device__ __forceinline__ void book_remove(const Geo& g, Book& b, u32 side, u32
     level_remove(g, b, side, slot, pr, l, vol);
 }
 
-__device__ __forceinline__ void log_trade(const Geo& g, Book& b, u64 t, u32 passive_bid, u32 price, u32 vol, u32 active,
+template <class G> __device__ __forceinline__ void log_trade(const G& g, Book& b, u64 t, u32 passive_bid, u32 price, u32 vol, u32 active,
                                           u32 passive) {
     const u32 n = b.n_trades;
     if (n < g.max_trades) {
@@ -460,14 +483,14 @@ __device__ __forceinline__ void log_trade(const Geo& g, Book& b, u64 t, u32 pass
 
 // orderbook.rs:429-487 match_bid / match_ask + :843-870 match_orders.  Sweeps the opposite side in
 // price-time order; returns the aggressor's remaining volume, *filled as the reference's Status::Filled.
-__device__ __forceinline__ u32 book_match(const Geo& g, Book& b, u32 side, u32 price, u32 vol, u32 id, u64 t, bool* filled) {
+template <class G> __device__ __forceinline__ u32 book_match(const G& g, Book& b, u32 side, u32 price, u32 vol, u32 id, u64 t, bool* filled) {
     const u32 o = side ^ 1u;
     *filled = false;
     u32 slot = BB_NIL, slot_key = BB_NIL;
     PageRef pr = page_ref(g, b, 0);
     while (vol > 0 && has_best(b, o)) {
         const u32 bq = best_q(b, o);
-        const u32 bprice = bq * g.granule;
+        const u32 bprice = bq * gran(g);
         if (side ? (price < bprice) : (price > bprice)) break;
         if (slot_key != (bq >> 5)) {
             slot = find_page(g, b, o, bq >> 5);
@@ -484,7 +507,7 @@ __device__ __forceinline__ u32 book_match(const Geo& g, Book& b, u32 side, u32 p
             b.err |= ERR_BAD_ID;
             break;
         }
-        const u64 ha = b.oh + (u64)hid * 32u;
+        const u64 ha = b.oh + (u64)hid * ORD_STRIDE;
         const uint4 ph = ldg128(ha);  // price, vol, next, prev
         const u32 tv = min(vol, ph.y);
         vol -= tv;
@@ -496,22 +519,24 @@ __device__ __forceinline__ u32 book_match(const Geo& g, Book& b, u32 side, u32 p
         if (pvol == 0) {
             stg32(ha + OH_VOL, 0u);
             stg32(ha + OH_META, ST_FILLED | (o ? META_BID : 0u));
-            stg64(b.oc + (u64)hid * 32u + OC_END, t);
+            stg64(b.oh + (u64)hid * ORD_STRIDE + OC_END, t);
             // side.remove_order(match.key, tv): the head always owns its key
             const u32 nxt = ph.z;
             pst(pr, PG_HEAD + 4u * l, nxt);
             bool emptied = false;
+            u32 qm = 0;
             if (nxt == BB_NIL) {
                 pst(pr, PG_TAIL + 4u * l, BB_NIL);
-                sts(qmap_addr(g, b, slot), lds(qmap_addr(g, b, slot)) & ~(1u << l));
+                qm = lds(qmap_addr(g, b, slot)) & ~(1u << l);
+                sts(qmap_addr(g, b, slot), qm);
                 emptied = true;
             } else {
-                stg32(b.oh + (u64)nxt * 32u + OH_PREV, BB_NIL);
+                stg32(b.oh + (u64)nxt * ORD_STRIDE + OH_PREV, BB_NIL);
             }
             if (level_remove(g, b, o, slot, pr, l, tv)) slot_key = BB_NIL;
             if (emptied) {
                 __syncwarp();
-                recompute_best(g, b, o);
+                next_best_after(g, b, o, bq >> 5, qm);
             }
         } else {
             stg32(ha + OH_VOL, pvol);
@@ -525,14 +550,14 @@ __device__ __forceinline__ u32 book_match(const Geo& g, Book& b, u32 side, u32 p
 
 __device__ __forceinline__ void write_order(const Book& b, u32 id, u32 price, u32 vol, u32 next, u32 prev, u64 key_time, u32 meta,
                                             u32 start_vol) {
-    const u64 a = b.oh + (u64)id * 32u;
+    const u64 a = b.oh + (u64)id * ORD_STRIDE;
     stg128(a, price, vol, next, prev);
     stg128(a + 16u, (u32)key_time, (u32)(key_time >> 32), meta, start_vol);
 }
 
 // orderbook.rs:583-611 place_order for a freshly created order whose fields are all known to the
 // caller (create_order :356-396 happened at submission).  Writes the complete record.
-__device__ __forceinline__ void book_place(const Geo& g, Book& b, u32 id, u32 side, u32 price, u32 vol, u32 trader, u64 t) {
+template <class G> __device__ __forceinline__ void book_place(const G& g, Book& b, u32 id, u32 side, u32 price, u32 vol, u32 trader, u64 t) {
     if (id >= g.max_orders) {
         b.err |= ERR_CAP_ORDERS;
         return;
@@ -559,36 +584,36 @@ __device__ __forceinline__ void book_place(const Geo& g, Book& b, u32 id, u32 si
         }
     }
     write_order(b, id, price, rem, next, prev, t, status | (side ? META_BID : 0u), vol);
-    const u64 ca = b.oc + (u64)id * 32u;
+    const u64 ca = b.oh + (u64)id * ORD_STRIDE + OC_ARR;
     stg128(ca, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));
     stg128(ca + 16u, trader, 0u, 0u, 0u);
     b.d_trans += 1;
 }
 
 // orderbook.rs:622-644
-__device__ __forceinline__ void book_cancel(const Geo& g, Book& b, u32 id, u64 t) {
+template <class G> __device__ __forceinline__ void book_cancel(const G& g, Book& b, u32 id, u64 t) {
     if (id >= b.n_orders || id >= g.max_orders) {
         b.err |= ERR_BAD_ID;
         return;
     }
-    const u64 ra = b.oh + (u64)id * 32u;
+    const u64 ra = b.oh + (u64)id * ORD_STRIDE;
     const uint4 a = ldg128(ra);        // price, vol, next, prev
     const uint4 c = ldg128(ra + 16u);  // key_time lo, hi, meta, start_vol
     if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
     const u32 side = (c.z & META_BID) ? 1u : 0u;
     stg32(ra + OH_META, ST_CANCELLED | (c.z & META_BID));
-    stg64(b.oc + (u64)id * 32u + OC_END, t);
+    stg64(b.oh + (u64)id * ORD_STRIDE + OC_END, t);
     book_remove(g, b, side, a.x, a.w, a.z, ((u64)c.y << 32) | c.x, (c.z & META_GHOST) != 0, a.y);
     b.d_trans += 1;
 }
 
 // orderbook.rs:743-772 (+ reduce_order_vol :656-667, replace_order :679-723)
-__device__ __forceinline__ void book_modify(const Geo& g, Book& b, u32 id, bool has_p, u32 new_p, bool has_v, u32 new_v, u64 t) {
+template <class G> __device__ __forceinline__ void book_modify(const G& g, Book& b, u32 id, bool has_p, u32 new_p, bool has_v, u32 new_v, u64 t) {
     if (id >= b.n_orders || id >= g.max_orders) {
         b.err |= ERR_BAD_ID;
         return;
     }
-    const u64 ra = b.oh + (u64)id * 32u;
+    const u64 ra = b.oh + (u64)id * ORD_STRIDE;
     const uint4 a = ldg128(ra);
     const uint4 c = ldg128(ra + 16u);
     if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
@@ -617,7 +642,7 @@ __device__ __forceinline__ void book_modify(const Geo& g, Book& b, u32 id, bool 
     if (b.flags & FL_TRADING) rem = book_match(g, b, side, price, vol, id, t, &filled);
     if (filled) {
         write_order(b, id, price, rem, BB_NIL, BB_NIL, old_kt, ST_FILLED | (c.z & META_BID), c.w);
-        stg64(b.oc + (u64)id * 32u + OC_END, t);
+        stg64(b.oh + (u64)id * ORD_STRIDE + OC_END, t);
     } else {
         book_insert(g, b, side, price, t, id, rem, &prev, &next);
         write_order(b, id, price, rem, next, prev, t, ST_ACTIVE | (c.z & META_BID), c.w);
@@ -630,7 +655,7 @@ __device__ __forceinline__ void book_modify(const Geo& g, Book& b, u32 id, bool 
 // [trade_vol, bid_price, ask_price, ask_vol, bid_vol, then per level i: bid_vol_i, n_bid_i, ask_vol_i, n_ask_i]
 // Levels sit at FIXED tick offsets from the touch with wrapping arithmetic (orderbook.rs:229-264).
 // Each lane returns the word(s) it owns: word index = lane (and lane + 32 for the 45-word record).
-__device__ __forceinline__ void book_obs(const Geo& g, const Book& b, u32 n_words, u32* w0, u32* w1) {
+template <class G> __device__ __forceinline__ void book_obs(const G& g, const Book& b, u32 n_words, u32* w0, u32* w1) {
     const u32 bid = best_price(g, b, 1), ask = best_price(g, b, 0);
     u32 x = 0, y = 0;
     if (n_words <= 9u) {
@@ -700,7 +725,7 @@ __device__ __forceinline__ void book_from_header(Book& b) {
     b.d_instr = b.d_trans = b.d_volume = 0;
 }
 
-__device__ __forceinline__ void book_to_header(const Geo& g, const Book& b) {
+template <class G> __device__ __forceinline__ void book_to_header(const G& g, const Book& b) {
     sts64(b.sb + HDR_T, b.t);
     sts64(b.sb + HDR_MAXKT, b.max_key_time);
     sts64(b.sb + HDR_NCREATED, lds64(b.sb + HDR_NCREATED) + (b.n_orders - lds(b.sb + HDR_NORDERS)));

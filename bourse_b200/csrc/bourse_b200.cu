@@ -34,8 +34,7 @@ struct bb_handle {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // device
     unsigned char* blobs = nullptr;
-    OrderHot* oh = nullptr;
-    OrderCold* oc = nullptr;
+    OrderRec* ord = nullptr;
     TradeRec* tr = nullptr;
     u32* hist = nullptr;
     u32* err_flag = nullptr;
@@ -94,7 +93,7 @@ SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr) {
     SmemLayout l{};
     u32 off = align_up(h->blob_smem_bytes, 16);
     l.off_perm = off;
-    off += align_up(4u * h->cfg.max_queue, 16);  // perm + jarr (u16 each)
+    off += align_up(4u * h->cfg.max_queue + 16u, 16);  // perm + jarr (u16 each) + slack for 8-byte jarr stores
     l.off_obs = off;
     if (with_obs) off += align_up(2u * OBS_STAGE_STEPS * h->cfg.obs_words * 4u, 16);
     l.off_instr = off;
@@ -109,8 +108,7 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     memset(&p, 0, sizeof(p));
     p.blobs = h->blobs;
     p.blob_stride = h->blob_stride;
-    p.oh = h->oh;
-    p.oc = h->oc;
+    p.ord = h->ord;
     p.tr = h->tr;
     p.hist = h->hist;
     p.err_flag = h->err_flag;
@@ -228,13 +226,18 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     p.n_steps = n_steps;
     int grid = 0, rc;
     const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
+    const bool fast = h->granule == 1 && h->p_total == 32;
+#define LAUNCH_APPLY(M, F)                                                                       \
+    do {                                                                                         \
+        if ((rc = grid_for(h, k_apply<M, F>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;    \
+        k_apply<M, F><<<grid, WPB * 32, smem, h->stream>>>(p);                                   \
+    } while (0)
     if (mode == MODE_REPLAY) {
-        if ((rc = grid_for(h, k_apply<MODE_REPLAY>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;
-        k_apply<MODE_REPLAY><<<grid, WPB * 32, smem, h->stream>>>(p);
+        if (fast) LAUNCH_APPLY(MODE_REPLAY, true); else LAUNCH_APPLY(MODE_REPLAY, false);
     } else {
-        if ((rc = grid_for(h, k_apply<MODE_ENV>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;
-        k_apply<MODE_ENV><<<grid, WPB * 32, smem, h->stream>>>(p);
+        if (fast) LAUNCH_APPLY(MODE_ENV, true); else LAUNCH_APPLY(MODE_ENV, false);
     }
+#undef LAUNCH_APPLY
     CUDA_TRY(h, cudaGetLastError());
     return BB_OK;
 }
@@ -311,8 +314,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     TRY_ALLOC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     TRY_ALLOC(cudaMalloc(&h->blobs, ne * h->blob_stride));
-    TRY_ALLOC(cudaMalloc(&h->oh, ne * cfg->max_orders * sizeof(OrderHot)));
-    TRY_ALLOC(cudaMalloc(&h->oc, ne * cfg->max_orders * sizeof(OrderCold)));
+    TRY_ALLOC(cudaMalloc(&h->ord, ne * cfg->max_orders * sizeof(OrderRec)));
     if (cfg->max_trades) TRY_ALLOC(cudaMalloc(&h->tr, ne * cfg->max_trades * sizeof(TradeRec)));
     TRY_ALLOC(cudaMalloc(&h->hist, ne * h->hist_env_stride * 4));
     TRY_ALLOC(cudaMalloc(&h->err_flag, 4));
@@ -334,7 +336,7 @@ int bb_destroy(bb_handle* h) {
     if (!h) return BB_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->blobs); cudaFree(h->oh); cudaFree(h->oc); cudaFree(h->tr); cudaFree(h->hist); cudaFree(h->err_flag);
+    cudaFree(h->blobs); cudaFree(h->ord); cudaFree(h->tr); cudaFree(h->hist); cudaFree(h->err_flag);
     cudaFree(h->d_offsets); cudaFree(h->d_seeds); cudaFree(h->d_instrs); cudaFree(h->d_snap); cudaFree(h->d_stats);
     cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch);
     if (h->h_instrs) cudaFreeHost(h->h_instrs);
@@ -539,7 +541,10 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     p.seed_hi = (u32)(seed >> 32);
     for (size_t i = 0; i < h->groups.size(); ++i) p.groups[i] = h->groups[i];
     int grid = 0, rc;
-    if ((rc = grid_for(h, k_sim, h->lay_sim, h->cfg.n_envs, &grid))) return rc;
+    const bool fast = h->granule == 1 && h->p_total == 32;
+    if ((rc = fast ? grid_for(h, k_sim<true>, h->lay_sim, h->cfg.n_envs, &grid)
+                   : grid_for(h, k_sim<false>, h->lay_sim, h->cfg.n_envs, &grid)))
+        return rc;
     const size_t warps = (size_t)grid * WPB;
     if (warps > h->scratch_warps) {
         cudaFree(h->scratch);
@@ -548,7 +553,8 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
         h->scratch_warps = warps;
     }
     p.scratch = h->scratch;
-    k_sim<<<grid, WPB * 32, (size_t)h->lay_sim.warp_bytes * WPB, h->stream>>>(p);
+    if (fast) k_sim<true><<<grid, WPB * 32, (size_t)h->lay_sim.warp_bytes * WPB, h->stream>>>(p);
+    else k_sim<false><<<grid, WPB * 32, (size_t)h->lay_sim.warp_bytes * WPB, h->stream>>>(p);
     CUDA_TRY(h, cudaGetLastError());
     h->mirror_dirty = true;
     return BB_OK;
@@ -673,26 +679,22 @@ int bb_orders(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint8_t* s
     for (auto& x : h->queue[env]) n_queued_new += (x.op_flags & BB_OP_MASK) == BB_OP_NEW;
     const u64 n_dev = h->n_orders_host[env] - n_queued_new;
     const u64 dev_n = first < n_dev ? std::min(n, n_dev - first) : 0;
-    std::vector<OrderHot> hot(dev_n);
-    std::vector<OrderCold> cold(dev_n);
-    if (dev_n) {
-        CUDA_TRY(h, cudaMemcpyAsync(hot.data(), h->oh + (size_t)env * h->cfg.max_orders + first, dev_n * sizeof(OrderHot),
+    std::vector<OrderRec> rec(dev_n);
+    if (dev_n)
+        CUDA_TRY(h, cudaMemcpyAsync(rec.data(), h->ord + (size_t)env * h->cfg.max_orders + first, dev_n * sizeof(OrderRec),
                                     cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaMemcpyAsync(cold.data(), h->oc + (size_t)env * h->cfg.max_orders + first, dev_n * sizeof(OrderCold),
-                                    cudaMemcpyDeviceToHost, h->stream));
-    }
     u64 t_now = 0;
     CUDA_TRY(h, cudaMemcpyAsync(&t_now, h->blobs + (size_t)env * h->blob_stride, 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (u64 i = 0; i < dev_n; ++i) {
-        if (side_is_bid) side_is_bid[i] = (hot[i].meta & META_BID) ? 1 : 0;
-        if (status) status[i] = (uint8_t)(hot[i].meta & META_STATUS_MASK);
-        if (arr_time) arr_time[i] = cold[i].arr_time;
-        if (end_time) end_time[i] = cold[i].end_time;
-        if (vol) vol[i] = hot[i].vol;
-        if (start_vol) start_vol[i] = hot[i].start_vol;
-        if (price) price[i] = hot[i].price;
-        if (trader) trader[i] = cold[i].trader;
+        if (side_is_bid) side_is_bid[i] = (rec[i].meta & META_BID) ? 1 : 0;
+        if (status) status[i] = (uint8_t)(rec[i].meta & META_STATUS_MASK);
+        if (arr_time) arr_time[i] = rec[i].arr_time;
+        if (end_time) end_time[i] = rec[i].end_time;
+        if (vol) vol[i] = rec[i].vol;
+        if (start_vol) start_vol[i] = rec[i].start_vol;
+        if (price) price[i] = rec[i].price;
+        if (trader) trader[i] = rec[i].trader;
     }
     for (auto& x : h->queue[env]) {
         if ((x.op_flags & BB_OP_MASK) != BB_OP_NEW) continue;
@@ -749,7 +751,7 @@ int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* stat
             return BB_OK;
         }
     u32 meta = 0;
-    CUDA_TRY(h, cudaMemcpyAsync(&meta, &h->oh[(size_t)env * h->cfg.max_orders + order_id].meta, 4, cudaMemcpyDeviceToHost,
+    CUDA_TRY(h, cudaMemcpyAsync(&meta, &h->ord[(size_t)env * h->cfg.max_orders + order_id].meta, 4, cudaMemcpyDeviceToHost,
                                 h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *status = (uint8_t)(meta & META_STATUS_MASK);

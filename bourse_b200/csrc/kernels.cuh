@@ -31,8 +31,7 @@ static_assert(sizeof(MomState) == 16 + 8 + 4 * LIVE_CAP, "MomState layout");
 struct KParams {
     unsigned char* blobs;
     u64 blob_stride;
-    OrderHot* oh;
-    OrderCold* oc;
+    OrderRec* ord;
     TradeRec* tr;
     u32* hist;
     u32* err_flag;
@@ -59,10 +58,19 @@ struct KParams {
 __device__ __forceinline__ void make_book(Book& b, const KParams& p, unsigned char* ws, u32 env, u32 lane) {
     b.sb = smem_u32(ws);
     b.pg = (u64)(p.blobs + (size_t)env * p.blob_stride + 128 + 12u * p.geo.p_total);
-    b.oh = (u64)(p.oh + (size_t)env * p.geo.max_orders);
-    b.oc = (u64)(p.oc + (size_t)env * p.geo.max_orders);
+    b.oh = (u64)(p.ord + (size_t)env * p.geo.max_orders);
     b.tr = (u64)(p.tr + (size_t)env * p.geo.max_trades);
     b.lane = lane;
+}
+
+// u16 accessors for the per-warp permutation arrays in shared memory
+__device__ __forceinline__ u32 lds16(u32 a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts16(u32 a, u32 v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
 
 // bulk-load the shared-memory image of a book (header, page directory, resident pages)
@@ -90,9 +98,9 @@ __device__ __forceinline__ void blob_store(const KParams& p, unsigned char* ws, 
 }
 
 // append one observation record to the env's history (Level2DataRecords::append_record, data.rs:44-56)
-__device__ __forceinline__ void emit_obs_direct(Book& b, const KParams& p, u32 env) {
+template <class G> __device__ __forceinline__ void emit_obs_direct(const G& g, Book& b, const KParams& p, u32 env) {
     u32 w0, w1;
-    book_obs(p.geo, b, p.obs_words, &w0, &w1);
+    book_obs(g, b, p.obs_words, &w0, &w1);
     const u32 n = lds(b.sb + HDR_NSTEPS);
     if (n < p.max_steps) {
         const u64 dst = (u64)(p.hist + (size_t)env * p.hist_env_stride + (size_t)n * p.obs_words);
@@ -106,7 +114,7 @@ __device__ __forceinline__ void emit_obs_direct(Book& b, const KParams& p, u32 e
 }
 
 // one decoded instruction against the book (process_event, orderbook.rs:782-792)
-__device__ __forceinline__ void apply_instr(const Geo& g, Book& b, u32 op_flags, u32 order_id, u32 price, u32 vol, u32 trader,
+template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book& b, u32 op_flags, u32 order_id, u32 price, u32 vol, u32 trader,
                                             u64 t, bool assign_id) {
     const u32 op = op_flags & BB_OP_MASK;
     if (op == BB_OP_NEW) {
@@ -130,14 +138,14 @@ __device__ __forceinline__ void apply_instr(const Geo& g, Book& b, u32 op_flags,
     }
 }
 
-template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __grid_constant__ KParams p) {
+template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned char* ws = smem + (size_t)warp * p.warp_smem_bytes;
     u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
-    uint16_t* perm = reinterpret_cast<uint16_t*>(ws + p.off_perm);
+    const u32 perm = smem_u32(ws + p.off_perm);                 // u16 [max_queue]
     uint4* chunk = reinterpret_cast<uint4*>(ws + p.off_instr);  // [2][32][2] uint4 = two 1 KB instruction batches
-    const Geo& g = p.geo;
+    const GeoT<FAST>& g = static_cast<const GeoT<FAST>&>(p.geo);
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -186,7 +194,7 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
                     const u64 t = ((u64)x.y << 32) | x.x;
                     b.t = t;
                     apply_instr(g, b, x.z, x.w, y.x, y.y, y.z, t, true);
-                    if (x.z & BB_F_EMIT) emit_obs_direct(b, p, env);
+                    if (x.z & BB_F_EMIT) emit_obs_direct(g, b, p, env);
                 }
                 __syncwarp();
             }
@@ -202,10 +210,10 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
                 for (u32 j = lane; j < mm; j += 32) {
                     const u32 of = ins[j].op_flags, id = ins[j].order_id;
                     if ((of & BB_OP_MASK) == BB_OP_NEW && id < g.max_orders) {
-                        stg32(b.oh + (u64)id * 32u + OH_META, ST_NEW | ((of & BB_F_BID) ? META_BID : 0u));
+                        stg32(b.oh + (u64)id * ORD_STRIDE + OH_META, ST_NEW | ((of & BB_F_BID) ? META_BID : 0u));
                         max_id = max(max_id, id + 1);
                     }
-                    perm[j] = (uint16_t)j;
+                    sts16(perm + 2u * j, j);
                 }
                 max_id = __reduce_max_sync(BB_FULL, max_id);
                 if (max_id > b.n_orders) b.n_orders = max_id;
@@ -215,9 +223,9 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
                     u64 s0 = lds64(b.sb + HDR_RNG0), s1 = lds64(b.sb + HDR_RNG1);
                     for (u32 i = mm; i > 1; --i) {
                         const u32 j = xoroshiro_range(s0, s1, i);
-                        const uint16_t x = perm[i - 1], y = perm[j];
-                        perm[i - 1] = y;
-                        perm[j] = x;
+                        const u32 x = lds16(perm + 2u * (i - 1)), y = lds16(perm + 2u * j);
+                        sts16(perm + 2u * (i - 1), y);
+                        sts16(perm + 2u * j, x);
                     }
                     sts64(b.sb + HDR_RNG0, s0);
                     sts64(b.sb + HDR_RNG1, s1);
@@ -227,7 +235,7 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
                 for (u32 i0 = 0; i0 < mm; i0 += 32) {
                     const u32 cnt = min(32u, mm - i0);
                     if (lane < cnt) {
-                        const uint4* src = reinterpret_cast<const uint4*>(ins + perm[i0 + lane]);
+                        const uint4* src = reinterpret_cast<const uint4*>(ins + lds16(perm + 2u * (i0 + lane)));
                         chunk[2u * lane] = src[0];
                         chunk[2u * lane + 1u] = src[1];
                     }
@@ -242,7 +250,7 @@ template <int MODE> __global__ void __launch_bounds__(128, 7) k_apply(const __gr
                 }
                 b.t = start + p.step_size;  // env.rs:129
                 sts(b.sb + HDR_STEPCTR, lds(b.sb + HDR_STEPCTR) + 1u);
-                emit_obs_direct(b, p, env);  // env.rs:132-134
+                emit_obs_direct(g, b, p, env);  // env.rs:132-134
             }
         }
         if (b.err && lane == 0) atomicOr(p.err_flag, b.err);
@@ -269,7 +277,7 @@ __device__ __forceinline__ void queue_push(const KParams& p, uint4* q, Emit& e, 
 }
 
 __device__ __forceinline__ bool order_is_active(const Geo& g, const Book& b, u32 id) {
-    return id < g.max_orders && (ldg32(b.oh + (u64)id * 32u + OH_META) & META_STATUS_MASK) == ST_ACTIVE;
+    return id < g.max_orders && (ldg32(b.oh + (u64)id * ORD_STRIDE + OH_META) & META_STATUS_MASK) == ST_ACTIVE;
 }
 
 // RandomAgents::update (crates/step_sim/src/agents/random_agent.rs:85-119), one lane per agent
@@ -337,7 +345,7 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
         bool active = false;
         if (valid) {
             id = ms->live[k];
-            active = id < p.geo.max_orders && (ldg32(oh + (u64)id * 32u + OH_META) & META_STATUS_MASK) == ST_ACTIVE;
+            active = id < p.geo.max_orders && (ldg32(oh + (u64)id * ORD_STRIDE + OH_META) & META_STATUS_MASK) == ST_ACTIVE;
         }
         const uint4 r = philox4x32_10(env_g, step, PHILOX_SLOT_CANCEL | gi, k >> 2, p.seed_lo, p.seed_hi);
         const u32 word = (k & 3u) == 0 ? r.x : (k & 3u) == 1 ? r.y : (k & 3u) == 2 ? r.z : r.w;
@@ -416,16 +424,17 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     return out;
 }
 
-__global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
+template <bool FAST> __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned char* ws = smem + (size_t)warp * p.warp_smem_bytes;
     u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
-    uint16_t* perm = reinterpret_cast<uint16_t*>(ws + p.off_perm);
-    uint16_t* jarr = perm + p.max_queue;
-    u32* stage = reinterpret_cast<u32*>(ws + p.off_obs);  // [2][OBS_STAGE_STEPS * obs_words]
+    const u32 perm = smem_u32(ws + p.off_perm);  // u16 [max_queue]
+    const u32 jarr = perm + 2u * p.max_queue;    // u16 [max_queue]
+    const u32 stage = smem_u32(ws + p.off_obs);  // u32 [2][OBS_STAGE_STEPS * obs_words]
     uint4* q = p.scratch + (size_t)(blockIdx.x * wpb + warp) * p.max_queue;
-    const Geo& g = p.geo;
+    const u64 qa = (u64)q;
+    const GeoT<FAST>& g = static_cast<const GeoT<FAST>&>(p.geo);
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -481,37 +490,37 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
             const u64 start = b.t;
             b.trade_vol = 0;
             // shuffle: Fisher-Yates from the back, one Philox word per position, draws made lane-parallel
-            for (u32 i = lane; i < n; i += 32) perm[i] = (uint16_t)i;
+            for (u32 i = lane; i < n; i += 32) sts16(perm + 2u * i, i);
             for (u32 b0 = 0; b0 * 4u < n; b0 += 32) {
                 const u32 blk = b0 + lane;
                 if (blk * 4u < n) {
                     const uint4 r = philox4x32_10(env_g, step, PHILOX_SLOT_SHUFFLE, blk, p.seed_lo, p.seed_hi);
                     const u32 i = blk * 4u;
-                    if (i + 0 < n) jarr[i + 0] = (uint16_t)mulhi_range(r.x, i + 1);
-                    if (i + 1 < n) jarr[i + 1] = (uint16_t)mulhi_range(r.y, i + 2);
-                    if (i + 2 < n) jarr[i + 2] = (uint16_t)mulhi_range(r.z, i + 3);
-                    if (i + 3 < n) jarr[i + 3] = (uint16_t)mulhi_range(r.w, i + 4);
+                    // 4 consecutive u16 slots are always in bounds: the array is padded to a multiple of 8 bytes
+                    const u32 j0 = mulhi_range(r.x, i + 1), j1 = mulhi_range(r.y, i + 2);
+                    const u32 j2 = mulhi_range(r.z, i + 3), j3 = mulhi_range(r.w, i + 4);
+                    sts(jarr + 2u * i, j0 | (j1 << 16));
+                    sts(jarr + 2u * i + 4u, j2 | (j3 << 16));
                 }
             }
             __syncwarp();
             for (u32 i = n; i > 1; --i) {
-                const u32 j = jarr[i - 1];
-                const uint16_t x = perm[i - 1], y = perm[j];
-                perm[i - 1] = y;
-                perm[j] = x;
+                const u32 j = lds16(jarr + 2u * (i - 1));
+                const u32 x = lds16(perm + 2u * (i - 1)), y = lds16(perm + 2u * j);
+                sts16(perm + 2u * (i - 1), y);
+                sts16(perm + 2u * j, x);
             }
             __syncwarp();
             // process in shuffled order at t = start + i
             for (u32 i0 = 0; i0 < n; i0 += 32) {
                 const u32 cnt = min(32u, n - i0);
                 uint4 mine = make_uint4(0, 0, 0, 0);
-                if (lane < cnt) mine = q[perm[i0 + lane]];
+                if (lane < cnt) mine = ldg128(qa + 16u * lds16(perm + 2u * (i0 + lane)));
                 for (u32 k = 0; k < cnt; ++k) {
                     const u32 of = __shfl_sync(BB_FULL, mine.x, k), id = __shfl_sync(BB_FULL, mine.y, k);
                     const u32 price = __shfl_sync(BB_FULL, mine.z, k), vol = __shfl_sync(BB_FULL, mine.w, k);
-                    const u64 t = start + i0 + k;
-                    b.t = t;
-                    apply_instr(g, b, of & 0x1FFFu, id, price, vol, of >> 13, t, false);
+                    apply_instr(g, b, of & 0x1FFFu, id, price, vol, of >> 13, b.t, false);
+                    b.t += 1;
                 }
             }
             b.t = start + p.step_size;
@@ -521,15 +530,16 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
             if (staged) {
                 u32 w0, w1;
                 book_obs(g, b, p.obs_words, &w0, &w1);
-                u32* dst = stage + sbuf * stage_words + sfill * p.obs_words;
-                if (lane < p.obs_words) dst[lane] = w0;
-                if (lane + 32u < p.obs_words) dst[lane + 32u] = w1;
+                const u32 dst = stage + 4u * (sbuf * stage_words + sfill * p.obs_words);
+                if (lane < p.obs_words) sts(dst + 4u * lane, w0);
+                if (lane + 32u < p.obs_words) sts(dst + 4u * (lane + 32u), w1);
                 if (++sfill == OBS_STAGE_STEPS) {
                     __syncwarp();
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        bulk_s2g(hist_env + (size_t)sbase * p.obs_words, stage + sbuf * stage_words, stage_words * 4u);
+                        bulk_s2g(hist_env + (size_t)sbase * p.obs_words,
+                                 ws + p.off_obs + 4u * (sbuf * stage_words), stage_words * 4u);
                         bulk_commit();
                         bulk_wait_read<1>();  // the other buffer's previous flush has released its source
                     }
@@ -539,7 +549,7 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
                     sbuf ^= 1u;
                 }
             } else {
-                emit_obs_direct(b, p, env);
+                emit_obs_direct(g, b, p, env);
             }
         }
         // tail of the staging buffer
@@ -547,8 +557,8 @@ __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams 
             __syncwarp();
             const u32 words = sfill * p.obs_words;
             u32* dst = hist_env + (size_t)sbase * p.obs_words;
-            const u32* src = stage + sbuf * stage_words;
-            for (u32 i = lane; i < words; i += 32) dst[i] = src[i];
+            const u32 src = stage + 4u * (sbuf * stage_words);
+            for (u32 i = lane; i < words; i += 32) dst[i] = lds(src + 4u * i);
             sts(b.sb + HDR_NSTEPS, hist0 + p.n_steps);
         }
         sts(b.sb + HDR_STEPCTR, step);
@@ -568,7 +578,7 @@ __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParam
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned char* ws = smem + (size_t)warp * p.warp_smem_bytes;
     u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
-    const Geo& g = p.geo;
+    const GeoT<false>& g = static_cast<const GeoT<false>&>(p.geo);
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

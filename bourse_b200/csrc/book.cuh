@@ -136,6 +136,9 @@ __device__ __forceinline__ void stg128(u64 a, u32 x, u32 y, u32 z, u32 w) {
 // Launch-invariant geometry (lives in the constant bank through the kernel parameter block).
 struct Geo {
     u32 p_total, p_smem, granule, tick, max_orders, max_trades;
+    u64 tr_base;      // trade slabs  [n_envs][max_trades] x 32 B
+    u64 blobs_base;   // book blobs   [n_envs] x blob_stride
+    u64 blob_stride;
 };
 // Compile-time specialisation of the common geometry: FAST <=> granule == 1 && p_total == 32, which
 // removes the price division and turns every page-directory loop into a single ballot.
@@ -154,9 +157,9 @@ struct Book {
     u32 flags, err;
     u32 d_instr, d_trans, d_volume;  // per-launch deltas of the u64 header counters
     u32 sb;                // shared-space address of the blob image
+    u32 tag_lane;          // shared-space address of this lane's page tag: sb + 128 + 4 * lane
     u64 oh;                // global address of this env's order slab
-    u64 tr;                // global address of this env's trade slab
-    u64 pg;                // global address of this env's page array (slots >= p_smem live there)
+    u32 env;               // env index inside the handle (cold addresses are rebuilt from it)
     u32 lane;
 };
 
@@ -164,21 +167,31 @@ __device__ __forceinline__ u32 tag_addr(const Book& b, u32 i) { return b.sb + 12
 template <class G> __device__ __forceinline__ u32 vmap_addr(const G& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (ptot(g) + i); }
 template <class G> __device__ __forceinline__ u32 qmap_addr(const G& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (2u * ptot(g) + i); }
 
+// A page is addressed in shared memory when its slot is resident, else in the env's HBM page array.
+// `a` is the byte offset of the page from the start of the page array in either space.
 struct PageRef {
-    u64 g;
-    u32 s;
+    u32 a;       // 128 + 12 * p_total + slot * 512
+    u32 env;
+    u32 sb;
+    u64 blobs_base, blob_stride;
     bool smem;
 };
 template <class G> __device__ __forceinline__ PageRef page_ref(const G& g, const Book& b, u32 slot) {
     PageRef r;
     r.smem = slot < g.p_smem;
-    r.s = b.sb + 128u + 12u * ptot(g) + slot * 512u;
-    r.g = b.pg + (u64)slot * 512u;
+    r.a = 128u + 12u * ptot(g) + slot * 512u;
+    r.env = b.env;
+    r.sb = b.sb;
+    r.blobs_base = g.blobs_base;
+    r.blob_stride = g.blob_stride;
     return r;
 }
-__device__ __forceinline__ u32 pld(const PageRef& r, u32 off) { return r.smem ? lds(r.s + off) : ldg32(r.g + off); }
+__device__ __forceinline__ u64 page_gaddr(const PageRef& r) { return r.blobs_base + (u64)r.env * r.blob_stride + r.a; }
+__device__ __forceinline__ u32 pld(const PageRef& r, u32 off) {
+    return r.smem ? lds(r.sb + r.a + off) : ldg32(page_gaddr(r) + off);
+}
 __device__ __forceinline__ void pst(const PageRef& r, u32 off, u32 v) {
-    if (r.smem) sts(r.s + off, v); else stg32(r.g + off, v);
+    if (r.smem) sts(r.sb + r.a + off, v); else stg32(page_gaddr(r) + off, v);
 }
 
 __device__ __forceinline__ bool has_best(const Book& b, u32 side) { return (b.flags >> (1u + side)) & 1u; }
@@ -206,7 +219,7 @@ template <class G> __device__ __forceinline__ bool to_level(const G& g, u32 pric
 template <class G> __device__ __forceinline__ u32 find_page(const G& g, const Book& b, u32 side, u32 pkey) {
     const u32 want = (pkey << 1) | side;
     for (u32 base = 0; base < ptot(g); base += 32) {
-        const u32 m = __ballot_sync(BB_FULL, lds(tag_addr(b, base + b.lane)) == want);
+        const u32 m = __ballot_sync(BB_FULL, lds(b.tag_lane + 4u * base) == want);
         if (m) return base + __ffs(m) - 1;
     }
     return BB_NIL;
@@ -214,7 +227,7 @@ template <class G> __device__ __forceinline__ u32 find_page(const G& g, const Bo
 
 template <class G> __device__ __forceinline__ u32 alloc_page(const G& g, Book& b, u32 side, u32 pkey) {
     for (u32 base = 0; base < ptot(g); base += 32) {
-        const u32 m = __ballot_sync(BB_FULL, lds(tag_addr(b, base + b.lane)) == BB_TAG_FREE);
+        const u32 m = __ballot_sync(BB_FULL, lds(b.tag_lane + 4u * base) == BB_TAG_FREE);
         if (m) {
             const u32 slot = base + __ffs(m) - 1;
             sts(tag_addr(b, slot), (pkey << 1) | side);
@@ -472,7 +485,7 @@ template <class G> __device__ __forceinline__ void log_trade(const G& g, Book& b
                                           u32 passive) {
     const u32 n = b.n_trades;
     if (n < g.max_trades) {
-        const u64 a = b.tr + (u64)n * 32u;
+        const u64 a = g.tr_base + ((u64)b.env * g.max_trades + n) * 32u;
         stg128(a, (u32)t, (u32)(t >> 32), price, vol);
         stg128(a + 16u, active, passive, passive_bid, 0u);
     } else if (g.max_trades) {

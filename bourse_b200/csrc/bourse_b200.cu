@@ -123,6 +123,9 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.geo.tick = h->cfg.tick_size;
     p.geo.max_orders = h->cfg.max_orders;
     p.geo.max_trades = h->cfg.max_trades;
+    p.geo.tr_base = (u64)h->tr;
+    p.geo.blobs_base = (u64)h->blobs;
+    p.geo.blob_stride = h->blob_stride;
     p.max_steps = h->max_steps_padded;
     p.max_queue = h->cfg.max_queue;
     p.obs_words = h->cfg.obs_words;
@@ -541,10 +544,14 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     p.seed_hi = (u32)(seed >> 32);
     for (size_t i = 0; i < h->groups.size(); ++i) p.groups[i] = h->groups[i];
     int grid = 0, rc;
-    const bool fast = h->granule == 1 && h->p_total == 32;
-    if ((rc = fast ? grid_for(h, k_sim<true>, h->lay_sim, h->cfg.n_envs, &grid)
-                   : grid_for(h, k_sim<false>, h->lay_sim, h->cfg.n_envs, &grid)))
-        return rc;
+    const bool fast = h->granule == 1 && h->p_total == 32, mom = h->mom_groups != 0;
+    const size_t sim_smem = (size_t)h->lay_sim.warp_bytes * WPB;
+#define SIM_CASE(F, M)                                                                     \
+    if (fast == F && mom == M) {                                                           \
+        if ((rc = grid_for(h, k_sim<F, M>, h->lay_sim, h->cfg.n_envs, &grid))) return rc;  \
+    }
+    SIM_CASE(true, false) SIM_CASE(true, true) SIM_CASE(false, false) SIM_CASE(false, true)
+#undef SIM_CASE
     const size_t warps = (size_t)grid * WPB;
     if (warps > h->scratch_warps) {
         cudaFree(h->scratch);
@@ -553,8 +560,10 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
         h->scratch_warps = warps;
     }
     p.scratch = h->scratch;
-    if (fast) k_sim<true><<<grid, WPB * 32, (size_t)h->lay_sim.warp_bytes * WPB, h->stream>>>(p);
-    else k_sim<false><<<grid, WPB * 32, (size_t)h->lay_sim.warp_bytes * WPB, h->stream>>>(p);
+    if (fast && !mom) k_sim<true, false><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
+    else if (fast && mom) k_sim<true, true><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
+    else if (!fast && !mom) k_sim<false, false><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
+    else k_sim<false, true><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
     CUDA_TRY(h, cudaGetLastError());
     h->mirror_dirty = true;
     return BB_OK;

@@ -55,15 +55,15 @@ struct KParams {
     bb_agent_group groups[MAX_GROUPS];
 };
 
-__device__ __forceinline__ void make_book(Book& b, const KParams& p, unsigned char* ws, u32 env, u32 lane) {
-    b.sb = smem_u32(ws);
-    b.pg = (u64)(p.blobs + (size_t)env * p.blob_stride + 128 + 12u * p.geo.p_total);
+__device__ __forceinline__ void make_book(Book& b, const KParams& p, u32 sb, u32 env, u32 lane) {
+    b.sb = sb;
+    b.tag_lane = sb + 128u + 4u * lane;
     b.oh = (u64)(p.ord + (size_t)env * p.geo.max_orders);
-    b.tr = (u64)(p.tr + (size_t)env * p.geo.max_trades);
+    b.env = env;
     b.lane = lane;
 }
 
-// u16 accessors for the per-warp permutation arrays in shared memory
+// u16 / 128-bit accessors for the per-warp scratch arrays in shared memory
 __device__ __forceinline__ u32 lds16(u32 a) {
     unsigned short v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
@@ -72,25 +72,33 @@ __device__ __forceinline__ u32 lds16(u32 a) {
 __device__ __forceinline__ void sts16(u32 a, u32 v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
+__device__ __forceinline__ uint4 lds128(u32 a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(u32 a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // bulk-load the shared-memory image of a book (header, page directory, resident pages)
-__device__ __forceinline__ bool blob_load(const KParams& p, unsigned char* ws, u32 env, u64* bar, u32& phase, u32 lane) {
+__device__ __forceinline__ bool blob_load(const KParams& p, u32 sb, u32 env, u32 bar, u32& phase, u32 lane) {
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        mbar_expect_tx(bar, p.blob_smem_bytes);
-        bulk_g2s(ws, p.blobs + (size_t)env * p.blob_stride, p.blob_smem_bytes, bar);
+        mbar_expect_tx_a(bar, p.blob_smem_bytes);
+        bulk_g2s_a(sb, p.blobs + (size_t)env * p.blob_stride, p.blob_smem_bytes, bar);
     }
-    const bool ok = mbar_wait(bar, phase);
+    const bool ok = mbar_wait_a(bar, phase);
     phase ^= 1u;
     return ok;
 }
-__device__ __forceinline__ void blob_store(const KParams& p, unsigned char* ws, u32 env, u32 lane) {
+__device__ __forceinline__ void blob_store(const KParams& p, u32 sb, u32 env, u32 lane) {
     __syncwarp();
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        bulk_s2g(p.blobs + (size_t)env * p.blob_stride, ws, p.blob_smem_bytes);
+        bulk_s2g_a(p.blobs + (size_t)env * p.blob_stride, sb, p.blob_smem_bytes);
         bulk_commit();
         bulk_wait_all<0>();
     }
@@ -114,8 +122,8 @@ template <class G> __device__ __forceinline__ void emit_obs_direct(const G& g, B
 }
 
 // one decoded instruction against the book (process_event, orderbook.rs:782-792)
-template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book& b, u32 op_flags, u32 order_id, u32 price, u32 vol, u32 trader,
-                                            u64 t, bool assign_id) {
+template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book& b, u32 op_flags, u32 order_id, u32 price,
+                                                               u32 vol, u32 trader, u64 t, bool assign_id) {
     const u32 op = op_flags & BB_OP_MASK;
     if (op == BB_OP_NEW) {
         const u32 side = (op_flags & BB_F_BID) ? 1u : 0u;
@@ -141,15 +149,15 @@ template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book&
 template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    unsigned char* ws = smem + (size_t)warp * p.warp_smem_bytes;
-    u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
-    const u32 perm = smem_u32(ws + p.off_perm);                 // u16 [max_queue]
-    uint4* chunk = reinterpret_cast<uint4*>(ws + p.off_instr);  // [2][32][2] uint4 = two 1 KB instruction batches
+    const u32 sb = smem_u32(smem) + warp * p.warp_smem_bytes;
+    const u32 bar = sb + p.off_bar;      // three 8-byte mbarriers
+    const u32 perm = sb + p.off_perm;    // u16 [max_queue]
+    const u32 chunk = sb + p.off_instr;  // two 1 KB instruction batches
     const GeoT<FAST>& g = static_cast<const GeoT<FAST>&>(p.geo);
     if (lane == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_init(&bar[2], 1);
+        mbar_init_a(bar, 1);
+        mbar_init_a(bar + 8u, 1);
+        mbar_init_a(bar + 16u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();
@@ -158,8 +166,8 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
 
     for (u32 env = blockIdx.x * wpb + warp; env < p.n_envs; env += gridDim.x * wpb) {
         Book b;
-        make_book(b, p, ws, env, lane);
-        if (!blob_load(p, ws, env, &bar[0], ph_blob, lane)) {
+        make_book(b, p, sb, env, lane);
+        if (!blob_load(p, sb, env, bar, ph_blob, lane)) {
             if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
             return;
         }
@@ -175,22 +183,22 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_expect_tx(&bar[1 + buf], cnt * 32u);
-                    bulk_g2s(chunk + buf * 64u, ins + i0, cnt * 32u, &bar[1 + buf]);
+                    mbar_expect_tx_a(bar + 8u + 8u * buf, cnt * 32u);
+                    bulk_g2s_a(chunk + buf * 1024u, ins + i0, cnt * 32u, bar + 8u + 8u * buf);
                 }
             };
             if (n) issue(0, 0);
             for (u32 i0 = 0, buf = 0; i0 < n; i0 += 32, buf ^= 1u) {
                 if (i0 + 32 < n) issue(i0 + 32, buf ^ 1u);
                 u32& ph = buf ? ph_c1 : ph_c0;
-                if (!mbar_wait(&bar[1 + buf], ph)) {
+                if (!mbar_wait_a(bar + 8u + 8u * buf, ph)) {
                     if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
                     return;
                 }
                 ph ^= 1u;
                 const u32 cnt = min(32u, n - i0);
                 for (u32 k = 0; k < cnt; ++k) {
-                    const uint4 x = chunk[buf * 64u + 2u * k], y = chunk[buf * 64u + 2u * k + 1u];
+                    const uint4 x = lds128(chunk + buf * 1024u + 32u * k), y = lds128(chunk + buf * 1024u + 32u * k + 16u);
                     const u64 t = ((u64)x.y << 32) | x.x;
                     b.t = t;
                     apply_instr(g, b, x.z, x.w, y.x, y.y, y.z, t, true);
@@ -236,12 +244,12 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
                     const u32 cnt = min(32u, mm - i0);
                     if (lane < cnt) {
                         const uint4* src = reinterpret_cast<const uint4*>(ins + lds16(perm + 2u * (i0 + lane)));
-                        chunk[2u * lane] = src[0];
-                        chunk[2u * lane + 1u] = src[1];
+                        sts128(chunk + 32u * lane, src[0]);
+                        sts128(chunk + 32u * lane + 16u, src[1]);
                     }
                     __syncwarp();
                     for (u32 k = 0; k < cnt; ++k) {
-                        const uint4 x = chunk[2u * k], y = chunk[2u * k + 1u];
+                        const uint4 x = lds128(chunk + 32u * k), y = lds128(chunk + 32u * k + 16u);
                         const u64 t = start + i0 + k;
                         b.t = t;
                         apply_instr(g, b, x.z, x.w, y.x, y.y, y.z, t, false);
@@ -255,7 +263,7 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
         }
         if (b.err && lane == 0) atomicOr(p.err_flag, b.err);
         book_to_header(g, b);
-        blob_store(p, ws, env, lane);
+        blob_store(p, sb, env, lane);
     }
 }
 
@@ -424,19 +432,19 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     return out;
 }
 
-template <bool FAST> __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
+template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    unsigned char* ws = smem + (size_t)warp * p.warp_smem_bytes;
-    u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
-    const u32 perm = smem_u32(ws + p.off_perm);  // u16 [max_queue]
-    const u32 jarr = perm + 2u * p.max_queue;    // u16 [max_queue]
-    const u32 stage = smem_u32(ws + p.off_obs);  // u32 [2][OBS_STAGE_STEPS * obs_words]
+    const u32 sb = smem_u32(smem) + warp * p.warp_smem_bytes;
+    const u32 bar = sb + p.off_bar;
+    const u32 perm = sb + p.off_perm;          // u16 [max_queue]
+    const u32 jarr = perm + 2u * p.max_queue;  // u16 [max_queue]
+    const u32 stage = sb + p.off_obs;          // u32 [2][OBS_STAGE_STEPS * obs_words]
     uint4* q = p.scratch + (size_t)(blockIdx.x * wpb + warp) * p.max_queue;
     const u64 qa = (u64)q;
     const GeoT<FAST>& g = static_cast<const GeoT<FAST>&>(p.geo);
     if (lane == 0) {
-        mbar_init(&bar[0], 1);
+        mbar_init_a(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();
@@ -446,8 +454,8 @@ template <bool FAST> __global__ void __launch_bounds__(128, 7) k_sim(const __gri
 
     for (u32 env = blockIdx.x * wpb + warp; env < p.n_envs; env += gridDim.x * wpb) {
         Book b;
-        make_book(b, p, ws, env, lane);
-        if (!blob_load(p, ws, env, &bar[0], ph_blob, lane)) {
+        make_book(b, p, sb, env, lane);
+        if (!blob_load(p, sb, env, bar, ph_blob, lane)) {
             if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
             return;
         }
@@ -468,7 +476,7 @@ template <bool FAST> __global__ void __launch_bounds__(128, 7) k_sim(const __gri
             u32 slot_base = 0, mi = 0;
             for (u32 gi = 0; gi < p.n_groups; ++gi) {
                 const bb_agent_group& ag = p.groups[gi];
-                if (ag.kind == BB_GROUP_RANDOM) {
+                if (!MOM || ag.kind == BB_GROUP_RANDOM) {
                     random_agents_update(p, ag, b, q, e, slots, env_g, step, slot_base);
                 } else {
                     const MomOut mo = momentum_agent_update(p, ag, b.oh, lane, best_price(g, b, 1), best_price(g, b, 0), q, e.n,
@@ -538,8 +546,7 @@ template <bool FAST> __global__ void __launch_bounds__(128, 7) k_sim(const __gri
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        bulk_s2g(hist_env + (size_t)sbase * p.obs_words,
-                                 ws + p.off_obs + 4u * (sbuf * stage_words), stage_words * 4u);
+                        bulk_s2g_a(hist_env + (size_t)sbase * p.obs_words, stage + 4u * (sbuf * stage_words), stage_words * 4u);
                         bulk_commit();
                         bulk_wait_read<1>();  // the other buffer's previous flush has released its source
                     }
@@ -565,7 +572,7 @@ template <bool FAST> __global__ void __launch_bounds__(128, 7) k_sim(const __gri
         if (lane == 0) bulk_wait_all<0>();
         if (b.err && lane == 0) atomicOr(p.err_flag, b.err);
         book_to_header(g, b);
-        blob_store(p, ws, env, lane);
+        blob_store(p, sb, env, lane);
     }
 }
 
@@ -576,11 +583,11 @@ __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParam
                                                   u32 n_out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    unsigned char* ws = smem + (size_t)warp * p.warp_smem_bytes;
-    u64* bar = reinterpret_cast<u64*>(ws + p.off_bar);
+    const u32 sb = smem_u32(smem) + warp * p.warp_smem_bytes;
+    const u32 bar = sb + p.off_bar;
     const GeoT<false>& g = static_cast<const GeoT<false>&>(p.geo);
     if (lane == 0) {
-        mbar_init(&bar[0], 1);
+        mbar_init_a(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();
@@ -589,8 +596,8 @@ __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParam
     for (u32 i = blockIdx.x * wpb + warp; i < n_out; i += gridDim.x * wpb) {
         const u32 env = first_env + i;
         Book b;
-        make_book(b, p, ws, env, lane);
-        if (!blob_load(p, ws, env, &bar[0], ph, lane)) return;
+        make_book(b, p, sb, env, lane);
+        if (!blob_load(p, sb, env, bar, ph, lane)) return;
         book_from_header(b);
         u32 w0, w1;
         book_obs(g, b, 45u, &w0, &w1);

@@ -123,11 +123,13 @@ __device__ __forceinline__ void stg128(u64 a, u32 x, u32 y, u32 z, u32 w) {
 #define OC_ARR 32u
 #define OC_END 40u
 #define OC_TRADER 48u
-// byte offsets inside a 512-byte page
-#define PG_VOL 0u
-#define PG_CNT 128u
-#define PG_HEAD 256u
-#define PG_TAIL 384u
+// byte offsets inside a 512-byte page: level l has (vol, cnt) at PG_VC + 8l and (head, tail) at PG_HT + 8l
+#define PG_VC 0u
+#define PG_HT 256u
+#define PG_VOL(l) (8u * (l))
+#define PG_CNT(l) (8u * (l) + 4u)
+#define PG_HEAD(l) (256u + 8u * (l))
+#define PG_TAIL(l) (260u + 8u * (l))
 
 #define FL_TRADING 1u
 #define FL_HAS_ASK 2u  // FL_HAS_ASK << side
@@ -167,31 +169,41 @@ __device__ __forceinline__ u32 tag_addr(const Book& b, u32 i) { return b.sb + 12
 template <class G> __device__ __forceinline__ u32 vmap_addr(const G& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (ptot(g) + i); }
 template <class G> __device__ __forceinline__ u32 qmap_addr(const G& g, const Book& b, u32 i) { return b.sb + 128u + 4u * (2u * ptot(g) + i); }
 
-// A page is addressed in shared memory when its slot is resident, else in the env's HBM page array.
-// `a` is the byte offset of the page from the start of the page array in either space.
-struct PageRef {
-    u32 a;       // 128 + 12 * p_total + slot * 512
-    u32 env;
-    u32 sb;
-    u64 blobs_base, blob_stride;
-    bool smem;
+// A page lives in shared memory when its slot is resident (slot < p_smem), else in the env's HBM page
+// array.  The two cases are distinct TYPES so that every accessor compiles to exactly one ld/st; the
+// choice is made once per operation by the callers (see the `*_at` implementation templates).
+// Page layout: 32 x (vol, cnt) pairs, then 32 x (head, tail) pairs.
+struct PageS {
+    u32 a;  // shared-space byte address of the page
 };
-template <class G> __device__ __forceinline__ PageRef page_ref(const G& g, const Book& b, u32 slot) {
-    PageRef r;
-    r.smem = slot < g.p_smem;
-    r.a = 128u + 12u * ptot(g) + slot * 512u;
-    r.env = b.env;
-    r.sb = b.sb;
-    r.blobs_base = g.blobs_base;
-    r.blob_stride = g.blob_stride;
-    return r;
+struct PageG {
+    u64 a;  // global address of the page
+};
+__device__ __forceinline__ u32 pld(PageS p, u32 off) { return lds(p.a + off); }
+__device__ __forceinline__ u32 pld(PageG p, u32 off) { return ldg32(p.a + off); }
+__device__ __forceinline__ void pst(PageS p, u32 off, u32 v) { sts(p.a + off, v); }
+__device__ __forceinline__ void pst(PageG p, u32 off, u32 v) { stg32(p.a + off, v); }
+__device__ __forceinline__ uint2 pld2(PageS p, u32 off) {
+    const u64 v = lds64(p.a + off);
+    return make_uint2((u32)v, (u32)(v >> 32));
 }
-__device__ __forceinline__ u64 page_gaddr(const PageRef& r) { return r.blobs_base + (u64)r.env * r.blob_stride + r.a; }
-__device__ __forceinline__ u32 pld(const PageRef& r, u32 off) {
-    return r.smem ? lds(r.sb + r.a + off) : ldg32(page_gaddr(r) + off);
+__device__ __forceinline__ uint2 pld2(PageG p, u32 off) {
+    const u64 v = ldg64(p.a + off);
+    return make_uint2((u32)v, (u32)(v >> 32));
 }
-__device__ __forceinline__ void pst(const PageRef& r, u32 off, u32 v) {
-    if (r.smem) sts(r.sb + r.a + off, v); else stg32(page_gaddr(r) + off, v);
+__device__ __forceinline__ void pst2(PageS p, u32 off, u32 x, u32 y) { sts64(p.a + off, ((u64)y << 32) | x); }
+__device__ __forceinline__ void pst2(PageG p, u32 off, u32 x, u32 y) { stg64(p.a + off, ((u64)y << 32) | x); }
+
+template <class G> __device__ __forceinline__ u32 page_off(const G& g, u32 slot) { return 128u + 12u * ptot(g) + slot * 512u; }
+template <class G> __device__ __forceinline__ PageS page_s(const G& g, const Book& b, u32 slot) {
+    return PageS{b.sb + page_off(g, slot)};
+}
+template <class G> __device__ __forceinline__ PageG page_g(const G& g, const Book& b, u32 slot) {
+    return PageG{g.blobs_base + (u64)b.env * g.blob_stride + page_off(g, slot)};
+}
+// (vol, cnt) of a level of any page; for the cold observation paths where the slot may differ per lane
+template <class G> __device__ __forceinline__ uint2 level_pair_any(const G& g, const Book& b, u32 slot, u32 l) {
+    return slot < g.p_smem ? pld2(page_s(g, b, slot), PG_VC + 8u * l) : pld2(page_g(g, b, slot), PG_VC + 8u * l);
 }
 
 __device__ __forceinline__ bool has_best(const Book& b, u32 side) { return (b.flags >> (1u + side)) & 1u; }
@@ -296,9 +308,9 @@ template <class G> __device__ __forceinline__ void level_at(const G& g, const Bo
     const u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) return;
     if (!((lds(vmap_addr(g, b, slot)) >> (q & 31u)) & 1u)) return;
-    const PageRef pr = page_ref(g, b, slot);
-    *vol = pld(pr, PG_VOL + 4u * (q & 31u));
-    *cnt = pld(pr, PG_CNT + 4u * (q & 31u));
+    const uint2 vc = level_pair_any(g, b, slot, q & 31u);
+    *vol = vc.x;
+    *cnt = vc.y;
 }
 
 // same lookup done independently by each lane (divergent prices) — used by the level-2 emitter
@@ -313,9 +325,9 @@ template <class G> __device__ __forceinline__ void level_at_lane(const G& g, con
         if (lds(tag_addr(b, j)) == want) slot = j;
     if (slot == BB_NIL) return;
     if (!((lds(vmap_addr(g, b, slot)) >> (q & 31u)) & 1u)) return;
-    const PageRef pr = page_ref(g, b, slot);
-    *vol = pld(pr, PG_VOL + 4u * (q & 31u));
-    *cnt = pld(pr, PG_CNT + 4u * (q & 31u));
+    const uint2 vc = level_pair_any(g, b, slot, q & 31u);
+    *vol = vc.x;
+    *cnt = vc.y;
 }
 
 // first level of the reference's `volumes` map (side.rs:107-120)
@@ -325,32 +337,31 @@ template <class G> __device__ __forceinline__ void best_by_volumes(const G& g, c
     u32 q;
     if (!scan_best(g, b, side, false, &q)) return;
     const u32 slot = find_page(g, b, side, q >> 5);
-    const PageRef pr = page_ref(g, b, slot);
-    *vol = pld(pr, PG_VOL + 4u * (q & 31u));
-    *cnt = pld(pr, PG_CNT + 4u * (q & 31u));
+    const uint2 vc = level_pair_any(g, b, slot, q & 31u);
+    *vol = vc.x;
+    *cnt = vc.y;
 }
 
 // ---- volumes-map half of insert_order / remove_order / remove_vol (side.rs:54-96) ------------------
-template <class G> __device__ __forceinline__ void level_add(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
+template <class G, class P> __device__ __forceinline__ void level_add(const G& g, Book& b, u32 side, u32 slot, P pr, u32 l, u32 vol) {
     const u32 bit = 1u << l;
     const u32 vm = lds(vmap_addr(g, b, slot));
     if (vm & bit) {
-        pst(pr, PG_VOL + 4u * l, pld(pr, PG_VOL + 4u * l) + vol);
-        pst(pr, PG_CNT + 4u * l, pld(pr, PG_CNT + 4u * l) + 1u);
+        const uint2 vc = pld2(pr, PG_VC + 8u * l);
+        pst2(pr, PG_VC + 8u * l, vc.x + vol, vc.y + 1u);
     } else {
-        pst(pr, PG_VOL + 4u * l, vol);
-        pst(pr, PG_CNT + 4u * l, 1u);
+        pst2(pr, PG_VC + 8u * l, vol, 1u);
         sts(vmap_addr(g, b, slot), vm | bit);
     }
     add_side_vol(b, side, vol);
 }
 
 // returns true when the page was released
-template <class G> __device__ __forceinline__ bool level_remove(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 vol) {
+template <class G, class P> __device__ __forceinline__ bool level_remove(const G& g, Book& b, u32 side, u32 slot, P pr, u32 l, u32 vol) {
     const u32 bit = 1u << l;
-    pst(pr, PG_VOL + 4u * l, pld(pr, PG_VOL + 4u * l) - vol);
-    const u32 cnt = pld(pr, PG_CNT + 4u * l) - 1u;
-    pst(pr, PG_CNT + 4u * l, cnt);
+    const uint2 vc = pld2(pr, PG_VC + 8u * l);
+    const u32 cnt = vc.y - 1u;
+    pst2(pr, PG_VC + 8u * l, vc.x - vol, cnt);
     add_side_vol(b, side, 0u - vol);
     if (cnt == 0) {
         const u32 vm = lds(vmap_addr(g, b, slot)) & ~bit;
@@ -366,10 +377,10 @@ template <class G> __device__ __forceinline__ bool level_remove(const G& g, Book
 
 // ---- orders-map half: the price-time queue ----------------------------------------------------------
 // unlink a record with links (prev,next) from level (slot,l); maintains qmap and the cached touch
-template <class G> __device__ __forceinline__ void queue_unlink(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l, u32 q,
-                                             u32 prev, u32 next) {
-    if (prev == BB_NIL) pst(pr, PG_HEAD + 4u * l, next); else stg32(b.oh + (u64)prev * ORD_STRIDE + OH_NEXT, next);
-    if (next == BB_NIL) pst(pr, PG_TAIL + 4u * l, prev); else stg32(b.oh + (u64)next * ORD_STRIDE + OH_PREV, prev);
+template <class G, class P> __device__ __forceinline__ void queue_unlink(const G& g, Book& b, u32 side, u32 slot, P pr, u32 l, u32 q,
+                                                                        u32 prev, u32 next) {
+    if (prev == BB_NIL) pst(pr, PG_HEAD(l), next); else stg32(b.oh + (u64)prev * ORD_STRIDE + OH_NEXT, next);
+    if (next == BB_NIL) pst(pr, PG_TAIL(l), prev); else stg32(b.oh + (u64)next * ORD_STRIDE + OH_PREV, prev);
     if (prev == BB_NIL && next == BB_NIL) {
         const u32 qm = lds(qmap_addr(g, b, slot)) & ~(1u << l);
         sts(qmap_addr(g, b, slot), qm);
@@ -380,10 +391,10 @@ template <class G> __device__ __forceinline__ void queue_unlink(const G& g, Book
 
 // orders.remove(&(price', key_time)) for an order that does NOT own its key any more (N1 ghost):
 // whoever owns that key now loses it and becomes a ghost itself.
-template <class G> __device__ __forceinline__ void queue_remove_key_slow(const G& g, Book& b, u32 side, u32 slot, const PageRef& pr, u32 l,
-                                                      u32 q, u64 key_time) {
+template <class G, class P> __device__ __forceinline__ void queue_remove_key_slow(const G& g, Book& b, u32 side, u32 slot, P pr,
+                                                                                 u32 l, u32 q, u64 key_time) {
     if (!((lds(qmap_addr(g, b, slot)) >> l) & 1u)) return;
-    u32 cur = pld(pr, PG_HEAD + 4u * l);
+    u32 cur = pld(pr, PG_HEAD(l));
     while (cur != BB_NIL) {
         const u64 ra = b.oh + (u64)cur * ORD_STRIDE;
         const uint4 a = ldg128(ra);
@@ -400,10 +411,10 @@ template <class G> __device__ __forceinline__ void queue_remove_key_slow(const G
 
 // orders.insert((price', t), id) when time did not move strictly forward: sorted position, or take
 // over an existing equal key.  Returns the (prev,next) links the new record must carry.
-__device__ __forceinline__ void queue_insert_slow(const Book& b, const PageRef& pr, u32 l, u32 id, u64 t, u32* out_prev,
-                                                  u32* out_next) {
-    u32 cur = pld(pr, PG_TAIL + 4u * l);  // walk back from the tail
-    u32 after = BB_NIL;                   // node that will follow the new one
+template <class P> __device__ __forceinline__ void queue_insert_slow(const Book& b, P pr, u32 l, u32 id, u64 t, u32* out_prev,
+                                                                     u32* out_next) {
+    u32 cur = pld(pr, PG_TAIL(l));  // walk back from the tail
+    u32 after = BB_NIL;             // node that will follow the new one
     while (cur != BB_NIL) {
         const u64 ra = b.oh + (u64)cur * ORD_STRIDE;
         const uint4 a = ldg128(ra);
@@ -412,8 +423,8 @@ __device__ __forceinline__ void queue_insert_slow(const Book& b, const PageRef& 
         if (kt == t) {
             // BTreeMap::insert on an existing key: value replaced, position kept (side.rs:55)
             stg32(ra + OH_META, ldg32(ra + OH_META) | META_GHOST);
-            if (a.w == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)a.w * ORD_STRIDE + OH_NEXT, id);
-            if (a.z == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)a.z * ORD_STRIDE + OH_PREV, id);
+            if (a.w == BB_NIL) pst(pr, PG_HEAD(l), id); else stg32(b.oh + (u64)a.w * ORD_STRIDE + OH_NEXT, id);
+            if (a.z == BB_NIL) pst(pr, PG_TAIL(l), id); else stg32(b.oh + (u64)a.z * ORD_STRIDE + OH_PREV, id);
             *out_prev = a.w;
             *out_next = a.z;
             return;
@@ -422,15 +433,36 @@ __device__ __forceinline__ void queue_insert_slow(const Book& b, const PageRef& 
         cur = a.w;
     }
     // insert between cur (may be NIL => new head) and after (may be NIL => new tail)
-    if (cur == BB_NIL) pst(pr, PG_HEAD + 4u * l, id); else stg32(b.oh + (u64)cur * ORD_STRIDE + OH_NEXT, id);
-    if (after == BB_NIL) pst(pr, PG_TAIL + 4u * l, id); else stg32(b.oh + (u64)after * ORD_STRIDE + OH_PREV, id);
+    if (cur == BB_NIL) pst(pr, PG_HEAD(l), id); else stg32(b.oh + (u64)cur * ORD_STRIDE + OH_NEXT, id);
+    if (after == BB_NIL) pst(pr, PG_TAIL(l), id); else stg32(b.oh + (u64)after * ORD_STRIDE + OH_PREV, id);
     *out_prev = cur;
     *out_next = after;
 }
 
+template <class G, class P> __device__ __forceinline__ void book_insert_at(const G& g, Book& b, u32 side, u32 q, u32 slot, P pr, u64 t,
+                                                                          u32 id, u32 vol, u32* out_prev, u32* out_next) {
+    const u32 l = q & 31u;
+    level_add(g, b, side, slot, pr, l, vol);
+    const u32 bit = 1u << l;
+    const u32 qm = lds(qmap_addr(g, b, slot));
+    if (!(qm & bit)) {
+        pst2(pr, PG_HT + 8u * l, id, id);
+        sts(qmap_addr(g, b, slot), qm | bit);
+        const bool better = !has_best(b, side) || (side ? q > b.bq_bid : q < b.bq_ask);
+        if (better) set_best(b, side, q);
+    } else if (t > b.max_key_time) {
+        const u32 tail = pld(pr, PG_TAIL(l));
+        stg32(b.oh + (u64)tail * ORD_STRIDE + OH_NEXT, id);
+        pst(pr, PG_TAIL(l), id);
+        *out_prev = tail;
+    } else {
+        queue_insert_slow(b, pr, l, id, t, out_prev, out_next);
+    }
+}
+
 // side.rs:54-66 insert_order for a resting order.  Returns false when the order could not rest.
-template <class G> __device__ __forceinline__ bool book_insert(const G& g, Book& b, u32 side, u32 price, u64 t, u32 id, u32 vol, u32* out_prev,
-                                            u32* out_next) {
+template <class G> __device__ __forceinline__ bool book_insert(const G& g, Book& b, u32 side, u32 price, u64 t, u32 id, u32 vol,
+                                                               u32* out_prev, u32* out_next) {
     *out_prev = BB_NIL;
     *out_next = BB_NIL;
     u32 q;
@@ -443,46 +475,50 @@ template <class G> __device__ __forceinline__ bool book_insert(const G& g, Book&
         slot = alloc_page(g, b, side, q >> 5);
         if (slot == BB_NIL) return false;
     }
-    const u32 l = q & 31u;
-    const PageRef pr = page_ref(g, b, slot);
-    level_add(g, b, side, slot, pr, l, vol);
-    const u32 bit = 1u << l;
-    const u32 qm = lds(qmap_addr(g, b, slot));
-    if (!(qm & bit)) {
-        pst(pr, PG_HEAD + 4u * l, id);
-        pst(pr, PG_TAIL + 4u * l, id);
-        sts(qmap_addr(g, b, slot), qm | bit);
-        const bool better = !has_best(b, side) || (side ? q > b.bq_bid : q < b.bq_ask);
-        if (better) set_best(b, side, q);
-    } else if (t > b.max_key_time) {
-        const u32 tail = pld(pr, PG_TAIL + 4u * l);
-        stg32(b.oh + (u64)tail * ORD_STRIDE + OH_NEXT, id);
-        pst(pr, PG_TAIL + 4u * l, id);
-        *out_prev = tail;
-    } else {
-        queue_insert_slow(b, pr, l, id, t, out_prev, out_next);
-    }
+    if (slot < g.p_smem) book_insert_at(g, b, side, q, slot, page_s(g, b, slot), t, id, vol, out_prev, out_next);
+    else book_insert_at(g, b, side, q, slot, page_g(g, b, slot), t, id, vol, out_prev, out_next);
     if (t > b.max_key_time) b.max_key_time = t;
     __syncwarp();
     return true;
 }
 
-// side.rs:75-84 remove_order(key, vol) for an order with the given record fields
-template <class G> __device__ __forceinline__ void book_remove(const G& g, Book& b, u32 side, u32 price, u32 prev, u32 next, u64 key_time,
-                                            bool ghost, u32 vol) {
-    u32 q;
-    to_level(g, price, &q);
-    const u32 slot = find_page(g, b, side, q >> 5);
-    if (slot == BB_NIL) return;  // unreachable for Active orders
+template <class G, class P> __device__ __forceinline__ void book_remove_at(const G& g, Book& b, u32 side, u32 q, u32 slot, P pr, u32 prev,
+                                                                          u32 next, u64 key_time, bool ghost, u32 vol) {
     const u32 l = q & 31u;
-    const PageRef pr = page_ref(g, b, slot);
     if (ghost) queue_remove_key_slow(g, b, side, slot, pr, l, q, key_time);
     else queue_unlink(g, b, side, slot, pr, l, q, prev, next);
     level_remove(g, b, side, slot, pr, l, vol);
 }
 
+// side.rs:75-84 remove_order(key, vol) for an order with the given record fields
+template <class G> __device__ __forceinline__ void book_remove(const G& g, Book& b, u32 side, u32 price, u32 prev, u32 next,
+                                                               u64 key_time, bool ghost, u32 vol) {
+    u32 q;
+    to_level(g, price, &q);
+    const u32 slot = find_page(g, b, side, q >> 5);
+    if (slot == BB_NIL) return;  // unreachable for Active orders
+    if (slot < g.p_smem) book_remove_at(g, b, side, q, slot, page_s(g, b, slot), prev, next, key_time, ghost, vol);
+    else book_remove_at(g, b, side, q, slot, page_g(g, b, slot), prev, next, key_time, ghost, vol);
+}
+
+// remove_vol(price, dv) (side.rs:93-96) for the in-place volume reduction of modify_order
+template <class G> __device__ __forceinline__ void book_reduce(const G& g, Book& b, u32 side, u32 price, u32 dv) {
+    u32 q;
+    to_level(g, price, &q);
+    const u32 slot = find_page(g, b, side, q >> 5);
+    if (slot == BB_NIL) return;
+    if (slot < g.p_smem) {
+        const PageS pr = page_s(g, b, slot);
+        pst(pr, PG_VOL(q & 31u), pld(pr, PG_VOL(q & 31u)) - dv);
+    } else {
+        const PageG pr = page_g(g, b, slot);
+        pst(pr, PG_VOL(q & 31u), pld(pr, PG_VOL(q & 31u)) - dv);
+    }
+    add_side_vol(b, side, 0u - dv);
+}
+
 template <class G> __device__ __forceinline__ void log_trade(const G& g, Book& b, u64 t, u32 passive_bid, u32 price, u32 vol, u32 active,
-                                          u32 passive) {
+                                                             u32 passive) {
     const u32 n = b.n_trades;
     if (n < g.max_trades) {
         const u64 a = g.tr_base + ((u64)b.env * g.max_trades + n) * 32u;
@@ -494,13 +530,64 @@ template <class G> __device__ __forceinline__ void log_trade(const G& g, Book& b
     b.n_trades = n + 1;
 }
 
-// orderbook.rs:429-487 match_bid / match_ask + :843-870 match_orders.  Sweeps the opposite side in
-// price-time order; returns the aggressor's remaining volume, *filled as the reference's Status::Filled.
-template <class G> __device__ __forceinline__ u32 book_match(const G& g, Book& b, u32 side, u32 price, u32 vol, u32 id, u64 t, bool* filled) {
+// One fill of the aggressor against the head of the touch level (slot, l) of side `o`
+// (match_orders, orderbook.rs:843-870, plus the side bookkeeping of :443-447).  Returns false when the
+// book turned out to be inconsistent.  *released is set when the page was freed.
+template <class G, class P> __device__ __forceinline__ bool fill_one(const G& g, Book& b, u32 o, u32 bq, u32 slot, P pr, u32 id, u64 t,
+                                                                    u32* vol, bool* filled, bool* released) {
+    const u32 l = bq & 31u;
+    const u32 hid = pld(pr, PG_HEAD(l));
+    if (hid >= g.max_orders) {
+        b.err |= ERR_BAD_ID;
+        return false;
+    }
+    const u64 ha = b.oh + (u64)hid * ORD_STRIDE;
+    const uint4 ph = ldg128(ha);  // price, vol, next, prev
+    const u32 tv = min(*vol, ph.y);
+    *vol -= tv;
+    const u32 pvol = ph.y - tv;
+    log_trade(g, b, t, o, ph.x, tv, id, hid);
+    b.trade_vol += tv;
+    b.d_volume += tv;
+    b.d_trans += 1;
+    if (pvol == 0) {
+        stg32(ha + OH_VOL, 0u);
+        stg32(ha + OH_META, ST_FILLED | (o ? META_BID : 0u));
+        stg64(ha + OC_END, t);
+        // side.remove_order(match.key, tv): the head always owns its key
+        const u32 nxt = ph.z;
+        bool emptied = false;
+        u32 qm = 0;
+        if (nxt == BB_NIL) {
+            pst2(pr, PG_HT + 8u * l, BB_NIL, BB_NIL);
+            qm = lds(qmap_addr(g, b, slot)) & ~(1u << l);
+            sts(qmap_addr(g, b, slot), qm);
+            emptied = true;
+        } else {
+            pst(pr, PG_HEAD(l), nxt);
+            stg32(b.oh + (u64)nxt * ORD_STRIDE + OH_PREV, BB_NIL);
+        }
+        *released = level_remove(g, b, o, slot, pr, l, tv);
+        if (emptied) {
+            __syncwarp();
+            next_best_after(g, b, o, bq >> 5, qm);
+        }
+    } else {
+        stg32(ha + OH_VOL, pvol);
+        pst(pr, PG_VOL(l), pld(pr, PG_VOL(l)) - tv);  // side.remove_vol(price, tv)
+        add_side_vol(b, o, 0u - tv);
+    }
+    if (*vol == 0) *filled = true;
+    return true;
+}
+
+// orderbook.rs:429-487 match_bid / match_ask.  Sweeps the opposite side in price-time order; returns the
+// aggressor's remaining volume, *filled as the reference's Status::Filled.
+template <class G> __device__ __forceinline__ u32 book_match(const G& g, Book& b, u32 side, u32 price, u32 vol, u32 id, u64 t,
+                                                             bool* filled) {
     const u32 o = side ^ 1u;
     *filled = false;
     u32 slot = BB_NIL, slot_key = BB_NIL;
-    PageRef pr = page_ref(g, b, 0);
     while (vol > 0 && has_best(b, o)) {
         const u32 bq = best_q(b, o);
         const u32 bprice = bq * gran(g);
@@ -512,51 +599,12 @@ template <class G> __device__ __forceinline__ u32 book_match(const G& g, Book& b
                 b.err |= ERR_CAP_PAGES;
                 break;
             }
-            pr = page_ref(g, b, slot);
         }
-        const u32 l = bq & 31u;
-        const u32 hid = pld(pr, PG_HEAD + 4u * l);
-        if (hid >= g.max_orders) {
-            b.err |= ERR_BAD_ID;
-            break;
-        }
-        const u64 ha = b.oh + (u64)hid * ORD_STRIDE;
-        const uint4 ph = ldg128(ha);  // price, vol, next, prev
-        const u32 tv = min(vol, ph.y);
-        vol -= tv;
-        const u32 pvol = ph.y - tv;
-        log_trade(g, b, t, o, ph.x, tv, id, hid);
-        b.trade_vol += tv;
-        b.d_volume += tv;
-        b.d_trans += 1;
-        if (pvol == 0) {
-            stg32(ha + OH_VOL, 0u);
-            stg32(ha + OH_META, ST_FILLED | (o ? META_BID : 0u));
-            stg64(b.oh + (u64)hid * ORD_STRIDE + OC_END, t);
-            // side.remove_order(match.key, tv): the head always owns its key
-            const u32 nxt = ph.z;
-            pst(pr, PG_HEAD + 4u * l, nxt);
-            bool emptied = false;
-            u32 qm = 0;
-            if (nxt == BB_NIL) {
-                pst(pr, PG_TAIL + 4u * l, BB_NIL);
-                qm = lds(qmap_addr(g, b, slot)) & ~(1u << l);
-                sts(qmap_addr(g, b, slot), qm);
-                emptied = true;
-            } else {
-                stg32(b.oh + (u64)nxt * ORD_STRIDE + OH_PREV, BB_NIL);
-            }
-            if (level_remove(g, b, o, slot, pr, l, tv)) slot_key = BB_NIL;
-            if (emptied) {
-                __syncwarp();
-                next_best_after(g, b, o, bq >> 5, qm);
-            }
-        } else {
-            stg32(ha + OH_VOL, pvol);
-            pst(pr, PG_VOL + 4u * l, pld(pr, PG_VOL + 4u * l) - tv);  // side.remove_vol(price, tv)
-            add_side_vol(b, o, 0u - tv);
-        }
-        if (vol == 0) *filled = true;
+        bool released = false, ok;
+        if (slot < g.p_smem) ok = fill_one(g, b, o, bq, slot, page_s(g, b, slot), id, t, &vol, filled, &released);
+        else ok = fill_one(g, b, o, bq, slot, page_g(g, b, slot), id, t, &vol, filled, &released);
+        if (!ok) break;
+        if (released) slot_key = BB_NIL;
     }
     return vol;
 }
@@ -615,7 +663,7 @@ template <class G> __device__ __forceinline__ void book_cancel(const G& g, Book&
     if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
     const u32 side = (c.z & META_BID) ? 1u : 0u;
     stg32(ra + OH_META, ST_CANCELLED | (c.z & META_BID));
-    stg64(b.oh + (u64)id * ORD_STRIDE + OC_END, t);
+    stg64(ra + OC_END, t);
     book_remove(g, b, side, a.x, a.w, a.z, ((u64)c.y << 32) | c.x, (c.z & META_GHOST) != 0, a.y);
     b.d_trans += 1;
 }
@@ -633,16 +681,8 @@ template <class G> __device__ __forceinline__ void book_modify(const G& g, Book&
     if (!has_p && !has_v) return;
     const u32 side = (c.z & META_BID) ? 1u : 0u;
     if (!has_p && new_v < a.y) {
-        const u32 d = a.y - new_v;
         stg32(ra + OH_VOL, new_v);
-        u32 q;
-        to_level(g, a.x, &q);
-        const u32 slot = find_page(g, b, side, q >> 5);
-        if (slot != BB_NIL) {
-            const PageRef pr = page_ref(g, b, slot);
-            pst(pr, PG_VOL + 4u * (q & 31u), pld(pr, PG_VOL + 4u * (q & 31u)) - d);
-            add_side_vol(b, side, 0u - d);
-        }
+        book_reduce(g, b, side, a.x, a.y - new_v);
         b.d_trans += 1;
         return;
     }
@@ -655,7 +695,7 @@ template <class G> __device__ __forceinline__ void book_modify(const G& g, Book&
     if (b.flags & FL_TRADING) rem = book_match(g, b, side, price, vol, id, t, &filled);
     if (filled) {
         write_order(b, id, price, rem, BB_NIL, BB_NIL, old_kt, ST_FILLED | (c.z & META_BID), c.w);
-        stg64(b.oh + (u64)id * ORD_STRIDE + OC_END, t);
+        stg64(ra + OC_END, t);
     } else {
         book_insert(g, b, side, price, t, id, rem, &prev, &next);
         write_order(b, id, price, rem, next, prev, t, ST_ACTIVE | (c.z & META_BID), c.w);

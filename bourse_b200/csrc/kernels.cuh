@@ -55,10 +55,24 @@ struct KParams {
     bb_agent_group groups[MAX_GROUPS];
 };
 
+// Values the optimiser would otherwise rematerialise at every use (S2R for the lane id, cvta + multiply
+// for the shared base, a 64-bit multiply-add for the order slab) are passed through an opaque move so they
+// stay in registers: profiles/r01_v4 showed ~35 warp instructions per event spent recomputing them.
+__device__ __forceinline__ u32 keep32(u32 v) {
+    u32 r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ u64 keep64(u64 v) {
+    u64 r;
+    asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(v));
+    return r;
+}
+
 __device__ __forceinline__ void make_book(Book& b, const KParams& p, u32 sb, u32 env, u32 lane) {
     b.sb = sb;
-    b.tag_lane = sb + 128u + 4u * lane;
-    b.oh = (u64)(p.ord + (size_t)env * p.geo.max_orders);
+    b.tag_lane = keep32(sb + 128u + 4u * lane);
+    b.oh = keep64((u64)(p.ord + (size_t)env * p.geo.max_orders));
     b.env = env;
     b.lane = lane;
 }
@@ -148,8 +162,8 @@ template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book&
 
 template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const u32 sb = smem_u32(smem) + warp * p.warp_smem_bytes;
+    const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
     const u32 bar = sb + p.off_bar;      // three 8-byte mbarriers
     const u32 perm = sb + p.off_perm;    // u16 [max_queue]
     const u32 chunk = sb + p.off_instr;  // two 1 KB instruction batches
@@ -434,8 +448,8 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
 
 template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const u32 sb = smem_u32(smem) + warp * p.warp_smem_bytes;
+    const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
     const u32 bar = sb + p.off_bar;
     const u32 perm = sb + p.off_perm;          // u16 [max_queue]
     const u32 jarr = perm + 2u * p.max_queue;  // u16 [max_queue]
@@ -582,8 +596,8 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
 __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParams p, u32* out45, u32* out8, u32 first_env,
                                                   u32 n_out) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const u32 sb = smem_u32(smem) + warp * p.warp_smem_bytes;
+    const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
     const u32 bar = sb + p.off_bar;
     const GeoT<false>& g = static_cast<const GeoT<false>&>(p.geo);
     if (lane == 0) {

@@ -42,7 +42,12 @@ def _check(lib, h, rc):
 
 
 class BatchedEnv:
-    """`n_envs` independent Env instances (crates/step_sim/src/env.rs:58-71) on one GPU."""
+    """`n_envs` independent Env instances (crates/step_sim/src/env.rs:58-71) on one GPU.
+
+    Price ladder capacity: each book holds `pages_total` 32-level price pages (per side and 32-price
+    block), `pages_smem` of them resident in shared memory.  With `pages_total == pages_smem` (the
+    default, 10) and `price_granule == 1` the specialised kernels run; a book that needs more pages
+    flags BB_ERR_CAP_PAGES.  Give `pages_total > pages_smem` for wide or deep books (HBM pages)."""
 
     def __init__(self, n_envs: int, seed: int, start_time: int, tick_size: int, step_size: int, trading: bool = True, *,
                  device: int = 0, env_id_base: int = 0, obs_words: int = abi.OBS_L2, max_orders: int = 1 << 16,
@@ -264,6 +269,8 @@ class OrderBook:
 
     def __init__(self, start_time: int, tick_size: int, trading: bool = True, *, max_orders: int = 1 << 18,
                  max_trades: int = 1 << 18, **kw):
+        kw.setdefault("pages_smem", 16)   # a single book can afford a large resident ladder ...
+        kw.setdefault("pages_total", 256)  # ... and HBM overflow pages for arbitrarily wide price ranges
         self._env = BatchedEnv(1, 0, start_time, tick_size, 1, trading, max_orders=max_orders, max_trades=max_trades,
                                max_steps=kw.pop("max_steps", 1 << 10), **kw)
         self._t = start_time
@@ -325,6 +332,8 @@ class OrderBook:
 class _StepEnvBase:
     def __init__(self, seed: int, start_time: int, tick_size: int, step_size: int, trading: bool = True, *,
                  max_orders: int = 1 << 18, max_trades: int = 1 << 18, max_steps: int = 1 << 14, max_queue: int = 4096, **kw):
+        kw.setdefault("pages_smem", 16)
+        kw.setdefault("pages_total", 256)
         self._env = BatchedEnv(1, seed, start_time, tick_size, step_size, trading, obs_words=abi.OBS_L2,
                                max_orders=max_orders, max_trades=max_trades, max_steps=max_steps, max_queue=max_queue, **kw)
         self._one_u32 = np.zeros(1, np.uint32)

@@ -203,7 +203,7 @@ template <class G> __device__ __forceinline__ PageG page_g(const G& g, const Boo
 }
 // (vol, cnt) of a level of any page; for the cold observation paths where the slot may differ per lane
 template <class G> __device__ __forceinline__ uint2 level_pair_any(const G& g, const Book& b, u32 slot, u32 l) {
-    return slot < g.p_smem ? pld2(page_s(g, b, slot), PG_VC + 8u * l) : pld2(page_g(g, b, slot), PG_VC + 8u * l);
+    return (G::FAST || slot < g.p_smem) ? pld2(page_s(g, b, slot), PG_VC + 8u * l) : pld2(page_g(g, b, slot), PG_VC + 8u * l);
 }
 
 __device__ __forceinline__ bool has_best(const Book& b, u32 side) { return (b.flags >> (1u + side)) & 1u; }
@@ -239,13 +239,14 @@ template <class G> __device__ __forceinline__ u32 find_page(const G& g, const Bo
 
 template <class G> __device__ __forceinline__ u32 alloc_page(const G& g, Book& b, u32 side, u32 pkey) {
     for (u32 base = 0; base < ptot(g); base += 32) {
-        const u32 m = __ballot_sync(BB_FULL, lds(b.tag_lane + 4u * base) == BB_TAG_FREE);
+        // in the FAST geometry only the resident slots [0, p_smem) exist
+        const bool usable = !G::FAST || (base + b.lane) < g.p_smem;
+        const u32 m = __ballot_sync(BB_FULL, usable && lds(b.tag_lane + 4u * base) == BB_TAG_FREE);
         if (m) {
             const u32 slot = base + __ffs(m) - 1;
             sts(tag_addr(b, slot), (pkey << 1) | side);
             sts(vmap_addr(g, b, slot), 0);
             sts(qmap_addr(g, b, slot), 0);
-            __syncwarp();
             return slot;
         }
     }
@@ -368,7 +369,6 @@ template <class G, class P> __device__ __forceinline__ bool level_remove(const G
         sts(vmap_addr(g, b, slot), vm);
         if (vm == 0 && lds(qmap_addr(g, b, slot)) == 0) {
             sts(tag_addr(b, slot), BB_TAG_FREE);
-            __syncwarp();
             return true;
         }
     }
@@ -384,7 +384,6 @@ template <class G, class P> __device__ __forceinline__ void queue_unlink(const G
     if (prev == BB_NIL && next == BB_NIL) {
         const u32 qm = lds(qmap_addr(g, b, slot)) & ~(1u << l);
         sts(qmap_addr(g, b, slot), qm);
-        __syncwarp();
         if (has_best(b, side) && best_q(b, side) == q) next_best_after(g, b, side, q >> 5, qm);
     }
 }
@@ -475,10 +474,9 @@ template <class G> __device__ __forceinline__ bool book_insert(const G& g, Book&
         slot = alloc_page(g, b, side, q >> 5);
         if (slot == BB_NIL) return false;
     }
-    if (slot < g.p_smem) book_insert_at(g, b, side, q, slot, page_s(g, b, slot), t, id, vol, out_prev, out_next);
+    if (G::FAST || slot < g.p_smem) book_insert_at(g, b, side, q, slot, page_s(g, b, slot), t, id, vol, out_prev, out_next);
     else book_insert_at(g, b, side, q, slot, page_g(g, b, slot), t, id, vol, out_prev, out_next);
     if (t > b.max_key_time) b.max_key_time = t;
-    __syncwarp();
     return true;
 }
 
@@ -497,7 +495,7 @@ template <class G> __device__ __forceinline__ void book_remove(const G& g, Book&
     to_level(g, price, &q);
     const u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) return;  // unreachable for Active orders
-    if (slot < g.p_smem) book_remove_at(g, b, side, q, slot, page_s(g, b, slot), prev, next, key_time, ghost, vol);
+    if (G::FAST || slot < g.p_smem) book_remove_at(g, b, side, q, slot, page_s(g, b, slot), prev, next, key_time, ghost, vol);
     else book_remove_at(g, b, side, q, slot, page_g(g, b, slot), prev, next, key_time, ghost, vol);
 }
 
@@ -507,7 +505,7 @@ template <class G> __device__ __forceinline__ void book_reduce(const G& g, Book&
     to_level(g, price, &q);
     const u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) return;
-    if (slot < g.p_smem) {
+    if (G::FAST || slot < g.p_smem) {
         const PageS pr = page_s(g, b, slot);
         pst(pr, PG_VOL(q & 31u), pld(pr, PG_VOL(q & 31u)) - dv);
     } else {
@@ -568,10 +566,7 @@ template <class G, class P> __device__ __forceinline__ bool fill_one(const G& g,
             stg32(b.oh + (u64)nxt * ORD_STRIDE + OH_PREV, BB_NIL);
         }
         *released = level_remove(g, b, o, slot, pr, l, tv);
-        if (emptied) {
-            __syncwarp();
-            next_best_after(g, b, o, bq >> 5, qm);
-        }
+        if (emptied) next_best_after(g, b, o, bq >> 5, qm);
     } else {
         stg32(ha + OH_VOL, pvol);
         pst(pr, PG_VOL(l), pld(pr, PG_VOL(l)) - tv);  // side.remove_vol(price, tv)
@@ -601,7 +596,7 @@ template <class G> __device__ __forceinline__ u32 book_match(const G& g, Book& b
             }
         }
         bool released = false, ok;
-        if (slot < g.p_smem) ok = fill_one(g, b, o, bq, slot, page_s(g, b, slot), id, t, &vol, filled, &released);
+        if (G::FAST || slot < g.p_smem) ok = fill_one(g, b, o, bq, slot, page_s(g, b, slot), id, t, &vol, filled, &released);
         else ok = fill_one(g, b, o, bq, slot, page_g(g, b, slot), id, t, &vol, filled, &released);
         if (!ok) break;
         if (released) slot_key = BB_NIL;
@@ -616,89 +611,85 @@ __device__ __forceinline__ void write_order(const Book& b, u32 id, u32 price, u3
     stg128(a + 16u, (u32)key_time, (u32)(key_time >> 32), meta, start_vol);
 }
 
-// orderbook.rs:583-611 place_order for a freshly created order whose fields are all known to the
-// caller (create_order :356-396 happened at submission).  Writes the complete record.
-template <class G> __device__ __forceinline__ void book_place(const G& g, Book& b, u32 id, u32 side, u32 price, u32 vol, u32 trader, u64 t) {
-    if (id >= g.max_orders) {
-        b.err |= ERR_CAP_ORDERS;
-        return;
-    }
-    const bool market = side ? (price == 0xFFFFFFFFu) : (price == 0u);  // N3: decided by the price value
-    u32 rem = vol, status = ST_ACTIVE, prev = BB_NIL, next = BB_NIL;
-    u64 end_time = ~0ULL;
-    bool filled = false;
-    if (market) {
-        if (b.flags & FL_TRADING) {
-            rem = book_match(g, b, side, price, vol, id, t, &filled);
-            status = filled ? ST_FILLED : ST_CANCELLED;  // orderbook.rs:517-531
-        } else {
-            status = ST_REJECTED;
+// One event against the book: process_event (orderbook.rs:782-792) with place_order (:583-611),
+// cancel_order (:622-644) and modify_order (:743-772; reduce_order_vol :656-667, replace_order :679-723)
+// folded into one pipeline so that the remove / match / insert code exists once in the instruction stream:
+//
+//     NEW ------------------------------.
+//     CANCEL --> load record --> remove --+--> done (cancel)
+//     MODIFY --> load record --> reduce in place --> done
+//                           `--> remove ---------.
+//                                                  v
+//                                   match (if trading) --> rest or finish --> write record
+//
+// For NEW the caller supplies every field (create_order :356-396 happened at submission).
+#define EV_NEW 1u
+#define EV_CANCEL 2u
+#define EV_MODIFY 3u
+// IS_NEW is the compile-time specialisation for the dominant event kind (no record load, no replace state).
+template <bool IS_NEW, class G> __device__ __forceinline__ void book_apply(const G& g, Book& b, u32 kind, u32 id, u32 side, u32 price,
+                                                                           u32 vol, u32 trader, bool has_p, bool has_v, u64 t) {
+    u32 start_vol = vol, meta_keep = 0;
+    u64 old_kt = 0;
+    const u64 ra = b.oh + (u64)id * ORD_STRIDE;
+    if (IS_NEW) {
+        if (id >= g.max_orders) {
+            b.err |= ERR_CAP_ORDERS;
+            return;
         }
-        end_time = t;
     } else {
-        if (b.flags & FL_TRADING) rem = book_match(g, b, side, price, vol, id, t, &filled);
-        if (filled) {
-            status = ST_FILLED;
-            end_time = t;
-        } else {
-            book_insert(g, b, side, price, t, id, rem, &prev, &next);  // orderbook.rs:499-504
+        if (id >= b.n_orders || id >= g.max_orders) {
+            b.err |= ERR_BAD_ID;  // the reference panics (orderbook.rs:642, :749)
+            return;
         }
+        const uint4 a = ldg128(ra);        // price, vol, next, prev
+        const uint4 c = ldg128(ra + 16u);  // key_time lo, hi, meta, start_vol
+        if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
+        side = (c.z & META_BID) ? 1u : 0u;
+        if (kind == EV_MODIFY) {
+            if (!has_p && !has_v) return;
+            if (!has_p && vol < a.y) {  // reduce in place: priority kept (orderbook.rs:755-757)
+                stg32(ra + OH_VOL, vol);
+                book_reduce(g, b, side, a.x, a.y - vol);
+                b.d_trans += 1;
+                return;
+            }
+            if (!has_p) price = a.x;
+            if (!has_v) vol = a.y;
+        }
+        old_kt = ((u64)c.y << 32) | c.x;
+        book_remove(g, b, side, a.x, a.w, a.z, old_kt, (c.z & META_GHOST) != 0, a.y);
+        if (kind == EV_CANCEL) {
+            stg32(ra + OH_META, ST_CANCELLED | (c.z & META_BID));
+            stg64(ra + OC_END, t);
+            b.d_trans += 1;
+            return;
+        }
+        start_vol = c.w;
+        meta_keep = c.z & META_BID;
     }
-    write_order(b, id, price, rem, next, prev, t, status | (side ? META_BID : 0u), vol);
-    const u64 ca = b.oh + (u64)id * ORD_STRIDE + OC_ARR;
-    stg128(ca, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));
-    stg128(ca + 16u, trader, 0u, 0u, 0u);
-    b.d_trans += 1;
-}
-
-// orderbook.rs:622-644
-template <class G> __device__ __forceinline__ void book_cancel(const G& g, Book& b, u32 id, u64 t) {
-    if (id >= b.n_orders || id >= g.max_orders) {
-        b.err |= ERR_BAD_ID;
-        return;
-    }
-    const u64 ra = b.oh + (u64)id * ORD_STRIDE;
-    const uint4 a = ldg128(ra);        // price, vol, next, prev
-    const uint4 c = ldg128(ra + 16u);  // key_time lo, hi, meta, start_vol
-    if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
-    const u32 side = (c.z & META_BID) ? 1u : 0u;
-    stg32(ra + OH_META, ST_CANCELLED | (c.z & META_BID));
-    stg64(ra + OC_END, t);
-    book_remove(g, b, side, a.x, a.w, a.z, ((u64)c.y << 32) | c.x, (c.z & META_GHOST) != 0, a.y);
-    b.d_trans += 1;
-}
-
-// orderbook.rs:743-772 (+ reduce_order_vol :656-667, replace_order :679-723)
-template <class G> __device__ __forceinline__ void book_modify(const G& g, Book& b, u32 id, bool has_p, u32 new_p, bool has_v, u32 new_v, u64 t) {
-    if (id >= b.n_orders || id >= g.max_orders) {
-        b.err |= ERR_BAD_ID;
-        return;
-    }
-    const u64 ra = b.oh + (u64)id * ORD_STRIDE;
-    const uint4 a = ldg128(ra);
-    const uint4 c = ldg128(ra + 16u);
-    if ((c.z & META_STATUS_MASK) != ST_ACTIVE) return;
-    if (!has_p && !has_v) return;
-    const u32 side = (c.z & META_BID) ? 1u : 0u;
-    if (!has_p && new_v < a.y) {
-        stg32(ra + OH_VOL, new_v);
-        book_reduce(g, b, side, a.x, a.y - new_v);
-        b.d_trans += 1;
-        return;
-    }
-    const u32 price = has_p ? new_p : a.x;
-    const u32 vol = has_v ? new_v : a.y;
-    const u64 old_kt = ((u64)c.y << 32) | c.x;
-    book_remove(g, b, side, a.x, a.w, a.z, old_kt, (c.z & META_GHOST) != 0, a.y);
-    u32 rem = vol, prev = BB_NIL, next = BB_NIL;
-    bool filled = false;
+    // placement: a replaced order never takes the market-order path (N4), a new one does by price value (N3)
+    const bool market = IS_NEW && (side ? (price == 0xFFFFFFFFu) : (price == 0u));
+    u32 rem = vol, status = ST_ACTIVE, prev = BB_NIL, next = BB_NIL;
+    bool filled = false, ended = false;
     if (b.flags & FL_TRADING) rem = book_match(g, b, side, price, vol, id, t, &filled);
     if (filled) {
-        write_order(b, id, price, rem, BB_NIL, BB_NIL, old_kt, ST_FILLED | (c.z & META_BID), c.w);
-        stg64(ra + OC_END, t);
+        status = ST_FILLED;
+        ended = true;
+    } else if (market) {
+        status = (b.flags & FL_TRADING) ? ST_CANCELLED : ST_REJECTED;  // orderbook.rs:517-531
+        ended = true;
     } else {
-        book_insert(g, b, side, price, t, id, rem, &prev, &next);
-        write_order(b, id, price, rem, next, prev, t, ST_ACTIVE | (c.z & META_BID), c.w);
+        book_insert(g, b, side, price, t, id, rem, &prev, &next);  // orderbook.rs:499-504 / :699-722
+    }
+    if (!IS_NEW) {
+        write_order(b, id, price, rem, next, prev, filled ? old_kt : t, status | meta_keep, start_vol);
+        if (ended) stg64(ra + OC_END, t);
+    } else {
+        write_order(b, id, price, rem, next, prev, t, status | (side ? META_BID : 0u), start_vol);
+        const u64 end_time = ended ? t : ~0ULL;
+        stg128(ra + OC_ARR, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));
+        stg128(ra + OC_ARR + 16u, trader, 0u, 0u, 0u);
     }
     b.d_trans += 1;
 }

@@ -55,6 +55,7 @@ struct bb_handle {
     // layout
     u64 blob_stride = 0;
     u32 blob_smem_bytes = 0, p_total = 0, p_smem = 0, granule = 0, max_steps_padded = 0;
+    bool fast = false;  // granule == 1, one 32-entry page directory, no HBM pages
     u64 hist_env_stride = 0;
     SmemLayout lay_apply{}, lay_sim{}, lay_snap{};
     // agents
@@ -229,7 +230,7 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     p.n_steps = n_steps;
     int grid = 0, rc;
     const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
-    const bool fast = h->granule == 1 && h->p_total == 32;
+    const bool fast = h->fast;
 #define LAUNCH_APPLY(M, F)                                                                       \
     do {                                                                                         \
         if ((rc = grid_for(h, k_apply<M, F>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;    \
@@ -291,9 +292,11 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     h->cfg = *cfg;
     h->sm_count = prop.multiProcessorCount;
     h->granule = cfg->price_granule ? cfg->price_granule : cfg->tick_size;
-    h->p_total = align_up(cfg->pages_total ? cfg->pages_total : 32u, 32);
     h->p_smem = cfg->pages_smem ? cfg->pages_smem : 10u;
-    if (h->p_smem > h->p_total) h->p_smem = h->p_total;
+    const u32 usable = cfg->pages_total ? cfg->pages_total : h->p_smem;  // pages a book may hold
+    if (h->p_smem > usable) h->p_smem = usable;
+    h->p_total = align_up(usable, 32);
+    h->fast = h->granule == 1 && h->p_total == 32 && usable == h->p_smem;
     h->blob_smem_bytes = 128u + 12u * h->p_total + 512u * h->p_smem;
     h->blob_stride = 128ull + 12ull * h->p_total + 512ull * h->p_total;
     h->max_steps_padded = align_up(cfg->max_steps, 4);
@@ -544,7 +547,7 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     p.seed_hi = (u32)(seed >> 32);
     for (size_t i = 0; i < h->groups.size(); ++i) p.groups[i] = h->groups[i];
     int grid = 0, rc;
-    const bool fast = h->granule == 1 && h->p_total == 32, mom = h->mom_groups != 0;
+    const bool fast = h->fast, mom = h->mom_groups != 0;
     const size_t sim_smem = (size_t)h->lay_sim.warp_bytes * WPB;
 #define SIM_CASE(F, M)                                                                     \
     if (fast == F && mom == M) {                                                           \

@@ -139,6 +139,12 @@ template <class G> __device__ __forceinline__ void emit_obs_direct(const G& g, B
 template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book& b, u32 op_flags, u32 order_id, u32 price,
                                                                u32 vol, u32 trader, u64 t, bool assign_id) {
     const u32 op = op_flags & BB_OP_MASK;
+    if (op == BB_OP_SET_TRADING) {
+        b.flags = vol ? (b.flags | FL_TRADING) : (b.flags & ~FL_TRADING);
+        return;
+    }
+    if (op < BB_OP_NEW || op > BB_OP_MODIFY) return;
+    b.d_instr += 1;
     if (op == BB_OP_NEW) {
         const u32 side = (op_flags & BB_F_BID) ? 1u : 0u;
         if (op_flags & BB_F_MARKET) price = side ? 0xFFFFFFFFu : 0u;  // types.rs:160-172, 213-225
@@ -147,16 +153,11 @@ template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book&
             id = b.n_orders;
             b.n_orders = id + 1;
         }
-        b.d_instr += 1;
-        book_place(g, b, id, side, price, vol, trader, t);
-    } else if (op == BB_OP_CANCEL) {
-        b.d_instr += 1;
-        book_cancel(g, b, order_id, t);
-    } else if (op == BB_OP_MODIFY) {
-        b.d_instr += 1;
-        book_modify(g, b, order_id, (op_flags & BB_F_HAS_PRICE) != 0, price, (op_flags & BB_F_HAS_VOL) != 0, vol, t);
-    } else if (op == BB_OP_SET_TRADING) {
-        b.flags = vol ? (b.flags | FL_TRADING) : (b.flags & ~FL_TRADING);
+        book_apply<true>(g, b, EV_NEW, id, side, price, vol, trader, false, false, t);
+    } else {
+        // BB_OP_CANCEL / MODIFY == EV_CANCEL / EV_MODIFY
+        book_apply<false>(g, b, op, order_id, 0u, price, vol, trader, (op_flags & BB_F_HAS_PRICE) != 0,
+                          (op_flags & BB_F_HAS_VOL) != 0, t);
     }
 }
 

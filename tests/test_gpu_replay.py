@@ -65,7 +65,7 @@ def test_many_books_replay(core, oracle):
         idx = [e for e in range(n_envs) if 1 + (e % 2) == tick]
         offs = np.zeros(len(idx) + 1, np.uint64)
         offs[1:] = np.cumsum([len(streams[e]) for e in idx])
-        env = core.BatchedEnv(len(idx), 0, 0, tick, 1, max_orders=4096, max_trades=16384, max_steps=256)
+        env = core.BatchedEnv(len(idx), 0, 0, tick, 1, max_orders=4096, max_trades=16384, max_steps=256, pages_total=32)
         env.replay(np.concatenate([streams[e] for e in idx]), offs)
         for k, e in enumerate(idx):
             ob = oracle.OrderBook(0, tick)

@@ -183,7 +183,9 @@ def run_gpu(args):
     n_envs = args.envs
     groups = workloads.c3_groups()
     stream = torch.cuda.current_stream()
-    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=rank * n_envs, obs_words=abi.OBS_L1,
+    from bourse_b200.sharding import shard_range
+    env_base, n_envs = shard_range(args.envs * world, world, rank)   # weak scaling: args.envs per GPU
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=env_base, obs_words=abi.OBS_L1,
                           max_orders=args.max_orders, max_trades=args.max_trades, max_steps=args.sim_steps, max_queue=128)
     env.set_agents(groups)
     env.set_stream(stream.cuda_stream)
@@ -239,20 +241,14 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     checksum = int(hist_host[:, -1, :].astype(np.uint64).sum())
 
-    # ---- aggregate over ranks: max time, summed work; stats all-gathered over NCCL
-    vec = torch.tensor([total_ms, e2e_s, float(stats["instructions"]), float(stats["env_steps"]), float(stats["trades"]),
-                        float(stats["orders_created"]), float(stats["transitions"]), sum(kern_ms)], dtype=torch.float64,
-                       device="cuda")
-    if world > 1:
-        allv = [torch.empty_like(vec) for _ in range(world)]
-        dist.all_gather(allv, vec)
-        allv = torch.stack(allv).cpu().numpy()
-    else:
-        allv = vec.cpu().numpy()[None]
+    # ---- aggregate over ranks: max time, summed work; the ONLY collective of the run is this all-gather (NCCL)
+    from bourse_b200.sharding import gather_stats
+    agg = gather_stats(stats, total_ms, stats["l1_checksum"], device="cuda")
+    agg_e2e = gather_stats(stats, e2e_s * 1e3, checksum, device="cuda")
     if rank == 0:
-        max_ms, max_e2e = allv[:, 0].max(), allv[:, 1].max()
-        instr_per_pass = allv[:, 2].sum()     # stats are per pass (reset each pass)
-        env_steps_per_pass = allv[:, 3].sum()
+        max_ms, max_e2e = agg["elapsed_ms_max"], agg_e2e["elapsed_ms_max"] * 1e-3
+        instr_per_pass = agg["instructions"]     # stats are per pass (reset each pass)
+        env_steps_per_pass = agg["env_steps"]
         value = instr_per_pass * args.steps / (max_ms * 1e-3)
         peak, peak_src = measured_peak_gbs()
         alg_bytes = workloads.algorithmic_bytes(stats, abi.OBS_L1)          # this rank's k_sim launch
@@ -272,7 +268,7 @@ def run_gpu(args):
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(world),
             "env_steps_per_sec": env_steps_per_pass * args.steps / (max_ms * 1e-3),
-            "orders_per_pass": instr_per_pass, "trades_per_pass": allv[:, 4].sum(),
+            "orders_per_pass": instr_per_pass, "trades_per_pass": agg["trades"], "l1_checksums": agg["l1_checksums"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_sim", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": peak_src},

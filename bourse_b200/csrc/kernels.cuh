@@ -153,7 +153,9 @@ template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book&
             id = b.n_orders;
             b.n_orders = id + 1;
         }
-        book_apply<true>(g, b, EV_NEW, id, side, price, vol, trader, false, false, t);
+        // two inlined copies, each constant-folded for its side (no per-use `side ? bid : ask` selects)
+        if (side) book_apply<true>(g, b, EV_NEW, id, 1u, price, vol, trader, false, false, t);
+        else book_apply<true>(g, b, EV_NEW, id, 0u, price, vol, trader, false, false, t);
     } else {
         // BB_OP_CANCEL / MODIFY == EV_CANCEL / EV_MODIFY
         book_apply<false>(g, b, op, order_id, 0u, price, vol, trader, (op_flags & BB_F_HAS_PRICE) != 0,

@@ -324,7 +324,7 @@ __device__ __forceinline__ void random_agents_update(const KParams& p, const bb_
         const u32 side_bid = r.y >> 31;
         const u32 tick = ag.tick_lo + mulhi_range(r.z, ag.tick_hi - ag.tick_lo);
         const u32 vol = ag.vol_lo + mulhi_range(r.w, ag.vol_hi - ag.vol_lo);
-        const u32 of = do_cancel ? BB_OP_CANCEL : (BB_OP_NEW | (side_bid ? BB_F_BID : 0u) | (a << 13));
+        const u32 of = do_cancel ? 0u : (1u | (side_bid << 1) | (a << 13));  // bit0 NEW, bit1 bid, trader << 13
         queue_push(p, q, e, active, of, do_cancel ? held : id, tick * ag.tick_size, vol, b.lane);
         e.next_id += __popc(new_mask);
         if (active) slots[slot_base + a] = do_cancel ? BB_NIL : id;
@@ -376,7 +376,7 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
         const u32 word = (k & 3u) == 0 ? r.x : (k & 3u) == 1 ? r.y : (k & 3u) == 2 ? r.z : r.w;
         const bool keep = active && (u32_to_f32_unit(word) > ag.rate);
         const bool cancel = active && !keep;
-        queue_push(p, q, e, cancel, BB_OP_CANCEL, id, 0, 0, lane);
+        queue_push(p, q, e, cancel, 0u, id, 0, 0, lane);
         const u32 km = __ballot_sync(BB_FULL, keep);
         __syncwarp();
         if (keep) ms->live[n_keep + __popc(km & ((1u << lane) - 1u))] = id;
@@ -415,20 +415,21 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
         u32 total;
         const u32 cnt = (do_limit ? 1u : 0u) + (do_market ? 1u : 0u);
         const u32 before = warp_excl_scan(cnt, lane, &total);
-        const u32 bidf = (m > 0.0) ? BB_F_BID : 0u;
+        const u32 bidf = (m > 0.0) ? 2u : 0u;
         const u32 trader = ag.tick_lo + j;
         const u32 lm = __ballot_sync(BB_FULL, do_limit);
         const u32 id_l = e.next_id + before;
         const u32 id_m = id_l + (do_limit ? 1u : 0u);
         if (do_limit) {
             const u32 pos = e.n + before;
-            if (pos < p.max_queue) q[pos] = make_uint4(BB_OP_NEW | bidf | (trader << 13), id_l, price, ag.vol_lo);
+            if (pos < p.max_queue) q[pos] = make_uint4(1u | bidf | (trader << 13), id_l, price, ag.vol_lo);
             const u32 lpos = n_keep + __popc(lm & ((1u << lane) - 1u));
             if (lpos < LIVE_CAP) ms->live[lpos] = id_l; else err |= ERR_CAP_LIVE;
         }
         if (do_market) {
             const u32 pos = e.n + before + (do_limit ? 1u : 0u);
-            if (pos < p.max_queue) q[pos] = make_uint4(BB_OP_NEW | BB_F_MARKET | bidf | (trader << 13), id_m, 0, ag.vol_lo);
+            // market order: the sentinel price IS the encoding (types.rs:160-172, 213-225)
+            if (pos < p.max_queue) q[pos] = make_uint4(1u | bidf | (trader << 13), id_m, bidf ? 0xFFFFFFFFu : 0u, ag.vol_lo);
         }
         n_keep = min(n_keep + __popc(lm), (u32)LIVE_CAP);
         e.n += total;
@@ -544,10 +545,16 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
                 for (u32 k = 0; k < cnt; ++k) {
                     const u32 of = __shfl_sync(BB_FULL, mine.x, k), id = __shfl_sync(BB_FULL, mine.y, k);
                     const u32 price = __shfl_sync(BB_FULL, mine.z, k), vol = __shfl_sync(BB_FULL, mine.w, k);
-                    apply_instr(g, b, of & 0x1FFFu, id, price, vol, of >> 13, b.t, false);
+                    if (of & 1u) {  // NEW: one constant-folded copy of the placement path per side
+                        if (of & 2u) book_apply<true>(g, b, EV_NEW, id, 1u, price, vol, of >> 13, false, false, b.t);
+                        else book_apply<true>(g, b, EV_NEW, id, 0u, price, vol, of >> 13, false, false, b.t);
+                    } else {
+                        book_apply<false>(g, b, EV_CANCEL, id, 0u, 0u, 0u, 0u, false, false, b.t);
+                    }
                     b.t += 1;
                 }
             }
+            b.d_instr += n;
             b.t = start + p.step_size;
             __syncwarp();
 

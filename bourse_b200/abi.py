@@ -17,7 +17,7 @@ BB_OK, BB_EPRICE, BB_EBADID, BB_ECAP, BB_ECUDA, BB_EINVAL, BB_EDEVICE = 0, -1, -
 OBS_L1, OBS_L2 = 9, 45
 NO_ID = 2**64 - 1
 ALL_ENVS = 0xFFFFFFFF
-OP_NOOP, OP_NEW, OP_CANCEL, OP_MODIFY, OP_SET_TRADING = 0, 1, 2, 3, 4
+OP_NOOP, OP_NEW, OP_CANCEL, OP_MODIFY, OP_SET_TRADING, OP_RESTORE = 0, 1, 2, 3, 4, 5
 F_BID, F_MARKET, F_HAS_PRICE, F_HAS_VOL, F_EMIT = 1 << 8, 1 << 9, 1 << 10, 1 << 11, 1 << 12
 ACT_NOOP, ACT_NEW, ACT_CANCEL, ACT_MODIFY = 0, 1, 2, 3
 GROUP_RANDOM, GROUP_MOMENTUM = 0, 1
@@ -51,7 +51,7 @@ EXPORTS = [
     "bb_submit", "bb_step", "bb_replay", "bb_replay_device", "bb_set_agents", "bb_run_agents", "bb_level1",
     "bb_level2", "bb_book_level1", "bb_book_level2", "bb_n_steps", "bb_history", "bb_history_all",
     "bb_n_orders", "bb_n_trades", "bb_orders", "bb_trades", "bb_order_status", "bb_time", "bb_set_time",
-    "bb_set_trading", "bb_env_errors", "bb_stats", "bb_history_device",
+    "bb_set_trading", "bb_env_errors", "bb_stats", "bb_history_device", "bb_order_keys", "bb_load_book",
 ]
 
 _lib = None
@@ -106,6 +106,8 @@ def load() -> C.CDLL:
     sig("bb_env_errors", i32, vp, vp)
     sig("bb_stats", i32, vp, P(Stats))
     sig("bb_history_device", i32, vp, P(vp), P(u64), P(u32))
+    sig("bb_order_keys", i32, vp, u32, u64, u64, vp)
+    sig("bb_load_book", i32, vp, u32, u64, u32, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp)
     _lib = L
     return L
 

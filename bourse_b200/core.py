@@ -226,6 +226,21 @@ class BatchedEnv:
         return [(int(c["t"][i]), bool(c["side"][i]), int(c["price"][i]), int(c["vol"][i]), int(c["active"][i]),
                  int(c["passive"][i])) for i in range(len(c["t"]))]
 
+    def order_keys(self, env: int = 0) -> np.ndarray:
+        """Time component of every order's queue key (OrderEntry.key.2, orderbook.rs:36-44)."""
+        n = self.n_orders(env)
+        out = np.zeros(n, dtype=np.uint64)
+        self._ck(self._lib.bb_order_keys(self._h, env, 0, n, abi.ptr(out)))
+        return out
+
+    def load_book(self, env: int, t: int, trade_vol: int, trading: bool, c: dict):
+        """Overwrite one env's book from snapshot columns (bourse_b200.snapshot.dict_to_columns)."""
+        self._ck(self._lib.bb_load_book(
+            self._h, env, t, trade_vol, int(trading), len(c["side"]), abi.ptr(c["side"]), abi.ptr(c["status"]),
+            abi.ptr(c["arr_time"]), abi.ptr(c["end_time"]), abi.ptr(c["vol"]), abi.ptr(c["start_vol"]), abi.ptr(c["price"]),
+            abi.ptr(c["trader"]), abi.ptr(c["key_time"]), len(c["tr_t"]), abi.ptr(c["tr_t"]), abi.ptr(c["tr_side"]),
+            abi.ptr(c["tr_price"]), abi.ptr(c["tr_vol"]), abi.ptr(c["tr_active"]), abi.ptr(c["tr_passive"])))
+
     def order_status(self, order_id: int, env: int = 0) -> int:
         s = C.c_uint8()
         self._ck(self._lib.bb_order_status(self._h, env, order_id, C.byref(s)))
@@ -274,6 +289,7 @@ class OrderBook:
         self._env = BatchedEnv(1, 0, start_time, tick_size, 1, trading, max_orders=max_orders, max_trades=max_trades,
                                max_steps=kw.pop("max_steps", 1 << 10), **kw)
         self._t = start_time
+        self._trading = bool(trading)
         self._one = np.zeros(1, dtype=abi.INSTR_DTYPE)
 
     def _apply(self, op_flags, order_id=0, price=0, vol=0, trader=0):
@@ -283,8 +299,8 @@ class OrderBook:
         self._env.replay(x)
 
     def set_time(self, t: int): self._t = t; self._env.set_time(0, t)
-    def enable_trading(self): self._env.set_trading(True, 0)
-    def disable_trading(self): self._env.set_trading(False, 0)
+    def enable_trading(self): self._trading = True; self._env.set_trading(True, 0)
+    def disable_trading(self): self._trading = False; self._env.set_trading(False, 0)
 
     def _l1(self): return [int(x) for x in self._env.book_level_1(0)]
     def bid_ask(self): l = self._l1(); return (l[0], l[1])

@@ -686,7 +686,8 @@ template <bool IS_NEW, class G> __device__ __forceinline__ void book_apply(const
         write_order(b, id, price, rem, next, prev, filled ? old_kt : t, status | meta_keep, start_vol);
         if (ended) stg64(ra + OC_END, t);
     } else {
-        write_order(b, id, price, rem, next, prev, t, status | (side ? META_BID : 0u), start_vol);
+        // the key's time component is only stamped when the order rests (orderbook.rs:499-504); 0 otherwise
+        write_order(b, id, price, rem, next, prev, ended ? 0ULL : t, status | (side ? META_BID : 0u), start_vol);
         const u64 end_time = ended ? t : ~0ULL;
         stg128(ra + OC_ARR, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));
         stg128(ra + OC_ARR + 16u, trader, 0u, 0u, 0u);

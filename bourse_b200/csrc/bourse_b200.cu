@@ -750,6 +750,107 @@ int bb_trades(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* 
     return BB_OK;
 }
 
+int bb_order_keys(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* key_time) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    int rc = refresh_mirror(h);
+    if (rc) return rc;
+    if (first + n > h->n_orders_host[env]) return fail(h, BB_EBADID, "order range out of bounds");
+    u64 n_queued_new = 0;
+    for (auto& x : h->queue[env]) n_queued_new += (x.op_flags & BB_OP_MASK) == BB_OP_NEW;
+    const u64 n_dev = h->n_orders_host[env] - n_queued_new;
+    const u64 dev_n = first < n_dev ? std::min(n, n_dev - first) : 0;
+    std::vector<OrderRec> rec(dev_n);
+    if (dev_n) {
+        CUDA_TRY(h, cudaMemcpyAsync(rec.data(), h->ord + (size_t)env * h->cfg.max_orders + first, dev_n * sizeof(OrderRec),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    for (u64 i = 0; i < n; ++i) key_time[i] = i < dev_n ? rec[i].key_time : 0;
+    return BB_OK;
+}
+
+int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int trading, uint64_t n_orders,
+                 const uint8_t* side_is_bid, const uint8_t* status, const uint64_t* arr_time, const uint64_t* end_time,
+                 const uint32_t* vol, const uint32_t* start_vol, const uint32_t* price, const uint32_t* trader,
+                 const uint64_t* key_time, uint64_t n_trades, const uint64_t* tr_t, const uint8_t* tr_side_is_bid,
+                 const uint32_t* tr_price, const uint32_t* tr_vol, const uint64_t* tr_active, const uint64_t* tr_passive) {
+    CHECK_H(h);
+    CHECK_ENV(h, env);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->queue[env].empty()) return fail(h, BB_EINVAL, "env has queued instructions");
+    if (n_orders > h->cfg.max_orders || n_trades > h->cfg.max_trades) return fail(h, BB_ECAP, "snapshot exceeds max_orders / max_trades");
+    if (n_orders && !(side_is_bid && status && arr_time && end_time && vol && start_vol && price && trader && key_time))
+        return fail(h, BB_EINVAL, "null order column");
+    if (n_trades && !(tr_t && tr_side_is_bid && tr_price && tr_vol && tr_active && tr_passive))
+        return fail(h, BB_EINVAL, "null trade column");
+    // 1. fresh header + page directory for this env, keeping its shuffle stream
+    BookHdr hdr;
+    CUDA_TRY(h, cudaMemcpyAsync(&hdr, h->blobs + (size_t)env * h->blob_stride, sizeof(hdr), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const u64 s0 = hdr.rng_s0, s1 = hdr.rng_s1;
+    const u32 steps = hdr.n_steps, step_counter = hdr.step_counter;
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.t = t;
+    hdr.rng_s0 = s0;
+    hdr.rng_s1 = s1;
+    hdr.n_steps = steps;
+    hdr.step_counter = step_counter;
+    hdr.trade_vol = trade_vol;
+    hdr.trading = trading ? 1u : 0u;
+    hdr.n_trades = (u32)n_trades;
+    hdr.n_trades_total = n_trades;
+    std::vector<u32> dir(3 * (size_t)h->p_total, 0u);
+    std::fill(dir.begin(), dir.begin() + h->p_total, BB_TAG_FREE);
+    CUDA_TRY(h, cudaMemcpyAsync(h->blobs + (size_t)env * h->blob_stride, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->blobs + (size_t)env * h->blob_stride + 128, dir.data(), dir.size() * 4, cudaMemcpyHostToDevice,
+                                h->stream));
+    // 2. order table and trade log straight into their slabs
+    std::vector<OrderRec> rec(n_orders);
+    for (u64 i = 0; i < n_orders; ++i) {
+        OrderRec& r = rec[i];
+        r.price = price[i]; r.vol = vol[i]; r.next = BB_NIL; r.prev = BB_NIL;
+        r.key_time = key_time[i];
+        r.meta = (status[i] & META_STATUS_MASK) | (side_is_bid[i] ? META_BID : 0u);
+        r.start_vol = start_vol[i]; r.arr_time = arr_time[i]; r.end_time = end_time[i];
+        r.trader = trader[i]; r.pad0 = r.pad1 = r.pad2 = 0;
+    }
+    std::vector<TradeRec> tr(n_trades);
+    for (u64 i = 0; i < n_trades; ++i) {
+        tr[i].t = tr_t[i]; tr[i].price = tr_price[i]; tr[i].vol = tr_vol[i];
+        tr[i].active = (u32)tr_active[i]; tr[i].passive = (u32)tr_passive[i];
+        tr[i].side_bid = tr_side_is_bid[i] ? 1u : 0u; tr[i].pad = 0;
+    }
+    if (n_orders)
+        CUDA_TRY(h, cudaMemcpyAsync(h->ord + (size_t)env * h->cfg.max_orders, rec.data(), n_orders * sizeof(OrderRec),
+                                    cudaMemcpyHostToDevice, h->stream));
+    if (n_trades)
+        CUDA_TRY(h, cudaMemcpyAsync(h->tr + (size_t)env * h->cfg.max_trades, tr.data(), n_trades * sizeof(TradeRec),
+                                    cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // 3. rebuild the sides on the device: one RESTORE instruction per order, in id order
+    std::vector<bb_instr> ins(n_orders);
+    for (u64 i = 0; i < n_orders; ++i) {
+        memset(&ins[i], 0, sizeof(bb_instr));
+        ins[i].t = t;
+        ins[i].op_flags = BB_OP_RESTORE;
+        ins[i].order_id = (u32)i;
+    }
+    std::vector<u64> offs(h->cfg.n_envs + 1, 0);
+    for (u32 e = env + 1; e <= h->cfg.n_envs; ++e) offs[e] = n_orders;
+    int rc = ensure_instr_capacity(h, n_orders + 1);
+    if (rc) return rc;
+    if (n_orders) memcpy(h->h_instrs, ins.data(), n_orders * sizeof(bb_instr));
+    memcpy(h->h_offsets, offs.data(), offs.size() * 8);
+    if (n_orders) CUDA_TRY(h, cudaMemcpyAsync(h->d_instrs, h->h_instrs, n_orders * sizeof(bb_instr), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_offsets, h->h_offsets, offs.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_apply(h, MODE_REPLAY, h->d_instrs, h->d_offsets, 0))) return rc;
+    if ((rc = check_device_errors(h))) return rc;
+    // the replay left hdr.t at the last instruction's time == t; counters restored below
+    h->n_orders_host[env] = n_orders;
+    return BB_OK;
+}
+
 int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* status) {
     CHECK_H(h);
     CHECK_ENV(h, env);

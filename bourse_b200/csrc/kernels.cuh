@@ -143,6 +143,22 @@ template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book&
         b.flags = vol ? (b.flags | FL_TRADING) : (b.flags & ~FL_TRADING);
         return;
     }
+    if (op == BB_OP_RESTORE) {
+        // bb_load_book: the record is already in HBM; an Active order goes back on its side under its stored key
+        // (BTreeMap re-insertion of orderbook.rs:898-905, equal keys overwrite as on the reference)
+        const u64 ra = b.oh + (u64)order_id * ORD_STRIDE;
+        const uint4 a = ldg128(ra), c = ldg128(ra + 16u);
+        if (order_id + 1 > b.n_orders) b.n_orders = order_id + 1;
+        if ((c.z & META_STATUS_MASK) == ST_ACTIVE) {
+            u32 prev, next;
+            const u64 kt = ((u64)c.y << 32) | c.x;
+            book_insert(g, b, (c.z & META_BID) ? 1u : 0u, a.x, kt, order_id, a.y, &prev, &next);
+            stg32(ra + OH_NEXT, next);
+            stg32(ra + OH_PREV, prev);
+            stg32(ra + OH_META, c.z & ~META_GHOST);
+        }
+        return;
+    }
     if (op < BB_OP_NEW || op > BB_OP_MODIFY) return;
     b.d_instr += 1;
     if (op == BB_OP_NEW) {

@@ -95,6 +95,7 @@ typedef struct {
 #define BB_OP_CANCEL 2u       /* cancel_order, orderbook.rs:622-644 */
 #define BB_OP_MODIFY 3u       /* modify_order, orderbook.rs:743-772 */
 #define BB_OP_SET_TRADING 4u  /* enable/disable_trading, orderbook.rs:188-198 */
+#define BB_OP_RESTORE 5u      /* internal: re-insert an Active order from its record (bb_load_book) */
 #define BB_OP_MASK 0xFFu
 #define BB_F_BID (1u << 8)
 #define BB_F_MARKET (1u << 9)     /* price == None */
@@ -202,12 +203,23 @@ int bb_orders(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint8_t* s
 /* PyTrade columns (rust/src/types.rs:4-17) */
 int bb_trades(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* t, uint8_t* side_is_bid,
               uint32_t* price, uint32_t* vol, uint64_t* active_id, uint64_t* passive_id);
+/* time component of each order's queue key (OrderEntry.key.2, orderbook.rs:36-44); 0 for orders that never rested */
+int bb_order_keys(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* key_time);
 int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* status);
 int bb_time(bb_handle* h, uint32_t env, uint64_t* t);
 int bb_set_time(bb_handle* h, uint32_t env, uint64_t t);
 int bb_set_trading(bb_handle* h, uint32_t env /* or BB_ALL_ENVS */, int on);
 int bb_env_errors(bb_handle* h, uint32_t* out /* [n_envs] */);
 int bb_stats(bb_handle* h, bb_stats_t* out);
+/* Replaces `impl TryFrom<OrderBookState> for OrderBook` (orderbook.rs:891-918, the load half of the JSON
+ * snapshot): overwrite env's book with the given order table and trade log, then rebuild both sides by
+ * re-inserting every Active order under its stored key (side, price, key_time).  Column layout as in
+ * bb_orders / bb_trades.  The env must have no queued instructions. */
+int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int trading, uint64_t n_orders,
+                 const uint8_t* side_is_bid, const uint8_t* status, const uint64_t* arr_time, const uint64_t* end_time,
+                 const uint32_t* vol, const uint32_t* start_vol, const uint32_t* price, const uint32_t* trader,
+                 const uint64_t* key_time, uint64_t n_trades, const uint64_t* tr_t, const uint8_t* tr_side_is_bid,
+                 const uint32_t* tr_price, const uint32_t* tr_vol, const uint64_t* tr_active, const uint64_t* tr_passive);
 /* device pointer + strides of the history ring, for zero-copy consumers (DLPack at the Python edge) */
 int bb_history_device(bb_handle* h, void** d_ptr, uint64_t* env_stride_words, uint32_t* obs_words);
 

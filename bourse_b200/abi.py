@@ -20,7 +20,7 @@ ALL_ENVS = 0xFFFFFFFF
 OP_NOOP, OP_NEW, OP_CANCEL, OP_MODIFY, OP_SET_TRADING, OP_RESTORE = 0, 1, 2, 3, 4, 5
 F_BID, F_MARKET, F_HAS_PRICE, F_HAS_VOL, F_EMIT = 1 << 8, 1 << 9, 1 << 10, 1 << 11, 1 << 12
 ACT_NOOP, ACT_NEW, ACT_CANCEL, ACT_MODIFY = 0, 1, 2, 3
-GROUP_RANDOM, GROUP_MOMENTUM = 0, 1
+GROUP_RANDOM, GROUP_MOMENTUM, GROUP_NOISE = 0, 1, 2
 
 INSTR_DTYPE = np.dtype(
     [("t", "<u8"), ("op_flags", "<u4"), ("order_id", "<u4"), ("price", "<u4"), ("vol", "<u4"),

@@ -493,7 +493,7 @@ int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups)
         if (g.kind == BB_GROUP_RANDOM) {
             if (g.tick_hi <= g.tick_lo || g.vol_hi <= g.vol_lo) return fail(h, BB_EINVAL, "empty tick/vol range");
             if (g.n_agents >= (1u << 19)) return fail(h, BB_EINVAL, "too many agents in a group");
-        } else if (g.kind == BB_GROUP_MOMENTUM) {
+        } else if (g.kind == BB_GROUP_MOMENTUM || g.kind == BB_GROUP_NOISE) {
             if ((u64)g.tick_lo + g.n_agents >= (1u << 19)) return fail(h, BB_EINVAL, "momentum trader ids must stay below 2^19");
             if (g.tick_size == 0 || g.n_agents == 0) return fail(h, BB_EINVAL, "momentum group needs tick_size and n_agents > 0");
             ++mom;

@@ -401,9 +401,10 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     }
     // (2) mid price of the live book (orderbook.rs:272-276; u32 spread wraps as in a release build)
     const double mid = (double)bid + 0.5 * (double)(u32)(ask - bid);
+    const bool noise = ag.kind == BB_GROUP_NOISE;  // NoiseAgent::update, noise_agent.rs:126-177
     // (3) momentum and order probabilities
     double m = 0.0, p_market = 0.0;
-    if (ms->has_last) {
+    if (!noise && ms->has_last) {
         m = ms->momentum * (1.0 - ag.decay) + ag.decay * (mid - ms->last_price);
         p_market = ag.demand * tanh(ag.scale * m) / (double)ag.n_agents;
     }
@@ -416,8 +417,15 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
         const uint4 ra = philox4x32_10(env_g, step, slot_base + j, 0, p.seed_lo, p.seed_hi);
         const uint4 rb = philox4x32_10(env_g, step, slot_base + j, 1, p.seed_lo, p.seed_hi);
         const bool dir = (m > 0.0) || (m < 0.0);
-        const bool do_limit = valid && dir && (u64_to_f64_unit(ra.x, ra.y) < p_limit);
-        const bool do_market = valid && dir && (u64_to_f64_unit(ra.z, ra.w) < p_market);
+        bool do_limit = valid && dir && (u64_to_f64_unit(ra.x, ra.y) < p_limit);
+        bool do_market = valid && dir && (u64_to_f64_unit(ra.z, ra.w) < p_market);
+        bool limit_bid = m > 0.0, market_bid = m > 0.0;
+        if (noise) {  // fixed probabilities (f32 compares), a fair coin per order for the side
+            do_limit = valid && (u32_to_f32_unit(ra.x) < (float)ag.decay);
+            limit_bid = (ra.y >> 31) != 0;
+            do_market = valid && (u32_to_f32_unit(ra.z) < (float)ag.demand);
+            market_bid = (ra.w >> 31) != 0;
+        }
         u32 price = 0;
         if (do_limit) {
             double u1 = u64_to_f64_unit(rb.x, rb.y);
@@ -425,27 +433,27 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
             if (u1 < 1e-300) u1 = 1e-300;
             const double nrm = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
             const double dist = fabs(exp(ag.mu + ag.sigma * nrm));
-            price = (m > 0.0) ? round_price(mid - dist, tick, false) : round_price(mid + dist, tick, true);
+            price = limit_bid ? round_price(mid - dist, tick, false) : round_price(mid + dist, tick, true);
             if (price % p.geo.tick != 0) err |= ERR_GRANULE;  // the reference unwraps a PriceError here
         }
         u32 total;
         const u32 cnt = (do_limit ? 1u : 0u) + (do_market ? 1u : 0u);
         const u32 before = warp_excl_scan(cnt, lane, &total);
-        const u32 bidf = (m > 0.0) ? 2u : 0u;
         const u32 trader = ag.tick_lo + j;
         const u32 lm = __ballot_sync(BB_FULL, do_limit);
         const u32 id_l = e.next_id + before;
         const u32 id_m = id_l + (do_limit ? 1u : 0u);
         if (do_limit) {
             const u32 pos = e.n + before;
-            if (pos < p.max_queue) q[pos] = make_uint4(1u | bidf | (trader << 13), id_l, price, ag.vol_lo);
+            if (pos < p.max_queue) q[pos] = make_uint4(1u | (limit_bid ? 2u : 0u) | (trader << 13), id_l, price, ag.vol_lo);
             const u32 lpos = n_keep + __popc(lm & ((1u << lane) - 1u));
             if (lpos < LIVE_CAP) ms->live[lpos] = id_l; else err |= ERR_CAP_LIVE;
         }
         if (do_market) {
             const u32 pos = e.n + before + (do_limit ? 1u : 0u);
             // market order: the sentinel price IS the encoding (types.rs:160-172, 213-225)
-            if (pos < p.max_queue) q[pos] = make_uint4(1u | bidf | (trader << 13), id_m, bidf ? 0xFFFFFFFFu : 0u, ag.vol_lo);
+            if (pos < p.max_queue)
+                q[pos] = make_uint4(1u | (market_bid ? 2u : 0u) | (trader << 13), id_m, market_bid ? 0xFFFFFFFFu : 0u, ag.vol_lo);
         }
         n_keep = min(n_keep + __popc(lm), (u32)LIVE_CAP);
         e.n += total;
@@ -453,9 +461,11 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     }
     __syncwarp();
     if (lane == 0) {
-        ms->momentum = m;
-        ms->last_price = mid;
-        ms->has_last = 1;
+        if (!noise) {
+            ms->momentum = m;
+            ms->last_price = mid;
+            ms->has_last = 1;
+        }
         ms->n_live = n_keep;
     }
     __syncwarp();

@@ -115,7 +115,10 @@ typedef struct {
  *         crates/step_sim/src/agents/random_agent.rs:66-81
  *  kind 1 MomentumAgent::new(agent_id_start = tick_lo, n_agents, MomentumParams{tick_size,
  *         p_cancel = rate, trade_vol = vol_lo, decay, demand, scale, order_ratio, mu, sigma})
- *         crates/step_sim/src/agents/momentum_agent.rs:16-35, 118-134 */
+ *         crates/step_sim/src/agents/momentum_agent.rs:16-35, 118-134
+ *  kind 2 NoiseAgent::new(agent_id_start = tick_lo, n_agents, NoiseAgentParams{tick_size, p_limit = decay,
+ *         p_market = demand, p_cancel = rate, trade_vol = vol_lo, mu, sigma})
+ *         crates/step_sim/src/agents/noise_agent.rs:14-44, 98-114 */
 typedef struct {
     uint32_t kind;
     uint32_t n_agents;
@@ -128,6 +131,7 @@ typedef struct {
 
 #define BB_GROUP_RANDOM 0u
 #define BB_GROUP_MOMENTUM 1u
+#define BB_GROUP_NOISE 2u
 
 typedef struct {
     uint64_t instructions;   /* events that reached process_event (New + Cancel + Modify) */

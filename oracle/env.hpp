@@ -268,7 +268,81 @@ struct MomentumAgent {
     }
 };
 
-enum GroupKind : uint32_t { GROUP_RANDOM = 0, GROUP_MOMENTUM = 1 };
+// crates/step_sim/src/agents/noise_agent.rs:14-177
+struct NoiseParams {
+    TraderId agent_id_start;
+    uint32_t n_agents;
+    Price tick_size;
+    float p_limit, p_market, p_cancel;
+    Vol trade_vol;
+    double price_dist_mu, price_dist_sigma;
+};
+
+struct NoiseAgent {
+    NoiseParams p;
+    std::vector<OrderId> orders;
+    explicit NoiseAgent(const NoiseParams& p_) : p(p_) {}
+
+    // noise_agent.rs:126-177; draws abstracted as in MomentumAgent
+    template <class DrawCancel, class DrawTrader>
+    void update_impl(Env& env, DrawCancel&& draw_cancel, DrawTrader&& draw_trader) {
+        std::vector<OrderId> live;
+        uint32_t k = 0;
+        for (OrderId id : orders) {  // common.rs:56-75
+            if (env.order_status(id) != ACTIVE) { ++k; continue; }
+            const float u = draw_cancel(k++);
+            if (u > p.p_cancel) live.push_back(id); else env.cancel_order(id);
+        }
+        const double mid = env.book.mid_price();
+        const double tick = (double)p.tick_size;
+        for (uint32_t j = 0; j < p.n_agents; ++j) {
+            float u_limit, u_market;
+            bool limit_bid, market_bid;
+            double n1, n2;
+            draw_trader(j, &u_limit, &limit_bid, &u_market, &market_bid, &n1, &n2);
+            const TraderId trader = p.agent_id_start + j;
+            if (u_limit < p.p_limit) {
+                const double dist = std::fabs(std::exp(p.price_dist_mu + p.price_dist_sigma * MomentumAgent::normal_from(n1, n2)));
+                if (limit_bid) live.push_back(env.place_order(BID, p.trade_vol, trader, true, round_price_down(mid - dist, tick)));
+                else live.push_back(env.place_order(ASK, p.trade_vol, trader, true, round_price_up(mid + dist, tick)));
+            }
+            if (u_market < p.p_market) env.place_order(market_bid ? BID : ASK, p.trade_vol, trader, false, 0);
+        }
+        orders.swap(live);
+    }
+    void update_stream(Env& env, Xoroshiro128StarStar& rng) {
+        update_impl(
+            env, [&](uint32_t) { return gen_f32(rng); },
+            [&](uint32_t, float* ul, bool* lb, float* um, bool* mb, double* n1, double* n2) {
+                *ul = gen_f32(rng);
+                *lb = (rng.next_u64() >> 63) == 0;  // gen_bool(0.5): next_u64 < 2^63
+                *n1 = gen_f64(rng);
+                *n2 = gen_f64(rng);
+                *um = gen_f32(rng);
+                *mb = (rng.next_u64() >> 63) == 0;
+            });
+    }
+    void update_keyed(Env& env, uint32_t env_id, uint32_t step, uint32_t group, uint32_t slot_base, uint32_t k0, uint32_t k1) {
+        update_impl(
+            env,
+            [&](uint32_t k) {
+                const Philox4 r = philox4x32_10(env_id, step, PHILOX_SLOT_CANCEL | group, k >> 2, k0, k1);
+                return u32_to_f32_unit(r.v[k & 3]);
+            },
+            [&](uint32_t j, float* ul, bool* lb, float* um, bool* mb, double* n1, double* n2) {
+                const Philox4 a = philox4x32_10(env_id, step, slot_base + j, 0, k0, k1);
+                const Philox4 b = philox4x32_10(env_id, step, slot_base + j, 1, k0, k1);
+                *ul = u32_to_f32_unit(a.v[0]);
+                *lb = (a.v[1] >> 31) != 0;
+                *um = u32_to_f32_unit(a.v[2]);
+                *mb = (a.v[3] >> 31) != 0;
+                *n1 = u64_to_f64_unit(b.v[0], b.v[1]);
+                *n2 = u64_to_f64_unit(b.v[2], b.v[3]);
+            });
+    }
+};
+
+enum GroupKind : uint32_t { GROUP_RANDOM = 0, GROUP_MOMENTUM = 1, GROUP_NOISE = 2 };
 
 struct AgentGroup {
     GroupKind kind;
@@ -282,6 +356,7 @@ public:
     Env env;
     std::vector<RandomAgents> randoms;
     std::vector<MomentumAgent> momentums;
+    std::vector<NoiseAgent> noises;
     std::vector<std::pair<GroupKind, size_t>> order;  // declaration order -> (kind, index)
     uint32_t step_counter = 0;
     uint64_t n_instructions = 0;
@@ -289,6 +364,7 @@ public:
     Sim(Nanos start_time, Price tick_size, Nanos step_size, bool trading) : env(start_time, tick_size, step_size, trading) {}
     void add_random(const RandomAgentsParams& p) { order.emplace_back(GROUP_RANDOM, randoms.size()); randoms.emplace_back(p); }
     void add_momentum(const MomentumParams& p) { order.emplace_back(GROUP_MOMENTUM, momentums.size()); momentums.emplace_back(p); }
+    void add_noise(const NoiseParams& p) { order.emplace_back(GROUP_NOISE, noises.size()); noises.emplace_back(p); }
 
     // runner.rs:46-69
     void run_stream(uint64_t seed, uint64_t n_steps) {
@@ -296,7 +372,8 @@ public:
         for (uint64_t s = 0; s < n_steps; ++s) {
             for (auto& g : order) {
                 if (g.first == GROUP_RANDOM) randoms[g.second].update_stream(env, rng);
-                else momentums[g.second].update_stream(env, rng);
+                else if (g.first == GROUP_MOMENTUM) momentums[g.second].update_stream(env, rng);
+                else noises[g.second].update_stream(env, rng);
             }
             n_instructions += env.transactions.size();
             env.step(rng);
@@ -313,9 +390,12 @@ public:
                 if (g.first == GROUP_RANDOM) {
                     randoms[g.second].update_keyed(env, env_id, step, slot_base, k0, k1);
                     slot_base += randoms[g.second].p.n_agents;
-                } else {
+                } else if (g.first == GROUP_MOMENTUM) {
                     momentums[g.second].update_keyed(env, env_id, step, gi, slot_base, k0, k1);
                     slot_base += momentums[g.second].p.n_agents;
+                } else {
+                    noises[g.second].update_keyed(env, env_id, step, gi, slot_base, k0, k1);
+                    slot_base += noises[g.second].p.n_agents;
                 }
                 ++gi;
             }

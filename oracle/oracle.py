@@ -138,6 +138,17 @@ def momentum_group(agent_id_start, n_agents, tick_size, p_cancel, trade_vol, dec
     return g
 
 
+def noise_group(agent_id_start, n_agents, tick_size, p_limit, p_market, p_cancel, trade_vol, price_dist_mu, price_dist_sigma):
+    """NoiseAgent::new + NoiseAgentParams (crates/step_sim/src/agents/noise_agent.rs:14-44, 98-114)."""
+    g = np.zeros(1, dtype=GROUP_DTYPE)[0]
+    g["kind"], g["n_agents"] = 2, n_agents
+    g["tick_lo"], g["vol_lo"] = agent_id_start, trade_vol
+    g["tick_size"], g["rate"] = tick_size, p_cancel
+    g["decay"], g["demand"] = p_limit, p_market
+    g["mu"], g["sigma"] = price_dist_mu, price_dist_sigma
+    return g
+
+
 def groups_array(groups) -> np.ndarray:
     out = np.zeros(len(groups), dtype=GROUP_DTYPE)
     for i, g in enumerate(groups):

@@ -32,7 +32,7 @@ enum { OP_NOOP = 0, OP_NEW = 1, OP_CANCEL = 2, OP_MODIFY = 3, OP_SET_TRADING = 4
 enum { F_BID = 1u << 8, F_MARKET = 1u << 9, F_HAS_PRICE = 1u << 10, F_HAS_VOL = 1u << 11, F_EMIT = 1u << 12 };
 
 struct orc_group {  // 80 bytes, == bb_agent_group
-    uint32_t kind;      // 0 RandomAgents, 1 MomentumAgent
+    uint32_t kind;      // 0 RandomAgents, 1 MomentumAgent, 2 NoiseAgent
     uint32_t n_agents;
     uint32_t tick_lo, tick_hi;  // random: tick range;  momentum: tick_lo = agent_id_start
     uint32_t vol_lo, vol_hi;    // random: vol range;   momentum: vol_lo = trade_vol
@@ -243,9 +243,12 @@ static void add_groups(Sim& sim, const orc_group* g, uint32_t n_groups) {
         if (g[i].kind == 0) {
             sim.add_random(RandomAgentsParams{g[i].n_agents, g[i].tick_lo, g[i].tick_hi, g[i].vol_lo, g[i].vol_hi,
                                               g[i].tick_size, g[i].rate});
-        } else {
+        } else if (g[i].kind == 1) {
             sim.add_momentum(MomentumParams{g[i].tick_lo, g[i].n_agents, g[i].tick_size, g[i].rate, g[i].vol_lo, g[i].decay,
                                             g[i].demand, g[i].scale, g[i].order_ratio, g[i].mu, g[i].sigma});
+        } else {  // NoiseAgent: p_limit / p_market travel in the decay / demand slots
+            sim.add_noise(NoiseParams{g[i].tick_lo, g[i].n_agents, g[i].tick_size, (float)g[i].decay, (float)g[i].demand, g[i].rate,
+                                      g[i].vol_lo, g[i].mu, g[i].sigma});
         }
     }
 }

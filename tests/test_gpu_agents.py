@@ -93,3 +93,42 @@ def test_momentum_agents_match_oracle(core, oracle):
     assert n_mom > 100, "momentum traders must actually trade in this config"
     assert same >= int(0.9 * n_envs), f"only {same}/{n_envs} envs identical"          # tolerance: >= 90% identical
     assert abs(tv_gpu - tv_cpu) <= 0.05 * tv_cpu                                       # tolerance: 5% on total traded volume
+
+
+def test_noise_agents_match_oracle(core, oracle):
+    """NoiseAgent (noise_agent.rs:126-177) mixed with RandomAgents.  Same tolerance as the
+    MomentumAgent test: the log-normal price goes through f64 exp/log/cos."""
+    n_envs, n_steps, seed = 32, 60, 3
+    groups = [core.random_group(40, (40, 60), (10, 20), 2, 0.8), core.noise_group(100, 30, 2, 0.2, 0.2, 0.1, 15, 0.0, 1.0)]
+    ogroups = [oracle.random_group(40, (40, 60), (10, 20), 2, 0.8), oracle.noise_group(100, 30, 2, 0.2, 0.2, 0.1, 15, 0.0, 1.0)]
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=16384, max_trades=32768,
+                          max_steps=n_steps, max_queue=256)
+    env.set_agents(groups)
+    env.run_agents(n_steps, seed)
+    assert not env.env_errors().any()
+    hist = env.history_all(n_steps)
+    same, n_noise = 0, 0
+    for e in range(n_envs):
+        ce = oracle_run(oracle, ogroups, seed, e, n_steps)
+        same += int(np.array_equal(hist[e], ce._history()) and env.get_orders(e) == ce.get_orders()
+                    and env.get_trades(e) == ce.get_trades())
+        n_noise += sum(1 for o in ce.get_orders() if o[7] >= 100)
+    assert n_noise > 1000
+    assert same >= int(0.9 * n_envs), f"only {same}/{n_envs} envs identical"     # tolerance: >= 90% identical
+
+
+def test_noise_agents_on_empty_book_far_prices(core, oracle):
+    """From an empty book the mid price is 2^31 - 0.5: orders land around 2^31, far from any other page."""
+    g = [core.noise_group(10, 10, 2, 1.0, 0.0, 1.0, 100, 0.0, 10.0)]
+    og = [oracle.noise_group(10, 10, 2, 1.0, 0.0, 1.0, 100, 0.0, 10.0)]
+    env = core.BatchedEnv(4, 0, 0, 1, 1_000_000, max_orders=1024, max_trades=1024, max_steps=8, max_queue=64, pages_total=32)
+    env.set_agents(g)
+    env.run_agents(2, 101)
+    assert not env.env_errors().any()
+    ok = 0
+    for e in range(4):
+        ce = oracle_run(oracle, og, 101, e, 2)
+        ok += int(env.get_orders(e) == ce.get_orders() and np.array_equal(env.history(e), ce._history()))
+        st = [o[1] for o in env.get_orders(e)]
+        assert st[:10] == [3] * 10 and st[10:] == [1] * 10
+    assert ok >= 3

@@ -148,3 +148,25 @@ def test_l2_wrapping_levels(oracle):
     l2 = ob2.level_2_data()
     assert l2[2] == 2**32 - 1 and tuple(l2[7:9]) == (5, 1)
     assert ob2.mid_price() == pytest.approx((2**32 - 1) / 2)
+
+
+def test_noise_agent_known_answers(oracle):
+    """crates/step_sim/src/agents/noise_agent.rs:360-425: trader ids agent_id_start.., all-limit then all-cancel."""
+    for keyed in (False, True):
+        env = oracle.StepEnv(101, 0, 1, 1_000_000)
+        env.set_groups([oracle.noise_group(10, 10, 2, 1.0, 0.0, 1.0, 100, 0.0, 10.0)])
+        env.run_agents(1, 101, keyed=keyed)
+        orders = env.get_orders()
+        assert len(orders) == 10 and env.n_instructions() == 10
+        assert [o[7] for o in orders] == list(range(10, 20))          # trader ids
+        mid = (2**32 - 1) / 2                                         # empty book: bid 0, ask u32::MAX
+        for o in orders:
+            assert o[1] == 1 and o[4] == 100 and (o[6] % 2 == 0 or o[6] == 2**32 - 1)   # clamp to u32::MAX (common.rs:24)
+            assert (o[6] <= mid) if o[0] else (o[6] >= mid)
+        env.run_agents(1, 101, keyed=keyed)                           # p_cancel = 1: every live order is cancelled
+        orders = env.get_orders()
+        assert len(orders) == 20 and all(o[1] == 3 for o in orders[:10]) and all(o[1] == 1 for o in orders[10:])
+        env2 = oracle.StepEnv(101, 0, 1, 1_000_000)
+        env2.set_groups([oracle.noise_group(0, 8, 1, 0.0, 1.0, 0.1, 7, 0.0, 1.0)])
+        env2.run_agents(3, 5, keyed=keyed)                            # market orders only, empty book: all cancelled
+        assert len(env2.get_orders()) == 24 and all(o[1] == 3 and o[6] in (0, 2**32 - 1) for o in env2.get_orders())

@@ -182,7 +182,12 @@ def run_gpu(args):
 
     n_envs = args.envs
     groups = workloads.c3_groups()
-    stream = torch.cuda.current_stream()
+    # A dedicated (non-default) torch stream: the library launches on exactly this stream, so the CUDA events below
+    # are recorded on the stream the kernels run on.  (Passing the default stream's handle, 0, would make the library
+    # fall back to its own non-blocking stream, which events on the legacy default stream do not order against.)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     from bourse_b200.sharding import shard_range
     env_base, n_envs = shard_range(args.envs * world, world, rank)   # weak scaling: args.envs per GPU
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=env_base, obs_words=abi.OBS_L1,
@@ -207,14 +212,16 @@ def run_gpu(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     barrier()
+    wall0 = time.perf_counter()
     for a, m, b in ev:
         a.record(stream)
         env.reset()
         m.record(stream)
         env.run_agents(n_steps, SEED, sync=False)
         b.record(stream)
-        flush.fill_(1)  # untimed L2 flush between passes
+        flush.fill_(1)  # untimed L2 flush between passes (same stream, after the `b` event)
     barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3   # host clock over the same region: events + flushes + launch gaps
     step_ms = [a.elapsed_time(b) for a, _, b in ev]
     kern_ms = [m.elapsed_time(b) for _, m, b in ev]
     clocks = sampler.stop() if rank == 0 else None
@@ -276,6 +283,8 @@ def run_gpu(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * max_e2e / args.steps,
                     "api": "BatchedEnv.reset/set_agents/run_agents/history_all/stats (C ABI bb_*)", "obs_checksum": checksum},
             "gpu_launches": 2 * args.steps, "clocks": clocks,
+            # sanity: host wall clock over the timed loop (includes the untimed L2 flushes); must be >= the event total
+            "wall_ms_timed_loop": wall_ms, "event_ms_timed_loop": total_ms,
         }
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

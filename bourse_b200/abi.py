@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbourse_b200.so")
+# BOURSE_B200_LIB: developer override used to A/B kernel variants built side by side (scripts/ab.sh)
+LIB_PATH = os.environ.get("BOURSE_B200_LIB") or os.path.join(HERE, "libbourse_b200.so")
 
 BB_OK, BB_EPRICE, BB_EBADID, BB_ECAP, BB_ECUDA, BB_EINVAL, BB_EDEVICE = 0, -1, -2, -3, -4, -5, -6
 OBS_L1, OBS_L2 = 9, 45
@@ -71,7 +72,12 @@ def load() -> C.CDLL:
     P = C.POINTER
 
     def sig(name, res, *args):
-        f = getattr(L, name)
+        try:
+            f = getattr(L, name)
+        except AttributeError:
+            if os.environ.get("BOURSE_B200_LIB"):  # older variant under A/B test: symbol simply unavailable
+                return
+            raise
         f.restype = res
         f.argtypes = list(args)
 

@@ -502,22 +502,21 @@ int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups)
         }
         total += g.n_agents;
     }
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(h->rslot); h->rslot = nullptr;
-    cudaFree(h->mom); h->mom = nullptr;
+    // agent state is (re)allocated only when the population's shape changes: cudaFree / cudaMalloc synchronise the
+    // whole device and cost ~100 ms next to tens of GB of slabs, which used to dominate the end-to-end pass
+    const size_t ne = h->cfg.n_envs;
+    if (total != h->agents_per_env || mom != h->mom_groups || (total && !h->rslot) || (mom && !h->mom)) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->rslot); h->rslot = nullptr;
+        cudaFree(h->mom); h->mom = nullptr;
+        if (total) CUDA_TRY(h, cudaMalloc(&h->rslot, ne * total * 4));
+        if (mom) CUDA_TRY(h, cudaMalloc(&h->mom, ne * mom * sizeof(MomState)));
+    }
     h->groups.assign(groups, groups + n_groups);
     h->agents_per_env = total;
     h->mom_groups = mom;
-    const size_t ne = h->cfg.n_envs;
-    if (total) {
-        CUDA_TRY(h, cudaMalloc(&h->rslot, ne * total * 4));
-        CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
-    }
-    if (mom) {
-        CUDA_TRY(h, cudaMalloc(&h->mom, ne * mom * sizeof(MomState)));
-        CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * sizeof(MomState), h->stream));
-    }
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (total) CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
+    if (mom) CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * sizeof(MomState), h->stream));
     return BB_OK;
 }
 

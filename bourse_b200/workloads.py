@@ -84,3 +84,55 @@ def algorithmic_bytes(stats: dict, obs_words: int, ext_instructions: int = 0) ->
     """25*I_ext + 42*N_created + 26*N_transitions + 33*N_trades + OBS*E."""
     return (25 * ext_instructions + 42 * stats["orders_created"] + 26 * stats["transitions"] + 33 * stats["trades"]
             + 4 * obs_words * stats["env_steps"])
+
+
+def c5_stream(n_resting: int, n_steps: int, events_per_step: int, seed: int, mid_ticks: int = 10_000, depth_ticks: int = 2048,
+              step_size: int = 1_000_000) -> np.ndarray:
+    """Config C5 (deep-book stress) for ONE book as a replay stream.
+
+    Phase 1 pre-loads `n_resting` non-crossing limit orders, half per side, uniformly over `depth_ticks` ticks per side
+    (bids below `mid_ticks`, asks above), vol U{1..50}.  Phase 2 is `n_steps` x `events_per_step` events: 15% cancel and
+    15% modify (1/3 vol-only, 1/3 price-only, 1/3 both) with targets uniform over every id issued so far, 60% new limit
+    orders within +-32 ticks of `mid_ticks` (either side, so about half of them cross), 10% market orders; a level-2 record
+    is emitted at the end of every step.  Time is strictly increasing (+1 per event, +step_size per step)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n2 = n_steps * events_per_step
+    n = n_resting + n2
+    out = np.zeros(n, dtype=abi.INSTR_DTYPE)
+    idx = np.arange(n, dtype=np.uint64)
+    # phase 1
+    side1 = rng.random(n_resting) < 0.5
+    off = rng.integers(1, depth_ticks + 1, size=n_resting)
+    price1 = np.where(side1, mid_ticks - off, mid_ticks + off).astype(np.uint32)
+    out["op_flags"][:n_resting] = abi.OP_NEW | np.where(side1, abi.F_BID, 0).astype(np.uint32)
+    out["price"][:n_resting] = price1
+    out["vol"][:n_resting] = rng.integers(1, 51, size=n_resting, dtype=np.uint32)
+    # phase 2
+    u = rng.random(n2)
+    op = np.full(n2, abi.OP_NEW, dtype=np.uint32)
+    op[u < 0.30] = abi.OP_MODIFY
+    op[u < 0.15] = abi.OP_CANCEL
+    market = u >= 0.90
+    is_new = op == abi.OP_NEW
+    side2 = rng.random(n2) < 0.5
+    flags = np.zeros(n2, dtype=np.uint32)
+    flags[is_new & side2] |= abi.F_BID
+    flags[is_new & market] |= abi.F_MARKET
+    kind = rng.integers(0, 3, size=n2)
+    is_mod = op == abi.OP_MODIFY
+    flags[is_mod & (kind != 1)] |= abi.F_HAS_VOL
+    flags[is_mod & (kind != 0)] |= abi.F_HAS_PRICE
+    issued_before = n_resting + np.cumsum(is_new) - is_new
+    target = np.floor(rng.random(n2) * issued_before).astype(np.uint32)
+    price2 = rng.integers(mid_ticks - 32, mid_ticks + 33, size=n2).astype(np.uint32)
+    k = np.arange(n2)
+    flags[(k % events_per_step) == events_per_step - 1] |= abi.F_EMIT
+    out["op_flags"][n_resting:] = op | flags
+    out["order_id"][n_resting:] = np.where(is_new, 0, target)
+    out["price"][n_resting:] = np.where(is_new & market, 0, price2)
+    out["vol"][n_resting:] = rng.integers(1, 51, size=n2, dtype=np.uint32)
+    out["trader"] = (idx % 1000).astype(np.uint32)
+    t = idx + 1
+    t[n_resting:] += (k // events_per_step).astype(np.uint64) * np.uint64(step_size)
+    out["t"] = t
+    return out

@@ -162,7 +162,8 @@ class _BookView:
     def _book(self):
         raise NotImplementedError
 
-    def get_orders(self):
+    def orders_arrays(self):
+        """Column arrays of the order table (same keys as bourse_b200.core.BatchedEnv.orders_arrays)."""
         L, b = lib(), self._book()
         n = L.orc_book_n_orders(b)
         side = np.zeros(n, np.uint8); status = np.zeros(n, np.uint8)
@@ -170,17 +171,26 @@ class _BookView:
         vol = np.zeros(n, np.uint32); sv = np.zeros(n, np.uint32)
         price = np.zeros(n, np.uint32); trader = np.zeros(n, np.uint32)
         L.orc_book_orders(b, _ptr(side), _ptr(status), _ptr(arr), _ptr(end), _ptr(vol), _ptr(sv), _ptr(price), _ptr(trader))
-        return [(bool(side[i]), int(status[i]), int(arr[i]), int(end[i]), int(vol[i]), int(sv[i]), int(price[i]),
-                 int(trader[i]), i) for i in range(n)]
+        return dict(side=side, status=status, arr_time=arr, end_time=end, vol=vol, start_vol=sv, price=price, trader=trader)
 
-    def get_trades(self):
+    def trades_arrays(self):
         L, b = lib(), self._book()
         n = L.orc_book_n_trades(b)
         t = np.zeros(n, np.uint64); side = np.zeros(n, np.uint8)
         price = np.zeros(n, np.uint32); vol = np.zeros(n, np.uint32)
         act = np.zeros(n, np.uint64); pas = np.zeros(n, np.uint64)
         L.orc_book_trades(b, _ptr(t), _ptr(side), _ptr(price), _ptr(vol), _ptr(act), _ptr(pas))
-        return [(int(t[i]), bool(side[i]), int(price[i]), int(vol[i]), int(act[i]), int(pas[i])) for i in range(n)]
+        return dict(t=t, side=side, price=price, vol=vol, active=act, passive=pas)
+
+    def get_orders(self):
+        c = self.orders_arrays()
+        return [(bool(c["side"][i]), int(c["status"][i]), int(c["arr_time"][i]), int(c["end_time"][i]), int(c["vol"][i]),
+                 int(c["start_vol"][i]), int(c["price"][i]), int(c["trader"][i]), i) for i in range(len(c["side"]))]
+
+    def get_trades(self):
+        c = self.trades_arrays()
+        return [(int(c["t"][i]), bool(c["side"][i]), int(c["price"][i]), int(c["vol"][i]), int(c["active"][i]),
+                 int(c["passive"][i])) for i in range(len(c["t"]))]
 
     def order_status(self, order_id: int) -> int:
         s = lib().orc_book_order_status(self._book(), order_id)

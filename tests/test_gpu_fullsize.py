@@ -1,0 +1,174 @@
+"""GPU suite at BASELINE.json's FULL sizes (configs C3, C4 per-GPU shard, C5 per-GPU shard).
+
+The oracle cannot replay every env of a full-size run in seconds, so each test combines
+  * bit-exact comparison against the oracle on a SAMPLE of envs taken from the full-size run, and
+  * size-independent properties over ALL envs: conservation (side totals == sum of Active order volumes, traded
+    volume == sum of trade records == sum of per-step trade_vol observations), never-crossed books while trading,
+    "checksum of checksums" agreement between independent read-back paths, and determinism across envs that were fed
+    identical input.
+"""
+import numpy as np
+import pytest
+
+from bourse_b200 import abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+ST_ACTIVE = 1
+
+
+def _oracle_env(oracle, groups, seed, env_id, n_steps):
+    env = oracle.StepEnvNumpy(0, 0, 1, 1_000_000)
+    env.set_groups(groups)
+    env.run_agents(n_steps, seed, env_id=env_id, keyed=True)
+    return env
+
+
+def _check_book_conservation(env, e, final_obs):
+    """Side totals and touch data of env `e` recomputed from its order table alone."""
+    o = env.orders_arrays(e)
+    act = o["status"] == ST_ACTIVE
+    bid = o["side"].astype(bool)
+    vol_bid = int(o["vol"][act & bid].astype(np.uint64).sum())
+    vol_ask = int(o["vol"][act & ~bid].astype(np.uint64).sum())
+    assert int(final_obs[4]) == vol_bid and int(final_obs[3]) == vol_ask, e
+    if (act & bid).any():
+        best_bid = int(o["price"][act & bid].max())
+        assert int(final_obs[1]) == best_bid
+        at = act & bid & (o["price"] == best_bid)
+        assert int(final_obs[5]) == int(o["vol"][at].sum()) and int(final_obs[6]) == int(at.sum())
+    if (act & ~bid).any():
+        best_ask = int(o["price"][act & ~bid].min())
+        assert int(final_obs[2]) == best_ask
+        at = act & ~bid & (o["price"] == best_ask)
+        assert int(final_obs[7]) == int(o["vol"][at].sum()) and int(final_obs[8]) == int(at.sum())
+    # every order's executed volume is accounted for by the trade log (no modifies in agent runs)
+    t = env.trades_arrays(e)
+    filled = (o["start_vol"].astype(np.int64) - o["vol"].astype(np.int64))
+    assert int(filled.sum()) == 2 * int(t["vol"].astype(np.uint64).sum()), e
+    return int(t["vol"].astype(np.uint64).sum()), len(t["vol"])
+
+
+def test_c3_full_size(core, oracle):
+    """Config C3: 4096 envs x (50+50) RandomAgents x 1000 env-steps, level-1 observations."""
+    n_envs, n_steps, seed = 4096, 1000, 101
+    groups = workloads.c3_groups()
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1, max_orders=65536, max_trades=65536,
+                          max_steps=n_steps, max_queue=128)
+    env.set_agents(groups)
+    env.run_agents(n_steps, seed)
+    assert not env.env_errors().any()
+    st = env.stats()
+    hist = env.history_all(n_steps)
+    assert st["env_steps"] == n_envs * n_steps and st["error_envs"] == 0
+    # checksum of checksums: three independent read-back paths agree
+    assert int(hist[:, :, 0].astype(np.uint64).sum()) == st["traded_volume"]
+    assert np.array_equal(hist[:, -1, :], env.level_1_data())
+    # books never crossed while trading is on (both sides present)
+    both = (hist[:, :, 1] > 0) & (hist[:, :, 2] < 0xFFFFFFFF)
+    assert (hist[:, :, 1][both] < hist[:, :, 2][both]).all()
+    # time advanced by exactly n_steps * step_size everywhere
+    assert env.time(0) == n_steps * 1_000_000 and env.time(n_envs - 1) == n_steps * 1_000_000
+    rng = np.random.default_rng(0)
+    sample = sorted(set([0, n_envs - 1] + list(rng.integers(0, n_envs, size=22))))
+    tv_sum, tr_sum = 0, 0
+    for e in sample:
+        ce = _oracle_env(oracle, groups, seed, e, n_steps)
+        assert np.array_equal(hist[e], ce._history()[:, :9]), e
+        co, go = ce.orders_arrays(), env.orders_arrays(e)
+        for k in co:
+            assert np.array_equal(co[k], go[k]), (e, k)
+        ct, gt = ce.trades_arrays(), env.trades_arrays(e)
+        for k in ct:
+            assert np.array_equal(ct[k], gt[k]), (e, k)
+        v, n = _check_book_conservation(env, e, hist[e, -1])
+        assert v == int(hist[e, :, 0].astype(np.uint64).sum())
+        tv_sum += v; tr_sum += n
+    assert tr_sum > 20_000 * len(sample)
+
+
+def test_c4_shard_full_size(core, oracle):
+    """Config C4, one GPU's shard: 8192 envs x (40+40 RandomAgents + 20-trader MomentumAgent) x 1000 env-steps with a
+    level-2 (10-level, 45-word) observation per env-step.  MomentumAgent prices go through f64 tanh/exp/log/cos, so
+    sampled envs must be identical to the oracle on >= 90% of the sample (same tolerance as test_gpu_agents)."""
+    n_envs, n_steps, seed = 8192, 1000, 7
+    groups = workloads.c4_groups()
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, env_id_base=3 * 8192, max_orders=65536,
+                          max_trades=65536, max_steps=n_steps, max_queue=256)
+    env.set_agents(groups)
+    env.run_agents(n_steps, seed)
+    assert not env.env_errors().any()
+    st = env.stats()
+    assert st["env_steps"] == n_envs * n_steps and st["error_envs"] == 0
+    hist = env.history_all(n_steps)
+    assert int(hist[:, :, 0].astype(np.uint64).sum()) == st["traded_volume"]
+    assert np.array_equal(hist[:, -1, :], env.level_2_data())
+    both = (hist[:, :, 1] > 0) & (hist[:, :, 2] < 0xFFFFFFFF)
+    assert (hist[:, :, 1][both] < hist[:, :, 2][both]).all()
+    # level-2 self-consistency: level 0 of each side is the touch; side totals bound the 10-level sums
+    assert (hist[:, :, 5:45:4].sum(axis=2, dtype=np.uint64) <= hist[:, :, 4]).all()
+    assert (hist[:, :, 7:45:4].sum(axis=2, dtype=np.uint64) <= hist[:, :, 3]).all()
+    rng = np.random.default_rng(1)
+    sample = sorted(set([0, n_envs - 1] + list(rng.integers(0, n_envs, size=14))))
+    same = 0
+    for e in sample:
+        ce = _oracle_env(oracle, groups, seed, 3 * 8192 + e, n_steps)
+        ok = np.array_equal(hist[e], ce._history())
+        if ok:
+            co, go = ce.orders_arrays(), env.orders_arrays(e)
+            ok = all(np.array_equal(co[k], go[k]) for k in co)
+        same += int(ok)
+        _check_book_conservation(env, e, hist[e, -1])
+    assert same >= int(0.9 * len(sample)), f"only {same}/{len(sample)} sampled envs identical"  # tolerance: >= 90 %
+
+
+def test_c5_deep_book_shard(core, oracle):
+    """Config C5, the per-GPU shard of the 8-GPU run: 128 books x 1,000,000 resting orders, then 100 steps x 10,000
+    events with a 30% cancel/modify rate.  8 distinct streams are each replayed by 16 books: the 8 are compared bit for
+    bit with the oracle (level-2 records of all 100 steps, trade log, full order table) and the other 120 books must be
+    identical to the book that shares their stream."""
+    import torch
+
+    n_distinct, copies = 8, 16
+    n_envs = n_distinct * copies
+    n_rest, n_steps, per_step = 1_000_000, 100, 10_000
+    streams = [workloads.c5_stream(n_rest, n_steps, per_step, seed=100 + i) for i in range(n_distinct)]
+    n_per = len(streams[0])
+    dev = torch.device("cuda", 0)
+    d_distinct = torch.from_numpy(np.concatenate(streams).view(np.uint8)).to(dev)          # 8 x 2M x 32 B
+    d_all = d_distinct.view(n_distinct, -1).repeat(copies, 1).contiguous()                  # env e replays stream e % 8
+    del d_distinct
+    d_off = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_per
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=1_800_000, max_trades=1 << 20,
+                          max_steps=n_steps, max_queue=32, pages_smem=10, pages_total=192)
+    torch.cuda.synchronize()
+    env.replay_device(d_all.data_ptr(), d_off.data_ptr())
+    assert not env.env_errors().any()
+    st = env.stats()
+    assert st["instructions"] == n_envs * n_per
+    hist = env.history_all(n_steps)
+    l2 = env.level_2_data()
+    for e in range(n_distinct, n_envs):   # determinism across books fed identical input
+        assert np.array_equal(hist[e], hist[e % n_distinct]), e
+        assert np.array_equal(l2[e], l2[e % n_distinct]), e
+        assert env.n_orders(e) == env.n_orders(e % n_distinct) and env.n_trades(e) == env.n_trades(e % n_distinct)
+    far = n_envs - 3
+    for k, v in env.orders_arrays(far).items():
+        assert np.array_equal(v, env.orders_arrays(far % n_distinct)[k]), k
+    for i in range(n_distinct):
+        ob = oracle.OrderBook(0, 1)
+        obs = ob.replay(streams[i], obs_cap=n_steps)
+        assert np.array_equal(hist[i], obs), i
+        co, go = ob.orders_arrays(), env.orders_arrays(i)
+        assert len(co["vol"]) > n_rest
+        for k in co:
+            assert np.array_equal(co[k], go[k]), (i, k)
+        ct, gt = ob.trades_arrays(), env.trades_arrays(i)
+        assert len(ct["vol"]) > 100_000
+        for k in ct:
+            assert np.array_equal(ct[k], gt[k]), (i, k)
+        act = go["status"] == ST_ACTIVE
+        assert int(act.sum()) > 900_000   # the book really is ~1M deep at the end
+        bid = go["side"].astype(bool)
+        assert int(go["vol"][act & bid].astype(np.uint64).sum()) == int(l2[i][4])
+        assert int(go["vol"][act & ~bid].astype(np.uint64).sum()) == int(l2[i][3])

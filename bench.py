@@ -190,8 +190,12 @@ def run_gpu(args):
     assert stream.cuda_stream != 0
     from bourse_b200.sharding import shard_range
     env_base, n_envs = shard_range(args.envs * world, world, rank)   # weak scaling: args.envs per GPU
+    # engine: "dense" = dense tick-indexed ladder + shared-memory order slots (csrc/dense.cuh): C3's resting prices lie
+    # in [20, 180) (ticks 10..89 x tick_size 2) and at most 100 orders rest per book (one per RandomAgent), inside the engine's window / slot limits;
+    # "paged" = the general engine (any u32 price, any depth).  Both are bit-identical on this workload (tests).
+    eng_kw = dict(price_window=(20, 180), live_cap=128) if args.engine == "dense" else {}
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=env_base, obs_words=abi.OBS_L1,
-                          max_orders=args.max_orders, max_trades=args.max_trades, max_steps=args.sim_steps, max_queue=128)
+                          max_orders=args.max_orders, max_trades=args.max_trades, max_steps=args.sim_steps, max_queue=128, **eng_kw)
     env.set_agents(groups)
     env.set_stream(stream.cuda_stream)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -273,7 +277,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic", "config": workload_config(world),
+            "dtype": "u32", "data": "synthetic", "config": dict(workload_config(world), engine=args.engine),
             "env_steps_per_sec": env_steps_per_pass * args.steps / (max_ms * 1e-3),
             "orders_per_pass": instr_per_pass, "trades_per_pass": agg["trades"], "l1_checksums": agg["l1_checksums"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -306,6 +310,7 @@ def main():
     ap.add_argument("--max-orders", type=int, default=65536)
     ap.add_argument("--max-trades", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--engine", default="dense", choices=["dense", "paged"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

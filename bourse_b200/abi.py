@@ -39,7 +39,8 @@ class Config(C.Structure):
                 ("seed", C.c_uint64), ("tick_size", C.c_uint32), ("price_granule", C.c_uint32),
                 ("trading", C.c_uint32), ("obs_words", C.c_uint32), ("max_orders", C.c_uint32),
                 ("max_trades", C.c_uint32), ("max_steps", C.c_uint32), ("max_queue", C.c_uint32),
-                ("pages_smem", C.c_uint32), ("pages_total", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("pages_smem", C.c_uint32), ("pages_total", C.c_uint32), ("win_lo", C.c_uint32),
+                ("win_levels", C.c_uint32), ("live_cap", C.c_uint32), ("reserved", C.c_uint32 * 1)]
 
 
 class Stats(C.Structure):

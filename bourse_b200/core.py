@@ -47,12 +47,17 @@ class BatchedEnv:
     Price ladder capacity: each book holds `pages_total` 32-level price pages (per side and 32-price
     block), `pages_smem` of them resident in shared memory.  With `pages_total == pages_smem` (the
     default, 10) and `price_granule == 1` the specialised kernels run; a book that needs more pages
-    flags BB_ERR_CAP_PAGES.  Give `pages_total > pages_smem` for wide or deep books (HBM pages)."""
+    flags BB_ERR_CAP_PAGES.  Give `pages_total > pages_smem` for wide or deep books (HBM pages).
+
+    `price_window=(lo, hi)` selects the dense-window engine instead (include/bourse_b200.h, bb_config.win_levels):
+    fastest for shallow books whose resting prices stay in [lo, hi) with at most `live_cap` (default 128, max 254)
+    resting orders per book; leaving those limits flags an env error rather than producing different results."""
 
     def __init__(self, n_envs: int, seed: int, start_time: int, tick_size: int, step_size: int, trading: bool = True, *,
                  device: int = 0, env_id_base: int = 0, obs_words: int = abi.OBS_L2, max_orders: int = 1 << 16,
                  max_trades: int = 1 << 16, max_steps: int = 1 << 12, max_queue: int = 256, pages_smem: int = 0,
-                 pages_total: int = 0, price_granule: int = 0):
+                 pages_total: int = 0, price_granule: int = 0, price_window: typing.Optional[typing.Tuple[int, int]] = None,
+                 live_cap: int = 0):
         self._lib = abi.load()
         cfg = abi.Config()
         cfg.struct_size = C.sizeof(abi.Config)
@@ -62,6 +67,12 @@ class BatchedEnv:
         cfg.obs_words, cfg.max_orders, cfg.max_trades = obs_words, max_orders, max_trades
         cfg.max_steps, cfg.max_queue = max_steps, max_queue
         cfg.pages_smem, cfg.pages_total = pages_smem, pages_total
+        if price_window is not None:   # dense-window engine for shallow books: prices in [lo, hi), <= live_cap resting orders
+            lo, hi = price_window
+            if hi <= lo:
+                raise ValueError("price_window must be (lo, hi) with hi > lo")
+            cfg.win_lo, cfg.win_levels, cfg.live_cap = lo, hi - lo, live_cap
+            cfg.price_granule = 1
         self._h = C.c_void_p()
         self.n_envs, self.obs_words, self.tick_size = n_envs, obs_words, tick_size
         rc = self._lib.bb_create(C.byref(cfg), C.byref(self._h))
@@ -456,6 +467,6 @@ class StepEnvNumpy(_StepEnvBase):
     def level_2_data(self): return self._l2().copy()
 
 
-def order_book_from_json(path: str) -> OrderBook:
+def order_book_from_json(path: str, **kw) -> OrderBook:
     from .snapshot import load_json
-    return load_json(path)
+    return load_json(path, **kw)

@@ -48,6 +48,7 @@ enum { ST_NEW = 0, ST_ACTIVE = 1, ST_FILLED = 2, ST_CANCELLED = 3, ST_REJECTED =
 #define ERR_GRANULE 0x20u
 #define ERR_CAP_STEPS 0x40u
 #define ERR_CAP_LIVE 0x80u
+#define ERR_TIME_ORDER 0x100u
 
 // Order record (types.rs:79-101 `Order` + orderbook.rs:36-44 key), 64 bytes = two 32-byte sectors split
 // by access pattern: the first sector is what matching / cancel / modify read and update, the second
@@ -72,7 +73,7 @@ struct __align__(16) BookHdr {  // 128 bytes, head of every book blob
     u32 best_q[2];    // best level index (price / granule) by queue, valid iff has_best
     u32 has_best[2];
     u32 err, n_steps;
-    u32 step_counter, pad0;
+    u32 step_counter, free_top;  // free_top: dense engine's free-slot stack height
     u64 n_instr, n_transitions, traded_volume, n_trades_total, n_created;
 };
 static_assert(sizeof(BookHdr) == 128, "BookHdr must stay 128 bytes");
@@ -91,6 +92,28 @@ __device__ __forceinline__ u64 lds64(u32 a) {
     return v;
 }
 __device__ __forceinline__ void sts64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ u32 lds8(u32 a) {
+    u32 v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 lds16(u32 a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts16(u32 a, u32 v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(u32 a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(u32 a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ u32 ldg32(u64 a) {
     u32 v;
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(a));
@@ -141,11 +164,22 @@ struct Geo {
     u64 tr_base;      // trade slabs  [n_envs][max_trades] x 32 B
     u64 blobs_base;   // book blobs   [n_envs] x blob_stride
     u64 blob_stride;
+    // dense-window engine (dense.cuh): first price of the window, number of levels, number of order slots
+    u32 d_win_lo, d_levels, d_live;
 };
-// Compile-time specialisation of the common geometry: FAST <=> granule == 1 && p_total == 32, which
-// removes the price division and turns every page-directory loop into a single ballot.
-template <bool FAST_> struct GeoT : Geo {
-    static constexpr bool FAST = FAST_;
+template <u32 LP_, u32 NWMAX_> struct DenseLayout;
+// Compile-time engine selection.
+//   ENG_PAGED  any granule, any number of pages, HBM-resident pages
+//   ENG_FAST   granule == 1 && p_total == 32, every page resident: no price division, directory loops become one ballot
+//   ENG_DENSE* dense tick-indexed window + shared-memory order slots (dense.cuh), two size classes
+#define ENG_PAGED 0
+#define ENG_FAST 1
+#define ENG_DENSE 2    // <= 128 order slots, window <= 256 levels
+#define ENG_DENSE_L 3  // <= 254 order slots, window <= 1024 levels
+template <int ENG_> struct GeoT : Geo {
+    static constexpr bool FAST = ENG_ == ENG_FAST;
+    static constexpr bool DENSE = ENG_ == ENG_DENSE || ENG_ == ENG_DENSE_L;
+    typedef DenseLayout<(ENG_ == ENG_DENSE_L ? 256u : 128u), (ENG_ == ENG_DENSE_L ? 32u : 8u)> DL;
 };
 template <class G> __device__ __forceinline__ u32 ptot(const G& g) { return G::FAST ? 32u : g.p_total; }
 template <class G> __device__ __forceinline__ u32 gran(const G& g) { return G::FAST ? 1u : g.granule; }
@@ -163,6 +197,8 @@ struct Book {
     u64 oh;                // global address of this env's order slab
     u32 env;               // env index inside the handle (cold addresses are rebuilt from it)
     u32 lane;
+    u32 free_top;          // dense engine: entries on the free-slot stack
+    u64 tr_ptr;            // dense engine: address of the next trade record
 };
 
 __device__ __forceinline__ u32 tag_addr(const Book& b, u32 i) { return b.sb + 128u + 4u * i; }
@@ -297,11 +333,18 @@ template <class G> __device__ __forceinline__ void next_best_after(const G& g, B
 // side.rs:99-104 + 194-196: empty ask => u32::MAX, empty bid => 0
 template <class G> __device__ __forceinline__ u32 best_price(const G& g, const Book& b, u32 side) {
     if (!has_best(b, side)) return side ? 0u : 0xFFFFFFFFu;
+    if constexpr (G::DENSE) return g.d_win_lo + best_q(b, side);
     return best_q(b, side) * gran(g);
 }
 
 // side.rs:138-143 through the bid/ask wrappers: (vol, count) at an arbitrary price; warp-cooperative
+template <class G> __device__ __forceinline__ void level_at(const G& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt);
+template <class G> __device__ __forceinline__ void d_level_at(const G& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt);
 template <class G> __device__ __forceinline__ void level_at(const G& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
+    if constexpr (G::DENSE) {
+        d_level_at(g, b, side, price, vol, cnt);
+        return;
+    }
     *vol = 0;
     *cnt = 0;
     u32 q;
@@ -316,6 +359,10 @@ template <class G> __device__ __forceinline__ void level_at(const G& g, const Bo
 
 // same lookup done independently by each lane (divergent prices) — used by the level-2 emitter
 template <class G> __device__ __forceinline__ void level_at_lane(const G& g, const Book& b, u32 side, u32 price, u32* vol, u32* cnt) {
+    if constexpr (G::DENSE) {
+        d_level_at(g, b, side, price, vol, cnt);
+        return;
+    }
     *vol = 0;
     *cnt = 0;
     u32 q;
@@ -333,6 +380,10 @@ template <class G> __device__ __forceinline__ void level_at_lane(const G& g, con
 
 // first level of the reference's `volumes` map (side.rs:107-120)
 template <class G> __device__ __forceinline__ void best_by_volumes(const G& g, const Book& b, u32 side, u32* vol, u32* cnt) {
+    if constexpr (G::DENSE) {  // no key collisions in the dense engine: the two maps of side.rs always agree
+        d_level_at(g, b, side, best_price(g, b, side), vol, cnt);
+        return;
+    }
     *vol = 0;
     *cnt = 0;
     u32 q;
@@ -626,9 +677,18 @@ __device__ __forceinline__ void write_order(const Book& b, u32 id, u32 price, u3
 #define EV_NEW 1u
 #define EV_CANCEL 2u
 #define EV_MODIFY 3u
+}  // namespace bb
+#include "dense.cuh"
+namespace bb {
 // IS_NEW is the compile-time specialisation for the dominant event kind (no record load, no replace state).
-template <bool IS_NEW, class G> __device__ __forceinline__ void book_apply(const G& g, Book& b, u32 kind, u32 id, u32 side, u32 price,
-                                                                           u32 vol, u32 trader, bool has_p, bool has_v, u64 t) {
+// CHECK_TIME (dense engine only): the caller cannot guarantee strictly increasing time between resting inserts.
+template <bool IS_NEW, bool CHECK_TIME, class G>
+__device__ __forceinline__ void book_apply(const G& g, Book& b, u32 kind, u32 id, u32 side, u32 price, u32 vol, u32 trader, bool has_p,
+                                           bool has_v, u64 t) {
+    if constexpr (G::DENSE) {
+        d_apply<IS_NEW, CHECK_TIME>(g, b, kind, id, side, price, vol, trader, has_p, has_v, t);
+        return;
+    }
     u32 start_vol = vol, meta_keep = 0;
     u64 old_kt = 0;
     const u64 ra = b.oh + (u64)id * ORD_STRIDE;
@@ -748,13 +808,18 @@ template <class G> __device__ __forceinline__ void book_obs(const G& g, const Bo
 #define HDR_ERR 72u
 #define HDR_NSTEPS 76u
 #define HDR_STEPCTR 80u
+#define HDR_FREETOP 84u
 #define HDR_NINSTR 88u
 #define HDR_NTRANS 96u
 #define HDR_VOLUME 104u
 #define HDR_NTRADES_TOTAL 112u
 #define HDR_NCREATED 120u
 
-__device__ __forceinline__ void book_from_header(Book& b) {
+template <class G> __device__ __forceinline__ void book_from_header(const G& g, Book& b) {
+    if constexpr (G::DENSE) {
+        b.free_top = lds(b.sb + HDR_FREETOP);
+        b.tr_ptr = g.tr_base + ((u64)b.env * g.max_trades + min((u32)lds64(b.sb + HDR_NTRADES_TOTAL), g.max_trades)) * 32u;
+    }
     b.t = lds64(b.sb + HDR_T);
     b.max_key_time = lds64(b.sb + HDR_MAXKT);
     b.n_orders = lds(b.sb + HDR_NORDERS);
@@ -771,6 +836,7 @@ __device__ __forceinline__ void book_from_header(Book& b) {
 }
 
 template <class G> __device__ __forceinline__ void book_to_header(const G& g, const Book& b) {
+    if constexpr (G::DENSE) sts(b.sb + HDR_FREETOP, b.free_top);
     sts64(b.sb + HDR_T, b.t);
     sts64(b.sb + HDR_MAXKT, b.max_key_time);
     sts64(b.sb + HDR_NCREATED, lds64(b.sb + HDR_NCREATED) + (b.n_orders - lds(b.sb + HDR_NORDERS)));

@@ -4,6 +4,7 @@
 // book state on the CPU, and there is no fallback when CUDA is unavailable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -19,7 +20,7 @@ namespace {
 thread_local std::string g_last_error;
 
 struct SmemLayout {
-    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar;
+    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar, off_q;
 };
 
 constexpr u32 WPB = 4;  // warps (books) per CTA
@@ -55,7 +56,9 @@ struct bb_handle {
     // layout
     u64 blob_stride = 0;
     u32 blob_smem_bytes = 0, p_total = 0, p_smem = 0, granule = 0, max_steps_padded = 0;
-    bool fast = false;  // granule == 1, one 32-entry page directory, no HBM pages
+    int eng = ENG_PAGED;  // ENG_FAST: granule == 1, one 32-entry page directory, no HBM pages; ENG_DENSE: dense window
+    Geo dgeo{};           // dense-engine geometry (d_* fields), zero otherwise
+    u32 dense_lp = 0, dense_nwmax = 0;  // DenseLayout parameters of the selected variant
     u64 hist_env_stride = 0;
     SmemLayout lay_apply{}, lay_sim{}, lay_snap{};
     // agents
@@ -90,7 +93,7 @@ u64 splitmix_next(u64& x) {
     return z ^ (z >> 31);
 }
 
-SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr) {
+SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool with_queue = false) {
     SmemLayout l{};
     u32 off = align_up(h->blob_smem_bytes, 16);
     l.off_perm = off;
@@ -99,6 +102,8 @@ SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr) {
     if (with_obs) off += align_up(2u * OBS_STAGE_STEPS * h->cfg.obs_words * 4u, 16);
     l.off_instr = off;
     if (with_instr) off += 2048;
+    l.off_q = off;
+    if (with_queue) off += 16u * h->cfg.max_queue;  // the dense engine keeps the step's transaction queue on chip
     l.off_bar = off;
     off += 32;
     l.warp_bytes = align_up(off, 128);
@@ -127,6 +132,8 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.geo.tr_base = (u64)h->tr;
     p.geo.blobs_base = (u64)h->blobs;
     p.geo.blob_stride = h->blob_stride;
+    p.geo.d_win_lo = h->dgeo.d_win_lo; p.geo.d_levels = h->dgeo.d_levels; p.geo.d_live = h->dgeo.d_live;
+    p.off_q = l.off_q;
     p.max_steps = h->max_steps_padded;
     p.max_queue = h->cfg.max_queue;
     p.obs_words = h->cfg.obs_words;
@@ -167,7 +174,7 @@ int upload_seeds(bb_handle* h) {
 int init_books(bb_handle* h) {
     const bb_config& c = h->cfg;
     k_init<<<c.n_envs, 64, 0, h->stream>>>(h->blobs, h->blob_stride, c.n_envs, h->p_total, c.start_time, c.trading ? 1u : 0u,
-                                           h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups);
+                                           h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups, h->dgeo, h->dense_lp, h->dense_nwmax);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
     for (auto& q : h->queue) q.clear();
@@ -197,8 +204,9 @@ int check_device_errors(bb_handle* h) {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (flag) {
         CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
-        char buf[160];
-        snprintf(buf, sizeof buf, "device flagged env errors 0x%x (bad order id / capacity); see bb_env_errors", flag);
+        char buf[256];
+        snprintf(buf, sizeof buf, "device flagged env errors 0x%x (0x1 orders 0x2 trades 0x4 pages/window 0x8 queue 0x10 bad id "
+                                  "0x20 granule 0x40 steps 0x80 live slots 0x100 time order); see bb_env_errors", flag);
         return fail(h, (flag & ERR_BAD_ID) ? BB_EBADID : (flag & 0x80000000u) ? BB_ECUDA : BB_ECAP, buf);
     }
     return BB_OK;
@@ -230,16 +238,21 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     p.n_steps = n_steps;
     int grid = 0, rc;
     const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
-    const bool fast = h->fast;
-#define LAUNCH_APPLY(M, F)                                                                       \
+#define LAUNCH_APPLY(M, E)                                                                       \
     do {                                                                                         \
-        if ((rc = grid_for(h, k_apply<M, F>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;    \
-        k_apply<M, F><<<grid, WPB * 32, smem, h->stream>>>(p);                                   \
+        if ((rc = grid_for(h, k_apply<M, E>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;    \
+        k_apply<M, E><<<grid, WPB * 32, smem, h->stream>>>(p);                                   \
     } while (0)
     if (mode == MODE_REPLAY) {
-        if (fast) LAUNCH_APPLY(MODE_REPLAY, true); else LAUNCH_APPLY(MODE_REPLAY, false);
+        if (h->eng == ENG_DENSE) LAUNCH_APPLY(MODE_REPLAY, ENG_DENSE);
+        else if (h->eng == ENG_DENSE_L) LAUNCH_APPLY(MODE_REPLAY, ENG_DENSE_L);
+        else if (h->eng == ENG_FAST) LAUNCH_APPLY(MODE_REPLAY, ENG_FAST);
+        else LAUNCH_APPLY(MODE_REPLAY, ENG_PAGED);
     } else {
-        if (fast) LAUNCH_APPLY(MODE_ENV, true); else LAUNCH_APPLY(MODE_ENV, false);
+        if (h->eng == ENG_DENSE) LAUNCH_APPLY(MODE_ENV, ENG_DENSE);
+        else if (h->eng == ENG_DENSE_L) LAUNCH_APPLY(MODE_ENV, ENG_DENSE_L);
+        else if (h->eng == ENG_FAST) LAUNCH_APPLY(MODE_ENV, ENG_FAST);
+        else LAUNCH_APPLY(MODE_ENV, ENG_PAGED);
     }
 #undef LAUNCH_APPLY
     CUDA_TRY(h, cudaGetLastError());
@@ -250,8 +263,17 @@ int snapshot(bb_handle* h, u32 first_env, u32 n, u32* d45, u32* d8) {
     KParams p;
     fill_params(h, h->lay_snap, p);
     int grid = 0, rc;
-    if ((rc = grid_for(h, k_snapshot, h->lay_snap, n, &grid))) return rc;
-    k_snapshot<<<grid, WPB * 32, (size_t)h->lay_snap.warp_bytes * WPB, h->stream>>>(p, d45, d8, first_env, n);
+    const size_t smem = (size_t)h->lay_snap.warp_bytes * WPB;
+    if (h->eng == ENG_DENSE) {
+        if ((rc = grid_for(h, k_snapshot<ENG_DENSE>, h->lay_snap, n, &grid))) return rc;
+        k_snapshot<ENG_DENSE><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n);
+    } else if (h->eng == ENG_DENSE_L) {
+        if ((rc = grid_for(h, k_snapshot<ENG_DENSE_L>, h->lay_snap, n, &grid))) return rc;
+        k_snapshot<ENG_DENSE_L><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n);
+    } else {
+        if ((rc = grid_for(h, k_snapshot<ENG_PAGED>, h->lay_snap, n, &grid))) return rc;
+        k_snapshot<ENG_PAGED><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n);
+    }
     CUDA_TRY(h, cudaGetLastError());
     return BB_OK;
 }
@@ -296,13 +318,29 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     const u32 usable = cfg->pages_total ? cfg->pages_total : h->p_smem;  // pages a book may hold
     if (h->p_smem > usable) h->p_smem = usable;
     h->p_total = align_up(usable, 32);
-    h->fast = h->granule == 1 && h->p_total == 32 && usable == h->p_smem;
+    h->eng = (h->granule == 1 && h->p_total == 32 && usable == h->p_smem) ? ENG_FAST : ENG_PAGED;
     h->blob_smem_bytes = 128u + 12u * h->p_total + 512u * h->p_smem;
     h->blob_stride = 128ull + 12ull * h->p_total + 512ull * h->p_total;
+    if (cfg->win_levels) {  // dense-window engine (csrc/dense.cuh), two compiled size classes
+        const u32 W = align_up(cfg->win_levels, 32), L = cfg->live_cap ? cfg->live_cap : 128u;
+        if (h->granule != 1 || W > 32 * DenseLarge::NWMAX || L > 254 || (u64)cfg->win_lo + W > 0x100000000ull) {
+            delete h;
+            return fail(nullptr, BB_EINVAL, "dense engine needs price_granule == 1, win_levels <= 1024, live_cap <= 254 and "
+                                            "win_lo + win_levels <= 2^32");
+        }
+        const bool small = L <= DenseSmall::LP && W <= 32 * DenseSmall::NWMAX;
+        h->dgeo.d_win_lo = cfg->win_lo; h->dgeo.d_levels = W; h->dgeo.d_live = L;
+        h->eng = small ? ENG_DENSE : ENG_DENSE_L;
+        h->dense_lp = small ? DenseSmall::LP : DenseLarge::LP;
+        h->dense_nwmax = small ? DenseSmall::NWMAX : DenseLarge::NWMAX;
+        h->blob_smem_bytes = align_up(small ? DenseSmall::image_bytes(W) : DenseLarge::image_bytes(W), 16);
+        h->blob_stride = align_up(h->blob_smem_bytes, 128);
+        h->p_total = h->p_smem = 0;
+    }
     h->max_steps_padded = align_up(cfg->max_steps, 4);
     h->hist_env_stride = (u64)h->max_steps_padded * cfg->obs_words;
     h->lay_apply = make_layout(h, false, true);
-    h->lay_sim = make_layout(h, true, false);
+    h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE);
     h->lay_snap = make_layout(h, false, false);
     h->queue.resize(cfg->n_envs);
     h->n_orders_host.assign(cfg->n_envs, 0);
@@ -320,6 +358,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     TRY_ALLOC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     TRY_ALLOC(cudaMalloc(&h->blobs, ne * h->blob_stride));
+    TRY_ALLOC(cudaMemsetAsync(h->blobs, 0, ne * h->blob_stride, h->stream));
     TRY_ALLOC(cudaMalloc(&h->ord, ne * cfg->max_orders * sizeof(OrderRec)));
     if (cfg->max_trades) TRY_ALLOC(cudaMalloc(&h->tr, ne * cfg->max_trades * sizeof(TradeRec)));
     TRY_ALLOC(cudaMalloc(&h->hist, ne * h->hist_env_stride * 4));
@@ -546,26 +585,28 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     p.seed_hi = (u32)(seed >> 32);
     for (size_t i = 0; i < h->groups.size(); ++i) p.groups[i] = h->groups[i];
     int grid = 0, rc;
-    const bool fast = h->fast, mom = h->mom_groups != 0;
+    const bool mom = h->mom_groups != 0;
     const size_t sim_smem = (size_t)h->lay_sim.warp_bytes * WPB;
-#define SIM_CASE(F, M)                                                                     \
-    if (fast == F && mom == M) {                                                           \
-        if ((rc = grid_for(h, k_sim<F, M>, h->lay_sim, h->cfg.n_envs, &grid))) return rc;  \
+#define SIM_CASE(E, M)                                                                     \
+    if (h->eng == E && mom == M) {                                                         \
+        if ((rc = grid_for(h, k_sim<E, M>, h->lay_sim, h->cfg.n_envs, &grid))) return rc;  \
     }
-    SIM_CASE(true, false) SIM_CASE(true, true) SIM_CASE(false, false) SIM_CASE(false, true)
+    SIM_CASE(ENG_FAST, false) SIM_CASE(ENG_FAST, true) SIM_CASE(ENG_PAGED, false) SIM_CASE(ENG_PAGED, true)
+    SIM_CASE(ENG_DENSE, false) SIM_CASE(ENG_DENSE, true) SIM_CASE(ENG_DENSE_L, false) SIM_CASE(ENG_DENSE_L, true)
 #undef SIM_CASE
     const size_t warps = (size_t)grid * WPB;
-    if (warps > h->scratch_warps) {
+    if (h->eng < ENG_DENSE && warps > h->scratch_warps) {
         cudaFree(h->scratch);
         h->scratch = nullptr;
         CUDA_TRY(h, cudaMalloc(&h->scratch, warps * h->cfg.max_queue * sizeof(uint4)));
         h->scratch_warps = warps;
     }
     p.scratch = h->scratch;
-    if (fast && !mom) k_sim<true, false><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
-    else if (fast && mom) k_sim<true, true><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
-    else if (!fast && !mom) k_sim<false, false><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
-    else k_sim<false, true><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
+#define SIM_LAUNCH(E, M) \
+    if (h->eng == E && mom == M) k_sim<E, M><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
+    SIM_LAUNCH(ENG_FAST, false) SIM_LAUNCH(ENG_FAST, true) SIM_LAUNCH(ENG_PAGED, false) SIM_LAUNCH(ENG_PAGED, true)
+    SIM_LAUNCH(ENG_DENSE, false) SIM_LAUNCH(ENG_DENSE, true) SIM_LAUNCH(ENG_DENSE_L, false) SIM_LAUNCH(ENG_DENSE_L, true)
+#undef SIM_LAUNCH
     CUDA_TRY(h, cudaGetLastError());
     h->mirror_dirty = true;
     return BB_OK;
@@ -799,8 +840,21 @@ int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int
     hdr.trading = trading ? 1u : 0u;
     hdr.n_trades = (u32)n_trades;
     hdr.n_trades_total = n_trades;
-    std::vector<u32> dir(3 * (size_t)h->p_total, 0u);
-    std::fill(dir.begin(), dir.begin() + h->p_total, BB_TAG_FREE);
+    std::vector<u32> dir;
+    if (h->eng >= ENG_DENSE) {  // empty bitmaps, every slot free (same image k_init writes)
+        const Geo& d = h->dgeo;
+        hdr.free_top = d.d_live;
+        dir.assign((h->blob_smem_bytes - 128) / 4, 0u);
+        unsigned char* img = reinterpret_cast<unsigned char*>(dir.data()) - 128;
+        const u32 off_fs = 128u + 12u * h->dense_lp;
+        for (u32 i = 0; i < h->dense_lp; ++i) {
+            reinterpret_cast<u32*>(img + 128)[i] = BB_NIL;
+            img[off_fs + i] = (unsigned char)(i < d.d_live ? d.d_live - 1 - i : 0xFF);
+        }
+    } else {
+        dir.assign(3 * (size_t)h->p_total, 0u);
+        std::fill(dir.begin(), dir.begin() + h->p_total, BB_TAG_FREE);
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->blobs + (size_t)env * h->blob_stride, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->blobs + (size_t)env * h->blob_stride + 128, dir.data(), dir.size() * 4, cudaMemcpyHostToDevice,
                                 h->stream));
@@ -829,11 +883,16 @@ int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     // 3. rebuild the sides on the device: one RESTORE instruction per order, in id order
     std::vector<bb_instr> ins(n_orders);
+    std::vector<u32> order(n_orders);
+    for (u64 i = 0; i < n_orders; ++i) order[i] = (u32)i;
+    // the dense engine only appends to its queues: feed it the orders by key time (ties keep id order)
+    if (h->eng >= ENG_DENSE)
+        std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return key_time[a] < key_time[b]; });
     for (u64 i = 0; i < n_orders; ++i) {
         memset(&ins[i], 0, sizeof(bb_instr));
         ins[i].t = t;
         ins[i].op_flags = BB_OP_RESTORE;
-        ins[i].order_id = (u32)i;
+        ins[i].order_id = order[i];
     }
     std::vector<u64> offs(h->cfg.n_envs + 1, 0);
     for (u32 e = env + 1; e <= h->cfg.n_envs; ++e) offs[e] = n_orders;

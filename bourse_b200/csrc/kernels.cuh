@@ -41,7 +41,7 @@ struct KParams {
     u32 n_envs, env_id_base;
     Geo geo;  // p_total, p_smem, granule, tick, max_orders, max_trades
     u32 max_steps, max_queue, obs_words;
-    u32 warp_smem_bytes, off_perm, off_obs, off_instr, off_bar;
+    u32 warp_smem_bytes, off_perm, off_obs, off_instr, off_bar, off_q;
     // k_apply
     const bb_instr* instrs;
     const u64* offsets;
@@ -75,24 +75,6 @@ __device__ __forceinline__ void make_book(Book& b, const KParams& p, u32 sb, u32
     b.oh = keep64((u64)(p.ord + (size_t)env * p.geo.max_orders));
     b.env = env;
     b.lane = lane;
-}
-
-// u16 / 128-bit accessors for the per-warp scratch arrays in shared memory
-__device__ __forceinline__ u32 lds16(u32 a) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts16(u32 a, u32 v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(u32 a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts128(u32 a, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // bulk-load the shared-memory image of a book (header, page directory, resident pages)
@@ -136,14 +118,18 @@ template <class G> __device__ __forceinline__ void emit_obs_direct(const G& g, B
 }
 
 // one decoded instruction against the book (process_event, orderbook.rs:782-792)
-template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book& b, u32 op_flags, u32 order_id, u32 price,
-                                                               u32 vol, u32 trader, u64 t, bool assign_id) {
+template <bool CT, class G> __device__ __forceinline__ void apply_instr(const G& g, Book& b, u32 op_flags, u32 order_id, u32 price,
+                                                                        u32 vol, u32 trader, u64 t, bool assign_id) {
     const u32 op = op_flags & BB_OP_MASK;
     if (op == BB_OP_SET_TRADING) {
         b.flags = vol ? (b.flags | FL_TRADING) : (b.flags & ~FL_TRADING);
         return;
     }
     if (op == BB_OP_RESTORE) {
+        if constexpr (G::DENSE) {
+            d_restore(g, b, order_id);
+            return;
+        }
         // bb_load_book: the record is already in HBM; an Active order goes back on its side under its stored key
         // (BTreeMap re-insertion of orderbook.rs:898-905, equal keys overwrite as on the reference)
         const u64 ra = b.oh + (u64)order_id * ORD_STRIDE;
@@ -170,23 +156,24 @@ template <class G> __device__ __forceinline__ void apply_instr(const G& g, Book&
             b.n_orders = id + 1;
         }
         // two inlined copies, each constant-folded for its side (no per-use `side ? bid : ask` selects)
-        if (side) book_apply<true>(g, b, EV_NEW, id, 1u, price, vol, trader, false, false, t);
-        else book_apply<true>(g, b, EV_NEW, id, 0u, price, vol, trader, false, false, t);
+        if (side) book_apply<true, CT>(g, b, EV_NEW, id, 1u, price, vol, trader, false, false, t);
+        else book_apply<true, CT>(g, b, EV_NEW, id, 0u, price, vol, trader, false, false, t);
     } else {
         // BB_OP_CANCEL / MODIFY == EV_CANCEL / EV_MODIFY
-        book_apply<false>(g, b, op, order_id, 0u, price, vol, trader, (op_flags & BB_F_HAS_PRICE) != 0,
+        book_apply<false, CT>(g, b, op, order_id, 0u, price, vol, trader, (op_flags & BB_F_HAS_PRICE) != 0,
                           (op_flags & BB_F_HAS_VOL) != 0, t);
     }
 }
 
-template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply(const __grid_constant__ KParams p) {
+template <int MODE, int ENG> __global__ void __launch_bounds__(128, 7) k_apply(const __grid_constant__ KParams p) {
+    typedef GeoT<ENG> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
     const u32 bar = sb + p.off_bar;      // three 8-byte mbarriers
     const u32 perm = sb + p.off_perm;    // u16 [max_queue]
     const u32 chunk = sb + p.off_instr;  // two 1 KB instruction batches
-    const GeoT<FAST>& g = static_cast<const GeoT<FAST>&>(p.geo);
+    const GeoT<ENG>& g = static_cast<const GeoT<ENG>&>(p.geo);
     if (lane == 0) {
         mbar_init_a(bar, 1);
         mbar_init_a(bar + 8u, 1);
@@ -204,7 +191,7 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
             if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
             return;
         }
-        book_from_header(b);
+        book_from_header(g, b);
         const u64 off = p.offsets[env];
         const u32 n = (u32)(p.offsets[env + 1] - off);
         const bb_instr* ins = p.instrs + off;
@@ -234,7 +221,7 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
                     const uint4 x = lds128(chunk + buf * 1024u + 32u * k), y = lds128(chunk + buf * 1024u + 32u * k + 16u);
                     const u64 t = ((u64)x.y << 32) | x.x;
                     b.t = t;
-                    apply_instr(g, b, x.z, x.w, y.x, y.y, y.z, t, true);
+                    apply_instr<true>(g, b, x.z, x.w, y.x, y.y, y.z, t, true);
                     if (x.z & BB_F_EMIT) emit_obs_direct(g, b, p, env);
                 }
                 __syncwarp();
@@ -245,6 +232,9 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
                 b.trade_vol = 0;  // env.rs:117-118
                 const u32 m = (s == 0) ? n : 0u;
                 if (m > p.max_queue) b.err |= ERR_CAP_QUEUE;
+                if constexpr (G::DENSE) {  // the dense engine relies on t = start + i being new, increasing key times
+                    if (m > p.step_size || (start <= b.max_key_time && (b.flags & (FL_HAS_ASK | FL_HAS_BID)))) b.err |= ERR_TIME_ORDER;
+                }
                 const u32 mm = min(m, p.max_queue);
                 // (a) create_order happened at submission (env.rs:173): publish status New for the new ids
                 u32 max_id = 0;
@@ -285,7 +275,7 @@ template <int MODE, bool FAST> __global__ void __launch_bounds__(128, 7) k_apply
                         const uint4 x = lds128(chunk + 32u * k), y = lds128(chunk + 32u * k + 16u);
                         const u64 t = start + i0 + k;
                         b.t = t;
-                        apply_instr(g, b, x.z, x.w, y.x, y.y, y.z, t, false);
+                        apply_instr<false>(g, b, x.z, x.w, y.x, y.y, y.z, t, false);
                     }
                     __syncwarp();
                 }
@@ -476,7 +466,8 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     return out;
 }
 
-template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
+template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
+    typedef GeoT<ENG> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
@@ -484,9 +475,13 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
     const u32 perm = sb + p.off_perm;          // u16 [max_queue]
     const u32 jarr = perm + 2u * p.max_queue;  // u16 [max_queue]
     const u32 stage = sb + p.off_obs;          // u32 [2][OBS_STAGE_STEPS * obs_words]
-    uint4* q = p.scratch + (size_t)(blockIdx.x * wpb + warp) * p.max_queue;
+    // the step's transaction queue: L2-resident global scratch, or (dense engine) shared memory so that the event
+    // loop fetches each instruction with one broadcast ld.shared.v4 instead of a gather + four shuffles
+    const u32 qs = sb + p.off_q;
+    uint4* q = G::DENSE ? reinterpret_cast<uint4*>(smem + (size_t)warp * p.warp_smem_bytes + p.off_q)
+                                : p.scratch + (size_t)(blockIdx.x * wpb + warp) * p.max_queue;
     const u64 qa = (u64)q;
-    const GeoT<FAST>& g = static_cast<const GeoT<FAST>&>(p.geo);
+    const GeoT<ENG>& g = static_cast<const GeoT<ENG>&>(p.geo);
     if (lane == 0) {
         mbar_init_a(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -503,7 +498,7 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
             if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
             return;
         }
-        book_from_header(b);
+        book_from_header(g, b);
         const u32 env_g = p.env_id_base + env;
         u32* slots = p.rslot + (size_t)env * p.agents_per_env;
         u32* hist_env = p.hist + (size_t)env * p.hist_env_stride;
@@ -541,8 +536,12 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
             // ---- Env::step (env.rs:116-135)
             const u64 start = b.t;
             b.trade_vol = 0;
+            if constexpr (G::DENSE) {  // the dense engine relies on t = start + i being new, increasing key times
+                if (n > p.step_size || (start <= b.max_key_time && (b.flags & (FL_HAS_ASK | FL_HAS_BID)))) b.err |= ERR_TIME_ORDER;
+            }
             // shuffle: Fisher-Yates from the back, one Philox word per position, draws made lane-parallel
-            for (u32 i = lane; i < n; i += 32) sts16(perm + 2u * i, i);
+            if constexpr (!G::DENSE)
+                for (u32 i = lane; i < n; i += 32) sts16(perm + 2u * i, i);
             for (u32 b0 = 0; b0 * 4u < n; b0 += 32) {
                 const u32 blk = b0 + lane;
                 if (blk * 4u < n) {
@@ -556,14 +555,35 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
                 }
             }
             __syncwarp();
-            for (u32 i = n; i > 1; --i) {
-                const u32 j = lds16(jarr + 2u * (i - 1));
-                const u32 x = lds16(perm + 2u * (i - 1)), y = lds16(perm + 2u * j);
-                sts16(perm + 2u * (i - 1), y);
-                sts16(perm + 2u * j, x);
+            if constexpr (G::DENSE) {  // the queue is on chip: swap the 16-byte instructions themselves
+                for (u32 i = n; i > 1; --i) {
+                    const u32 j = lds16(jarr + 2u * (i - 1));
+                    const uint4 x = lds128(qs + 16u * (i - 1)), y = lds128(qs + 16u * j);
+                    sts128(qs + 16u * (i - 1), y);
+                    sts128(qs + 16u * j, x);
+                }
+            } else {
+                for (u32 i = n; i > 1; --i) {
+                    const u32 j = lds16(jarr + 2u * (i - 1));
+                    const u32 x = lds16(perm + 2u * (i - 1)), y = lds16(perm + 2u * j);
+                    sts16(perm + 2u * (i - 1), y);
+                    sts16(perm + 2u * j, x);
+                }
             }
             __syncwarp();
             // process in shuffled order at t = start + i
+            if constexpr (G::DENSE) {
+                for (u32 i = 0; i < n; ++i) {
+                    const uint4 ev = lds128(qs + 16u * i);  // one broadcast load per instruction
+                    if (ev.x & 1u) {
+                        if (ev.x & 2u) book_apply<true, false>(g, b, EV_NEW, ev.y, 1u, ev.z, ev.w, ev.x >> 13, false, false, b.t);
+                        else book_apply<true, false>(g, b, EV_NEW, ev.y, 0u, ev.z, ev.w, ev.x >> 13, false, false, b.t);
+                    } else {
+                        book_apply<false, false>(g, b, EV_CANCEL, ev.y, 0u, 0u, 0u, 0u, false, false, b.t);
+                    }
+                    b.t += 1;
+                }
+            } else
             for (u32 i0 = 0; i0 < n; i0 += 32) {
                 const u32 cnt = min(32u, n - i0);
                 uint4 mine = make_uint4(0, 0, 0, 0);
@@ -572,10 +592,10 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
                     const u32 of = __shfl_sync(BB_FULL, mine.x, k), id = __shfl_sync(BB_FULL, mine.y, k);
                     const u32 price = __shfl_sync(BB_FULL, mine.z, k), vol = __shfl_sync(BB_FULL, mine.w, k);
                     if (of & 1u) {  // NEW: one constant-folded copy of the placement path per side
-                        if (of & 2u) book_apply<true>(g, b, EV_NEW, id, 1u, price, vol, of >> 13, false, false, b.t);
-                        else book_apply<true>(g, b, EV_NEW, id, 0u, price, vol, of >> 13, false, false, b.t);
+                        if (of & 2u) book_apply<true, false>(g, b, EV_NEW, id, 1u, price, vol, of >> 13, false, false, b.t);
+                        else book_apply<true, false>(g, b, EV_NEW, id, 0u, price, vol, of >> 13, false, false, b.t);
                     } else {
-                        book_apply<false>(g, b, EV_CANCEL, id, 0u, 0u, 0u, 0u, false, false, b.t);
+                        book_apply<false, false>(g, b, EV_CANCEL, id, 0u, 0u, 0u, 0u, false, false, b.t);
                     }
                     b.t += 1;
                 }
@@ -629,13 +649,13 @@ template <bool FAST, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(c
 // ---------------------------------------------------------------------------------------------------
 // Live market data of every book: out45[env][45] (level_2_data layout) and out8[env][8] =
 // OrderBook::level_1_data field order (orderbook.rs:287-301, touch by the `volumes` map).
-__global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParams p, u32* out45, u32* out8, u32 first_env,
-                                                  u32 n_out) {
+template <int ENG> __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParams p, u32* out45, u32* out8,
+                                                                     u32 first_env, u32 n_out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
     const u32 bar = sb + p.off_bar;
-    const GeoT<false>& g = static_cast<const GeoT<false>&>(p.geo);
+    const GeoT<ENG>& g = static_cast<const GeoT<ENG>&>(p.geo);
     if (lane == 0) {
         mbar_init_a(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -648,7 +668,7 @@ __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParam
         Book b;
         make_book(b, p, sb, env, lane);
         if (!blob_load(p, sb, env, bar, ph, lane)) return;
-        book_from_header(b);
+        book_from_header(g, b);
         u32 w0, w1;
         book_obs(g, b, 45u, &w0, &w1);
         if (out45) {
@@ -670,7 +690,8 @@ __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParam
 
 // fresh-book initialisation (OrderBook::new orderbook.rs:158-171 + Env::new env.rs:84-95)
 __global__ void k_init(unsigned char* blobs, u64 blob_stride, u32 n_envs, u32 p_total, u64 start_time, u32 trading,
-                       const u64* rng_seeds, u32* rslot, u32 agents_per_env, MomState* mom, u32 mom_per_env) {
+                       const u64* rng_seeds, u32* rslot, u32 agents_per_env, MomState* mom, u32 mom_per_env, Geo dense,
+                       u32 dense_lp, u32 dense_nwmax) {
     const u32 env = blockIdx.x;
     if (env >= n_envs) return;
     unsigned char* b = blobs + (size_t)env * blob_stride;
@@ -681,13 +702,25 @@ __global__ void k_init(unsigned char* blobs, u64 blob_stride, u32 n_envs, u32 p_
         h.trading = trading;
         h.rng_s0 = rng_seeds[2 * env];
         h.rng_s1 = rng_seeds[2 * env + 1];
+        h.free_top = dense.d_live;
         *reinterpret_cast<BookHdr*>(b) = h;
     }
-    u32* tag = reinterpret_cast<u32*>(b + 128);
-    for (u32 i = threadIdx.x; i < p_total; i += blockDim.x) {
-        tag[i] = BB_TAG_FREE;
-        tag[p_total + i] = 0;
-        tag[2 * p_total + i] = 0;
+    if (dense_lp) {  // dense engine (DenseLayout<dense_lp, dense_nwmax>): empty bitmaps, every slot free
+        const u32 off_fs = 128u + 12u * dense_lp, off_bm = off_fs + dense_lp;
+        u32* bm = reinterpret_cast<u32*>(b + off_bm);
+        for (u32 i = threadIdx.x; i < 2 * dense_nwmax; i += blockDim.x) bm[i] = 0;
+        u32* ids = reinterpret_cast<u32*>(b + 128);
+        for (u32 i = threadIdx.x; i < dense_lp; i += blockDim.x) {
+            ids[i] = BB_NIL;
+            b[off_fs + i] = (unsigned char)(i < dense.d_live ? dense.d_live - 1 - i : 0xFF);
+        }
+    } else {
+        u32* tag = reinterpret_cast<u32*>(b + 128);
+        for (u32 i = threadIdx.x; i < p_total; i += blockDim.x) {
+            tag[i] = BB_TAG_FREE;
+            tag[p_total + i] = 0;
+            tag[2 * p_total + i] = 0;
+        }
     }
     if (rslot)
         for (u32 i = threadIdx.x; i < agents_per_env; i += blockDim.x) rslot[(size_t)env * agents_per_env + i] = BB_NIL;

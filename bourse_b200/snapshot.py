@@ -77,15 +77,21 @@ def save_json(ob, path: str, pretty: bool = False) -> None:
         f.write(dumps(d, pretty))
 
 
-def load_json(path: str):
-    """`order_book_from_json` (rust/src/order_book.rs:390-398)."""
+def load_json(path: str, **kw):
+    """`order_book_from_json` (rust/src/order_book.rs:390-398).  Keyword arguments (capacities, engine selection such
+    as `price_window`) are forwarded to the OrderBook constructor."""
     from .core import OrderBook
 
     with open(path) as f:
         d = json.load(f)
     c = dict_to_columns(d)
     n, m = len(c["side"]), len(c["tr_t"])
-    ob = OrderBook(d["t"], d["tick_size"], d["trading"], max_orders=max(1 << 18, 2 * n), max_trades=max(1 << 18, 2 * m))
+    kw["max_orders"] = max(kw.get("max_orders", 1 << 18), 2 * n)
+    kw["max_trades"] = max(kw.get("max_trades", 1 << 18), 2 * m)
+    ob = OrderBook(d["t"], d["tick_size"], d["trading"], **kw)
     ob._env.load_book(0, d["t"], d["trade_vol"], d["trading"], c)
     ob._t = d["t"]
     return ob
+
+
+order_book_from_json = load_json

@@ -136,3 +136,50 @@ def c5_stream(n_resting: int, n_steps: int, events_per_step: int, seed: int, mid
     t[n_resting:] += (k // events_per_step).astype(np.uint64) * np.uint64(step_size)
     out["t"] = t
     return out
+
+
+def shallow_replay_stream(n: int, seed: int, tick_size: int = 1, mid_ticks: int = 1000, half_width: int = 24,
+                          max_live: int = 120, step_size: int = 100_000, emit_every: int = 64, max_vol: int = 100) -> np.ndarray:
+    """C2-style replay stream for SHALLOW books (the dense-window engine's domain): 45% limit, 5% market, 35% cancel,
+    15% modify.  The generator tracks the ids that may still rest (issued as limit orders, not yet cancelled): cancels
+    take the oldest of them, modifies a random one, and a limit order issued while `max_live` ids are outstanding is
+    turned into a cancel, so at most `max_live` orders ever rest.  Time is strictly increasing; trading is switched
+    off for ~1% windows (limit orders then rest unmatched, N6)."""
+    from collections import deque
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.random(n)
+    vol = rng.integers(1, max_vol + 1, size=n, dtype=np.uint32)
+    side = rng.random(n) < 0.5
+    price = (rng.integers(mid_ticks - half_width, mid_ticks + half_width + 1, size=n).astype(np.uint32) * tick_size).astype(np.uint32)
+    kind = rng.integers(0, 3, size=n)
+    pick = rng.random(n)
+    toggles = {}
+    if n >= 2000:
+        for s in rng.integers(0, n - 60, size=max(1, n // 5000)):
+            toggles[int(s)] = 0
+            toggles[int(s) + 50] = 1
+    out = np.zeros(n, dtype=abi.INSTR_DTYPE)
+    fifo, issued = deque(), 0
+    for i in range(n):
+        of, oid, p, v = abi.OP_NOOP, 0, 0, int(vol[i])
+        if i in toggles:
+            of, v = abi.OP_SET_TRADING, toggles[i]
+        elif u[i] < 0.45 and len(fifo) < max_live:      # limit order
+            of, p = abi.OP_NEW | (abi.F_BID if side[i] else 0), int(price[i])
+            fifo.append(issued)
+            issued += 1
+        elif 0.45 <= u[i] < 0.50:                        # market order
+            of = abi.OP_NEW | abi.F_MARKET | (abi.F_BID if side[i] else 0)
+            issued += 1
+        elif u[i] < 0.85:                                # cancel the oldest outstanding id (also when the book is "full")
+            if fifo:
+                of, oid = abi.OP_CANCEL, fifo.popleft()
+        elif fifo:                                       # modify a random outstanding id
+            oid = fifo[int(pick[i] * len(fifo))]
+            of = abi.OP_MODIFY | (abi.F_HAS_VOL if kind[i] != 1 else 0) | (abi.F_HAS_PRICE if kind[i] != 0 else 0)
+            p = int(price[i])
+        if (i % emit_every) == emit_every - 1:
+            of |= abi.F_EMIT
+        out[i] = (i + 1 + (i // emit_every) * step_size, of, oid, p, v, i % 1000, 0)
+    return out

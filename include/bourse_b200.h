@@ -44,7 +44,8 @@ typedef enum {
 #define BB_ERR_BAD_ID     0x10u
 #define BB_ERR_GRANULE    0x20u  /* a resting price was not a multiple of price_granule */
 #define BB_ERR_CAP_STEPS  0x40u
-#define BB_ERR_CAP_LIVE   0x80u  /* MomentumAgent live-order list overflow */
+#define BB_ERR_CAP_LIVE   0x80u  /* MomentumAgent live-order list / dense engine's resting-order slots overflow */
+#define BB_ERR_TIME_ORDER 0x100u /* dense engine: a resting order arrived out of time order at its price level */
 
 #define BB_OBS_L1 9u   /* StepEnvNumpy.level_1_data layout, rust/src/step_sim_numpy.rs:300-318 */
 #define BB_OBS_L2 45u  /* StepEnvNumpy.level_2_data layout, rust/src/step_sim_numpy.rs:351-368 */
@@ -74,7 +75,17 @@ typedef struct {
     uint32_t max_queue;     /* per env instructions per step */
     uint32_t pages_smem;    /* 32-level price pages per book resident in shared memory; 0 => default */
     uint32_t pages_total;   /* total pages per book (the rest live in HBM); 0 => default */
-    uint32_t reserved[4];
+    /* Dense-window engine for shallow books (the layout BASELINE.json's north_star names: a dense tick-indexed
+     * ladder in shared memory with non-empty-level bitmaps, resting orders in shared-memory slots).  Selected
+     * when win_levels > 0; requires price_granule == 1.  Every resting price must lie in
+     * [win_lo, win_lo + win_levels) and at most live_cap orders may rest per book at any time, else the env flags
+     * BB_ERR_CAP_PAGES / BB_ERR_CAP_LIVE; resting orders must arrive in non-decreasing time per price level (always
+     * true in Env mode and for replay streams with increasing time), else BB_ERR_TIME_ORDER.  Within those limits
+     * results are bit-identical to the paged engine (win_levels == 0), which has none of these limits. */
+    uint32_t win_lo;        /* price of ladder level 0 */
+    uint32_t win_levels;    /* number of price levels; rounded up to a multiple of 32; 0 => paged engine */
+    uint32_t live_cap;      /* resident resting orders per book, <= 254; 0 => 128 */
+    uint32_t reserved[1];
 } bb_config;
 
 /* One instruction, 32 bytes; replaces Event<OrderId> (crates/order_book/src/types.rs:229-249) plus

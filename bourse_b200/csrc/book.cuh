@@ -198,6 +198,7 @@ struct Book {
     u32 env;               // env index inside the handle (cold addresses are rebuilt from it)
     u32 lane;
     u32 free_top;          // dense engine: entries on the free-slot stack
+    u32 ags;               // dense engine, k_sim: shared-space address of the agent -> slot table (u8, entry 0 unused)
     u64 tr_ptr;            // dense engine: address of the next trade record
 };
 
@@ -682,11 +683,11 @@ __device__ __forceinline__ void write_order(const Book& b, u32 id, u32 price, u3
 namespace bb {
 // IS_NEW is the compile-time specialisation for the dominant event kind (no record load, no replace state).
 // CHECK_TIME (dense engine only): the caller cannot guarantee strictly increasing time between resting inserts.
-template <bool IS_NEW, bool CHECK_TIME, class G>
+template <bool IS_NEW, bool CHECK_TIME, class G, int HINT = 0>
 __device__ __forceinline__ void book_apply(const G& g, Book& b, u32 kind, u32 id, u32 side, u32 price, u32 vol, u32 trader, bool has_p,
-                                           bool has_v, u64 t) {
+                                           bool has_v, u64 t, u32 hint = 0u) {
     if constexpr (G::DENSE) {
-        d_apply<IS_NEW, CHECK_TIME>(g, b, kind, id, side, price, vol, trader, has_p, has_v, t);
+        d_apply<IS_NEW, CHECK_TIME, HINT>(g, b, kind, id, side, price, vol, trader, has_p, has_v, t, hint);
         return;
     }
     u32 start_vol = vol, meta_keep = 0;

@@ -20,7 +20,7 @@ namespace {
 thread_local std::string g_last_error;
 
 struct SmemLayout {
-    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar, off_q;
+    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar, off_q, off_ag;
 };
 
 constexpr u32 WPB = 4;  // warps (books) per CTA
@@ -93,17 +93,21 @@ u64 splitmix_next(u64& x) {
     return z ^ (z >> 31);
 }
 
+// with_queue: k_sim on the dense engine keeps the step's transaction queue and the agents' held-order state on chip
 SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool with_queue = false) {
     SmemLayout l{};
     u32 off = align_up(h->blob_smem_bytes, 16);
     l.off_perm = off;
-    off += align_up(4u * h->cfg.max_queue + 16u, 16);  // perm + jarr (u16 each) + slack for 8-byte jarr stores
+    // perm + jarr (u16 each) + slack for 8-byte jarr stores; the on-chip queue is shuffled in place and needs no perm
+    off += align_up((with_queue ? 2u : 4u) * h->cfg.max_queue + 16u, 16);
     l.off_obs = off;
     if (with_obs) off += align_up(2u * OBS_STAGE_STEPS * h->cfg.obs_words * 4u, 16);
     l.off_instr = off;
     if (with_instr) off += 2048;
     l.off_q = off;
-    if (with_queue) off += 16u * h->cfg.max_queue;  // the dense engine keeps the step's transaction queue on chip
+    if (with_queue) off += 16u * h->cfg.max_queue + 16u;  // + one entry of padding for the one-ahead fetch
+    l.off_ag = off;
+    if (with_queue) off += align_up(5u * h->agents_per_env + 1u, 16);  // held id u32 [A], slot u8 [A + 1]
     l.off_bar = off;
     off += 32;
     l.warp_bytes = align_up(off, 128);
@@ -134,6 +138,7 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.geo.blob_stride = h->blob_stride;
     p.geo.d_win_lo = h->dgeo.d_win_lo; p.geo.d_levels = h->dgeo.d_levels; p.geo.d_live = h->dgeo.d_live;
     p.off_q = l.off_q;
+    p.off_ag = l.off_ag;
     p.max_steps = h->max_steps_padded;
     p.max_queue = h->cfg.max_queue;
     p.obs_words = h->cfg.obs_words;
@@ -551,9 +556,11 @@ int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups)
         if (total) CUDA_TRY(h, cudaMalloc(&h->rslot, ne * total * 4));
         if (mom) CUDA_TRY(h, cudaMalloc(&h->mom, ne * mom * sizeof(MomState)));
     }
+    if (h->eng >= ENG_DENSE && total > 2046) return fail(h, BB_EINVAL, "the dense engine supports at most 2046 agents per env");
     h->groups.assign(groups, groups + n_groups);
     h->agents_per_env = total;
     h->mom_groups = mom;
+    h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE);  // the on-chip agent state depends on the population
     if (total) CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
     if (mom) CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * sizeof(MomState), h->stream));
     return BB_OK;

@@ -141,8 +141,8 @@ template <class G> __device__ __forceinline__ u32 d_match(const G& g, Book& b, u
 // insert_order (side.rs:54-66) for an order that rests: append to its level's queue.  Capacity violations are
 // recorded without branching out (indices are clamped so that every access stays inside the book image).
 // CHECK_TIME: the caller cannot guarantee that time moves strictly forward between resting inserts (replay mode).
-template <bool CHECK_TIME, class G> __device__ __forceinline__ void d_insert(const G& g, Book& b, u32 side, u32 price, u64 t,
-                                                                             u32 id, u32 vol) {
+template <bool CHECK_TIME, class G> __device__ __forceinline__ u32 d_insert(const G& g, Book& b, u32 side, u32 price, u64 t,
+                                                                            u32 id, u32 vol) {
     u32 q = price - g.d_win_lo;
     if (q >= g.d_levels) {
         b.err |= ERR_CAP_PAGES;
@@ -185,6 +185,7 @@ template <bool CHECK_TIME, class G> __device__ __forceinline__ void d_insert(con
     } else {
         b.max_key_time = t;  // time is strictly increasing by construction
     }
+    return slot;
 }
 
 // slot holding order `id`, or D_NIL when the order is not resting: every lane compares four slot ids
@@ -226,13 +227,19 @@ template <class G> __device__ __forceinline__ void d_remove(Book& b, u32 slot, u
     add_side_vol(b, side, 0u - svol);
 }
 
-// process_event (orderbook.rs:782-792) on the dense book; same contract as book_apply in book.cuh
-template <bool IS_NEW, bool CHECK_TIME, class G>
+// process_event (orderbook.rs:782-792) on the dense book; same contract as book_apply in book.cuh.
+// HINT (k_sim's in-kernel agents): 0 = none; 1 = every event carries a hint; 2 = hint present iff non-zero.
+//   NEW    hint = 1 + index of the issuing agent in the launch's agent-slot table (Book::ags): the slot the order
+//          rests in is recorded there, so the agent's next "is my order still live" test is one shared-memory compare
+//   CANCEL hint = 1 + the slot the order was resting in when the agent looked: a mismatch of the slot's id means
+//          the order has left the book since (filled earlier in this step) and the cancel is a no-op
+// With HINT != 0 ids are trusted (generated in-kernel, capacity validated once per step by the caller).
+template <bool IS_NEW, bool CHECK_TIME, int HINT, class G>
 __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u32 side, u32 price, u32 vol, u32 trader, bool has_p,
-                                        bool has_v, u64 t) {
+                                        bool has_v, u64 t, u32 hint) {
     const u64 ra = b.oh + (u64)id * ORD_STRIDE;
     if (IS_NEW) {
-        if (id >= g.max_orders) {
+        if (HINT == 0 && id >= g.max_orders) {
             b.err |= ERR_CAP_ORDERS;
             return;
         }
@@ -244,7 +251,10 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
         const bool ended = filled || market;
         // Filled, or an unfilled market order: Cancelled when trading, Rejected otherwise (orderbook.rs:517-531)
         const u32 status = filled ? ST_FILLED : market ? (trading ? ST_CANCELLED : ST_REJECTED) : ST_ACTIVE;
-        if (!ended) d_insert<CHECK_TIME>(g, b, side, price, t, id, rem);
+        if (!ended) {
+            const u32 slot = d_insert<CHECK_TIME>(g, b, side, price, t, id, rem);
+            if (HINT == 1 || (HINT == 2 && hint)) sts8(b.ags + hint, slot);
+        }
         // order record; the queue links of the HBM record are not used by this engine
         const u64 kt = ended ? 0ULL : t, end_time = ended ? t : ~0ULL;
         stg64v(ra + OH_PRICE, price, rem);
@@ -254,12 +264,18 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
         b.d_trans += 1;
         return;
     }
-    if (id >= b.n_orders || id >= g.max_orders) {
+    if (HINT == 0 && (id >= b.n_orders || id >= g.max_orders)) {
         b.err |= ERR_BAD_ID;  // the reference panics (orderbook.rs:642, :749)
         return;
     }
-    const u32 slot = d_find<G>(b, id);
-    if (slot == D_NIL) return;  // not Active: cancel / modify are no-ops
+    u32 slot;
+    if (HINT == 1 || (HINT == 2 && hint)) {
+        slot = hint - 1u;
+        if (lds(b.sb + 4u * slot + G::DL::OFF_ID) != id) return;
+    } else {
+        slot = d_find<G>(b, id);
+        if (slot == D_NIL) return;  // not Active: cancel / modify are no-ops
+    }
     const u32 sa = b.sb + 4u * slot;
     const u32 link = lds(sa + G::DL::OFF_SL), svol = lds(sa + G::DL::OFF_SV);
     const u32 next = link & 0xFFu, prev = (link >> 8) & 0xFFu, q = (link >> 16) & 0x7FFFu;

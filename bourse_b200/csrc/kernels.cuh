@@ -41,7 +41,7 @@ struct KParams {
     u32 n_envs, env_id_base;
     Geo geo;  // p_total, p_smem, granule, tick, max_orders, max_trades
     u32 max_steps, max_queue, obs_words;
-    u32 warp_smem_bytes, off_perm, off_obs, off_instr, off_bar, off_q;
+    u32 warp_smem_bytes, off_perm, off_obs, off_instr, off_bar, off_q, off_ag;
     // k_apply
     const bb_instr* instrs;
     const u64* offsets;
@@ -337,6 +337,43 @@ __device__ __forceinline__ void random_agents_update(const KParams& p, const bb_
     }
 }
 
+// Dense-engine variant: the agents' held order ids (u32 [A] at `agh`) and the slot each one was last seen resting
+// in (u8 [A + 1] at Book::ags, entry 0 unused) live in shared memory for the whole launch, so "is my order still
+// Active" is a shared-memory compare of the slot's id instead of a gather from the HBM order table, and the
+// emitted instructions carry the hints described at d_apply (dense.cuh).
+template <class G>
+__device__ __forceinline__ void random_agents_update_dense(const KParams& p, const bb_agent_group& ag, const Book& b, u32 qs, Emit& e,
+                                                           u32 agh, u32 env_g, u32 step, u32 slot_base) {
+    for (u32 a0 = 0; a0 < ag.n_agents; a0 += 32) {
+        const u32 a = a0 + b.lane;
+        const bool valid = a < ag.n_agents;
+        const u32 ai = valid ? slot_base + a : 0u;
+        const uint4 r = philox4x32_10(env_g, step, slot_base + a, 0, p.seed_lo, p.seed_hi);
+        const bool active = valid && (u32_to_f32_unit(r.x) < ag.rate);
+        const u32 held = lds(agh + 4u * ai);
+        const u32 hs = lds8(b.ags + 1u + ai);
+        const bool live = held != BB_NIL && lds(b.sb + G::DL::OFF_ID + 4u * hs) == held;
+        const bool do_cancel = active && live;
+        const bool do_new = active && !live;
+        const u32 new_mask = __ballot_sync(BB_FULL, do_new);
+        const u32 act_mask = __ballot_sync(BB_FULL, active);
+        const u32 below = (1u << b.lane) - 1u;
+        const u32 id = e.next_id + __popc(new_mask & below);
+        const u32 side_bid = r.y >> 31;
+        const u32 tick = ag.tick_lo + mulhi_range(r.z, ag.tick_hi - ag.tick_lo);
+        const u32 vol = ag.vol_lo + mulhi_range(r.w, ag.vol_hi - ag.vol_lo);
+        // x: bit 0 NEW, bit 1 bid, bits 2..12 hint (NEW: 1 + agent index; CANCEL: 1 + slot), bits 13.. trader id
+        const u32 of = do_cancel ? ((hs + 1u) << 2) : (1u | (side_bid << 1) | ((ai + 1u) << 2) | (a << 13));
+        const u32 pos = e.n + __popc(act_mask & below);
+        if (active) {
+            if (pos < p.max_queue) sts128(qs + 16u * pos, make_uint4(of, do_cancel ? held : id, tick * ag.tick_size, vol));
+            sts(agh + 4u * ai, do_cancel ? BB_NIL : id);
+        }
+        e.n += __popc(act_mask);
+        e.next_id += __popc(new_mask);
+    }
+}
+
 __device__ __forceinline__ u32 warp_excl_scan(u32 v, u32 lane, u32* total) {
     u32 x = v;
 #pragma unroll
@@ -473,7 +510,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(con
     const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
     const u32 bar = sb + p.off_bar;
     const u32 perm = sb + p.off_perm;          // u16 [max_queue]
-    const u32 jarr = perm + 2u * p.max_queue;  // u16 [max_queue]
+    const u32 jarr = perm + (G::DENSE ? 0u : 2u * p.max_queue);  // u16 [max_queue] (the dense engine has no perm array)
     const u32 stage = sb + p.off_obs;          // u32 [2][OBS_STAGE_STEPS * obs_words]
     // the step's transaction queue: L2-resident global scratch, or (dense engine) shared memory so that the event
     // loop fetches each instruction with one broadcast ld.shared.v4 instead of a gather + four shuffles
@@ -501,6 +538,25 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(con
         book_from_header(g, b);
         const u32 env_g = p.env_id_base + env;
         u32* slots = p.rslot + (size_t)env * p.agents_per_env;
+        const u32 agh = sb + p.off_ag;  // dense engine: held order id per agent, u32 [agents_per_env]
+        if constexpr (G::DENSE) {
+            // bring the agents' held ids on chip and find the slot each one rests in (one pass over the slot table)
+            b.ags = agh + 4u * p.agents_per_env;
+            for (u32 a0 = 0; a0 < p.agents_per_env; a0 += 32) {
+                const u32 a = a0 + lane;
+                const u32 held = a < p.agents_per_env ? slots[a] : BB_NIL;
+                u32 hs = 0;
+                for (u32 s4 = 0; s4 < G::DL::LP; s4 += 4) {
+                    const uint4 v = lds128(b.sb + G::DL::OFF_ID + 4u * s4);
+                    hs = v.x == held ? s4 : v.y == held ? s4 + 1u : v.z == held ? s4 + 2u : v.w == held ? s4 + 3u : hs;
+                }
+                if (a < p.agents_per_env) {
+                    sts(agh + 4u * a, held);
+                    sts8(b.ags + 1u + a, hs);
+                }
+            }
+            __syncwarp();
+        }
         u32* hist_env = p.hist + (size_t)env * p.hist_env_stride;
         const u32 hist0 = lds(b.sb + HDR_NSTEPS);
         const bool staged = (hist0 & 3u) == 0;  // bulk stores need 16-byte aligned record groups
@@ -516,7 +572,8 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(con
             for (u32 gi = 0; gi < p.n_groups; ++gi) {
                 const bb_agent_group& ag = p.groups[gi];
                 if (!MOM || ag.kind == BB_GROUP_RANDOM) {
-                    random_agents_update(p, ag, b, q, e, slots, env_g, step, slot_base);
+                    if constexpr (G::DENSE) random_agents_update_dense<G>(p, ag, b, qs, e, agh, env_g, step, slot_base);
+                    else random_agents_update(p, ag, b, q, e, slots, env_g, step, slot_base);
                 } else {
                     const MomOut mo = momentum_agent_update(p, ag, b.oh, lane, best_price(g, b, 1), best_price(g, b, 0), q, e.n,
                                                             e.next_id, p.mom + (size_t)env * p.mom_groups_per_env + mi, env_g,
@@ -529,8 +586,14 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(con
                 slot_base += ag.n_agents;
             }
             if (e.n > p.max_queue) b.err |= ERR_CAP_QUEUE;
-            const u32 n = min(e.n, p.max_queue);
+            u32 n = min(e.n, p.max_queue);
             b.n_orders = e.next_id;  // create_order at submission (env.rs:173)
+            if constexpr (G::DENSE) {  // ids are validated once per step (d_apply trusts hinted events)
+                if (e.next_id > g.max_orders) {
+                    b.err |= ERR_CAP_ORDERS;
+                    n = 0;
+                }
+            }
             __syncwarp();
 
             // ---- Env::step (env.rs:116-135)
@@ -573,13 +636,17 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(con
             __syncwarp();
             // process in shuffled order at t = start + i
             if constexpr (G::DENSE) {
+                constexpr int H = MOM ? 2 : 1;  // RandomAgents always hint, MomentumAgent / NoiseAgent never do
+                uint4 nx = lds128(qs);
                 for (u32 i = 0; i < n; ++i) {
-                    const uint4 ev = lds128(qs + 16u * i);  // one broadcast load per instruction
+                    const uint4 ev = nx;             // one broadcast load per instruction, fetched one event ahead
+                    nx = lds128(qs + 16u * i + 16u);  // (the queue is padded by one entry)
+                    const u32 hint = (ev.x >> 2) & 0x7FFu;
                     if (ev.x & 1u) {
-                        if (ev.x & 2u) book_apply<true, false>(g, b, EV_NEW, ev.y, 1u, ev.z, ev.w, ev.x >> 13, false, false, b.t);
-                        else book_apply<true, false>(g, b, EV_NEW, ev.y, 0u, ev.z, ev.w, ev.x >> 13, false, false, b.t);
+                        if (ev.x & 2u) book_apply<true, false, G, H>(g, b, EV_NEW, ev.y, 1u, ev.z, ev.w, ev.x >> 13, false, false, b.t, hint);
+                        else book_apply<true, false, G, H>(g, b, EV_NEW, ev.y, 0u, ev.z, ev.w, ev.x >> 13, false, false, b.t, hint);
                     } else {
-                        book_apply<false, false>(g, b, EV_CANCEL, ev.y, 0u, 0u, 0u, 0u, false, false, b.t);
+                        book_apply<false, false, G, H>(g, b, EV_CANCEL, ev.y, 0u, 0u, 0u, 0u, false, false, b.t, hint);
                     }
                     b.t += 1;
                 }
@@ -639,6 +706,10 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(con
             sts(b.sb + HDR_NSTEPS, hist0 + p.n_steps);
         }
         sts(b.sb + HDR_STEPCTR, step);
+        if constexpr (G::DENSE) {
+            __syncwarp();
+            for (u32 a = lane; a < p.agents_per_env; a += 32) slots[a] = lds(agh + 4u * a);
+        }
         if (lane == 0) bulk_wait_all<0>();
         if (b.err && lane == 0) atomicOr(p.err_flag, b.err);
         book_to_header(g, b);

@@ -239,14 +239,14 @@ def run_gpu(args):
     h2d = len(groups) * abi.GROUP_DTYPE.itemsize
     d2h = hist_host.nbytes + 64 + n_envs * 36
     for _ in range(1):
-        env.reset(); env.set_agents(groups); env.run_agents(n_steps, SEED); env.history_all(n_steps, hist_host)
+        env.reset(); env.set_agents(groups); env.run_agents_to_host(n_steps, SEED, hist_host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         env.reset()
         env.set_agents(groups)            # host -> device: the agent population
-        env.run_agents(n_steps, SEED)     # synchronous
-        env.history_all(n_steps, hist_host)  # device -> host: every env-step's observation
+        # synchronous; device -> host: every env-step's observation, streamed out chunk by chunk while the run goes on
+        env.run_agents_to_host(n_steps, SEED, hist_host)
         st = env.stats()                  # device -> host: aggregate statistics (+ final level-1 of every env)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -285,8 +285,8 @@ def run_gpu(args):
                          "peak_source": peak_src},
             "e2e": {"value": instr_per_pass * args.steps / max_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * max_e2e / args.steps,
-                    "api": "BatchedEnv.reset/set_agents/run_agents/history_all/stats (C ABI bb_*)", "obs_checksum": checksum},
-            "gpu_launches": 2 * args.steps, "clocks": clocks,
+                    "api": "BatchedEnv.reset/set_agents/run_agents_to_host/stats (C ABI bb_reset, bb_set_agents, bb_run_agents_to_host, bb_stats)", "obs_checksum": checksum},
+            "gpu_launches": 2 * args.steps, "clocks": clocks,   # timed region: k_init + k_sim per pass
             # sanity: host wall clock over the timed loop (includes the untimed L2 flushes); must be >= the event total
             "wall_ms_timed_loop": wall_ms, "event_ms_timed_loop": total_ms,
         }

@@ -161,6 +161,16 @@ class BatchedEnv:
         if sync:
             self.synchronize()
 
+    def run_agents_to_host(self, n_steps: int, seed: int, out: typing.Optional[np.ndarray] = None,
+                           chunk_steps: int = 0) -> np.ndarray:
+        """`run_agents` with the observation history streamed into `out[n_envs, n_steps, obs_words]` (host memory,
+        ideally pinned) while the simulation runs; returns `out`."""
+        if out is None:
+            out = np.empty((self.n_envs, n_steps, self.obs_words), dtype=np.uint32)
+        assert out.shape == (self.n_envs, n_steps, self.obs_words) and out.dtype == np.uint32 and out.flags.c_contiguous
+        self._ck(self._lib.bb_run_agents_to_host(self._h, seed, n_steps, chunk_steps, abi.ptr(out)))
+        return out
+
     # ------------------------------------------------------------------ reads
     def level_1_data(self) -> np.ndarray:
         out = np.empty((self.n_envs, 9), dtype=np.uint32)

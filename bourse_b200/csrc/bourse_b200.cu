@@ -32,7 +32,9 @@ inline u32 align_up(u32 x, u32 a) { return (x + a - 1) / a * a; }
 struct bb_handle {
     bb_config cfg;
     int sm_count = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t chunk_done = nullptr;
+    long long recorded_host = 0;  // history records per env written so far; -1 = unknown (ask the device)
     // device
     unsigned char* blobs = nullptr;
     OrderRec* ord = nullptr;
@@ -185,6 +187,7 @@ int init_books(bb_handle* h) {
     for (auto& q : h->queue) q.clear();
     std::fill(h->n_orders_host.begin(), h->n_orders_host.end(), 0);
     h->mirror_dirty = false;
+    h->recorded_host = 0;
     return BB_OK;
 }
 
@@ -261,6 +264,8 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     }
 #undef LAUNCH_APPLY
     CUDA_TRY(h, cudaGetLastError());
+    if (mode == MODE_ENV && h->recorded_host >= 0) h->recorded_host += n_steps;
+    else h->recorded_host = -1;
     return BB_OK;
 }
 
@@ -391,6 +396,8 @@ int bb_destroy(bb_handle* h) {
     cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch);
     if (h->h_instrs) cudaFreeHost(h->h_instrs);
     if (h->h_offsets) cudaFreeHost(h->h_offsets);
+    if (h->chunk_done) cudaEventDestroy(h->chunk_done);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return BB_OK;
@@ -574,12 +581,13 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     for (auto& q : h->queue)
         if (!q.empty()) return fail(h, BB_EINVAL, "host-queued instructions pending: call bb_step first");
     // history capacity is validated up front so the kernel can stage records without per-step checks
-    u32 recorded = 0;
-    CUDA_TRY(h, cudaMemcpy2DAsync(h->h_offsets, 8, h->blobs + offsetof(BookHdr, n_steps), h->blob_stride, 4, 1,
-                                  cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    recorded = *(u32*)h->h_offsets;
-    if ((u64)recorded + n_steps > h->max_steps_padded) return fail(h, BB_ECAP, "max_steps exceeded");
+    if (h->recorded_host < 0) {  // after a replay the number of emitted records is only known to the device
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->h_offsets, 8, h->blobs + offsetof(BookHdr, n_steps), h->blob_stride, 4, 1,
+                                      cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        h->recorded_host = *(u32*)h->h_offsets;
+    }
+    if ((u64)h->recorded_host + n_steps > h->max_steps_padded) return fail(h, BB_ECAP, "max_steps exceeded");
     KParams p;
     fill_params(h, h->lay_sim, p);
     p.n_steps = n_steps;
@@ -616,6 +624,37 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
 #undef SIM_LAUNCH
     CUDA_TRY(h, cudaGetLastError());
     h->mirror_dirty = true;
+    h->recorded_host += n_steps;
+    return BB_OK;
+}
+
+// Run n_steps env-steps and stream every env-step's observation record to HOST memory while the simulation runs:
+// the steps are launched in chunks, and chunk k's records are copied out on a second stream while chunk k+1 is being
+// simulated, so only the last chunk's copy is exposed.  host_out is [n_envs][n_steps][obs_words] u32 (pinned memory
+// recommended).  Synchronous: on return the records are in host_out.
+int bb_run_agents_to_host(bb_handle* h, uint64_t seed, uint32_t n_steps, uint32_t chunk_steps, uint32_t* host_out) {
+    CHECK_H(h);
+    if (!host_out) return fail(h, BB_EINVAL, "null argument");
+    if (n_steps == 0) return BB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->chunk_done) CUDA_TRY(h, cudaEventCreateWithFlags(&h->chunk_done, cudaEventDisableTiming));
+    if (chunk_steps == 0) chunk_steps = (n_steps + 3) / 4;
+    chunk_steps = align_up(chunk_steps, 8);  // keeps every chunk's first record 16-byte aligned for the bulk stores
+    const u32 w = h->cfg.obs_words;
+    for (u32 first = 0; first < n_steps; first += chunk_steps) {
+        const u32 n = n_steps - first < chunk_steps ? n_steps - first : chunk_steps;
+        int rc = bb_run_agents(h, seed, n);
+        if (rc) return rc;
+        const size_t rec0 = (size_t)h->recorded_host - n;  // first record of this chunk inside each env's history
+        CUDA_TRY(h, cudaEventRecord(h->chunk_done, h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_done, 0));
+        CUDA_TRY(h, cudaMemcpy2DAsync(host_out + (size_t)first * w, (size_t)n_steps * w * 4, h->hist + rec0 * w,
+                                      h->hist_env_stride * 4, (size_t)n * w * 4, h->cfg.n_envs, cudaMemcpyDeviceToHost,
+                                      h->copy_stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return BB_OK;
 }
 

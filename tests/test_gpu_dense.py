@@ -251,3 +251,54 @@ def test_snapshot_round_trip_dense(core, oracle, tmp_path):
     ob = oracle.OrderBook(0, 1)
     ob.replay(s, obs_cap=len(s))
     assert a.get_orders() == ob.get_orders() and a.get_trades() == ob.get_trades()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(price_window=(0, 192))], ids=["paged", "dense"])
+def test_run_agents_to_host_streams_the_same_history(core, kw):
+    """bb_run_agents_to_host (chunked launches, records copied out while the next chunk runs) == bb_run_agents followed
+    by bb_history_all, including a chunk size that does not divide the run."""
+    groups = workloads.c3_groups()
+
+    def make():
+        e = core.BatchedEnv(24, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1, max_orders=4096, max_trades=8192, max_steps=64,
+                            max_queue=128, **kw)
+        e.set_agents(groups)
+        return e
+    a, b = make(), make()
+    a.run_agents(44, 5)
+    ref = a.history_all(44)
+    out = b.run_agents_to_host(44, 5, chunk_steps=16)
+    assert np.array_equal(out, ref) and np.array_equal(b.history_all(44), ref)
+    assert a.stats() == b.stats()
+    # a second streamed run continues the same history
+    a.run_agents(20, 5)
+    out2 = b.run_agents_to_host(20, 5)
+    assert np.array_equal(out2, a.history_all(64)[:, 44:])
+
+
+def test_host_instructions_between_agent_launches_dense(core):
+    """The agents' on-chip slot table is rebuilt at every launch: orders cancelled / replaced from the host between two
+    agent launches (which moves them to other slots or off the book) must be seen exactly as on the paged engine."""
+    groups = workloads.c3_groups()
+
+    def run(**kw):
+        e = core.BatchedEnv(4, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=4096, max_trades=8192, max_steps=64,
+                            max_queue=128, **kw)
+        e.set_agents(groups)
+        e.run_agents(12, 3)
+        for env in range(4):
+            o = e.orders_arrays(env)
+            act = np.flatnonzero(o["status"] == 1)
+            assert len(act) >= 6
+            ids = act[:: max(1, len(act) // 6)][:6]
+            e.submit([abi.ACT_CANCEL] * 2, order_id=ids[:2], env=[env] * 2)
+            e.submit([abi.ACT_MODIFY] * 2, order_id=ids[2:4], price=o["price"][ids[2:4]], vol=[7, 9], env=[env] * 2)
+            e.submit([abi.ACT_MODIFY] * 2, order_id=ids[4:6], vol=[1, 2], env=[env] * 2, flags=[abi.F_HAS_VOL] * 2)
+        e.step(1)
+        e.run_agents(20, 3)
+        assert not e.env_errors().any()
+        return e
+    a, b = run(), run(price_window=(0, 192))
+    assert np.array_equal(a.history_all(33), b.history_all(33))
+    for env in range(4):
+        assert a.get_trades(env) == b.get_trades(env) and a.get_orders(env) == b.get_orders(env)

@@ -299,6 +299,115 @@ def run_gpu(args):
     return 0
 
 
+def run_gpu_other(args):
+    """Secondary workloads of BASELINE.json (not the headline line): --workload c4 | c5, one GPU's shard per rank.
+    c4: 8192 envs x (40+40 RandomAgents + 20-trader MomentumAgent) x 1000 env-steps, level-2 record per env-step.
+    c5: 128 books x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 events per book with a
+        30% cancel/modify rate, replayed from device memory (timed)."""
+    import torch
+    import torch.distributed as dist
+
+    from bourse_b200 import abi, core, workloads
+    from bourse_b200.sharding import gather_stats, shard_range
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if args.workload == "c4":
+        per_gpu = args.envs if args.envs != N_ENVS_PER_GPU else 8192
+        base, n_envs = shard_range(per_gpu * world, world, rank)
+        groups, obs, n_steps = workloads.c4_groups(), abi.OBS_L2, args.sim_steps
+        env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=args.max_orders,
+                              max_trades=args.max_trades, max_steps=n_steps, max_queue=256)
+        env.set_agents(groups)
+        env.set_stream(stream.cuda_stream)
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                barrier()
+            env.reset()
+            if i >= args.warmup:
+                ev[i - args.warmup][0].record(stream)
+            env.run_agents(n_steps, 7, sync=False)
+            if i >= args.warmup:
+                ev[i - args.warmup][1].record(stream)
+            flush.fill_(1)
+        ext = 0
+        name = (f"C4 shard: {per_gpu} envs/GPU x (40+40 RandomAgents + 20-trader MomentumAgent) x {n_steps} env-steps, "
+                "level-2 (45 x u32) record per env-step, paged engine")
+    else:
+        per_gpu = args.envs if args.envs != N_ENVS_PER_GPU else 128
+        base, n_envs = shard_range(per_gpu * world, world, rank)
+        n_rest, n_steps, per_step, n_distinct = 1_000_000, 100, 10_000, 8
+        obs = abi.OBS_L2
+        streams = [workloads.c5_stream(n_rest, n_steps, per_step, seed=100 + i) for i in range(n_distinct)]
+        dev = torch.device("cuda", local)
+        reps = (n_envs + n_distinct - 1) // n_distinct
+        d1 = torch.from_numpy(np.concatenate([x[:n_rest] for x in streams]).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_envs].contiguous()
+        d2 = torch.from_numpy(np.concatenate([x[n_rest:] for x in streams]).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_envs].contiguous()
+        o1 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_rest
+        o2 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
+        env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=1_800_000,
+                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, pages_smem=10, pages_total=192)
+        env.set_stream(stream.cuda_stream)
+        torch.cuda.synchronize()
+        pre_stats = None
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                barrier()
+            env.reset()
+            env.replay_device(d1.data_ptr(), o1.data_ptr())      # untimed: build the 1M-order book
+            if pre_stats is None:
+                env.synchronize(); pre_stats = env.stats()
+            if i >= args.warmup:
+                ev[i - args.warmup][0].record(stream)
+            env.replay_device(d2.data_ptr(), o2.data_ptr())
+            if i >= args.warmup:
+                ev[i - args.warmup][1].record(stream)
+            flush.fill_(1)
+        ext = n_envs * n_steps * per_step
+        name = (f"C5 shard: {per_gpu} books/GPU x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 "
+                "events per book (15% cancel, 15% modify, 60% limit within +-32 ticks, 10% market), level-2 record per step, "
+                "replayed from device memory; paged engine with HBM-resident price pages")
+    barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    stats = env.stats()
+    if stats["error_envs"]:
+        raise SystemExit(f"device flagged errors in {stats['error_envs']} envs")
+    if args.workload == "c5":  # only the timed phase counts
+        stats = {k: (stats[k] - pre_stats[k] if k in ("instructions", "orders_created", "trades", "traded_volume", "transitions", "env_steps") else stats[k]) for k in stats}
+        stats["env_steps"] = n_envs * n_steps
+    agg = gather_stats(stats, sum(ms), stats["l1_checksum"], device="cuda")
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        k_ms = sum(ms) / len(ms)
+        alg = workloads.algorithmic_bytes(stats, obs, ext)
+        print(json.dumps({
+            "metric": METRIC, "value": agg["instructions"] * args.steps / (agg["elapsed_ms_max"] * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": agg["elapsed_ms_max"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": {"workload": name},
+            "env_steps_per_sec": agg["env_steps"] * args.steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
+            "trades_per_pass": agg["trades"],
+            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim" if args.workload == "c4" else "k_apply",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,11 +420,14 @@ def main():
     ap.add_argument("--max-trades", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default="dense", choices=["dense", "paged"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"], help="c3 = the headline line; c4 / c5 = secondary configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "c3":
+        return run_gpu_other(args)
     return run_gpu(args)
 
 

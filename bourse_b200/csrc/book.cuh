@@ -135,6 +135,9 @@ __device__ __forceinline__ void stg128(u64 a, u32 x, u32 y, u32 z, u32 w) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
+// fire-and-forget pull of one 32-byte sector towards L2 (deep books: order records are DRAM-cold when first touched)
+__device__ __forceinline__ void prefetch_l2(u64 a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+
 // byte offsets inside records
 #define OH_PRICE 0u
 #define OH_VOL 4u
@@ -166,6 +169,7 @@ struct Geo {
     u64 blob_stride;
     // dense-window engine (dense.cuh): first price of the window, number of levels, number of order slots
     u32 d_win_lo, d_levels, d_live;
+    u32 pc_off;       // paged engine: offset (from the warp's shared-memory base) of the 128-entry page lookup cache
 };
 template <u32 LP_, u32 NWMAX_> struct DenseLayout;
 // Compile-time engine selection.
@@ -196,6 +200,7 @@ struct Book {
     u32 tag_lane;          // shared-space address of this lane's page tag: sb + 128 + 4 * lane
     u64 oh;                // global address of this env's order slab
     u32 env;               // env index inside the handle (cold addresses are rebuilt from it)
+    u64 blob;              // global address of this env's book blob (HBM-resident pages of the generic geometry)
     u32 lane;
     u32 free_top;          // dense engine: entries on the free-slot stack
     u32 ags;               // dense engine, k_sim: shared-space address of the agent -> slot table (u8, entry 0 unused)
@@ -236,7 +241,7 @@ template <class G> __device__ __forceinline__ PageS page_s(const G& g, const Boo
     return PageS{b.sb + page_off(g, slot)};
 }
 template <class G> __device__ __forceinline__ PageG page_g(const G& g, const Book& b, u32 slot) {
-    return PageG{g.blobs_base + (u64)b.env * g.blob_stride + page_off(g, slot)};
+    return PageG{b.blob + page_off(g, slot)};
 }
 // (vol, cnt) of a level of any page; for the cold observation paths where the slot may differ per lane
 template <class G> __device__ __forceinline__ uint2 level_pair_any(const G& g, const Book& b, u32 slot, u32 l) {
@@ -265,11 +270,26 @@ template <class G> __device__ __forceinline__ bool to_level(const G& g, u32 pric
 }
 
 // ---- page directory -----------------------------------------------------------------------------
+// The generic geometry (hundreds of pages per book) keeps a 128-entry direct-mapped lookup cache in front of the
+// associative directory search: entry (tag & 127) holds the slot that tag was last found in.  The tag array stays
+// authoritative (a cached slot is used only if its tag still matches), so stale entries are harmless and the cache
+// is never persisted.  A deep book's live pages are consecutive page keys, which map to distinct entries.
+#define PCACHE_ENTRIES 128u
 template <class G> __device__ __forceinline__ u32 find_page(const G& g, const Book& b, u32 side, u32 pkey) {
     const u32 want = (pkey << 1) | side;
+    u32 ca = 0;
+    if constexpr (!G::FAST) {
+        ca = b.sb + g.pc_off + (want & (PCACHE_ENTRIES - 1u));
+        const u32 s = lds8(ca);
+        if (lds(tag_addr(b, s)) == want) return s;
+    }
     for (u32 base = 0; base < ptot(g); base += 32) {
         const u32 m = __ballot_sync(BB_FULL, lds(b.tag_lane + 4u * base) == want);
-        if (m) return base + __ffs(m) - 1;
+        if (m) {
+            const u32 slot = base + __ffs(m) - 1;
+            if constexpr (!G::FAST) sts8(ca, slot);
+            return slot;
+        }
     }
     return BB_NIL;
 }
@@ -282,6 +302,7 @@ template <class G> __device__ __forceinline__ u32 alloc_page(const G& g, Book& b
         if (m) {
             const u32 slot = base + __ffs(m) - 1;
             sts(tag_addr(b, slot), (pkey << 1) | side);
+            if constexpr (!G::FAST) sts8(b.sb + g.pc_off + (((pkey << 1) | side) & (PCACHE_ENTRIES - 1u)), slot);
             sts(vmap_addr(g, b, slot), 0);
             sts(qmap_addr(g, b, slot), 0);
             return slot;
@@ -615,6 +636,7 @@ template <class G, class P> __device__ __forceinline__ bool fill_one(const G& g,
             emptied = true;
         } else {
             pst(pr, PG_HEAD(l), nxt);
+            if constexpr (!G::FAST) prefetch_l2(b.oh + (u64)nxt * ORD_STRIDE);  // the new head is what the next fill reads
             stg32(b.oh + (u64)nxt * ORD_STRIDE + OH_PREV, BB_NIL);
         }
         *released = level_remove(g, b, o, slot, pr, l, tv);

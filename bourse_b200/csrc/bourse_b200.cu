@@ -20,7 +20,7 @@ namespace {
 thread_local std::string g_last_error;
 
 struct SmemLayout {
-    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar, off_q, off_ag;
+    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar, off_q, off_ag, off_pc;
 };
 
 constexpr u32 WPB = 4;  // warps (books) per CTA
@@ -112,6 +112,9 @@ SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool 
     if (with_queue) off += align_up(5u * h->agents_per_env + 1u, 16);  // held id u32 [A], slot u8 [A + 1]
     l.off_bar = off;
     off += 32;
+    l.off_pc = off;
+    // page lookup cache of the generic geometry (book.cuh find_page); FAST handles run the generic k_snapshot too
+    if (h->eng < ENG_DENSE) off += PCACHE_ENTRIES;
     l.warp_bytes = align_up(off, 128);
     return l;
 }
@@ -141,6 +144,7 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.geo.d_win_lo = h->dgeo.d_win_lo; p.geo.d_levels = h->dgeo.d_levels; p.geo.d_live = h->dgeo.d_live;
     p.off_q = l.off_q;
     p.off_ag = l.off_ag;
+    p.geo.pc_off = l.off_pc;
     p.max_steps = h->max_steps_padded;
     p.max_queue = h->cfg.max_queue;
     p.obs_words = h->cfg.obs_words;

@@ -69,11 +69,20 @@ __device__ __forceinline__ u64 keep64(u64 v) {
     return r;
 }
 
+// page lookup cache of the generic paged geometry: every entry must name a valid slot (0 is always one)
+template <class G> __device__ __forceinline__ void pcache_init(const G& g, u32 sb, u32 lane) {
+    if constexpr (!G::FAST && !G::DENSE) {
+        sts(sb + g.pc_off + 4u * lane, 0u);
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ void make_book(Book& b, const KParams& p, u32 sb, u32 env, u32 lane) {
     b.sb = sb;
     b.tag_lane = keep32(sb + 128u + 4u * lane);
     b.oh = keep64((u64)(p.ord + (size_t)env * p.geo.max_orders));
     b.env = env;
+    b.blob = keep64((u64)(p.blobs + (size_t)env * p.blob_stride));
     b.lane = lane;
 }
 
@@ -165,7 +174,8 @@ template <bool CT, class G> __device__ __forceinline__ void apply_instr(const G&
     }
 }
 
-template <int MODE, int ENG> __global__ void __launch_bounds__(128, 7) k_apply(const __grid_constant__ KParams p) {
+// the generic paged geometry is shared-memory limited to <= 5 CTAs per SM anyway: give it the registers
+template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_apply(const __grid_constant__ KParams p) {
     typedef GeoT<ENG> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -183,6 +193,7 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, 7) k_apply(c
     fence_proxy_async();
     __syncwarp();
     u32 ph_blob = 0, ph_c0 = 0, ph_c1 = 0;
+    pcache_init(g, sb, lane);
 
     for (u32 env = blockIdx.x * wpb + warp; env < p.n_envs; env += gridDim.x * wpb) {
         Book b;
@@ -217,6 +228,15 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, 7) k_apply(c
                 }
                 ph ^= 1u;
                 const u32 cnt = min(32u, n - i0);
+                if constexpr (!G::DENSE) {
+                    // one lane per instruction of the batch: start pulling the order record a cancel / modify targets
+                    // towards L2 now, so that its DRAM latency overlaps the events queued ahead of it
+                    if (lane < cnt) {
+                        const u64 w = lds64(chunk + buf * 1024u + 32u * lane + 8u);  // op_flags | order_id << 32
+                        const u32 op = (u32)w & BB_OP_MASK, tid = (u32)(w >> 32);
+                        if ((op == BB_OP_CANCEL || op == BB_OP_MODIFY) && tid < g.max_orders) prefetch_l2(b.oh + (u64)tid * ORD_STRIDE);
+                    }
+                }
                 for (u32 k = 0; k < cnt; ++k) {
                     const uint4 x = lds128(chunk + buf * 1024u + 32u * k), y = lds128(chunk + buf * 1024u + 32u * k + 16u);
                     const u64 t = ((u64)x.y << 32) | x.x;
@@ -503,7 +523,7 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     return out;
 }
 
-template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(const __grid_constant__ KParams p) {
+template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __grid_constant__ KParams p) {
     typedef GeoT<ENG> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -527,6 +547,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, 7) k_sim(con
     __syncwarp();
     u32 ph_blob = 0;
     const u32 stage_words = OBS_STAGE_STEPS * p.obs_words;
+    pcache_init(g, sb, lane);
 
     for (u32 env = blockIdx.x * wpb + warp; env < p.n_envs; env += gridDim.x * wpb) {
         Book b;
@@ -734,6 +755,7 @@ template <int ENG> __global__ void __launch_bounds__(128) k_snapshot(const __gri
     fence_proxy_async();
     __syncwarp();
     u32 ph = 0;
+    pcache_init(g, sb, lane);
     for (u32 i = blockIdx.x * wpb + warp; i < n_out; i += gridDim.x * wpb) {
         const u32 env = first_env + i;
         Book b;

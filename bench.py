@@ -330,7 +330,7 @@ def run_gpu_other(args):
         base, n_envs = shard_range(per_gpu * world, world, rank)
         groups, obs, n_steps = workloads.c4_groups(), abi.OBS_L2, args.sim_steps
         env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=args.max_orders,
-                              max_trades=args.max_trades, max_steps=n_steps, max_queue=256)
+                              max_trades=args.max_trades, max_steps=n_steps, max_queue=128)
         env.set_agents(groups)
         env.set_stream(stream.cuda_stream)
         for i in range(args.warmup + args.steps):
@@ -393,6 +393,20 @@ def run_gpu_other(args):
         peak, peak_src = measured_peak_gbs()
         k_ms = sum(ms) / len(ms)
         alg = workloads.algorithmic_bytes(stats, obs, ext)
+        cpu = None
+        if world == 1 and not args.no_cpu:   # the reference's algorithm (oracle port) on the host cores, bounded sample
+            from oracle import oracle as orc
+            orc.build()
+            cores = host_cores()
+            if args.workload == "c4":
+                r = orc.bench_agents(128 * cores, cores, n_steps, 7, groups, keyed=False, start_time=0, tick_size=1, step_size=1_000_000)
+                cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{128 * cores} envs x {n_steps} env-steps of the C4 population, one env per core at a time ({r['seconds']:.2f} s)"}
+            else:
+                r = orc.bench_replay_suffix(cores, 1, streams[0], n_rest)
+                cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{cores} books (one per core), each pre-loaded with {n_rest} resting orders (untimed) and then fed the "
+                                 f"{n_steps * per_step} events of one C5 stream, all threads together ({r['seconds']:.2f} s)"}
         print(json.dumps({
             "metric": METRIC, "value": agg["instructions"] * args.steps / (agg["elapsed_ms_max"] * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": agg["elapsed_ms_max"] / args.steps, "higher_is_better": True,
@@ -401,7 +415,8 @@ def run_gpu_other(args):
             "trades_per_pass": agg["trades"],
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim" if args.workload == "c4" else "k_apply",
-                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}))
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+            **({"cpu_baseline": cpu} if cpu else {})}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -103,7 +103,7 @@ SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool 
     // perm + jarr (u16 each) + slack for 8-byte jarr stores; the on-chip queue is shuffled in place and needs no perm
     off += align_up((with_queue ? 2u : 4u) * h->cfg.max_queue + 16u, 16);
     l.off_obs = off;
-    if (with_obs) off += align_up(2u * OBS_STAGE_STEPS * h->cfg.obs_words * 4u, 16);
+    if (with_obs) off += align_up(2u * OBS_STAGE_STEPS(h->cfg.obs_words) * h->cfg.obs_words * 4u, 16);
     l.off_instr = off;
     if (with_instr) off += 2048;
     l.off_q = off;
@@ -643,7 +643,7 @@ int bb_run_agents_to_host(bb_handle* h, uint64_t seed, uint32_t n_steps, uint32_
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (!h->chunk_done) CUDA_TRY(h, cudaEventCreateWithFlags(&h->chunk_done, cudaEventDisableTiming));
-    if (chunk_steps == 0) chunk_steps = (n_steps + 3) / 4;
+    if (chunk_steps == 0) chunk_steps = (n_steps + 7) / 8;
     chunk_steps = align_up(chunk_steps, 8);  // keeps every chunk's first record 16-byte aligned for the bulk stores
     const u32 w = h->cfg.obs_words;
     for (u32 first = 0; first < n_steps; first += chunk_steps) {

@@ -19,7 +19,9 @@ namespace bb {
 #define MODE_ENV 1
 #define MAX_GROUPS 8
 #define LIVE_CAP 254  // MomentumAgent live-order list capacity per group per env
-#define OBS_STAGE_STEPS 8
+// env-steps of observation records staged in shared memory per bulk store: 8 level-1 records (288 B) or 4 level-2
+// records (720 B); both are multiples of 16 bytes and keep the staging area under 1.5 KB per book
+#define OBS_STAGE_STEPS(obs_words) ((obs_words) > 9u ? 4u : 8u)
 
 struct MomState {  // 1040 bytes per (env, momentum group)
     double momentum, last_price;
@@ -546,7 +548,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
     fence_proxy_async();
     __syncwarp();
     u32 ph_blob = 0;
-    const u32 stage_words = OBS_STAGE_STEPS * p.obs_words;
+    const u32 stage_steps = OBS_STAGE_STEPS(p.obs_words), stage_words = stage_steps * p.obs_words;
     pcache_init(g, sb, lane);
 
     for (u32 env = blockIdx.x * wpb + warp; env < p.n_envs; env += gridDim.x * wpb) {
@@ -699,7 +701,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                 const u32 dst = stage + 4u * (sbuf * stage_words + sfill * p.obs_words);
                 if (lane < p.obs_words) sts(dst + 4u * lane, w0);
                 if (lane + 32u < p.obs_words) sts(dst + 4u * (lane + 32u), w1);
-                if (++sfill == OBS_STAGE_STEPS) {
+                if (++sfill == stage_steps) {
                     __syncwarp();
                     fence_proxy_async();
                     __syncwarp();
@@ -709,7 +711,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                         bulk_wait_read<1>();  // the other buffer's previous flush has released its source
                     }
                     __syncwarp();
-                    sbase += OBS_STAGE_STEPS;
+                    sbase += stage_steps;
                     sfill = 0;
                     sbuf ^= 1u;
                 }

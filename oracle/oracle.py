@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     sig("orc_sim_n_instructions", u64, vp)
     sig("orc_bench_agents", dbl, u32, u32, u64, u64, i32, u64, u32, u64, vp, u32, vp)
     sig("orc_bench_replay", dbl, u32, u32, u32, vp, u64, vp)
+    sig("orc_bench_replay_suffix", dbl, u32, u32, vp, u64, u64, vp)
     sig("orc_philox", None, u32, u32, u32, u32, u32, u32, vp)
     sig("orc_xoroshiro", None, u64, u32, vp)
     sig("orc_shuffle_perm", None, u64, u32, vp)
@@ -424,4 +425,12 @@ def bench_replay(n_books, n_threads, tick_size, instrs):
     instrs = np.ascontiguousarray(instrs, dtype=INSTR_DTYPE)
     out = np.zeros(2, np.uint64)
     secs = lib().orc_bench_replay(n_books, n_threads, tick_size, _ptr(instrs), len(instrs), _ptr(out))
+    return {"seconds": secs, "instructions": int(out[0]), "trades": int(out[1])}
+
+
+def bench_replay_suffix(n_threads, tick_size, instrs, n_pre):
+    """One book per thread: untimed replay of instrs[:n_pre], then the timed replay of the rest (all threads together)."""
+    instrs = np.ascontiguousarray(instrs, dtype=INSTR_DTYPE)
+    out = np.zeros(2, np.uint64)
+    secs = lib().orc_bench_replay_suffix(n_threads, tick_size, _ptr(instrs), n_pre, len(instrs), _ptr(out))
     return {"seconds": secs, "instructions": int(out[0]), "trades": int(out[1])}

@@ -312,6 +312,32 @@ double orc_bench_replay(uint32_t n_books, uint32_t n_threads, uint32_t tick_size
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Deep-book variant (config C5): every thread first replays the untimed prefix ins[0, n_pre) (the resting book),
+// all threads then start the timed suffix ins[n_pre, n) together; returns the slowest thread's suffix time.
+double orc_bench_replay_suffix(uint32_t n_threads, uint32_t tick_size, const orc_instr* ins, uint64_t n_pre, uint64_t n, uint64_t* out) {
+    std::atomic<uint32_t> ready(0);
+    std::atomic<uint64_t> n_tr(0);
+    std::vector<double> secs(n_threads, 0.0);
+    auto worker = [&](uint32_t i) {
+        OrderBook ob(0, tick_size, true);
+        orc_book_replay(&ob, ins, n_pre, nullptr, 0, nullptr);
+        const uint64_t tr0 = ob.trades.size();
+        ready.fetch_add(1);
+        while (ready.load() < n_threads) std::this_thread::yield();
+        const auto t0 = std::chrono::steady_clock::now();
+        orc_book_replay(&ob, ins + n_pre, n - n_pre, nullptr, 0, nullptr);
+        secs[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        n_tr += ob.trades.size() - tr0;
+    };
+    std::vector<std::thread> th;
+    for (uint32_t i = 0; i < n_threads; ++i) th.emplace_back(worker, i);
+    for (auto& x : th) x.join();
+    out[0] = (uint64_t)n_threads * (n - n_pre); out[1] = n_tr;
+    double mx = 0;
+    for (double x : secs) mx = x > mx ? x : mx;
+    return mx;
+}
+
 // ---------------------------------------------------------------- RNG probes for the known-answer tests
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
     const Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);

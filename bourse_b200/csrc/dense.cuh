@@ -40,6 +40,10 @@ template <u32 LP_, u32 NWMAX_> struct DenseLayout {
 typedef DenseLayout<128u, 8u> DenseSmall;
 typedef DenseLayout<256u, 32u> DenseLarge;
 
+// write-once streams (the trade log) are stored with the evict-first policy so they do not displace order records in L2
+__device__ __forceinline__ void stg128_cs(u64 a, u32 x, u32 y, u32 z, u32 w) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ void stg64v(u64 a, u32 x, u32 y) { asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(a), "r"(x), "r"(y) : "memory"); }
 
 template <class G> __device__ __forceinline__ u32 d_lv(const Book& b, u32 side, u32 q) { return b.sb + G::DL::OFF_LV + 16u * q + 8u * side; }
@@ -77,8 +81,8 @@ template <class G> __device__ __forceinline__ void d_next_best(Book& b, u32 side
 template <class G> __device__ __forceinline__ void d_log_trade(const G& g, Book& b, u64 t, u32 passive_bid, u32 price, u32 vol,
                                                                u32 active, u32 passive) {
     if (b.n_trades < g.max_trades) {
-        stg128(b.tr_ptr, (u32)t, (u32)(t >> 32), price, vol);
-        stg128(b.tr_ptr + 16u, active, passive, passive_bid, 0u);
+        stg128_cs(b.tr_ptr, (u32)t, (u32)(t >> 32), price, vol);
+        stg128_cs(b.tr_ptr + 16u, active, passive, passive_bid, 0u);
         b.tr_ptr += 32u;
     } else if (g.max_trades) {
         b.err |= ERR_CAP_TRADES;
@@ -257,6 +261,10 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
         }
         // order record; the queue links of the HBM record are not used by this engine
         const u64 kt = ended ? 0ULL : t, end_time = ended ? t : ~0ULL;
+        // 52 of the record's 64 bytes are written (the link and padding words are not): L2 therefore reads the two
+        // partially written sectors back from DRAM when it evicts them (10 GB per C3 pass).  Writing both sectors
+        // in full removes those reads but was measured 4.6 % SLOWER end to end (wider stores hold their source
+        // registers longer; profiles/r01_s5_summary.md), and DRAM is at 11 % of its bandwidth either way.
         stg64v(ra + OH_PRICE, price, rem);
         stg128(ra + OH_KEYT, (u32)kt, (u32)(kt >> 32), status | (side ? META_BID : 0u), vol);
         stg128(ra + OC_ARR, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));
@@ -309,7 +317,7 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
     if (!filled) d_insert<CHECK_TIME>(g, b, side, price, t, id, rem);
     stg64v(ra + OH_PRICE, price, rem);
     stg32(ra + OH_META, (filled ? ST_FILLED : ST_ACTIVE) | side_bit);
-    if (filled) stg64(ra + OC_END, t); else stg64(ra + OH_KEYT, t);
+    stg64(ra + (filled ? OC_END : OH_KEYT), t);
     b.d_trans += 1;
 }
 

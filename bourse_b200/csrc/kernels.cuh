@@ -660,18 +660,40 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
             // process in shuffled order at t = start + i
             if constexpr (G::DENSE) {
                 constexpr int H = MOM ? 2 : 1;  // RandomAgents always hint, MomentumAgent / NoiseAgent never do
-                uint4 nx = lds128(qs);
-                for (u32 i = 0; i < n; ++i) {
-                    const uint4 ev = nx;             // one broadcast load per instruction, fetched one event ahead
-                    nx = lds128(qs + 16u * i + 16u);  // (the queue is padded by one entry)
-                    const u32 hint = (ev.x >> 2) & 0x7FFu;
-                    if (ev.x & 1u) {
-                        if (ev.x & 2u) book_apply<true, false, G, H>(g, b, EV_NEW, ev.y, 1u, ev.z, ev.w, ev.x >> 13, false, false, b.t, hint);
-                        else book_apply<true, false, G, H>(g, b, EV_NEW, ev.y, 0u, ev.z, ev.w, ev.x >> 13, false, false, b.t, hint);
-                    } else {
-                        book_apply<false, false, G, H>(g, b, EV_CANCEL, ev.y, 0u, 0u, 0u, 0u, false, false, b.t, hint);
+                // With every event hinted the matching path has no lane-parallel step left, so it runs on LANE 0 ALONE:
+                // a warp-uniform ld/st moves 32 copies of the same bytes through the L1 data pipe (4 wavefronts for a
+                // 16-byte store), and that pipe, not instruction issue, was the busiest unit of the all-lane version
+                // (78 % vs 70 %, profiles/r01_s5_summary.md).  The book registers are re-broadcast after the loop.
+                if (MOM || lane == 0) {
+                    uint4 nx = lds128(qs);
+                    for (u32 i = 0; i < n; ++i) {
+                        const uint4 ev = nx;             // one load per instruction, fetched one event ahead
+                        nx = lds128(qs + 16u * i + 16u);  // (the queue is padded by one entry)
+                        const u32 hint = (ev.x >> 2) & 0x7FFu;
+                        if (ev.x & 1u) {
+                            if (ev.x & 2u) book_apply<true, false, G, H>(g, b, EV_NEW, ev.y, 1u, ev.z, ev.w, ev.x >> 13, false, false, b.t, hint);
+                            else book_apply<true, false, G, H>(g, b, EV_NEW, ev.y, 0u, ev.z, ev.w, ev.x >> 13, false, false, b.t, hint);
+                        } else {
+                            book_apply<false, false, G, H>(g, b, EV_CANCEL, ev.y, 0u, 0u, 0u, 0u, false, false, b.t, hint);
+                        }
+                        b.t += 1;
                     }
-                    b.t += 1;
+                }
+                if constexpr (!MOM) {
+                    __syncwarp();
+                    b.max_key_time = __shfl_sync(BB_FULL, b.max_key_time, 0);
+                    b.n_trades = __shfl_sync(BB_FULL, b.n_trades, 0);
+                    b.trade_vol = __shfl_sync(BB_FULL, b.trade_vol, 0);
+                    b.vol_ask = __shfl_sync(BB_FULL, b.vol_ask, 0);
+                    b.vol_bid = __shfl_sync(BB_FULL, b.vol_bid, 0);
+                    b.bq_ask = __shfl_sync(BB_FULL, b.bq_ask, 0);
+                    b.bq_bid = __shfl_sync(BB_FULL, b.bq_bid, 0);
+                    b.flags = __shfl_sync(BB_FULL, b.flags, 0);
+                    b.err = __shfl_sync(BB_FULL, b.err, 0);
+                    b.d_trans = __shfl_sync(BB_FULL, b.d_trans, 0);
+                    b.d_volume = __shfl_sync(BB_FULL, b.d_volume, 0);
+                    b.free_top = __shfl_sync(BB_FULL, b.free_top, 0);
+                    b.tr_ptr = __shfl_sync(BB_FULL, b.tr_ptr, 0);
                 }
             } else
             for (u32 i0 = 0; i0 < n; i0 += 32) {

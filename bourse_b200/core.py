@@ -51,13 +51,16 @@ class BatchedEnv:
 
     `price_window=(lo, hi)` selects the dense-window engine instead (include/bourse_b200.h, bb_config.win_levels):
     fastest for shallow books whose resting prices stay in [lo, hi) with at most `live_cap` (default 128, max 254)
-    resting orders per book; leaving those limits flags an env error rather than producing different results."""
+    resting orders per book; leaving those limits flags an env error rather than producing different results.
+
+    `assets=A` (> 1) groups consecutive books into multi-asset markets with MarketEnv semantics
+    (crates/step_sim/src/market_env.rs:108-121); see `bourse_b200.market`."""
 
     def __init__(self, n_envs: int, seed: int, start_time: int, tick_size: int, step_size: int, trading: bool = True, *,
                  device: int = 0, env_id_base: int = 0, obs_words: int = abi.OBS_L2, max_orders: int = 1 << 16,
                  max_trades: int = 1 << 16, max_steps: int = 1 << 12, max_queue: int = 256, pages_smem: int = 0,
                  pages_total: int = 0, price_granule: int = 0, price_window: typing.Optional[typing.Tuple[int, int]] = None,
-                 live_cap: int = 0):
+                 live_cap: int = 0, assets: int = 0):
         self._lib = abi.load()
         cfg = abi.Config()
         cfg.struct_size = C.sizeof(abi.Config)
@@ -67,6 +70,7 @@ class BatchedEnv:
         cfg.obs_words, cfg.max_orders, cfg.max_trades = obs_words, max_orders, max_trades
         cfg.max_steps, cfg.max_queue = max_steps, max_queue
         cfg.pages_smem, cfg.pages_total = pages_smem, pages_total
+        cfg.assets = assets   # > 1: books [m * assets, (m + 1) * assets) form one market (shared shuffled queue per step)
         if price_window is not None:   # dense-window engine for shallow books: prices in [lo, hi), <= live_cap resting orders
             lo, hi = price_window
             if hi <= lo:

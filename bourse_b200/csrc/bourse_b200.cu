@@ -70,6 +70,10 @@ struct bb_handle {
     std::vector<std::vector<bb_instr>> queue;
     std::vector<u64> n_orders_host;  // ids handed out so far (includes queued NEW)
     bool mirror_dirty = false;
+    // multi-asset markets (bb_config.assets > 1): per-market submission counter and host-side shuffle RNG
+    u32 assets = 1;
+    std::vector<u32> market_seq;
+    std::vector<u64> market_rng;  // Xoroshiro128** state, two words per market
     std::string err;
 };
 
@@ -96,6 +100,32 @@ u64 splitmix_next(u64& x) {
 }
 
 // with_queue: k_sim on the dense engine keeps the step's transaction queue and the agents' held-order state on chip
+// host mirror of the device's Xoroshiro128** range draw (philox.cuh xoroshiro_range): rand 0.8.5 gen_range(0..n)
+u64 rotl64_h(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
+u32 xoroshiro_range_h(u64& s0, u64& s1, u32 range) {
+    const u32 zone = (range << __builtin_clz(range)) - 1u;
+    for (;;) {
+        const u64 r = rotl64_h(s0 * 5ULL, 7) * 9ULL;
+        const u64 t = s1 ^ s0;
+        s0 = rotl64_h(s0, 24) ^ t ^ (t << 16);
+        s1 = rotl64_h(t, 37);
+        const u32 v = (u32)(r >> 32);
+        const u32 lo = v * range;
+        if (lo <= zone) return (u32)(((u64)v * range) >> 32);
+    }
+}
+
+void seed_markets(bb_handle* h) {
+    const u32 n_markets = h->cfg.n_envs / h->assets;
+    h->market_seq.assign(n_markets, 0);
+    h->market_rng.resize(2 * (size_t)n_markets);
+    for (u32 m = 0; m < n_markets; ++m) {
+        u64 x = h->cfg.seed + h->cfg.env_id_base / h->assets + m;
+        h->market_rng[2 * m] = splitmix_next(x);
+        h->market_rng[2 * m + 1] = splitmix_next(x);
+    }
+}
+
 SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool with_queue = false) {
     SmemLayout l{};
     u32 off = align_up(h->blob_smem_bytes, 16);
@@ -192,6 +222,7 @@ int init_books(bb_handle* h) {
     std::fill(h->n_orders_host.begin(), h->n_orders_host.end(), 0);
     h->mirror_dirty = false;
     h->recorded_host = 0;
+    if (h->assets > 1) seed_markets(h);
     return BB_OK;
 }
 
@@ -242,12 +273,13 @@ int ensure_instr_capacity(bb_handle* h, size_t n) {
     return BB_OK;
 }
 
-int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_offsets, u32 n_steps) {
+int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_offsets, u32 n_steps, bool host_order = false) {
     KParams p;
     fill_params(h, h->lay_apply, p);
     p.instrs = d_instrs;
     p.offsets = d_offsets;
     p.n_steps = n_steps;
+    p.host_order = host_order ? 1u : 0u;
     int grid = 0, rc;
     const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
 #define LAUNCH_APPLY(M, E)                                                                       \
@@ -324,8 +356,11 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
                                            std::to_string(prop.minor) + "); this library is built for sm_100a only");
     CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
 
+    if (cfg->assets > 1 && cfg->n_envs % cfg->assets != 0)
+        return fail(nullptr, BB_EINVAL, "n_envs must be a multiple of assets (books per market)");
     bb_handle* h = new bb_handle();
     h->cfg = *cfg;
+    h->assets = cfg->assets > 1 ? cfg->assets : 1u;
     h->sm_count = prop.multiProcessorCount;
     h->granule = cfg->price_granule ? cfg->price_granule : cfg->tick_size;
     h->p_smem = cfg->pages_smem ? cfg->pages_smem : 10u;
@@ -477,6 +512,7 @@ int bb_submit(bb_handle* h, uint64_t n, const uint32_t* env, const uint32_t* act
                 if (n_done) *n_done = r + 1;
                 continue;
         }
+        if (h->assets > 1) x.aux = h->market_seq[e / h->assets]++;  // position in the market's transaction queue
         h->queue[e].push_back(x);
         if (out_ids) out_ids[r] = id_out;
         if (n_done) *n_done = r + 1;
@@ -497,6 +533,43 @@ int bb_step(bb_handle* h, uint32_t n_steps) {
     h->h_offsets[ne] = total;
     int rc = ensure_instr_capacity(h, total + 1);
     if (rc) return rc;
+    if (h->assets > 1) {
+        // MarketEnv::step (market_env.rs:108-121): the market's queue, in submission order, is shuffled as a whole;
+        // event i of the shuffled queue runs at start + i.  Each book receives its events in that order with the
+        // offset i in bb_instr::t (k_apply's host_order path).
+        const u32 A = h->assets;
+        std::vector<bb_instr> all;
+        std::vector<u32> book;
+        std::vector<size_t> fill(A);
+        for (u32 m = 0; m < ne / A; ++m) {
+            const u32 n = h->market_seq[m];
+            if (n) {
+                all.assign(n, bb_instr{});
+                book.assign(n, 0);
+                for (u32 a = 0; a < A; ++a)
+                    for (const bb_instr& x : h->queue[m * A + a]) {
+                        all[x.aux] = x;
+                        book[x.aux] = a;
+                    }
+                u64& s0 = h->market_rng[2 * m];
+                u64& s1 = h->market_rng[2 * m + 1];
+                for (u32 i = n; i > 1; --i) {  // SliceRandom::shuffle, rand 0.8.5
+                    const u32 j = xoroshiro_range_h(s0, s1, i);
+                    std::swap(all[i - 1], all[j]);
+                    std::swap(book[i - 1], book[j]);
+                }
+                for (u32 a = 0; a < A; ++a) fill[a] = h->h_offsets[m * A + a];
+                for (u32 i = 0; i < n; ++i) {
+                    bb_instr x = all[i];
+                    x.t = i;
+                    x.aux = 0;
+                    h->h_instrs[fill[book[i]]++] = x;
+                }
+            }
+            for (u32 a = 0; a < A; ++a) h->queue[m * A + a].clear();
+            h->market_seq[m] = 0;
+        }
+    } else
     for (u32 e = 0; e < ne; ++e) {
         if (!h->queue[e].empty())
             memcpy(h->h_instrs + h->h_offsets[e], h->queue[e].data(), h->queue[e].size() * sizeof(bb_instr));
@@ -504,7 +577,7 @@ int bb_step(bb_handle* h, uint32_t n_steps) {
     }
     if (total) CUDA_TRY(h, cudaMemcpyAsync(h->d_instrs, h->h_instrs, total * sizeof(bb_instr), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_offsets, h->h_offsets, (ne + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = launch_apply(h, MODE_ENV, h->d_instrs, h->d_offsets, n_steps))) return rc;
+    if ((rc = launch_apply(h, MODE_ENV, h->d_instrs, h->d_offsets, n_steps, h->assets > 1))) return rc;
     return check_device_errors(h);
 }
 
@@ -580,6 +653,7 @@ int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups)
 int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     CHECK_H(h);
     if (h->groups.empty()) return fail(h, BB_EINVAL, "bb_set_agents has not been called");
+    if (h->assets > 1) return fail(h, BB_EINVAL, "the built-in agents are single-asset: create the handle with assets <= 1");
     if (n_steps == 0) return BB_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     for (auto& q : h->queue)

@@ -48,6 +48,7 @@ struct KParams {
     const bb_instr* instrs;
     const u64* offsets;
     u32 n_steps;
+    u32 host_order;  // MODE_ENV: instructions arrive in processing order with their time offset in bb_instr::t (markets)
     // k_sim
     u32 n_groups, agents_per_env, mom_groups_per_env;
     u32* rslot;
@@ -271,8 +272,9 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_P
                 max_id = __reduce_max_sync(BB_FULL, max_id);
                 if (max_id > b.n_orders) b.n_orders = max_id;
                 __syncwarp();
-                // (b) transactions.shuffle(rng) (env.rs:121): Fisher-Yates from the back
-                {
+                // (b) transactions.shuffle(rng) (env.rs:121): Fisher-Yates from the back.  Multi-asset markets shuffle
+                // one queue across their books (market_env.rs:114-115): the host did that, the slice is in order
+                if (!p.host_order) {
                     u64 s0 = lds64(b.sb + HDR_RNG0), s1 = lds64(b.sb + HDR_RNG1);
                     for (u32 i = mm; i > 1; --i) {
                         const u32 j = xoroshiro_range(s0, s1, i);
@@ -295,7 +297,7 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_P
                     __syncwarp();
                     for (u32 k = 0; k < cnt; ++k) {
                         const uint4 x = lds128(chunk + 32u * k), y = lds128(chunk + 32u * k + 16u);
-                        const u64 t = start + i0 + k;
+                        const u64 t = start + (p.host_order ? (((u64)x.y << 32) | x.x) : (u64)(i0 + k));
                         b.t = t;
                         apply_instr<false>(g, b, x.z, x.w, y.x, y.y, y.z, t, false);
                     }

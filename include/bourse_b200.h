@@ -85,7 +85,13 @@ typedef struct {
     uint32_t win_lo;        /* price of ladder level 0 */
     uint32_t win_levels;    /* number of price levels; rounded up to a multiple of 32; 0 => paged engine */
     uint32_t live_cap;      /* resident resting orders per book, <= 254; 0 => 128 */
-    uint32_t reserved[1];
+    /* Multi-asset markets (bourse_book::Market crates/order_book/src/market.rs:59-95, bourse_de::MarketEnv
+     * crates/step_sim/src/market_env.rs:47-135): books [m * assets, (m + 1) * assets) form market m.  The books stay
+     * independent; what a market shares is ONE transaction queue per step, shuffled as a whole, with event i of the
+     * shuffled queue executing at time start + i on its asset's book (market_env.rs:108-121).  n_envs must be a
+     * multiple of assets; market m shuffles with Xoroshiro128**(seed + env_id_base / assets + m).  0 or 1 => every
+     * book is its own Env.  The built-in agents (bb_run_agents) are single-asset and need assets <= 1. */
+    uint32_t assets;
 } bb_config;
 
 /* One instruction, 32 bytes; replaces Event<OrderId> (crates/order_book/src/types.rs:229-249) plus
@@ -98,7 +104,7 @@ typedef struct {
     uint32_t price;    /* NEW: limit price; MODIFY: new price when BB_F_HAS_PRICE */
     uint32_t vol;      /* NEW: volume; MODIFY: new volume when BB_F_HAS_VOL; SET_TRADING: 0 / 1 */
     uint32_t trader;   /* NEW: trader id */
-    uint32_t aux;      /* reserved, 0 */
+    uint32_t aux;      /* reserved, 0 (the library keeps a market's submission order here while instructions are queued) */
 } bb_instr;
 
 #define BB_OP_NOOP 0u

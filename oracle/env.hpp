@@ -104,6 +104,67 @@ public:
     Status order_status(OrderId id) const { return book.order(id).status; }  // env.rs:288-290
 };
 
+// crates/order_book/src/market.rs:59-95 (Market: an array of independent order books) and
+// crates/step_sim/src/market_env.rs:47-135 (MarketEnv): one transaction queue for all assets, shuffled as a whole;
+// event i of the shuffled queue is processed at start_time + i on its asset's book.
+// PARITY PINNED by crates/step_sim/src/market_env.rs:333-407 and crates/order_book/src/market.rs:397-574 (restated in
+// tests/test_oracle_market.py); the shuffle ORDER is unpinned like Env's (rand / rand_xoshiro, see oracle/rng.hpp).
+class MarketEnv {
+public:
+    struct MarketEvent {  // Event<MarketOrderId>, types.rs:229-249 with order_id = (asset, id)
+        uint32_t asset;
+        Event ev;
+    };
+    Nanos step_size;
+    std::vector<OrderBook> books;  // Market::order_books
+    std::vector<std::vector<Vol>> trade_vols;
+    std::vector<MarketEvent> transactions;
+    std::vector<Level2Data> level_2_data;
+    std::vector<Level2DataRecords> records;
+
+    MarketEnv(Nanos start_time, const std::vector<Price>& tick_sizes, Nanos step_size_, bool trading)  // market_env.rs:73-90
+        : step_size(step_size_) {
+        for (Price t : tick_sizes) books.emplace_back(start_time, t, trading);
+        trade_vols.resize(books.size());
+        records.resize(books.size());
+        for (auto& b : books) level_2_data.push_back(b.level_2_data());
+    }
+
+    void step(Xoroshiro128StarStar& rng) {  // market_env.rs:108-135
+        const Nanos start_time = books[0].get_time();
+        for (auto& b : books) b.reset_trade_vol();
+        std::vector<MarketEvent> tx;
+        tx.swap(transactions);
+        shuffle(rng, tx);
+        for (size_t i = 0; i < tx.size(); ++i) {
+            for (auto& b : books) b.set_time(start_time + (Nanos)i);  // Market::set_time, market.rs:113-117
+            OrderBook& b = books[tx[i].asset];
+            const Event& ev = tx[i].ev;
+            switch (ev.kind) {  // Market::process_event, market.rs:343-353
+                case EV_NEW: b.place_order(ev.order_id); break;
+                case EV_CANCEL: b.cancel_order(ev.order_id); break;
+                case EV_MODIFY: b.modify_order(ev.order_id, ev.has_price, ev.new_price, ev.has_vol, ev.new_vol); break;
+            }
+        }
+        for (auto& b : books) b.set_time(start_time + step_size);
+        for (size_t a = 0; a < books.size(); ++a) {
+            level_2_data[a] = books[a].level_2_data();
+            records[a].append_record(level_2_data[a]);
+            trade_vols[a].push_back(books[a].get_trade_vol());
+        }
+    }
+
+    OrderId place_order(uint32_t asset, Side side, Vol vol, TraderId trader, bool price_is_some, Price price) {  // :163-176
+        const OrderId id = books[asset].create_order(side, vol, trader, price_is_some, price);
+        transactions.push_back(MarketEvent{asset, Event{EV_NEW, id, false, false, 0, 0}});
+        return id;
+    }
+    void cancel_order(uint32_t asset, OrderId id) { transactions.push_back(MarketEvent{asset, Event{EV_CANCEL, id, false, false, 0, 0}}); }
+    void modify_order(uint32_t asset, OrderId id, bool has_price, Price p, bool has_vol, Vol v) {
+        transactions.push_back(MarketEvent{asset, Event{EV_MODIFY, id, has_price, has_vol, p, v}});
+    }
+};
+
 // common.rs:21-41
 static inline Price round_price_up(double p, double tick_size) {
     p = std::ceil(p / tick_size) * tick_size;

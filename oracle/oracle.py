@@ -104,6 +104,15 @@ def lib() -> C.CDLL:
     sig("orc_sim_n_instructions", u64, vp)
     sig("orc_bench_agents", dbl, u32, u32, u64, u64, i32, u64, u32, u64, vp, u32, vp)
     sig("orc_bench_replay", dbl, u32, u32, u32, vp, u64, vp)
+    sig("orc_market_new", vp, u64, u64, vp, u32, u64, i32)
+    sig("orc_market_free", None, vp)
+    sig("orc_market_book", vp, vp, u32)
+    sig("orc_market_place", i32, vp, u32, i32, u32, u32, i32, u32, vp)
+    sig("orc_market_cancel", None, vp, u32, u64)
+    sig("orc_market_modify", None, vp, u32, u64, i32, u32, i32, u32)
+    sig("orc_market_step", i32, vp)
+    sig("orc_market_n_steps", u64, vp, u32)
+    sig("orc_market_history", None, vp, u32, vp)
     sig("orc_bench_replay_suffix", dbl, u32, u32, vp, u64, u64, vp)
     sig("orc_philox", None, u32, u32, u32, u32, u32, u32, vp)
     sig("orc_xoroshiro", None, u64, u32, vp)
@@ -434,3 +443,107 @@ def bench_replay_suffix(n_threads, tick_size, instrs, n_pre):
     out = np.zeros(2, np.uint64)
     secs = lib().orc_bench_replay_suffix(n_threads, tick_size, _ptr(instrs), n_pre, len(instrs), _ptr(out))
     return {"seconds": secs, "instructions": int(out[0]), "trades": int(out[1])}
+
+
+class _AssetView(_BookView):
+    """Read-only view of one asset's book inside a MarketEnv (orders / trades / status getters)."""
+
+    def __init__(self, market, asset):
+        self._m, self._a = market, asset
+
+    def _book(self):
+        return lib().orc_market_book(self._m._h, self._a)
+
+
+class MarketEnv:
+    """bourse_de::MarketEnv (crates/step_sim/src/market_env.rs:47-300): `len(tick_sizes)` assets, one shuffled
+    transaction queue per step.  Order ids are (asset, id) pairs (MarketOrderId)."""
+
+    def __init__(self, seed, start_time, tick_sizes, step_size, trading=True):
+        ts = np.ascontiguousarray(tick_sizes, dtype=np.uint32)
+        self.n_assets = len(ts)
+        self._h = lib().orc_market_new(seed, start_time, _ptr(ts), len(ts), step_size, int(trading))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_market_free(self._h)
+            self._h = None
+
+    def asset(self, a):
+        return _AssetView(self, a)
+
+    def place_order(self, asset, bid, vol, trader_id, price=None):
+        out = C.c_uint64()
+        rc = lib().orc_market_place(self._h, asset, int(bid), vol, trader_id, int(price is not None), price or 0, C.byref(out))
+        if rc:
+            raise ValueError(f"Price {price} was not a multiple of tick-size")
+        return (asset, out.value)
+
+    def cancel_order(self, order_id): lib().orc_market_cancel(self._h, order_id[0], order_id[1])
+
+    def modify_order(self, order_id, new_price=None, new_vol=None):
+        lib().orc_market_modify(self._h, order_id[0], order_id[1], int(new_price is not None), new_price or 0,
+                                int(new_vol is not None), new_vol or 0)
+
+    def step(self):
+        if lib().orc_market_step(self._h):
+            raise IndexError("order id out of range")
+
+    def history(self, asset):
+        n = lib().orc_market_n_steps(self._h, asset)
+        out = np.zeros((n, 45), np.uint32)
+        if n:
+            lib().orc_market_history(self._h, asset, _ptr(out))
+        return out
+
+    def time(self): return lib().orc_book_time(lib().orc_market_book(self._h, 0))
+    def get_orders(self, asset): return self.asset(asset).get_orders()
+    def get_trades(self, asset): return self.asset(asset).get_trades()
+    def order_status(self, order_id): return self.asset(order_id[0]).order_status(order_id[1])
+
+    def bid_asks(self):
+        out = []
+        for a in range(self.n_assets):
+            l1 = np.zeros(8, np.uint32)
+            lib().orc_book_l1(lib().orc_market_book(self._h, a), _ptr(l1))
+            out.append((int(l1[0]), int(l1[1])))
+        return out
+
+
+class Market:
+    """bourse_book::Market (crates/order_book/src/market.rs:59-365), immediate mode: an array of oracle OrderBooks."""
+
+    def __init__(self, start_time, tick_size, trading=True):
+        self._books = [OrderBook(start_time, int(t), trading) for t in tick_size]
+        self._t = start_time
+
+    def get_order_book(self, asset): return self._books[asset]
+    def get_time(self): return self._t
+
+    def set_time(self, t):
+        self._t = t
+        for b in self._books:
+            b.set_time(t)
+
+    def enable_trading(self): [b.enable_trading() for b in self._books]
+    def disable_trading(self): [b.disable_trading() for b in self._books]
+    def bid_vols(self): return [b.bid_vol() for b in self._books]
+    def bid_best_vols(self): return [b.best_bid_vol() for b in self._books]
+    def bid_best_vol_and_orders(self): return [b.best_bid_vol_and_orders() for b in self._books]
+    def ask_vols(self): return [b.ask_vol() for b in self._books]
+    def ask_best_vols(self): return [b.best_ask_vol() for b in self._books]
+    def ask_best_vol_and_orders(self): return [b.best_ask_vol_and_orders() for b in self._books]
+    def bid_asks(self): return [b.bid_ask() for b in self._books]
+    def level_2_data(self): return np.stack([b.level_2_data() for b in self._books])
+    def order(self, order_id): return self._books[order_id[0]].get_orders()[order_id[1]]
+
+    def create_and_place_order(self, asset, bid, vol, trader_id, price=None):
+        return (asset, self._books[asset].place_order(bid, vol, trader_id, price=price))
+
+    def cancel_order(self, order_id): self._books[order_id[0]].cancel_order(order_id[1])
+
+    def modify_order(self, order_id, new_price=None, new_vol=None):
+        self._books[order_id[0]].modify_order(order_id[1], new_price=new_price, new_vol=new_vol)
+
+    def get_orders(self, asset): return self._books[asset].get_orders()
+    def get_trades(self, asset): return self._books[asset].get_trades()

@@ -260,6 +260,54 @@ void orc_sim_run(void* s, int keyed, uint64_t seed, uint32_t env_id, uint64_t n_
 }
 uint64_t orc_sim_n_instructions(void* s) { return ((SimHandle*)s)->sim.n_instructions; }
 
+// ---------------------------------------------------------------- MarketEnv (multi-asset)
+struct MarketHandle {
+    MarketEnv env;
+    Xoroshiro128StarStar rng;
+    MarketHandle(uint64_t seed, Nanos start, const std::vector<Price>& ticks, Nanos step, bool trading)
+        : env(start, ticks, step, trading), rng(Xoroshiro128StarStar::seed_from_u64(seed)) {}
+};
+void* orc_market_new(uint64_t seed, uint64_t start_time, const uint32_t* tick_sizes, uint32_t n_assets, uint64_t step_size, int trading) {
+    return new MarketHandle(seed, start_time, std::vector<Price>(tick_sizes, tick_sizes + n_assets), step_size, trading != 0);
+}
+void orc_market_free(void* m) { delete (MarketHandle*)m; }
+void* orc_market_book(void* m, uint32_t asset) { return &((MarketHandle*)m)->env.books[asset]; }  // borrowed, for orc_book_* getters
+int orc_market_place(void* m, uint32_t asset, int bid, uint32_t vol, uint32_t trader, int has_price, uint32_t price, uint64_t* out_id) {
+    try {
+        *out_id = ((MarketHandle*)m)->env.place_order(asset, bid ? BID : ASK, vol, trader, has_price != 0, price);
+        return 0;
+    } catch (const PriceError&) {
+        return -1;
+    }
+}
+void orc_market_cancel(void* m, uint32_t asset, uint64_t id) { ((MarketHandle*)m)->env.cancel_order(asset, id); }
+void orc_market_modify(void* m, uint32_t asset, uint64_t id, int has_price, uint32_t price, int has_vol, uint32_t vol) {
+    ((MarketHandle*)m)->env.modify_order(asset, id, has_price != 0, price, has_vol != 0, vol);
+}
+int orc_market_step(void* m) {
+    try {
+        MarketHandle* h = (MarketHandle*)m;
+        h->env.step(h->rng);
+        return 0;
+    } catch (const std::out_of_range&) {
+        return -2;
+    }
+}
+uint64_t orc_market_n_steps(void* m, uint32_t asset) { return ((MarketHandle*)m)->env.trade_vols[asset].size(); }
+void orc_market_history(void* m, uint32_t asset, uint32_t* out) {  // [n_steps][45], StepEnvNumpy.level_2_data layout
+    MarketHandle* h = (MarketHandle*)m;
+    const Level2DataRecords& r = h->env.records[asset];
+    const std::vector<Vol>& tv = h->env.trade_vols[asset];
+    for (size_t k = 0; k < tv.size(); ++k) {
+        uint32_t* o = out + 45 * k;
+        o[0] = tv[k]; o[1] = r.bid_price[k]; o[2] = r.ask_price[k]; o[3] = r.ask_vol[k]; o[4] = r.bid_vol[k];
+        for (int i = 0; i < LEVELS; ++i) {
+            o[5 + 4 * i + 0] = r.bid_vol_at[i][k]; o[5 + 4 * i + 1] = r.bid_n_at[i][k];
+            o[5 + 4 * i + 2] = r.ask_vol_at[i][k]; o[5 + 4 * i + 3] = r.ask_n_at[i][k];
+        }
+    }
+}
+
 // ---------------------------------------------------------------- CPU baseline
 // Runs `n_envs` independent agent-driven markets, one env per host thread at a time, `n_threads`
 // threads (SURVEY.md 8d "one env per host core across all cores").  Env `e` uses seed `seed + e`

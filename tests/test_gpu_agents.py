@@ -1,8 +1,10 @@
 """GPU suite: the persistent agents+step kernel against the oracle driven by the same Philox contract.
 RandomAgents involve only integer and f32-compare arithmetic, so the whole market history, order
-table and trade log must match bit for bit.  MomentumAgent goes through f64 tanh/exp/log/cos whose
-last-ulp behaviour may differ between CUDA and glibc; tolerance: identical results on at least 90% of
-envs, and summary statistics within 5% (stated per assertion below)."""
+table and trade log must match bit for bit.  MomentumAgent / NoiseAgent go through f64 tanh/exp/log/cos
+whose last-ulp behaviour may differ between CUDA and glibc, but a differing ulp only matters when it
+flips a probability compare or moves a price across a tick boundary (~1e-14 per draw): measured on
+B200, 96 of 96 envs x 1000 env-steps of the C4 population and 96 of 96 x 600 steps of the noise
+population are bit-identical (scripts/dbg_mom_parity.py), so these tests assert identity on EVERY env."""
 import numpy as np
 import pytest
 
@@ -91,13 +93,13 @@ def test_momentum_agents_match_oracle(core, oracle):
         tv_gpu += int(hist[e][:, 0].sum()); tv_cpu += int(h[:, 0].sum())
         n_mom += sum(1 for o in ce.get_orders() if o[7] >= 80)
     assert n_mom > 100, "momentum traders must actually trade in this config"
-    assert same >= int(0.9 * n_envs), f"only {same}/{n_envs} envs identical"          # tolerance: >= 90% identical
-    assert abs(tv_gpu - tv_cpu) <= 0.05 * tv_cpu                                       # tolerance: 5% on total traded volume
+    assert same == n_envs, f"only {same}/{n_envs} envs identical"   # bit-exact: histories and order tables of every env
+    assert tv_gpu == tv_cpu
 
 
 def test_noise_agents_match_oracle(core, oracle):
-    """NoiseAgent (noise_agent.rs:126-177) mixed with RandomAgents.  Same tolerance as the
-    MomentumAgent test: the log-normal price goes through f64 exp/log/cos."""
+    """NoiseAgent (noise_agent.rs:126-177) mixed with RandomAgents; bit-exact like the
+    MomentumAgent test (the log-normal price goes through f64 exp/log/cos)."""
     n_envs, n_steps, seed = 32, 60, 3
     groups = [core.random_group(40, (40, 60), (10, 20), 2, 0.8), core.noise_group(100, 30, 2, 0.2, 0.2, 0.1, 15, 0.0, 1.0)]
     ogroups = [oracle.random_group(40, (40, 60), (10, 20), 2, 0.8), oracle.noise_group(100, 30, 2, 0.2, 0.2, 0.1, 15, 0.0, 1.0)]
@@ -114,7 +116,7 @@ def test_noise_agents_match_oracle(core, oracle):
                     and env.get_trades(e) == ce.get_trades())
         n_noise += sum(1 for o in ce.get_orders() if o[7] >= 100)
     assert n_noise > 1000
-    assert same >= int(0.9 * n_envs), f"only {same}/{n_envs} envs identical"     # tolerance: >= 90% identical
+    assert same == n_envs, f"only {same}/{n_envs} envs identical"
 
 
 def test_noise_agents_on_empty_book_far_prices(core, oracle):
@@ -131,4 +133,4 @@ def test_noise_agents_on_empty_book_far_prices(core, oracle):
         ok += int(env.get_orders(e) == ce.get_orders() and np.array_equal(env.history(e), ce._history()))
         st = [o[1] for o in env.get_orders(e)]
         assert st[:10] == [3] * 10 and st[10:] == [1] * 10
-    assert ok >= 3
+    assert ok == 4

@@ -55,6 +55,7 @@ struct bb_handle {
     bb_instr* h_instrs = nullptr;
     size_t h_instrs_cap = 0;
     u64* h_offsets = nullptr;
+    u32* h_snap = nullptr;  // [n_envs][45] pinned: snapshots come back as ONE contiguous copy and are compacted here
     // layout
     u64 blob_stride = 0;
     u32 blob_smem_bytes = 0, p_total = 0, p_smem = 0, granule = 0, max_steps_padded = 0;
@@ -417,6 +418,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     TRY_ALLOC(cudaMalloc(&h->d_snap, ne * 45 * 4));
     TRY_ALLOC(cudaMalloc(&h->d_stats, 8 * 8));
     TRY_ALLOC(cudaMallocHost(&h->h_offsets, (ne + 1) * 8));
+    TRY_ALLOC(cudaMallocHost(&h->h_snap, ne * 45 * 4));
 #undef TRY_ALLOC
     int rc = upload_seeds(h);
     if (!rc) rc = init_books(h);
@@ -435,6 +437,7 @@ int bb_destroy(bb_handle* h) {
     cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch);
     if (h->h_instrs) cudaFreeHost(h->h_instrs);
     if (h->h_offsets) cudaFreeHost(h->h_offsets);
+    if (h->h_snap) cudaFreeHost(h->h_snap);
     if (h->chunk_done) cudaEventDestroy(h->chunk_done);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -717,11 +720,16 @@ int bb_run_agents_to_host(bb_handle* h, uint64_t seed, uint32_t n_steps, uint32_
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (!h->chunk_done) CUDA_TRY(h, cudaEventCreateWithFlags(&h->chunk_done, cudaEventDisableTiming));
-    if (chunk_steps == 0) chunk_steps = (n_steps + 7) / 8;
-    chunk_steps = align_up(chunk_steps, 8);  // keeps every chunk's first record 16-byte aligned for the bulk stores
+    // chunk_steps == 0: geometric schedule (half of what is left, at least 32 steps): few launches, and the last
+    // chunk, whose copy cannot overlap anything, is small.  Chunk sizes are multiples of 8 so that every chunk's first
+    // record stays 16-byte aligned for the bulk stores.
+    const bool geometric = chunk_steps == 0;
+    chunk_steps = align_up(chunk_steps, 8);
     const u32 w = h->cfg.obs_words;
-    for (u32 first = 0; first < n_steps; first += chunk_steps) {
-        const u32 n = n_steps - first < chunk_steps ? n_steps - first : chunk_steps;
+    for (u32 first = 0, n = 0; first < n_steps; first += n) {
+        const u32 left = n_steps - first;
+        n = geometric ? align_up(left / 2 > 32 ? left / 2 : 32, 8) : chunk_steps;
+        if (n > left) n = left;
         int rc = bb_run_agents(h, seed, n);
         if (rc) return rc;
         const size_t rec0 = (size_t)h->recorded_host - n;  // first record of this chunk inside each env's history
@@ -753,8 +761,11 @@ int bb_level1(bb_handle* h, uint32_t* out) {
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = snapshot(h, 0, h->cfg.n_envs, h->d_snap, nullptr);
     if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpy2DAsync(out, 36, h->d_snap, 180, 36, h->cfg.n_envs, cudaMemcpyDeviceToHost, h->stream));
+    // one contiguous copy into pinned memory, compacted on the host: a strided 2-D copy of 36-byte rows costs the
+    // copy engine ~0.3 us per row (1.2 ms for 4096 envs, measured), the contiguous 737 KB take ~30 us
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_snap, h->d_snap, (size_t)h->cfg.n_envs * 45 * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (size_t e = 0; e < h->cfg.n_envs; ++e) memcpy(out + 9 * e, h->h_snap + 45 * e, 36);
     return BB_OK;
 }
 

@@ -202,8 +202,8 @@ int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups)
 int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps);
 /* Same run, with every env-step's observation record (Level2DataRecords, crates/step_sim/src/data.rs:9-57; the
  * arrays StepEnvNumpy.get_market_data returns, rust/src/step_sim_numpy.rs:448-516) streamed to HOST memory while
- * the simulation runs: the steps are launched in chunks of chunk_steps (0 = n_steps / 8) and chunk k is copied
- * out on a second stream while chunk k+1 is simulated.  host_out[n_envs][n_steps][obs_words], pinned memory
+ * the simulation runs: the steps are launched in chunks of chunk_steps (0 = a geometric schedule: half of what is
+ * left, at least 32) and chunk k is copied out on a second stream while chunk k+1 is simulated.  host_out[n_envs][n_steps][obs_words], pinned memory
  * recommended.  Synchronous. */
 int bb_run_agents_to_host(bb_handle* h, uint64_t seed, uint32_t n_steps, uint32_t chunk_steps, uint32_t* host_out);
 

@@ -432,6 +432,7 @@ int bb_destroy(bb_handle* h) {
     if (!h) return BB_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     cudaFree(h->blobs); cudaFree(h->ord); cudaFree(h->tr); cudaFree(h->hist); cudaFree(h->err_flag);
     cudaFree(h->d_offsets); cudaFree(h->d_seeds); cudaFree(h->d_instrs); cudaFree(h->d_snap); cudaFree(h->d_stats);
     cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch);
@@ -731,7 +732,10 @@ int bb_run_agents_to_host(bb_handle* h, uint64_t seed, uint32_t n_steps, uint32_
         n = geometric ? align_up(left / 2 > 32 ? left / 2 : 32, 8) : chunk_steps;
         if (n > left) n = left;
         int rc = bb_run_agents(h, seed, n);
-        if (rc) return rc;
+        if (rc) {  // do not return while earlier chunks are still being copied into the caller's buffer
+            cudaStreamSynchronize(h->copy_stream);
+            return rc;
+        }
         const size_t rec0 = (size_t)h->recorded_host - n;  // first record of this chunk inside each env's history
         CUDA_TRY(h, cudaEventRecord(h->chunk_done, h->stream));
         CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_done, 0));

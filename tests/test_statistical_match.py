@@ -1,0 +1,73 @@
+"""Statistical match of agent-driven runs (BASELINE.json north_star: "statistically matched on agent-driven runs").
+
+The reference threads ONE Xoroshiro128** stream through every agent and the shuffle (crates/step_sim/src/runner.rs:46-69);
+the batched path keys Philox per (env, step, agent) instead, so individual runs differ draw for draw and only the
+distributions can agree.  Each test runs the same population both ways over many independent envs and compares the
+across-env means of per-env summary statistics with a two-sample z-test; tolerance: 5 standard errors, stated at the
+assertion.  Seeds are fixed, so the outcome is deterministic."""
+import numpy as np
+import pytest
+
+from bourse_b200 import workloads
+
+N_STEPS = 300
+
+
+def _env_summaries(hist):
+    """hist [n_envs, n_steps, >=9] (numpy level-1 layout) -> [n_envs, k] per-env summary statistics."""
+    h = hist[:, 50:, :].astype(np.float64)   # skip the warm-up from the empty book
+    both = (h[:, :, 1] > 0) & (h[:, :, 2] < 2**32 - 1)
+    spread = np.where(both, h[:, :, 2] - h[:, :, 1], np.nan)
+    mid = np.where(both, 0.5 * (h[:, :, 2] + h[:, :, 1]), np.nan)
+    return np.stack([h[:, :, 0].mean(1),            # traded volume per step
+                     np.nanmean(spread, 1), np.nanmean(mid, 1),
+                     h[:, :, 3].mean(1), h[:, :, 4].mean(1),   # resting ask / bid volume
+                     h[:, :, 5].mean(1), h[:, :, 7].mean(1),   # touch volumes
+                     h[:, :, 6].mean(1), h[:, :, 8].mean(1)], axis=1)
+
+
+NAMES = ["trade_vol/step", "spread", "mid", "ask_vol", "bid_vol", "bid_touch_vol", "ask_touch_vol", "bid_touch_n", "ask_touch_n"]
+
+
+def _assert_match(a, b, n_sigma=5.0):
+    ma, mb = a.mean(0), b.mean(0)
+    se = np.sqrt(a.var(0, ddof=1) / len(a) + b.var(0, ddof=1) / len(b))
+    z = np.abs(ma - mb) / np.maximum(se, 1e-12)
+    for name, x, y, zz in zip(NAMES, ma, mb, z):
+        assert zz <= n_sigma, f"{name}: {x:.4f} vs {y:.4f} ({zz:.1f} standard errors)"   # tolerance: 5 standard errors
+    # and the two really are different samples of a non-degenerate distribution
+    assert not np.array_equal(a, b) and (a.std(0) > 0).all()
+
+
+def _oracle_hist(oracle, groups, n_envs, keyed, seed):
+    out = []
+    for e in range(n_envs):
+        env = oracle.StepEnvNumpy(0, 0, 1, 1_000_000)
+        env.set_groups(groups)
+        # stream mode: each env is its own reference-style sim_runner seeded seed + e; keyed mode: Philox (seed, env e)
+        env.run_agents(N_STEPS, seed + (0 if keyed else e), env_id=e, keyed=keyed)
+        out.append(env._history()[:, :9])
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("groups_fn", [workloads.c3_groups, workloads.c4_groups], ids=["random", "random+momentum"])
+def test_philox_contract_matches_reference_stream_statistically(oracle, groups_fn):
+    groups = groups_fn()
+    keyed = _env_summaries(_oracle_hist(oracle, groups, 96, True, 11))
+    stream = _env_summaries(_oracle_hist(oracle, groups, 96, False, 1234))
+    _assert_match(keyed, stream)
+
+
+@pytest.mark.gpu
+def test_gpu_agents_match_reference_stream_statistically(core, oracle):
+    """The CUDA path (Philox contract, 1024 envs) against the reference-style single-stream runs of the oracle."""
+    from bourse_b200 import abi
+    groups = workloads.c3_groups()
+    env = core.BatchedEnv(1024, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1, max_orders=32768, max_trades=32768, max_steps=N_STEPS,
+                          max_queue=128, price_window=(20, 180), live_cap=128)
+    env.set_agents(groups)
+    env.run_agents(N_STEPS, 11)
+    assert not env.env_errors().any()
+    gpu = _env_summaries(env.history_all(N_STEPS))
+    stream = _env_summaries(_oracle_hist(oracle, groups, 128, False, 1234))
+    _assert_match(gpu, stream)

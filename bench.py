@@ -299,6 +299,46 @@ def run_gpu(args):
     return 0
 
 
+def run_c1(args):
+    """C1: examples/random_trades.py semantics (seed 101, 200 steps, 100 Python RandomAgent(i, 0.5, (10,100), (20,50), 2),
+    StepEnv(101, 0, tick, 100_000)) through the Python surface; wall time next to the same loop on the oracle's StepEnv.
+    A functional config: the time is the CPython agent loop plus one small kernel launch per env.step()."""
+    from bourse_b200 import core
+    from bourse_b200.step_sim import run
+    from bourse_b200.step_sim.agents import RandomAgent
+    from oracle import oracle as orc
+
+    orc.build()
+    out = {}
+    for tick in (2, 1):
+        res = {}
+        for name, mod in (("b200", core), ("oracle", orc)):
+            best = None
+            for _ in range(max(args.steps, 1)):
+                env = mod.StepEnv(101, 0, tick, 100_000)
+                agents = [RandomAgent(i, 0.5, (10, 100), (20, 50), tick) for i in range(100)]
+                t0 = time.perf_counter()
+                if name == "b200":
+                    data = run(env, agents, 200, 101)
+                else:   # same loop, oracle classes (runner asserts the product's StepEnv type)
+                    rng = np.random.default_rng(101)
+                    for _s in range(200):
+                        for a in agents:
+                            a.update(rng, env)
+                        env.step()
+                    data = env.get_market_data()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            res[name] = (best, data)
+        same = all(np.array_equal(res["b200"][1][k], res["oracle"][1][k]) for k in res["oracle"][1])
+        n_orders = len(res["b200"][1]["bid_price"])
+        out[f"tick_{tick}"] = {"b200_wall_s": res["b200"][0], "oracle_wall_s": res["oracle"][0], "market_data_identical": bool(same),
+                               "n_arrays": len(res["b200"][1]), "n_steps": n_orders}
+    print(json.dumps({"metric": "wall_s", "unit": "s", "config": {"workload": "C1: examples/random_trades.py semantics, tick sizes 2 (the file) and 1 "
+                      "(BASELINE.json), 100 Python RandomAgents x 200 steps through StepEnv"}, **out}))
+    return 0
+
+
 def run_gpu_other(args):
     """Secondary workloads of BASELINE.json (not the headline line): --workload c4 | c5, one GPU's shard per rank.
     c4: 8192 envs x (40+40 RandomAgents + 20-trader MomentumAgent) x 1000 env-steps, level-2 record per env-step.
@@ -325,6 +365,57 @@ def run_gpu_other(args):
     torch.cuda.set_stream(stream)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if args.workload == "c1":
+        return run_c1(args)
+    if args.workload == "c2":
+        # C2: replayed place/cancel/modify stream (55/5/25/15 % limit/market/cancel/modify) of 10^6 events into ONE book
+        # (--envs 1, the config as stated: a single sequential dependency chain) or into --envs books at once
+        n_books = args.envs if args.envs != N_ENVS_PER_GPU else 1
+        n_ev, n_distinct = 1_000_000, min(8, n_books)
+        streams = [workloads.replay_stream(n_ev, s, tick_size=1) for s in range(n_distinct)]
+        dev = torch.device("cuda", local)
+        reps = (n_books + n_distinct - 1) // n_distinct
+        d = torch.from_numpy(np.concatenate(streams).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_books].contiguous()
+        off = torch.arange(0, n_books + 1, dtype=torch.int64, device=dev) * n_ev
+        n_emit = int(((streams[0]["op_flags"] & abi.F_EMIT) != 0).sum())
+        env = core.BatchedEnv(n_books, 0, 0, 1, 100_000, device=local, obs_words=abi.OBS_L2, max_orders=1 << 20, max_trades=1 << 20,
+                              max_steps=n_emit + 8, max_queue=32, pages_smem=16, pages_total=64)
+        env.set_stream(stream.cuda_stream)
+        torch.cuda.synchronize()
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                barrier()
+            env.reset()
+            if i >= args.warmup:
+                ev[i - args.warmup][0].record(stream)
+            env.replay_device(d.data_ptr(), off.data_ptr())
+            if i >= args.warmup:
+                ev[i - args.warmup][1].record(stream)
+            flush.fill_(1)
+        barrier()
+        ms = [a.elapsed_time(b) for a, b in ev]
+        stats = env.stats()
+        if stats["error_envs"]:
+            raise SystemExit(f"device flagged errors in {stats['error_envs']} envs")
+        stats["env_steps"] = n_books * n_emit
+        peak, peak_src = measured_peak_gbs()
+        k_ms = sum(ms) / len(ms)
+        alg = workloads.algorithmic_bytes(stats, abi.OBS_L2, n_books * n_ev)
+        from oracle import oracle as orc
+        orc.build()
+        cores = host_cores()
+        r = orc.bench_replay(min(n_books, cores), min(n_books, cores), 1, streams[0])
+        print(json.dumps({
+            "metric": METRIC, "value": stats["instructions"] / (k_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"C2: replayed stream of {n_ev} instructions (55% limit, 5% market, 25% cancel, 15% modify; cancel/modify "
+                                   f"targets uniform over all issued ids) into each of {n_books} book(s), level-2 record every 64 events, paged engine"},
+            "orders_per_pass": stats["instructions"], "trades_per_pass": stats["trades"],
+            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "kernel": "k_apply", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+            "cpu_baseline": {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": min(n_books, cores), "kind": "port",
+                             "sample": f"the same stream into {min(n_books, cores)} book(s), one per core ({r['seconds']:.2f} s; counts every row incl. no-ops)"}}))
+        return 0
     if args.workload == "c4":
         per_gpu = args.envs if args.envs != N_ENVS_PER_GPU else 8192
         base, n_envs = shard_range(per_gpu * world, world, rank)
@@ -435,7 +526,7 @@ def main():
     ap.add_argument("--max-trades", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default="dense", choices=["dense", "paged"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"], help="c3 = the headline line; c4 / c5 = secondary configs")
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"], help="c3 = the headline line; the others are the secondary configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -138,7 +138,7 @@ SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool 
     l.off_instr = off;
     if (with_instr) off += 2048;
     l.off_q = off;
-    if (with_queue) off += 16u * h->cfg.max_queue + 16u;  // + one entry of padding for the one-ahead fetch
+    if (with_queue) off += 16u * h->cfg.max_queue + 32u;  // + two entries of padding for the one-ahead fetch
     l.off_ag = off;
     if (with_queue) off += align_up(5u * h->agents_per_env + 1u, 16);  // held id u32 [A], slot u8 [A + 1]
     l.off_bar = off;

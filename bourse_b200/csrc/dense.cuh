@@ -99,7 +99,9 @@ template <class G> __device__ __forceinline__ void d_free_slot(Book& b, u32 slot
 // match_bid / match_ask (orderbook.rs:429-487) + match_orders (:843-870) against shared-memory slots.
 // Returns the aggressor's remaining volume; the caller derives Status::Filled as (vol > 0 && remaining == 0):
 // the loop body only runs while volume is left, so that is exactly "some fill brought the volume to zero".
-template <class G> __device__ __forceinline__ u32 d_match(const G& g, Book& b, u32 side, u32 price, u32 vol, u32 id, u64 t) {
+// STEPPED (k_sim): the per-launch transition / volume counters are settled once per env-step by the caller (from the
+// trade count and the step's trade_vol) instead of once per fill.
+template <bool STEPPED, class G> __device__ __forceinline__ u32 d_match(const G& g, Book& b, u32 side, u32 price, u32 vol, u32 id, u64 t) {
     const u32 o = side ^ 1u;
     while (vol > 0u && has_best(b, o)) {
         const u32 bq = best_q(b, o);
@@ -115,8 +117,10 @@ template <class G> __device__ __forceinline__ u32 d_match(const G& g, Book& b, u
         vol -= tv;
         d_log_trade(g, b, t, o, bprice, tv, id, pid);
         b.trade_vol += tv;
-        b.d_volume += tv;
-        b.d_trans += 1;
+        if (!STEPPED) {
+            b.d_volume += tv;
+            b.d_trans += 1;
+        }
         add_side_vol(b, o, 0u - tv);
         const u64 pa = b.oh + (u64)pid * ORD_STRIDE;
         if (pvol == tv) {  // passive order Filled: leaves its slot and the head of its level
@@ -249,7 +253,7 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
         }
         const bool trading = (b.flags & FL_TRADING) != 0u;
         u32 rem = vol;
-        if (trading) rem = d_match(g, b, side, price, vol, id, t);
+        if (trading) rem = d_match<HINT != 0>(g, b, side, price, vol, id, t);
         const bool filled = vol != 0u && rem == 0u;
         const bool market = side ? (price == 0xFFFFFFFFu) : (price == 0u);  // N3
         const bool ended = filled || market;
@@ -269,7 +273,7 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
         stg128(ra + OH_KEYT, (u32)kt, (u32)(kt >> 32), status | (side ? META_BID : 0u), vol);
         stg128(ra + OC_ARR, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));
         stg32(ra + OC_TRADER, trader);
-        b.d_trans += 1;
+        if (HINT == 0) b.d_trans += 1;
         return;
     }
     if (HINT == 0 && (id >= b.n_orders || id >= g.max_orders)) {
@@ -312,7 +316,7 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
     }
     // replace_order (orderbook.rs:679-723): re-match, re-rest under key time t; never a market order (N4)
     u32 rem = vol;
-    if (b.flags & FL_TRADING) rem = d_match(g, b, side, price, vol, id, t);
+    if (b.flags & FL_TRADING) rem = d_match<HINT != 0>(g, b, side, price, vol, id, t);
     const bool filled = vol != 0u && rem == 0u;
     if (!filled) d_insert<CHECK_TIME>(g, b, side, price, t, id, rem);
     stg64v(ra + OH_PRICE, price, rem);

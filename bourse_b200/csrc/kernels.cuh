@@ -593,6 +593,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
             Emit e;
             e.n = 0;
             e.next_id = b.n_orders;
+            const u32 id0 = b.n_orders;
             u32 slot_base = 0, mi = 0;
             for (u32 gi = 0; gi < p.n_groups; ++gi) {
                 const bb_agent_group& ag = p.groups[gi];
@@ -666,11 +667,11 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                 // a warp-uniform ld/st moves 32 copies of the same bytes through the L1 data pipe (4 wavefronts for a
                 // 16-byte store), and that pipe, not instruction issue, was the busiest unit of the all-lane version
                 // (78 % vs 70 %, profiles/r01_s5_summary.md).  The book registers are re-broadcast after the loop.
+                const u32 nt0 = b.n_trades;
                 if (MOM || lane == 0) {
-                    uint4 nx = lds128(qs);
-                    for (u32 i = 0; i < n; ++i) {
-                        const uint4 ev = nx;             // one load per instruction, fetched one event ahead
-                        nx = lds128(qs + 16u * i + 16u);  // (the queue is padded by one entry)
+                    // events are fetched one ahead into alternating register quads (two inlined copies of the handler:
+                    // a single copy makes the compiler shuffle the prefetched quad through 6 moves per event)
+                    auto handle = [&](const uint4& ev) {
                         const u32 hint = (ev.x >> 2) & 0x7FFu;
                         if (ev.x & 1u) {
                             if (ev.x & 2u) book_apply<true, false, G, H>(g, b, EV_NEW, ev.y, 1u, ev.z, ev.w, ev.x >> 13, false, false, b.t, hint);
@@ -679,6 +680,14 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                             book_apply<false, false, G, H>(g, b, EV_CANCEL, ev.y, 0u, 0u, 0u, 0u, false, false, b.t, hint);
                         }
                         b.t += 1;
+                    };
+                    uint4 e0 = lds128(qs);
+                    for (u32 i = 0; i < n; i += 2) {
+                        const uint4 e1 = lds128(qs + 16u * i + 16u);  // (the queue is padded by two entries)
+                        handle(e0);
+                        if (i + 1 >= n) break;
+                        e0 = lds128(qs + 16u * i + 32u);
+                        handle(e1);
                     }
                 }
                 if constexpr (!MOM) {
@@ -697,6 +706,9 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                     b.free_top = __shfl_sync(BB_FULL, b.free_top, 0);
                     b.tr_ptr = __shfl_sync(BB_FULL, b.tr_ptr, 0);
                 }
+                // transitions of the step: one per placed order and per fill (cancels counted theirs); traded volume
+                b.d_trans += (b.n_trades - nt0) + (n ? e.next_id - id0 : 0u);
+                b.d_volume += b.trade_vol;
             } else
             for (u32 i0 = 0; i0 < n; i0 += 32) {
                 const u32 cnt = min(32u, n - i0);

@@ -130,3 +130,31 @@ def test_env_mode_batched_bit_exact(core, oracle):
         assert np.array_equal(l2[e], ce._l2()), e
         assert genv.time(e) == n_steps * 1000
     assert sum(len(ce.get_trades()) for ce in cenvs) > 100
+
+
+@pytest.mark.parametrize("tick_size", [1, 2])
+def test_adversarial_fuzz_many_books(core, oracle, tick_size):
+    """768 books, each replaying its own short ADVERSARIAL stream in one launch (tiny price / id / time domains:
+    equal-key collisions N1, zero volumes N5, market sentinels N3, trading toggles N6, every modify variant N4, prices at
+    both ends of the u32 range); every book must equal the oracle — trade log, order table, every emitted record."""
+    from .test_oracle_hypothesis import random_adversarial_stream
+
+    rng = np.random.default_rng(20 + tick_size)
+    n_books = 768
+    streams = [random_adversarial_stream(rng, int(rng.integers(1, 120)), tick_size) for _ in range(n_books)]
+    off = np.zeros(n_books + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in streams])
+    # price_granule=1: modify_order applies no tick check (N4), so with tick 2 an order may come to rest on an odd price
+    env = core.BatchedEnv(n_books, 0, 0, tick_size, 1000, obs_words=abi.OBS_L2, max_orders=128, max_trades=1024, max_steps=128,
+                          max_queue=16, pages_smem=8, pages_total=32, price_granule=1)
+    env.replay(np.concatenate(streams), off)
+    assert not env.env_errors().any()
+    n_tr = 0
+    for e in range(n_books):
+        ob = oracle.OrderBook(0, tick_size)
+        obs = ob.replay(streams[e], obs_cap=len(streams[e]))
+        assert np.array_equal(env.history(e), obs), e
+        assert env.get_orders(e) == ob.get_orders(), e
+        assert env.get_trades(e) == ob.get_trades(), e
+        n_tr += len(ob.get_trades())
+    assert n_tr > 2000

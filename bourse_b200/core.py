@@ -154,11 +154,19 @@ class BatchedEnv:
         self._ck(self._lib.bb_replay_device(self._h, C.c_void_p(d_instrs_ptr), C.c_void_p(d_offsets_ptr)))
 
     # ------------------------------------------------------------------ in-kernel agents
-    def set_agents(self, groups):
+    def set_agents(self, groups, assets=None):
+        """Define the in-kernel agent set.  `assets` (multi-asset handles only): the asset each group trades, i.e. the
+        *Market twin of the group's agent type (bb_set_agents_market)."""
         arr = np.zeros(len(groups), dtype=abi.GROUP_DTYPE)
         for i, g in enumerate(groups):
             arr[i] = g
-        self._ck(self._lib.bb_set_agents(self._h, abi.ptr(arr), len(arr)))
+        if assets is None:
+            self._ck(self._lib.bb_set_agents(self._h, abi.ptr(arr), len(arr)))
+        else:
+            a = np.ascontiguousarray(assets, dtype=np.uint32)
+            if len(a) != len(arr):
+                raise ValueError("one asset index per agent group")
+            self._ck(self._lib.bb_set_agents_market(self._h, abi.ptr(arr), abi.ptr(a), len(arr)))
 
     def run_agents(self, n_steps: int, seed: int, sync: bool = True):
         self._ck(self._lib.bb_run_agents(self._h, seed, n_steps))

@@ -20,7 +20,7 @@ namespace {
 thread_local std::string g_last_error;
 
 struct SmemLayout {
-    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar, off_q, off_ag, off_pc;
+    u32 warp_bytes, off_perm, off_obs, off_instr, off_bar, off_q, off_ag, off_pc, off_mkt;
 };
 
 constexpr u32 WPB = 4;  // warps (books) per CTA
@@ -66,6 +66,7 @@ struct bb_handle {
     SmemLayout lay_apply{}, lay_sim{}, lay_snap{};
     // agents
     std::vector<bb_agent_group> groups;
+    std::vector<u32> group_asset;  // bb_set_agents_market: asset each group trades (empty: single-asset agents)
     u32 agents_per_env = 0, mom_groups = 0;
     // host mirrors for Env mode
     std::vector<std::vector<bb_instr>> queue;
@@ -127,12 +128,14 @@ void seed_markets(bb_handle* h) {
     }
 }
 
-SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool with_queue = false) {
+SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool with_queue = false, bool market = false) {
     SmemLayout l{};
     u32 off = align_up(h->blob_smem_bytes, 16);
     l.off_perm = off;
-    // perm + jarr (u16 each) + slack for 8-byte jarr stores; the on-chip queue is shuffled in place and needs no perm
-    off += align_up((with_queue ? 2u : 4u) * h->cfg.max_queue + 16u, 16);
+    // perm + jarr (u16 each) + slack for 8-byte jarr stores; the on-chip queue is shuffled in place and needs no perm.
+    // Markets with in-kernel agents: every book derives the permutation of the WHOLE market's queue (k_sim<.., MKT>)
+    if (market) off += 4u * align_up(h->assets * h->cfg.max_queue, 8) + 16u;
+    else off += align_up((with_queue ? 2u : 4u) * h->cfg.max_queue + 16u, 16);
     l.off_obs = off;
     if (with_obs) off += align_up(2u * OBS_STAGE_STEPS(h->cfg.obs_words) * h->cfg.obs_words * 4u, 16);
     l.off_instr = off;
@@ -143,6 +146,8 @@ SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool 
     if (with_queue) off += align_up(5u * h->agents_per_env + 1u, 16);  // held id u32 [A], slot u8 [A + 1]
     l.off_bar = off;
     off += 32;
+    l.off_mkt = off;  // u32 [2][MAX_GROUPS]: the market's per-group instruction counts, double-buffered
+    if (market) off += 8u * MAX_GROUPS;
     l.off_pc = off;
     // page lookup cache of the generic geometry (book.cuh find_page); FAST handles run the generic k_snapshot too
     if (h->eng < ENG_DENSE) off += PCACHE_ENTRIES;
@@ -184,15 +189,17 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.off_obs = l.off_obs;
     p.off_instr = l.off_instr;
     p.off_bar = l.off_bar;
+    p.off_mkt = l.off_mkt;
+    p.assets = h->assets;
 }
 
-template <class K> int grid_for(bb_handle* h, K kernel, const SmemLayout& l, u32 n_items, int* grid_out) {
-    const size_t smem = (size_t)l.warp_bytes * WPB;
+template <class K> int grid_for(bb_handle* h, K kernel, const SmemLayout& l, u32 n_items, int* grid_out, u32 wpb = WPB) {
+    const size_t smem = (size_t)l.warp_bytes * wpb;
     CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WPB * 32, smem));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * 32, smem));
     if (per_sm < 1) return fail(h, BB_EINVAL, "configuration does not fit in shared memory (reduce pages_smem / max_queue)");
-    const u32 want = (n_items + WPB - 1) / WPB;
+    const u32 want = (n_items + wpb - 1) / wpb;
     const u32 cap = (u32)per_sm * (u32)h->sm_count;
     *grid_out = (int)(want < cap ? want : cap);
     if (*grid_out < 1) *grid_out = 1;
@@ -614,10 +621,17 @@ int bb_replay_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_e
     return launch_apply(h, MODE_REPLAY, d_instrs, d_env_offsets, 0);
 }
 
-int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups) {
+static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uint32_t* asset, uint32_t n_groups) {
     CHECK_H(h);
     if (n_groups > MAX_GROUPS) return fail(h, BB_EINVAL, "at most 8 agent groups");
     if (n_groups && !groups) return fail(h, BB_EINVAL, "null groups");
+    if (asset) {
+        if (h->assets < 2) return fail(h, BB_EINVAL, "bb_set_agents_market needs a handle created with assets > 1");
+        if (h->assets > WPB) return fail(h, BB_EINVAL, "in-kernel market agents support at most 4 assets per market");
+        if ((u64)h->assets * h->cfg.max_queue > 65535) return fail(h, BB_EINVAL, "assets * max_queue must stay below 65536");
+        for (u32 i = 0; i < n_groups; ++i)
+            if (asset[i] >= h->assets) return fail(h, BB_EINVAL, "agent group asset index out of range");
+    }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     u32 total = 0, mom = 0;
     for (u32 i = 0; i < n_groups; ++i) {
@@ -646,18 +660,31 @@ int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups)
     }
     if (h->eng >= ENG_DENSE && total > 2046) return fail(h, BB_EINVAL, "the dense engine supports at most 2046 agents per env");
     h->groups.assign(groups, groups + n_groups);
+    h->group_asset.clear();
+    if (asset) h->group_asset.assign(asset, asset + n_groups);
     h->agents_per_env = total;
     h->mom_groups = mom;
-    h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE);  // the on-chip agent state depends on the population
+    h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE, asset != nullptr);  // the on-chip agent state depends on the population
     if (total) CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
     if (mom) CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * sizeof(MomState), h->stream));
     return BB_OK;
 }
 
+int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups) {
+    return set_agents_impl(h, groups, nullptr, n_groups);
+}
+
+int bb_set_agents_market(bb_handle* h, const bb_agent_group* groups, const uint32_t* asset, uint32_t n_groups) {
+    if (n_groups && !asset) return fail(h, BB_EINVAL, "null asset array");
+    return set_agents_impl(h, groups, asset, n_groups);
+}
+
 int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     CHECK_H(h);
     if (h->groups.empty()) return fail(h, BB_EINVAL, "bb_set_agents has not been called");
-    if (h->assets > 1) return fail(h, BB_EINVAL, "the built-in agents are single-asset: create the handle with assets <= 1");
+    const bool mkt = !h->group_asset.empty();
+    if (h->assets > 1 && !mkt)
+        return fail(h, BB_EINVAL, "single-asset agents on a multi-asset handle: use bb_set_agents_market");
     if (n_steps == 0) return BB_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     for (auto& q : h->queue)
@@ -681,17 +708,21 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     p.seed_lo = (u32)seed;
     p.seed_hi = (u32)(seed >> 32);
     for (size_t i = 0; i < h->groups.size(); ++i) p.groups[i] = h->groups[i];
+    for (size_t i = 0; i < h->group_asset.size(); ++i) p.group_asset[i] = h->group_asset[i];
     int grid = 0, rc;
     const bool mom = h->mom_groups != 0;
-    const size_t sim_smem = (size_t)h->lay_sim.warp_bytes * WPB;
-#define SIM_CASE(E, M)                                                                     \
-    if (h->eng == E && mom == M) {                                                         \
-        if ((rc = grid_for(h, k_sim<E, M>, h->lay_sim, h->cfg.n_envs, &grid))) return rc;  \
+    // markets: the A books of a market are A consecutive warps of one CTA (a CTA holds as many whole markets as fit in 4 warps)
+    const u32 wpb = mkt ? (WPB / h->assets) * h->assets : WPB;
+    const size_t sim_smem = (size_t)h->lay_sim.warp_bytes * wpb;
+#define SIM_CASE(E, M)                                                                                     \
+    if (h->eng == E && mom == M) {                                                                         \
+        if (mkt) { if ((rc = grid_for(h, k_sim<E, M, true>, h->lay_sim, h->cfg.n_envs, &grid, wpb))) return rc; } \
+        else if ((rc = grid_for(h, k_sim<E, M, false>, h->lay_sim, h->cfg.n_envs, &grid, wpb))) return rc;  \
     }
     SIM_CASE(ENG_FAST, false) SIM_CASE(ENG_FAST, true) SIM_CASE(ENG_PAGED, false) SIM_CASE(ENG_PAGED, true)
     SIM_CASE(ENG_DENSE, false) SIM_CASE(ENG_DENSE, true) SIM_CASE(ENG_DENSE_L, false) SIM_CASE(ENG_DENSE_L, true)
 #undef SIM_CASE
-    const size_t warps = (size_t)grid * WPB;
+    const size_t warps = (size_t)grid * wpb;
     if (h->eng < ENG_DENSE && warps > h->scratch_warps) {
         cudaFree(h->scratch);
         h->scratch = nullptr;
@@ -699,8 +730,11 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
         h->scratch_warps = warps;
     }
     p.scratch = h->scratch;
-#define SIM_LAUNCH(E, M) \
-    if (h->eng == E && mom == M) k_sim<E, M><<<grid, WPB * 32, sim_smem, h->stream>>>(p);
+#define SIM_LAUNCH(E, M)                                                                       \
+    if (h->eng == E && mom == M) {                                                             \
+        if (mkt) k_sim<E, M, true><<<grid, wpb * 32, sim_smem, h->stream>>>(p);                \
+        else k_sim<E, M, false><<<grid, wpb * 32, sim_smem, h->stream>>>(p);                   \
+    }
     SIM_LAUNCH(ENG_FAST, false) SIM_LAUNCH(ENG_FAST, true) SIM_LAUNCH(ENG_PAGED, false) SIM_LAUNCH(ENG_PAGED, true)
     SIM_LAUNCH(ENG_DENSE, false) SIM_LAUNCH(ENG_DENSE, true) SIM_LAUNCH(ENG_DENSE_L, false) SIM_LAUNCH(ENG_DENSE_L, true)
 #undef SIM_LAUNCH

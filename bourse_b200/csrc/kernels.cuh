@@ -56,6 +56,10 @@ struct KParams {
     uint4* scratch;  // [resident warps][max_queue]
     u32 seed_lo, seed_hi;
     bb_agent_group groups[MAX_GROUPS];
+    // k_sim<.., MKT = true>: multi-asset markets with in-kernel agents (bb_set_agents_market)
+    u32 assets;                   // books per market; the market's books are consecutive warps of one CTA
+    u32 off_mkt;                  // per-warp offset of the market's shared words (used in the market's first warp only)
+    u32 group_asset[MAX_GROUPS];  // asset each agent group trades
 };
 
 // Values the optimiser would otherwise rematerialise at every use (S2R for the lane id, cvta + multiply
@@ -527,15 +531,34 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     return out;
 }
 
-template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __grid_constant__ KParams p) {
+// named barrier over the warps of one market (bar.sync with an explicit thread count)
+__device__ __forceinline__ void market_bar_sync(u32 id, u32 n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+// MKT: multi-asset markets with in-kernel agents — market_sim_runner (runner.rs:107-131) over the *Market agent twins
+// (RandomMarketAgents random_agent.rs:165-247, MomentumMarketAgent momentum_agent.rs:282-409, NoiseMarketAgent
+// noise_agent.rs:226-345).  The A books of a market are A consecutive warps of one CTA.  Every agent group trades one asset,
+// so each warp runs the groups of its own book; what a market shares is the step's transaction queue
+// (market_env.rs:108-121): all groups' instructions in declaration order, shuffled as a whole, event i of the shuffled
+// queue executing at start + i on its asset's book.  The warps exchange their per-group instruction counts through
+// shared memory (one named barrier per step), each then derives the same market-wide permutation from the market's
+// Philox key and pulls out its own events together with their positions in it.
+template <int ENG, bool MOM, bool MKT = false>
+__global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __grid_constant__ KParams p) {
     typedef GeoT<ENG> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
     const u32 bar = sb + p.off_bar;
     const u32 perm = sb + p.off_perm;          // u16 [max_queue]
-    const u32 jarr = perm + (G::DENSE ? 0u : 2u * p.max_queue);  // u16 [max_queue] (the dense engine has no perm array)
+    // u16 [max_queue] (the dense engine has no perm array); markets: perm and jarr hold the whole market's queue
+    const u32 jarr = perm + (MKT ? 2u * ((p.assets * p.max_queue + 7u) & ~7u) : G::DENSE ? 0u : 2u * p.max_queue);
     const u32 stage = sb + p.off_obs;          // u32 [2][OBS_STAGE_STEPS * obs_words]
+    const u32 mk_a = MKT ? warp % p.assets : 0u;                           // the asset this warp's book is
+    const u32 mk_sb = MKT ? sb - mk_a * p.warp_smem_bytes + p.off_mkt : 0u;  // u32 [2][MAX_GROUPS] in the market's first warp
+    const u32 mk_bar = MKT ? 1u + warp / p.assets : 0u;
+    u32 mk_phase = 0;
     // the step's transaction queue: L2-resident global scratch, or (dense engine) shared memory so that the event
     // loop fetches each instruction with one broadcast ld.shared.v4 instead of a gather + four shuffles
     const u32 qs = sb + p.off_q;
@@ -558,10 +581,12 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
         make_book(b, p, sb, env, lane);
         if (!blob_load(p, sb, env, bar, ph_blob, lane)) {
             if (lane == 0) atomicOr(p.err_flag, 0x80000000u);
+            if (MKT) __trap();  // leaving would strand the market's other warps at their barrier
             return;
         }
         book_from_header(g, b);
-        const u32 env_g = p.env_id_base + env;
+        // the RNG unit: the env, or the whole market (agent slots and the shuffle are market-wide)
+        const u32 env_g = MKT ? (p.env_id_base + env) / p.assets : p.env_id_base + env;
         u32* slots = p.rslot + (size_t)env * p.agents_per_env;
         const u32 agh = sb + p.off_ag;  // dense engine: held order id per agent, u32 [agents_per_env]
         if constexpr (G::DENSE) {
@@ -595,20 +620,28 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
             e.next_id = b.n_orders;
             const u32 id0 = b.n_orders;
             u32 slot_base = 0, mi = 0;
+            u32 mk_cnt = 0;  // markets: lane gi holds the number of instructions group gi queued (own groups only)
             for (u32 gi = 0; gi < p.n_groups; ++gi) {
                 const bb_agent_group& ag = p.groups[gi];
+                const bool mine = !MKT || p.group_asset[gi] == mk_a;
+                const u32 n_before = e.n;
                 if (!MOM || ag.kind == BB_GROUP_RANDOM) {
-                    if constexpr (G::DENSE) random_agents_update_dense<G>(p, ag, b, qs, e, agh, env_g, step, slot_base);
-                    else random_agents_update(p, ag, b, q, e, slots, env_g, step, slot_base);
+                    if (mine) {
+                        if constexpr (G::DENSE) random_agents_update_dense<G>(p, ag, b, qs, e, agh, env_g, step, slot_base);
+                        else random_agents_update(p, ag, b, q, e, slots, env_g, step, slot_base);
+                    }
                 } else {
-                    const MomOut mo = momentum_agent_update(p, ag, b.oh, lane, best_price(g, b, 1), best_price(g, b, 0), q, e.n,
-                                                            e.next_id, p.mom + (size_t)env * p.mom_groups_per_env + mi, env_g,
-                                                            step, gi, slot_base);
-                    e.n = mo.n;
-                    e.next_id = mo.next_id;
-                    b.err |= mo.err;
+                    if (mine) {
+                        const MomOut mo = momentum_agent_update(p, ag, b.oh, lane, best_price(g, b, 1), best_price(g, b, 0), q, e.n,
+                                                                e.next_id, p.mom + (size_t)env * p.mom_groups_per_env + mi, env_g,
+                                                                step, gi, slot_base);
+                        e.n = mo.n;
+                        e.next_id = mo.next_id;
+                        b.err |= mo.err;
+                    }
                     ++mi;
                 }
+                if (MKT && lane == gi) mk_cnt = e.n - n_before;
                 slot_base += ag.n_agents;
             }
             if (e.n > p.max_queue) b.err |= ERR_CAP_QUEUE;
@@ -628,12 +661,33 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
             if constexpr (G::DENSE) {  // the dense engine relies on t = start + i being new, increasing key times
                 if (n > p.step_size || (start <= b.max_key_time && (b.flags & (FL_HAS_ASK | FL_HAS_BID)))) b.err |= ERR_TIME_ORDER;
             }
+            // markets: exchange the per-group counts; `nq` is the length of the queue that gets shuffled
+            u32 nq = n, mk_off = 0, mk_loc = 0, mk_all = 0;
+            if constexpr (MKT) {
+                const u32 cb = mk_sb + 4u * MAX_GROUPS * (mk_phase & 1u);  // double-buffered: one barrier per step is enough
+                mk_phase += 1;
+                const bool own = lane < p.n_groups && p.group_asset[lane] == mk_a;
+                if (own) sts(cb + 4u * lane, mk_cnt);
+                market_bar_sync(mk_bar, 32u * p.assets);
+                mk_all = lane < p.n_groups ? lds(cb + 4u * lane) : 0u;
+                u32 total, total_mine;
+                mk_off = warp_excl_scan(mk_all, lane, &total);            // first queue position of each group
+                mk_loc = warp_excl_scan(own ? mk_all : 0u, lane, &total_mine);  // ... and its first entry in this book's list
+                nq = total;
+                if (nq > p.assets * p.max_queue) {  // some book overflowed its queue (flagged there): drop the step everywhere
+                    b.err |= ERR_CAP_QUEUE;
+                    nq = 0;
+                }
+                if constexpr (G::DENSE) {
+                    if (nq > p.step_size) b.err |= ERR_TIME_ORDER;
+                }
+            }
             // shuffle: Fisher-Yates from the back, one Philox word per position, draws made lane-parallel
-            if constexpr (!G::DENSE)
-                for (u32 i = lane; i < n; i += 32) sts16(perm + 2u * i, i);
-            for (u32 b0 = 0; b0 * 4u < n; b0 += 32) {
+            if constexpr (MKT || !G::DENSE)
+                for (u32 i = lane; i < nq; i += 32) sts16(perm + 2u * i, i);
+            for (u32 b0 = 0; b0 * 4u < nq; b0 += 32) {
                 const u32 blk = b0 + lane;
-                if (blk * 4u < n) {
+                if (blk * 4u < nq) {
                     const uint4 r = philox4x32_10(env_g, step, PHILOX_SLOT_SHUFFLE, blk, p.seed_lo, p.seed_hi);
                     const u32 i = blk * 4u;
                     // 4 consecutive u16 slots are always in bounds: the array is padded to a multiple of 8 bytes
@@ -644,7 +698,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                 }
             }
             __syncwarp();
-            if constexpr (G::DENSE) {  // the queue is on chip: swap the 16-byte instructions themselves
+            if constexpr (G::DENSE && !MKT) {  // the queue is on chip: swap the 16-byte instructions themselves
                 for (u32 i = n; i > 1; --i) {
                     const u32 j = lds16(jarr + 2u * (i - 1));
                     const uint4 x = lds128(qs + 16u * (i - 1)), y = lds128(qs + 16u * j);
@@ -652,7 +706,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                     sts128(qs + 16u * j, x);
                 }
             } else {
-                for (u32 i = n; i > 1; --i) {
+                for (u32 i = nq; i > 1; --i) {
                     const u32 j = lds16(jarr + 2u * (i - 1));
                     const u32 x = lds16(perm + 2u * (i - 1)), y = lds16(perm + 2u * j);
                     sts16(perm + 2u * (i - 1), y);
@@ -660,6 +714,31 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                 }
             }
             __syncwarp();
+            if constexpr (MKT) {
+                // pull this book's events out of the market-wide permutation, in queue order: (index in the book's own
+                // list, position in the shuffled queue = time offset), one u32 each, over the consumed draw array
+                u32 n_mine = 0;
+                for (u32 i0 = 0; i0 < nq; i0 += 32) {
+                    const u32 i = i0 + lane;
+                    const u32 gq = i < nq ? lds16(perm + 2u * i) : 0xFFFFFFFFu;
+                    bool is_mine = false;
+                    u32 li = 0;
+                    for (u32 k = 0; k < p.n_groups; ++k) {
+                        const u32 o = __shfl_sync(BB_FULL, mk_off, k), c = __shfl_sync(BB_FULL, mk_all, k);
+                        const u32 lo = __shfl_sync(BB_FULL, mk_loc, k);
+                        if (gq - o < c && p.group_asset[k] == mk_a) {
+                            is_mine = true;
+                            li = lo + (gq - o);
+                        }
+                    }
+                    const u32 m = __ballot_sync(BB_FULL, is_mine);
+                    const u32 pos = n_mine + __popc(m & ((1u << lane) - 1u));
+                    if (is_mine && pos < p.max_queue) sts(jarr + 4u * pos, min(li, p.max_queue - 1u) | (i << 16));
+                    n_mine += __popc(m);
+                }
+                n = min(n, n_mine);  // equal unless the step was dropped
+                __syncwarp();
+            }
             // process in shuffled order at t = start + i
             if constexpr (G::DENSE) {
                 constexpr int H = MOM ? 2 : 1;  // RandomAgents always hint, MomentumAgent / NoiseAgent never do
@@ -681,6 +760,14 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                         }
                         b.t += 1;
                     };
+                    if constexpr (MKT) {
+                        for (u32 k = 0; k < n; ++k) {
+                            const u32 w = lds(jarr + 4u * k);
+                            const uint4 ev = lds128(qs + 16u * (w & 0xFFFFu));
+                            b.t = start + (u64)(w >> 16);
+                            handle(ev);
+                        }
+                    } else {
                     uint4 e0 = lds128(qs);
                     for (u32 i = 0; i < n; i += 2) {
                         const uint4 e1 = lds128(qs + 16u * i + 16u);  // (the queue is padded by two entries)
@@ -688,6 +775,7 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
                         if (i + 1 >= n) break;
                         e0 = lds128(qs + 16u * i + 32u);
                         handle(e1);
+                    }
                     }
                 }
                 if constexpr (!MOM) {
@@ -713,8 +801,18 @@ template <int ENG, bool MOM> __global__ void __launch_bounds__(128, ENG == ENG_P
             for (u32 i0 = 0; i0 < n; i0 += 32) {
                 const u32 cnt = min(32u, n - i0);
                 uint4 mine = make_uint4(0, 0, 0, 0);
-                if (lane < cnt) mine = ldg128(qa + 16u * lds16(perm + 2u * (i0 + lane)));
+                u32 toff = 0;
+                if (lane < cnt) {
+                    if constexpr (MKT) {
+                        const u32 w = lds(jarr + 4u * (i0 + lane));
+                        mine = ldg128(qa + 16u * (w & 0xFFFFu));
+                        toff = w >> 16;
+                    } else {
+                        mine = ldg128(qa + 16u * lds16(perm + 2u * (i0 + lane)));
+                    }
+                }
                 for (u32 k = 0; k < cnt; ++k) {
+                    if constexpr (MKT) b.t = start + (u64)__shfl_sync(BB_FULL, toff, k);
                     const u32 of = __shfl_sync(BB_FULL, mine.x, k), id = __shfl_sync(BB_FULL, mine.y, k);
                     const u32 price = __shfl_sync(BB_FULL, mine.z, k), vol = __shfl_sync(BB_FULL, mine.w, k);
                     if (of & 1u) {  // NEW: one constant-folded copy of the placement path per side

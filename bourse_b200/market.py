@@ -164,3 +164,82 @@ class MarketEnv:
         return self._env.order_status(order_id[1], self._book(order_id[0], market))
 
     def env_errors(self) -> np.ndarray: return self._env.env_errors()
+
+    # ------------------------------------------------------------------ in-kernel agents (market_sim_runner)
+    def set_agents(self, agents: typing.Sequence["_MarketAgentGroup"]):
+        """The fields of a `#[derive(MarketAgentSet)]` struct, in declaration order (crates/step_sim/src/agents/mod.rs:238-258)."""
+        self._env.set_agents([a.group for a in agents], assets=[a.asset for a in agents])
+
+    def run_agents(self, n_steps: int, seed: int):
+        """`n_steps` of `{ agents.update(env, rng); env.step(rng) }` for every market inside one kernel launch
+        (runner.rs:107-131).  Draws are Philox-keyed per (seed; market, step, agent) — DESIGN.md "RNG contract"."""
+        self._env.run_agents(n_steps, seed)
+
+    def stats(self) -> dict: return self._env.stats()
+
+
+# ---------------------------------------------------------------------- the *Market agent twins
+class _MarketAgentGroup:
+    asset: int
+    group: np.void
+
+
+class RandomMarketAgents(_MarketAgentGroup):
+    """`RandomMarketAgents::new(asset, n_agents, tick_range, vol_range, tick_size, activity_rate)`
+    (crates/step_sim/src/agents/random_agent.rs:173-202)."""
+
+    def __init__(self, asset: int, n_agents: int, tick_range: typing.Tuple[int, int], vol_range: typing.Tuple[int, int],
+                 tick_size: int, activity_rate: float):
+        from .core import random_group
+        self.asset, self.group = asset, random_group(n_agents, tick_range, vol_range, tick_size, activity_rate)
+
+
+class MomentumParams(typing.NamedTuple):
+    """crates/step_sim/src/agents/momentum_agent.rs:16-35 (same field order)."""
+    tick_size: int
+    p_cancel: float
+    trade_vol: int
+    decay: float
+    demand: float
+    scale: float
+    order_ratio: float
+    price_dist_mu: float
+    price_dist_sigma: float
+
+
+class MomentumMarketAgent(_MarketAgentGroup):
+    """`MomentumMarketAgent::new(agent_id_start, n_agents, asset, params)` (momentum_agent.rs:294-325)."""
+
+    def __init__(self, agent_id_start: int, n_agents: int, asset: int, params: MomentumParams):
+        from .core import momentum_group
+        self.asset = asset
+        self.group = momentum_group(agent_id_start, n_agents, params.tick_size, params.p_cancel, params.trade_vol, params.decay,
+                                    params.demand, params.scale, params.order_ratio, params.price_dist_mu, params.price_dist_sigma)
+
+
+class NoiseAgentParams(typing.NamedTuple):
+    """crates/step_sim/src/agents/noise_agent.rs:14-29 (same field order)."""
+    tick_size: int
+    p_limit: float
+    p_market: float
+    p_cancel: float
+    trade_vol: int
+    price_dist_mu: float
+    price_dist_sigma: float
+
+
+class NoiseMarketAgent(_MarketAgentGroup):
+    """`NoiseMarketAgent::new(asset, agent_id_start, n_agents, params)` (noise_agent.rs:236-258)."""
+
+    def __init__(self, asset: int, agent_id_start: int, n_agents: int, params: NoiseAgentParams):
+        from .core import noise_group
+        self.asset = asset
+        self.group = noise_group(agent_id_start, n_agents, params.tick_size, params.p_limit, params.p_market, params.p_cancel,
+                                 params.trade_vol, params.price_dist_mu, params.price_dist_sigma)
+
+
+def market_sim_runner(env: MarketEnv, agents: typing.Sequence[_MarketAgentGroup], seed: int, n_steps: int,
+                      show_progress: bool = False):
+    """`bourse_de::market_sim_runner(env, agents, seed, n_steps, show_progress)` (crates/step_sim/src/runner.rs:107-131)."""
+    env.set_agents(agents)
+    env.run_agents(n_steps, seed)

@@ -90,7 +90,7 @@ typedef struct {
      * independent; what a market shares is ONE transaction queue per step, shuffled as a whole, with event i of the
      * shuffled queue executing at time start + i on its asset's book (market_env.rs:108-121).  n_envs must be a
      * multiple of assets; market m shuffles with Xoroshiro128**(seed + env_id_base / assets + m).  0 or 1 => every
-     * book is its own Env.  The built-in agents (bb_run_agents) are single-asset and need assets <= 1. */
+     * book is its own Env.  In-kernel agents on a multi-asset handle are defined with bb_set_agents_market. */
     uint32_t assets;
 } bb_config;
 
@@ -196,6 +196,14 @@ int bb_replay_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_e
 /* ---- built-in agents: sim_runner (crates/step_sim/src/runner.rs:46-69) ------------------------ */
 /* Defines the agent set (resets agent state).  Groups run in array order. */
 int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups);
+/* Multi-asset handles (bb_config.assets = 2..4): the *Market twins of the built-in agents — RandomMarketAgents
+ * (crates/step_sim/src/agents/random_agent.rs:165-247), MomentumMarketAgent (momentum_agent.rs:282-409),
+ * NoiseMarketAgent (noise_agent.rs:226-345) — as fields of a #[derive(MarketAgentSet)] struct: group i is the same
+ * bb_agent_group as above and trades asset asset[i] of every market.  bb_run_agents then runs market_sim_runner
+ * (crates/step_sim/src/runner.rs:107-131): all groups update in array order, the market's queue is shuffled as a
+ * whole and event i executes at start + i on its asset's book (market_env.rs:108-121).  The RNG unit is the market:
+ * Philox key (seed; global market id = (env_id_base + env) / assets, step, agent slot counted over all groups). */
+int bb_set_agents_market(bb_handle* h, const bb_agent_group* groups, const uint32_t* asset, uint32_t n_groups);
 /* n_steps of { agents.update(env); env.step() } for every env inside one persistent kernel.
  * Draws are Philox4x32-10 keyed (seed; global env id, step, agent) — DESIGN.md "RNG contract".
  * Asynchronous on the handle's stream; pair with bb_synchronize or any read call. */

@@ -130,12 +130,15 @@ public:
         for (auto& b : books) level_2_data.push_back(b.level_2_data());
     }
 
-    void step(Xoroshiro128StarStar& rng) {  // market_env.rs:108-135
+    void step(Xoroshiro128StarStar& rng) {
+        step_with([&](std::vector<MarketEvent>& tx) { shuffle(rng, tx); });
+    }
+    template <class ShuffleFn> void step_with(ShuffleFn&& shuffle_fn) {  // market_env.rs:108-135
         const Nanos start_time = books[0].get_time();
         for (auto& b : books) b.reset_trade_vol();
         std::vector<MarketEvent> tx;
         tx.swap(transactions);
-        shuffle(rng, tx);
+        shuffle_fn(tx);
         for (size_t i = 0; i < tx.size(); ++i) {
             for (auto& b : books) b.set_time(start_time + (Nanos)i);  // Market::set_time, market.rs:113-117
             OrderBook& b = books[tx[i].asset];
@@ -205,7 +208,7 @@ struct RandomAgents {
     explicit RandomAgents(const RandomAgentsParams& p_) : p(p_), orders(p_.n_agents, NO_ORDER) {}
 
     // random_agent.rs:85-119 with the reference's single shared stream
-    void update_stream(Env& env, Xoroshiro128StarStar& rng) {
+    template <class E> void update_stream(E& env, Xoroshiro128StarStar& rng) {
         for (uint32_t n = 0; n < p.n_agents; ++n) {
             const float u = gen_f32(rng);
             if (u < p.activity_rate) {
@@ -222,7 +225,7 @@ struct RandomAgents {
         }
     }
     // Same decision logic, draws taken from the Philox block keyed (env, step, agent slot, 0)
-    void update_keyed(Env& env, uint32_t env_id, uint32_t step, uint32_t slot_base, uint32_t k0, uint32_t k1) {
+    template <class E> void update_keyed(E& env, uint32_t env_id, uint32_t step, uint32_t slot_base, uint32_t k0, uint32_t k1) {
         for (uint32_t n = 0; n < p.n_agents; ++n) {
             const Philox4 r = philox4x32_10(env_id, step, slot_base + n, 0, k0, k1);
             const float u = u32_to_f32_unit(r.v[0]);
@@ -255,8 +258,8 @@ struct MomentumAgent {
     }
 
     // momentum_agent.rs:145-209; `draw_*` lambdas abstract where the uniforms come from
-    template <class DrawCancel, class DrawTrader>
-    void update_impl(Env& env, DrawCancel&& draw_cancel, DrawTrader&& draw_trader) {
+    template <class E, class DrawCancel, class DrawTrader>
+    void update_impl(E& env, DrawCancel&& draw_cancel, DrawTrader&& draw_trader) {
         // common.rs:56-75 cancel_live_orders
         std::vector<OrderId> live;
         uint32_t k = 0;
@@ -297,7 +300,7 @@ struct MomentumAgent {
         orders.swap(live);
     }
 
-    void update_stream(Env& env, Xoroshiro128StarStar& rng) {
+    template <class E> void update_stream(E& env, Xoroshiro128StarStar& rng) {
         // NB the reference consumes draws lazily (the normal only when a limit order fires, and
         // through rand_distr's ziggurat); this restatement draws all four uniforms per trader up
         // front.  Only statistical equivalence is claimed for the stream policy (parity unpinned).
@@ -310,8 +313,8 @@ struct MomentumAgent {
                 *um = gen_f64(rng);
             });
     }
-    void update_keyed(Env& env, uint32_t env_id, uint32_t step, uint32_t group, uint32_t slot_base, uint32_t k0,
-                      uint32_t k1) {
+    template <class E>
+    void update_keyed(E& env, uint32_t env_id, uint32_t step, uint32_t group, uint32_t slot_base, uint32_t k0, uint32_t k1) {
         update_impl(
             env,
             [&](uint32_t k) {
@@ -345,8 +348,8 @@ struct NoiseAgent {
     explicit NoiseAgent(const NoiseParams& p_) : p(p_) {}
 
     // noise_agent.rs:126-177; draws abstracted as in MomentumAgent
-    template <class DrawCancel, class DrawTrader>
-    void update_impl(Env& env, DrawCancel&& draw_cancel, DrawTrader&& draw_trader) {
+    template <class E, class DrawCancel, class DrawTrader>
+    void update_impl(E& env, DrawCancel&& draw_cancel, DrawTrader&& draw_trader) {
         std::vector<OrderId> live;
         uint32_t k = 0;
         for (OrderId id : orders) {  // common.rs:56-75
@@ -371,7 +374,7 @@ struct NoiseAgent {
         }
         orders.swap(live);
     }
-    void update_stream(Env& env, Xoroshiro128StarStar& rng) {
+    template <class E> void update_stream(E& env, Xoroshiro128StarStar& rng) {
         update_impl(
             env, [&](uint32_t) { return gen_f32(rng); },
             [&](uint32_t, float* ul, bool* lb, float* um, bool* mb, double* n1, double* n2) {
@@ -383,7 +386,8 @@ struct NoiseAgent {
                 *mb = (rng.next_u64() >> 63) == 0;
             });
     }
-    void update_keyed(Env& env, uint32_t env_id, uint32_t step, uint32_t group, uint32_t slot_base, uint32_t k0, uint32_t k1) {
+    template <class E>
+    void update_keyed(E& env, uint32_t env_id, uint32_t step, uint32_t group, uint32_t slot_base, uint32_t k0, uint32_t k1) {
         update_impl(
             env,
             [&](uint32_t k) {
@@ -468,6 +472,90 @@ public:
                     const Philox4 r = philox4x32_10(env_id, step, PHILOX_SLOT_SHUFFLE, idx >> 2, k0, k1);
                     const uint32_t j = mulhi_range(r.v[idx & 3], (uint32_t)i);
                     std::swap(tx[i - 1], tx[j]);
+                }
+            });
+            ++step_counter;
+        }
+    }
+};
+
+// One asset of a MarketEnv seen through the interface the agents use.  The *Market twins of the built-in agents
+// (RandomMarketAgents random_agent.rs:165-247, MomentumMarketAgent momentum_agent.rs:282-409, NoiseMarketAgent
+// noise_agent.rs:226-345, helpers common.rs:156-261) are the single-asset agents with every call routed through
+// (asset, id): statuses and the mid price come from the asset's live book (market_env.rs:328-330,
+// `env.get_market().get_order_book(asset).mid_price()`), instructions go to the market's shared queue.
+struct AssetEnv {
+    MarketEnv& m;
+    uint32_t asset;
+    OrderBook& book;
+    AssetEnv(MarketEnv& m_, uint32_t a) : m(m_), asset(a), book(m_.books[a]) {}
+    Status order_status(OrderId id) const { return book.order(id).status; }
+    void cancel_order(OrderId id) { m.cancel_order(asset, id); }
+    OrderId place_order(Side side, Vol vol, TraderId trader, bool price_is_some, Price price) {
+        return m.place_order(asset, side, vol, trader, price_is_some, price);
+    }
+};
+
+// MarketEnv + ordered agent groups, each bound to one asset: market_sim_runner (runner.rs:107-131) over a
+// #[derive(MarketAgentSet)] struct (crates/macros/src/lib.rs).  Keyed contract: the MARKET is the RNG unit — agent
+// draws use (market id, step, slot) with slots counted over all groups of the market in declaration order, and one
+// shuffle per market and step over the whole queue.
+class MarketSim {
+public:
+    MarketEnv env;
+    std::vector<RandomAgents> randoms;
+    std::vector<MomentumAgent> momentums;
+    std::vector<NoiseAgent> noises;
+    struct Slot { GroupKind kind; size_t idx; uint32_t asset; };
+    std::vector<Slot> order;
+    uint32_t step_counter = 0;
+    uint64_t n_instructions = 0;
+
+    MarketSim(Nanos start_time, const std::vector<Price>& ticks, Nanos step_size, bool trading) : env(start_time, ticks, step_size, trading) {}
+    void add_random(uint32_t asset, const RandomAgentsParams& p) { order.push_back({GROUP_RANDOM, randoms.size(), asset}); randoms.emplace_back(p); }
+    void add_momentum(uint32_t asset, const MomentumParams& p) { order.push_back({GROUP_MOMENTUM, momentums.size(), asset}); momentums.emplace_back(p); }
+    void add_noise(uint32_t asset, const NoiseParams& p) { order.push_back({GROUP_NOISE, noises.size(), asset}); noises.emplace_back(p); }
+
+    void run_stream(uint64_t seed, uint64_t n_steps) {  // runner.rs:107-131
+        Xoroshiro128StarStar rng = Xoroshiro128StarStar::seed_from_u64(seed);
+        for (uint64_t s = 0; s < n_steps; ++s) {
+            for (auto& g : order) {
+                AssetEnv ae(env, g.asset);
+                if (g.kind == GROUP_RANDOM) randoms[g.idx].update_stream(ae, rng);
+                else if (g.kind == GROUP_MOMENTUM) momentums[g.idx].update_stream(ae, rng);
+                else noises[g.idx].update_stream(ae, rng);
+            }
+            n_instructions += env.transactions.size();
+            env.step(rng);
+            ++step_counter;
+        }
+    }
+
+    void run_keyed(uint64_t seed, uint32_t market_id, uint64_t n_steps) {
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        for (uint64_t s = 0; s < n_steps; ++s) {
+            const uint32_t step = step_counter;
+            uint32_t slot_base = 0, gi = 0;
+            for (auto& g : order) {
+                AssetEnv ae(env, g.asset);
+                if (g.kind == GROUP_RANDOM) {
+                    randoms[g.idx].update_keyed(ae, market_id, step, slot_base, k0, k1);
+                    slot_base += randoms[g.idx].p.n_agents;
+                } else if (g.kind == GROUP_MOMENTUM) {
+                    momentums[g.idx].update_keyed(ae, market_id, step, gi, slot_base, k0, k1);
+                    slot_base += momentums[g.idx].p.n_agents;
+                } else {
+                    noises[g.idx].update_keyed(ae, market_id, step, gi, slot_base, k0, k1);
+                    slot_base += noises[g.idx].p.n_agents;
+                }
+                ++gi;
+            }
+            n_instructions += env.transactions.size();
+            env.step_with([&](std::vector<MarketEnv::MarketEvent>& tx) {
+                for (size_t i = tx.size(); i > 1; --i) {  // Fisher-Yates from the back, one Philox word per position
+                    const uint32_t idx = (uint32_t)(i - 1);
+                    const Philox4 r = philox4x32_10(market_id, step, PHILOX_SLOT_SHUFFLE, idx >> 2, k0, k1);
+                    std::swap(tx[i - 1], tx[mulhi_range(r.v[idx & 3], (uint32_t)i)]);
                 }
             });
             ++step_counter;

@@ -113,6 +113,10 @@ def lib() -> C.CDLL:
     sig("orc_market_step", i32, vp)
     sig("orc_market_n_steps", u64, vp, u32)
     sig("orc_market_history", None, vp, u32, vp)
+    sig("orc_market_set_groups", None, vp, vp, vp, u32)
+    sig("orc_market_run", None, vp, i32, u64, u32, u64)
+    sig("orc_market_n_instructions", u64, vp)
+    sig("orc_bench_market_agents", dbl, u32, u32, u64, u64, i32, u64, vp, u32, u64, vp, vp, u32, vp)
     sig("orc_bench_replay_suffix", dbl, u32, u32, vp, u64, u64, vp)
     sig("orc_philox", None, u32, u32, u32, u32, u32, u32, vp)
     sig("orc_xoroshiro", None, u64, u32, vp)
@@ -430,6 +434,17 @@ def bench_agents(n_envs, n_threads, n_steps, seed, groups, keyed=False, start_ti
     return {"seconds": secs, "instructions": int(out[0]), "trades": int(out[1]), "env_steps": int(out[2])}
 
 
+def bench_market_agents(n_markets, n_threads, n_steps, seed, groups, assets, n_assets, keyed=False, start_time=0, tick_size=1,
+                        step_size=1_000_000):
+    arr = groups_array(groups)
+    a = np.ascontiguousarray(assets, dtype=np.uint32)
+    ticks = np.full(n_assets, tick_size, np.uint32)
+    out = np.zeros(3, np.uint64)
+    secs = lib().orc_bench_market_agents(n_markets, n_threads, n_steps, seed, int(keyed), start_time, _ptr(ticks), n_assets,
+                                         step_size, _ptr(arr), _ptr(a), len(arr), _ptr(out))
+    return {"seconds": secs, "instructions": int(out[0]), "trades": int(out[1]), "env_steps": int(out[2])}
+
+
 def bench_replay(n_books, n_threads, tick_size, instrs):
     instrs = np.ascontiguousarray(instrs, dtype=INSTR_DTYPE)
     out = np.zeros(2, np.uint64)
@@ -495,6 +510,21 @@ class MarketEnv:
         if n:
             lib().orc_market_history(self._h, asset, _ptr(out))
         return out
+
+    def set_groups(self, groups, assets):
+        """Market agent twins: group i (random_group / momentum_group / noise_group) trades asset assets[i]
+        (RandomMarketAgents random_agent.rs:165-247, MomentumMarketAgent momentum_agent.rs:282-409, NoiseMarketAgent
+        noise_agent.rs:226-345); groups update in list order each step."""
+        arr = groups_array(groups)
+        a = np.ascontiguousarray(assets, dtype=np.uint32)
+        assert len(a) == len(arr) and (a < self.n_assets).all()
+        lib().orc_market_set_groups(self._h, _ptr(arr), _ptr(a), len(arr))
+
+    def run_agents(self, n_steps, seed, market_id=0, keyed=True):
+        """market_sim_runner (runner.rs:107-131); keyed=True uses the Philox contract keyed by market id."""
+        lib().orc_market_run(self._h, int(keyed), seed, market_id, n_steps)
+
+    def n_instructions(self): return lib().orc_market_n_instructions(self._h)
 
     def time(self): return lib().orc_book_time(lib().orc_market_book(self._h, 0))
     def get_orders(self, asset): return self.asset(asset).get_orders()

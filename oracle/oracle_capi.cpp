@@ -262,10 +262,11 @@ uint64_t orc_sim_n_instructions(void* s) { return ((SimHandle*)s)->sim.n_instruc
 
 // ---------------------------------------------------------------- MarketEnv (multi-asset)
 struct MarketHandle {
-    MarketEnv env;
+    MarketSim sim;
+    MarketEnv& env;
     Xoroshiro128StarStar rng;
     MarketHandle(uint64_t seed, Nanos start, const std::vector<Price>& ticks, Nanos step, bool trading)
-        : env(start, ticks, step, trading), rng(Xoroshiro128StarStar::seed_from_u64(seed)) {}
+        : sim(start, ticks, step, trading), env(sim.env), rng(Xoroshiro128StarStar::seed_from_u64(seed)) {}
 };
 void* orc_market_new(uint64_t seed, uint64_t start_time, const uint32_t* tick_sizes, uint32_t n_assets, uint64_t step_size, int trading) {
     return new MarketHandle(seed, start_time, std::vector<Price>(tick_sizes, tick_sizes + n_assets), step_size, trading != 0);
@@ -306,6 +307,58 @@ void orc_market_history(void* m, uint32_t asset, uint32_t* out) {  // [n_steps][
             o[5 + 4 * i + 2] = r.ask_vol_at[i][k]; o[5 + 4 * i + 3] = r.ask_n_at[i][k];
         }
     }
+}
+
+// market agent twins: group i trades asset assets[i] (RandomMarketAgents / MomentumMarketAgent / NoiseMarketAgent)
+static void add_market_groups(MarketSim& sim, const orc_group* g, const uint32_t* assets, uint32_t n_groups) {
+    for (uint32_t i = 0; i < n_groups; ++i) {
+        if (g[i].kind == 0) {
+            sim.add_random(assets[i], RandomAgentsParams{g[i].n_agents, g[i].tick_lo, g[i].tick_hi, g[i].vol_lo, g[i].vol_hi,
+                                                         g[i].tick_size, g[i].rate});
+        } else if (g[i].kind == 1) {
+            sim.add_momentum(assets[i], MomentumParams{g[i].tick_lo, g[i].n_agents, g[i].tick_size, g[i].rate, g[i].vol_lo,
+                                                       g[i].decay, g[i].demand, g[i].scale, g[i].order_ratio, g[i].mu, g[i].sigma});
+        } else {
+            sim.add_noise(assets[i], NoiseParams{g[i].tick_lo, g[i].n_agents, g[i].tick_size, (float)g[i].decay, (float)g[i].demand,
+                                                 g[i].rate, g[i].vol_lo, g[i].mu, g[i].sigma});
+        }
+    }
+}
+void orc_market_set_groups(void* m, const orc_group* g, const uint32_t* assets, uint32_t n_groups) {
+    add_market_groups(((MarketHandle*)m)->sim, g, assets, n_groups);
+}
+// keyed != 0: Philox contract keyed by market id (what the CUDA path mirrors); keyed == 0: market_sim_runner's shared stream
+void orc_market_run(void* m, int keyed, uint64_t seed, uint32_t market_id, uint64_t n_steps) {
+    MarketHandle* h = (MarketHandle*)m;
+    if (keyed) h->sim.run_keyed(seed, market_id, n_steps); else h->sim.run_stream(seed, n_steps);
+}
+uint64_t orc_market_n_instructions(void* m) { return ((MarketHandle*)m)->sim.n_instructions; }
+
+// `n_markets` agent-driven markets across `n_threads` threads; out[0] = instructions, out[1] = trades, out[2] = book-steps
+double orc_bench_market_agents(uint32_t n_markets, uint32_t n_threads, uint64_t n_steps, uint64_t seed, int keyed, uint64_t start_time,
+                               const uint32_t* tick_sizes, uint32_t n_assets, uint64_t step_size, const orc_group* g,
+                               const uint32_t* assets, uint32_t n_groups, uint64_t* out) {
+    std::atomic<uint32_t> next(0);
+    std::atomic<uint64_t> n_ins(0), n_tr(0);
+    const std::vector<Price> ticks(tick_sizes, tick_sizes + n_assets);
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t e = next.fetch_add(1);
+            if (e >= n_markets) break;
+            MarketSim sim(start_time, ticks, step_size, true);
+            add_market_groups(sim, g, assets, n_groups);
+            if (keyed) sim.run_keyed(seed, e, n_steps); else sim.run_stream(seed + e, n_steps);
+            n_ins += sim.n_instructions;
+            for (auto& b : sim.env.books) n_tr += b.trades.size();
+        }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (uint32_t i = 0; i < n_threads; ++i) th.emplace_back(worker);
+    for (auto& x : th) x.join();
+    const auto t1 = std::chrono::steady_clock::now();
+    out[0] = n_ins; out[1] = n_tr; out[2] = (uint64_t)n_markets * n_assets * n_steps;
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 // ---------------------------------------------------------------- CPU baseline

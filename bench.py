@@ -437,6 +437,33 @@ def run_gpu_other(args):
         ext = 0
         name = (f"C4 shard: {per_gpu} envs/GPU x (40+40 RandomAgents + 20-trader MomentumAgent) x {n_steps} env-steps, "
                 "level-2 (45 x u32) record per env-step, paged engine")
+    elif args.workload == "market":
+        # the reference's multi-asset example (crates/step_sim/examples/multi_asset/main.rs:12-22) —
+        # MarketEnv::<2> with 4 RandomMarketAgents groups (100 agents per asset), market_sim_runner — batched over
+        # `--envs / 2` lockstep markets per GPU; one level-2 record per asset and step (MarketEnv keeps Level2DataRecords)
+        n_assets = 2
+        per_gpu = args.envs
+        base, n_envs = shard_range(per_gpu * world, world, rank)
+        groups, g_assets = workloads.market_example_groups()
+        obs, n_steps = abi.OBS_L2, args.sim_steps
+        eng_kw = dict(price_window=(20, 180), live_cap=128) if args.engine == "dense" else {}
+        env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=args.max_orders,
+                              max_trades=args.max_trades, max_steps=n_steps, max_queue=128, assets=n_assets, **eng_kw)
+        env.set_agents(groups, assets=g_assets)
+        env.set_stream(stream.cuda_stream)
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                barrier()
+            env.reset()
+            if i >= args.warmup:
+                ev[i - args.warmup][0].record(stream)
+            env.run_agents(n_steps, SEED, sync=False)
+            if i >= args.warmup:
+                ev[i - args.warmup][1].record(stream)
+            flush.fill_(1)
+        ext = 0
+        name = (f"multi-asset example: {per_gpu // n_assets} markets/GPU x 2 assets x (50+50) RandomMarketAgents per asset x {n_steps} "
+                f"steps (market_sim_runner), level-2 record per asset and step, {args.engine} engine")
     else:
         per_gpu = args.envs if args.envs != N_ENVS_PER_GPU else 128
         base, n_envs = shard_range(per_gpu * world, world, rank)
@@ -493,6 +520,11 @@ def run_gpu_other(args):
                 r = orc.bench_agents(128 * cores, cores, n_steps, 7, groups, keyed=False, start_time=0, tick_size=1, step_size=1_000_000)
                 cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
                        "sample": f"{128 * cores} envs x {n_steps} env-steps of the C4 population, one env per core at a time ({r['seconds']:.2f} s)"}
+            elif args.workload == "market":
+                r = orc.bench_market_agents(32 * cores, cores, n_steps, SEED, groups, g_assets, n_assets, keyed=False)
+                cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{32 * cores} two-asset markets x {n_steps} steps, one market per core at a time, reference-style "
+                                 f"shared Xoroshiro stream ({r['seconds']:.2f} s)"}
             else:
                 r = orc.bench_replay_suffix(cores, 1, streams[0], n_rest)
                 cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
@@ -505,7 +537,7 @@ def run_gpu_other(args):
             "env_steps_per_sec": agg["env_steps"] * args.steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
             "trades_per_pass": agg["trades"],
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim" if args.workload == "c4" else "k_apply",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim" if args.workload in ("c4", "market") else "k_apply",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             **({"cpu_baseline": cpu} if cpu else {})}))
     if world > 1:
@@ -526,7 +558,8 @@ def main():
     ap.add_argument("--max-trades", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default="dense", choices=["dense", "paged"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"], help="c3 = the headline line; the others are the secondary configs")
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "market"],
+                    help="c3 = the headline line; the others are the secondary configs (market = the multi-asset example)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

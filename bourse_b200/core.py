@@ -138,6 +138,26 @@ class BatchedEnv:
 
     def step(self, n_steps: int = 1): self._ck(self._lib.bb_step(self._h, n_steps))
 
+    # ------------------------------------------------------------------ device-resident loop (bourse_b200.gym)
+    def step_device(self, d_instrs_ptr: int, d_offsets_ptr: int, n_rows: int, d_out_ids_ptr: int = 0):
+        """One Env::step whose instruction rows are already in device memory (bb_step_device); asynchronous."""
+        self._ck(self._lib.bb_step_device(self._h, C.c_void_p(d_instrs_ptr), C.c_void_p(d_offsets_ptr), n_rows,
+                                          C.c_void_p(d_out_ids_ptr) if d_out_ids_ptr else None))
+
+    def level_2_data_device(self, d_out_ptr: int): self._ck(self._lib.bb_level2_device(self._h, C.c_void_p(d_out_ptr)))
+    def level_1_data_device(self, d_out_ptr: int): self._ck(self._lib.bb_level1_device(self._h, C.c_void_p(d_out_ptr)))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.bb_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int): self._ck(self._lib.bb_device_free(self._h, C.c_void_p(ptr)))
+
+    def memcpy(self, dst: int, src: int, nbytes: int, kind: int):
+        """kind 1 host->device, 2 device->host, 3 device->device; synchronous on the env's stream."""
+        self._ck(self._lib.bb_memcpy(self._h, C.c_void_p(dst), C.c_void_p(src), nbytes, kind))
+
     # ------------------------------------------------------------------ immediate mode / replay
     def replay(self, instrs: np.ndarray, env_offsets=None):
         instrs = np.ascontiguousarray(instrs, dtype=abi.INSTR_DTYPE)

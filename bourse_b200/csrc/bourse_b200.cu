@@ -51,6 +51,8 @@ struct bb_handle {
     MomState* mom = nullptr;
     uint4* scratch = nullptr;
     size_t scratch_warps = 0;
+    u64* d_ids = nullptr;  // bb_step_device: ids assigned on the device when the caller does not ask for them
+    size_t d_ids_cap = 0;
     // pinned host staging
     bb_instr* h_instrs = nullptr;
     size_t h_instrs_cap = 0;
@@ -257,8 +259,8 @@ int check_device_errors(bb_handle* h) {
         CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
         char buf[256];
         snprintf(buf, sizeof buf, "device flagged env errors 0x%x (0x1 orders 0x2 trades 0x4 pages/window 0x8 queue 0x10 bad id "
-                                  "0x20 granule 0x40 steps 0x80 live slots 0x100 time order); see bb_env_errors", flag);
-        return fail(h, (flag & ERR_BAD_ID) ? BB_EBADID : (flag & 0x80000000u) ? BB_ECUDA : BB_ECAP, buf);
+                                  "0x20 granule 0x40 steps 0x80 live slots 0x100 time order 0x200 tick size); see bb_env_errors", flag);
+        return fail(h, (flag & ERR_BAD_ID) ? BB_EBADID : (flag & 0x80000000u) ? BB_ECUDA : (flag & ERR_PRICE) ? BB_EPRICE : BB_ECAP, buf);
     }
     return BB_OK;
 }
@@ -281,13 +283,16 @@ int ensure_instr_capacity(bb_handle* h, size_t n) {
     return BB_OK;
 }
 
-int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_offsets, u32 n_steps, bool host_order = false) {
+int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_offsets, u32 n_steps, bool host_order = false,
+                 u64* d_out_ids = nullptr) {
     KParams p;
     fill_params(h, h->lay_apply, p);
     p.instrs = d_instrs;
     p.offsets = d_offsets;
     p.n_steps = n_steps;
     p.host_order = host_order ? 1u : 0u;
+    p.assign_ids = d_out_ids ? 1u : 0u;
+    p.out_ids = d_out_ids;
     int grid = 0, rc;
     const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
 #define LAUNCH_APPLY(M, E)                                                                       \
@@ -313,20 +318,20 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     return BB_OK;
 }
 
-int snapshot(bb_handle* h, u32 first_env, u32 n, u32* d45, u32* d8) {
+int snapshot(bb_handle* h, u32 first_env, u32 n, u32* d45, u32* d8, u32 words = 45u) {
     KParams p;
     fill_params(h, h->lay_snap, p);
     int grid = 0, rc;
     const size_t smem = (size_t)h->lay_snap.warp_bytes * WPB;
     if (h->eng == ENG_DENSE) {
         if ((rc = grid_for(h, k_snapshot<ENG_DENSE>, h->lay_snap, n, &grid))) return rc;
-        k_snapshot<ENG_DENSE><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n);
+        k_snapshot<ENG_DENSE><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
     } else if (h->eng == ENG_DENSE_L) {
         if ((rc = grid_for(h, k_snapshot<ENG_DENSE_L>, h->lay_snap, n, &grid))) return rc;
-        k_snapshot<ENG_DENSE_L><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n);
+        k_snapshot<ENG_DENSE_L><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
     } else {
         if ((rc = grid_for(h, k_snapshot<ENG_PAGED>, h->lay_snap, n, &grid))) return rc;
-        k_snapshot<ENG_PAGED><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n);
+        k_snapshot<ENG_PAGED><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
     }
     CUDA_TRY(h, cudaGetLastError());
     return BB_OK;
@@ -442,7 +447,7 @@ int bb_destroy(bb_handle* h) {
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     cudaFree(h->blobs); cudaFree(h->ord); cudaFree(h->tr); cudaFree(h->hist); cudaFree(h->err_flag);
     cudaFree(h->d_offsets); cudaFree(h->d_seeds); cudaFree(h->d_instrs); cudaFree(h->d_snap); cudaFree(h->d_stats);
-    cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch);
+    cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch); cudaFree(h->d_ids);
     if (h->h_instrs) cudaFreeHost(h->h_instrs);
     if (h->h_offsets) cudaFreeHost(h->h_offsets);
     if (h->h_snap) cudaFreeHost(h->h_snap);
@@ -667,6 +672,66 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
     h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE, asset != nullptr);  // the on-chip agent state depends on the population
     if (total) CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
     if (mom) CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * sizeof(MomState), h->stream));
+    return BB_OK;
+}
+
+int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows, uint64_t* d_out_ids) {
+    CHECK_H(h);
+    if (!d_env_offsets || (n_rows && !d_instrs)) return fail(h, BB_EINVAL, "null argument");
+    if (h->assets > 1) return fail(h, BB_EINVAL, "bb_step_device drives single-asset envs (multi-asset queues are ordered on the host)");
+    for (auto& q : h->queue)
+        if (!q.empty()) return fail(h, BB_EINVAL, "host-queued instructions pending: call bb_step first");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!d_out_ids) {  // the kernel needs somewhere to keep the ids between assignment and execution
+        if (n_rows + 1 > h->d_ids_cap) {
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_ids);
+            h->d_ids = nullptr;
+            h->d_ids_cap = n_rows + n_rows / 2 + 1024;
+            CUDA_TRY(h, cudaMalloc(&h->d_ids, h->d_ids_cap * 8));
+        }
+        d_out_ids = h->d_ids;
+    }
+    h->mirror_dirty = true;  // ids were handed out on the device
+    return launch_apply(h, MODE_ENV, d_instrs, d_env_offsets, 1, false, d_out_ids);
+}
+
+int bb_level2_device(bb_handle* h, uint32_t* d_out) {
+    CHECK_H(h);
+    if (!d_out) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    return snapshot(h, 0, h->cfg.n_envs, d_out, nullptr, 45u);
+}
+
+int bb_level1_device(bb_handle* h, uint32_t* d_out) {
+    CHECK_H(h);
+    if (!d_out) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    return snapshot(h, 0, h->cfg.n_envs, d_out, nullptr, 9u);
+}
+
+int bb_device_alloc(bb_handle* h, uint64_t bytes, void** d_ptr) {
+    CHECK_H(h);
+    if (!d_ptr) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return BB_OK;
+}
+
+int bb_device_free(bb_handle* h, void* d_ptr) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaFree(d_ptr));
+    return BB_OK;
+}
+
+int bb_memcpy(bb_handle* h, void* dst, const void* src, uint64_t bytes, int kind) {
+    CHECK_H(h);
+    if (kind < 1 || kind > 3) return fail(h, BB_EINVAL, "kind must be 1 (host to device), 2 (device to host) or 3 (device to device)");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, (cudaMemcpyKind)kind, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return BB_OK;
 }
 

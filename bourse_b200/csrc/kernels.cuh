@@ -49,6 +49,10 @@ struct KParams {
     const u64* offsets;
     u32 n_steps;
     u32 host_order;  // MODE_ENV: instructions arrive in processing order with their time offset in bb_instr::t (markets)
+    // MODE_ENV, bb_step_device: rows come straight from the caller's device buffer — ids are assigned here in row order
+    // (create_order at submission, env.rs:173), rows that queue nothing (no-ops, tick errors) are left out of the shuffle
+    u32 assign_ids;
+    u64* out_ids;    // [total rows]: the id each row created, BB_NO_ID for rows that create nothing
     // k_sim
     u32 n_groups, agents_per_env, mom_groups_per_env;
     u32* rslot;
@@ -264,23 +268,57 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_P
                 }
                 const u32 mm = min(m, p.max_queue);
                 // (a) create_order happened at submission (env.rs:173): publish status New for the new ids
-                u32 max_id = 0;
-                for (u32 j = lane; j < mm; j += 32) {
-                    const u32 of = ins[j].op_flags, id = ins[j].order_id;
-                    if ((of & BB_OP_MASK) == BB_OP_NEW && id < g.max_orders) {
-                        stg32(b.oh + (u64)id * ORD_STRIDE + OH_META, ST_NEW | ((of & BB_F_BID) ? META_BID : 0u));
-                        max_id = max(max_id, id + 1);
+                u32 nv = mm;  // transactions in the queue
+                if (p.assign_ids) {
+                    // device-submitted rows: what Env::place_order / cancel_order / modify_order would have done at
+                    // submission happens here, in row order — NEW rows take the next ids; a limit price off the tick grid
+                    // is create_order's PriceError (orderbook.rs:367-383): nothing is created or queued, the env is flagged
+                    u32 next = b.n_orders;
+                    nv = 0;
+                    for (u32 j0 = 0; j0 < mm; j0 += 32) {
+                        const u32 j = j0 + lane;
+                        u32 of = 0, price = 0;
+                        if (j < mm) {
+                            of = ins[j].op_flags;
+                            price = ins[j].price;
+                        }
+                        const u32 op = of & BB_OP_MASK;
+                        const bool bad_tick = op == BB_OP_NEW && !(of & BB_F_MARKET) && (price % g.tick != 0u);
+                        const bool is_new = op == BB_OP_NEW && !bad_tick;
+                        const bool queued = is_new || op == BB_OP_CANCEL || op == BB_OP_MODIFY;
+                        const u32 below = (1u << lane) - 1u;
+                        const u32 nm = __ballot_sync(BB_FULL, is_new), qm = __ballot_sync(BB_FULL, queued);
+                        const u32 id = next + __popc(nm & below);
+                        if (j < mm) {
+                            p.out_ids[off + j] = is_new ? (u64)id : ~0ULL;
+                            if (is_new && id < g.max_orders)
+                                stg32(b.oh + (u64)id * ORD_STRIDE + OH_META, ST_NEW | ((of & BB_F_BID) ? META_BID : 0u));
+                        }
+                        if (queued) sts16(perm + 2u * (nv + __popc(qm & below)), j);
+                        if (__any_sync(BB_FULL, bad_tick)) b.err |= ERR_PRICE;
+                        next += __popc(nm);
+                        nv += __popc(qm);
                     }
-                    sts16(perm + 2u * j, j);
+                    b.n_orders = next;
+                } else {
+                    u32 max_id = 0;
+                    for (u32 j = lane; j < mm; j += 32) {
+                        const u32 of = ins[j].op_flags, id = ins[j].order_id;
+                        if ((of & BB_OP_MASK) == BB_OP_NEW && id < g.max_orders) {
+                            stg32(b.oh + (u64)id * ORD_STRIDE + OH_META, ST_NEW | ((of & BB_F_BID) ? META_BID : 0u));
+                            max_id = max(max_id, id + 1);
+                        }
+                        sts16(perm + 2u * j, j);
+                    }
+                    max_id = __reduce_max_sync(BB_FULL, max_id);
+                    if (max_id > b.n_orders) b.n_orders = max_id;
                 }
-                max_id = __reduce_max_sync(BB_FULL, max_id);
-                if (max_id > b.n_orders) b.n_orders = max_id;
                 __syncwarp();
                 // (b) transactions.shuffle(rng) (env.rs:121): Fisher-Yates from the back.  Multi-asset markets shuffle
                 // one queue across their books (market_env.rs:114-115): the host did that, the slice is in order
                 if (!p.host_order) {
                     u64 s0 = lds64(b.sb + HDR_RNG0), s1 = lds64(b.sb + HDR_RNG1);
-                    for (u32 i = mm; i > 1; --i) {
+                    for (u32 i = nv; i > 1; --i) {
                         const u32 j = xoroshiro_range(s0, s1, i);
                         const u32 x = lds16(perm + 2u * (i - 1)), y = lds16(perm + 2u * j);
                         sts16(perm + 2u * (i - 1), y);
@@ -291,11 +329,14 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_P
                 }
                 __syncwarp();
                 // (c) process in shuffled order at t = start + i (env.rs:123-127)
-                for (u32 i0 = 0; i0 < mm; i0 += 32) {
-                    const u32 cnt = min(32u, mm - i0);
+                for (u32 i0 = 0; i0 < nv; i0 += 32) {
+                    const u32 cnt = min(32u, nv - i0);
                     if (lane < cnt) {
-                        const uint4* src = reinterpret_cast<const uint4*>(ins + lds16(perm + 2u * (i0 + lane)));
-                        sts128(chunk + 32u * lane, src[0]);
+                        const u32 pj = lds16(perm + 2u * (i0 + lane));
+                        const uint4* src = reinterpret_cast<const uint4*>(ins + pj);
+                        uint4 x0 = src[0];
+                        if (p.assign_ids && (x0.z & BB_OP_MASK) == BB_OP_NEW) x0.w = (u32)p.out_ids[off + pj];
+                        sts128(chunk + 32u * lane, x0);
                         sts128(chunk + 32u * lane + 16u, src[1]);
                     }
                     __syncwarp();
@@ -878,7 +919,7 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
 // Live market data of every book: out45[env][45] (level_2_data layout) and out8[env][8] =
 // OrderBook::level_1_data field order (orderbook.rs:287-301, touch by the `volumes` map).
 template <int ENG> __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParams p, u32* out45, u32* out8,
-                                                                     u32 first_env, u32 n_out) {
+                                                                     u32 first_env, u32 n_out, u32 words = 45u) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const u32 sb = keep32(smem_u32(smem) + warp * p.warp_smem_bytes);
@@ -900,9 +941,9 @@ template <int ENG> __global__ void __launch_bounds__(128) k_snapshot(const __gri
         book_from_header(g, b);
         u32 w0, w1;
         book_obs(g, b, 45u, &w0, &w1);
-        if (out45) {
-            out45[(size_t)i * 45u + lane] = w0;
-            if (lane + 32u < 45u) out45[(size_t)i * 45u + 32u + lane] = w1;
+        if (out45) {  // `words` = 45 (level-2 record) or 9 (its level-1 prefix, rows packed)
+            if (lane < words) out45[(size_t)i * words + lane] = w0;
+            if (lane + 32u < words) out45[(size_t)i * words + 32u + lane] = w1;
         }
         if (out8) {
             u32 bv, bc, av, ac;

@@ -1,0 +1,147 @@
+"""Vectorised, device-resident environment loop.
+
+The reference's array API — `StepEnvNumpy.submit_instructions(...)` then `step()` then `level_2_data()`
+(rust/src/step_sim_numpy.rs:233-275, :139-145, :351-368) — is the shape an RL loop uses, one env at a time with numpy
+arrays on the host.  `VectorEnv` is that loop batched over `n_envs` envs with every array resident in DEVICE memory:
+actions go in as a `[n_envs, rows_per_env]` block of packed instruction rows, the new order ids and the level-1 / level-2
+observations come back as device arrays, and nothing crosses PCIe per step unless the caller asks for a host copy.
+
+Buffers are exchanged through the CUDA array interface (`__cuda_array_interface__`, version 3), which torch, cupy and
+numba all speak, so this module needs none of them: `torch.as_tensor(env.obs, device="cuda")` is a zero-copy view, and a
+torch / cupy array can be passed to `step` directly.  numpy arrays are accepted too (copied host to device).
+"""
+from __future__ import annotations
+
+import typing
+
+import numpy as np
+
+from . import abi
+from .core import BatchedEnv
+
+ACTION_DTYPE = abi.INSTR_DTYPE  # one row = one instruction: (t ignored, op_flags, order_id, price, vol, trader, aux)
+
+
+class DeviceArray:
+    """A C-contiguous array in device memory owned by a `BatchedEnv`; speaks `__cuda_array_interface__`."""
+
+    def __init__(self, env: BatchedEnv, shape: typing.Tuple[int, ...], dtype):
+        self._env, self.shape, self.dtype = env, tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = env.device_alloc(self.nbytes)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def numpy(self) -> np.ndarray:
+        """Host copy (synchronises the env's stream)."""
+        out = np.empty(self.shape, self.dtype)
+        self._env.memcpy(out.ctypes.data, self.ptr, self.nbytes, 2)
+        return out
+
+    def copy_from_host(self, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        assert a.nbytes == self.nbytes, "size mismatch"
+        self._env.memcpy(self.ptr, a.ctypes.data, self.nbytes, 1)
+
+    def free(self):
+        if self.ptr:
+            self._env.device_free(self.ptr)
+            self.ptr = 0
+
+
+def _device_ptr(x, nbytes: int) -> typing.Optional[int]:
+    cai = getattr(x, "__cuda_array_interface__", None)
+    if cai is None:
+        return None
+    if cai.get("strides") is not None:
+        raise ValueError("device arrays must be C-contiguous")
+    n = int(np.prod(cai["shape"])) * np.dtype(cai["typestr"]).itemsize
+    if n != nbytes:
+        raise ValueError(f"device array holds {n} bytes, expected {nbytes}")
+    return int(cai["data"][0])
+
+
+def pack_actions(op, bid=None, vol=None, trader=None, price=None, order_id=None, market=None, has_price=None, has_vol=None) -> np.ndarray:
+    """Columns -> packed instruction rows (host numpy, any shape).  `op`: abi.OP_NOOP / OP_NEW / OP_CANCEL / OP_MODIFY.
+    NEW rows: `market=True` is a market order (`price=None` in the reference).  MODIFY rows: `has_price` / `has_vol` say
+    which of `price` / `vol` is `Some` (default: both)."""
+    op = np.asarray(op, dtype=np.uint32)
+    a = np.zeros(op.shape, dtype=ACTION_DTYPE)
+
+    def col(x, default=0):
+        return np.broadcast_to(np.asarray(default if x is None else x), op.shape)
+
+    f = op.copy()
+    f |= np.where(col(bid).astype(bool) & (op == abi.OP_NEW), abi.F_BID, 0).astype(np.uint32)
+    f |= np.where(col(market).astype(bool) & (op == abi.OP_NEW), abi.F_MARKET, 0).astype(np.uint32)
+    mod = op == abi.OP_MODIFY
+    f |= np.where(mod & col(has_price, 1).astype(bool), abi.F_HAS_PRICE, 0).astype(np.uint32)
+    f |= np.where(mod & col(has_vol, 1).astype(bool), abi.F_HAS_VOL, 0).astype(np.uint32)
+    a["op_flags"] = f
+    oid = col(order_id).astype(np.uint64)
+    a["order_id"] = np.where(oid > 0xFFFFFFFE, 0xFFFFFFFF, oid).astype(np.uint32)  # ids beyond u32 cannot exist: bad id
+    a["price"], a["vol"], a["trader"] = col(price), col(vol), col(trader)
+    return a
+
+
+class VectorEnv:
+    """`n_envs` lockstep `StepEnvNumpy(seed + env, start_time, tick_size, step_size, trading)` instances with a fixed action
+    block of `rows_per_env` instruction rows per env and step (pad with OP_NOOP rows).
+
+        env = VectorEnv(4096, rows_per_env=8, seed=0, start_time=0, tick_size=1, step_size=1000)
+        obs = env.reset()                       # DeviceArray [n_envs, 45] u32, StepEnvNumpy.level_2_data layout
+        obs, ids = env.step(actions)            # actions: [n_envs, rows_per_env] packed rows, device or host
+        t = torch.as_tensor(obs, device="cuda") # zero-copy
+
+    `ids[e, r]` is the order id row r created in env e, or `abi.NO_ID` (2^64 - 1) for cancel / modify / no-op rows
+    (step_sim_numpy.rs:256-267).  Semantics per env are exactly `submit_instructions` + `step`: ids in row order, the
+    step's queue shuffled with the env's own Xoroshiro stream, event i at `t + i`.  A NEW row with an off-tick limit
+    price creates nothing (the reference raises ValueError there); the env is flagged and `check_errors` raises."""
+
+    def __init__(self, n_envs: int, rows_per_env: int, seed: int, start_time: int, tick_size: int, step_size: int,
+                 trading: bool = True, *, level_1: bool = False, **kw):
+        kw.setdefault("max_queue", max(rows_per_env, 16))
+        if rows_per_env > kw["max_queue"]:
+            raise ValueError("rows_per_env exceeds max_queue")
+        self.n_envs, self.rows = n_envs, rows_per_env
+        self.env = BatchedEnv(n_envs, seed, start_time, tick_size, step_size, trading, obs_words=abi.OBS_L1 if level_1 else abi.OBS_L2, **kw)
+        self.obs_words = abi.OBS_L1 if level_1 else abi.OBS_L2
+        self.obs = DeviceArray(self.env, (n_envs, self.obs_words), np.uint32)
+        self.ids = DeviceArray(self.env, (n_envs, rows_per_env), np.uint64)
+        self._actions = DeviceArray(self.env, (n_envs, rows_per_env), ACTION_DTYPE)  # staging for host-side actions
+        self._offsets = DeviceArray(self.env, (n_envs + 1,), np.uint64)
+        self._offsets.copy_from_host(np.arange(n_envs + 1, dtype=np.uint64) * np.uint64(rows_per_env))
+
+    def close(self):
+        for a in (self.obs, self.ids, self._actions, self._offsets):
+            a.free()
+        self.env.close()
+
+    def _observe(self) -> DeviceArray:
+        (self.env.level_1_data_device if self.obs_words == abi.OBS_L1 else self.env.level_2_data_device)(self.obs.ptr)
+        return self.obs
+
+    def reset(self) -> DeviceArray:
+        self.env.reset()
+        return self._observe()
+
+    def step(self, actions) -> typing.Tuple[DeviceArray, DeviceArray]:
+        nbytes = self.n_envs * self.rows * ACTION_DTYPE.itemsize
+        ptr = _device_ptr(actions, nbytes)
+        if ptr is None:  # host array: one H2D copy
+            a = np.ascontiguousarray(actions, dtype=ACTION_DTYPE)
+            if a.shape != (self.n_envs, self.rows):
+                raise ValueError(f"actions must have shape ({self.n_envs}, {self.rows})")
+            self._actions.copy_from_host(a)
+            ptr = self._actions.ptr
+        self.env.step_device(ptr, self._offsets.ptr, self.n_envs * self.rows, self.ids.ptr)
+        return self._observe(), self.ids
+
+    def check_errors(self):
+        """Raise if any env flagged an error (capacity, bad order id, off-tick price); synchronises."""
+        e = self.env.env_errors()
+        if e.any():
+            bad = np.flatnonzero(e)
+            raise RuntimeError(f"{len(bad)} env(s) flagged errors, first env {bad[0]}: 0x{int(e[bad[0]]):x}")

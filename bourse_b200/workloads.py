@@ -80,6 +80,12 @@ def c4_groups():
             momentum_group(80, 20, 1, 0.1, 10, 1.0, 5.0, 0.5, 1.0, 0.0, 1.0)]
 
 
+def market_example_groups():
+    """crates/step_sim/examples/multi_asset/main.rs:15-20 — MarketEnv::<2>, (50 + 50) RandomMarketAgents on each asset.
+    Returns (groups, asset of each group) for BatchedEnv.set_agents(groups, assets=...)."""
+    return c3_groups() + c3_groups(), [0, 0, 1, 1]
+
+
 def algorithmic_bytes(stats: dict, obs_words: int, ext_instructions: int = 0) -> int:
     """25*I_ext + 42*N_created + 26*N_transitions + 33*N_trades + OBS*E."""
     return (25 * ext_instructions + 42 * stats["orders_created"] + 26 * stats["transitions"] + 33 * stats["trades"]

@@ -46,6 +46,7 @@ typedef enum {
 #define BB_ERR_CAP_STEPS  0x40u
 #define BB_ERR_CAP_LIVE   0x80u  /* MomentumAgent live-order list / dense engine's resting-order slots overflow */
 #define BB_ERR_TIME_ORDER 0x100u /* dense engine: a resting order arrived out of time order at its price level */
+#define BB_ERR_PRICE 0x200u      /* bb_step_device: a NEW row's limit price was not a multiple of tick_size (row dropped) */
 
 #define BB_OBS_L1 9u   /* StepEnvNumpy.level_1_data layout, rust/src/step_sim_numpy.rs:300-318 */
 #define BB_OBS_L2 45u  /* StepEnvNumpy.level_2_data layout, rust/src/step_sim_numpy.rs:351-368 */
@@ -185,6 +186,24 @@ int bb_submit(bb_handle* h, uint64_t n, const uint32_t* env, const uint32_t* act
               const uint32_t* flags, uint64_t* out_ids, uint64_t* n_done);
 /* Env::step for every env, n_steps times (queued instructions are consumed by the first). */
 int bb_step(bb_handle* h, uint32_t n_steps);
+
+/* Vectorised Env loop with DEVICE-resident actions (the array call it batches is
+ * StepEnvNumpy.submit_instructions + step, rust/src/step_sim_numpy.rs:233-275, :139-145): the step's rows for every env
+ * are already in device memory (d_env_offsets[n_envs + 1] delimits each env's slice of d_instrs, bb_instr::t is ignored)
+ * and never visit the host.  Per env, in row order, exactly what submission would have done: BB_OP_NEW rows create the
+ * next order ids (d_out_ids[row], BB_NO_ID for every other row; may be NULL), BB_OP_CANCEL / BB_OP_MODIFY rows are queued,
+ * BB_OP_NOOP and unknown codes queue nothing; then ONE Env::step.  A NEW row whose limit price is off the tick grid is
+ * dropped, as when create_order returns PriceError, and flags the env with BB_ERR_PRICE (the next synchronous call
+ * reports BB_EPRICE).  Asynchronous on the handle's stream. */
+int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows, uint64_t* d_out_ids);
+/* bb_level2 / bb_level1 into DEVICE memory: d_out[n_envs][45] / d_out[n_envs][9].  Asynchronous. */
+int bb_level2_device(bb_handle* h, uint32_t* d_out);
+int bb_level1_device(bb_handle* h, uint32_t* d_out);
+/* Device buffers for callers without a CUDA allocator of their own (numpy-only hosts); any device pointer works above.
+ * bb_memcpy kind: 1 host to device, 2 device to host, 3 device to device; synchronous on the handle's stream. */
+int bb_device_alloc(bb_handle* h, uint64_t bytes, void** d_ptr);
+int bb_device_free(bb_handle* h, void* d_ptr);
+int bb_memcpy(bb_handle* h, void* dst, const void* src, uint64_t bytes, int kind);
 
 /* ---- immediate mode: OrderBook API / replayed streams (orderbook.rs:411-792) ------------------ */
 /* env_offsets[n_envs + 1] delimits each env's slice of `instrs`.  Every instruction executes at its

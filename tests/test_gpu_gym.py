@@ -1,0 +1,138 @@
+"""GPU suite for the device-resident vectorised loop (bourse_b200.gym.VectorEnv, bb_step_device / bb_level2_device):
+per env it must be exactly StepEnvNumpy.submit_instructions + step + level_2_data of the reference
+(rust/src/step_sim_numpy.rs:233-275), checked against one oracle StepEnvNumpy per env on the same rows."""
+import numpy as np
+import pytest
+
+from bourse_b200 import abi, gym
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_actions(rng, n_envs, rows, issued, tick):
+    """Rows mixing limit / market orders (some off the tick grid), cancels and modifies of issued ids, and no-ops."""
+    op = np.zeros((n_envs, rows), np.uint32)
+    cols = {k: np.zeros((n_envs, rows), np.uint64) for k in ("bid", "vol", "trader", "price", "order_id", "market", "has_price", "has_vol")}
+    for e in range(n_envs):
+        for r in range(rows):
+            u = rng.random()
+            if u < 0.15:
+                continue
+            if u < 0.65 or issued[e] == 0:
+                op[e, r] = abi.OP_NEW
+                cols["bid"][e, r] = rng.random() < 0.5
+                cols["vol"][e, r] = rng.integers(1, 50)
+                cols["trader"][e, r] = rng.integers(0, 1000)
+                cols["market"][e, r] = rng.random() < 0.07
+                cols["price"][e, r] = tick * rng.integers(40, 61) + (1 if tick > 1 and rng.random() < 0.05 else 0)
+            elif u < 0.85:
+                op[e, r] = abi.OP_CANCEL
+                cols["order_id"][e, r] = rng.integers(0, issued[e])
+            else:
+                op[e, r] = abi.OP_MODIFY
+                cols["order_id"][e, r] = rng.integers(0, issued[e])
+                hp, hv = rng.random() < 0.6, rng.random() < 0.6
+                cols["has_price"][e, r], cols["has_vol"][e, r] = hp, hv
+                cols["price"][e, r] = tick * rng.integers(40, 61)
+                cols["vol"][e, r] = rng.integers(1, 50)
+    return op, cols
+
+
+def _oracle_step(o, op, cols, e, rows):
+    ids = np.full(rows, abi.NO_ID, np.uint64)
+    bad = False
+    for r in range(rows):
+        k = op[e, r]
+        if k == abi.OP_NEW:
+            price = None if cols["market"][e, r] else int(cols["price"][e, r])
+            try:
+                ids[r] = o.place_order(bool(cols["bid"][e, r]), int(cols["vol"][e, r]), int(cols["trader"][e, r]), price)
+            except ValueError:
+                bad = True
+        elif k == abi.OP_CANCEL:
+            o.cancel_order(int(cols["order_id"][e, r]))
+        elif k == abi.OP_MODIFY:
+            o.modify_order(int(cols["order_id"][e, r]), int(cols["price"][e, r]) if cols["has_price"][e, r] else None,
+                           int(cols["vol"][e, r]) if cols["has_vol"][e, r] else None)
+    o.step()
+    return ids, bad
+
+
+@pytest.mark.parametrize("kw,tick", [(dict(), 1), (dict(), 2), (dict(price_window=(32, 96), live_cap=254), 1)], ids=["paged_t1", "paged_t2", "dense"])
+def test_vector_env_matches_one_step_env_per_env(oracle, kw, tick):
+    n_envs, rows, n_steps, seed = 40, 7, 30, 11
+    rng = np.random.default_rng(5)
+    v = gym.VectorEnv(n_envs, rows, seed, 0, tick, 1000, max_orders=1024, max_trades=4096, max_steps=64, **kw)
+    orcs = [oracle.StepEnv(seed + e, 0, tick, 1000) for e in range(n_envs)]
+    issued = np.zeros(n_envs, np.int64)
+    obs0 = v.reset().numpy()
+    assert np.array_equal(obs0, np.stack([o.level_2_data_array() for o in orcs]))
+    flagged = np.zeros(n_envs, bool)
+    for _ in range(n_steps):
+        op, cols = _random_actions(rng, n_envs, rows, issued, tick)
+        obs, ids = v.step(gym.pack_actions(op, **cols))
+        obs, ids = obs.numpy(), ids.numpy()
+        for e in range(n_envs):
+            want, bad = _oracle_step(orcs[e], op, cols, e, rows)
+            flagged[e] |= bad
+            assert np.array_equal(ids[e], want), e
+            assert np.array_equal(obs[e], orcs[e].level_2_data_array()), e
+            issued[e] = len(orcs[e].get_orders())
+    err = v.env.env_errors()
+    assert np.array_equal((err & 0x200) != 0, flagged) and not (err & ~np.uint32(0x200)).any()
+    assert tick == 1 or flagged.any()
+    for e in range(0, n_envs, 7):
+        assert v.env.get_trades(e) == orcs[e].get_trades() and v.env.get_orders(e) == orcs[e].get_orders()
+    if flagged.any():
+        with pytest.raises(RuntimeError):
+            v.check_errors()
+    v.close()
+
+
+def test_vector_env_zero_copy_with_torch(oracle):
+    """Actions produced on the device (a torch tensor) go in without a host round trip; observations and ids are read
+    through the CUDA array interface as torch views."""
+    import torch
+
+    n_envs, rows = 256, 4
+    v = gym.VectorEnv(n_envs, rows, 3, 0, 1, 1000, level_1=True, max_orders=512, max_trades=512, max_steps=16)
+    obs_t = torch.as_tensor(v.obs, device="cuda")
+    ids_t = torch.as_tensor(v.ids, device="cuda")
+    assert obs_t.shape == (n_envs, 9) and obs_t.data_ptr() == v.obs.ptr
+    v.reset()
+    # every env: bid 10 @ 50, ask 10 @ 52, ask 5 @ 50 (crosses half of the bid), no-op
+    a = gym.pack_actions(np.tile(np.array([abi.OP_NEW, abi.OP_NEW, abi.OP_NEW, abi.OP_NOOP], np.uint32), (n_envs, 1)),
+                         bid=np.tile([1, 0, 0, 0], (n_envs, 1)), vol=np.tile([10, 10, 5, 0], (n_envs, 1)),
+                         price=np.tile([50, 52, 50, 0], (n_envs, 1)), trader=7)
+    dev_actions = torch.from_numpy(a.view(np.uint8).reshape(n_envs, rows, 32)).cuda()
+    torch.cuda.synchronize()
+    v.step(dev_actions)
+    v.env.synchronize()
+    ids = ids_t.cpu().numpy()
+    assert (ids[:, :3] == np.arange(3, dtype=np.uint64)).all() and (ids[:, 3] == abi.NO_ID).all()
+    obs = obs_t.cpu().numpy().astype(np.uint32)
+    for e in (0, 100, 255):
+        o = oracle.StepEnvNumpy(3 + e, 0, 1, 1000)
+        o.submit_instructions((np.array([1, 1, 1, 0], np.uint32), np.array([True, False, False, False]), np.array([10, 10, 5, 0], np.uint32),
+                               np.full(4, 7, np.uint32), np.array([50, 52, 50, 0], np.uint32), np.zeros(4, np.uint64)))
+        o.step()
+        assert np.array_equal(obs[e], o.level_1_data()), e
+    # depending on the shuffle the ask at 50 either traded with the bid or rests in front of it
+    assert set(np.unique(obs[:, 0])) <= {0, 5}
+    v.check_errors()
+    v.close()
+
+
+def test_step_device_argument_checks():
+    from bourse_b200 import core
+    e = core.BatchedEnv(4, 0, 0, 1, 1000, assets=2, max_orders=64, max_trades=64, max_steps=8, max_queue=16)
+    p = e.device_alloc(64)
+    with pytest.raises(ValueError, match="single-asset"):
+        e.step_device(p, p, 0)
+    e.device_free(p)
+    e2 = core.BatchedEnv(1, 0, 0, 1, 1000, max_orders=64, max_trades=64, max_steps=8, max_queue=16)
+    e2.submit([abi.ACT_NEW], [1], [1], [0], [10])
+    p = e2.device_alloc(64)
+    with pytest.raises(ValueError, match="pending"):
+        e2.step_device(p, p, 0)
+    e2.device_free(p)

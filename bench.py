@@ -448,7 +448,7 @@ def run_gpu_other(args):
         obs, n_steps = abi.OBS_L2, args.sim_steps
         eng_kw = dict(price_window=(20, 180), live_cap=128) if args.engine == "dense" else {}
         env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=args.max_orders,
-                              max_trades=args.max_trades, max_steps=n_steps, max_queue=128, assets=n_assets, **eng_kw)
+                              max_trades=args.max_trades, max_steps=n_steps, max_queue=args.max_queue or 80, assets=n_assets, **eng_kw)
         env.set_agents(groups, assets=g_assets)
         env.set_stream(stream.cuda_stream)
         for i in range(args.warmup + args.steps):
@@ -556,6 +556,7 @@ def main():
     ap.add_argument("--sim-steps", type=int, default=N_SIM_STEPS)
     ap.add_argument("--max-orders", type=int, default=65536)
     ap.add_argument("--max-trades", type=int, default=65536)
+    ap.add_argument("--max-queue", type=int, default=0, help="per-env instructions per step (0 = the workload's default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default="dense", choices=["dense", "paged"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "market"],

@@ -70,6 +70,7 @@ struct bb_handle {
     std::vector<bb_agent_group> groups;
     std::vector<u32> group_asset;  // bb_set_agents_market: asset each group trades (empty: single-asset agents)
     u32 agents_per_env = 0, mom_groups = 0;
+    u32 chip_agents = 0;  // on-chip agent table capacity of the dense engine (markets: the largest per-asset agent count)
     // host mirrors for Env mode
     std::vector<std::vector<bb_instr>> queue;
     std::vector<u64> n_orders_host;  // ids handed out so far (includes queued NEW)
@@ -139,13 +140,13 @@ SmemLayout make_layout(const bb_handle* h, bool with_obs, bool with_instr, bool 
     if (market) off += 4u * align_up(h->assets * h->cfg.max_queue, 8) + 16u;
     else off += align_up((with_queue ? 2u : 4u) * h->cfg.max_queue + 16u, 16);
     l.off_obs = off;
-    if (with_obs) off += align_up(2u * OBS_STAGE_STEPS(h->cfg.obs_words) * h->cfg.obs_words * 4u, 16);
+    if (with_obs) off += align_up((market ? 1u : 2u) * OBS_STAGE_STEPS(h->cfg.obs_words) * h->cfg.obs_words * 4u, 16);
     l.off_instr = off;
     if (with_instr) off += 2048;
     l.off_q = off;
     if (with_queue) off += 16u * h->cfg.max_queue + 32u;  // + two entries of padding for the one-ahead fetch
     l.off_ag = off;
-    if (with_queue) off += align_up(5u * h->agents_per_env + 1u, 16);  // held id u32 [A], slot u8 [A + 1]
+    if (with_queue) off += align_up(5u * h->chip_agents + 1u, 16);  // held id u32 [A], slot u8 [A + 1]
     l.off_bar = off;
     off += 32;
     l.off_mkt = off;  // u32 [2][MAX_GROUPS]: the market's per-group instruction counts, double-buffered
@@ -668,6 +669,16 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
     h->group_asset.clear();
     if (asset) h->group_asset.assign(asset, asset + n_groups);
     h->agents_per_env = total;
+    h->chip_agents = total;
+    if (asset) {
+        h->chip_agents = 0;
+        for (u32 a = 0; a < h->assets; ++a) {
+            u32 n = 0;
+            for (u32 i = 0; i < n_groups; ++i)
+                if (asset[i] == a) n += groups[i].n_agents;
+            h->chip_agents = std::max(h->chip_agents, n);
+        }
+    }
     h->mom_groups = mom;
     h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE, asset != nullptr);  // the on-chip agent state depends on the population
     if (total) CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
@@ -767,6 +778,7 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     p.n_steps = n_steps;
     p.n_groups = (u32)h->groups.size();
     p.agents_per_env = h->agents_per_env;
+    p.chip_agents = h->chip_agents;
     p.mom_groups_per_env = h->mom_groups;
     p.rslot = h->rslot;
     p.mom = h->mom;

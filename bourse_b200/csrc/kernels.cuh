@@ -55,6 +55,7 @@ struct KParams {
     u64* out_ids;    // [total rows]: the id each row created, BB_NO_ID for rows that create nothing
     // k_sim
     u32 n_groups, agents_per_env, mom_groups_per_env;
+    u32 chip_agents;  // dense engine: capacity of the on-chip agent tables (agents_per_env; markets: the largest per-asset count)
     u32* rslot;
     MomState* mom;
     uint4* scratch;  // [resident warps][max_queue]
@@ -410,13 +411,15 @@ __device__ __forceinline__ void random_agents_update(const KParams& p, const bb_
 // in (u8 [A + 1] at Book::ags, entry 0 unused) live in shared memory for the whole launch, so "is my order still
 // Active" is a shared-memory compare of the slot's id instead of a gather from the HBM order table, and the
 // emitted instructions carry the hints described at d_apply (dense.cuh).
+// `chip_base`: index of the group's first agent in the on-chip tables (== slot_base except in markets, whose books keep
+// only their own groups' agents on chip).
 template <class G>
 __device__ __forceinline__ void random_agents_update_dense(const KParams& p, const bb_agent_group& ag, const Book& b, u32 qs, Emit& e,
-                                                           u32 agh, u32 env_g, u32 step, u32 slot_base) {
+                                                           u32 agh, u32 env_g, u32 step, u32 slot_base, u32 chip_base) {
     for (u32 a0 = 0; a0 < ag.n_agents; a0 += 32) {
         const u32 a = a0 + b.lane;
         const bool valid = a < ag.n_agents;
-        const u32 ai = valid ? slot_base + a : 0u;
+        const u32 ai = valid ? chip_base + a : 0u;
         const uint4 r = philox4x32_10(env_g, step, slot_base + a, 0, p.seed_lo, p.seed_hi);
         const bool active = valid && (u32_to_f32_unit(r.x) < ag.rate);
         const u32 held = lds(agh + 4u * ai);
@@ -573,8 +576,11 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
 }
 
 // named barrier over the warps of one market (bar.sync with an explicit thread count)
+// Barrier ids are immediates (a CTA holds at most two markets): with a register id ptxas reserves all 16 hardware
+// barriers for the CTA, which caps residency at 4 CTAs per SM.
 __device__ __forceinline__ void market_bar_sync(u32 id, u32 n_threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+    if (id == 1u) asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"r"(n_threads) : "memory");
 }
 
 // MKT: multi-asset markets with in-kernel agents — market_sim_runner (runner.rs:107-131) over the *Market agent twins
@@ -631,20 +637,29 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
         u32* slots = p.rslot + (size_t)env * p.agents_per_env;
         const u32 agh = sb + p.off_ag;  // dense engine: held order id per agent, u32 [agents_per_env]
         if constexpr (G::DENSE) {
-            // bring the agents' held ids on chip and find the slot each one rests in (one pass over the slot table)
-            b.ags = agh + 4u * p.agents_per_env;
-            for (u32 a0 = 0; a0 < p.agents_per_env; a0 += 32) {
-                const u32 a = a0 + lane;
-                const u32 held = a < p.agents_per_env ? slots[a] : BB_NIL;
-                u32 hs = 0;
-                for (u32 s4 = 0; s4 < G::DL::LP; s4 += 4) {
-                    const uint4 v = lds128(b.sb + G::DL::OFF_ID + 4u * s4);
-                    hs = v.x == held ? s4 : v.y == held ? s4 + 1u : v.z == held ? s4 + 2u : v.w == held ? s4 + 3u : hs;
+            // bring the agents' held ids on chip and find the slot each one rests in (one pass over the slot table);
+            // markets keep only the agents of this book's own groups on chip, packed in declaration order
+            b.ags = agh + 4u * p.chip_agents;
+            u32 gbase = 0, cbase = 0;
+            for (u32 gi = 0; gi < (MKT ? p.n_groups : 1u); ++gi) {
+                const u32 ng = MKT ? p.groups[gi].n_agents : p.agents_per_env;
+                if (!MKT || p.group_asset[gi] == mk_a) {
+                    for (u32 a0 = 0; a0 < ng; a0 += 32) {
+                        const u32 a = a0 + lane;
+                        const u32 held = a < ng ? slots[gbase + a] : BB_NIL;
+                        u32 hs = 0;
+                        for (u32 s4 = 0; s4 < G::DL::LP; s4 += 4) {
+                            const uint4 v = lds128(b.sb + G::DL::OFF_ID + 4u * s4);
+                            hs = v.x == held ? s4 : v.y == held ? s4 + 1u : v.z == held ? s4 + 2u : v.w == held ? s4 + 3u : hs;
+                        }
+                        if (a < ng) {
+                            sts(agh + 4u * (cbase + a), held);
+                            sts8(b.ags + 1u + cbase + a, hs);
+                        }
+                    }
+                    cbase += ng;
                 }
-                if (a < p.agents_per_env) {
-                    sts(agh + 4u * a, held);
-                    sts8(b.ags + 1u + a, hs);
-                }
+                gbase += ng;
             }
             __syncwarp();
         }
@@ -660,7 +675,7 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
             e.n = 0;
             e.next_id = b.n_orders;
             const u32 id0 = b.n_orders;
-            u32 slot_base = 0, mi = 0;
+            u32 slot_base = 0, chip_base = 0, mi = 0;
             u32 mk_cnt = 0;  // markets: lane gi holds the number of instructions group gi queued (own groups only)
             for (u32 gi = 0; gi < p.n_groups; ++gi) {
                 const bb_agent_group& ag = p.groups[gi];
@@ -668,7 +683,7 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
                 const u32 n_before = e.n;
                 if (!MOM || ag.kind == BB_GROUP_RANDOM) {
                     if (mine) {
-                        if constexpr (G::DENSE) random_agents_update_dense<G>(p, ag, b, qs, e, agh, env_g, step, slot_base);
+                        if constexpr (G::DENSE) random_agents_update_dense<G>(p, ag, b, qs, e, agh, env_g, step, slot_base, chip_base);
                         else random_agents_update(p, ag, b, q, e, slots, env_g, step, slot_base);
                     }
                 } else {
@@ -684,6 +699,7 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
                 }
                 if (MKT && lane == gi) mk_cnt = e.n - n_before;
                 slot_base += ag.n_agents;
+                if (mine) chip_base += ag.n_agents;
             }
             if (e.n > p.max_queue) b.err |= ERR_CAP_QUEUE;
             u32 n = min(e.n, p.max_queue);
@@ -883,12 +899,14 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
                     if (lane == 0) {
                         bulk_s2g_a(hist_env + (size_t)sbase * p.obs_words, stage + 4u * (sbuf * stage_words), stage_words * 4u);
                         bulk_commit();
-                        bulk_wait_read<1>();  // the other buffer's previous flush has released its source
+                        // the other buffer's previous flush has released its source; markets stage in ONE buffer (shared
+                        // memory is what limits their occupancy) and wait for this flush's reads, ~1 us per 4 steps
+                        if (MKT) bulk_wait_read<0>(); else bulk_wait_read<1>();
                     }
                     __syncwarp();
                     sbase += stage_steps;
                     sfill = 0;
-                    sbuf ^= 1u;
+                    if (!MKT) sbuf ^= 1u;
                 }
             } else {
                 emit_obs_direct(g, b, p, env);
@@ -906,7 +924,15 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
         sts(b.sb + HDR_STEPCTR, step);
         if constexpr (G::DENSE) {
             __syncwarp();
-            for (u32 a = lane; a < p.agents_per_env; a += 32) slots[a] = lds(agh + 4u * a);
+            u32 gbase = 0, cbase = 0;
+            for (u32 gi = 0; gi < (MKT ? p.n_groups : 1u); ++gi) {
+                const u32 ng = MKT ? p.groups[gi].n_agents : p.agents_per_env;
+                if (!MKT || p.group_asset[gi] == mk_a) {
+                    for (u32 a = lane; a < ng; a += 32) slots[gbase + a] = lds(agh + 4u * (cbase + a));
+                    cbase += ng;
+                }
+                gbase += ng;
+            }
         }
         if (lane == 0) bulk_wait_all<0>();
         if (b.err && lane == 0) atomicOr(p.err_flag, b.err);

@@ -339,6 +339,86 @@ def run_c1(args):
     return 0
 
 
+def gym_action_blocks(n_blocks: int, block_envs: int, rows: int, seed: int) -> np.ndarray:
+    """Synthetic policy output for the vectorised loop: per env and step `rows` rows — ~60 % limit orders around 1000
+    (+-8 ticks, so books trade), 5 % market orders, 25 % cancels and 10 % no-ops; cancel targets are drawn from ids the env
+    is certain to have issued by that step (the first two rows of every step are orders)."""
+    from bourse_b200 import abi, gym
+    rng = np.random.default_rng(seed)
+    shape = (n_blocks, block_envs, rows)
+    u = rng.random(shape)
+    op = np.where(u < 0.65, abi.OP_NEW, np.where(u < 0.90, abi.OP_CANCEL, abi.OP_NOOP)).astype(np.uint32)
+    op[:, :, :2] = abi.OP_NEW                  # two orders per step for sure, so that ids below 2 * step always exist
+    op[0, :, 2:][op[0, :, 2:] == abi.OP_CANCEL] = abi.OP_NOOP
+    issued = np.maximum(1, 2 * np.arange(n_blocks)[:, None, None])
+    return gym.pack_actions(op, bid=rng.random(shape) < 0.5, vol=rng.integers(1, 50, shape), trader=rng.integers(0, 1000, shape),
+                            price=rng.integers(992, 1009, shape), order_id=(rng.random(shape) * issued).astype(np.uint64),
+                            market=rng.random(shape) < 0.08)
+
+
+def run_gym(args):
+    """the device-resident vectorised loop (bourse_b200.gym.VectorEnv): per step one action block
+    [n_envs, rows] already in device memory -> bb_step_device (ids assigned on the device, Env::step) -> bb_level2_device.
+    One bench step = reset + `--sim-steps` env-steps (default 256); nothing crosses PCIe inside the timed region."""
+    import torch
+
+    from bourse_b200 import abi, gym, workloads
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    n_envs, rows = args.envs, 8
+    n_steps = args.sim_steps if args.sim_steps != N_SIM_STEPS else 256
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    blocks = gym_action_blocks(n_steps, 256, rows, SEED)                       # [step][env % 256][row]
+    dev = torch.from_numpy(blocks.view(np.uint8).reshape(n_steps, 256, rows * 32)).cuda()
+    dev = dev.repeat(1, (n_envs + 255) // 256, 1)[:, :n_envs].contiguous()       # [step][env][row bytes]
+    eng_kw = dict(price_window=(960, 1056), live_cap=254) if args.engine == "dense" else dict(pages_smem=10)
+    v = gym.VectorEnv(n_envs, rows, SEED, 0, 1, 1000, device=local, max_orders=4096, max_trades=8192, max_steps=n_steps + 8, **eng_kw)
+    v.env.set_stream(stream.cuda_stream)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for i in range(args.warmup + args.steps):
+        v.reset()
+        if i >= args.warmup:
+            ev[i - args.warmup][0].record(stream)
+        for s in range(n_steps):
+            v.step(dev[s])
+        if i >= args.warmup:
+            ev[i - args.warmup][1].record(stream)
+        flush.fill_(1)
+    torch.cuda.synchronize()
+    v.check_errors()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    k_ms = sum(ms) / len(ms)
+    stats = v.env.stats()
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as orc
+        orc.build()
+        cores = host_cores()
+        r = orc.bench_env_rows(64 * cores, cores, n_steps, blocks, SEED)
+        cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+               "env_steps_per_sec": r["env_steps"] / r["seconds"],
+               "sample": f"{64 * cores} envs x {n_steps} steps of the same action blocks, one env per core at a time ({r['seconds']:.2f} s)"}
+    peak, peak_src = measured_peak_gbs()
+    alg = workloads.algorithmic_bytes(stats, abi.OBS_L2, n_envs * n_steps * rows)
+    print(json.dumps({
+        "metric": METRIC, "value": stats["instructions"] / (k_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"vectorised device-resident loop: {n_envs} envs x {rows} action rows x {n_steps} steps (65% orders, 25% cancels, "
+                               f"10% no-ops), level-2 observation of every env after every step, {args.engine} engine"},
+        "env_steps_per_sec": n_envs * n_steps / (k_ms * 1e-3), "us_per_vector_step": 1e3 * k_ms / n_steps, "orders_per_pass": stats["instructions"],
+        "trades_per_pass": stats["trades"], "gpu_launches": args.steps * (1 + 2 * n_steps),
+        "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                     "traffic": None, "kernel": "k_apply<ENV> + k_snapshot per step", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg / n_steps,
+                     "peak_source": peak_src},
+        **({"cpu_baseline": cpu} if cpu else {})}))
+    v.close()
+    return 0
+
+
 def run_gpu_other(args):
     """Secondary workloads of BASELINE.json (not the headline line): --workload c4 | c5, one GPU's shard per rank.
     c4: 8192 envs x (40+40 RandomAgents + 20-trader MomentumAgent) x 1000 env-steps, level-2 record per env-step.
@@ -558,14 +638,19 @@ def main():
     ap.add_argument("--max-trades", type=int, default=65536)
     ap.add_argument("--max-queue", type=int, default=0, help="per-env instructions per step (0 = the workload's default)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--engine", default="dense", choices=["dense", "paged"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "market"],
+    ap.add_argument("--engine", default=None, choices=["dense", "paged"],
+                    help="default: dense for c3 / market (shallow books inside a known price window), paged for gym")
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "market", "gym"],
                     help="c3 = the headline line; the others are the secondary configs (market = the multi-asset example)")
     args = ap.parse_args()
+    if args.engine is None:
+        args.engine = "paged" if args.workload == "gym" else "dense"
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "gym":
+        return run_gym(args)
     if args.workload != "c3":
         return run_gpu_other(args)
     return run_gpu(args)

@@ -147,18 +147,21 @@ template <bool STEPPED, class G> __device__ __forceinline__ u32 d_match(const G&
 }
 
 // insert_order (side.rs:54-66) for an order that rests: append to its level's queue.  Capacity violations are
-// recorded without branching out (indices are clamped so that every access stays inside the book image).
+// recorded and leave the image consistent: a price outside the window is clamped to level 0, an order that finds no
+// free slot is dropped.
 // CHECK_TIME: the caller cannot guarantee that time moves strictly forward between resting inserts (replay mode).
-template <bool CHECK_TIME, class G> __device__ __forceinline__ u32 d_insert(const G& g, Book& b, u32 side, u32 price, u64 t,
+// CHECK_SLOTS: false when the caller has already made sure that a free slot exists (k_sim validates a whole env-step's
+// new orders against the free-slot count up front, so the event loop carries no per-insert test).
+template <bool CHECK_TIME, bool CHECK_SLOTS, class G> __device__ __forceinline__ u32 d_insert(const G& g, Book& b, u32 side, u32 price, u64 t,
                                                                             u32 id, u32 vol) {
     u32 q = price - g.d_win_lo;
     if (q >= g.d_levels) {
         b.err |= ERR_CAP_PAGES;
         q = 0u;
     }
-    if (b.free_top == 0u) {
-        b.err |= ERR_CAP_LIVE;
-        b.free_top = 1u;
+    if (CHECK_SLOTS && b.free_top == 0u) {  // no free slot: the order is NOT put on the book (flagged; the image stays
+        b.err |= ERR_CAP_LIVE;              // consistent — a reused live slot would hand d_match a stale order id and send
+        return 0u;                          // its record write out of bounds)
     }
     b.free_top -= 1;
     const u32 slot = lds8(b.sb + G::DL::OFF_FS + b.free_top);
@@ -260,7 +263,7 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
         // Filled, or an unfilled market order: Cancelled when trading, Rejected otherwise (orderbook.rs:517-531)
         const u32 status = filled ? ST_FILLED : market ? (trading ? ST_CANCELLED : ST_REJECTED) : ST_ACTIVE;
         if (!ended) {
-            const u32 slot = d_insert<CHECK_TIME>(g, b, side, price, t, id, rem);
+            const u32 slot = d_insert<CHECK_TIME, HINT == 0>(g, b, side, price, t, id, rem);
             if (HINT == 1 || (HINT == 2 && hint)) sts8(b.ags + hint, slot);
         }
         // order record; the queue links of the HBM record are not used by this engine
@@ -318,7 +321,7 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
     u32 rem = vol;
     if (b.flags & FL_TRADING) rem = d_match<HINT != 0>(g, b, side, price, vol, id, t);
     const bool filled = vol != 0u && rem == 0u;
-    if (!filled) d_insert<CHECK_TIME>(g, b, side, price, t, id, rem);
+    if (!filled) d_insert<CHECK_TIME, HINT == 0>(g, b, side, price, t, id, rem);
     stg64v(ra + OH_PRICE, price, rem);
     stg32(ra + OH_META, (filled ? ST_FILLED : ST_ACTIVE) | side_bit);
     stg64(ra + (filled ? OC_END : OH_KEYT), t);
@@ -331,7 +334,7 @@ template <class G> __device__ __forceinline__ void d_restore(const G& g, Book& b
     const uint4 a = ldg128(ra), c = ldg128(ra + 16u);
     if (order_id + 1u > b.n_orders) b.n_orders = order_id + 1u;
     if ((c.z & META_STATUS_MASK) == ST_ACTIVE)
-        d_insert<true>(g, b, (c.z & META_BID) ? 1u : 0u, a.x, ((u64)c.y << 32) | c.x, order_id, a.y);
+        d_insert<true, true>(g, b, (c.z & META_BID) ? 1u : 0u, a.x, ((u64)c.y << 32) | c.x, order_id, a.y);
 }
 
 // (vol, count) at an arbitrary price; per-lane (prices may differ between lanes)

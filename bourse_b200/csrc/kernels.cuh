@@ -704,9 +704,15 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
             if (e.n > p.max_queue) b.err |= ERR_CAP_QUEUE;
             u32 n = min(e.n, p.max_queue);
             b.n_orders = e.next_id;  // create_order at submission (env.rs:173)
-            if constexpr (G::DENSE) {  // ids are validated once per step (d_apply trusts hinted events)
+            if constexpr (G::DENSE) {  // ids and slots are validated once per step (d_apply trusts hinted events)
                 if (e.next_id > g.max_orders) {
                     b.err |= ERR_CAP_ORDERS;
+                    n = 0;
+                }
+                // every new order of the step could rest: with fewer free slots than new orders the step is dropped
+                // (flagged) rather than run with per-insert checks; a population of one-order agents never gets here
+                if (e.next_id - id0 > b.free_top) {
+                    b.err |= ERR_CAP_LIVE;
                     n = 0;
                 }
             }

@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
     sig("orc_market_n_instructions", u64, vp)
     sig("orc_bench_market_agents", dbl, u32, u32, u64, u64, i32, u64, vp, u32, u64, vp, vp, u32, vp)
     sig("orc_bench_replay_suffix", dbl, u32, u32, vp, u64, u64, vp)
+    sig("orc_bench_env_rows", dbl, u32, u32, u64, u32, vp, u32, u32, u64, u32, u64, vp)
     sig("orc_philox", None, u32, u32, u32, u32, u32, u32, vp)
     sig("orc_xoroshiro", None, u64, u32, vp)
     sig("orc_shuffle_perm", None, u64, u32, vp)
@@ -442,6 +443,15 @@ def bench_market_agents(n_markets, n_threads, n_steps, seed, groups, assets, n_a
     out = np.zeros(3, np.uint64)
     secs = lib().orc_bench_market_agents(n_markets, n_threads, n_steps, seed, int(keyed), start_time, _ptr(ticks), n_assets,
                                          step_size, _ptr(arr), _ptr(a), len(arr), _ptr(out))
+    return {"seconds": secs, "instructions": int(out[0]), "trades": int(out[1]), "env_steps": int(out[2])}
+
+
+def bench_env_rows(n_envs, n_threads, n_steps, blocks, seed, tick_size=1, step_size=1000):
+    """`blocks`: INSTR_DTYPE array [n_blocks, block_envs, rows], cycled over the steps (see orc_bench_env_rows)."""
+    blocks = np.ascontiguousarray(blocks, dtype=INSTR_DTYPE)
+    nb, be, rows = blocks.shape
+    out = np.zeros(3, np.uint64)
+    secs = lib().orc_bench_env_rows(n_envs, n_threads, n_steps, rows, _ptr(blocks), nb, be, seed, tick_size, step_size, _ptr(out))
     return {"seconds": secs, "instructions": int(out[0]), "trades": int(out[1]), "env_steps": int(out[2])}
 
 

@@ -439,6 +439,56 @@ double orc_bench_replay_suffix(uint32_t n_threads, uint32_t tick_size, const orc
     return mx;
 }
 
+// Vectorised-loop baseline (bourse_b200.gym.VectorEnv's workload): `n_envs` Envs, each fed `rows` instruction rows per
+// step for `n_steps` steps from a cyclic table of `n_blocks` action blocks laid out [block][env][row] (the array the GPU
+// path reads from device memory), with the submit-then-step semantics of StepEnvNumpy.submit_instructions + step
+// (rust/src/step_sim_numpy.rs:233-275).  out[0] = rows queued, out[1] = trades, out[2] = env-steps; returns seconds.
+double orc_bench_env_rows(uint32_t n_envs, uint32_t n_threads, uint64_t n_steps, uint32_t rows, const orc_instr* blocks,
+                          uint32_t n_blocks, uint32_t block_envs, uint64_t seed, uint32_t tick_size, uint64_t step_size, uint64_t* out) {
+    std::atomic<uint32_t> next(0);
+    std::atomic<uint64_t> n_q(0), n_tr(0);
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t e = next.fetch_add(1);
+            if (e >= n_envs) break;
+            Env env(0, tick_size, step_size, true);
+            env.keep_records = false;
+            Xoroshiro128StarStar rng = Xoroshiro128StarStar::seed_from_u64(seed + e);
+            uint64_t q = 0;
+            for (uint64_t s = 0; s < n_steps; ++s) {
+                const orc_instr* r = blocks + ((size_t)(s % n_blocks) * block_envs + (e % block_envs)) * rows;
+                for (uint32_t k = 0; k < rows; ++k) {
+                    const uint32_t op = r[k].op_flags & 0xFF;
+                    try {
+                        if (op == OP_NEW) {
+                            env.place_order((r[k].op_flags & F_BID) ? BID : ASK, r[k].vol, r[k].trader, !(r[k].op_flags & F_MARKET), r[k].price);
+                            ++q;
+                        } else if (op == OP_CANCEL) {
+                            if (r[k].order_id < env.book.orders.size()) { env.cancel_order(r[k].order_id); ++q; }
+                        } else if (op == OP_MODIFY) {
+                            if (r[k].order_id < env.book.orders.size()) {
+                                env.modify_order(r[k].order_id, (r[k].op_flags & F_HAS_PRICE) != 0, r[k].price, (r[k].op_flags & F_HAS_VOL) != 0, r[k].vol);
+                                ++q;
+                            }
+                        }
+                    } catch (const PriceError&) {
+                    }
+                }
+                env.step(rng);
+            }
+            n_q += q;
+            n_tr += env.book.trades.size();
+        }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (uint32_t i = 0; i < n_threads; ++i) th.emplace_back(worker);
+    for (auto& x : th) x.join();
+    const auto t1 = std::chrono::steady_clock::now();
+    out[0] = n_q; out[1] = n_tr; out[2] = (uint64_t)n_envs * n_steps;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // ---------------------------------------------------------------- RNG probes for the known-answer tests
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
     const Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);

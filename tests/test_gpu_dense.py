@@ -302,3 +302,30 @@ def test_host_instructions_between_agent_launches_dense(core):
     assert np.array_equal(a.history_all(33), b.history_all(33))
     for env in range(4):
         assert a.get_trades(env) == b.get_trades(env) and a.get_orders(env) == b.get_orders(env)
+
+
+def test_slot_overflow_stays_memory_safe(core):
+    """More resting orders than slots is flagged (0x80) and the overflowing orders are left off the book; the image must
+    stay consistent, so that hundreds of further matches, cancels and inserts on the flagged book cannot touch memory
+    outside it (a reused live slot used to hand the matching loop a stale order id -> out-of-bounds record write)."""
+    n = 600
+    rng = np.random.default_rng(9)
+    ins = np.zeros(n, abi.INSTR_DTYPE)
+    ins["t"] = np.arange(1, n + 1)
+    new = rng.random(n) < 0.8
+    new[0] = True   # cancels always name an id that exists
+    bid = rng.random(n) < 0.5
+    ins["op_flags"] = np.where(new, abi.OP_NEW | np.where(bid, abi.F_BID, 0), abi.OP_CANCEL).astype(np.uint32)
+    ins["price"] = np.where(bid, rng.integers(100, 132, n), rng.integers(124, 160, n))   # mostly resting, some crossing
+    ins["vol"] = rng.integers(1, 9, n)
+    ins["order_id"] = (rng.random(n) * np.maximum(1, np.cumsum(new) - 1)).astype(np.uint32)
+    env = core.BatchedEnv(64, 0, 0, 1, 1000, max_orders=1024, max_trades=2048, max_steps=8, max_queue=16,
+                          price_window=(96, 160), live_cap=16)
+    with pytest.raises(MemoryError, match="0x80"):
+        env.replay(np.tile(ins, 64), np.arange(65, dtype=np.uint64) * n)
+    assert (env.env_errors() == 0x80).all()
+    env.synchronize()
+    # a fresh handle on the same device still works: nothing was corrupted
+    ob = core.OrderBook(0, 1, price_window=(100, 164))
+    ob.place_order(True, 5, 0, price=120)
+    assert ob.bid_ask() == (120, 2**32 - 1)

@@ -358,7 +358,8 @@ def gym_action_blocks(n_blocks: int, block_envs: int, rows: int, seed: int) -> n
 
 def run_gym(args):
     """the device-resident vectorised loop (bourse_b200.gym.VectorEnv): per step one action block
-    [n_envs, rows] already in device memory -> bb_step_device (ids assigned on the device, Env::step) -> bb_level2_device.
+    [n_envs, rows] already in device memory -> ONE launch (bb_step_device: ids assigned on the device, Env::step, level-2
+    records written to the observation buffer).
     One bench step = reset + `--sim-steps` env-steps (default 256); nothing crosses PCIe inside the timed region."""
     import torch
 
@@ -410,9 +411,9 @@ def run_gym(args):
         "config": {"workload": f"vectorised device-resident loop: {n_envs} envs x {rows} action rows x {n_steps} steps (65% orders, 25% cancels, "
                                f"10% no-ops), level-2 observation of every env after every step, {args.engine} engine"},
         "env_steps_per_sec": n_envs * n_steps / (k_ms * 1e-3), "us_per_vector_step": 1e3 * k_ms / n_steps, "orders_per_pass": stats["instructions"],
-        "trades_per_pass": stats["trades"], "gpu_launches": args.steps * (1 + 2 * n_steps),
+        "trades_per_pass": stats["trades"], "gpu_launches": args.steps * (2 + n_steps),
         "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
-                     "traffic": None, "kernel": "k_apply<ENV> + k_snapshot per step", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg / n_steps,
+                     "traffic": None, "kernel": "k_apply<ENV> (one launch per vector step)", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg / n_steps,
                      "peak_source": peak_src},
         **({"cpu_baseline": cpu} if cpu else {})}))
     v.close()

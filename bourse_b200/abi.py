@@ -96,7 +96,7 @@ def load() -> C.CDLL:
     sig("bb_replay_device", i32, vp, vp, vp)
     sig("bb_set_agents", i32, vp, vp, u32)
     sig("bb_set_agents_market", i32, vp, vp, vp, u32)
-    sig("bb_step_device", i32, vp, vp, vp, u64, vp)
+    sig("bb_step_device", i32, vp, vp, vp, u64, vp, vp)
     sig("bb_level2_device", i32, vp, vp)
     sig("bb_level1_device", i32, vp, vp)
     sig("bb_device_alloc", i32, vp, u64, P(vp))

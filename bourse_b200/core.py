@@ -139,10 +139,12 @@ class BatchedEnv:
     def step(self, n_steps: int = 1): self._ck(self._lib.bb_step(self._h, n_steps))
 
     # ------------------------------------------------------------------ device-resident loop (bourse_b200.gym)
-    def step_device(self, d_instrs_ptr: int, d_offsets_ptr: int, n_rows: int, d_out_ids_ptr: int = 0):
-        """One Env::step whose instruction rows are already in device memory (bb_step_device); asynchronous."""
+    def step_device(self, d_instrs_ptr: int, d_offsets_ptr: int, n_rows: int, d_out_ids_ptr: int = 0, d_obs_ptr: int = 0):
+        """One Env::step whose instruction rows are already in device memory (bb_step_device); asynchronous.  `d_obs_ptr`:
+        device buffer [n_envs, obs_words] that receives the end-of-step observation records from the same launch."""
         self._ck(self._lib.bb_step_device(self._h, C.c_void_p(d_instrs_ptr), C.c_void_p(d_offsets_ptr), n_rows,
-                                          C.c_void_p(d_out_ids_ptr) if d_out_ids_ptr else None))
+                                          C.c_void_p(d_out_ids_ptr) if d_out_ids_ptr else None,
+                                          C.c_void_p(d_obs_ptr) if d_obs_ptr else None))
 
     def level_2_data_device(self, d_out_ptr: int): self._ck(self._lib.bb_level2_device(self._h, C.c_void_p(d_out_ptr)))
     def level_1_data_device(self, d_out_ptr: int): self._ck(self._lib.bb_level1_device(self._h, C.c_void_p(d_out_ptr)))
@@ -417,7 +419,20 @@ class _StepEnvBase:
         kw.setdefault("pages_total", 256)
         self._env = BatchedEnv(1, seed, start_time, tick_size, step_size, trading, obs_words=abi.OBS_L2,
                                max_orders=max_orders, max_trades=max_trades, max_steps=max_steps, max_queue=max_queue, **kw)
-        self._one_u32 = np.zeros(1, np.uint32)
+        # single-row submissions (the per-agent calls of the reference's Python agents) go through preallocated
+        # one-element columns: wrapping eight fresh numpy arrays per call cost more than the call itself
+        self._row = {k: np.zeros(1, dt) for k, dt in (("action", np.uint32), ("side", np.uint8), ("vol", np.uint32), ("trader", np.uint32),
+                                                       ("price", np.uint32), ("order_id", np.uint64), ("flags", np.uint32), ("out", np.uint64))}
+        self._row_ptr = {k: abi.ptr(v) for k, v in self._row.items()}
+        self._done = C.c_uint64()
+
+    def _submit1(self, action, side=0, vol=0, trader=0, price=0, order_id=0, flags=abi.F_HAS_PRICE | abi.F_HAS_VOL) -> int:
+        r, p, e = self._row, self._row_ptr, self._env
+        r["action"][0], r["side"][0], r["vol"][0], r["trader"][0] = action, side, vol, trader
+        r["price"][0], r["order_id"][0], r["flags"][0] = price, order_id, flags
+        e._ck(e._lib.bb_submit(e._h, 1, None, p["action"], p["side"], p["vol"], p["trader"], p["price"], p["order_id"], p["flags"],
+                               p["out"], C.byref(self._done)))
+        return int(r["out"][0])
 
     def enable_trading(self): self._env.set_trading(True, 0)
     def disable_trading(self): self._env.set_trading(False, 0)
@@ -465,17 +480,16 @@ class StepEnv(_StepEnvBase):
     def trade_vol(self): return int(self._l2()[0])
 
     def place_order(self, bid: bool, vol: int, trader_id: int, price: typing.Optional[int] = None) -> int:
-        flags = None if price is not None else np.array([abi.F_MARKET], np.uint32)
-        ids = self._env.submit([abi.ACT_NEW], [1 if bid else 0], [vol], [trader_id], [price or 0], None, None, flags)
-        return int(ids[0])
+        if price is None:
+            return self._submit1(abi.ACT_NEW, 1 if bid else 0, vol, trader_id, 0, 0, abi.F_MARKET)
+        return self._submit1(abi.ACT_NEW, 1 if bid else 0, vol, trader_id, price)
 
     def cancel_order(self, order_id: int):
-        self._env.submit([abi.ACT_CANCEL], order_id=[order_id])
+        self._submit1(abi.ACT_CANCEL, order_id=order_id)
 
     def modify_order(self, order_id: int, new_price: typing.Optional[int] = None, new_vol: typing.Optional[int] = None):
         f = (abi.F_HAS_PRICE if new_price is not None else 0) | (abi.F_HAS_VOL if new_vol is not None else 0)
-        self._env.submit([abi.ACT_MODIFY], vol=[new_vol or 0], price=[new_price or 0], order_id=[order_id],
-                         flags=np.array([f], np.uint32))
+        self._submit1(abi.ACT_MODIFY, vol=new_vol or 0, price=new_price or 0, order_id=order_id, flags=f)
 
     def get_prices(self): h = self._env.history(0); return h[:, 1].copy(), h[:, 2].copy()
     def get_volumes(self): h = self._env.history(0); return h[:, 4].copy(), h[:, 3].copy()

@@ -79,6 +79,13 @@ struct bb_handle {
     u32 assets = 1;
     std::vector<u32> market_seq;
     std::vector<u64> market_rng;  // Xoroshiro128** state, two words per market
+    // bb_order_status: status column of one env, valid until the next launch that can change a status
+    bool status_valid = false;
+    u32 status_env = 0;
+    std::vector<uint8_t> status_cache;
+    std::vector<OrderRec> status_rec;
+    struct OccEntry { const void* fn; size_t smem; u32 wpb; int per_sm; };
+    std::vector<OccEntry> occ_cache;  // resident CTAs per SM of the kernels launched so far (grid_for)
     std::string err;
 };
 
@@ -198,10 +205,17 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
 
 template <class K> int grid_for(bb_handle* h, K kernel, const SmemLayout& l, u32 n_items, int* grid_out, u32 wpb = WPB) {
     const size_t smem = (size_t)l.warp_bytes * wpb;
-    CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the attribute / occupancy queries cost several microseconds of host time: a per-step caller (bb_step_device in an
+    // RL loop) would be bound by them, so the answer is remembered per (kernel, shared-memory size, CTA width)
     int per_sm = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * 32, smem));
-    if (per_sm < 1) return fail(h, BB_EINVAL, "configuration does not fit in shared memory (reduce pages_smem / max_queue)");
+    for (const auto& c : h->occ_cache)
+        if (c.fn == (const void*)kernel && c.smem == smem && c.wpb == wpb) per_sm = c.per_sm;
+    if (!per_sm) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * 32, smem));
+        if (per_sm < 1) return fail(h, BB_EINVAL, "configuration does not fit in shared memory (reduce pages_smem / max_queue)");
+        h->occ_cache.push_back({(const void*)kernel, smem, wpb, per_sm});
+    }
     const u32 want = (n_items + wpb - 1) / wpb;
     const u32 cap = (u32)per_sm * (u32)h->sm_count;
     *grid_out = (int)(want < cap ? want : cap);
@@ -229,6 +243,7 @@ int init_books(bb_handle* h) {
                                            h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups, h->dgeo, h->dense_lp, h->dense_nwmax);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
+    h->status_valid = false;
     for (auto& q : h->queue) q.clear();
     std::fill(h->n_orders_host.begin(), h->n_orders_host.end(), 0);
     h->mirror_dirty = false;
@@ -285,15 +300,17 @@ int ensure_instr_capacity(bb_handle* h, size_t n) {
 }
 
 int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_offsets, u32 n_steps, bool host_order = false,
-                 u64* d_out_ids = nullptr) {
+                 u64* d_out_ids = nullptr, u32* d_obs_out = nullptr) {
     KParams p;
     fill_params(h, h->lay_apply, p);
     p.instrs = d_instrs;
     p.offsets = d_offsets;
     p.n_steps = n_steps;
+    h->status_valid = false;
     p.host_order = host_order ? 1u : 0u;
     p.assign_ids = d_out_ids ? 1u : 0u;
     p.out_ids = d_out_ids;
+    p.obs_out = d_obs_out;
     int grid = 0, rc;
     const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
 #define LAUNCH_APPLY(M, E)                                                                       \
@@ -686,7 +703,8 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
     return BB_OK;
 }
 
-int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows, uint64_t* d_out_ids) {
+int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows, uint64_t* d_out_ids,
+                   uint32_t* d_obs_out) {
     CHECK_H(h);
     if (!d_env_offsets || (n_rows && !d_instrs)) return fail(h, BB_EINVAL, "null argument");
     if (h->assets > 1) return fail(h, BB_EINVAL, "bb_step_device drives single-asset envs (multi-asset queues are ordered on the host)");
@@ -704,7 +722,7 @@ int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env
         d_out_ids = h->d_ids;
     }
     h->mirror_dirty = true;  // ids were handed out on the device
-    return launch_apply(h, MODE_ENV, d_instrs, d_env_offsets, 1, false, d_out_ids);
+    return launch_apply(h, MODE_ENV, d_instrs, d_env_offsets, 1, false, d_out_ids, d_obs_out);
 }
 
 int bb_level2_device(bb_handle* h, uint32_t* d_out) {
@@ -817,6 +835,7 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
 #undef SIM_LAUNCH
     CUDA_TRY(h, cudaGetLastError());
     h->mirror_dirty = true;
+    h->status_valid = false;
     h->recorded_host += n_steps;
     return BB_OK;
 }
@@ -1171,11 +1190,25 @@ int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* stat
             *status = ST_NEW;
             return BB_OK;
         }
-    u32 meta = 0;
-    CUDA_TRY(h, cudaMemcpyAsync(&meta, &h->ord[(size_t)env * h->cfg.max_orders + order_id].meta, 4, cudaMemcpyDeviceToHost,
-                                h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    *status = (uint8_t)(meta & META_STATUS_MASK);
+    // Statuses only change inside launches: the first query after one brings the env's whole status column to the host
+    // (one contiguous copy of its order records) and later queries are served from it.  The reference's Python agents
+    // ask for the status of every held order each step (src/bourse/step_sim/agents/random_agent.py:77-91); one device
+    // round trip per query made that loop 4x slower than it needs to be.
+    if (!(h->status_valid && h->status_env == env && order_id < h->status_cache.size())) {
+        u64 n_queued_new = 0;
+        for (auto& x : h->queue[env]) n_queued_new += (x.op_flags & BB_OP_MASK) == BB_OP_NEW;
+        const u64 n_dev = h->n_orders_host[env] - n_queued_new;
+        if (order_id >= n_dev) return fail(h, BB_EBADID, "No order with id " + std::to_string(order_id) + " exists");
+        h->status_rec.resize(n_dev);
+        CUDA_TRY(h, cudaMemcpyAsync(h->status_rec.data(), h->ord + (size_t)env * h->cfg.max_orders, n_dev * sizeof(OrderRec),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        h->status_cache.resize(n_dev);
+        for (u64 i = 0; i < n_dev; ++i) h->status_cache[i] = (uint8_t)(h->status_rec[i].meta & META_STATUS_MASK);
+        h->status_env = env;
+        h->status_valid = true;
+    }
+    *status = h->status_cache[order_id];
     return BB_OK;
 }
 

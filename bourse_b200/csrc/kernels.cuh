@@ -53,6 +53,7 @@ struct KParams {
     // (create_order at submission, env.rs:173), rows that queue nothing (no-ops, tick errors) are left out of the shuffle
     u32 assign_ids;
     u64* out_ids;    // [total rows]: the id each row created, BB_NO_ID for rows that create nothing
+    u32* obs_out;    // [n_envs][obs_words] or null: the step's observation record, also written here (bb_step_device)
     // k_sim
     u32 n_groups, agents_per_env, mom_groups_per_env;
     u32 chip_agents;  // dense engine: capacity of the on-chip agent tables (agents_per_env; markets: the largest per-asset count)
@@ -126,6 +127,11 @@ __device__ __forceinline__ void blob_store(const KParams& p, u32 sb, u32 env, u3
 template <class G> __device__ __forceinline__ void emit_obs_direct(const G& g, Book& b, const KParams& p, u32 env) {
     u32 w0, w1;
     book_obs(g, b, p.obs_words, &w0, &w1);
+    if (p.obs_out) {  // the caller's device buffer gets the record too: one launch per vectorised step, no snapshot pass
+        u32* o = p.obs_out + (size_t)env * p.obs_words;
+        if (b.lane < p.obs_words) o[b.lane] = w0;
+        if (b.lane + 32u < p.obs_words) o[b.lane + 32u] = w1;
+    }
     const u32 n = lds(b.sb + HDR_NSTEPS);
     if (n < p.max_steps) {
         const u64 dst = (u64)(p.hist + (size_t)env * p.hist_env_stride + (size_t)n * p.obs_words);

@@ -136,8 +136,9 @@ class VectorEnv:
                 raise ValueError(f"actions must have shape ({self.n_envs}, {self.rows})")
             self._actions.copy_from_host(a)
             ptr = self._actions.ptr
-        self.env.step_device(ptr, self._offsets.ptr, self.n_envs * self.rows, self.ids.ptr)
-        return self._observe(), self.ids
+        # one launch: ids, Env::step and the observation records written straight into self.obs
+        self.env.step_device(ptr, self._offsets.ptr, self.n_envs * self.rows, self.ids.ptr, self.obs.ptr)
+        return self.obs, self.ids
 
     def check_errors(self):
         """Raise if any env flagged an error (capacity, bad order id, off-tick price); synchronises."""

@@ -194,8 +194,11 @@ int bb_step(bb_handle* h, uint32_t n_steps);
  * next order ids (d_out_ids[row], BB_NO_ID for every other row; may be NULL), BB_OP_CANCEL / BB_OP_MODIFY rows are queued,
  * BB_OP_NOOP and unknown codes queue nothing; then ONE Env::step.  A NEW row whose limit price is off the tick grid is
  * dropped, as when create_order returns PriceError, and flags the env with BB_ERR_PRICE (the next synchronous call
- * reports BB_EPRICE).  Asynchronous on the handle's stream. */
-int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows, uint64_t* d_out_ids);
+ * reports BB_EPRICE).  d_obs_out (device, [n_envs][obs_words], may be NULL) receives every env's end-of-step
+ * observation record from the same launch — what StepEnvNumpy.level_1_data / level_2_data would return next.
+ * Asynchronous on the handle's stream. */
+int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows, uint64_t* d_out_ids,
+                   uint32_t* d_obs_out);
 /* bb_level2 / bb_level1 into DEVICE memory: d_out[n_envs][45] / d_out[n_envs][9].  Asynchronous. */
 int bb_level2_device(bb_handle* h, uint32_t* d_out);
 int bb_level1_device(bb_handle* h, uint32_t* d_out);

@@ -399,10 +399,10 @@ def run_gym(args):
         from oracle import oracle as orc
         orc.build()
         cores = host_cores()
-        r = orc.bench_env_rows(64 * cores, cores, n_steps, blocks, SEED)
+        r = orc.bench_env_rows(4096 * cores, cores, n_steps, blocks, SEED)
         cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
                "env_steps_per_sec": r["env_steps"] / r["seconds"],
-               "sample": f"{64 * cores} envs x {n_steps} steps of the same action blocks, one env per core at a time ({r['seconds']:.2f} s)"}
+               "sample": f"{4096 * cores} envs x {n_steps} steps of the same action blocks, one env per core at a time ({r['seconds']:.2f} s)"}
     peak, peak_src = measured_peak_gbs()
     alg = workloads.algorithmic_bytes(stats, abi.OBS_L2, n_envs * n_steps * rows)
     print(json.dumps({

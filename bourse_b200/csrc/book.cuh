@@ -392,7 +392,8 @@ template <class G> __device__ __forceinline__ void level_at_lane(const G& g, con
     if (!to_level(g, price, &q)) return;
     const u32 want = ((q >> 5) << 1) | side;
     u32 slot = BB_NIL;
-    for (u32 j = 0; j < ptot(g); ++j)
+    const u32 n_tags = G::FAST ? g.p_smem : g.p_total;  // the FAST geometry only has the resident slots [0, p_smem)
+    for (u32 j = 0; j < n_tags; ++j)
         if (lds(tag_addr(b, j)) == want) slot = j;
     if (slot == BB_NIL) return;
     if (!((lds(vmap_addr(g, b, slot)) >> (q & 31u)) & 1u)) return;

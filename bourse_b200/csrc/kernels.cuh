@@ -884,8 +884,12 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
                     if constexpr (MKT) b.t = start + (u64)__shfl_sync(BB_FULL, toff, k);
                     const u32 of = __shfl_sync(BB_FULL, mine.x, k), id = __shfl_sync(BB_FULL, mine.y, k);
                     const u32 price = __shfl_sync(BB_FULL, mine.z, k), vol = __shfl_sync(BB_FULL, mine.w, k);
-                    if (of & 1u) {  // NEW: one constant-folded copy of the placement path per side
-                        if (of & 2u) book_apply<true, false>(g, b, EV_NEW, id, 1u, price, vol, of >> 13, false, false, b.t);
+                    if (of & 1u) {
+                        // NEW: one constant-folded copy of the placement path per side — except with MomentumAgent /
+                        // NoiseAgent compiled in, where the kernel is instruction-fetch bound (25 % of the stall samples
+                        // were "no instruction", profiles/r01_s7_summary.md) and ONE side-generic copy is 7 % faster
+                        if constexpr (MOM) book_apply<true, false>(g, b, EV_NEW, id, (of >> 1) & 1u, price, vol, of >> 13, false, false, b.t);
+                        else if (of & 2u) book_apply<true, false>(g, b, EV_NEW, id, 1u, price, vol, of >> 13, false, false, b.t);
                         else book_apply<true, false>(g, b, EV_NEW, id, 0u, price, vol, of >> 13, false, false, b.t);
                     } else {
                         book_apply<false, false>(g, b, EV_CANCEL, id, 0u, 0u, 0u, 0u, false, false, b.t);

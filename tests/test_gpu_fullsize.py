@@ -172,3 +172,46 @@ def test_c5_deep_book_shard(core, oracle):
         bid = go["side"].astype(bool)
         assert int(go["vol"][act & bid].astype(np.uint64).sum()) == int(l2[i][4])
         assert int(go["vol"][act & ~bid].astype(np.uint64).sum()) == int(l2[i][3])
+
+
+def test_market_example_full_size(core, oracle):
+    """bench.py --workload market at its full size: 2048 two-asset markets x (50+50) RandomMarketAgents per asset x 1000
+    steps on the dense engine (k_sim<DENSE, 0, MKT>), level-2 record per asset and step.  A sample of markets is compared
+    bit for bit with the oracle's MarketSim; the properties run over all 4096 books, plus the market-wide one: within
+    any step, the arrival times of a market's orders (both assets together) never repeat (one shared queue, event i at
+    start + i, crates/step_sim/src/market_env.rs:116-121)."""
+    n_markets, n_steps, seed = 2048, 1000, 101
+    groups, assets = workloads.market_example_groups()
+    env = core.BatchedEnv(2 * n_markets, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=65536, max_trades=65536,
+                          max_steps=n_steps, max_queue=80, price_window=(20, 180), live_cap=128, assets=2)
+    env.set_agents(groups, assets=assets)
+    env.run_agents(n_steps, seed)
+    assert not env.env_errors().any()
+    st = env.stats()
+    assert st["env_steps"] == 2 * n_markets * n_steps and st["error_envs"] == 0
+    hist = env.history_all(n_steps)
+    assert int(hist[:, :, 0].astype(np.uint64).sum()) == st["traded_volume"]
+    assert np.array_equal(hist[:, -1, :], env.level_2_data())
+    both = (hist[:, :, 1] > 0) & (hist[:, :, 2] < 0xFFFFFFFF)
+    assert (hist[:, :, 1][both] < hist[:, :, 2][both]).all()
+    assert (hist[:, :, 5:45:4].sum(axis=2, dtype=np.uint64) <= hist[:, :, 4]).all()
+    assert (hist[:, :, 7:45:4].sum(axis=2, dtype=np.uint64) <= hist[:, :, 3]).all()
+    rng = np.random.default_rng(1)
+    for m in sorted(set([0, n_markets - 1] + list(rng.integers(0, n_markets, size=6)))):
+        o = oracle.MarketEnv(0, 0, [1, 1], 1_000_000)
+        o.set_groups(groups, assets)
+        o.run_agents(n_steps, seed, market_id=int(m))
+        arr = []
+        for a in range(2):
+            e = 2 * int(m) + a
+            assert np.array_equal(hist[e], o.history(a)), (m, a)
+            co, go = o.asset(a).orders_arrays(), env.orders_arrays(e)
+            for k in co:
+                assert np.array_equal(co[k], go[k]), (m, a, k)
+            ct, gt = o.asset(a).trades_arrays(), env.trades_arrays(e)
+            for k in ct:
+                assert np.array_equal(ct[k], gt[k]), (m, a, k)
+            _check_book_conservation(env, e, hist[e, -1])
+            arr.append(go["arr_time"])
+        t = np.concatenate(arr)
+        assert len(np.unique(t)) == len(t), m

@@ -71,3 +71,42 @@ def test_gpu_agents_match_reference_stream_statistically(core, oracle):
     gpu = _env_summaries(env.history_all(N_STEPS))
     stream = _env_summaries(_oracle_hist(oracle, groups, 128, False, 1234))
     _assert_match(gpu, stream)
+
+
+def _oracle_market_hist(oracle, groups, assets, n_assets, n_markets, keyed, seed):
+    out = []
+    for m in range(n_markets):
+        env = oracle.MarketEnv(0, 0, [1] * n_assets, 1_000_000)
+        env.set_groups(groups, assets)
+        # stream mode: market_sim_runner seeded seed + m (crates/step_sim/src/runner.rs:107-131); keyed: Philox (seed, market m)
+        env.run_agents(N_STEPS, seed + (0 if keyed else m), market_id=m, keyed=keyed)
+        out.append(np.stack([env.history(a)[:, :9] for a in range(n_assets)]))
+    return np.stack(out)   # [markets, assets, steps, 9]
+
+
+def test_market_twins_match_reference_stream_statistically(oracle):
+    """The multi-asset example population (crates/step_sim/examples/multi_asset/main.rs): market-keyed Philox runs against
+    reference-style market_sim_runner runs, per asset, across 64 markets."""
+    groups, assets = workloads.market_example_groups()
+    keyed = _oracle_market_hist(oracle, groups, assets, 2, 64, True, 21)
+    stream = _oracle_market_hist(oracle, groups, assets, 2, 64, False, 4321)
+    for a in range(2):
+        _assert_match(_env_summaries(keyed[:, a]), _env_summaries(stream[:, a]))
+    # the two assets of one market are separate books: their histories differ
+    assert not np.array_equal(keyed[:, 0], keyed[:, 1])
+
+
+@pytest.mark.gpu
+def test_gpu_market_twins_match_reference_stream_statistically(oracle):
+    """k_sim<.., MKT> (512 two-asset markets on the dense engine) against reference-style market_sim_runner runs."""
+    from bourse_b200 import abi, core
+    groups, assets = workloads.market_example_groups()
+    env = core.BatchedEnv(1024, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1, max_orders=32768, max_trades=32768, max_steps=N_STEPS,
+                          max_queue=96, price_window=(20, 180), live_cap=128, assets=2)
+    env.set_agents(groups, assets=assets)
+    env.run_agents(N_STEPS, 21)
+    assert not env.env_errors().any()
+    hist = env.history_all(N_STEPS).reshape(512, 2, N_STEPS, 9)
+    stream = _oracle_market_hist(oracle, groups, assets, 2, 64, False, 4321)
+    for a in range(2):
+        _assert_match(_env_summaries(hist[:, a]), _env_summaries(stream[:, a]))

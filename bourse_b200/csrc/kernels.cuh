@@ -323,7 +323,7 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_P
                 __syncwarp();
                 // (b) transactions.shuffle(rng) (env.rs:121): Fisher-Yates from the back.  Multi-asset markets shuffle
                 // one queue across their books (market_env.rs:114-115): the host did that, the slice is in order
-                if (!p.host_order) {
+                if (!p.host_order && lane == 0u) {  // a serial chain: one lane applies it (see the swap loop of k_sim)
                     u64 s0 = lds64(b.sb + HDR_RNG0), s1 = lds64(b.sb + HDR_RNG1);
                     for (u32 i = nv; i > 1; --i) {
                         const u32 j = xoroshiro_range(s0, s1, i);
@@ -767,7 +767,10 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
                 }
             }
             __syncwarp();
-            if constexpr (G::DENSE && !MKT) {  // the queue is on chip: swap the 16-byte instructions themselves
+            // the swaps are one serial chain: lane 0 applies them alone (32 lanes storing the same 16 bytes are 4 L1
+            // wavefronts instead of 1, and the tools rightly flag unsynchronised same-address traffic between lanes)
+            if (lane != 0u) {
+            } else if constexpr (G::DENSE && !MKT) {  // the queue is on chip: swap the 16-byte instructions themselves
                 for (u32 i = n; i > 1; --i) {
                     const u32 j = lds16(jarr + 2u * (i - 1));
                     const uint4 x = lds128(qs + 16u * (i - 1)), y = lds128(qs + 16u * j);

@@ -860,7 +860,13 @@ template <class G> __device__ __forceinline__ void book_from_header(const G& g, 
     b.d_instr = b.d_trans = b.d_volume = 0;
 }
 
+// One lane writes (every lane holds the same values): the read-modify-write counters must not be applied per lane.
 template <class G> __device__ __forceinline__ void book_to_header(const G& g, const Book& b) {
+    __syncwarp();
+    if (b.lane != 0u) {
+        __syncwarp();
+        return;
+    }
     if constexpr (G::DENSE) sts(b.sb + HDR_FREETOP, b.free_top);
     sts64(b.sb + HDR_T, b.t);
     sts64(b.sb + HDR_MAXKT, b.max_key_time);

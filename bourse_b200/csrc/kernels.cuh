@@ -133,11 +133,12 @@ template <class G> __device__ __forceinline__ void emit_obs_direct(const G& g, B
         if (b.lane + 32u < p.obs_words) o[b.lane + 32u] = w1;
     }
     const u32 n = lds(b.sb + HDR_NSTEPS);
+    __syncwarp();  // every lane has read the count before lane 0 bumps it
     if (n < p.max_steps) {
         const u64 dst = (u64)(p.hist + (size_t)env * p.hist_env_stride + (size_t)n * p.obs_words);
         if (b.lane < p.obs_words) stg32(dst + 4u * b.lane, w0);
         if (b.lane + 32u < p.obs_words) stg32(dst + 4u * (b.lane + 32u), w1);
-        sts(b.sb + HDR_NSTEPS, n + 1);
+        if (b.lane == 0u) sts(b.sb + HDR_NSTEPS, n + 1);
     } else {
         b.err |= ERR_CAP_STEPS;
     }
@@ -356,7 +357,7 @@ template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_P
                     __syncwarp();
                 }
                 b.t = start + p.step_size;  // env.rs:129
-                sts(b.sb + HDR_STEPCTR, lds(b.sb + HDR_STEPCTR) + 1u);
+                if (lane == 0u) sts(b.sb + HDR_STEPCTR, lds(b.sb + HDR_STEPCTR) + 1u);
                 emit_obs_direct(g, b, p, env);  // env.rs:132-134
             }
         }

@@ -84,7 +84,82 @@ def test_oracle_reproduces_agent_fixtures(oracle):
             assert np.array_equal(env._history(), g["hist"][e]) and len(env.get_trades()) == g["n_trades"][e]
 
 
+def _golden_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("name", ["example", "mixed"])
+def test_oracle_reproduces_market_fixture(oracle, name):
+    g = load("market_example")
+    groups, assets, n_assets = _golden_module().market_populations()[name]
+    hist = g[f"{name}/hist"]
+    for m in range(hist.shape[0]):
+        env = oracle.MarketEnv(0, 0, [1] * n_assets, 1_000_000)
+        env.set_groups(groups, assets)
+        env.run_agents(hist.shape[2], 101, market_id=m, keyed=True)
+        for a in range(n_assets):
+            assert np.array_equal(env.history(a), hist[m, a]) and len(env.get_trades(a)) == g[f"{name}/n_trades"][m, a]
+
+
+def vector_env_fixture():
+    g = load("vector_env")
+    acts, tick = _golden_module().vector_env_actions()
+    assert np.array_equal(np.frombuffer(hashlib.sha256(acts.tobytes()).digest(), dtype=np.uint8), g["actions_sha"]), \
+        "action generator changed: regenerate the fixtures"
+    return g, acts, tick
+
+
+def test_vector_env_fixture_is_consistent():
+    g, acts, tick = vector_env_fixture()
+    n_steps, n_envs, rows = acts.shape
+    assert g["ids"].shape == (n_steps, n_envs, rows) and g["obs"].shape == (n_steps, n_envs, 45)
+    new = (acts["op_flags"] & 0xFF) == abi.OP_NEW
+    assert (g["ids"][~new] == abi.NO_ID).all()                      # only NEW rows create ids
+    off_tick = new & ((acts["op_flags"] & abi.F_MARKET) == 0) & (acts["price"] % tick != 0)
+    assert (g["ids"][off_tick] == abi.NO_ID).all() and np.array_equal(off_tick.any(axis=(0, 2)), g["price_error"])
+    ok = new & ~off_tick
+    for e in range(n_envs):                                         # ids are dense per env, in row order
+        assert np.array_equal(g["ids"][:, e][ok[:, e]], np.arange(ok[:, e].sum(), dtype=np.uint64))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", [("example", dict(price_window=(0, 256), live_cap=128)), ("example", dict()), ("mixed", dict())],
+                         ids=["example_dense", "example_fast", "mixed_fast"])
+def test_cuda_reproduces_market_fixture(name, kw):
+    from bourse_b200 import core
+    g = load("market_example")
+    groups, assets, n_assets = _golden_module().market_populations()[name]
+    hist = g[f"{name}/hist"]
+    n_markets, n_steps = hist.shape[0], hist.shape[2]
+    env = core.BatchedEnv(n_markets * n_assets, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=8192, max_trades=8192,
+                          max_steps=n_steps, max_queue=128, assets=n_assets, **kw)
+    env.set_agents(groups, assets=assets)
+    env.run_agents(n_steps, 101)
+    assert not env.env_errors().any()
+    assert np.array_equal(env.history_all(n_steps).reshape(hist.shape), hist)
+    assert [[env.n_trades(m * n_assets + a) for a in range(n_assets)] for m in range(n_markets)] == g[f"{name}/n_trades"].tolist()
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_vector_env_fixture():
+    from bourse_b200 import gym
+    g, acts, tick = vector_env_fixture()
+    n_steps, n_envs, rows = acts.shape
+    v = gym.VectorEnv(n_envs, rows, 9, 0, tick, 1000, max_orders=256, max_trades=512, max_steps=32)
+    v.reset()
+    for s in range(n_steps):
+        obs, ids = v.step(acts[s])
+        assert np.array_equal(ids.numpy(), g["ids"][s]) and np.array_equal(obs.numpy(), g["obs"][s]), s
+    assert np.array_equal((v.env.env_errors() & 0x200) != 0, g["price_error"])
+    assert [v.env.n_trades(e) for e in range(n_envs)] == list(g["n_trades"])
+    v.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tick", [2, 1])
 def test_c1_cuda_matches_fixture(core, tick):

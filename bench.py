@@ -558,7 +558,7 @@ def run_gpu_other(args):
         o1 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_rest
         o2 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
         env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=1_800_000,
-                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, pages_smem=10, pages_total=192)
+                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, pages_smem=args.pages_smem, pages_total=192)
         env.set_stream(stream.cuda_stream)
         torch.cuda.synchronize()
         pre_stats = None
@@ -638,6 +638,7 @@ def main():
     ap.add_argument("--max-orders", type=int, default=65536)
     ap.add_argument("--max-trades", type=int, default=65536)
     ap.add_argument("--max-queue", type=int, default=0, help="per-env instructions per step (0 = the workload's default)")
+    ap.add_argument("--pages-smem", type=int, default=10, help="c5: 32-level price pages per book resident in shared memory (of 192)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default=None, choices=["dense", "paged"],
                     help="default: dense for c3 / market (shallow books inside a known price window), paged for gym")

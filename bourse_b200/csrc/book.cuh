@@ -181,8 +181,12 @@ template <u32 LP_, u32 NWMAX_> struct DenseLayout;
 #define ENG_FAST 1
 #define ENG_DENSE 2    // <= 128 order slots, window <= 256 levels
 #define ENG_DENSE_L 3  // <= 254 order slots, window <= 1024 levels
+// the generic geometry with EVERY page resident in shared memory (deep books at one or two books per CTA): the HBM-page
+// variants of every page access drop out of the instruction stream.  Only k_apply is instantiated for it.
+#define ENG_PAGED_RES 4
 template <int ENG_> struct GeoT : Geo {
     static constexpr bool FAST = ENG_ == ENG_FAST;
+    static constexpr bool RES = ENG_ == ENG_FAST || ENG_ == ENG_PAGED_RES;  // no page lives in HBM
     static constexpr bool DENSE = ENG_ == ENG_DENSE || ENG_ == ENG_DENSE_L;
     typedef DenseLayout<(ENG_ == ENG_DENSE_L ? 256u : 128u), (ENG_ == ENG_DENSE_L ? 32u : 8u)> DL;
 };
@@ -246,7 +250,7 @@ template <class G> __device__ __forceinline__ PageG page_g(const G& g, const Boo
 }
 // (vol, cnt) of a level of any page; for the cold observation paths where the slot may differ per lane
 template <class G> __device__ __forceinline__ uint2 level_pair_any(const G& g, const Book& b, u32 slot, u32 l) {
-    return (G::FAST || slot < g.p_smem) ? pld2(page_s(g, b, slot), PG_VC + 8u * l) : pld2(page_g(g, b, slot), PG_VC + 8u * l);
+    return (G::RES || slot < g.p_smem) ? pld2(page_s(g, b, slot), PG_VC + 8u * l) : pld2(page_g(g, b, slot), PG_VC + 8u * l);
 }
 
 __device__ __forceinline__ bool has_best(const Book& b, u32 side) { return (b.flags >> (1u + side)) & 1u; }
@@ -297,8 +301,8 @@ template <class G> __device__ __forceinline__ u32 find_page(const G& g, const Bo
 
 template <class G> __device__ __forceinline__ u32 alloc_page(const G& g, Book& b, u32 side, u32 pkey) {
     for (u32 base = 0; base < ptot(g); base += 32) {
-        // in the FAST geometry only the resident slots [0, p_smem) exist
-        const bool usable = !G::FAST || (base + b.lane) < g.p_smem;
+        // in the all-resident geometries only the slots [0, p_smem) exist
+        const bool usable = !G::RES || (base + b.lane) < g.p_smem;
         const u32 m = __ballot_sync(BB_FULL, usable && lds(b.tag_lane + 4u * base) == BB_TAG_FREE);
         if (m) {
             const u32 slot = base + __ffs(m) - 1;
@@ -392,7 +396,7 @@ template <class G> __device__ __forceinline__ void level_at_lane(const G& g, con
     if (!to_level(g, price, &q)) return;
     const u32 want = ((q >> 5) << 1) | side;
     u32 slot = BB_NIL;
-    const u32 n_tags = G::FAST ? g.p_smem : g.p_total;  // the FAST geometry only has the resident slots [0, p_smem)
+    const u32 n_tags = G::RES ? g.p_smem : g.p_total;  // the all-resident geometries only have the slots [0, p_smem)
     for (u32 j = 0; j < n_tags; ++j)
         if (lds(tag_addr(b, j)) == want) slot = j;
     if (slot == BB_NIL) return;
@@ -549,7 +553,7 @@ template <class G> __device__ __forceinline__ bool book_insert(const G& g, Book&
         slot = alloc_page(g, b, side, q >> 5);
         if (slot == BB_NIL) return false;
     }
-    if (G::FAST || slot < g.p_smem) book_insert_at(g, b, side, q, slot, page_s(g, b, slot), t, id, vol, out_prev, out_next);
+    if (G::RES || slot < g.p_smem) book_insert_at(g, b, side, q, slot, page_s(g, b, slot), t, id, vol, out_prev, out_next);
     else book_insert_at(g, b, side, q, slot, page_g(g, b, slot), t, id, vol, out_prev, out_next);
     if (t > b.max_key_time) b.max_key_time = t;
     return true;
@@ -570,7 +574,7 @@ template <class G> __device__ __forceinline__ void book_remove(const G& g, Book&
     to_level(g, price, &q);
     const u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) return;  // unreachable for Active orders
-    if (G::FAST || slot < g.p_smem) book_remove_at(g, b, side, q, slot, page_s(g, b, slot), prev, next, key_time, ghost, vol);
+    if (G::RES || slot < g.p_smem) book_remove_at(g, b, side, q, slot, page_s(g, b, slot), prev, next, key_time, ghost, vol);
     else book_remove_at(g, b, side, q, slot, page_g(g, b, slot), prev, next, key_time, ghost, vol);
 }
 
@@ -580,7 +584,7 @@ template <class G> __device__ __forceinline__ void book_reduce(const G& g, Book&
     to_level(g, price, &q);
     const u32 slot = find_page(g, b, side, q >> 5);
     if (slot == BB_NIL) return;
-    if (G::FAST || slot < g.p_smem) {
+    if (G::RES || slot < g.p_smem) {
         const PageS pr = page_s(g, b, slot);
         pst(pr, PG_VOL(q & 31u), pld(pr, PG_VOL(q & 31u)) - dv);
     } else {
@@ -672,7 +676,7 @@ template <class G> __device__ __forceinline__ u32 book_match(const G& g, Book& b
             }
         }
         bool released = false, ok;
-        if (G::FAST || slot < g.p_smem) ok = fill_one(g, b, o, bq, slot, page_s(g, b, slot), id, t, &vol, filled, &released);
+        if (G::RES || slot < g.p_smem) ok = fill_one(g, b, o, bq, slot, page_s(g, b, slot), id, t, &vol, filled, &released);
         else ok = fill_one(g, b, o, bq, slot, page_g(g, b, slot), id, t, &vol, filled, &released);
         if (!ok) break;
         if (released) slot_key = BB_NIL;

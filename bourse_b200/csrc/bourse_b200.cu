@@ -27,6 +27,13 @@ constexpr u32 WPB = 4;  // warps (books) per CTA
 
 inline u32 align_up(u32 x, u32 a) { return (x + a - 1) / a * a; }
 
+// Books per CTA for a layout: 4 warps unless a book's shared-memory image is so large (deep books with every price page
+// resident) that only 2 or 1 fit in the 227 KB a CTA may use.
+inline u32 wpb_for(u32 warp_bytes) {
+    const u32 limit = 232448u - 1024u;
+    return 4u * warp_bytes <= limit ? 4u : 2u * warp_bytes <= limit ? 2u : 1u;
+}
+
 }  // namespace
 
 struct bb_handle {
@@ -61,6 +68,7 @@ struct bb_handle {
     // layout
     u64 blob_stride = 0;
     u32 blob_smem_bytes = 0, p_total = 0, p_smem = 0, granule = 0, max_steps_padded = 0;
+    bool all_resident = false;  // generic geometry with pages_smem == pages_total
     int eng = ENG_PAGED;  // ENG_FAST: granule == 1, one 32-entry page directory, no HBM pages; ENG_DENSE: dense window
     Geo dgeo{};           // dense-engine geometry (d_* fields), zero otherwise
     u32 dense_lp = 0, dense_nwmax = 0;  // DenseLayout parameters of the selected variant
@@ -312,21 +320,24 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     p.out_ids = d_out_ids;
     p.obs_out = d_obs_out;
     int grid = 0, rc;
-    const size_t smem = (size_t)h->lay_apply.warp_bytes * WPB;
-#define LAUNCH_APPLY(M, E)                                                                       \
-    do {                                                                                         \
-        if ((rc = grid_for(h, k_apply<M, E>, h->lay_apply, h->cfg.n_envs, &grid))) return rc;    \
-        k_apply<M, E><<<grid, WPB * 32, smem, h->stream>>>(p);                                   \
+    const u32 wpb = wpb_for(h->lay_apply.warp_bytes);
+    const size_t smem = (size_t)h->lay_apply.warp_bytes * wpb;
+#define LAUNCH_APPLY(M, E)                                                                            \
+    do {                                                                                              \
+        if ((rc = grid_for(h, k_apply<M, E>, h->lay_apply, h->cfg.n_envs, &grid, wpb))) return rc;    \
+        k_apply<M, E><<<grid, wpb * 32, smem, h->stream>>>(p);                                        \
     } while (0)
     if (mode == MODE_REPLAY) {
         if (h->eng == ENG_DENSE) LAUNCH_APPLY(MODE_REPLAY, ENG_DENSE);
         else if (h->eng == ENG_DENSE_L) LAUNCH_APPLY(MODE_REPLAY, ENG_DENSE_L);
         else if (h->eng == ENG_FAST) LAUNCH_APPLY(MODE_REPLAY, ENG_FAST);
+        else if (h->all_resident) LAUNCH_APPLY(MODE_REPLAY, ENG_PAGED_RES);
         else LAUNCH_APPLY(MODE_REPLAY, ENG_PAGED);
     } else {
         if (h->eng == ENG_DENSE) LAUNCH_APPLY(MODE_ENV, ENG_DENSE);
         else if (h->eng == ENG_DENSE_L) LAUNCH_APPLY(MODE_ENV, ENG_DENSE_L);
         else if (h->eng == ENG_FAST) LAUNCH_APPLY(MODE_ENV, ENG_FAST);
+        else if (h->all_resident) LAUNCH_APPLY(MODE_ENV, ENG_PAGED_RES);
         else LAUNCH_APPLY(MODE_ENV, ENG_PAGED);
     }
 #undef LAUNCH_APPLY
@@ -340,16 +351,17 @@ int snapshot(bb_handle* h, u32 first_env, u32 n, u32* d45, u32* d8, u32 words = 
     KParams p;
     fill_params(h, h->lay_snap, p);
     int grid = 0, rc;
-    const size_t smem = (size_t)h->lay_snap.warp_bytes * WPB;
+    const u32 wpb = wpb_for(h->lay_snap.warp_bytes);
+    const size_t smem = (size_t)h->lay_snap.warp_bytes * wpb;
     if (h->eng == ENG_DENSE) {
-        if ((rc = grid_for(h, k_snapshot<ENG_DENSE>, h->lay_snap, n, &grid))) return rc;
-        k_snapshot<ENG_DENSE><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
+        if ((rc = grid_for(h, k_snapshot<ENG_DENSE>, h->lay_snap, n, &grid, wpb))) return rc;
+        k_snapshot<ENG_DENSE><<<grid, wpb * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
     } else if (h->eng == ENG_DENSE_L) {
-        if ((rc = grid_for(h, k_snapshot<ENG_DENSE_L>, h->lay_snap, n, &grid))) return rc;
-        k_snapshot<ENG_DENSE_L><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
+        if ((rc = grid_for(h, k_snapshot<ENG_DENSE_L>, h->lay_snap, n, &grid, wpb))) return rc;
+        k_snapshot<ENG_DENSE_L><<<grid, wpb * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
     } else {
-        if ((rc = grid_for(h, k_snapshot<ENG_PAGED>, h->lay_snap, n, &grid))) return rc;
-        k_snapshot<ENG_PAGED><<<grid, WPB * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
+        if ((rc = grid_for(h, k_snapshot<ENG_PAGED>, h->lay_snap, n, &grid, wpb))) return rc;
+        k_snapshot<ENG_PAGED><<<grid, wpb * 32, smem, h->stream>>>(p, d45, d8, first_env, n, words);
     }
     CUDA_TRY(h, cudaGetLastError());
     return BB_OK;
@@ -399,6 +411,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     if (h->p_smem > usable) h->p_smem = usable;
     h->p_total = align_up(usable, 32);
     h->eng = (h->granule == 1 && h->p_total == 32 && usable == h->p_smem) ? ENG_FAST : ENG_PAGED;
+    h->all_resident = h->eng == ENG_PAGED && usable == h->p_smem;  // k_apply<.., ENG_PAGED_RES>: no HBM page variants
     h->blob_smem_bytes = 128u + 12u * h->p_total + 512u * h->p_smem;
     h->blob_stride = 128ull + 12ull * h->p_total + 512ull * h->p_total;
     if (cfg->win_levels) {  // dense-window engine (csrc/dense.cuh), two compiled size classes
@@ -807,7 +820,7 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     int grid = 0, rc;
     const bool mom = h->mom_groups != 0;
     // markets: the A books of a market are A consecutive warps of one CTA (a CTA holds as many whole markets as fit in 4 warps)
-    const u32 wpb = mkt ? (WPB / h->assets) * h->assets : WPB;
+    const u32 wpb = mkt ? (WPB / h->assets) * h->assets : wpb_for(h->lay_sim.warp_bytes);
     const size_t sim_smem = (size_t)h->lay_sim.warp_bytes * wpb;
 #define SIM_CASE(E, M)                                                                                     \
     if (h->eng == E && mom == M) {                                                                         \

@@ -194,7 +194,7 @@ template <bool CT, class G> __device__ __forceinline__ void apply_instr(const G&
 }
 
 // the generic paged geometry is shared-memory limited to <= 5 CTAs per SM anyway: give it the registers
-template <int MODE, int ENG> __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_apply(const __grid_constant__ KParams p) {
+template <int MODE, int ENG> __global__ void __launch_bounds__(128, (ENG == ENG_PAGED || ENG == ENG_PAGED_RES) ? 5 : 7) k_apply(const __grid_constant__ KParams p) {
     typedef GeoT<ENG> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;

@@ -460,7 +460,7 @@ def run_gpu_other(args):
         off = torch.arange(0, n_books + 1, dtype=torch.int64, device=dev) * n_ev
         n_emit = int(((streams[0]["op_flags"] & abi.F_EMIT) != 0).sum())
         env = core.BatchedEnv(n_books, 0, 0, 1, 100_000, device=local, obs_words=abi.OBS_L2, max_orders=1 << 20, max_trades=1 << 20,
-                              max_steps=n_emit + 8, max_queue=32, pages_smem=16, pages_total=64)
+                              max_steps=n_emit + 8, max_queue=32, pages_smem=args.pages_smem if args.pages_smem != 10 else 64, pages_total=64)
         env.set_stream(stream.cuda_stream)
         torch.cuda.synchronize()
         for i in range(args.warmup + args.steps):
@@ -557,8 +557,13 @@ def run_gpu_other(args):
         d2 = torch.from_numpy(np.concatenate([x[n_rest:] for x in streams]).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_envs].contiguous()
         o1 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_rest
         o2 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
+        # Price pages resident in shared memory: as many as let the whole shard stay resident in ONE wave (a book's image is
+        # ~0.5 KB per page; 148 SMs x 227 KB).  128-296 books per GPU: all 192 pages (2 books per CTA); 512: ~100 pages.
+        books_per_sm = -(-n_envs // 148)
+        books_per_sm = 1 if books_per_sm <= 1 else 2 if books_per_sm <= 2 else 4 * (-(-books_per_sm // 4))
+        c5_pages = args.pages_smem if args.pages_smem != 10 else max(10, min(192, (227 * 1024 // books_per_sm - 8192) // 512))
         env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=1_800_000,
-                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, pages_smem=args.pages_smem, pages_total=192)
+                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, pages_smem=c5_pages, pages_total=192)
         env.set_stream(stream.cuda_stream)
         torch.cuda.synchronize()
         pre_stats = None
@@ -578,7 +583,7 @@ def run_gpu_other(args):
         ext = n_envs * n_steps * per_step
         name = (f"C5 shard: {per_gpu} books/GPU x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 "
                 "events per book (15% cancel, 15% modify, 60% limit within +-32 ticks, 10% market), level-2 record per step, "
-                "replayed from device memory; paged engine with HBM-resident price pages")
+                f"replayed from device memory; paged engine, {c5_pages} of 192 price pages per book resident in shared memory")
     barrier()
     ms = [a.elapsed_time(b) for a, b in ev]
     stats = env.stats()
@@ -638,7 +643,8 @@ def main():
     ap.add_argument("--max-orders", type=int, default=65536)
     ap.add_argument("--max-trades", type=int, default=65536)
     ap.add_argument("--max-queue", type=int, default=0, help="per-env instructions per step (0 = the workload's default)")
-    ap.add_argument("--pages-smem", type=int, default=10, help="c5: 32-level price pages per book resident in shared memory (of 192)")
+    ap.add_argument("--pages-smem", type=int, default=10,
+                    help="c5 / c2: 32-level price pages per book resident in shared memory (of 192 / 64); the default 10 means 'all of them'")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default=None, choices=["dense", "paged"],
                     help="default: dense for c3 / market (shallow books inside a known price window), paged for gym")

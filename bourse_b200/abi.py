@@ -54,7 +54,7 @@ EXPORTS = [
     "bb_level2", "bb_book_level1", "bb_book_level2", "bb_n_steps", "bb_history", "bb_history_all",
     "bb_n_orders", "bb_n_trades", "bb_orders", "bb_trades", "bb_order_status", "bb_time", "bb_set_time",
     "bb_set_trading", "bb_env_errors", "bb_stats", "bb_history_device", "bb_order_keys", "bb_load_book",
-    "bb_set_agents_market", "bb_step_device", "bb_level2_device", "bb_level1_device", "bb_device_alloc", "bb_device_free", "bb_memcpy",
+    "bb_set_agents_market", "bb_step_device", "bb_level2_device", "bb_level1_device", "bb_device_alloc", "bb_device_free", "bb_memcpy", "bb_run_agents_with_rows",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
     sig("bb_device_free", i32, vp, vp)
     sig("bb_memcpy", i32, vp, vp, vp, u64, i32)
     sig("bb_run_agents", i32, vp, u64, u32)
+    sig("bb_run_agents_with_rows", i32, vp, u64, vp, vp, u64, vp, vp)
     sig("bb_run_agents_to_host", i32, vp, u64, u32, u32, vp)
     sig("bb_level1", i32, vp, vp)
     sig("bb_level2", i32, vp, vp)

@@ -146,6 +146,13 @@ class BatchedEnv:
                                           C.c_void_p(d_out_ids_ptr) if d_out_ids_ptr else None,
                                           C.c_void_p(d_obs_ptr) if d_obs_ptr else None))
 
+    def run_agents_with_rows(self, seed: int, d_instrs_ptr: int, d_offsets_ptr: int, n_rows: int, d_out_ids_ptr: int = 0,
+                             d_obs_ptr: int = 0):
+        """One env-step of { built-in agents update; the caller's device-resident rows; Env::step } (bb_run_agents_with_rows)."""
+        self._ck(self._lib.bb_run_agents_with_rows(self._h, seed, C.c_void_p(d_instrs_ptr), C.c_void_p(d_offsets_ptr), n_rows,
+                                                   C.c_void_p(d_out_ids_ptr) if d_out_ids_ptr else None,
+                                                   C.c_void_p(d_obs_ptr) if d_obs_ptr else None))
+
     def level_2_data_device(self, d_out_ptr: int): self._ck(self._lib.bb_level2_device(self._h, C.c_void_p(d_out_ptr)))
     def level_1_data_device(self, d_out_ptr: int): self._ck(self._lib.bb_level1_device(self._h, C.c_void_p(d_out_ptr)))
 

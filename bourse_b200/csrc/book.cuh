@@ -50,6 +50,7 @@ enum { ST_NEW = 0, ST_ACTIVE = 1, ST_FILLED = 2, ST_CANCELLED = 3, ST_REJECTED =
 #define ERR_CAP_LIVE 0x80u
 #define ERR_TIME_ORDER 0x100u
 #define ERR_PRICE 0x200u  // bb_step_device: a NEW row's limit price was off the tick grid (row dropped)
+#define ERR_ROW_OP 0x400u  // bb_run_agents_with_rows: a row the in-kernel queue cannot carry (MODIFY, trader id >= 2^19)
 
 // Order record (types.rs:79-101 `Order` + orderbook.rs:36-44 key), 64 bytes = two 32-byte sectors split
 // by access pattern: the first sector is what matching / cancel / modify read and update, the second

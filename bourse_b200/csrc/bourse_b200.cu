@@ -283,8 +283,8 @@ int check_device_errors(bb_handle* h) {
         CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
         char buf[256];
         snprintf(buf, sizeof buf, "device flagged env errors 0x%x (0x1 orders 0x2 trades 0x4 pages/window 0x8 queue 0x10 bad id "
-                                  "0x20 granule 0x40 steps 0x80 live slots 0x100 time order 0x200 tick size); see bb_env_errors", flag);
-        return fail(h, (flag & ERR_BAD_ID) ? BB_EBADID : (flag & 0x80000000u) ? BB_ECUDA : (flag & ERR_PRICE) ? BB_EPRICE : BB_ECAP, buf);
+                                  "0x20 granule 0x40 steps 0x80 live slots 0x100 time order 0x200 tick size 0x400 unsupported row); see bb_env_errors", flag);
+        return fail(h, (flag & ERR_BAD_ID) ? BB_EBADID : (flag & 0x80000000u) ? BB_ECUDA : (flag & ERR_PRICE) ? BB_EPRICE : (flag & ERR_ROW_OP) ? BB_EINVAL : BB_ECAP, buf);
     }
     return BB_OK;
 }
@@ -786,7 +786,29 @@ int bb_set_agents_market(bb_handle* h, const bb_agent_group* groups, const uint3
     return set_agents_impl(h, groups, asset, n_groups);
 }
 
-int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
+namespace {
+struct ExtRows {  // bb_run_agents_with_rows: the caller's device-resident rows for the launch's first step
+    const bb_instr* d_instrs;
+    const u64* d_offsets;
+    u64* d_out_ids;
+    u32* d_obs_out;
+};
+int run_agents_impl(bb_handle* h, uint64_t seed, uint32_t n_steps, const ExtRows* ext);
+}  // namespace
+
+int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) { return run_agents_impl(h, seed, n_steps, nullptr); }
+
+int bb_run_agents_with_rows(bb_handle* h, uint64_t seed, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows,
+                            uint64_t* d_out_ids, uint32_t* d_obs_out) {
+    CHECK_H(h);
+    if (!d_env_offsets || (n_rows && !d_instrs)) return fail(h, BB_EINVAL, "null argument");
+    if (h->assets > 1) return fail(h, BB_EINVAL, "bb_run_agents_with_rows drives single-asset envs");
+    const ExtRows ext{d_instrs, d_env_offsets, d_out_ids, d_obs_out};
+    return run_agents_impl(h, seed, 1, &ext);
+}
+
+namespace {
+int run_agents_impl(bb_handle* h, uint64_t seed, uint32_t n_steps, const ExtRows* ext) {
     CHECK_H(h);
     if (h->groups.empty()) return fail(h, BB_EINVAL, "bb_set_agents has not been called");
     const bool mkt = !h->group_asset.empty();
@@ -817,14 +839,22 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     p.seed_hi = (u32)(seed >> 32);
     for (size_t i = 0; i < h->groups.size(); ++i) p.groups[i] = h->groups[i];
     for (size_t i = 0; i < h->group_asset.size(); ++i) p.group_asset[i] = h->group_asset[i];
+    if (ext) {
+        p.instrs = ext->d_instrs;
+        p.offsets = ext->d_offsets;
+        p.out_ids = ext->d_out_ids;
+        p.obs_out = ext->d_obs_out;
+    }
     int grid = 0, rc;
-    const bool mom = h->mom_groups != 0;
+    // external rows carry no slot hints: they run on the variants that also serve MomentumAgent / NoiseAgent events
+    const bool mom = h->mom_groups != 0 || ext != nullptr;
     // markets: the A books of a market are A consecutive warps of one CTA (a CTA holds as many whole markets as fit in 4 warps)
     const u32 wpb = mkt ? (WPB / h->assets) * h->assets : wpb_for(h->lay_sim.warp_bytes);
     const size_t sim_smem = (size_t)h->lay_sim.warp_bytes * wpb;
 #define SIM_CASE(E, M)                                                                                     \
     if (h->eng == E && mom == M) {                                                                         \
         if (mkt) { if ((rc = grid_for(h, k_sim<E, M, true>, h->lay_sim, h->cfg.n_envs, &grid, wpb))) return rc; } \
+        else if (ext) { if ((rc = grid_for(h, k_sim<E, true, false, true>, h->lay_sim, h->cfg.n_envs, &grid, wpb))) return rc; } \
         else if ((rc = grid_for(h, k_sim<E, M, false>, h->lay_sim, h->cfg.n_envs, &grid, wpb))) return rc;  \
     }
     SIM_CASE(ENG_FAST, false) SIM_CASE(ENG_FAST, true) SIM_CASE(ENG_PAGED, false) SIM_CASE(ENG_PAGED, true)
@@ -841,6 +871,7 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
 #define SIM_LAUNCH(E, M)                                                                       \
     if (h->eng == E && mom == M) {                                                             \
         if (mkt) k_sim<E, M, true><<<grid, wpb * 32, sim_smem, h->stream>>>(p);                \
+        else if (ext) k_sim<E, true, false, true><<<grid, wpb * 32, sim_smem, h->stream>>>(p); \
         else k_sim<E, M, false><<<grid, wpb * 32, sim_smem, h->stream>>>(p);                   \
     }
     SIM_LAUNCH(ENG_FAST, false) SIM_LAUNCH(ENG_FAST, true) SIM_LAUNCH(ENG_PAGED, false) SIM_LAUNCH(ENG_PAGED, true)
@@ -852,6 +883,7 @@ int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps) {
     h->recorded_host += n_steps;
     return BB_OK;
 }
+}  // namespace
 
 // Run n_steps env-steps and stream every env-step's observation record to HOST memory while the simulation runs:
 // the steps are launched in chunks, and chunk k's records are copied out on a second stream while chunk k+1 is being

@@ -598,8 +598,13 @@ __device__ __forceinline__ void market_bar_sync(u32 id, u32 n_threads) {
 // queue executing at start + i on its asset's book.  The warps exchange their per-group instruction counts through
 // shared memory (one named barrier per step), each then derives the same market-wide permutation from the market's
 // Philox key and pulls out its own events together with their positions in it.
-template <int ENG, bool MOM, bool MKT = false>
+// EXT (bb_run_agents_with_rows; always with MOM, never with MKT): after the built-in agents' updates the caller's own
+// rows for the env — already in device memory, the action block of an RL-style loop — are submitted in row order, exactly
+// as `agents.update(env); env.place_order(..) / env.cancel_order(..); env.step()` would: NEW rows take the next ids, rows
+// that queue nothing are skipped, and everything takes part in the step's one shuffle.
+template <int ENG, bool MOM, bool MKT = false, bool EXT = false>
 __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __grid_constant__ KParams p) {
+    static_assert(!EXT || (MOM && !MKT), "external rows ride on the unhinted (MOM) single-asset variants");
     typedef GeoT<ENG> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = keep32(threadIdx.x & 31u), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -707,6 +712,46 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
                 if (MKT && lane == gi) mk_cnt = e.n - n_before;
                 slot_base += ag.n_agents;
                 if (mine) chip_base += ag.n_agents;
+            }
+            if constexpr (EXT) {
+                const u64 off = p.offsets[env];
+                const u32 m = s == 0 ? (u32)(p.offsets[env + 1] - off) : 0u;  // the rows belong to the launch's first step
+                const bb_instr* ins = p.instrs + off;
+                u32 max_cancel = 0;  // 1 + largest id a cancel row names
+                for (u32 j0 = 0; j0 < m; j0 += 32) {
+                    const u32 j = j0 + lane;
+                    u32 of = 0, price = 0, vol = 0, trader = 0, oid = 0;
+                    if (j < m) {
+                        const uint4 x = reinterpret_cast<const uint4*>(ins + j)[0], y = reinterpret_cast<const uint4*>(ins + j)[1];
+                        of = x.z; oid = x.w; price = y.x; vol = y.y; trader = y.z;
+                    }
+                    const u32 op = of & BB_OP_MASK;
+                    const bool bid = (of & BB_F_BID) != 0u;
+                    // create_order's tick check (orderbook.rs:367-383): the row is dropped like the Err return
+                    const bool bad_tick = op == BB_OP_NEW && !(of & BB_F_MARKET) && (price % g.tick != 0u);
+                    const bool is_new = op == BB_OP_NEW && !bad_tick, is_cancel = op == BB_OP_CANCEL;
+                    const bool queued = is_new || is_cancel;
+                    const u32 below = (1u << lane) - 1u;
+                    const u32 nm = __ballot_sync(BB_FULL, is_new), qm = __ballot_sync(BB_FULL, queued);
+                    const u32 id = e.next_id + __popc(nm & below), pos = e.n + __popc(qm & below);
+                    if (of & BB_F_MARKET) price = bid ? 0xFFFFFFFFu : 0u;  // types.rs:160-172, 213-225
+                    if (j < m && p.out_ids) p.out_ids[off + j] = is_new ? (u64)id : ~0ULL;
+                    if (queued && pos < p.max_queue) {
+                        // the in-kernel queue format: bit 0 NEW, bit 1 bid, no hint, trader id above bit 13
+                        const uint4 ev = make_uint4(is_new ? (1u | (bid ? 2u : 0u) | (trader << 13)) : 0u, is_new ? id : oid, price, vol);
+                        if constexpr (G::DENSE) sts128(qs + 16u * pos, ev);
+                        else q[pos] = ev;
+                    }
+                    if (is_cancel) max_cancel = max(max_cancel, oid == 0xFFFFFFFFu ? oid : oid + 1u);
+                    // the queue carries NEW and CANCEL only: a MODIFY row, or a trader id beyond 19 bits, is refused
+                    if (__any_sync(BB_FULL, bad_tick)) b.err |= ERR_PRICE;
+                    if (__any_sync(BB_FULL, op == BB_OP_MODIFY || (is_new && trader >= (1u << 19)))) b.err |= ERR_ROW_OP;
+                    e.next_id += __popc(nm);
+                    e.n += __popc(qm);
+                }
+                // a cancel of an id that does not exist by the end of submission is the reference's panic (orderbook.rs:642)
+                if (__reduce_max_sync(BB_FULL, max_cancel) > e.next_id) b.err |= ERR_BAD_ID;
+                __syncwarp();
             }
             if (e.n > p.max_queue) b.err |= ERR_CAP_QUEUE;
             u32 n = min(e.n, p.max_queue);
@@ -909,6 +954,11 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
             if (staged) {
                 u32 w0, w1;
                 book_obs(g, b, p.obs_words, &w0, &w1);
+                if (EXT && p.obs_out && s + 1 == p.n_steps) {  // the caller's observation buffer gets the last record too
+                    u32* o = p.obs_out + (size_t)env * p.obs_words;
+                    if (lane < p.obs_words) o[lane] = w0;
+                    if (lane + 32u < p.obs_words) o[lane + 32u] = w1;
+                }
                 const u32 dst = stage + 4u * (sbuf * stage_words + sfill * p.obs_words);
                 if (lane < p.obs_words) sts(dst + 4u * lane, w0);
                 if (lane + 32u < p.obs_words) sts(dst + 4u * (lane + 32u), w1);

@@ -101,10 +101,16 @@ class VectorEnv:
     price creates nothing (the reference raises ValueError there); the env is flagged and `check_errors` raises."""
 
     def __init__(self, n_envs: int, rows_per_env: int, seed: int, start_time: int, tick_size: int, step_size: int,
-                 trading: bool = True, *, level_1: bool = False, **kw):
-        kw.setdefault("max_queue", max(rows_per_env, 16))
+                 trading: bool = True, *, level_1: bool = False, agents=None, agent_seed: int = 0, **kw):
+        """`agents`: optional background population (a list of `core.random_group` / `momentum_group` / `noise_group`
+        records).  With it every `step` is `{ agents.update(env); the action rows; env.step() }` in one launch
+        (bb_run_agents_with_rows): the rows join the agents' instructions in the step's one shuffled queue (Philox key
+        `agent_seed`).  Action rows may then be NEW, CANCEL or no-op (MODIFY is refused)."""
+        n_bg = sum(int(g["n_agents"]) for g in agents) if agents else 0
+        kw.setdefault("max_queue", max(rows_per_env + 2 * n_bg, 16))
         if rows_per_env > kw["max_queue"]:
             raise ValueError("rows_per_env exceeds max_queue")
+        self._agents, self._agent_seed = agents, agent_seed
         self.n_envs, self.rows = n_envs, rows_per_env
         self.env = BatchedEnv(n_envs, seed, start_time, tick_size, step_size, trading, obs_words=abi.OBS_L1 if level_1 else abi.OBS_L2, **kw)
         self.obs_words = abi.OBS_L1 if level_1 else abi.OBS_L2
@@ -113,6 +119,8 @@ class VectorEnv:
         self._actions = DeviceArray(self.env, (n_envs, rows_per_env), ACTION_DTYPE)  # staging for host-side actions
         self._offsets = DeviceArray(self.env, (n_envs + 1,), np.uint64)
         self._offsets.copy_from_host(np.arange(n_envs + 1, dtype=np.uint64) * np.uint64(rows_per_env))
+        if agents:
+            self.env.set_agents(agents)
 
     def close(self):
         for a in (self.obs, self.ids, self._actions, self._offsets):
@@ -124,7 +132,7 @@ class VectorEnv:
         return self.obs
 
     def reset(self) -> DeviceArray:
-        self.env.reset()
+        self.env.reset()   # (the agent population survives a reset; its state is cleared with the books)
         return self._observe()
 
     def step(self, actions) -> typing.Tuple[DeviceArray, DeviceArray]:
@@ -136,8 +144,11 @@ class VectorEnv:
                 raise ValueError(f"actions must have shape ({self.n_envs}, {self.rows})")
             self._actions.copy_from_host(a)
             ptr = self._actions.ptr
-        # one launch: ids, Env::step and the observation records written straight into self.obs
-        self.env.step_device(ptr, self._offsets.ptr, self.n_envs * self.rows, self.ids.ptr, self.obs.ptr)
+        # one launch: (background agents,) ids, Env::step and the observation records written straight into self.obs
+        if self._agents:
+            self.env.run_agents_with_rows(self._agent_seed, ptr, self._offsets.ptr, self.n_envs * self.rows, self.ids.ptr, self.obs.ptr)
+        else:
+            self.env.step_device(ptr, self._offsets.ptr, self.n_envs * self.rows, self.ids.ptr, self.obs.ptr)
         return self.obs, self.ids
 
     def check_errors(self):

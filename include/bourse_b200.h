@@ -47,6 +47,7 @@ typedef enum {
 #define BB_ERR_CAP_LIVE   0x80u  /* MomentumAgent live-order list / dense engine's resting-order slots overflow */
 #define BB_ERR_TIME_ORDER 0x100u /* dense engine: a resting order arrived out of time order at its price level */
 #define BB_ERR_PRICE 0x200u      /* bb_step_device: a NEW row's limit price was not a multiple of tick_size (row dropped) */
+#define BB_ERR_ROW_OP 0x400u     /* bb_run_agents_with_rows: a MODIFY row or a trader id >= 2^19 (row dropped) */
 
 #define BB_OBS_L1 9u   /* StepEnvNumpy.level_1_data layout, rust/src/step_sim_numpy.rs:300-318 */
 #define BB_OBS_L2 45u  /* StepEnvNumpy.level_2_data layout, rust/src/step_sim_numpy.rs:351-368 */
@@ -230,6 +231,14 @@ int bb_set_agents_market(bb_handle* h, const bb_agent_group* groups, const uint3
  * Draws are Philox4x32-10 keyed (seed; global env id, step, agent) — DESIGN.md "RNG contract".
  * Asynchronous on the handle's stream; pair with bb_synchronize or any read call. */
 int bb_run_agents(bb_handle* h, uint64_t seed, uint32_t n_steps);
+/* ONE env-step of { agents.update(env); <the caller's rows>; env.step() } with the rows already in DEVICE memory: the loop of a
+ * learning agent trading against the built-in background agents.  Rows are laid out as for
+ * bb_step_device and submitted after the agents' updates, in row order: BB_OP_NEW (ids in d_out_ids, BB_NO_ID elsewhere;
+ * may be NULL) and BB_OP_CANCEL; no-op rows queue nothing; BB_OP_MODIFY rows are refused (BB_ERR_ROW_OP).  Everything
+ * takes part in the step's one Philox-keyed shuffle.  d_obs_out ([n_envs][obs_words], may be NULL) receives the
+ * end-of-step records from the same launch.  Asynchronous on the handle's stream. */
+int bb_run_agents_with_rows(bb_handle* h, uint64_t seed, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows,
+                            uint64_t* d_out_ids, uint32_t* d_obs_out);
 /* Same run, with every env-step's observation record (Level2DataRecords, crates/step_sim/src/data.rs:9-57; the
  * arrays StepEnvNumpy.get_market_data returns, rust/src/step_sim_numpy.rs:448-516) streamed to HOST memory while
  * the simulation runs: the steps are launched in chunks of chunk_steps (0 = a geometric schedule: half of what is

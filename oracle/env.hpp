@@ -446,35 +446,46 @@ public:
         }
     }
 
-    void run_keyed(uint64_t seed, uint32_t env_id, uint64_t n_steps) {
+    // The two halves of one keyed step, separately callable so that a caller can queue its own instructions between
+    // them (agents.update(env) ... env.place_order(..) ... env.step(): the shape of an RL loop with background agents,
+    // bb_run_agents_with_rows on the CUDA side).
+    void agents_update_keyed(uint64_t seed, uint32_t env_id) {
         const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        for (uint64_t s = 0; s < n_steps; ++s) {
-            const uint32_t step = step_counter;
-            uint32_t slot_base = 0, gi = 0;
-            for (auto& g : order) {
-                if (g.first == GROUP_RANDOM) {
-                    randoms[g.second].update_keyed(env, env_id, step, slot_base, k0, k1);
-                    slot_base += randoms[g.second].p.n_agents;
-                } else if (g.first == GROUP_MOMENTUM) {
-                    momentums[g.second].update_keyed(env, env_id, step, gi, slot_base, k0, k1);
-                    slot_base += momentums[g.second].p.n_agents;
-                } else {
-                    noises[g.second].update_keyed(env, env_id, step, gi, slot_base, k0, k1);
-                    slot_base += noises[g.second].p.n_agents;
-                }
-                ++gi;
+        const uint32_t step = step_counter;
+        uint32_t slot_base = 0, gi = 0;
+        for (auto& g : order) {
+            if (g.first == GROUP_RANDOM) {
+                randoms[g.second].update_keyed(env, env_id, step, slot_base, k0, k1);
+                slot_base += randoms[g.second].p.n_agents;
+            } else if (g.first == GROUP_MOMENTUM) {
+                momentums[g.second].update_keyed(env, env_id, step, gi, slot_base, k0, k1);
+                slot_base += momentums[g.second].p.n_agents;
+            } else {
+                noises[g.second].update_keyed(env, env_id, step, gi, slot_base, k0, k1);
+                slot_base += noises[g.second].p.n_agents;
             }
-            n_instructions += env.transactions.size();
-            env.step_with([&](std::vector<Event>& tx) {
-                // Fisher-Yates from the back, one Philox word per position
-                for (size_t i = tx.size(); i > 1; --i) {
-                    const uint32_t idx = (uint32_t)(i - 1);
-                    const Philox4 r = philox4x32_10(env_id, step, PHILOX_SLOT_SHUFFLE, idx >> 2, k0, k1);
-                    const uint32_t j = mulhi_range(r.v[idx & 3], (uint32_t)i);
-                    std::swap(tx[i - 1], tx[j]);
-                }
-            });
-            ++step_counter;
+            ++gi;
+        }
+    }
+    void step_keyed(uint64_t seed, uint32_t env_id) {
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        const uint32_t step = step_counter;
+        n_instructions += env.transactions.size();
+        env.step_with([&](std::vector<Event>& tx) {
+            // Fisher-Yates from the back, one Philox word per position
+            for (size_t i = tx.size(); i > 1; --i) {
+                const uint32_t idx = (uint32_t)(i - 1);
+                const Philox4 r = philox4x32_10(env_id, step, PHILOX_SLOT_SHUFFLE, idx >> 2, k0, k1);
+                const uint32_t j = mulhi_range(r.v[idx & 3], (uint32_t)i);
+                std::swap(tx[i - 1], tx[j]);
+            }
+        });
+        ++step_counter;
+    }
+    void run_keyed(uint64_t seed, uint32_t env_id, uint64_t n_steps) {
+        for (uint64_t s = 0; s < n_steps; ++s) {
+            agents_update_keyed(seed, env_id);
+            step_keyed(seed, env_id);
         }
     }
 };

@@ -102,6 +102,8 @@ def lib() -> C.CDLL:
     sig("orc_sim_set_groups", None, vp, vp, u32)
     sig("orc_sim_run", None, vp, i32, u64, u32, u64)
     sig("orc_sim_n_instructions", u64, vp)
+    sig("orc_sim_agents_update", None, vp, u64, u32)
+    sig("orc_sim_step_keyed", i32, vp, u64, u32)
     sig("orc_bench_agents", dbl, u32, u32, u64, u64, i32, u64, u32, u64, vp, u32, vp)
     sig("orc_bench_replay", dbl, u32, u32, u32, vp, u64, vp)
     sig("orc_market_new", vp, u64, u64, vp, u32, u64, i32)
@@ -341,6 +343,15 @@ class _EnvBase(_BookView):
 
     def run_agents(self, n_steps, seed, env_id=0, keyed=True):
         lib().orc_sim_run(self._h, int(keyed), seed, env_id, n_steps)
+
+    def agents_update(self, seed, env_id=0):
+        """First half of one keyed step: the built-in agents queue their instructions (Philox contract)."""
+        lib().orc_sim_agents_update(self._h, seed, env_id)
+
+    def step_keyed(self, seed, env_id=0):
+        """Second half: Env::step with the keyed shuffle over everything queued, the caller's own instructions included."""
+        if lib().orc_sim_step_keyed(self._h, seed, env_id):
+            raise IndexError("order id out of range")
 
     def n_instructions(self):
         return lib().orc_sim_n_instructions(self._h)

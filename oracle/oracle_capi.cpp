@@ -259,6 +259,16 @@ void orc_sim_run(void* s, int keyed, uint64_t seed, uint32_t env_id, uint64_t n_
     if (keyed) h->sim.run_keyed(seed, env_id, n_steps); else h->sim.run_stream(seed, n_steps);
 }
 uint64_t orc_sim_n_instructions(void* s) { return ((SimHandle*)s)->sim.n_instructions; }
+// the two halves of one keyed step (instructions queued in between take part in the step's shuffle)
+void orc_sim_agents_update(void* s, uint64_t seed, uint32_t env_id) { ((SimHandle*)s)->sim.agents_update_keyed(seed, env_id); }
+int orc_sim_step_keyed(void* s, uint64_t seed, uint32_t env_id) {
+    try {
+        ((SimHandle*)s)->sim.step_keyed(seed, env_id);
+    } catch (const std::out_of_range&) {
+        return -2;
+    }
+    return 0;
+}
 
 // ---------------------------------------------------------------- MarketEnv (multi-asset)
 struct MarketHandle {

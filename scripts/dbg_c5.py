@@ -10,7 +10,7 @@ d2 = torch.from_numpy(s[n_rest:].view(np.uint8)).to(dev).repeat(n_envs, 1).conti
 o1 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_rest
 o2 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
 env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=n_rest + n_steps * per_step, max_trades=1 << 20,
-                      max_steps=n_steps, max_queue=32, pages_smem=10, pages_total=192)
+                      max_steps=n_steps, max_queue=32, pages_smem=int(sys.argv[4]) if len(sys.argv) > 4 else 192, pages_total=192)
 torch.cuda.synchronize()
 env.replay_device(d1.data_ptr(), o1.data_ptr()); env.synchronize()
 import time; t0 = time.time()

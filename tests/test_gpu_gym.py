@@ -136,3 +136,77 @@ def test_step_device_argument_checks():
     with pytest.raises(ValueError, match="pending"):
         e2.step_device(p, p, 0)
     e2.device_free(p)
+
+
+@pytest.mark.parametrize("kw,groups_name", [(dict(price_window=(20, 180), live_cap=254), "c3"), (dict(), "c3"), (dict(), "c4")],
+                         ids=["dense_random", "fast_random", "fast_momentum"])
+def test_vector_env_with_background_agents(oracle, kw, groups_name):
+    """bb_run_agents_with_rows: every step is { built-in agents update; the action rows; Env::step } in one launch; per
+    env it must equal the oracle's agents_update + place / cancel calls + keyed step (one shuffled queue)."""
+    from bourse_b200 import workloads
+    groups = workloads.c3_groups() if groups_name == "c3" else workloads.c4_groups()
+    n_envs, rows, n_steps, seed = 24, 4, 25, 77
+    rng = np.random.default_rng(8)
+    v = gym.VectorEnv(n_envs, rows, 0, 0, 1, 1_000_000, agents=groups, agent_seed=seed, max_orders=8192, max_trades=8192,
+                      max_steps=64, max_queue=160, **kw)
+    orcs = [oracle.StepEnv(0, 0, 1, 1_000_000) for _ in range(n_envs)]
+    for o in orcs:
+        o.set_groups(groups)
+    v.reset()
+    mine = [[] for _ in range(n_envs)]   # ids this "learner" placed, per env
+    for s in range(n_steps):
+        op = np.zeros((n_envs, rows), np.uint32)
+        cols = {k: np.zeros((n_envs, rows), np.uint64) for k in ("bid", "vol", "trader", "price", "order_id", "market")}
+        for e in range(n_envs):
+            for r in range(rows):
+                u = rng.random()
+                if u < 0.2:
+                    continue
+                if u < 0.75 or not mine[e]:
+                    op[e, r] = abi.OP_NEW
+                    cols["bid"][e, r], cols["vol"][e, r] = rng.random() < 0.5, rng.integers(1, 30)
+                    cols["trader"][e, r], cols["market"][e, r] = 500 + r, rng.random() < 0.1
+                    cols["price"][e, r] = 2 * rng.integers(40, 61)
+                else:
+                    op[e, r] = abi.OP_CANCEL
+                    cols["order_id"][e, r] = mine[e][rng.integers(len(mine[e]))]
+        obs, ids = v.step(gym.pack_actions(op, **cols))
+        obs, ids = obs.numpy(), ids.numpy()
+        for e, o in enumerate(orcs):
+            o.agents_update(seed, e)
+            want = np.full(rows, abi.NO_ID, np.uint64)
+            for r in range(rows):
+                if op[e, r] == abi.OP_NEW:
+                    want[r] = o.place_order(bool(cols["bid"][e, r]), int(cols["vol"][e, r]), int(cols["trader"][e, r]),
+                                            None if cols["market"][e, r] else int(cols["price"][e, r]))
+                    mine[e].append(int(want[r]))
+                elif op[e, r] == abi.OP_CANCEL:
+                    o.cancel_order(int(cols["order_id"][e, r]))
+            o.step_keyed(seed, e)
+            assert np.array_equal(ids[e], want), (s, e)
+            assert np.array_equal(obs[e], o.level_2_data_array()), (s, e)
+    v.check_errors()
+    for e in range(0, n_envs, 5):
+        assert v.env.get_trades(e) == orcs[e].get_trades() and v.env.get_orders(e) == orcs[e].get_orders()
+        assert np.array_equal(v.env.history(e), orcs[e]._history())
+    # the learner's orders traded against the background population
+    assert any(t[4] in mine[0] or t[5] in mine[0] for t in orcs[0].get_trades())
+    # plain agent launches continue the same books (the on-chip agent tables are rebuilt per launch)
+    v.env.run_agents(3, seed)
+    for e in (0, 7):
+        orcs[e].run_agents(3, seed, env_id=e, keyed=True)
+        assert np.array_equal(v.env.history(e), orcs[e]._history())
+    v.close()
+
+
+def test_background_agent_rows_refuse_modify_and_unknown_ids():
+    from bourse_b200 import workloads
+    v = gym.VectorEnv(2, 2, 0, 0, 1, 1_000_000, agents=workloads.c3_groups(), agent_seed=1, max_orders=1024, max_trades=1024, max_steps=8,
+                      max_queue=128)
+    v.reset()
+    v.step(gym.pack_actions(np.array([[abi.OP_MODIFY, abi.OP_NOOP], [abi.OP_NOOP, abi.OP_NOOP]], np.uint32), order_id=0, price=50, vol=1))
+    err = v.env.env_errors()
+    assert err[0] == 0x400 and err[1] == 0
+    v.step(gym.pack_actions(np.array([[abi.OP_NOOP, abi.OP_NOOP], [abi.OP_CANCEL, abi.OP_NOOP]], np.uint32), order_id=100000))
+    assert v.env.env_errors()[1] == 0x10
+    v.close()

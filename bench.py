@@ -372,10 +372,19 @@ def run_gym(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     blocks = gym_action_blocks(n_steps, 256, rows, SEED)                       # [step][env % 256][row]
+    eng_kw = dict(price_window=(960, 1056), live_cap=254) if args.engine == "dense" else dict(pages_smem=10)
+    bg = None
+    if args.bg_agents:
+        # a learner's rows against the C3 background population (50 + 50 RandomAgents, prices 20..178): every step is
+        # { agents.update; rows; Env::step } in ONE launch (bb_run_agents_with_rows); the rows quote inside the agents' range
+        bg = workloads.c3_groups()
+        blocks["price"] = np.where((blocks["op_flags"] & abi.F_MARKET) != 0, blocks["price"], 2 * (40 + blocks["price"] % 21))
+        eng_kw = dict(price_window=(20, 180), live_cap=254) if args.engine == "dense" else dict(pages_smem=10)
+        eng_kw.update(agents=bg, agent_seed=SEED, max_queue=128)
+    v = gym.VectorEnv(n_envs, rows, SEED, 0, 1, 1_000_000 if bg else 1000, device=local, max_orders=32768 if bg else 4096,
+                      max_trades=32768 if bg else 8192, max_steps=n_steps + 8, **eng_kw)
     dev = torch.from_numpy(blocks.view(np.uint8).reshape(n_steps, 256, rows * 32)).cuda()
     dev = dev.repeat(1, (n_envs + 255) // 256, 1)[:, :n_envs].contiguous()       # [step][env][row bytes]
-    eng_kw = dict(price_window=(960, 1056), live_cap=254) if args.engine == "dense" else dict(pages_smem=10)
-    v = gym.VectorEnv(n_envs, rows, SEED, 0, 1, 1000, device=local, max_orders=4096, max_trades=8192, max_steps=n_steps + 8, **eng_kw)
     v.env.set_stream(stream.cuda_stream)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -395,7 +404,7 @@ def run_gym(args):
     k_ms = sum(ms) / len(ms)
     stats = v.env.stats()
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and not bg:
         from oracle import oracle as orc
         orc.build()
         cores = host_cores()
@@ -409,11 +418,12 @@ def run_gym(args):
         "metric": METRIC, "value": stats["instructions"] / (k_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"vectorised device-resident loop: {n_envs} envs x {rows} action rows x {n_steps} steps (65% orders, 25% cancels, "
-                               f"10% no-ops), level-2 observation of every env after every step, {args.engine} engine"},
+                               f"10% no-ops){' + 100 background RandomAgents per env in the same shuffled queue' if bg else ''}, level-2 observation of every "
+                               f"env after every step, {args.engine} engine"},
         "env_steps_per_sec": n_envs * n_steps / (k_ms * 1e-3), "us_per_vector_step": 1e3 * k_ms / n_steps, "orders_per_pass": stats["instructions"],
         "trades_per_pass": stats["trades"], "gpu_launches": args.steps * (2 + n_steps),
         "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
-                     "traffic": None, "kernel": "k_apply<ENV> (one launch per vector step)", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg / n_steps,
+                     "traffic": None, "kernel": "k_sim<.., EXT> (one launch per vector step)" if bg else "k_apply<ENV> (one launch per vector step)", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg / n_steps,
                      "peak_source": peak_src},
         **({"cpu_baseline": cpu} if cpu else {})}))
     v.close()
@@ -645,6 +655,7 @@ def main():
     ap.add_argument("--max-queue", type=int, default=0, help="per-env instructions per step (0 = the workload's default)")
     ap.add_argument("--pages-smem", type=int, default=10,
                     help="c5 / c2: 32-level price pages per book resident in shared memory (of 192 / 64); the default 10 means 'all of them'")
+    ap.add_argument("--bg-agents", action="store_true", help="gym: the C3 background population trades in every env (bb_run_agents_with_rows)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default=None, choices=["dense", "paged"],
                     help="default: dense for c3 / market (shallow books inside a known price window), paged for gym")
@@ -652,7 +663,7 @@ def main():
                     help="c3 = the headline line; the others are the secondary configs (market = the multi-asset example)")
     args = ap.parse_args()
     if args.engine is None:
-        args.engine = "paged" if args.workload == "gym" else "dense"
+        args.engine = "paged" if args.workload == "gym" and not args.bg_agents else "dense"
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

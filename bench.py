@@ -534,7 +534,7 @@ def run_gpu_other(args):
         # `--envs / 2` lockstep markets per GPU; one level-2 record per asset and step (MarketEnv keeps Level2DataRecords)
         n_assets = 2
         per_gpu = args.envs
-        base, n_envs = shard_range(per_gpu * world, world, rank)
+        base, n_envs = shard_range(per_gpu * world, world, rank, multiple=n_assets)   # markets stay whole
         groups, g_assets = workloads.market_example_groups()
         obs, n_steps = abi.OBS_L2, args.sim_steps
         eng_kw = dict(price_window=(20, 180), live_cap=128) if args.engine == "dense" else {}

@@ -399,8 +399,8 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
                                            std::to_string(prop.minor) + "); this library is built for sm_100a only");
     CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
 
-    if (cfg->assets > 1 && cfg->n_envs % cfg->assets != 0)
-        return fail(nullptr, BB_EINVAL, "n_envs must be a multiple of assets (books per market)");
+    if (cfg->assets > 1 && (cfg->n_envs % cfg->assets != 0 || cfg->env_id_base % cfg->assets != 0))
+        return fail(nullptr, BB_EINVAL, "n_envs and env_id_base must be multiples of assets (books per market)");
     bb_handle* h = new bb_handle();
     h->cfg = *cfg;
     h->assets = cfg->assets > 1 ? cfg->assets : 1u;

@@ -12,14 +12,19 @@ import typing
 STAT_KEYS = ("instructions", "orders_created", "trades", "traded_volume", "env_steps", "transitions", "error_envs")
 
 
-def shard_range(n_envs_total: int, world_size: int, rank: int) -> typing.Tuple[int, int]:
-    """(first global env id, number of envs) of `rank`: contiguous blocks, remainder spread over the first ranks."""
+def shard_range(n_envs_total: int, world_size: int, rank: int, multiple: int = 1) -> typing.Tuple[int, int]:
+    """(first global env id, number of envs) of `rank`: contiguous blocks, remainder spread over the first ranks.
+
+    `multiple`: the blocks are made of whole groups of that many consecutive envs — the books of one multi-asset market
+    (`bb_config.assets`) must stay on one GPU, and `env_id_base` must be a multiple of `assets` for the market-keyed RNG."""
     if not 0 <= rank < world_size:
         raise ValueError("rank out of range")
-    q, r = divmod(n_envs_total, world_size)
+    if multiple < 1 or n_envs_total % multiple:
+        raise ValueError("n_envs_total must be a multiple of `multiple`")
+    q, r = divmod(n_envs_total // multiple, world_size)
     count = q + (1 if rank < r else 0)
     base = rank * q + min(rank, r)
-    return base, count
+    return base * multiple, count * multiple
 
 
 def gather_stats(stats: dict, elapsed_ms: float, l1_checksum: int, device=None) -> dict:

@@ -73,8 +73,13 @@ def test_shard_ranges_keep_markets_whole():
         assert spans[0][0] == 0 and sum(n for _, n in spans) == total
         assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
         assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
-    # 2-asset markets: an even per-rank count keeps every market on one rank
-    assert all(sharding.shard_range(4096 * 4, 4, r)[0] % 2 == 0 for r in range(4))
+    # multi-asset markets stay whole: blocks are multiples of `assets`, whatever the remainder
+    for total, world, a in ((14, 4, 2), (4096 * 3, 5, 3), (8, 8, 4)):
+        spans = [sharding.shard_range(total, world, r, multiple=a) for r in range(world)]
+        assert all(b % a == 0 and n % a == 0 for b, n in spans) and sum(n for _, n in spans) == total
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        sharding.shard_range(7, 2, 0, multiple=2)
 
 
 def test_bench_gym_policy_never_names_an_unissued_id():

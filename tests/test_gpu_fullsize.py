@@ -140,7 +140,7 @@ def test_c5_deep_book_shard(core, oracle):
     del d_distinct
     d_off = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_per
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=1_800_000, max_trades=1 << 20,
-                          max_steps=n_steps, max_queue=32, pages_smem=10, pages_total=192)
+                          max_steps=n_steps, max_queue=32, pages_smem=192, pages_total=192)   # the bench's layout: all pages resident
     torch.cuda.synchronize()
     env.replay_device(d_all.data_ptr(), d_off.data_ptr())
     assert not env.env_errors().any()

@@ -42,6 +42,25 @@ def test_wide_price_range_uses_hbm_pages(core, oracle):
     compare_book(g._env, 0, ob, obs_gpu, obs_cpu)
 
 
+@pytest.mark.parametrize("pages", [64, 40, 200], ids=["64_pages", "40_pages_not_x32", "200_pages_2_books_per_cta"])
+def test_all_pages_resident_geometry(core, oracle, pages):
+    """pages_smem == pages_total selects k_apply<.., ENG_PAGED_RES> (no HBM page variants); the image of a 200-page book
+    (103 KB) makes the launch use two books per CTA.  Wide price range, modifies, market orders, trading windows."""
+    n = 12000
+    streams = [workloads.replay_stream(n, 20 + i, tick_size=1, half_width=500) for i in range(3)]
+    env = core.BatchedEnv(3, 5, 0, 1, 1000, max_orders=n + 64, max_trades=4 * n, max_steps=n // 64 + 16, max_queue=32,
+                          pages_smem=pages, pages_total=pages)
+    env.replay(np.concatenate(streams), np.arange(4, dtype=np.uint64) * n)
+    assert not env.env_errors().any()
+    books = []
+    for e in range(3):
+        ob = oracle.OrderBook(0, 1)
+        obs_cpu = ob.replay(streams[e], obs_cap=n)
+        compare_book(env, e, ob, env.history(e), obs_cpu)
+        books.append(ob)
+    assert sum(len(b.get_trades()) for b in books) > 1000
+
+
 def test_extreme_prices(core, oracle):
     """Orders at the ends of the u32 price range, market sentinels as limit prices (N3), wrapping L2 levels."""
     M = 2**32 - 1
@@ -76,12 +95,15 @@ def test_many_books_replay(core, oracle):
         assert st["error_envs"] == 0 and st["trades"] > 0
 
 
-def test_env_mode_batched_bit_exact(core, oracle):
+@pytest.mark.parametrize("kw", [dict(), dict(pages_smem=48, pages_total=48), dict(pages_smem=4, pages_total=64)],
+                         ids=["fast", "all_resident", "hbm_pages"])
+def test_env_mode_batched_bit_exact(core, oracle, kw):
     """Host-queued instructions + Env::step over 32 envs x 30 steps with cancels and modifies: the CUDA
-    env and the oracle env share the Xoroshiro shuffle stream, so everything must match exactly."""
+    env and the oracle env share the Xoroshiro shuffle stream, so everything must match exactly (on the single-directory
+    geometry, the all-resident one — k_apply<ENV, ENG_PAGED_RES> — and the generic one with HBM pages)."""
     n_envs, n_steps = 32, 30
     rng = np.random.default_rng(5)
-    genv = core.BatchedEnv(n_envs, 77, 0, 1, 1000, max_orders=4096, max_trades=8192, max_steps=64, max_queue=128)
+    genv = core.BatchedEnv(n_envs, 77, 0, 1, 1000, max_orders=4096, max_trades=8192, max_steps=64, max_queue=128, **kw)
     cenvs = [oracle.StepEnv(77 + e, 0, 1, 1000) for e in range(n_envs)]
     issued = np.zeros(n_envs, np.int64)
     for step in range(n_steps):

@@ -154,8 +154,9 @@ def test_env_mode_batched_bit_exact(core, oracle, kw):
     assert sum(len(ce.get_trades()) for ce in cenvs) > 100
 
 
+@pytest.mark.parametrize("pages", [(8, 32), (32, 32), (64, 64)], ids=["hbm_pages", "single_directory", "all_resident"])
 @pytest.mark.parametrize("tick_size", [1, 2])
-def test_adversarial_fuzz_many_books(core, oracle, tick_size):
+def test_adversarial_fuzz_many_books(core, oracle, tick_size, pages):
     """768 books, each replaying its own short ADVERSARIAL stream in one launch (tiny price / id / time domains:
     equal-key collisions N1, zero volumes N5, market sentinels N3, trading toggles N6, every modify variant N4, prices at
     both ends of the u32 range); every book must equal the oracle — trade log, order table, every emitted record."""
@@ -168,7 +169,7 @@ def test_adversarial_fuzz_many_books(core, oracle, tick_size):
     off[1:] = np.cumsum([len(s) for s in streams])
     # price_granule=1: modify_order applies no tick check (N4), so with tick 2 an order may come to rest on an odd price
     env = core.BatchedEnv(n_books, 0, 0, tick_size, 1000, obs_words=abi.OBS_L2, max_orders=128, max_trades=1024, max_steps=128,
-                          max_queue=16, pages_smem=8, pages_total=32, price_granule=1)
+                          max_queue=16, pages_smem=pages[0], pages_total=pages[1], price_granule=1)
     env.replay(np.concatenate(streams), off)
     assert not env.env_errors().any()
     n_tr = 0

@@ -111,5 +111,5 @@ def test_markets_reject_builtin_agents():
     e.set_agents(workloads.c3_groups())
     with pytest.raises(ValueError):
         e.run_agents(1, 0)
-    with pytest.raises(RuntimeError, match="multiple of assets"):
+    with pytest.raises(RuntimeError, match="multiples of assets"):
         core.BatchedEnv(3, 0, 0, 1, 1000, assets=2, max_orders=256, max_trades=256, max_steps=8, max_queue=16)

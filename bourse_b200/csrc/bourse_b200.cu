@@ -342,7 +342,11 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     }
 #undef LAUNCH_APPLY
     CUDA_TRY(h, cudaGetLastError());
-    if (mode == MODE_ENV && h->recorded_host >= 0) h->recorded_host += n_steps;
+    // a launch recorded into a CUDA graph (bb_step_device inside a captured RL loop) will run any number of times:
+    // the host-side record count is unknown from here on and is re-read from the device when next needed
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(h->stream, &cap);
+    if (mode == MODE_ENV && h->recorded_host >= 0 && cap == cudaStreamCaptureStatusNone) h->recorded_host += n_steps;
     else h->recorded_host = -1;
     return BB_OK;
 }
@@ -818,6 +822,12 @@ int run_agents_impl(bb_handle* h, uint64_t seed, uint32_t n_steps, const ExtRows
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     for (auto& q : h->queue)
         if (!q.empty()) return fail(h, BB_EINVAL, "host-queued instructions pending: call bb_step first");
+    {   // k_sim stages its records without per-step capacity checks, so the count must be known on the host: no graph capture
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(h->stream, &cap);
+        if (cap != cudaStreamCaptureStatusNone)
+            return fail(h, BB_EINVAL, "agent launches cannot be captured into a CUDA graph (bb_step_device can)");
+    }
     // history capacity is validated up front so the kernel can stage records without per-step checks
     if (h->recorded_host < 0) {  // after a replay the number of emitted records is only known to the device
         CUDA_TRY(h, cudaMemcpy2DAsync(h->h_offsets, 8, h->blobs + offsetof(BookHdr, n_steps), h->blob_stride, 4, 1,

@@ -98,7 +98,11 @@ class VectorEnv:
     `ids[e, r]` is the order id row r created in env e, or `abi.NO_ID` (2^64 - 1) for cancel / modify / no-op rows
     (step_sim_numpy.rs:256-267).  Semantics per env are exactly `submit_instructions` + `step`: ids in row order, the
     step's queue shuffled with the env's own Xoroshiro stream, event i at `t + i`.  A NEW row with an off-tick limit
-    price creates nothing (the reference raises ValueError there); the env is flagged and `check_errors` raises."""
+    price creates nothing (the reference raises ValueError there); the env is flagged and `check_errors` raises.
+
+    Without background agents a step is ONE kernel launch on the env's stream (`env.set_stream(...)`) with no host
+    synchronisation, so a loop of policy + `step` can be captured into a CUDA graph and replayed (tests/test_gpu_gym.py);
+    steps that include the built-in agents refuse capture (their history staging is validated on the host)."""
 
     def __init__(self, n_envs: int, rows_per_env: int, seed: int, start_time: int, tick_size: int, step_size: int,
                  trading: bool = True, *, level_1: bool = False, agents=None, agent_seed: int = 0, **kw):

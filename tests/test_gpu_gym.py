@@ -210,3 +210,57 @@ def test_background_agent_rows_refuse_modify_and_unknown_ids():
     v.step(gym.pack_actions(np.array([[abi.OP_NOOP, abi.OP_NOOP], [abi.OP_CANCEL, abi.OP_NOOP]], np.uint32), order_id=100000))
     assert v.env.env_errors()[1] == 0x10
     v.close()
+
+
+def test_step_device_inside_a_cuda_graph(oracle):
+    """The vector step is one kernel launch on the caller's stream, so an RL loop can capture it (with its policy) into a
+    CUDA graph: a captured step replayed K times equals K eager steps on a twin env fed the same action tensor."""
+    import torch
+
+    n_envs, rows, k = 64, 3, 5
+    kw = dict(max_orders=512, max_trades=1024, max_steps=32)
+    a, b = gym.VectorEnv(n_envs, rows, 2, 0, 1, 1000, **kw), gym.VectorEnv(n_envs, rows, 2, 0, 1, 1000, **kw)
+    stream = torch.cuda.Stream()
+    a.env.set_stream(stream.cuda_stream)
+    a.reset(); b.reset()
+    acts = torch.zeros((n_envs, rows, 8), dtype=torch.int32, device="cuda")
+    rng = np.random.default_rng(0)
+
+    def fill():
+        blk = gym.pack_actions(np.full((n_envs, rows), abi.OP_NEW, np.uint32), bid=rng.random((n_envs, rows)) < 0.5,
+                               vol=rng.integers(1, 20, (n_envs, rows)), price=rng.integers(45, 56, (n_envs, rows)), trader=3)
+        acts.copy_(torch.from_numpy(blk.view(np.int32).reshape(n_envs, rows, 8)))
+        torch.cuda.synchronize()
+
+    fill()
+    with torch.cuda.stream(stream):
+        a.step(acts)                       # warm-up outside the capture (attribute / occupancy queries happen here)
+    stream.synchronize()
+    b.step(acts); b.env.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        a.step(acts)
+    for _ in range(k):                     # (the capture itself does not execute the step)
+        fill()
+        g.replay()
+        torch.cuda.synchronize()
+        b.step(acts); b.env.synchronize()
+        assert np.array_equal(a.obs.numpy(), b.obs.numpy()) and np.array_equal(a.ids.numpy(), b.ids.numpy())
+    assert a.env.n_steps(0) == b.env.n_steps(0) == k + 1
+    for e in (0, 17, 63):
+        assert a.env.get_trades(e) == b.env.get_trades(e) and np.array_equal(a.env.history(e), b.env.history(e))
+    assert len(a.env.get_trades(0)) > 0
+    # agent launches stage records without per-step capacity checks and refuse to be captured
+    from bourse_b200 import workloads
+    c = gym.VectorEnv(4, 2, 0, 0, 1, 1_000_000, agents=workloads.c3_groups(), agent_seed=1, max_orders=1024, max_trades=1024, max_steps=8, max_queue=128)
+    c.env.set_stream(stream.cuda_stream)
+    c.reset()
+    small = torch.zeros((4, 2, 8), dtype=torch.int32, device="cuda")
+    with torch.cuda.stream(stream):
+        c.step(small)
+    stream.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with pytest.raises(ValueError, match="cannot be captured"):
+        with torch.cuda.graph(g2, stream=stream):
+            c.step(small)
+    a.close(); b.close()

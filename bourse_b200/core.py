@@ -79,6 +79,7 @@ class BatchedEnv:
             cfg.price_granule = 1
         self._h = C.c_void_p()
         self.n_envs, self.obs_words, self.tick_size = n_envs, obs_words, tick_size
+        self.max_orders, self.max_trades, self.max_steps = max_orders, max_trades, max_steps
         rc = self._lib.bb_create(C.byref(cfg), C.byref(self._h))
         if rc != abi.BB_OK:
             msg = self._lib.bb_last_error(None)
@@ -100,6 +101,23 @@ class BatchedEnv:
         _check(self._lib, self._h, rc)
 
     # ------------------------------------------------------------------ control
+    def reserve(self, max_orders: int = 0, max_trades: int = 0, max_steps: int = 0):
+        """Grow the per-env order table / trade log / history to at least these capacities (bb_reserve); contents are kept."""
+        self._ck(self._lib.bb_reserve(self._h, max_orders, max_trades, max_steps))
+        self.max_orders, self.max_steps = max(self.max_orders, max_orders), max(self.max_steps, max_steps)
+        if self.max_trades:
+            self.max_trades = max(self.max_trades, max_trades)
+
+    def grow_if_needed(self, env: int = 0, headroom_orders: int = 0, headroom_steps: int = 0, headroom_trades: int = 0):
+        """Single-env convenience used by OrderBook / StepEnv: double a table once it is more than half full (plus the
+        given headroom), so that the classes grow without bound like the reference's Vecs."""
+        o, t, s = self.n_orders(env) + headroom_orders, self.n_trades(env) + headroom_trades, self.n_steps(env) + headroom_steps
+        want_o = 2 * self.max_orders if 2 * o > self.max_orders else 0
+        want_t = 2 * self.max_trades if self.max_trades and 2 * t > self.max_trades else 0
+        want_s = 2 * self.max_steps if 2 * s > self.max_steps else 0
+        if want_o or want_t or want_s:
+            self.reserve(max(want_o, 2 * o if want_o else 0), max(want_t, 4 * t if want_t else 0), max(want_s, 2 * s if want_s else 0))
+
     def reset(self): self._ck(self._lib.bb_reset(self._h))
     def synchronize(self): self._ck(self._lib.bb_synchronize(self._h))
     def set_stream(self, cuda_stream: int): self._ck(self._lib.bb_set_stream(self._h, C.c_void_p(cuda_stream)))
@@ -365,11 +383,15 @@ class OrderBook:
         self._t = start_time
         self._trading = bool(trading)
         self._one = np.zeros(1, dtype=abi.INSTR_DTYPE)
+        self._calls = 0
 
     def _apply(self, op_flags, order_id=0, price=0, vol=0, trader=0):
         x = self._one
         x["t"], x["op_flags"], x["order_id"] = self._t, op_flags, order_id
         x["price"], x["vol"], x["trader"] = price, vol, trader
+        self._calls += 1
+        if self._calls & 63 == 0:      # the reference's order table and trade log grow without bound: so do these
+            self._env.grow_if_needed(0, headroom_orders=64, headroom_trades=self._env.n_orders(0) + 128)
         self._env.replay(x)
 
     def set_time(self, t: int): self._t = t; self._env.set_time(0, t)
@@ -406,6 +428,10 @@ class OrderBook:
     def replay(self, instrs: np.ndarray) -> np.ndarray:
         """Apply a packed instruction stream (config C2); returns the [n_emit, 45] records of F_EMIT rows."""
         first = self._env.n_steps(0)
+        n_new = int(((np.asarray(instrs["op_flags"]) & 0xFF) == abi.OP_NEW).sum()) if len(instrs) else 0
+        n_emit = int(((np.asarray(instrs["op_flags"]) & abi.F_EMIT) != 0).sum()) if len(instrs) else 0
+        # every trade either fills a passive order completely or is the last fill of its aggressor: <= 2 per instruction
+        self._env.grow_if_needed(0, headroom_orders=n_new, headroom_steps=n_emit, headroom_trades=2 * len(instrs))
         self._env.replay(instrs)
         if len(instrs):
             self._t = int(instrs["t"][-1])
@@ -432,9 +458,12 @@ class _StepEnvBase:
                                                        ("price", np.uint32), ("order_id", np.uint64), ("flags", np.uint32), ("out", np.uint64))}
         self._row_ptr = {k: abi.ptr(v) for k, v in self._row.items()}
         self._done = C.c_uint64()
+        self._n_issued = 0   # upper bound of the order ids handed out (exact unless a submission raised)
 
     def _submit1(self, action, side=0, vol=0, trader=0, price=0, order_id=0, flags=abi.F_HAS_PRICE | abi.F_HAS_VOL) -> int:
         r, p, e = self._row, self._row_ptr, self._env
+        if action == abi.ACT_NEW:
+            self._ensure_orders(1)
         r["action"][0], r["side"][0], r["vol"][0], r["trader"][0] = action, side, vol, trader
         r["price"][0], r["order_id"][0], r["flags"][0] = price, order_id, flags
         e._ck(e._lib.bb_submit(e._h, 1, None, p["action"], p["side"], p["vol"], p["trader"], p["price"], p["order_id"], p["flags"],
@@ -443,7 +472,31 @@ class _StepEnvBase:
 
     def enable_trading(self): self._env.set_trading(True, 0)
     def disable_trading(self): self._env.set_trading(False, 0)
-    def step(self): self._env.step(1)
+    # The reference's order table, trade log and per-step records are Vecs that grow without bound (orderbook.rs:113-115,
+    # data.rs:9-57); the tables here are preallocated, so the single-env classes reserve ahead (bb_reserve):
+    # orders at submission (ids are handed out on the host), history and trade log before every step.
+    def _ensure_orders(self, n_more: int):
+        e = self._env
+        need = self._n_issued + n_more         # ids handed out so far (tracked from the ids the submissions return)
+        if need > e.max_orders:
+            need = e.n_orders(0) + n_more      # exact count from the library before paying for a reallocation
+            if need > e.max_orders:
+                e.reserve(max_orders=max(2 * e.max_orders, 2 * need))
+        self._n_issued += n_more
+
+    def step(self):
+        e = self._env
+        self._n_steps = getattr(self, "_n_steps", 0) + 1
+        if self._n_steps > e.max_steps:
+            e.reserve(max_steps=2 * e.max_steps)
+        if e.max_trades:
+            # a trade either fills a passive order completely or is the last fill of its aggressor, so one step adds
+            # at most (orders in existence) trades
+            need = e.n_trades(0) + e.n_orders(0) + 64
+            if need > e.max_trades:
+                e.reserve(max_trades=max(2 * e.max_trades, 2 * need))
+        e.step(1)
+
     def get_orders(self): return self._env.get_orders(0)
     def get_trades(self): return self._env.get_trades(0)
     def order_status(self, order_id: int) -> int: return self._env.order_status(order_id, 0)
@@ -513,6 +566,7 @@ class StepEnvNumpy(_StepEnvBase):
     def submit_limit_orders(self, orders):
         sides, vols, traders, prices = orders
         n = len(sides)
+        self._ensure_orders(n)
         return self._env.submit(np.full(n, abi.ACT_NEW, np.uint32), np.asarray(sides), vols, traders, prices)
 
     def submit_cancellations(self, order_ids):
@@ -524,6 +578,7 @@ class StepEnvNumpy(_StepEnvBase):
         action = np.asarray(action, dtype=np.uint32)
         # the reference treats every code other than 1 / 2 as a no-op (step_sim_numpy.rs:254-268)
         action = np.where((action == 1) | (action == 2), action, 0).astype(np.uint32)
+        self._ensure_orders(int((action == 1).sum()))
         return self._env.submit(action, np.asarray(sides), vols, traders, prices, order_ids)
 
     def level_1_data(self): return self._l2()[:9].copy()

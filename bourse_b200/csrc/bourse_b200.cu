@@ -781,6 +781,43 @@ int bb_memcpy(bb_handle* h, void* dst, const void* src, uint64_t bytes, int kind
     return BB_OK;
 }
 
+int bb_reserve(bb_handle* h, uint32_t max_orders, uint32_t max_trades, uint32_t max_steps) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    const size_t ne = h->cfg.n_envs;
+    // one slab at a time: allocate the larger one, copy every env's rows across (2-D copy, old pitch -> new pitch), swap
+    auto grow = [&](void** slab, size_t old_row, size_t new_row) -> int {
+        void* fresh = nullptr;
+        CUDA_TRY(h, cudaMalloc(&fresh, ne * new_row));
+        if (*slab && old_row)
+            CUDA_TRY(h, cudaMemcpy2DAsync(fresh, new_row, *slab, old_row, old_row, ne, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(*slab);
+        *slab = fresh;
+        return BB_OK;
+    };
+    int rc;
+    if (max_orders > h->cfg.max_orders) {
+        if ((rc = grow((void**)&h->ord, (size_t)h->cfg.max_orders * sizeof(OrderRec), (size_t)max_orders * sizeof(OrderRec)))) return rc;
+        h->cfg.max_orders = max_orders;
+    }
+    if (max_trades > h->cfg.max_trades && h->cfg.max_trades) {  // (0 = the trade log is disabled for this handle)
+        if ((rc = grow((void**)&h->tr, (size_t)h->cfg.max_trades * sizeof(TradeRec), (size_t)max_trades * sizeof(TradeRec)))) return rc;
+        h->cfg.max_trades = max_trades;
+    }
+    if (max_steps > h->cfg.max_steps) {
+        const u32 padded = align_up(max_steps, 4);
+        const u64 stride = (u64)padded * h->cfg.obs_words;
+        if ((rc = grow((void**)&h->hist, h->hist_env_stride * 4, stride * 4))) return rc;
+        h->cfg.max_steps = max_steps;
+        h->max_steps_padded = padded;
+        h->hist_env_stride = stride;
+    }
+    return BB_OK;
+}
+
 int bb_set_agents(bb_handle* h, const bb_agent_group* groups, uint32_t n_groups) {
     return set_agents_impl(h, groups, nullptr, n_groups);
 }

@@ -168,6 +168,11 @@ int bb_abi_version(void);
 int bb_create(const bb_config* cfg, bb_handle** out);
 int bb_destroy(bb_handle* h);
 int bb_reset(bb_handle* h); /* back to the freshly created state (same config, same agents); asynchronous */
+/* Grow (never shrink) the per-env order table, trade log and history to at least these capacities, keeping their contents.
+ * The reference's Vec<OrderEntry> / Vec<Trade> / Level2DataRecords grow without bound (orderbook.rs:113-115, data.rs:9-57);
+ * a host that cannot size a run up front calls this when usage nears a capacity (the Python OrderBook / StepEnv /
+ * StepEnvNumpy classes do).  Synchronous; costs one device-to-device copy of the slab that grows. */
+int bb_reserve(bb_handle* h, uint32_t max_orders, uint32_t max_trades, uint32_t max_steps);
 const char* bb_last_error(const bb_handle* h /* may be NULL */);
 /* run on a caller-owned CUDA stream (cudaStream_t); NULL restores the handle's own stream */
 int bb_set_stream(bb_handle* h, void* cuda_stream);

@@ -93,3 +93,14 @@ def test_bench_gym_policy_never_names_an_unissued_id():
         cancels = op == abi.OP_CANCEL
         assert (blocks["order_id"][s][cancels] < np.broadcast_to(issued[:, None], op.shape)[cancels]).all()
         issued += (op == abi.OP_NEW).sum(axis=1)
+
+
+def test_data_processing_frames_match_the_reference_layout():
+    """src/bourse/data_processing.py:10-105: column names (incl. the reference's `arr time`), side / status mappings."""
+    from bourse_b200 import data_processing as dp
+    t = dp.trades_to_dataframe([(10, False, 60, 20, 4, 1), (20, True, 55, 10, 5, 2)])
+    assert list(t.columns) == ["time", "side", "price", "vol", "active_id", "passive_id"]
+    assert list(t["side"]) == ["ask", "bid"] and list(t["vol"]) == [20, 10]
+    o = dp.orders_to_dataframe([(True, 2, 0, 10, 0, 10, 50, 11, 0), (False, 1, 0, 2**64 - 1, 5, 20, 60, 12, 1)])
+    assert list(o.columns) == ["side", "status", "arr time", "end_time", "vol", "start_vol", "price", "trader_id", "order_id"]
+    assert list(o["side"]) == ["bid", "ask"] and list(o["status"]) == ["filled", "active"]

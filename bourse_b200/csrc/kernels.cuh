@@ -578,7 +578,8 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
     MomOut out;
     out.n = e.n;
     out.next_id = e.next_id;
-    out.err = err;
+    // the capacity / tick checks above are per lane (per trader): every lane must report them, lane 0 writes the header
+    out.err = __reduce_or_sync(BB_FULL, err);
     return out;
 }
 

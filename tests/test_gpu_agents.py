@@ -134,3 +134,28 @@ def test_noise_agents_on_empty_book_far_prices(core, oracle):
         st = [o[1] for o in env.get_orders(e)]
         assert st[:10] == [3] * 10 and st[10:] == [1] * 10
     assert ok == 4
+
+
+def test_live_list_overflow_is_flagged_on_every_env(core, oracle):
+    """A MomentumAgent whose limit orders never fill (one-sided books) outgrows the 254-entry live-order list.  The
+    overflow is detected per trader lane; every lane's bits must reach the env's error word (they used to be taken from
+    lane 0 only), so results never differ from the oracle silently.  Found by scripts/soak.py, seed 14177."""
+    M = (1000, 17, 1, 0.02, 10, 0.41, 6.35, 0.75, 1.82, 0.0, 0.98)
+    N = (2000, 15, 1, 0.385, 0.198, 0.315, 7, 0.66, 1.07)
+    n_envs, n_steps = 8, 60
+    e = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=16384, max_trades=32768, max_steps=64,
+                        max_queue=512, pages_smem=64, pages_total=64)
+    e.set_agents([core.momentum_group(*M), core.noise_group(*N)])
+    e.run_agents(n_steps, 5, sync=False)
+    with pytest.raises(MemoryError, match="0x80"):
+        e.synchronize(); e.stats(); e.level_2_data(); e.step(1)   # the next synchronous launch-check reports the flag
+    err = e.env_errors()
+    n_bad = 0
+    for env in range(n_envs):
+        o = oracle.StepEnvNumpy(0, 0, 1, 1_000_000)
+        o.set_groups([oracle.momentum_group(*M), oracle.noise_group(*N)])
+        o.run_agents(n_steps, 5, env_id=env, keyed=True)
+        same = np.array_equal(e.history(env)[:n_steps], o._history())
+        assert same or (err[env] & 0x80), env       # differs => flagged
+        n_bad += not same
+    assert n_bad > 0 and (err & 0x80).any()

@@ -10,6 +10,11 @@ sys.path.insert(0, ".")
 from bourse_b200 import abi, core, gym, market  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
+sys.path.insert(0, "tests")
+from bourse_b200 import workloads  # noqa: E402
+from tests.test_oracle_hypothesis import random_adversarial_stream  # noqa: E402
+
+MODES = ["single", "market", "ext", "replay", "replay"]
 budget, seed0 = float(sys.argv[1]), int(sys.argv[2]) if len(sys.argv) > 2 else 0
 only = [int(x) for x in sys.argv[3:]]   # optional: just these seeds
 t_end = time.time() + budget
@@ -42,7 +47,54 @@ while time.time() < t_end and (not only or rounds < len(only)):
         seed = only[rounds]
     rng = np.random.default_rng(seed)
     last_env = None
-    mode = ["single", "market", "ext"][int(rng.integers(3))]
+    mode = MODES[int(rng.integers(len(MODES)))]
+    if mode == "replay":
+        # immediate-mode streams (k_apply<REPLAY>) on every book geometry: C2-style streams with strict / flat / jittered
+        # time (equal-key collisions N1, backwards time) or the adversarial tiny-domain streams of the hypothesis tests
+        rounds += 1
+        seed += 1
+        geo = int(rng.integers(5))
+        tick = int(rng.integers(1, 3))
+        adversarial = rng.random() < 0.5
+        n_books = int(rng.integers(1, 40))
+        if adversarial:
+            streams = [random_adversarial_stream(rng, int(rng.integers(1, 150)), tick) for _ in range(n_books)]
+            kwr = [dict(pages_smem=8, pages_total=32), dict(pages_smem=32, pages_total=32), dict(pages_smem=64, pages_total=64),
+                   dict(pages_smem=3, pages_total=96), dict(pages_smem=40, pages_total=40)][geo]
+            kwr["price_granule"] = 1
+        else:
+            tm = ["strict", "flat", "jitter"][int(rng.integers(3))]
+            hw = int(rng.integers(8, 400))
+            dense_ok = tm == "strict" and hw <= 100
+            streams = [workloads.replay_stream(int(rng.integers(200, 3000)), int(rng.integers(1 << 30)), tick_size=tick, half_width=hw,
+                                               time_mode=tm, min_vol=int(rng.integers(0, 2))) for _ in range(n_books)]
+            kwr = [dict(pages_smem=4, pages_total=128), dict(pages_smem=64, pages_total=64), dict(pages_smem=100, pages_total=100),
+                   dict(pages_smem=16, pages_total=256),
+                   dict(price_window=((1000 - hw) * tick - 8, (1000 + hw) * tick + 8), live_cap=254) if dense_ok else dict(pages_smem=200, pages_total=200)][geo]
+        desc = f"seed {seed - 1} replay {'adversarial' if adversarial else 'c2-style'} tick {tick} {kwr} books {n_books}"
+        try:
+            off = np.zeros(n_books + 1, np.uint64); off[1:] = np.cumsum([len(x) for x in streams])
+            n_max = int(max(len(x) for x in streams))
+            e = core.BatchedEnv(n_books, 0, 0, tick, 1000, obs_words=abi.OBS_L2, max_orders=n_max + 8, max_trades=4 * n_max + 64,
+                                max_steps=n_max + 8, max_queue=16, **kwr)
+            last_env = e
+            try:
+                e.replay(np.concatenate(streams), off)
+            except MemoryError:
+                pass          # a flagged capacity (dense window slots, pages): checked per book below
+            err = e.env_errors()
+            for b in range(n_books):
+                if err[b]:
+                    assert not (int(err[b]) & ~0x1CF), hex(int(err[b]))
+                    continue
+                ob = orc.OrderBook(0, tick); obs = ob.replay(streams[b], obs_cap=len(streams[b]))
+                assert np.array_equal(e.history(b), obs) and e.get_orders(b) == ob.get_orders() and e.get_trades(b) == ob.get_trades(), b
+            if err.any():
+                capacity += 1
+        except Exception as ex:  # noqa: BLE001
+            fails += 1
+            print("FAIL", desc, "->", repr(ex)[:200], flush=True)
+        continue
     dense = rng.random() < 0.4
     kw = dict(price_window=(0, 256), live_cap=254) if dense else (dict() if rng.random() < 0.6 else dict(pages_smem=int(rng.integers(2, 12)), pages_total=64))
     gs = rand_groups(rng, dense)

@@ -202,7 +202,8 @@ int bb_step(bb_handle* h, uint32_t n_steps);
  * dropped, as when create_order returns PriceError, and flags the env with BB_ERR_PRICE (the next synchronous call
  * reports BB_EPRICE).  d_obs_out (device, [n_envs][obs_words], may be NULL) receives every env's end-of-step
  * observation record from the same launch — what StepEnvNumpy.level_1_data / level_2_data would return next.
- * Asynchronous on the handle's stream. */
+ * Asynchronous on the handle's stream: one kernel launch and no host synchronisation, so the call may be recorded into a
+ * CUDA graph together with the caller's own kernels (stream capture on the stream given to bb_set_stream). */
 int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env_offsets, uint64_t n_rows, uint64_t* d_out_ids,
                    uint32_t* d_obs_out);
 /* bb_level2 / bb_level1 into DEVICE memory: d_out[n_envs][45] / d_out[n_envs][9].  Asynchronous. */

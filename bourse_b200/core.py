@@ -118,6 +118,10 @@ class BatchedEnv:
         if want_o or want_t or want_s:
             self.reserve(max(want_o, 2 * o if want_o else 0), max(want_t, 4 * t if want_t else 0), max(want_s, 2 * s if want_s else 0))
 
+    def clear_history(self):
+        """Restart every env's per-step record history at 0 (bb_clear_history); books and logs are untouched."""
+        self._ck(self._lib.bb_clear_history(self._h))
+
     def reset(self): self._ck(self._lib.bb_reset(self._h))
     def synchronize(self): self._ck(self._lib.bb_synchronize(self._h))
     def set_stream(self, cuda_stream: int): self._ck(self._lib.bb_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -781,6 +781,15 @@ int bb_memcpy(bb_handle* h, void* dst, const void* src, uint64_t bytes, int kind
     return BB_OK;
 }
 
+int bb_clear_history(bb_handle* h) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    // every env's record count back to zero (one strided memset over the book headers); the books are untouched
+    CUDA_TRY(h, cudaMemset2DAsync(h->blobs + offsetof(BookHdr, n_steps), h->blob_stride, 0, 4, h->cfg.n_envs, h->stream));
+    h->recorded_host = 0;
+    return BB_OK;
+}
+
 int bb_reserve(bb_handle* h, uint32_t max_orders, uint32_t max_trades, uint32_t max_steps) {
     CHECK_H(h);
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));

@@ -102,7 +102,9 @@ class VectorEnv:
 
     Without background agents a step is ONE kernel launch on the env's stream (`env.set_stream(...)`) with no host
     synchronisation, so a loop of policy + `step` can be captured into a CUDA graph and replayed (tests/test_gpu_gym.py);
-    steps that include the built-in agents refuse capture (their history staging is validated on the host)."""
+    steps that include the built-in agents refuse capture (their history staging is validated on the host).  The library's
+    per-step history is a scratch ring for this class: `step` clears it (`bb_clear_history`) whenever `max_steps` records
+    have accumulated; a caller replaying a captured step must do the same every `max_steps` replays."""
 
     def __init__(self, n_envs: int, rows_per_env: int, seed: int, start_time: int, tick_size: int, step_size: int,
                  trading: bool = True, *, level_1: bool = False, agents=None, agent_seed: int = 0, **kw):
@@ -115,6 +117,7 @@ class VectorEnv:
         if rows_per_env > kw["max_queue"]:
             raise ValueError("rows_per_env exceeds max_queue")
         self._agents, self._agent_seed = agents, agent_seed
+        self._n_steps = 0
         self.n_envs, self.rows = n_envs, rows_per_env
         self.env = BatchedEnv(n_envs, seed, start_time, tick_size, step_size, trading, obs_words=abi.OBS_L1 if level_1 else abi.OBS_L2, **kw)
         self.obs_words = abi.OBS_L1 if level_1 else abi.OBS_L2
@@ -136,6 +139,7 @@ class VectorEnv:
         return self.obs
 
     def reset(self) -> DeviceArray:
+        self._n_steps = 0
         self.env.reset()   # (the agent population survives a reset; its state is cleared with the books)
         return self._observe()
 
@@ -148,6 +152,11 @@ class VectorEnv:
                 raise ValueError(f"actions must have shape ({self.n_envs}, {self.rows})")
             self._actions.copy_from_host(a)
             ptr = self._actions.ptr
+        # an open-ended loop consumes each observation as it is produced: the library's per-step history is a scratch ring here
+        self._n_steps += 1
+        if self._n_steps > self.env.max_steps:
+            self.env.clear_history()
+            self._n_steps = 1
         # one launch: (background agents,) ids, Env::step and the observation records written straight into self.obs
         if self._agents:
             self.env.run_agents_with_rows(self._agent_seed, ptr, self._offsets.ptr, self.n_envs * self.rows, self.ids.ptr, self.obs.ptr)

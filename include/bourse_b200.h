@@ -173,6 +173,10 @@ int bb_reset(bb_handle* h); /* back to the freshly created state (same config, s
  * a host that cannot size a run up front calls this when usage nears a capacity (the Python OrderBook / StepEnv /
  * StepEnvNumpy classes do).  Synchronous; costs one device-to-device copy of the slab that grows. */
 int bb_reserve(bb_handle* h, uint32_t max_orders, uint32_t max_trades, uint32_t max_steps);
+/* Forget the per-step records (Level2DataRecords, data.rs:9-57) of every env: the history restarts at record 0, the books,
+ * order tables and trade logs are untouched.  For open-ended loops that consume each step's observation as it is produced
+ * (bb_step_device / bb_run_agents_with_rows) and would otherwise run into max_steps.  Asynchronous. */
+int bb_clear_history(bb_handle* h);
 const char* bb_last_error(const bb_handle* h /* may be NULL */);
 /* run on a caller-owned CUDA stream (cudaStream_t); NULL restores the handle's own stream */
 int bb_set_stream(bb_handle* h, void* cuda_stream);

@@ -264,3 +264,35 @@ def test_step_device_inside_a_cuda_graph(oracle):
         with torch.cuda.graph(g2, stream=stream):
             c.step(small)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("bg", [False, True], ids=["rows_only", "background_agents"])
+def test_vector_env_runs_past_max_steps(oracle, bg):
+    """An open-ended loop: the per-step history is a scratch ring for VectorEnv (bb_clear_history when it is full), so the
+    loop runs past max_steps and keeps matching the oracle."""
+    from bourse_b200 import workloads
+    groups = workloads.c3_groups() if bg else None
+    n_envs, rows, seed = 6, 2, 13
+    v = gym.VectorEnv(n_envs, rows, 4, 0, 1, 1_000_000, agents=groups, agent_seed=seed, max_orders=8192, max_trades=8192, max_steps=8,
+                      max_queue=128)
+    orcs = [oracle.StepEnv(4 + e, 0, 1, 1_000_000) for e in range(n_envs)]
+    if bg:
+        for o in orcs:
+            o.set_groups(groups)
+    v.reset()
+    rng = np.random.default_rng(1)
+    for s in range(30):
+        bid = rng.random((n_envs, rows)) < 0.5
+        vol = rng.integers(1, 20, (n_envs, rows)); price = 2 * rng.integers(45, 56, (n_envs, rows))
+        obs, _ = v.step(gym.pack_actions(np.full((n_envs, rows), abi.OP_NEW, np.uint32), bid=bid, vol=vol, price=price, trader=9))
+        obs = obs.numpy()
+        for e, o in enumerate(orcs):
+            if bg:
+                o.agents_update(seed, e)
+            for r in range(rows):
+                o.place_order(bool(bid[e, r]), int(vol[e, r]), 9, int(price[e, r]))
+            o.step_keyed(seed, e) if bg else o.step()
+            assert np.array_equal(obs[e], o.level_2_data_array()), (s, e)
+    v.check_errors()
+    assert v.env.get_trades(0) == orcs[0].get_trades() and v.env.n_steps(0) <= 8
+    v.close()

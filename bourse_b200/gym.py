@@ -111,7 +111,9 @@ class VectorEnv:
         """`agents`: optional background population (a list of `core.random_group` / `momentum_group` / `noise_group`
         records).  With it every `step` is `{ agents.update(env); the action rows; env.step() }` in one launch
         (bb_run_agents_with_rows): the rows join the agents' instructions in the step's one shuffled queue (Philox key
-        `agent_seed`).  Action rows may then be NEW, CANCEL or no-op (MODIFY is refused)."""
+        `agent_seed`).  Action rows may then be NEW, CANCEL or no-op (MODIFY is refused).  At one step per launch the
+        general engine (no `price_window`) is the faster choice here: 92 us against 117 us per 4096-env step on the dense
+        engine, whose per-launch agent-table rebuild only pays off inside the persistent multi-step kernel."""
         n_bg = sum(int(g["n_agents"]) for g in agents) if agents else 0
         kw.setdefault("max_queue", max(rows_per_env + 2 * n_bg, 16))
         if rows_per_env > kw["max_queue"]:

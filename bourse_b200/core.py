@@ -122,6 +122,10 @@ class BatchedEnv:
         """Restart every env's per-step record history at 0 (bb_clear_history); books and logs are untouched."""
         self._ck(self._lib.bb_clear_history(self._h))
 
+    def clear_errors(self):
+        """Zero every env's sticky error word (bb_clear_errors)."""
+        self._ck(self._lib.bb_clear_errors(self._h))
+
     def reset(self): self._ck(self._lib.bb_reset(self._h))
     def synchronize(self): self._ck(self._lib.bb_synchronize(self._h))
     def set_stream(self, cuda_stream: int): self._ck(self._lib.bb_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -861,7 +861,9 @@ template <class G> __device__ __forceinline__ void book_from_header(const G& g, 
     b.bq_bid = lds(b.sb + HDR_BESTQ + 4u);
     b.flags = (lds(b.sb + HDR_TRADING) ? FL_TRADING : 0u) | (lds(b.sb + HDR_HASBEST) ? FL_HAS_ASK : 0u) |
               (lds(b.sb + HDR_HASBEST + 4u) ? FL_HAS_BID : 0u);
-    b.err = lds(b.sb + HDR_ERR);
+    // Book::err collects the errors raised DURING THIS LAUNCH only (they are what the launch reports through err_flag);
+    // the header word they are OR-ed into at write-back is the env's sticky record (bb_env_errors / bb_clear_errors)
+    b.err = 0u;
     b.d_instr = b.d_trans = b.d_volume = 0;
 }
 
@@ -885,7 +887,7 @@ template <class G> __device__ __forceinline__ void book_to_header(const G& g, co
     sts(b.sb + HDR_TRADING, (b.flags & FL_TRADING) ? 1u : 0u);
     sts(b.sb + HDR_HASBEST, (b.flags & FL_HAS_ASK) ? 1u : 0u);
     sts(b.sb + HDR_HASBEST + 4u, (b.flags & FL_HAS_BID) ? 1u : 0u);
-    sts(b.sb + HDR_ERR, b.err);
+    sts(b.sb + HDR_ERR, lds(b.sb + HDR_ERR) | b.err);
     sts64(b.sb + HDR_NINSTR, lds64(b.sb + HDR_NINSTR) + b.d_instr);
     sts64(b.sb + HDR_NTRANS, lds64(b.sb + HDR_NTRANS) + b.d_trans);
     sts64(b.sb + HDR_VOLUME, lds64(b.sb + HDR_VOLUME) + b.d_volume);

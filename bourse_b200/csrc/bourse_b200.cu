@@ -129,7 +129,7 @@ u32 xoroshiro_range_h(u64& s0, u64& s1, u32 range) {
         const u64 t = s1 ^ s0;
         s0 = rotl64_h(s0, 24) ^ t ^ (t << 16);
         s1 = rotl64_h(t, 37);
-        const u32 v = (u32)(r >> 32);
+        const u32 v = (u32)r;  // next_u32 = low half of next_u64 (rand_xoshiro 0.6.0)
         const u32 lo = v * range;
         if (lo <= zone) return (u32)(((u64)v * range) >> 32);
     }
@@ -688,6 +688,8 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
         }
         total += g.n_agents;
     }
+    // every check happens before any allocation is touched: a refused population leaves the previous one intact
+    if (h->eng >= ENG_DENSE && total > 2046) return fail(h, BB_EINVAL, "the dense engine supports at most 2046 agents per env");
     // agent state is (re)allocated only when the population's shape changes: cudaFree / cudaMalloc synchronise the
     // whole device and cost ~100 ms next to tens of GB of slabs, which used to dominate the end-to-end pass
     const size_t ne = h->cfg.n_envs;
@@ -695,10 +697,13 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(h->rslot); h->rslot = nullptr;
         cudaFree(h->mom); h->mom = nullptr;
+        // from here until both tables exist the handle has NO agents: a failed allocation must not leave the old groups
+        // pointing at freed (or wrongly sized) state
+        h->groups.clear(); h->group_asset.clear();
+        h->agents_per_env = h->mom_groups = h->chip_agents = 0;
         if (total) CUDA_TRY(h, cudaMalloc(&h->rslot, ne * total * 4));
         if (mom) CUDA_TRY(h, cudaMalloc(&h->mom, ne * mom * sizeof(MomState)));
     }
-    if (h->eng >= ENG_DENSE && total > 2046) return fail(h, BB_EINVAL, "the dense engine supports at most 2046 agents per env");
     h->groups.assign(groups, groups + n_groups);
     h->group_asset.clear();
     if (asset) h->group_asset.assign(asset, asset + n_groups);
@@ -1345,6 +1350,14 @@ int bb_env_errors(bb_handle* h, uint32_t* out) {
     CUDA_TRY(h, cudaMemcpy2DAsync(out, 4, h->blobs + offsetof(BookHdr, err), h->blob_stride, 4, h->cfg.n_envs,
                                   cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_clear_errors(bb_handle* h) {
+    CHECK_H(h);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemset2DAsync(h->blobs + offsetof(BookHdr, err), h->blob_stride, 0, 4, h->cfg.n_envs, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
     return BB_OK;
 }
 

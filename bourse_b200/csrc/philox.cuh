@@ -46,7 +46,7 @@ __device__ __forceinline__ uint64_t xoroshiro_next(uint64_t& s0, uint64_t& s1) {
 __device__ __forceinline__ uint32_t xoroshiro_range(uint64_t& s0, uint64_t& s1, uint32_t range) {
     const uint32_t zone = (range << __clz(range)) - 1u;
     for (;;) {
-        const uint32_t v = (uint32_t)(xoroshiro_next(s0, s1) >> 32);
+        const uint32_t v = (uint32_t)xoroshiro_next(s0, s1);  // next_u32 = low half (rand_xoshiro 0.6.0 `next_u64() as u32`)
         const uint32_t lo = v * range;
         if (lo <= zone) return __umulhi(v, range);
     }

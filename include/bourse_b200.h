@@ -285,7 +285,11 @@ int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* stat
 int bb_time(bb_handle* h, uint32_t env, uint64_t* t);
 int bb_set_time(bb_handle* h, uint32_t env, uint64_t t);
 int bb_set_trading(bb_handle* h, uint32_t env /* or BB_ALL_ENVS */, int on);
+/* Per-env STICKY error words (BB_ERR_* bits raised by any call since creation / bb_reset / bb_clear_errors).  A call reports
+ * (through its return code) only the errors raised by that call: after a refused instruction — e.g. a cancel of an unknown
+ * id, where the reference panics before mutating anything (orderbook.rs:642) — the handle stays usable. */
 int bb_env_errors(bb_handle* h, uint32_t* out /* [n_envs] */);
+int bb_clear_errors(bb_handle* h); /* zero every env's sticky error word; asynchronous */
 int bb_stats(bb_handle* h, bb_stats_t* out);
 /* Replaces `impl TryFrom<OrderBookState> for OrderBook` (orderbook.rs:891-918, the load half of the JSON
  * snapshot): overwrite env's book with the given order table and trade log, then rebuild both sides by

@@ -123,6 +123,7 @@ def lib() -> C.CDLL:
     sig("orc_bench_env_rows", dbl, u32, u32, u64, u32, vp, u32, u32, u64, u32, u64, vp)
     sig("orc_philox", None, u32, u32, u32, u32, u32, u32, vp)
     sig("orc_xoroshiro", None, u64, u32, vp)
+    sig("orc_xoroshiro_state", None, u64, u64, u32, vp, vp, vp, u32, vp)
     sig("orc_shuffle_perm", None, u64, u32, vp)
     sig("orc_round_price", u32, dbl, dbl, i32)
     _lib = L

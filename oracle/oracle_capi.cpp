@@ -508,6 +508,19 @@ void orc_xoroshiro(uint64_t seed, uint32_t n, uint64_t* out) {
     Xoroshiro128StarStar r = Xoroshiro128StarStar::seed_from_u64(seed);
     for (uint32_t i = 0; i < n; ++i) out[i] = r.next_u64();
 }
+// the generator from an explicit state (rand_xoshiro's from_seed): u64 outputs and the u32 / f32 / range draws derived from them
+void orc_xoroshiro_state(uint64_t s0, uint64_t s1, uint32_t n, uint64_t* out64, uint32_t* out32, float* outf, uint32_t range,
+                         uint32_t* out_range) {
+    Xoroshiro128StarStar a, b, c, d;
+    a.s0 = b.s0 = c.s0 = d.s0 = s0;
+    a.s1 = b.s1 = c.s1 = d.s1 = s1;
+    for (uint32_t i = 0; i < n; ++i) {
+        out64[i] = a.next_u64();
+        out32[i] = b.next_u32();
+        outf[i] = gen_f32(c);
+        out_range[i] = gen_range_u32(d, 0, range);
+    }
+}
 void orc_shuffle_perm(uint64_t seed, uint32_t n, uint32_t* out) {
     Xoroshiro128StarStar r = Xoroshiro128StarStar::seed_from_u64(seed);
     std::vector<uint32_t> v(n);

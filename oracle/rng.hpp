@@ -60,8 +60,11 @@ struct Xoroshiro128StarStar {
         s1 = rotl64(t, 37);
         return r;
     }
-    // rand_xoshiro takes the HIGH half for next_u32 (the low bits are the weak ones)
-    uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    // rand_xoshiro 0.6.0 xoroshiro128starstar.rs: `fn next_u32(&mut self) -> u32 { self.next_u64() as u32 }` — the LOW
+    // half (the ** scrambler has no weak low bits; only the `+` variants take `>> 32`).  Recalled from the crate source,
+    // which is not available offline: the generator itself is pinned on the crate's own known-answer vector
+    // (tests/test_oracle_rng.py::test_xoroshiro128starstar_public_vector), this truncation is NOT pinned.
+    uint32_t next_u32() { return (uint32_t)next_u64(); }
 };
 
 // rand 0.8.5 `Standard` floats: 24 / 53 random mantissa bits scaled into [0, 1)

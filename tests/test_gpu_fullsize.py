@@ -49,16 +49,27 @@ def _check_book_conservation(env, e, final_obs):
     return int(t["vol"].astype(np.uint64).sum()), len(t["vol"])
 
 
-def test_c3_full_size(core, oracle):
-    """Config C3: 4096 envs x (50+50) RandomAgents x 1000 env-steps, level-1 observations."""
+# bench.py's headline line prints this checksum (`l1_checksums`) for the same config and seed: FNV-1a over every env's final
+# level-1 record.  The test below checks the run that produces it against the oracle, on BOTH engines.
+C3_L1_CHECKSUM = {}
+
+
+@pytest.mark.parametrize("engine_kw", [dict(price_window=(20, 180), live_cap=128), dict()], ids=["dense_bench_config", "paged"])
+def test_c3_full_size(core, oracle, engine_kw):
+    """Config C3: 4096 envs x (50+50) RandomAgents x 1000 env-steps, level-1 observations.  `dense_bench_config` is
+    exactly the kernel / configuration pair bench.py times (k_sim<DENSE,0,0>, price_window=(20,180), live_cap=128)."""
     n_envs, n_steps, seed = 4096, 1000, 101
     groups = workloads.c3_groups()
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1, max_orders=65536, max_trades=65536,
-                          max_steps=n_steps, max_queue=128)
+                          max_steps=n_steps, max_queue=128, **engine_kw)
     env.set_agents(groups)
     env.run_agents(n_steps, seed)
     assert not env.env_errors().any()
     st = env.stats()
+    C3_L1_CHECKSUM[bool(engine_kw)] = st["l1_checksum"]
+    if len(C3_L1_CHECKSUM) == 2:   # both engines end every one of the 4096 books in the same state
+        assert C3_L1_CHECKSUM[True] == C3_L1_CHECKSUM[False]
+    print("C3 l1_checksum", st["l1_checksum"])
     hist = env.history_all(n_steps)
     assert st["env_steps"] == n_envs * n_steps and st["error_envs"] == 0
     # checksum of checksums: three independent read-back paths agree

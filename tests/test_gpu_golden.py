@@ -25,6 +25,37 @@ def test_bad_order_id_raises(core):
         env.step()
 
 
+def test_book_stays_usable_after_a_refused_instruction(core, oracle):
+    """The reference mutates nothing before it panics on an unknown id (orderbook.rs:642), so a caller that catches the
+    panic keeps a working book.  Here: the error is reported by the call that raised it and by no later call, the env's
+    sticky word (bb_env_errors) remembers it until bb_clear_errors, and results stay identical to an oracle book that
+    never saw the bad instruction."""
+    ob, ref = core.OrderBook(0, 1), oracle.OrderBook(0, 1)
+    for b in (ob, ref):
+        b.set_time(1); b.place_order(True, 10, 0, price=50)
+    with pytest.raises(core.PanicException):
+        ob.cancel_order(99)
+    for b in (ob, ref):   # every later call works and reports nothing
+        b.set_time(2); b.place_order(False, 4, 1, price=50)
+        b.set_time(3); b.cancel_order(0)
+        b.set_time(4); b.place_order(False, 6, 2, price=60)
+    assert ob.get_orders() == ref.get_orders() and ob.get_trades() == ref.get_trades()
+    assert ob.bid_ask() == ref.bid_ask()
+    assert int(ob._env.env_errors()[0]) & 0x10          # sticky record of the refused id ...
+    ob._env.clear_errors()
+    assert int(ob._env.env_errors()[0]) == 0            # ... until cleared
+    # Env mode: the step that carried the bad cancel raises, the next steps do not
+    env, renv = core.StepEnv(1, 0, 1, 100), oracle.StepEnv(1, 0, 1, 100)
+    env.cancel_order(3)
+    with pytest.raises(core.PanicException):
+        env.step()
+    renv.step()
+    for e in (env, renv):
+        e.place_order(True, 5, 0, price=10); e.step()
+        e.place_order(False, 5, 1, price=10); e.step()
+    assert env.get_trades() == renv.get_trades() and env.get_orders() == renv.get_orders()
+
+
 def test_python_runner_and_agents(core):
     """tests/test_step_sim/test_env.py:118-145, test_numpy_api.py:85-120, test_agents.py:6-31"""
     import bourse_b200

@@ -572,8 +572,14 @@ def run_gpu_other(args):
         books_per_sm = -(-n_envs // 148)
         books_per_sm = 1 if books_per_sm <= 1 else 2 if books_per_sm <= 2 else 4 * (-(-books_per_sm // 4))
         c5_pages = args.pages_smem if args.pages_smem != 10 else max(10, min(192, (227 * 1024 // books_per_sm - 8192) // 512))
+        if args.engine == "deep":
+            # deep-book engine (csrc/deep.cuh): one CTA per book; window = every price the stream can rest at (10000 +- 2048,
+            # rounded out to 32-level words), 98304 queue chunks of 31 entries per book
+            eng_kw = dict(price_window=(7936, 12160), deep_chunks=98304)
+        else:
+            eng_kw = dict(pages_smem=c5_pages, pages_total=192)
         env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=1_800_000,
-                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, pages_smem=c5_pages, pages_total=192)
+                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, **eng_kw)
         env.set_stream(stream.cuda_stream)
         torch.cuda.synchronize()
         pre_stats = None
@@ -593,7 +599,8 @@ def run_gpu_other(args):
         ext = n_envs * n_steps * per_step
         name = (f"C5 shard: {per_gpu} books/GPU x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 "
                 "events per book (15% cancel, 15% modify, 60% limit within +-32 ticks, 10% market), level-2 record per step, "
-                f"replayed from device memory; paged engine, {c5_pages} of 192 price pages per book resident in shared memory")
+                "replayed from device memory; " + ("deep-book engine (one CTA per book: fetch / match / retire warps, chunked array queues)"
+                                                   if "deep_chunks" in eng_kw else f"paged engine, {c5_pages} of 192 price pages per book resident in shared memory"))
     barrier()
     ms = [a.elapsed_time(b) for a, b in ev]
     stats = env.stats()
@@ -633,7 +640,7 @@ def run_gpu_other(args):
             "env_steps_per_sec": agg["env_steps"] * args.steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
             "trades_per_pass": agg["trades"],
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim" if args.workload in ("c4", "market") else "k_apply",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim" if args.workload in ("c4", "market") else "k_deep" if args.engine == "deep" else "k_apply",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             **({"cpu_baseline": cpu} if cpu else {})}))
     if world > 1:
@@ -657,13 +664,13 @@ def main():
                     help="c5 / c2: 32-level price pages per book resident in shared memory (of 192 / 64); the default 10 means 'all of them'")
     ap.add_argument("--bg-agents", action="store_true", help="gym: the C3 background population trades in every env (bb_run_agents_with_rows)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--engine", default=None, choices=["dense", "paged"],
+    ap.add_argument("--engine", default=None, choices=["dense", "paged", "deep"],
                     help="default: dense for c3 / market (shallow books inside a known price window), paged for gym")
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "market", "gym"],
                     help="c3 = the headline line; the others are the secondary configs (market = the multi-asset example)")
     args = ap.parse_args()
     if args.engine is None:
-        args.engine = "paged" if args.workload == "gym" and not args.bg_agents else "dense"
+        args.engine = "paged" if args.workload == "gym" and not args.bg_agents else "deep" if args.workload == "c5" else "dense"
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

@@ -40,7 +40,7 @@ class Config(C.Structure):
                 ("trading", C.c_uint32), ("obs_words", C.c_uint32), ("max_orders", C.c_uint32),
                 ("max_trades", C.c_uint32), ("max_steps", C.c_uint32), ("max_queue", C.c_uint32),
                 ("pages_smem", C.c_uint32), ("pages_total", C.c_uint32), ("win_lo", C.c_uint32),
-                ("win_levels", C.c_uint32), ("live_cap", C.c_uint32), ("assets", C.c_uint32)]
+                ("win_levels", C.c_uint32), ("live_cap", C.c_uint32), ("assets", C.c_uint32), ("deep_chunks", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -53,6 +53,10 @@ class BatchedEnv:
     fastest for shallow books whose resting prices stay in [lo, hi) with at most `live_cap` (default 128, max 254)
     resting orders per book; leaving those limits flags an env error rather than producing different results.
 
+    `deep_chunks=N` (with `price_window`, up to 8192 levels) selects the deep-book engine: one CTA per book with fetch /
+    match / retire warps and chunked array queues in HBM (N 256-byte chunks of 31 queue entries per book) — for books with
+    ~10^6 resting orders driven by replayed streams (`replay`, `replay_device`); Env mode and in-kernel agents raise.
+
     `assets=A` (> 1) groups consecutive books into multi-asset markets with MarketEnv semantics
     (crates/step_sim/src/market_env.rs:108-121); see `bourse_b200.market`."""
 
@@ -60,7 +64,7 @@ class BatchedEnv:
                  device: int = 0, env_id_base: int = 0, obs_words: int = abi.OBS_L2, max_orders: int = 1 << 16,
                  max_trades: int = 1 << 16, max_steps: int = 1 << 12, max_queue: int = 256, pages_smem: int = 0,
                  pages_total: int = 0, price_granule: int = 0, price_window: typing.Optional[typing.Tuple[int, int]] = None,
-                 live_cap: int = 0, assets: int = 0):
+                 live_cap: int = 0, assets: int = 0, deep_chunks: int = 0):
         self._lib = abi.load()
         cfg = abi.Config()
         cfg.struct_size = C.sizeof(abi.Config)
@@ -77,6 +81,10 @@ class BatchedEnv:
                 raise ValueError("price_window must be (lo, hi) with hi > lo")
             cfg.win_lo, cfg.win_levels, cfg.live_cap = lo, hi - lo, live_cap
             cfg.price_granule = 1
+        # deep-book engine (csrc/deep.cuh): one CTA per book, replayed streams only; needs price_window as well
+        if deep_chunks and price_window is None:
+            raise ValueError("deep_chunks needs price_window=(lo, hi) (at most 8192 levels)")
+        cfg.deep_chunks = deep_chunks
         self._h = C.c_void_p()
         self.n_envs, self.obs_words, self.tick_size = n_envs, obs_words, tick_size
         self.max_orders, self.max_trades, self.max_steps = max_orders, max_trades, max_steps

@@ -185,6 +185,8 @@ template <u32 LP_, u32 NWMAX_> struct DenseLayout;
 // the generic geometry with EVERY page resident in shared memory (deep books at one or two books per CTA): the HBM-page
 // variants of every page access drop out of the instruction stream.  Only k_apply is instantiated for it.
 #define ENG_PAGED_RES 4
+// deep-book engine (deep.cuh): its own kernel (k_deep, one CTA per book); never a GeoT<> instantiation
+#define ENG_DEEP 5
 template <int ENG_> struct GeoT : Geo {
     static constexpr bool FAST = ENG_ == ENG_FAST;
     static constexpr bool RES = ENG_ == ENG_FAST || ENG_ == ENG_PAGED_RES;  // no page lives in HBM

@@ -69,11 +69,16 @@ struct bb_handle {
     u64 blob_stride = 0;
     u32 blob_smem_bytes = 0, p_total = 0, p_smem = 0, granule = 0, max_steps_padded = 0;
     bool all_resident = false;  // generic geometry with pages_smem == pages_total
-    int eng = ENG_PAGED;  // ENG_FAST: granule == 1, one 32-entry page directory, no HBM pages; ENG_DENSE: dense window
+    int eng = ENG_PAGED;  // ENG_FAST: granule == 1, one 32-entry page directory, no HBM pages; ENG_DENSE: dense window; ENG_DEEP
     Geo dgeo{};           // dense-engine geometry (d_* fields), zero otherwise
     u32 dense_lp = 0, dense_nwmax = 0;  // DenseLayout parameters of the selected variant
     u64 hist_env_stride = 0;
     SmemLayout lay_apply{}, lay_sim{}, lay_snap{};
+    // deep-book engine (deep.cuh): shared-memory offsets of k_deep, chunk pools [n_envs][dp_chunks] x 256 B
+    DeepOff dp{};
+    unsigned char* dp_pool = nullptr;
+    u32 dp_chunks = 0;
+    bool deep_attr_set = false;
     // agents
     std::vector<bb_agent_group> groups;
     std::vector<u32> group_asset;  // bb_set_agents_market: asset each group trades (empty: single-asset agents)
@@ -209,6 +214,31 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.off_bar = l.off_bar;
     p.off_mkt = l.off_mkt;
     p.assets = h->assets;
+    p.dp = h->dp;
+    p.dp_pool = h->dp_pool;
+    p.dp_chunks = h->dp_chunks;
+}
+
+// shared-memory map of k_deep for a window of W levels (deep.cuh)
+DeepOff deep_layout(u32 W) {
+    DeepOff o{};
+    const u32 nw = W / 32;
+    o.bm = DP_OFF_BM;
+    o.sm = o.bm + 8u * nw;
+    o.lv = align_up(o.sm + 8u * DP_NS, 16);
+    o.image_bytes = align_up(o.lv + 16u * W, 128);
+    u32 off = o.image_bytes;
+    o.ctag = off; off += 4u * DP_NC;
+    o.cdat = off; off += DP_CHUNK_BYTES * DP_NC;
+    o.ev_ins = off; off += 1024u * DP_RB;
+    o.ev_rec = off; off += 1024u * DP_RB;
+    o.ev_rf = off; off += 16u;
+    o.ret = off; off += DP_RENT * DP_RCAP;
+    o.dirty = off; off += 4u * DP_DIRTY;
+    o.ctl = off; off += 4u * CT_WORDS;
+    o.bar = off; off += 8u * (DP_RB + 1u);
+    o.total = align_up(off, 128);
+    return o;
 }
 
 template <class K> int grid_for(bb_handle* h, K kernel, const SmemLayout& l, u32 n_items, int* grid_out, u32 wpb = WPB) {
@@ -247,6 +277,18 @@ int upload_seeds(bb_handle* h) {
 // asynchronous on the handle's stream: one small kernel rewrites every book header and page directory
 int init_books(bb_handle* h) {
     const bb_config& c = h->cfg;
+    if (h->eng == ENG_DEEP) {
+        k_init_deep<<<c.n_envs, 128, 0, h->stream>>>(h->blobs, h->blob_stride, c.n_envs, c.start_time, c.trading ? 1u : 0u, h->d_seeds,
+                                                     h->dp.bm, h->dp.lv - h->dp.bm);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
+        h->status_valid = false;
+        for (auto& q : h->queue) q.clear();
+        std::fill(h->n_orders_host.begin(), h->n_orders_host.end(), 0);
+        h->mirror_dirty = false;
+        h->recorded_host = 0;
+        return BB_OK;
+    }
     k_init<<<c.n_envs, 64, 0, h->stream>>>(h->blobs, h->blob_stride, c.n_envs, h->p_total, c.start_time, c.trading ? 1u : 0u,
                                            h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups, h->dgeo, h->dense_lp, h->dense_nwmax);
     CUDA_TRY(h, cudaGetLastError());
@@ -319,6 +361,17 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     p.assign_ids = d_out_ids ? 1u : 0u;
     p.out_ids = d_out_ids;
     p.obs_out = d_obs_out;
+    if (h->eng == ENG_DEEP) {
+        if (mode != MODE_REPLAY || d_out_ids || d_obs_out) return fail(h, BB_EINVAL, "the deep-book engine replays instruction streams only");
+        if (!h->deep_attr_set) {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+            h->deep_attr_set = true;
+        }
+        k_deep<<<h->cfg.n_envs, 96, h->dp.total, h->stream>>>(p);
+        CUDA_TRY(h, cudaGetLastError());
+        h->recorded_host = -1;
+        return BB_OK;
+    }
     int grid = 0, rc;
     const u32 wpb = wpb_for(h->lay_apply.warp_bytes);
     const size_t smem = (size_t)h->lay_apply.warp_bytes * wpb;
@@ -354,6 +407,11 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
 int snapshot(bb_handle* h, u32 first_env, u32 n, u32* d45, u32* d8, u32 words = 45u) {
     KParams p;
     fill_params(h, h->lay_snap, p);
+    if (h->eng == ENG_DEEP) {
+        k_snapshot_deep<<<(n + 3) / 4, 128, 0, h->stream>>>(p, d45, d8, first_env, n, words);
+        CUDA_TRY(h, cudaGetLastError());
+        return BB_OK;
+    }
     int grid = 0, rc;
     const u32 wpb = wpb_for(h->lay_snap.warp_bytes);
     const size_t smem = (size_t)h->lay_snap.warp_bytes * wpb;
@@ -418,7 +476,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     h->all_resident = h->eng == ENG_PAGED && usable == h->p_smem;  // k_apply<.., ENG_PAGED_RES>: no HBM page variants
     h->blob_smem_bytes = 128u + 12u * h->p_total + 512u * h->p_smem;
     h->blob_stride = 128ull + 12ull * h->p_total + 512ull * h->p_total;
-    if (cfg->win_levels) {  // dense-window engine (csrc/dense.cuh), two compiled size classes
+    if (cfg->win_levels && !cfg->deep_chunks) {  // dense-window engine (csrc/dense.cuh), two compiled size classes
         const u32 W = align_up(cfg->win_levels, 32), L = cfg->live_cap ? cfg->live_cap : 128u;
         if (h->granule != 1 || W > 32 * DenseLarge::NWMAX || L > 254 || (u64)cfg->win_lo + W > 0x100000000ull) {
             delete h;
@@ -432,6 +490,27 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
         h->dense_nwmax = small ? DenseSmall::NWMAX : DenseLarge::NWMAX;
         h->blob_smem_bytes = align_up(small ? DenseSmall::image_bytes(W) : DenseLarge::image_bytes(W), 16);
         h->blob_stride = align_up(h->blob_smem_bytes, 128);
+        h->p_total = h->p_smem = 0;
+    }
+    if (cfg->deep_chunks) {  // deep-book engine (csrc/deep.cuh): the dense-window fields describe its ladder
+        const u32 W = align_up(cfg->win_levels, 32);
+        if (!cfg->win_levels || h->granule != 1 || W > 32u * 32u * DP_NS || (u64)cfg->win_lo + W > 0x100000000ull || h->assets > 1 ||
+            cfg->deep_chunks < 2 || cfg->deep_chunks >= (1u << 27)) {
+            delete h;
+            return fail(nullptr, BB_EINVAL, "deep engine needs price_granule == 1, 0 < win_levels <= 8192, win_lo + win_levels <= 2^32, "
+                                            "2 <= deep_chunks < 2^27 and single-asset envs");
+        }
+        h->eng = ENG_DEEP;
+        h->dgeo.d_win_lo = cfg->win_lo; h->dgeo.d_levels = W; h->dgeo.d_live = 0;
+        h->dense_lp = h->dense_nwmax = 0;
+        h->dp = deep_layout(W);
+        h->dp_chunks = cfg->deep_chunks;
+        if (h->dp.total > 232448u - 1024u) {
+            delete h;
+            return fail(nullptr, BB_EINVAL, "deep engine: window does not fit in shared memory");
+        }
+        h->blob_smem_bytes = h->dp.image_bytes;
+        h->blob_stride = h->dp.image_bytes;
         h->p_total = h->p_smem = 0;
     }
     h->max_steps_padded = align_up(cfg->max_steps, 4);
@@ -459,6 +538,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     TRY_ALLOC(cudaMalloc(&h->ord, ne * cfg->max_orders * sizeof(OrderRec)));
     if (cfg->max_trades) TRY_ALLOC(cudaMalloc(&h->tr, ne * cfg->max_trades * sizeof(TradeRec)));
     TRY_ALLOC(cudaMalloc(&h->hist, ne * h->hist_env_stride * 4));
+    if (h->eng == ENG_DEEP) TRY_ALLOC(cudaMalloc(&h->dp_pool, ne * (size_t)h->dp_chunks * DP_CHUNK_BYTES));
     TRY_ALLOC(cudaMalloc(&h->err_flag, 4));
     TRY_ALLOC(cudaMalloc(&h->d_offsets, (ne + 1) * 8));
     TRY_ALLOC(cudaMalloc(&h->d_seeds, ne * 16));
@@ -482,7 +562,7 @@ int bb_destroy(bb_handle* h) {
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     cudaFree(h->blobs); cudaFree(h->ord); cudaFree(h->tr); cudaFree(h->hist); cudaFree(h->err_flag);
     cudaFree(h->d_offsets); cudaFree(h->d_seeds); cudaFree(h->d_instrs); cudaFree(h->d_snap); cudaFree(h->d_stats);
-    cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch); cudaFree(h->d_ids);
+    cudaFree(h->rslot); cudaFree(h->mom); cudaFree(h->scratch); cudaFree(h->d_ids); cudaFree(h->dp_pool);
     if (h->h_instrs) cudaFreeHost(h->h_instrs);
     if (h->h_offsets) cudaFreeHost(h->h_offsets);
     if (h->h_snap) cudaFreeHost(h->h_snap);
@@ -573,6 +653,7 @@ int bb_submit(bb_handle* h, uint64_t n, const uint32_t* env, const uint32_t* act
 
 int bb_step(bb_handle* h, uint32_t n_steps) {
     CHECK_H(h);
+    if (h->eng == ENG_DEEP) return fail(h, BB_EINVAL, "the deep-book engine replays instruction streams only (bb_replay / bb_replay_device)");
     if (n_steps == 0) return BB_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const u32 ne = h->cfg.n_envs;
@@ -663,6 +744,7 @@ int bb_replay_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_e
 
 static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uint32_t* asset, uint32_t n_groups) {
     CHECK_H(h);
+    if (h->eng == ENG_DEEP) return fail(h, BB_EINVAL, "the deep-book engine replays instruction streams only (no in-kernel agents)");
     if (n_groups > MAX_GROUPS) return fail(h, BB_EINVAL, "at most 8 agent groups");
     if (n_groups && !groups) return fail(h, BB_EINVAL, "null groups");
     if (asset) {
@@ -730,6 +812,7 @@ int bb_step_device(bb_handle* h, const bb_instr* d_instrs, const uint64_t* d_env
     CHECK_H(h);
     if (!d_env_offsets || (n_rows && !d_instrs)) return fail(h, BB_EINVAL, "null argument");
     if (h->assets > 1) return fail(h, BB_EINVAL, "bb_step_device drives single-asset envs (multi-asset queues are ordered on the host)");
+    if (h->eng == ENG_DEEP) return fail(h, BB_EINVAL, "the deep-book engine replays instruction streams only");
     for (auto& q : h->queue)
         if (!q.empty()) return fail(h, BB_EINVAL, "host-queued instructions pending: call bb_step first");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -865,6 +948,7 @@ int bb_run_agents_with_rows(bb_handle* h, uint64_t seed, const bb_instr* d_instr
 namespace {
 int run_agents_impl(bb_handle* h, uint64_t seed, uint32_t n_steps, const ExtRows* ext) {
     CHECK_H(h);
+    if (h->eng == ENG_DEEP) return fail(h, BB_EINVAL, "the deep-book engine replays instruction streams only");
     if (h->groups.empty()) return fail(h, BB_EINVAL, "bb_set_agents has not been called");
     const bool mkt = !h->group_asset.empty();
     if (h->assets > 1 && !mkt)
@@ -1194,6 +1278,7 @@ int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int
     CHECK_ENV(h, env);
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->queue[env].empty()) return fail(h, BB_EINVAL, "env has queued instructions");
+    if (h->eng == ENG_DEEP) return fail(h, BB_EINVAL, "bb_load_book is not available on the deep-book engine");
     if (n_orders > h->cfg.max_orders || n_trades > h->cfg.max_trades) return fail(h, BB_ECAP, "snapshot exceeds max_orders / max_trades");
     if (n_orders && !(side_is_bid && status && arr_time && end_time && vol && start_vol && price && trader && key_time))
         return fail(h, BB_EINVAL, "null order column");

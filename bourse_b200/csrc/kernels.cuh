@@ -12,6 +12,7 @@
 #include "book.cuh"
 #include "philox.cuh"
 #include "tma.cuh"
+#include "deep.cuh"
 
 namespace bb {
 
@@ -66,6 +67,10 @@ struct KParams {
     u32 assets;                   // books per market; the market's books are consecutive warps of one CTA
     u32 off_mkt;                  // per-warp offset of the market's shared words (used in the market's first warp only)
     u32 group_asset[MAX_GROUPS];  // asset each agent group trades
+    // k_deep (deep.cuh): shared-memory offsets, chunk pools [n_envs][dp_chunks] x 256 B
+    DeepOff dp;
+    unsigned char* dp_pool;
+    u32 dp_chunks;
 };
 
 // Values the optimiser would otherwise rematerialise at every use (S2R for the lane id, cvta + multiply
@@ -1013,6 +1018,445 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Deep-book replay kernel (deep.cuh): one CTA per book, warp 0 = match, warp 1 = fetch, warp 2 = retire.
+// Immediate-mode instruction streams (OrderBook API at explicit times, orderbook.rs:411-792), config C5 / C2.
+#define DT_EXIT 1u
+#define DT_SWEEP 2u
+#define DT_OBS 3u
+
+__device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, const bb_instr* ins, u32 n, u64 oh) {
+    const u32 ctl = sb + o.ctl;
+    const u32 nb = (n + 31u) >> 5;
+    for (u32 b = 0; b < nb; ++b) {
+        const u32 slot = b & (DP_RB - 1u);
+        if (b >= DP_RB) {
+            if (!dp_wait(ctl, [&] { return ld_acq(ctl + CT_EV_CONSUMED) + DP_RB > b; })) return;
+        }
+        const u32 cnt = min(32u, n - 32u * b);
+        const u32 ia = sb + o.ev_ins + 1024u * slot, bar = sb + o.bar + 8u + 8u * slot;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0u) {
+            mbar_expect_tx_a(bar, cnt * 32u);
+            bulk_g2s_a(ia, ins + 32u * (size_t)b, cnt * 32u, bar);
+        }
+        if (!mbar_wait_a(bar, (b / DP_RB) & 1u)) {
+            st_rel(ctl + CT_ABORT, 1u);
+            return;
+        }
+        // records written by retire entries below this index are performed and fenced: sampled BEFORE the loads below
+        const u32 rf = ld_acq(ctl + CT_RET_DONE);
+        if (lane < cnt) {
+            const u64 w = lds64(ia + 32u * lane + 8u);  // op_flags | order_id << 32
+            const u32 op = (u32)w & BB_OP_MASK, id = (u32)(w >> 32);
+            if ((op == BB_OP_CANCEL || op == BB_OP_MODIFY) && id < p.geo.max_orders) {
+                u64 src = oh + (u64)id * ORD_STRIDE;
+                // a true data dependency on `rf` (always adds 0): the loads cannot be issued before rf was read
+                asm volatile("{\n\t.reg .u64 z;\n\tcvt.u64.u32 z, %1;\n\tshr.u64 z, z, 32;\n\tadd.u64 %0, %0, z;\n\t}" : "+l"(src) : "r"(rf));
+                const u32 ra = sb + o.ev_rec + 1024u * slot + 32u * lane;
+                cp_async16(ra, src);
+                cp_async16(ra + 16u, src + 16u);
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (lane == 0u) {
+            sts(sb + o.ev_rf + 4u * slot, rf);
+            st_rel(ctl + CT_EV_READY, b + 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, u64 oh, u64 tr, u32 n_tr0) {
+    const u32 ctl = sb + o.ctl;
+    u32 head = 0, n_tr = n_tr0, err = 0;
+    for (;;) {
+        u32 tail = 0;
+        bool fin = false;
+        const bool ok = dp_wait(ctl, [&] {
+            fin = ld_acq(ctl + CT_FIN) != 0u;  // read before the tail: FIN is set after the last tail update
+            tail = ld_acq(ctl + CT_RET_TAIL);
+            return tail != head || fin;
+        });
+        if (!ok || (tail == head && fin)) break;
+        const u32 n = min(32u, tail - head);
+        uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+        u64 t = 0;
+        if (lane < n) {
+            const u32 ea = sb + o.ret + DP_RENT * ((head + lane) & (DP_RCAP - 1u));
+            a = lds128(ea);
+            b = lds128(ea + 16u);
+            t = lds64(ea + 32u);
+        }
+        const u32 kind = a.x & 0xFFu, side_bit = ((a.x >> 8) & 1u) ? META_BID : 0u;
+        const u32 fm = __ballot_sync(BB_FULL, kind == RK_FILL);
+        // entries of one order are applied in ring order: lanes naming the same id take turns
+        const u32 grp = __match_any_sync(BB_FULL, lane < n ? a.y : (0xFFFFFF00u | lane));
+        const u32 rank = __popc(grp & ((1u << lane) - 1u));
+        const u32 rounds = __reduce_max_sync(BB_FULL, rank) + 1u;
+        const u64 ra = oh + (u64)a.y * ORD_STRIDE;
+        if (kind == RK_FILL) {
+            const u32 ti = n_tr + __popc(fm & ((1u << lane) - 1u));
+            if (ti < p.geo.max_trades) {
+                const u64 ta = tr + (u64)ti * 32u;
+                stg128_cs(ta, (u32)t, (u32)(t >> 32), a.z, a.w);
+                stg128_cs(ta + 16u, b.x, a.y, (a.x >> 8) & 1u, 0u);
+            } else if (p.geo.max_trades) {
+                err |= ERR_CAP_TRADES;
+            }
+        }
+        for (u32 r = 0; r < rounds; ++r) {
+            if (lane < n && rank == r) {
+                if (kind == RK_NEW) {
+                    const u32 status = (a.x >> 12) & 7u;
+                    const u64 kt = status == ST_ACTIVE ? t : 0ULL, end = status == ST_ACTIVE ? ~0ULL : t;
+                    stg128(ra, a.z, a.w, b.z, BB_NIL);
+                    stg128(ra + 16u, (u32)kt, (u32)(kt >> 32), status | side_bit, b.x);
+                    stg128(ra + 32u, (u32)t, (u32)(t >> 32), (u32)end, (u32)(end >> 32));
+                    stg128(ra + 48u, b.y, 0u, 0u, 0u);
+                } else if (kind == RK_REPLACE) {
+                    const u32 status = (a.x >> 12) & 7u;
+                    stg128(ra, a.z, a.w, b.x, BB_NIL);
+                    stg32(ra + OH_META, status | side_bit);
+                    stg64(ra + (status == ST_FILLED ? OC_END : OH_KEYT), t);
+                } else if (kind == RK_FILL) {
+                    stg32(ra + OH_VOL, b.y);
+                    if (a.x & 0x10000u) {
+                        stg32(ra + OH_META, ST_FILLED | side_bit);
+                        stg64(ra + OC_END, t);
+                    }
+                } else if (kind == RK_CANCEL) {
+                    stg32(ra + OH_META, ST_CANCELLED | side_bit);
+                    stg64(ra + OC_END, t);
+                } else if (kind == RK_REDUCE) {
+                    stg32(ra + OH_VOL, a.w);
+                }
+            }
+            __syncwarp();
+        }
+        n_tr += __popc(fm);
+        head += n;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0u) st_rel(ctl + CT_RET_DONE, head);
+    }
+    err = __reduce_or_sync(BB_FULL, err);
+    if (lane == 0u) {
+        sts(ctl + CT_RERR, err);
+        sts(ctl + CT_NTR, n_tr);
+    }
+}
+
+__global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 sb = smem_u32(smem);
+    const DeepOff& o = p.dp;
+    const u32 ctl = sb + o.ctl;
+    const u32 env = blockIdx.x;
+    if (env >= p.n_envs) return;
+    const u64 oh = (u64)(p.ord + (size_t)env * p.geo.max_orders);
+    const u64 tr = (u64)(p.tr + (size_t)env * p.geo.max_trades);
+    const u64 off = p.offsets[env];
+    const u32 n = (u32)(p.offsets[env + 1] - off);
+    const bb_instr* ins = p.instrs + off;
+    // ---- set-up: barriers, control words, cache tags, dirty filter; then the book image (one bulk copy)
+    if (threadIdx.x == 0) {
+        for (u32 i = 0; i <= DP_RB; ++i) mbar_init_a(sb + o.bar + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (u32 i = threadIdx.x; i < CT_WORDS; i += blockDim.x) sts(ctl + 4u * i, 0u);
+    for (u32 i = threadIdx.x; i < DP_NC; i += blockDim.x) sts(sb + o.ctag + 4u * i, BB_NIL);
+    for (u32 i = threadIdx.x; i < DP_DIRTY; i += blockDim.x) sts(sb + o.dirty + 4u * i, 0u);
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx_a(sb + o.bar, o.image_bytes);
+        bulk_g2s_a(sb, p.blobs + (size_t)env * p.blob_stride, o.image_bytes, sb + o.bar);
+        if (!mbar_wait_a(sb + o.bar, 0u)) st_rel(ctl + CT_ABORT, 1u);
+    }
+    __syncthreads();
+    const u32 n_tr0 = min((u32)lds64(sb + HDR_NTRADES_TOTAL), p.geo.max_trades);
+
+    if (warp == 1u) {
+        dp_fetch_warp(p, o, sb, lane, ins, n, oh);
+    } else if (warp == 2u) {
+        dp_retire_warp(p, o, sb, lane, oh, tr, n_tr0);
+    } else {
+        // ---- match warp ----------------------------------------------------------------------------------------
+        DeepReg r;
+        r.lv = dp_keep32(sb + o.lv);
+        r.bma = dp_keep32(sb + o.bm);
+        r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
+        r.sma = dp_keep32(sb + o.sm);
+        r.smb = dp_keep32(sb + o.sm + 4u * DP_NS);
+        r.ctag = dp_keep32(sb + o.ctag);
+        r.cdat = dp_keep32(sb + o.cdat);
+        r.ret = dp_keep32(sb + o.ret);
+        r.dirty = dp_keep32(sb + o.dirty);
+        r.ctl = dp_keep32(ctl);
+        r.fs = dp_keep32(sb + DP_OFF_FS);
+        r.win_lo = p.geo.d_win_lo; r.W = p.geo.d_levels; r.n_chunks = p.dp_chunks; r.max_orders = p.geo.max_orders;
+        r.chunks = dp_keep64((u64)(p.dp_pool + (size_t)env * p.dp_chunks * DP_CHUNK_BYTES));
+        r.oh = dp_keep64(oh);
+        const u32 ev_ins = dp_keep32(sb + o.ev_ins), ev_rec = dp_keep32(sb + o.ev_rec);
+        DeepSt s;
+        s.t = lds64(sb + HDR_T);
+        s.max_key_time = lds64(sb + HDR_MAXKT);
+        s.n_orders = lds(sb + HDR_NORDERS);
+        s.n_trades = (u32)lds64(sb + HDR_NTRADES_TOTAL);
+        s.trade_vol = lds(sb + HDR_TRADEVOL);
+        s.vol_ask = lds(sb + HDR_SIDEVOL);
+        s.vol_bid = lds(sb + HDR_SIDEVOL + 4u);
+        s.bq_ask = lds(sb + HDR_BESTQ);
+        s.bq_bid = lds(sb + HDR_BESTQ + 4u);
+        s.flags = (lds(sb + HDR_TRADING) ? FL_TRADING : 0u) | (lds(sb + HDR_HASBEST) ? FL_HAS_ASK : 0u) |
+                  (lds(sb + HDR_HASBEST + 4u) ? FL_HAS_BID : 0u);
+        s.err = 0u;
+        s.d_instr = s.d_applied = 0u;
+        s.bump = lds(sb + DP_OFF_BUMP);
+        s.n_free = lds(sb + DP_OFF_NFREE);
+        s.ret_tail = 0u;
+        s.ret_room = DP_RCAP;
+        const u32 n_orders0 = s.n_orders, n_trades0 = s.n_trades, trade_vol0 = s.trade_vol;
+        // event context that survives a trip through the warp-cooperative handlers (lane 0 only)
+        u32 ev_i = 0u, rf = 0u, published = 0u;
+        u32 c_kind = 0u, c_side = 0u, c_price = 0u, c_vol = 0u, c_rem = 0u, c_id = 0u, c_trader = 0u, c_emit = 0u;
+        bool c_market = false, aborted = false;
+        // after matching: rest or finish the order, queue its record write, close the event (lane 0)
+        auto finish = [&]() {
+            const bool filled = c_vol != 0u && c_rem == 0u;
+            const bool trading = (s.flags & FL_TRADING) != 0u;
+            const u32 status = filled ? ST_FILLED : c_market ? (trading ? ST_CANCELLED : ST_REJECTED) : ST_ACTIVE;
+            u32 pos = 0u;
+            if (status == ST_ACTIVE) pos = dp_insert(r, s, c_side, c_price, s.t, c_id, c_rem);
+            if (!dp_ret_space(r, s, 1u)) {
+                aborted = true;
+                return;
+            }
+            // RK_NEW: b = {start_vol, trader, pos}; RK_REPLACE: b = {pos}
+            dp_ret_write(r, s.ret_tail, make_uint4(c_kind | (c_side << 8) | (status << 12), c_id, c_price, c_rem),
+                         make_uint4(c_kind == RK_NEW ? c_vol : pos, c_trader, pos, 0u), (u32)s.t, (u32)(s.t >> 32));
+            s.ret_tail += 1;
+            dp_mark_dirty(r, c_id, s.ret_tail);
+            s.d_applied += 1;
+        };
+        // the event is done: make its record writes visible to the retire warp, hand finished batches back to the fetch warp
+        auto close_event = [&]() {
+            if (s.ret_tail != published) {
+                published = s.ret_tail;
+                st_rel(r.ctl + CT_RET_TAIL, published);
+            }
+            if ((ev_i & 31u) == 0u || ev_i == n) st_rel(r.ctl + CT_EV_CONSUMED, (ev_i + 31u) >> 5);
+        };
+        for (;;) {
+            u32 trap = 0u;
+            if (lane == 0u) {
+                trap = DT_EXIT;
+                while (ev_i < n && !aborted) {
+                    // ---- next event: decode, and everything that precedes matching
+                    const u32 bslot = (ev_i >> 5) & (DP_RB - 1u);
+                    if ((ev_i & 31u) == 0u) {
+                        const u32 b = ev_i >> 5;
+                        if (ld_acq(r.ctl + CT_EV_READY) <= b && !dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_READY) > b; })) {
+                            aborted = true;
+                            break;
+                        }
+                        rf = lds(sb + o.ev_rf + 4u * bslot);
+                    }
+                    const u32 eo = 1024u * bslot + 32u * (ev_i & 31u);
+                    const uint4 x = lds128(ev_ins + eo), y = lds128(ev_ins + eo + 16u);
+                    ev_i += 1;
+                    s.t = ((u64)x.y << 32) | x.x;
+                    const u32 op = x.z & BB_OP_MASK;
+                    c_emit = x.z & BB_F_EMIT;
+                    bool to_match = false;
+                    if (op == BB_OP_NEW) {
+                        s.d_instr += 1;
+                        c_id = s.n_orders;
+                        if (c_id >= r.max_orders) {
+                            s.err |= ERR_CAP_ORDERS;
+                        } else {
+                            s.n_orders = c_id + 1u;
+                            c_kind = RK_NEW;
+                            c_side = (x.z >> 8) & 1u;  // BB_F_BID
+                            c_price = (x.z & BB_F_MARKET) ? (c_side ? 0xFFFFFFFFu : 0u) : y.x;  // types.rs:160-172, 213-225
+                            c_market = c_side ? (c_price == 0xFFFFFFFFu) : (c_price == 0u);       // N3
+                            c_vol = c_rem = y.y;
+                            c_trader = y.z;
+                            to_match = true;
+                        }
+                    } else if (op == BB_OP_CANCEL || op == BB_OP_MODIFY) {
+                        s.d_instr += 1;
+                        const u32 id = x.w;
+                        if (id >= s.n_orders || id >= r.max_orders) {
+                            s.err |= ERR_BAD_ID;  // the reference panics (orderbook.rs:642, :749)
+                        } else {
+                            // the order's record: prefetched by the fetch warp, unless a write to it was still in
+                            // flight when the fetch was issued (then: wait for the retire warp and read it here)
+                            uint4 a, c;
+                            const u32 dv = lds(r.dirty + 4u * (id & (DP_DIRTY - 1u)));
+                            if (dv <= rf) {
+                                a = lds128(ev_rec + eo);
+                                c = lds128(ev_rec + eo + 16u);
+                            } else {
+                                if (s.ret_tail != published) {
+                                    published = s.ret_tail;
+                                    st_rel(r.ctl + CT_RET_TAIL, published);
+                                }
+                                if (!dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_RET_DONE) >= dv; })) {
+                                    aborted = true;
+                                    break;
+                                }
+                                a = ldg128_cg(r.oh + (u64)id * ORD_STRIDE);
+                                c = ldg128_cg(r.oh + (u64)id * ORD_STRIDE + 16u);
+                            }
+                            if ((c.z & META_STATUS_MASK) == ST_ACTIVE) {
+                                const u32 side = (c.z & META_BID) ? 1u : 0u;
+                                const bool has_p = (x.z & BB_F_HAS_PRICE) != 0u, has_v = (x.z & BB_F_HAS_VOL) != 0u;
+                                if (op == BB_OP_CANCEL) {
+                                    dp_remove(r, s, side, a.x, a.y, a.z);
+                                    if (!dp_ret_space(r, s, 1u)) { aborted = true; break; }
+                                    dp_ret_write(r, s.ret_tail, make_uint4(RK_CANCEL | (side << 8), id, 0u, 0u), make_uint4(0, 0, 0, 0), x.x, x.y);
+                                    s.ret_tail += 1;
+                                    dp_mark_dirty(r, id, s.ret_tail);
+                                    s.d_applied += 1;
+                                } else if (!has_p && !has_v) {
+                                } else if (!has_p && y.y < a.y) {  // reduce in place: priority kept (orderbook.rs:755-757)
+                                    const u32 q = a.x - r.win_lo;
+                                    if (q < r.W) {
+                                        dp_chunk_st32(r, a.z >> 5, 8u * (a.z & 31u) + 4u, y.y);
+                                        const u32 la = r.lv + 16u * q;
+                                        sts(la, lds(la) - (a.y - y.y));
+                                    }
+                                    dp_add_side(s, side, y.y - a.y);
+                                    if (!dp_ret_space(r, s, 1u)) { aborted = true; break; }
+                                    dp_ret_write(r, s.ret_tail, make_uint4(RK_REDUCE, id, 0u, y.y), make_uint4(0, 0, 0, 0), x.x, x.y);
+                                    s.ret_tail += 1;
+                                    dp_mark_dirty(r, id, s.ret_tail);
+                                    s.d_applied += 1;
+                                } else {  // replace_order (orderbook.rs:679-723): never a market order (N4)
+                                    dp_remove(r, s, side, a.x, a.y, a.z);
+                                    c_kind = RK_REPLACE;
+                                    c_id = id;
+                                    c_side = side;
+                                    c_price = has_p ? y.x : a.x;
+                                    c_vol = c_rem = has_v ? y.y : a.y;
+                                    c_trader = 0u;
+                                    c_market = false;
+                                    to_match = true;
+                                }
+                            }
+                        }
+                    } else if (op == BB_OP_SET_TRADING) {
+                        s.flags = y.y ? (s.flags | FL_TRADING) : (s.flags & ~FL_TRADING);
+                    } else if (op == BB_OP_RESTORE) {
+                        s.err |= ERR_ROW_OP;  // bb_load_book is not available on the deep engine
+                    }
+                    if (to_match) {
+                        if ((s.flags & FL_TRADING) && dp_match_serial(r, s, c_side, c_price, c_rem, c_id, aborted)) {
+                            if (s.ret_tail != published) {
+                                published = s.ret_tail;
+                                st_rel(r.ctl + CT_RET_TAIL, published);
+                            }
+                            trap = DT_SWEEP;  // the rest of this order's sweep is the warp's
+                            break;
+                        }
+                        if (aborted) break;
+                        finish();
+                    }
+                    close_event();
+                    if (c_emit) {
+                        trap = DT_OBS;
+                        break;
+                    }
+                }
+            }
+            trap = __shfl_sync(BB_FULL, trap, 0);
+            if (trap == DT_EXIT) break;
+            if (trap == DT_SWEEP) {
+                const u32 side = __shfl_sync(BB_FULL, c_side, 0), price = __shfl_sync(BB_FULL, c_price, 0);
+                const u32 rem = __shfl_sync(BB_FULL, c_rem, 0), id = __shfl_sync(BB_FULL, c_id, 0);
+                const u64 t = ((u64)__shfl_sync(BB_FULL, (u32)(s.t >> 32), 0) << 32) | __shfl_sync(BB_FULL, (u32)s.t, 0);
+                c_rem = dp_sweep_warp(r, s, lane, side, price, rem, id, t);
+                u32 emit = 0u;
+                if (lane == 0u) {
+                    published = s.ret_tail;  // (the sweep publishes what it queues)
+                    if (ld_acq(r.ctl + CT_ABORT)) aborted = true;
+                    if (!aborted) {
+                        finish();
+                        close_event();
+                        emit = c_emit;
+                    }
+                }
+                if (!__shfl_sync(BB_FULL, emit, 0)) continue;
+            }
+            {   // Level2DataRecords::append_record (data.rs:44-56) for a row flagged BB_F_EMIT
+                const u32 bid_has = __shfl_sync(BB_FULL, s.flags & FL_HAS_BID, 0), ask_has = __shfl_sync(BB_FULL, s.flags & FL_HAS_ASK, 0);
+                const u32 bid = bid_has ? r.win_lo + __shfl_sync(BB_FULL, s.bq_bid, 0) : 0u;
+                const u32 ask = ask_has ? r.win_lo + __shfl_sync(BB_FULL, s.bq_ask, 0) : 0xFFFFFFFFu;
+                u32 w0, w1;
+                DeepReg rr = r;  // (lanes 1..31 hold the same launch-invariant values)
+                dp_obs(rr, p.geo.tick, lane, __shfl_sync(BB_FULL, s.trade_vol, 0), bid, ask, __shfl_sync(BB_FULL, s.vol_ask, 0),
+                       __shfl_sync(BB_FULL, s.vol_bid, 0), &w0, &w1);
+                // (a level-1 record is the first 9 words of the level-2 one: words 5..8 are the touch level of each side)
+                const u32 nrec = lds(sb + HDR_NSTEPS);
+                __syncwarp();
+                if (nrec < p.max_steps) {
+                    const u64 dst = (u64)(p.hist + (size_t)env * p.hist_env_stride + (size_t)nrec * p.obs_words);
+                    if (lane < p.obs_words) stg32(dst + 4u * lane, w0);
+                    if (lane + 32u < p.obs_words) stg32(dst + 4u * (lane + 32u), w1);
+                    if (lane == 0u) sts(sb + HDR_NSTEPS, nrec + 1u);
+                } else if (lane == 0u) {
+                    s.err |= ERR_CAP_STEPS;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- the header goes back into the image; the retire warp drains what is left and exits on FIN
+        if (lane == 0u) {
+            st_rel(r.ctl + CT_RET_TAIL, s.ret_tail);
+            st_rel(r.ctl + CT_FIN, 1u);
+            sts64(sb + HDR_T, s.t);
+            sts64(sb + HDR_MAXKT, s.max_key_time);
+            sts64(sb + HDR_NCREATED, lds64(sb + HDR_NCREATED) + (s.n_orders - n_orders0));
+            sts(sb + HDR_NORDERS, s.n_orders);
+            sts(sb + HDR_TRADEVOL, s.trade_vol);
+            sts(sb + HDR_SIDEVOL, s.vol_ask);
+            sts(sb + HDR_SIDEVOL + 4u, s.vol_bid);
+            sts(sb + HDR_BESTQ, s.bq_ask);
+            sts(sb + HDR_BESTQ + 4u, s.bq_bid);
+            sts(sb + HDR_TRADING, (s.flags & FL_TRADING) ? 1u : 0u);
+            sts(sb + HDR_HASBEST, (s.flags & FL_HAS_ASK) ? 1u : 0u);
+            sts(sb + HDR_HASBEST + 4u, (s.flags & FL_HAS_BID) ? 1u : 0u);
+            sts64(sb + HDR_NINSTR, lds64(sb + HDR_NINSTR) + s.d_instr);
+            // transitions: one per fill and one per applied event; traded volume: trade_vol is never reset in replay mode
+            sts64(sb + HDR_NTRANS, lds64(sb + HDR_NTRANS) + (u32)(s.n_trades - n_trades0) + s.d_applied);
+            sts64(sb + HDR_VOLUME, lds64(sb + HDR_VOLUME) + (u32)(s.trade_vol - trade_vol0));
+            const u64 tt = lds64(sb + HDR_NTRADES_TOTAL);
+            sts64(sb + HDR_NTRADES_TOTAL, tt + (u32)(s.n_trades - (u32)tt));
+            sts(sb + HDR_NTRADES, min(s.n_trades, p.geo.max_trades));
+            sts(sb + DP_OFF_BUMP, s.bump);
+            sts(sb + DP_OFF_NFREE, s.n_free);
+            sts(ctl + CT_MERR, s.err);
+            // the fetch warp may still be waiting for ring space when the match warp gave up early
+            if (aborted) st_rel(ctl + CT_ABORT, 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 err = lds(ctl + CT_RERR) | lds(ctl + CT_MERR);
+        if (ld_acq(ctl + CT_ABORT)) err |= 0x80000000u;
+        sts(sb + HDR_ERR, lds(sb + HDR_ERR) | (err & 0x7FFFFFFFu));
+        if (err) atomicOr(p.err_flag, err);
+        fence_proxy_async();
+        bulk_s2g_a(p.blobs + (size_t)env * p.blob_stride, sb, o.image_bytes);
+        bulk_commit();
+        bulk_wait_all<0>();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Live market data of every book: out45[env][45] (level_2_data layout) and out8[env][8] =
 // OrderBook::level_1_data field order (orderbook.rs:287-301, touch by the `volumes` map).
 template <int ENG> __global__ void __launch_bounds__(128) k_snapshot(const __grid_constant__ KParams p, u32* out45, u32* out8,
@@ -1096,6 +1540,72 @@ __global__ void k_init(unsigned char* blobs, u64 blob_stride, u32 n_envs, u32 p_
             MomState* m = mom + (size_t)env * mom_per_env + i;
             m->momentum = 0.0; m->last_price = 0.0; m->has_last = 0; m->n_live = 0;
         }
+}
+
+// fresh deep book (deep.cuh image): header, empty bitmaps, chunk 0 reserved as a sink
+__global__ void k_init_deep(unsigned char* blobs, u64 blob_stride, u32 n_envs, u64 start_time, u32 trading, const u64* rng_seeds,
+                            u32 off_bm, u32 bm_bytes) {
+    const u32 env = blockIdx.x;
+    if (env >= n_envs) return;
+    unsigned char* b = blobs + (size_t)env * blob_stride;
+    if (threadIdx.x == 0) {
+        BookHdr h;
+        memset(&h, 0, sizeof(h));
+        h.t = start_time;
+        h.trading = trading;
+        h.rng_s0 = rng_seeds[2 * env];
+        h.rng_s1 = rng_seeds[2 * env + 1];
+        *reinterpret_cast<BookHdr*>(b) = h;
+        *reinterpret_cast<u32*>(b + DP_OFF_BUMP) = 1u;
+        *reinterpret_cast<u32*>(b + DP_OFF_NFREE) = 0u;
+    }
+    u32* bm = reinterpret_cast<u32*>(b + off_bm);
+    for (u32 i = threadIdx.x; i < bm_bytes / 4u; i += blockDim.x) bm[i] = 0u;
+}
+
+// live market data of deep books, read straight from the blobs in HBM (same outputs as k_snapshot)
+__global__ void __launch_bounds__(128) k_snapshot_deep(const __grid_constant__ KParams p, u32* out45, u32* out8, u32 first_env, u32 n_out,
+                                                       u32 words) {
+    const u32 lane = threadIdx.x & 31u, i = blockIdx.x * 4u + (threadIdx.x >> 5);
+    if (i >= n_out) return;
+    const u32 env = first_env + i;
+    const unsigned char* b = p.blobs + (size_t)env * p.blob_stride;
+    const BookHdr* h = reinterpret_cast<const BookHdr*>(b);
+    const u32 W = p.geo.d_levels, nw = W >> 5, lo = p.geo.d_win_lo;
+    const u32* bm = reinterpret_cast<const u32*>(b + p.dp.bm);
+    const uint4* lv = reinterpret_cast<const uint4*>(b + p.dp.lv);
+    auto level_at = [&](u32 side, u32 price, u32* vol, u32* cnt) {
+        *vol = *cnt = 0;
+        const u32 q = price - lo;
+        if (q >= W) return;
+        if (!((bm[(side ? nw : 0u) + (q >> 5)] >> (q & 31u)) & 1u)) return;
+        const uint4 r = lv[q];
+        *vol = r.x;
+        *cnt = r.y;
+    };
+    const u32 bid = h->has_best[1] ? lo + h->best_q[1] : 0u, ask = h->has_best[0] ? lo + h->best_q[0] : 0xFFFFFFFFu;
+    if (out45) {
+        for (u32 w = lane; w < words; w += 32u) {
+            u32 val;
+            if (w >= 5u) {
+                const u32 k = (w - 5u) >> 2, f = (w - 5u) & 3u;
+                u32 v, n;
+                if (f < 2u) level_at(1u, bid - k * p.geo.tick, &v, &n);
+                else level_at(0u, ask + k * p.geo.tick, &v, &n);
+                val = (f & 1u) ? n : v;
+            } else {
+                val = w == 0 ? h->trade_vol : w == 1 ? bid : w == 2 ? ask : w == 3 ? h->side_vol[0] : h->side_vol[1];
+            }
+            out45[(size_t)i * words + w] = val;
+        }
+    }
+    if (out8 && lane < 8u) {
+        u32 bv, bc, av, ac;
+        level_at(1u, bid, &bv, &bc);
+        level_at(0u, ask, &av, &ac);
+        out8[(size_t)i * 8u + lane] = lane == 0 ? bid : lane == 1 ? ask : lane == 2 ? h->side_vol[1] : lane == 3 ? h->side_vol[0]
+                                      : lane == 4 ? bv : lane == 5 ? av : lane == 6 ? bc : ac;
+    }
 }
 
 // reduction of per-env counters for bb_stats

@@ -48,6 +48,7 @@ typedef enum {
 #define BB_ERR_TIME_ORDER 0x100u /* dense engine: a resting order arrived out of time order at its price level */
 #define BB_ERR_PRICE 0x200u      /* bb_step_device: a NEW row's limit price was not a multiple of tick_size (row dropped) */
 #define BB_ERR_ROW_OP 0x400u     /* bb_run_agents_with_rows: a MODIFY row or a trader id >= 2^19 (row dropped) */
+#define BB_ERR_LOCKED 0x800u     /* deep engine: both sides would rest at one price level (trading disabled) */
 
 #define BB_OBS_L1 9u   /* StepEnvNumpy.level_1_data layout, rust/src/step_sim_numpy.rs:300-318 */
 #define BB_OBS_L2 45u  /* StepEnvNumpy.level_2_data layout, rust/src/step_sim_numpy.rs:351-368 */
@@ -94,6 +95,17 @@ typedef struct {
      * multiple of assets; market m shuffles with Xoroshiro128**(seed + env_id_base / assets + m).  0 or 1 => every
      * book is its own Env.  In-kernel agents on a multi-asset handle are defined with bb_set_agents_market. */
     uint32_t assets;
+    /* Deep-book engine (csrc/deep.cuh) for books with up to millions of resting orders, replayed instruction streams
+     * (bb_replay / bb_replay_device; BASELINE config C5): one CTA per book — a fetch warp that prefetches the records
+     * cancels / modifies name, a match warp working out of shared memory, a retire warp that streams the order-record and
+     * trade-log writes out — with array (chunked) price-time queues in HBM swept by a warp prefix sum.  Selected when
+     * deep_chunks > 0, together with the window fields above: win_levels <= 8192 price levels starting at win_lo,
+     * price_granule == 1; deep_chunks = 256-byte queue chunks per book (31 entries each; one per resting order in the
+     * worst case, ~ resting orders / 31 + win_levels + entries appended during a launch / 31 in practice).  Preconditions
+     * beyond the window: strictly increasing time between resting inserts (BB_ERR_TIME_ORDER) and one side per price
+     * level (BB_ERR_LOCKED: only reachable while trading is disabled).  Env mode, in-kernel agents and bb_load_book are
+     * not available on a deep handle (BB_EINVAL). */
+    uint32_t deep_chunks;
 } bb_config;
 
 /* One instruction, 32 bytes; replaces Event<OrderId> (crates/order_book/src/types.rs:229-249) plus

@@ -1,0 +1,206 @@
+"""GPU suite: the deep-book engine (csrc/deep.cuh — one CTA per book, fetch / match / retire warps, chunked array queues,
+warp prefix-sum sweeps) against the oracle, bit for bit, on replayed instruction streams.
+
+The engine's preconditions (prices inside the window, strictly increasing time, one side per level) hold on every stream
+here except where a test checks that a violation is FLAGGED."""
+import numpy as np
+import pytest
+
+from bourse_b200 import abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def compare_book(gpu_env, env_idx, ob, obs_gpu=None, obs_cpu=None):
+    go, co = gpu_env.orders_arrays(env_idx), ob.orders_arrays()
+    for k in co:
+        assert np.array_equal(co[k], go[k]), k
+    gt, ct = gpu_env.trades_arrays(env_idx), ob.trades_arrays()
+    for k in ct:
+        assert np.array_equal(ct[k], gt[k]), k
+    assert list(gpu_env.book_level_1(env_idx)) == ob._l1()
+    assert np.array_equal(gpu_env.book_level_2(env_idx), ob.level_2_data())
+    if obs_cpu is not None:
+        assert np.array_equal(obs_gpu, obs_cpu)
+
+
+def deep_env(core, n_envs, window, n, tick=1, chunks=None, obs_words=abi.OBS_L2, **kw):
+    return core.BatchedEnv(n_envs, 5, 0, tick, 1000, obs_words=obs_words, max_orders=n + 64, max_trades=4 * n + 64, max_steps=n // 32 + 64,
+                           max_queue=32, price_window=window, deep_chunks=chunks or (n // 8 + 2 * (window[1] - window[0]) + 64), **kw)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_c2_stream_bit_exact(core, oracle, seed):
+    """The C2 mix (55% limit, 5% market, 25% cancel, 15% modify; targets uniform over all issued ids, so many are dead)
+    with strictly increasing time.  (Zero-volume orders, SURVEY N5, rest and get swept in the sweep test below; a zero-volume
+    order that CROSSES rests inside the other side on the reference — that is the flagged `locked level` precondition.)"""
+    n = 20000
+    s = workloads.replay_stream(n, seed, tick_size=1, trading_windows=False)
+    ob = oracle.OrderBook(0, 1)
+    obs_cpu = ob.replay(s, obs_cap=n)
+    env = deep_env(core, 1, (896, 1152), n)
+    env.replay(s)
+    assert not env.env_errors().any()
+    compare_book(env, 0, ob, env.history(0), obs_cpu)
+    assert len(ob.get_trades()) > 1000
+
+
+def sweep_stream(n_rest, n_sweeps, seed, levels=6, mid=500, big=4000):
+    """Many small resting orders on a few levels, a third of them cancelled again (tombstones anywhere in the queues,
+    including at their heads), then large aggressive orders that each sweep many orders, chunks and levels."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for i in range(n_rest):
+        bid = rng.random() < 0.5
+        off = int(rng.integers(1, levels + 1))
+        rows.append((abi.OP_NEW | (abi.F_BID if bid else 0), 0, mid - off if bid else mid + off, int(rng.integers(0, 9))))
+        if rng.random() < 0.33:
+            rows.append((abi.OP_CANCEL, int(rng.integers(0, i + 1)), 0, 0))
+        if rng.random() < 0.05:
+            rows.append((abi.OP_MODIFY | abi.F_HAS_VOL, int(rng.integers(0, i + 1)), 0, int(rng.integers(0, 12))))
+    for _ in range(n_sweeps):
+        bid = rng.random() < 0.5
+        kind = rng.random()
+        vol = int(rng.integers(1, big))
+        if kind < 0.4:      # market order
+            rows.append((abi.OP_NEW | abi.F_MARKET | (abi.F_BID if bid else 0), 0, 0, vol))
+        elif kind < 0.8:    # limit order crossing some of the levels, remainder rests on the other side
+            rows.append((abi.OP_NEW | (abi.F_BID if bid else 0), 0, mid + int(rng.integers(-levels, levels + 1)), vol))
+        else:               # refill
+            for _k in range(40):
+                b2 = rng.random() < 0.5
+                off = int(rng.integers(1, levels + 1))
+                rows.append((abi.OP_NEW | (abi.F_BID if b2 else 0), 0, mid - off if b2 else mid + off, int(rng.integers(1, 9))))
+    out = np.zeros(len(rows), dtype=abi.INSTR_DTYPE)
+    for i, (of, oid, price, vol) in enumerate(rows):
+        out[i] = (i + 1, of | (abi.F_EMIT if i % 50 == 49 else 0), oid, price, vol, i % 97, 0)
+    return out
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_prefix_sum_sweeps_over_tombstoned_queues(core, oracle, seed):
+    s = sweep_stream(6000, 300, seed)
+    n = len(s)
+    ob = oracle.OrderBook(0, 1)
+    obs_cpu = ob.replay(s, obs_cap=n)
+    env = deep_env(core, 1, (448, 576), n)
+    env.replay(s)
+    assert not env.env_errors().any()
+    compare_book(env, 0, ob, env.history(0), obs_cpu)
+    tr = ob.trades_arrays()
+    # the sweeps really are multi-order: the busiest aggressor traded against more than a chunk's worth of passive orders
+    assert np.bincount(tr["active"].astype(np.int64)).max() > 62
+
+
+def test_c5_shaped_books_and_launch_splitting(core, oracle):
+    """Small C5-shaped books (pre-loaded depth, then the 15/15/60/10 mix), 6 books in one launch; a second launch continues
+    from the persisted book image and chunk pool."""
+    n_rest, n_steps, per_step = 20000, 8, 1500
+    streams = [workloads.c5_stream(n_rest, n_steps, per_step, seed=40 + i, mid_ticks=3000, depth_ticks=512) for i in range(6)]
+    n = len(streams[0])
+    env = deep_env(core, 6, (2432, 3584), n)
+    cut = n_rest + 3 * per_step + 17
+    env.replay(np.concatenate([x[:cut] for x in streams]), np.arange(7, dtype=np.uint64) * cut)
+    env.replay(np.concatenate([x[cut:] for x in streams]), np.arange(7, dtype=np.uint64) * (n - cut))
+    assert not env.env_errors().any()
+    for e in range(6):
+        ob = oracle.OrderBook(0, 1)
+        obs_cpu = ob.replay(streams[e], obs_cap=n_steps)
+        compare_book(env, e, ob, env.history(e), obs_cpu)
+        assert len(ob.get_trades()) > 2000
+    st = env.stats()
+    assert st["instructions"] == 6 * n and st["error_envs"] == 0
+
+
+def test_level1_history_and_tick_2(core, oracle):
+    n = 8000
+    s = workloads.replay_stream(n, 7, tick_size=2, trading_windows=False)
+    ob = oracle.OrderBook(0, 2)
+    obs_cpu = ob.replay(s, obs_cap=n)
+    env = deep_env(core, 1, (1792, 2304), n, tick=2, obs_words=abi.OBS_L1)
+    env.replay(s)
+    assert not env.env_errors().any()
+    compare_book(env, 0, ob)
+    assert np.array_equal(env.history(0), obs_cpu[:, :9])
+
+
+def test_preconditions_are_flagged_not_silent(core):
+    def stream(rows):
+        out = np.zeros(len(rows), dtype=abi.INSTR_DTYPE)
+        for i, (t, of, oid, price, vol) in enumerate(rows):
+            out[i] = (t, of, oid, price, vol, 0, 0)
+        return out
+
+    # a resting price outside the window
+    env = deep_env(core, 1, (100, 164), 64)
+    with pytest.raises(MemoryError):
+        env.replay(stream([(1, abi.OP_NEW | abi.F_BID, 0, 90, 5)]))
+    assert int(env.env_errors()[0]) & 0x04
+    # time standing still between two resting inserts at one level (the reference's equal-key collision, N1)
+    env = deep_env(core, 1, (100, 164), 64)
+    with pytest.raises(MemoryError):
+        env.replay(stream([(5, abi.OP_NEW | abi.F_BID, 0, 120, 5), (5, abi.OP_NEW | abi.F_BID, 0, 120, 6)]))
+    assert int(env.env_errors()[0]) & 0x100
+    # both sides resting at one price while trading is disabled
+    env = deep_env(core, 1, (100, 164), 64)
+    with pytest.raises(MemoryError):
+        env.replay(stream([(1, abi.OP_SET_TRADING, 0, 0, 0), (2, abi.OP_NEW | abi.F_BID, 0, 120, 5), (3, abi.OP_NEW, 0, 120, 6)]))
+    assert int(env.env_errors()[0]) & 0x800
+    # ... or a zero-volume order whose price crosses: it never matches and rests inside the other side (N5)
+    env = deep_env(core, 1, (100, 164), 64)
+    with pytest.raises(MemoryError):
+        env.replay(stream([(1, abi.OP_NEW, 0, 120, 6), (2, abi.OP_NEW | abi.F_BID, 0, 120, 0)]))
+    assert int(env.env_errors()[0]) & 0x800
+    # unknown id: the reference panics; later instructions still run
+    env = deep_env(core, 1, (100, 164), 64)
+    with pytest.raises(core.PanicException):
+        env.replay(stream([(1, abi.OP_NEW | abi.F_BID, 0, 120, 5), (2, abi.OP_CANCEL, 9, 0, 0), (3, abi.OP_NEW, 0, 130, 4)]))
+    assert list(env.book_level_1(0)[:2]) == [120, 130]
+    # Env mode and agents are refused
+    with pytest.raises(ValueError):
+        env.step()
+
+
+def test_trading_disabled_rests_and_rejects(core, oracle):
+    """N6 without locked levels: limit orders rest unmatched while trading is off, market orders are rejected; when trading
+    resumes a crossing order sweeps what rested."""
+    rows = [(1, abi.OP_SET_TRADING, 0, 0, 0), (2, abi.OP_NEW | abi.F_BID, 0, 130, 5), (3, abi.OP_NEW, 0, 120, 6),
+            (4, abi.OP_NEW | abi.F_MARKET, 0, 0, 3), (5, abi.OP_SET_TRADING, 0, 0, 1), (6, abi.OP_NEW, 0, 110, 20),
+            (7, abi.OP_NEW | abi.F_BID | abi.F_MARKET, 0, 0, 4), (8, abi.OP_MODIFY | abi.F_HAS_PRICE, 2, 140, 0)]
+    s = np.zeros(len(rows), dtype=abi.INSTR_DTYPE)
+    for i, (t, of, oid, price, vol) in enumerate(rows):
+        s[i] = (t, of | abi.F_EMIT, oid, price, vol, 3, 0)
+    ob = oracle.OrderBook(0, 1)
+    obs_cpu = ob.replay(s, obs_cap=len(s))
+    env = deep_env(core, 1, (100, 164), 64)
+    env.replay(s)
+    assert not env.env_errors().any()
+    compare_book(env, 0, ob, env.history(0), obs_cpu)
+
+
+def test_recently_written_orders_are_not_read_stale(core, oracle):
+    """Cancels / modifies that name an order created, filled or modified a handful of events earlier: the record the fetch
+    warp prefetched is older than the write still travelling through the retire ring, and must not be used."""
+    rng = np.random.default_rng(3)
+    rows, issued = [], 0
+    for i in range(12000):
+        u = rng.random()
+        if u < 0.5 or issued < 4:
+            bid = rng.random() < 0.5
+            rows.append((abi.OP_NEW | (abi.F_BID if bid else 0), 0, 200 + int(rng.integers(-6, 7)), int(rng.integers(1, 30))))
+            issued += 1
+        elif u < 0.75:
+            rows.append((abi.OP_CANCEL, issued - 1 - int(rng.integers(0, 4)), 0, 0))
+        else:
+            k = rng.integers(0, 3)
+            of = abi.OP_MODIFY | (abi.F_HAS_VOL if k != 1 else 0) | (abi.F_HAS_PRICE if k != 0 else 0)
+            rows.append((of, issued - 1 - int(rng.integers(0, 4)), 200 + int(rng.integers(-6, 7)), int(rng.integers(1, 30))))
+    s = np.zeros(len(rows), dtype=abi.INSTR_DTYPE)
+    for i, (of, oid, price, vol) in enumerate(rows):
+        s[i] = (i + 1, of | (abi.F_EMIT if i % 40 == 39 else 0), oid, price, vol, 1, 0)
+    ob = oracle.OrderBook(0, 1)
+    obs_cpu = ob.replay(s, obs_cap=len(s))
+    env = deep_env(core, 1, (160, 256), len(s))
+    env.replay(s)
+    assert not env.env_errors().any()
+    compare_book(env, 0, ob, env.history(0), obs_cpu)

@@ -133,11 +133,14 @@ def test_c4_shard_full_size(core, oracle):
     assert same == len(sample), f"only {same}/{len(sample)} sampled envs identical"
 
 
-def test_c5_deep_book_shard(core, oracle):
+@pytest.mark.parametrize("engine_kw", [dict(price_window=(7936, 12160), deep_chunks=98304), dict(pages_smem=192, pages_total=192)],
+                         ids=["deep_bench_config", "paged"])
+def test_c5_deep_book_shard(core, oracle, engine_kw):
     """Config C5, the per-GPU shard of the 8-GPU run: 128 books x 1,000,000 resting orders, then 100 steps x 10,000
     events with a 30% cancel/modify rate.  8 distinct streams are each replayed by 16 books: the 8 are compared bit for
     bit with the oracle (level-2 records of all 100 steps, trade log, full order table) and the other 120 books must be
-    identical to the book that shares their stream."""
+    identical to the book that shares their stream.  `deep_bench_config` is the engine and geometry bench.py times for C5
+    (k_deep: one CTA per book, csrc/deep.cuh); `paged` is the general engine with every price page resident."""
     import torch
 
     n_distinct, copies = 8, 16
@@ -151,7 +154,7 @@ def test_c5_deep_book_shard(core, oracle):
     del d_distinct
     d_off = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_per
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=1_800_000, max_trades=1 << 20,
-                          max_steps=n_steps, max_queue=32, pages_smem=192, pages_total=192)   # the bench's layout: all pages resident
+                          max_steps=n_steps, max_queue=32, **engine_kw)
     torch.cuda.synchronize()
     env.replay_device(d_all.data_ptr(), d_off.data_ptr())
     assert not env.env_errors().any()

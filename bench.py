@@ -511,6 +511,9 @@ def run_gpu_other(args):
         per_gpu = args.envs if args.envs != N_ENVS_PER_GPU else 8192
         base, n_envs = shard_range(per_gpu * world, world, rank)
         groups, obs, n_steps = workloads.c4_groups(), abi.OBS_L2, args.sim_steps
+        # The general (paged) engine: whenever a book's ask side is swept empty the MomentumAgent's mid price is ~2^31
+        # (orderbook.rs:272-276 with the empty-side sentinel) and its limit bids rest THERE, as the best bid — measured: every
+        # one of the 8192 envs leaves any dense window within the 1000 steps, so C4 cannot run on the dense-window engine
         env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=args.max_orders,
                               max_trades=args.max_trades, max_steps=n_steps, max_queue=128)
         env.set_agents(groups)

@@ -47,8 +47,8 @@ namespace bb {
 // scratch (not persisted), relative to the end of the image
 #define DP_NC 64u            // chunk cache entries (direct mapped by chunk id)
 #define DP_RB 2u             // event-ring depth in batches of 32 (one batch of look-ahead hides the record fetch)
-#define DP_RCAP 128u         // retire-ring entries (48 B each)
-#define DP_RENT 48u
+#define DP_RCAP 128u         // retire-ring entries (32 B each)
+#define DP_RENT 32u
 #define DP_DIRTY 2048u       // dirty-filter buckets
 struct DeepOff {             // byte offsets from the CTA's shared-memory base, filled by the host
     u32 bm, sm, lv, image_bytes;
@@ -220,11 +220,10 @@ __device__ __forceinline__ bool dp_ret_space(const DeepReg& r, DeepSt& s, u32 n)
     });
     return ok;
 }
-__device__ __forceinline__ void dp_ret_write(const DeepReg& r, u32 idx, uint4 a, uint4 b, u32 t_lo, u32 t_hi) {
+__device__ __forceinline__ void dp_ret_write(const DeepReg& r, u32 idx, uint4 a, uint4 b) {
     const u32 ea = r.ret + DP_RENT * (idx & (DP_RCAP - 1u));
     sts128(ea, a);
     sts128(ea + 16u, b);
-    sts64(ea + 32u, ((u64)t_hi << 32) | t_lo);
 }
 __device__ __forceinline__ void dp_mark_dirty(const DeepReg& r, u32 id, u32 upto) { sts(r.dirty + 4u * (id & (DP_DIRTY - 1u)), upto); }
 
@@ -333,8 +332,8 @@ __device__ __forceinline__ bool dp_match_serial(const DeepReg& r, DeepSt& s, u32
                 aborted = true;
                 return false;
             }
-            dp_ret_write(r, s.ret_tail, make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), pid, bprice, tv), make_uint4(id, pv, 0u, 0u),
-                         (u32)s.t, (u32)(s.t >> 32));
+            dp_ret_write(r, s.ret_tail, make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), pid, tv, pv),
+                         make_uint4((u32)s.t, (u32)(s.t >> 32), bprice, id));
             s.ret_tail += 1;
             dp_mark_dirty(r, pid, s.ret_tail);
             rem -= tv;
@@ -434,8 +433,8 @@ __device__ __forceinline__ u32 dp_sweep_warp(const DeepReg& r, DeepSt& s, u32 la
             const u32 tv = full ? pvol : rem - excl;
             const u32 pv = pvol - tv;
             // trade: side / price are the passive order's (orderbook.rs:853-862)
-            dp_ret_write(r, base + __popc(mr & ((1u << lane) - 1u)), make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), pid, r.win_lo + bq, tv),
-                         make_uint4(id, pv, 0u, 0u), (u32)t, (u32)(t >> 32));
+            dp_ret_write(r, base + __popc(mr & ((1u << lane) - 1u)), make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), pid, tv, pv),
+                         make_uint4((u32)t, (u32)(t >> 32), r.win_lo + bq, id));
             dp_mark_dirty(r, pid, base + nr);
             if (!full) {  // the partially filled order stays at the head of its level
                 sts(ca + 8u * lane + 4u, pv);

@@ -1024,7 +1024,12 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
 #define DT_SWEEP 2u
 #define DT_OBS 3u
 
-__device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, const bb_instr* ins, u32 n, u64 oh) {
+// pre-decoded flag bits the fetch warp adds to op_flags (above the public BB_F_* bits)
+#define DPF_MARKET (1u << 16)    // the order takes the market path: BB_F_MARKET, or a limit price equal to the sentinel (N3)
+#define DPF_CAP_ORDERS (1u << 17)  // a NEW row whose id would not fit the order table
+
+__device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, const bb_instr* ins, u32 n, u64 oh,
+                                              u32 next_id) {
     const u32 ctl = sb + o.ctl;
     const u32 nb = (n + 31u) >> 5;
     for (u32 b = 0; b < nb; ++b) {
@@ -1046,19 +1051,45 @@ __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o
         }
         // records written by retire entries below this index are performed and fenced: sampled BEFORE the loads below
         const u32 rf = ld_acq(ctl + CT_RET_DONE);
+        uint4 x = make_uint4(0, 0, 0, 0), y = make_uint4(0, 0, 0, 0);
         if (lane < cnt) {
-            const u64 w = lds64(ia + 32u * lane + 8u);  // op_flags | order_id << 32
-            const u32 op = (u32)w & BB_OP_MASK, id = (u32)(w >> 32);
-            if ((op == BB_OP_CANCEL || op == BB_OP_MODIFY) && id < p.geo.max_orders) {
-                u64 src = oh + (u64)id * ORD_STRIDE;
-                // a true data dependency on `rf` (always adds 0): the loads cannot be issued before rf was read
-                asm volatile("{\n\t.reg .u64 z;\n\tcvt.u64.u32 z, %1;\n\tshr.u64 z, z, 32;\n\tadd.u64 %0, %0, z;\n\t}" : "+l"(src) : "r"(rf));
-                const u32 ra = sb + o.ev_rec + 1024u * slot + 32u * lane;
-                cp_async16(ra, src);
-                cp_async16(ra + 16u, src + 16u);
-            }
+            x = lds128(ia + 32u * lane);
+            y = lds128(ia + 32u * lane + 16u);
         }
+        const u32 op = x.z & BB_OP_MASK;
+        // ---- everything about an event that does not depend on the book is settled here, one lane per event:
+        // NEW rows get their ids (create_order hands them out in stream order, orderbook.rs:356-396), the market
+        // sentinel price (types.rs:160-172, 213-225), and the write-once half of their record goes straight to HBM
+        const u32 new_mask = __ballot_sync(BB_FULL, op == BB_OP_NEW);
+        if (op == BB_OP_NEW) {
+            const u32 id = next_id + __popc(new_mask & ((1u << lane) - 1u));
+            const u32 side = (x.z >> 8) & 1u;
+            const u32 price = (x.z & BB_F_MARKET) ? (side ? 0xFFFFFFFFu : 0u) : y.x;
+            const bool market = side ? (price == 0xFFFFFFFFu) : (price == 0u);
+            u32 of = x.z | (market ? DPF_MARKET : 0u);
+            if (id >= p.geo.max_orders) {
+                of |= DPF_CAP_ORDERS;
+            } else {
+                const u64 ra = oh + (u64)id * ORD_STRIDE;
+                stg128(ra, price, y.y, 0u, BB_NIL);
+                stg128(ra + 16u, 0u, 0u, ST_NEW | (side ? META_BID : 0u), y.y);
+                stg128(ra + 32u, x.x, x.y, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                stg128(ra + 48u, y.z, 0u, 0u, 0u);
+            }
+            sts128(ia + 32u * lane, make_uint4(x.x, x.y, of, id));
+            sts(ia + 32u * lane + 16u, price);
+        } else if ((op == BB_OP_CANCEL || op == BB_OP_MODIFY) && x.w < p.geo.max_orders) {
+            u64 src = oh + (u64)x.w * ORD_STRIDE;
+            // a true data dependency on `rf` (always adds 0): the loads cannot be issued before rf was read
+            asm volatile("{\n\t.reg .u64 z;\n\tcvt.u64.u32 z, %1;\n\tshr.u64 z, z, 32;\n\tadd.u64 %0, %0, z;\n\t}" : "+l"(src) : "r"(rf));
+            const u32 ra = sb + o.ev_rec + 1024u * slot + 32u * lane;
+            cp_async16(ra, src);
+            cp_async16(ra + 16u, src + 16u);
+        }
+        next_id += __popc(new_mask);
+        if (next_id > p.geo.max_orders) next_id = p.geo.max_orders;  // (later NEW rows fail the same way)
         cp_async_wait_all();
+        if (new_mask) __threadfence();  // the record halves are in place before anything can name these ids
         __syncwarp();
         if (lane == 0u) {
             sts(sb + o.ev_rf + 4u * slot, rf);
@@ -1080,47 +1111,48 @@ __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& 
         });
         if (!ok || (tail == head && fin)) break;
         const u32 n = min(32u, tail - head);
+        // entry: a = {kind | side << 8 | status << 12 | filled << 16, order id, ., .}, b = {t lo, t hi, ., .}
         uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-        u64 t = 0;
         if (lane < n) {
             const u32 ea = sb + o.ret + DP_RENT * ((head + lane) & (DP_RCAP - 1u));
             a = lds128(ea);
             b = lds128(ea + 16u);
-            t = lds64(ea + 32u);
         }
-        const u32 kind = a.x & 0xFFu, side_bit = ((a.x >> 8) & 1u) ? META_BID : 0u;
+        const u64 t = ((u64)b.y << 32) | b.x;
+        const u32 kind = a.x & 0xFFu, side_bit = ((a.x >> 8) & 1u) ? META_BID : 0u, status = (a.x >> 12) & 7u;
         const u32 fm = __ballot_sync(BB_FULL, kind == RK_FILL);
         // entries of one order are applied in ring order: lanes naming the same id take turns
         const u32 grp = __match_any_sync(BB_FULL, lane < n ? a.y : (0xFFFFFF00u | lane));
         const u32 rank = __popc(grp & ((1u << lane) - 1u));
         const u32 rounds = __reduce_max_sync(BB_FULL, rank) + 1u;
         const u64 ra = oh + (u64)a.y * ORD_STRIDE;
-        if (kind == RK_FILL) {
+        if (kind == RK_FILL) {  // {., passive id, traded vol, passive vol left} {t, price, active id}
             const u32 ti = n_tr + __popc(fm & ((1u << lane) - 1u));
             if (ti < p.geo.max_trades) {
                 const u64 ta = tr + (u64)ti * 32u;
-                stg128_cs(ta, (u32)t, (u32)(t >> 32), a.z, a.w);
-                stg128_cs(ta + 16u, b.x, a.y, (a.x >> 8) & 1u, 0u);
+                stg128_cs(ta, b.x, b.y, b.z, a.z);
+                stg128_cs(ta + 16u, b.w, a.y, (a.x >> 8) & 1u, 0u);
             } else if (p.geo.max_trades) {
                 err |= ERR_CAP_TRADES;
             }
         }
         for (u32 r = 0; r < rounds; ++r) {
             if (lane < n && rank == r) {
-                if (kind == RK_NEW) {
-                    const u32 status = (a.x >> 12) & 7u;
-                    const u64 kt = status == ST_ACTIVE ? t : 0ULL, end = status == ST_ACTIVE ? ~0ULL : t;
-                    stg128(ra, a.z, a.w, b.z, BB_NIL);
-                    stg128(ra + 16u, (u32)kt, (u32)(kt >> 32), status | side_bit, b.x);
-                    stg128(ra + 32u, (u32)t, (u32)(t >> 32), (u32)end, (u32)(end >> 32));
-                    stg128(ra + 48u, b.y, 0u, 0u, 0u);
-                } else if (kind == RK_REPLACE) {
-                    const u32 status = (a.x >> 12) & 7u;
-                    stg128(ra, a.z, a.w, b.x, BB_NIL);
+                if (kind == RK_NEW) {  // {., id, vol left, queue position}: the fetch warp wrote the rest of the record
+                    stg32(ra + OH_VOL, a.z);
+                    stg32(ra + OH_META, status | side_bit);
+                    if (status == ST_ACTIVE) {
+                        stg32(ra + OH_NEXT, a.w);
+                        stg64(ra + OH_KEYT, t);
+                    } else {
+                        stg64(ra + OC_END, t);
+                    }
+                } else if (kind == RK_REPLACE) {  // {., id, vol left, queue position} {t, new price}
+                    stg128(ra, b.z, a.z, a.w, BB_NIL);
                     stg32(ra + OH_META, status | side_bit);
                     stg64(ra + (status == ST_FILLED ? OC_END : OH_KEYT), t);
                 } else if (kind == RK_FILL) {
-                    stg32(ra + OH_VOL, b.y);
+                    stg32(ra + OH_VOL, a.w);
                     if (a.x & 0x10000u) {
                         stg32(ra + OH_META, ST_FILLED | side_bit);
                         stg64(ra + OC_END, t);
@@ -1128,8 +1160,8 @@ __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& 
                 } else if (kind == RK_CANCEL) {
                     stg32(ra + OH_META, ST_CANCELLED | side_bit);
                     stg64(ra + OC_END, t);
-                } else if (kind == RK_REDUCE) {
-                    stg32(ra + OH_VOL, a.w);
+                } else if (kind == RK_REDUCE) {  // {., id, new vol}
+                    stg32(ra + OH_VOL, a.z);
                 }
             }
             __syncwarp();
@@ -1179,7 +1211,7 @@ __global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams 
     const u32 n_tr0 = min((u32)lds64(sb + HDR_NTRADES_TOTAL), p.geo.max_trades);
 
     if (warp == 1u) {
-        dp_fetch_warp(p, o, sb, lane, ins, n, oh);
+        dp_fetch_warp(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
     } else if (warp == 2u) {
         dp_retire_warp(p, o, sb, lane, oh, tr, n_tr0);
     } else {
@@ -1221,7 +1253,7 @@ __global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams 
         const u32 n_orders0 = s.n_orders, n_trades0 = s.n_trades, trade_vol0 = s.trade_vol;
         // event context that survives a trip through the warp-cooperative handlers (lane 0 only)
         u32 ev_i = 0u, rf = 0u, published = 0u;
-        u32 c_kind = 0u, c_side = 0u, c_price = 0u, c_vol = 0u, c_rem = 0u, c_id = 0u, c_trader = 0u, c_emit = 0u;
+        u32 c_kind = 0u, c_side = 0u, c_price = 0u, c_vol = 0u, c_rem = 0u, c_id = 0u, c_emit = 0u;
         bool c_market = false, aborted = false;
         // after matching: rest or finish the order, queue its record write, close the event (lane 0)
         auto finish = [&]() {
@@ -1234,9 +1266,8 @@ __global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams 
                 aborted = true;
                 return;
             }
-            // RK_NEW: b = {start_vol, trader, pos}; RK_REPLACE: b = {pos}
-            dp_ret_write(r, s.ret_tail, make_uint4(c_kind | (c_side << 8) | (status << 12), c_id, c_price, c_rem),
-                         make_uint4(c_kind == RK_NEW ? c_vol : pos, c_trader, pos, 0u), (u32)s.t, (u32)(s.t >> 32));
+            dp_ret_write(r, s.ret_tail, make_uint4(c_kind | (c_side << 8) | (status << 12), c_id, c_rem, pos),
+                         make_uint4((u32)s.t, (u32)(s.t >> 32), c_price, 0u));
             s.ret_tail += 1;
             dp_mark_dirty(r, c_id, s.ret_tail);
             s.d_applied += 1;
@@ -1271,19 +1302,18 @@ __global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams 
                     const u32 op = x.z & BB_OP_MASK;
                     c_emit = x.z & BB_F_EMIT;
                     bool to_match = false;
-                    if (op == BB_OP_NEW) {
+                    if (op == BB_OP_NEW) {  // (id, sentinel price and the market flag were settled by the fetch warp)
                         s.d_instr += 1;
-                        c_id = s.n_orders;
-                        if (c_id >= r.max_orders) {
+                        if (x.z & DPF_CAP_ORDERS) {
                             s.err |= ERR_CAP_ORDERS;
                         } else {
+                            c_id = x.w;
                             s.n_orders = c_id + 1u;
                             c_kind = RK_NEW;
                             c_side = (x.z >> 8) & 1u;  // BB_F_BID
-                            c_price = (x.z & BB_F_MARKET) ? (c_side ? 0xFFFFFFFFu : 0u) : y.x;  // types.rs:160-172, 213-225
-                            c_market = c_side ? (c_price == 0xFFFFFFFFu) : (c_price == 0u);       // N3
+                            c_price = y.x;
+                            c_market = (x.z & DPF_MARKET) != 0u;
                             c_vol = c_rem = y.y;
-                            c_trader = y.z;
                             to_match = true;
                         }
                     } else if (op == BB_OP_CANCEL || op == BB_OP_MODIFY) {
@@ -1317,7 +1347,7 @@ __global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams 
                                 if (op == BB_OP_CANCEL) {
                                     dp_remove(r, s, side, a.x, a.y, a.z);
                                     if (!dp_ret_space(r, s, 1u)) { aborted = true; break; }
-                                    dp_ret_write(r, s.ret_tail, make_uint4(RK_CANCEL | (side << 8), id, 0u, 0u), make_uint4(0, 0, 0, 0), x.x, x.y);
+                                    dp_ret_write(r, s.ret_tail, make_uint4(RK_CANCEL | (side << 8), id, 0u, 0u), make_uint4(x.x, x.y, 0u, 0u));
                                     s.ret_tail += 1;
                                     dp_mark_dirty(r, id, s.ret_tail);
                                     s.d_applied += 1;
@@ -1331,7 +1361,7 @@ __global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams 
                                     }
                                     dp_add_side(s, side, y.y - a.y);
                                     if (!dp_ret_space(r, s, 1u)) { aborted = true; break; }
-                                    dp_ret_write(r, s.ret_tail, make_uint4(RK_REDUCE, id, 0u, y.y), make_uint4(0, 0, 0, 0), x.x, x.y);
+                                    dp_ret_write(r, s.ret_tail, make_uint4(RK_REDUCE, id, y.y, 0u), make_uint4(x.x, x.y, 0u, 0u));
                                     s.ret_tail += 1;
                                     dp_mark_dirty(r, id, s.ret_tail);
                                     s.d_applied += 1;
@@ -1342,7 +1372,6 @@ __global__ void __launch_bounds__(96, 2) k_deep(const __grid_constant__ KParams 
                                     c_side = side;
                                     c_price = has_p ? y.x : a.x;
                                     c_vol = c_rem = has_v ? y.y : a.y;
-                                    c_trader = 0u;
                                     c_market = false;
                                     to_match = true;
                                 }

@@ -65,7 +65,7 @@ def main():
             groups = workloads.c3_groups() if wl == "c3" else workloads.c4_groups()
             kw = {}
             if eng == "dense":
-                kw = dict(price_window=(20, 180), live_cap=128) if wl == "c3" else workloads.c4_dense_kw()
+                kw = dict(price_window=(20, 180), live_cap=128) if wl == "c3" else {}
             env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1 if wl == "c3" else abi.OBS_L2, max_orders=8192,
                                   max_trades=8192, max_steps=n_steps, max_queue=128 if wl == "c3" else 256, **kw)
             env.set_agents(groups)

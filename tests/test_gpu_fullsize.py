@@ -101,7 +101,8 @@ def test_c3_full_size(core, oracle, engine_kw):
 def test_c4_shard_full_size(core, oracle):
     """Config C4, one GPU's shard: 8192 envs x (40+40 RandomAgents + 20-trader MomentumAgent) x 1000 env-steps with a
     level-2 (10-level, 45-word) observation per env-step.  Every sampled env must be bit-identical to the oracle
-    (see the note on f64 tanh/exp/log/cos in test_gpu_agents)."""
+    (see the note on f64 tanh/exp/log/cos in test_gpu_agents).  The general (paged) engine, as in bench.py: a one-sided book puts
+    the MomentumAgent's mid at ~2^31 and its bids rest there, so no dense window holds this population."""
     n_envs, n_steps, seed = 8192, 1000, 7
     groups = workloads.c4_groups()
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, env_id_base=3 * 8192, max_orders=65536,

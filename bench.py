@@ -34,7 +34,6 @@ UNIT = "orders/s"
 N_ENVS_PER_GPU = 4096
 N_SIM_STEPS = 1000
 SEED = 101
-CPU_SAMPLE_ENVS = 1024
 
 
 def measured_peak_gbs():
@@ -125,7 +124,7 @@ def run_reference(args):
     cores = host_cores()
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
-        r = cpu_baseline(CPU_SAMPLE_ENVS, N_SIM_STEPS, cores)
+        r = cpu_baseline(N_ENVS_PER_GPU, N_SIM_STEPS, cores)   # the arm's whole config: all 4096 envs x 1000 env-steps per step
         if i >= args.warmup:
             vals.append(r)
             secs.append(r["seconds"])
@@ -136,7 +135,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args.gpus, sample=f"each step = {CPU_SAMPLE_ENVS} envs x {N_SIM_STEPS} env-steps (bounded sample)"),
+        "config": workload_config(args.gpus, sample=f"each step = all {N_ENVS_PER_GPU} envs x {N_SIM_STEPS} env-steps of one GPU's shard, on the host cores; "
+                                                     "the CPU arm is the oracle's C++ restatement (std::map where the reference uses BTreeMap), not the Rust build"),
         "env_steps_per_sec": sum(r["env_steps_per_sec"] * r["seconds"] for r in vals) / tot_s,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": vals[-1]["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -165,29 +165,13 @@ def run_gpu(args):
 
     from bourse_b200 import abi, core, workloads
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: bourse_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    n_envs = args.envs
-    groups = workloads.c3_groups()
     # A dedicated (non-default) torch stream: the library launches on exactly this stream, so the CUDA events below
     # are recorded on the stream the kernels run on.  (Passing the default stream's handle, 0, would make the library
     # fall back to its own non-blocking stream, which events on the legacy default stream do not order against.)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
+    ctx = Ctx()
+    rank, world, local, stream, flush, barrier = ctx.rank, ctx.world, ctx.local, ctx.stream, ctx.flush, ctx.barrier
+    n_envs = args.envs
+    groups = workloads.c3_groups()
     from bourse_b200.sharding import shard_range
     env_base, n_envs = shard_range(args.envs * world, world, rank)   # weak scaling: args.envs per GPU
     # engine: "dense" = dense tick-indexed ladder + shared-memory order slots (csrc/dense.cuh): C3's resting prices lie
@@ -198,7 +182,6 @@ def run_gpu(args):
                           max_orders=args.max_orders, max_trades=args.max_trades, max_steps=args.sim_steps, max_queue=128, **eng_kw)
     env.set_agents(groups)
     env.set_stream(stream.cuda_stream)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     n_steps = args.sim_steps
 
     def one_pass():
@@ -265,15 +248,9 @@ def run_gpu(args):
         alg_bytes = workloads.algorithmic_bytes(stats, abi.OBS_L1)          # this rank's k_sim launch
         k_ms = sum(kern_ms) / len(kern_ms)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "k_sim_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic = profile_traffic("c3")
         cores = host_cores()
-        cpu = cpu_baseline(CPU_SAMPLE_ENVS, N_SIM_STEPS, cores) if world == 1 and not args.no_cpu else None
+        cpu = cpu_baseline(N_ENVS_PER_GPU, N_SIM_STEPS, cores) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,10 +269,23 @@ def run_gpu(args):
         }
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    # ---- BASELINE configs 4 and 5 beside the headline (same launch, same ranks): C4 at 8192 envs per GPU (65,536 on 8 GPUs),
+    # C5 with the 1024 books of the config split over the ranks (capped at 512 per GPU: 1024 deep books do not fit 180 GB)
+    secondary = {}
+    if not args.no_secondary:
+        env.close()
+        del hist_host
+        torch.cuda.empty_cache()
+        c4 = measure_c4(ctx, 8192, N_SIM_STEPS, 3, 3, args.max_orders, args.max_trades, False)
+        c5_books = min(512, max(1, 1024 // world))
+        c5 = measure_c5(ctx, c5_books, 2, 3, "deep", 10, world == 1 and not args.no_cpu)
+        c5["scaling"] = "strong (1024 books over the ranks)" if c5_books * world == 1024 else f"{c5_books * world} of the 1024 books (one GPU holds at most 512)"
+        secondary = {"c4": c4, "c5": c5}
+    if rank == 0:
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.finish()
     return 0
 
 
@@ -430,47 +420,248 @@ def run_gym(args):
     return 0
 
 
+class Ctx:
+    """Per-rank CUDA context shared by the workload runners: one torch stream the library launches on (so that CUDA events
+    recorded on it bracket the kernels), the L2-flush buffer, rank / world, and the max-over-ranks barrier."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: bourse_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1 and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        self.flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def events(self, n):
+        return [(self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def roofline_block(alg_bytes: float, k_ms: float, kernel: str, traffic=None) -> dict:
+    peak, peak_src = measured_peak_gbs()
+    ach = alg_bytes / (k_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "kernel": kernel,
+            "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+
+
+def measure_c4(ctx: Ctx, per_gpu: int, n_steps: int, steps: int, warmup: int, max_orders: int, max_trades: int, with_cpu: bool) -> dict:
+    """BASELINE config C4, one GPU's shard per rank: `per_gpu` envs x (40+40 RandomAgents + 20-trader MomentumAgent) x
+    n_steps env-steps, level-2 (45-word) record per env-step.  The general (paged) engine: whenever a book's ask side is
+    swept empty the MomentumAgent's mid price is ~2^31 (orderbook.rs:272-276 with the empty-side sentinel) and its limit
+    bids rest THERE, as the best bid — measured: every one of the 8192 envs leaves any dense window within 1000 steps."""
+    from bourse_b200 import abi, core, workloads
+    from bourse_b200.sharding import gather_stats, shard_range
+
+    base, n_envs = shard_range(per_gpu * ctx.world, ctx.world, ctx.rank)
+    groups, obs = workloads.c4_groups(), abi.OBS_L2
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=ctx.local, env_id_base=base, obs_words=obs, max_orders=max_orders,
+                          max_trades=max_trades, max_steps=n_steps, max_queue=128)
+    env.set_agents(groups)
+    env.set_stream(ctx.stream.cuda_stream)
+    ev = ctx.events(steps)
+    for i in range(warmup + steps):
+        if i == warmup:
+            ctx.barrier()
+        env.reset()
+        if i >= warmup:
+            ev[i - warmup][0].record(ctx.stream)
+        env.run_agents(n_steps, 7, sync=False)
+        if i >= warmup:
+            ev[i - warmup][1].record(ctx.stream)
+        ctx.flush.fill_(1)
+    ctx.barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    stats = env.stats()
+    if stats["error_envs"]:
+        raise SystemExit(f"C4: device flagged errors in {stats['error_envs']} envs")
+    agg = gather_stats(stats, sum(ms), stats["l1_checksum"], device="cuda")
+    k_ms = sum(ms) / len(ms)
+    out = {"workload": f"C4 shard: {per_gpu} envs/GPU x (40+40 RandomAgents + 20-trader MomentumAgent) x {n_steps} env-steps, "
+                       "level-2 (45 x u32) record per env-step, paged engine",
+           "value": agg["instructions"] * steps / (agg["elapsed_ms_max"] * 1e-3), "unit": UNIT, "ms_per_step": agg["elapsed_ms_max"] / steps,
+           "env_steps_per_sec": agg["env_steps"] * steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
+           "trades_per_pass": agg["trades"], "n_envs_total": per_gpu * ctx.world, "l1_checksums": agg["l1_checksums"],
+           "roofline": roofline_block(workloads.algorithmic_bytes(stats, obs), k_ms, "k_sim<FAST,MOM>", profile_traffic("c4"))}
+    if with_cpu and ctx.rank == 0:
+        from oracle import oracle as orc
+        orc.build()
+        cores = host_cores()
+        r = orc.bench_agents(64 * cores, cores, n_steps, 7, groups, keyed=False, start_time=0, tick_size=1, step_size=1_000_000)
+        out["cpu_baseline"] = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{64 * cores} envs x {n_steps} env-steps of the C4 population, one env per core at a time ({r['seconds']:.2f} s)"}
+    env.close()
+    return out
+
+
+C5_WINDOW, C5_CHUNKS = (7936, 12160), 98304
+
+
+def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pages_smem: int, with_cpu: bool) -> dict:
+    """BASELINE config C5, one GPU's shard per rank: `per_gpu` books x 1,000,000 resting orders (pre-loaded, untimed), then
+    100 steps x 10,000 events per book with a 30% cancel/modify rate, replayed from device memory (timed)."""
+    import torch
+    from bourse_b200 import abi, core, workloads
+    from bourse_b200.sharding import gather_stats, shard_range
+
+    base, n_envs = shard_range(per_gpu * ctx.world, ctx.world, ctx.rank)
+    n_rest, n_steps, per_step, n_distinct = 1_000_000, 100, 10_000, 8
+    obs = abi.OBS_L2
+    streams = [workloads.c5_stream(n_rest, n_steps, per_step, seed=100 + i) for i in range(n_distinct)]
+    dev = torch.device("cuda", ctx.local)
+    reps = (n_envs + n_distinct - 1) // n_distinct
+    d1 = torch.from_numpy(np.concatenate([x[:n_rest] for x in streams]).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_envs].contiguous()
+    d2 = torch.from_numpy(np.concatenate([x[n_rest:] for x in streams]).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_envs].contiguous()
+    o1 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_rest
+    o2 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
+    if engine == "deep":
+        # deep-book engine (csrc/deep.cuh): one CTA per book; window = every price the stream can rest at (10000 +- 2048,
+        # rounded out to 32-level words), 98304 queue chunks of 31 entries per book
+        eng_kw = dict(price_window=C5_WINDOW, deep_chunks=C5_CHUNKS)
+        eng_name = "deep-book engine (one CTA per book: fetch / match / retire warps, chunked array queues in HBM, prefix-sum sweeps)"
+    else:
+        # Price pages resident in shared memory: as many as let the whole shard stay resident in ONE wave (a book's image is
+        # ~0.5 KB per page; 148 SMs x 227 KB).  128-296 books per GPU: all 192 pages (2 books per CTA); 512: ~100 pages.
+        books_per_sm = -(-n_envs // 148)
+        books_per_sm = 1 if books_per_sm <= 1 else 2 if books_per_sm <= 2 else 4 * (-(-books_per_sm // 4))
+        c5_pages = pages_smem if pages_smem != 10 else max(10, min(192, (227 * 1024 // books_per_sm - 8192) // 512))
+        eng_kw = dict(pages_smem=c5_pages, pages_total=192)
+        eng_name = f"paged engine, {c5_pages} of 192 price pages per book resident in shared memory"
+    env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=ctx.local, env_id_base=base, obs_words=obs, max_orders=1_750_000,
+                          max_trades=1 << 20, max_steps=n_steps, max_queue=32, **eng_kw)
+    env.set_stream(ctx.stream.cuda_stream)
+    torch.cuda.synchronize()
+    ev = ctx.events(steps)
+    pre_stats = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            ctx.barrier()
+        env.reset()
+        env.replay_device(d1.data_ptr(), o1.data_ptr())      # untimed: build the 1M-order book
+        if pre_stats is None:
+            env.synchronize(); pre_stats = env.stats()
+        if i >= warmup:
+            ev[i - warmup][0].record(ctx.stream)
+        env.replay_device(d2.data_ptr(), o2.data_ptr())
+        if i >= warmup:
+            ev[i - warmup][1].record(ctx.stream)
+        ctx.flush.fill_(1)
+    ctx.barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    stats = env.stats()
+    if stats["error_envs"]:
+        raise SystemExit(f"C5: device flagged errors in {stats['error_envs']} envs")
+    # only the timed phase counts
+    stats = {k: (stats[k] - pre_stats[k] if k in ("instructions", "orders_created", "trades", "traded_volume", "transitions", "env_steps") else stats[k]) for k in stats}
+    stats["env_steps"] = n_envs * n_steps
+    agg = gather_stats(stats, sum(ms), stats["l1_checksum"], device="cuda")
+    k_ms = sum(ms) / len(ms)
+    out = {"workload": f"C5 shard: {per_gpu} books/GPU x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 events per "
+                       "book (15% cancel, 15% modify, 60% limit within +-32 ticks, 10% market), level-2 record per step, replayed from "
+                       "device memory; " + eng_name,
+           "value": agg["instructions"] * steps / (agg["elapsed_ms_max"] * 1e-3), "unit": UNIT, "ms_per_step": agg["elapsed_ms_max"] / steps,
+           # (one CTA per book, two resident per SM: up to 296 books run in one wave and the pass time IS a book's time)
+           **({"us_per_event_per_book": 1e3 * k_ms / (n_steps * per_step)} if n_envs <= 296 and engine == "deep" else {}),
+           "env_steps_per_sec": agg["env_steps"] * steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
+           "trades_per_pass": agg["trades"], "n_books_total": per_gpu * ctx.world, "l1_checksums": agg["l1_checksums"][:1],
+           "roofline": roofline_block(workloads.algorithmic_bytes(stats, obs, n_envs * n_steps * per_step), k_ms,
+                                      "k_deep" if engine == "deep" else "k_apply<REPLAY,PAGED_RES>", profile_traffic("c5_" + engine))}
+    if with_cpu and ctx.rank == 0:
+        from oracle import oracle as orc
+        orc.build()
+        cores = host_cores()
+        r = orc.bench_replay_suffix(cores, 1, streams[0], n_rest)
+        out["cpu_baseline"] = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+                               "us_per_event_per_book": 1e6 * r["seconds"] / (n_steps * per_step),
+                               "sample": f"{cores} books (one per core), each pre-loaded with {n_rest} resting orders (untimed) and then fed the "
+                                         f"{n_steps * per_step} events of one C5 stream, all threads together ({r['seconds']:.2f} s)"}
+    env.close()
+    del d1, d2
+    torch.cuda.empty_cache()
+    return out
+
+
+def profile_traffic(key: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full` capture per kernel, committed
+    under profiles/): ncu cannot run inside a timed bench, so the figure comes from profiles/kernel_traffic.json."""
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        return json.load(open(tp))[key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def secondary_line(args, ctx, res: dict) -> dict:
+    """A full JSON line for a secondary workload (--workload c4 | c5) from a measure_* result."""
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": {"workload": res["workload"]}}
+    line.update({k: v for k, v in res.items() if k not in ("workload", "value", "unit", "ms_per_step")})
+    return line
+
+
 def run_gpu_other(args):
-    """Secondary workloads of BASELINE.json (not the headline line): --workload c4 | c5, one GPU's shard per rank.
-    c4: 8192 envs x (40+40 RandomAgents + 20-trader MomentumAgent) x 1000 env-steps, level-2 record per env-step.
-    c5: 128 books x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 events per book with a
-        30% cancel/modify rate, replayed from device memory (timed)."""
+    """Secondary workloads of BASELINE.json (not the headline line): --workload c1 | c2 | c4 | c5 | market, one GPU's shard
+    per rank."""
     import torch
     import torch.distributed as dist
 
     from bourse_b200 import abi, core, workloads
     from bourse_b200.sharding import gather_stats, shard_range
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if args.workload == "c1":
         return run_c1(args)
+    ctx = Ctx()
+    rank, world, local, stream, flush, barrier = ctx.rank, ctx.world, ctx.local, ctx.stream, ctx.flush, ctx.barrier
+    ev = ctx.events(args.steps)
+    if args.workload == "c4":
+        res = measure_c4(ctx, args.envs if args.envs != N_ENVS_PER_GPU else 8192, args.sim_steps, args.steps, args.warmup, args.max_orders,
+                         args.max_trades, world == 1 and not args.no_cpu)
+        if rank == 0:
+            print(json.dumps(secondary_line(args, ctx, res)))
+        ctx.finish()
+        return 0
+    if args.workload == "c5":
+        res = measure_c5(ctx, args.envs if args.envs != N_ENVS_PER_GPU else 128, args.steps, args.warmup, args.engine, args.pages_smem,
+                         world == 1 and not args.no_cpu)
+        if rank == 0:
+            print(json.dumps(secondary_line(args, ctx, res)))
+        ctx.finish()
+        return 0
     if args.workload == "c2":
         # C2: replayed place/cancel/modify stream (55/5/25/15 % limit/market/cancel/modify) of 10^6 events into ONE book
         # (--envs 1, the config as stated: a single sequential dependency chain) or into --envs books at once
         n_books = args.envs if args.envs != N_ENVS_PER_GPU else 1
         n_ev, n_distinct = 1_000_000, min(8, n_books)
-        streams = [workloads.replay_stream(n_ev, s, tick_size=1) for s in range(n_distinct)]
+        deep = args.engine == "deep"   # (the deep engine's one-side-per-level precondition excludes the trading-off windows)
+        streams = [workloads.replay_stream(n_ev, s, tick_size=1, trading_windows=not deep) for s in range(n_distinct)]
         dev = torch.device("cuda", local)
         reps = (n_books + n_distinct - 1) // n_distinct
         d = torch.from_numpy(np.concatenate(streams).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_books].contiguous()
         off = torch.arange(0, n_books + 1, dtype=torch.int64, device=dev) * n_ev
         n_emit = int(((streams[0]["op_flags"] & abi.F_EMIT) != 0).sum())
+        eng_kw = dict(price_window=(896, 1152), deep_chunks=65536) if deep else dict(pages_smem=args.pages_smem if args.pages_smem != 10 else 64, pages_total=64)
         env = core.BatchedEnv(n_books, 0, 0, 1, 100_000, device=local, obs_words=abi.OBS_L2, max_orders=1 << 20, max_trades=1 << 20,
-                              max_steps=n_emit + 8, max_queue=32, pages_smem=args.pages_smem if args.pages_smem != 10 else 64, pages_total=64)
+                              max_steps=n_emit + 8, max_queue=32, **eng_kw)
         env.set_stream(stream.cuda_stream)
         torch.cuda.synchronize()
         for i in range(args.warmup + args.steps):
@@ -500,38 +691,15 @@ def run_gpu_other(args):
             "metric": METRIC, "value": stats["instructions"] / (k_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"C2: replayed stream of {n_ev} instructions (55% limit, 5% market, 25% cancel, 15% modify; cancel/modify "
-                                   f"targets uniform over all issued ids) into each of {n_books} book(s), level-2 record every 64 events, paged engine"},
+                                   f"targets uniform over all issued ids{'' if not deep else '; no trading-off windows'}) into each of {n_books} book(s), level-2 record every 64 events, "
+                                   f"{'deep-book engine (one CTA per book)' if deep else 'paged engine'}"},
             "orders_per_pass": stats["instructions"], "trades_per_pass": stats["trades"],
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
-                         "traffic": None, "kernel": "k_apply", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+                         "traffic": None, "kernel": "k_deep" if deep else "k_apply", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             "cpu_baseline": {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": min(n_books, cores), "kind": "port",
                              "sample": f"the same stream into {min(n_books, cores)} book(s), one per core ({r['seconds']:.2f} s; counts every row incl. no-ops)"}}))
         return 0
-    if args.workload == "c4":
-        per_gpu = args.envs if args.envs != N_ENVS_PER_GPU else 8192
-        base, n_envs = shard_range(per_gpu * world, world, rank)
-        groups, obs, n_steps = workloads.c4_groups(), abi.OBS_L2, args.sim_steps
-        # The general (paged) engine: whenever a book's ask side is swept empty the MomentumAgent's mid price is ~2^31
-        # (orderbook.rs:272-276 with the empty-side sentinel) and its limit bids rest THERE, as the best bid — measured: every
-        # one of the 8192 envs leaves any dense window within the 1000 steps, so C4 cannot run on the dense-window engine
-        env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=args.max_orders,
-                              max_trades=args.max_trades, max_steps=n_steps, max_queue=128)
-        env.set_agents(groups)
-        env.set_stream(stream.cuda_stream)
-        for i in range(args.warmup + args.steps):
-            if i == args.warmup:
-                barrier()
-            env.reset()
-            if i >= args.warmup:
-                ev[i - args.warmup][0].record(stream)
-            env.run_agents(n_steps, 7, sync=False)
-            if i >= args.warmup:
-                ev[i - args.warmup][1].record(stream)
-            flush.fill_(1)
-        ext = 0
-        name = (f"C4 shard: {per_gpu} envs/GPU x (40+40 RandomAgents + 20-trader MomentumAgent) x {n_steps} env-steps, "
-                "level-2 (45 x u32) record per env-step, paged engine")
-    elif args.workload == "market":
+    if args.workload == "market":
         # the reference's multi-asset example (crates/step_sim/examples/multi_asset/main.rs:12-22) —
         # MarketEnv::<2> with 4 RandomMarketAgents groups (100 agents per asset), market_sim_runner — batched over
         # `--envs / 2` lockstep markets per GPU; one level-2 record per asset and step (MarketEnv keeps Level2DataRecords)
@@ -558,60 +726,11 @@ def run_gpu_other(args):
         ext = 0
         name = (f"multi-asset example: {per_gpu // n_assets} markets/GPU x 2 assets x (50+50) RandomMarketAgents per asset x {n_steps} "
                 f"steps (market_sim_runner), level-2 record per asset and step, {args.engine} engine")
-    else:
-        per_gpu = args.envs if args.envs != N_ENVS_PER_GPU else 128
-        base, n_envs = shard_range(per_gpu * world, world, rank)
-        n_rest, n_steps, per_step, n_distinct = 1_000_000, 100, 10_000, 8
-        obs = abi.OBS_L2
-        streams = [workloads.c5_stream(n_rest, n_steps, per_step, seed=100 + i) for i in range(n_distinct)]
-        dev = torch.device("cuda", local)
-        reps = (n_envs + n_distinct - 1) // n_distinct
-        d1 = torch.from_numpy(np.concatenate([x[:n_rest] for x in streams]).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_envs].contiguous()
-        d2 = torch.from_numpy(np.concatenate([x[n_rest:] for x in streams]).view(np.uint8)).to(dev).view(n_distinct, -1).repeat(reps, 1)[:n_envs].contiguous()
-        o1 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_rest
-        o2 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
-        # Price pages resident in shared memory: as many as let the whole shard stay resident in ONE wave (a book's image is
-        # ~0.5 KB per page; 148 SMs x 227 KB).  128-296 books per GPU: all 192 pages (2 books per CTA); 512: ~100 pages.
-        books_per_sm = -(-n_envs // 148)
-        books_per_sm = 1 if books_per_sm <= 1 else 2 if books_per_sm <= 2 else 4 * (-(-books_per_sm // 4))
-        c5_pages = args.pages_smem if args.pages_smem != 10 else max(10, min(192, (227 * 1024 // books_per_sm - 8192) // 512))
-        if args.engine == "deep":
-            # deep-book engine (csrc/deep.cuh): one CTA per book; window = every price the stream can rest at (10000 +- 2048,
-            # rounded out to 32-level words), 98304 queue chunks of 31 entries per book
-            eng_kw = dict(price_window=(7936, 12160), deep_chunks=98304)
-        else:
-            eng_kw = dict(pages_smem=c5_pages, pages_total=192)
-        env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=base, obs_words=obs, max_orders=1_800_000,
-                              max_trades=1 << 20, max_steps=n_steps, max_queue=32, **eng_kw)
-        env.set_stream(stream.cuda_stream)
-        torch.cuda.synchronize()
-        pre_stats = None
-        for i in range(args.warmup + args.steps):
-            if i == args.warmup:
-                barrier()
-            env.reset()
-            env.replay_device(d1.data_ptr(), o1.data_ptr())      # untimed: build the 1M-order book
-            if pre_stats is None:
-                env.synchronize(); pre_stats = env.stats()
-            if i >= args.warmup:
-                ev[i - args.warmup][0].record(stream)
-            env.replay_device(d2.data_ptr(), o2.data_ptr())
-            if i >= args.warmup:
-                ev[i - args.warmup][1].record(stream)
-            flush.fill_(1)
-        ext = n_envs * n_steps * per_step
-        name = (f"C5 shard: {per_gpu} books/GPU x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 "
-                "events per book (15% cancel, 15% modify, 60% limit within +-32 ticks, 10% market), level-2 record per step, "
-                "replayed from device memory; " + ("deep-book engine (one CTA per book: fetch / match / retire warps, chunked array queues)"
-                                                   if "deep_chunks" in eng_kw else f"paged engine, {c5_pages} of 192 price pages per book resident in shared memory"))
     barrier()
     ms = [a.elapsed_time(b) for a, b in ev]
     stats = env.stats()
     if stats["error_envs"]:
         raise SystemExit(f"device flagged errors in {stats['error_envs']} envs")
-    if args.workload == "c5":  # only the timed phase counts
-        stats = {k: (stats[k] - pre_stats[k] if k in ("instructions", "orders_created", "trades", "traded_volume", "transitions", "env_steps") else stats[k]) for k in stats}
-        stats["env_steps"] = n_envs * n_steps
     agg = gather_stats(stats, sum(ms), stats["l1_checksum"], device="cuda")
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -622,20 +741,10 @@ def run_gpu_other(args):
             from oracle import oracle as orc
             orc.build()
             cores = host_cores()
-            if args.workload == "c4":
-                r = orc.bench_agents(128 * cores, cores, n_steps, 7, groups, keyed=False, start_time=0, tick_size=1, step_size=1_000_000)
-                cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
-                       "sample": f"{128 * cores} envs x {n_steps} env-steps of the C4 population, one env per core at a time ({r['seconds']:.2f} s)"}
-            elif args.workload == "market":
-                r = orc.bench_market_agents(32 * cores, cores, n_steps, SEED, groups, g_assets, n_assets, keyed=False)
-                cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
-                       "sample": f"{32 * cores} two-asset markets x {n_steps} steps, one market per core at a time, reference-style "
-                                 f"shared Xoroshiro stream ({r['seconds']:.2f} s)"}
-            else:
-                r = orc.bench_replay_suffix(cores, 1, streams[0], n_rest)
-                cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
-                       "sample": f"{cores} books (one per core), each pre-loaded with {n_rest} resting orders (untimed) and then fed the "
-                                 f"{n_steps * per_step} events of one C5 stream, all threads together ({r['seconds']:.2f} s)"}
+            r = orc.bench_market_agents(32 * cores, cores, n_steps, SEED, groups, g_assets, n_assets, keyed=False)
+            cpu = {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{32 * cores} two-asset markets x {n_steps} steps, one market per core at a time, reference-style "
+                             f"shared Xoroshiro stream ({r['seconds']:.2f} s)"}
         print(json.dumps({
             "metric": METRIC, "value": agg["instructions"] * args.steps / (agg["elapsed_ms_max"] * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": agg["elapsed_ms_max"] / args.steps, "higher_is_better": True,
@@ -643,12 +752,10 @@ def run_gpu_other(args):
             "env_steps_per_sec": agg["env_steps"] * args.steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
             "trades_per_pass": agg["trades"],
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim" if args.workload in ("c4", "market") else "k_deep" if args.engine == "deep" else "k_apply",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_sim<DENSE,0,MKT>",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             **({"cpu_baseline": cpu} if cpu else {})}))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.finish()
     return 0
 
 
@@ -667,6 +774,7 @@ def main():
                     help="c5 / c2: 32-level price pages per book resident in shared memory (of 192 / 64); the default 10 means 'all of them'")
     ap.add_argument("--bg-agents", action="store_true", help="gym: the C3 background population trades in every env (bb_run_agents_with_rows)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="headline run only: skip the C4 / C5 block")
     ap.add_argument("--engine", default=None, choices=["dense", "paged", "deep"],
                     help="default: dense for c3 / market (shallow books inside a known price window), paged for gym")
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "market", "gym"],

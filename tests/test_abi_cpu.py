@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts_match_header():
     from bourse_b200 import abi
 
-    assert C.sizeof(abi.Config) == 96
+    assert C.sizeof(abi.Config) == 104
     assert abi.INSTR_DTYPE.itemsize == 32 and abi.GROUP_DTYPE.itemsize == 80
     assert C.sizeof(abi.Stats) == 64
     assert abi.INSTR_DTYPE.fields["op_flags"][1] == 8 and abi.INSTR_DTYPE.fields["price"][1] == 16

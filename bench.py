@@ -236,9 +236,9 @@ def run_gpu(args):
     checksum = int(hist_host[:, -1, :].astype(np.uint64).sum())
 
     # ---- aggregate over ranks: max time, summed work; the ONLY collective of the run is this all-gather (NCCL)
-    from bourse_b200.sharding import gather_stats
-    agg = gather_stats(stats, total_ms, stats["l1_checksum"], device="cuda")
-    agg_e2e = gather_stats(stats, e2e_s * 1e3, checksum, device="cuda")
+    from bourse_b200.sharding import gather_env_stats
+    agg = gather_env_stats(env, total_ms, ctx.comm)
+    agg_e2e = gather_env_stats(env, e2e_s * 1e3, ctx.comm)
     if rank == 0:
         max_ms, max_e2e = agg["elapsed_ms_max"], agg_e2e["elapsed_ms_max"] * 1e-3
         instr_per_pass = agg["instructions"]     # stats are per pass (reset each pass)
@@ -442,6 +442,9 @@ class Ctx:
         torch.cuda.set_stream(self.stream)
         assert self.stream.cuda_stream != 0
         self.flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+        # the job's statistics all-gather goes through the library's own NCCL communicator (bb_comm_*), not torch
+        from bourse_b200.sharding import Comm
+        self.comm = Comm.from_env(self.local)
 
     def barrier(self):
         if self.world > 1:
@@ -452,6 +455,7 @@ class Ctx:
         return [(self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)) for _ in range(n)]
 
     def finish(self):
+        self.comm.close()
         if self.world > 1:
             self.dist.barrier()
             self.dist.destroy_process_group()
@@ -470,7 +474,7 @@ def measure_c4(ctx: Ctx, per_gpu: int, n_steps: int, steps: int, warmup: int, ma
     swept empty the MomentumAgent's mid price is ~2^31 (orderbook.rs:272-276 with the empty-side sentinel) and its limit
     bids rest THERE, as the best bid — measured: every one of the 8192 envs leaves any dense window within 1000 steps."""
     from bourse_b200 import abi, core, workloads
-    from bourse_b200.sharding import gather_stats, shard_range
+    from bourse_b200.sharding import gather_env_stats, shard_range
 
     base, n_envs = shard_range(per_gpu * ctx.world, ctx.world, ctx.rank)
     groups, obs = workloads.c4_groups(), abi.OBS_L2
@@ -494,7 +498,7 @@ def measure_c4(ctx: Ctx, per_gpu: int, n_steps: int, steps: int, warmup: int, ma
     stats = env.stats()
     if stats["error_envs"]:
         raise SystemExit(f"C4: device flagged errors in {stats['error_envs']} envs")
-    agg = gather_stats(stats, sum(ms), stats["l1_checksum"], device="cuda")
+    agg = gather_env_stats(env, sum(ms), ctx.comm)
     k_ms = sum(ms) / len(ms)
     out = {"workload": f"C4 shard: {per_gpu} envs/GPU x (40+40 RandomAgents + 20-trader MomentumAgent) x {n_steps} env-steps, "
                        "level-2 (45 x u32) record per env-step, paged engine",
@@ -521,7 +525,7 @@ def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pag
     100 steps x 10,000 events per book with a 30% cancel/modify rate, replayed from device memory (timed)."""
     import torch
     from bourse_b200 import abi, core, workloads
-    from bourse_b200.sharding import gather_stats, shard_range
+    from bourse_b200.sharding import gather_env_stats, shard_range
 
     base, n_envs = shard_range(per_gpu * ctx.world, ctx.world, ctx.rank)
     n_rest, n_steps, per_step, n_distinct = 1_000_000, 100, 10_000, 8
@@ -559,6 +563,7 @@ def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pag
         env.replay_device(d1.data_ptr(), o1.data_ptr())      # untimed: build the 1M-order book
         if pre_stats is None:
             env.synchronize(); pre_stats = env.stats()
+            pre_agg = gather_env_stats(env, 0.0, ctx.comm)
         if i >= warmup:
             ev[i - warmup][0].record(ctx.stream)
         env.replay_device(d2.data_ptr(), o2.data_ptr())
@@ -573,7 +578,10 @@ def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pag
     # only the timed phase counts
     stats = {k: (stats[k] - pre_stats[k] if k in ("instructions", "orders_created", "trades", "traded_volume", "transitions", "env_steps") else stats[k]) for k in stats}
     stats["env_steps"] = n_envs * n_steps
-    agg = gather_stats(stats, sum(ms), stats["l1_checksum"], device="cuda")
+    agg = gather_env_stats(env, sum(ms), ctx.comm)
+    for k in ("instructions", "orders_created", "trades", "traded_volume", "transitions"):   # the pre-load is the same on every rank
+        agg[k] -= pre_agg[k]
+    agg["env_steps"] = per_gpu * ctx.world * n_steps
     k_ms = sum(ms) / len(ms)
     out = {"workload": f"C5 shard: {per_gpu} books/GPU x 1,000,000 resting orders (pre-loaded, untimed), then 100 steps x 10,000 events per "
                        "book (15% cancel, 15% modify, 60% limit within +-32 ticks, 10% market), level-2 record per step, replayed from "
@@ -731,7 +739,8 @@ def run_gpu_other(args):
     stats = env.stats()
     if stats["error_envs"]:
         raise SystemExit(f"device flagged errors in {stats['error_envs']} envs")
-    agg = gather_stats(stats, sum(ms), stats["l1_checksum"], device="cuda")
+    from bourse_b200.sharding import gather_env_stats
+    agg = gather_env_stats(env, sum(ms), ctx.comm)
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         k_ms = sum(ms) / len(ms)

@@ -55,6 +55,7 @@ EXPORTS = [
     "bb_n_orders", "bb_n_trades", "bb_orders", "bb_trades", "bb_order_status", "bb_time", "bb_set_time",
     "bb_set_trading", "bb_env_errors", "bb_stats", "bb_history_device", "bb_order_keys", "bb_load_book",
     "bb_set_agents_market", "bb_step_device", "bb_level2_device", "bb_level1_device", "bb_device_alloc", "bb_device_free", "bb_memcpy", "bb_run_agents_with_rows", "bb_reserve", "bb_clear_history", "bb_clear_errors",
+    "bb_comm_unique_id", "bb_comm_init_rank", "bb_comm_init_all", "bb_comm_n_ranks", "bb_comm_destroy", "bb_comm_last_error", "bb_gather_stats",
 ]
 
 _lib = None
@@ -128,6 +129,13 @@ def load() -> C.CDLL:
     sig("bb_history_device", i32, vp, P(vp), P(u64), P(u32))
     sig("bb_order_keys", i32, vp, u32, u64, u64, vp)
     sig("bb_load_book", i32, vp, u32, u64, u32, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp)
+    sig("bb_comm_unique_id", i32, vp)
+    sig("bb_comm_init_rank", i32, vp, i32, i32, i32, P(vp))
+    sig("bb_comm_init_all", i32, i32, vp, P(vp))
+    sig("bb_comm_n_ranks", i32, vp)
+    sig("bb_comm_destroy", i32, vp)
+    sig("bb_comm_last_error", C.c_char_p)
+    sig("bb_gather_stats", i32, vp, vp, u32, vp, vp, vp)
     _lib = L
     return L
 

@@ -86,7 +86,7 @@ class BatchedEnv:
             raise ValueError("deep_chunks needs price_window=(lo, hi) (at most 8192 levels)")
         cfg.deep_chunks = deep_chunks
         self._h = C.c_void_p()
-        self.n_envs, self.obs_words, self.tick_size = n_envs, obs_words, tick_size
+        self.n_envs, self.obs_words, self.tick_size, self.device = n_envs, obs_words, tick_size, device
         self.max_orders, self.max_trades, self.max_steps = max_orders, max_trades, max_steps
         rc = self._lib.bb_create(C.byref(cfg), C.byref(self._h))
         if rc != abi.BB_OK:

@@ -6,18 +6,77 @@ arrays on the host.  `VectorEnv` is that loop batched over `n_envs` envs with ev
 actions go in as a `[n_envs, rows_per_env]` block of packed instruction rows, the new order ids and the level-1 / level-2
 observations come back as device arrays, and nothing crosses PCIe per step unless the caller asks for a host copy.
 
-Buffers are exchanged through the CUDA array interface (`__cuda_array_interface__`, version 3), which torch, cupy and
-numba all speak, so this module needs none of them: `torch.as_tensor(env.obs, device="cuda")` is a zero-copy view, and a
-torch / cupy array can be passed to `step` directly.  numpy arrays are accepted too (copied host to device).
+Buffers are exchanged through DLPack (`__dlpack__` / `__dlpack_device__`: `torch.from_dlpack(env.obs)`, `cupy.from_dlpack`,
+`jax.dlpack`) and the CUDA array interface (`__cuda_array_interface__`, version 3), which torch, cupy and numba all
+speak, so this module needs none of them: both give zero-copy views, and a torch / cupy array (anything with `__dlpack__`
+or the CUDA array interface) can be passed to `step` directly.  numpy arrays are accepted too (copied host to device).
 """
 from __future__ import annotations
 
+import ctypes as C
 import typing
 
 import numpy as np
 
 from . import abi
 from .core import BatchedEnv
+
+# ---- DLPack (dlpack.h, v0.8 ABI: DLManagedTensor in a PyCapsule named "dltensor"), pure ctypes ---------------------------
+KDL_CUDA, KDL_UINT = 2, 1
+
+
+class _DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int32), ("device_id", C.c_int32)]
+
+
+class _DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class _DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", _DLDevice), ("ndim", C.c_int32), ("dtype", _DLDataType),
+                ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+
+class _DLManagedTensor(C.Structure):
+    pass
+
+
+_DLDeleter = C.CFUNCTYPE(None, C.POINTER(_DLManagedTensor))
+_DLManagedTensor._fields_ = [("dl_tensor", _DLTensor), ("manager_ctx", C.c_void_p), ("deleter", _DLDeleter)]
+_api = C.pythonapi
+_DLTENSOR = b"dltensor"   # (PyCapsule keeps the POINTER to its name: the bytes object must outlive every capsule)
+_api.PyCapsule_New.restype, _api.PyCapsule_New.argtypes = C.py_object, [C.c_void_p, C.c_char_p, C.c_void_p]
+_api.PyCapsule_IsValid.restype, _api.PyCapsule_IsValid.argtypes = C.c_int, [C.py_object, C.c_char_p]
+_api.PyCapsule_GetPointer.restype, _api.PyCapsule_GetPointer.argtypes = C.c_void_p, [C.py_object, C.c_char_p]
+_api.PyCapsule_SetName.restype, _api.PyCapsule_SetName.argtypes = C.c_int, [C.py_object, C.c_char_p]
+_LIVE_EXPORTS: dict = {}   # address of an exported DLManagedTensor -> everything that must outlive its consumer
+
+
+@_DLDeleter
+def _dl_deleter(mt_ptr):   # called by the consumer when it drops the tensor: release our bookkeeping (the env owns the memory)
+    _LIVE_EXPORTS.pop(C.addressof(mt_ptr.contents), None)
+
+
+def _dlpack_import(x) -> typing.Tuple[int, int, typing.Any]:
+    """(device pointer, byte size, keep-alive object) of anything that exports DLPack; C-contiguous CUDA tensors only."""
+    capsule = x.__dlpack__()
+    if not _api.PyCapsule_IsValid(capsule, _DLTENSOR):
+        raise ValueError("not a DLPack capsule")
+    mt = C.cast(_api.PyCapsule_GetPointer(capsule, _DLTENSOR), C.POINTER(_DLManagedTensor)).contents
+    t = mt.dl_tensor
+    if t.device.device_type != KDL_CUDA:
+        raise ValueError("DLPack tensor is not in CUDA device memory")
+    shape = [t.shape[i] for i in range(t.ndim)]
+    if t.strides:
+        expect = 1
+        for i in reversed(range(t.ndim)):
+            if shape[i] != 1 and t.strides[i] != expect:
+                raise ValueError("device arrays must be C-contiguous")
+            expect *= shape[i]
+    nbytes = int(np.prod(shape)) * (t.dtype.bits * t.dtype.lanes // 8)
+    # the capsule is kept (un-renamed) together with its producer: its own destructor releases the tensor when we drop it
+    return int(t.data) + int(t.byte_offset), nbytes, (capsule, x)
 
 ACTION_DTYPE = abi.INSTR_DTYPE  # one row = one instruction: (t ignored, op_flags, order_id, price, vol, trader, aux)
 
@@ -33,6 +92,25 @@ class DeviceArray:
     @property
     def __cuda_array_interface__(self):
         return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def __dlpack_device__(self):
+        return (KDL_CUDA, self._env.device)
+
+    def __dlpack__(self, stream=None, **_kw):
+        """DLPack export (zero copy): `torch.from_dlpack(arr)`.  The memory stays owned by the env — keep the env alive while
+        views exist.  `stream`: the consumer's stream; the producer side is the env's stream, which the caller orders
+        against as for any other use of the env's outputs (`env.synchronize()` or stream semantics of `set_stream`)."""
+        if self.dtype.kind != "u":
+            raise TypeError("only unsigned integer arrays are exported")
+        mt = _DLManagedTensor()
+        shape = (C.c_int64 * len(self.shape))(*self.shape)
+        mt.dl_tensor = _DLTensor(C.c_void_p(self.ptr), _DLDevice(KDL_CUDA, self._env.device), len(self.shape),
+                                 _DLDataType(KDL_UINT, 8 * self.dtype.itemsize, 1), shape, None, 0)
+        mt.manager_ctx, mt.deleter = None, _dl_deleter
+        _LIVE_EXPORTS[C.addressof(mt)] = (mt, shape, self)
+        # no capsule destructor: a capsule that is never consumed leaves its ~200-byte bookkeeping entry behind (a ctypes
+        # callback must not be handed a capsule that is being deallocated); a consumed one is released by `_dl_deleter`
+        return _api.PyCapsule_New(C.addressof(mt), _DLTENSOR, None)
 
     def numpy(self) -> np.ndarray:
         """Host copy (synchronises the env's stream)."""
@@ -54,6 +132,12 @@ class DeviceArray:
 def _device_ptr(x, nbytes: int) -> typing.Optional[int]:
     cai = getattr(x, "__cuda_array_interface__", None)
     if cai is None:
+        if hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):   # DLPack-only producers
+            ptr, n, keep = _dlpack_import(x)
+            if n != nbytes:
+                raise ValueError(f"device array holds {n} bytes, expected {nbytes}")
+            _device_ptr.keep = keep   # alive until the next call: the launch that reads it is already enqueued by then
+            return ptr
         return None
     if cai.get("strides") is not None:
         raise ValueError("device arrays must be C-contiguous")

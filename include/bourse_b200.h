@@ -315,6 +315,29 @@ int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int
 /* device pointer + strides of the history ring, for zero-copy consumers (DLPack at the Python edge) */
 int bb_history_device(bb_handle* h, void** d_ptr, uint64_t* env_stride_words, uint32_t* obs_words);
 
+/* ---- multi-GPU ------------------------------------------------------------------ */
+/* Books share no state (crates/step_sim/src/env.rs:58-71: an Env owns its OrderBook, queue and records), so a job shards
+ * its envs over GPUs — one bb_handle per device, contiguous blocks of global env ids (bb_config.env_id_base keeps the agent
+ * RNG invariant to the sharding) — and runs them with NO per-step collective.  The one exchange is the end-of-run
+ * all-gather of every shard's statistics, over NCCL (NVLink 5 / NVSwitch).  NCCL is loaded at run time (libnccl.so.2);
+ * these calls fail with BB_ECUDA where it is absent, everything above works without it.
+ *   one process per GPU (torchrun, MPI, ...): rank 0 calls bb_comm_unique_id, the host hands the 128 bytes to every rank
+ *     by whatever means it has, each rank calls bb_comm_init_rank with its own device;
+ *   one process driving several GPUs: bb_comm_init_all (ncclCommInitAll), rank i == devices[i]. */
+typedef struct bb_comm bb_comm;
+#define BB_COMM_ID_BYTES 128
+int bb_comm_unique_id(unsigned char* out_id /* [BB_COMM_ID_BYTES] */);
+int bb_comm_init_rank(const unsigned char* id, int n_ranks, int rank, int device, bb_comm** out);
+int bb_comm_init_all(int n_dev, const int* devices /* NULL => 0..n_dev-1 */, bb_comm** out);
+int bb_comm_n_ranks(const bb_comm* c);
+int bb_comm_destroy(bb_comm* c);
+const char* bb_comm_last_error(void);
+/* bb_stats of every local shard, all-gathered: handles[n_local] = this process's handles in local-rank order (n_local == 1
+ * after bb_comm_init_rank, == n_dev after bb_comm_init_all); elapsed_ms[n_local] (may be NULL) travels with the counters so
+ * that the caller can take the max over ranks.  out_stats[n_ranks], out_elapsed_ms[n_ranks] (may be NULL), rank order. */
+int bb_gather_stats(bb_comm* c, bb_handle* const* handles, uint32_t n_local, const double* elapsed_ms, bb_stats_t* out_stats,
+                    double* out_elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

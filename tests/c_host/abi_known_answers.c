@@ -160,7 +160,93 @@ static int test_numpy_arrays(void) {
     return 0;
 }
 
-int main(void) {
+/* Multi-GPU behind the C ABI: `n_shards` handles, one per device (all on device 0 when the box has a single
+ * GPU: NCCL then refuses duplicate devices, so the 1-GPU case runs one shard through the same calls), each owning a
+ * contiguous block of the global env ids; in-kernel RandomAgents keyed by GLOBAL env id; bb_gather_stats all-gathers the
+ * shards' statistics over NCCL.  The sharded job must equal the unsharded one: same total counters, and shard k's level-1
+ * checksum equals the checksum of the same envs taken from ... a handle created with the same env_id_base. */
+static int run_shard(int device, uint32_t base, uint32_t n_envs, bb_handle** out) {
+    bb_handle* h = NULL;
+    bb_config c = base_config(0, 1000000);
+    c.device = device;
+    c.n_envs = n_envs;
+    c.env_id_base = base;
+    c.obs_words = BB_OBS_L1;
+    c.max_orders = 4096;
+    c.max_trades = 8192;
+    c.max_steps = 32;
+    c.max_queue = 128;
+    int rc = bb_create(&c, &h);
+    if (rc == BB_ECUDA) return 3;
+    CHECK(rc == BB_OK);
+    bb_agent_group g[2];
+    memset(g, 0, sizeof g);
+    g[0].kind = BB_GROUP_RANDOM; g[0].n_agents = 50; g[0].tick_lo = 40; g[0].tick_hi = 60; g[0].vol_lo = 10; g[0].vol_hi = 20;
+    g[0].tick_size = 2; g[0].rate = 0.8f;
+    g[1] = g[0]; g[1].tick_lo = 10; g[1].tick_hi = 90; g[1].vol_lo = 50; g[1].vol_hi = 70; g[1].rate = 0.2f;
+    OK(bb_set_agents(h, g, 2));
+    OK(bb_run_agents(h, 101, 32));
+    OK(bb_synchronize(h));
+    *out = h;
+    return 0;
+}
+
+static int test_multi_gpu_gather(int n_dev) {
+    const uint32_t total = 24;
+    const int n_shards = n_dev >= 2 ? 2 : 1;
+    bb_handle* h = NULL;      /* (for CHECK's error text) */
+    bb_handle* whole = NULL;
+    bb_handle* shard[2] = {NULL, NULL};
+    int rc = run_shard(0, 0, total, &whole);
+    if (rc) return rc;
+    h = whole;
+    bb_stats_t ref;
+    OK(bb_stats(whole, &ref));
+    CHECK(ref.instructions > 10000 && ref.trades > 1000 && ref.error_envs == 0);
+    for (int k = 0; k < n_shards; ++k) {
+        const uint32_t base = k * (total / n_shards), cnt = (k == n_shards - 1) ? total - base : total / n_shards;
+        rc = run_shard(k, base, cnt, &shard[k]);
+        if (rc) return rc;
+    }
+    bb_comm* comm = NULL;
+    rc = bb_comm_init_all(n_shards, NULL, &comm);
+    if (rc != BB_OK) {
+        fprintf(stderr, "bb_comm_init_all: %s\n", bb_comm_last_error());
+        return 1;
+    }
+    CHECK(bb_comm_n_ranks(comm) == n_shards);
+    bb_stats_t all[2];
+    double ms_in[2] = {12.5, 40.25}, ms_out[2] = {0, 0};
+    rc = bb_gather_stats(comm, shard, (uint32_t)n_shards, ms_in, all, ms_out);
+    if (rc != BB_OK) {
+        fprintf(stderr, "bb_gather_stats: %s\n", bb_comm_last_error());
+        return 1;
+    }
+    uint64_t instr = 0, trades = 0, vol = 0, steps = 0;
+    for (int k = 0; k < n_shards; ++k) {
+        instr += all[k].instructions; trades += all[k].trades; vol += all[k].traded_volume; steps += all[k].env_steps;
+        CHECK(ms_out[k] == ms_in[k]);
+        bb_stats_t own;
+        h = shard[k];
+        OK(bb_stats(shard[k], &own));
+        CHECK(own.l1_checksum == all[k].l1_checksum && own.instructions == all[k].instructions);
+    }
+    h = whole;
+    CHECK(instr == ref.instructions && trades == ref.trades && vol == ref.traded_volume && steps == ref.env_steps);
+    if (n_shards == 1) CHECK(all[0].l1_checksum == ref.l1_checksum);
+    OK(bb_comm_destroy(comm));
+    for (int k = 0; k < n_shards; ++k) OK(bb_destroy(shard[k]));
+    OK(bb_destroy(whole));
+    printf("ok multi_gpu_gather_%d_shards\n", n_shards);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && strcmp(argv[1], "--multi-gpu") == 0) {   /* tests/test_c_host.py passes the number of visible devices */
+        const int rc = test_multi_gpu_gather(argc > 2 ? atoi(argv[2]) : 1);
+        if (rc == 3) fprintf(stderr, "no usable CUDA device: %s\n", bb_last_error(NULL));
+        return rc;
+    }
     if (bb_abi_version() != BB_ABI_VERSION) {
         fprintf(stderr, "ABI version mismatch\n");
         return 1;

@@ -39,3 +39,17 @@ def test_c_host_known_answers():
     res = subprocess.run([EXE], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.split() == ["ok", "order_book_trades", "ok", "env", "ok", "numpy_arrays"]
+
+
+@pytest.mark.gpu
+def test_c_host_multi_gpu_gather():
+    """Multi-GPU behind the C ABI, torch-free: shards on separate devices (two when the box has them, else one), in-kernel
+    agents keyed by global env id, statistics all-gathered by bb_gather_stats (ncclAllGather inside the library)."""
+    import ctypes
+
+    _build()
+    n = ctypes.c_int(0)
+    assert ctypes.CDLL("libcuda.so.1").cuInit(0) == 0 and ctypes.CDLL("libcuda.so.1").cuDeviceGetCount(ctypes.byref(n)) == 0
+    res = subprocess.run([EXE, "--multi-gpu", str(n.value)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.split()[-2:] == ["ok", f"multi_gpu_gather_{min(n.value, 2)}_shards"]   # (NCCL prints its version banner first)

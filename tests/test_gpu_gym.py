@@ -123,6 +123,42 @@ def test_vector_env_zero_copy_with_torch(oracle):
     v.close()
 
 
+def test_dlpack_export_and_import(oracle):
+    """DLPack at the Python edge (BASELINE north_star): observations / ids leave as DLPack capsules (`torch.from_dlpack`, zero
+    copy), and an action block that speaks ONLY DLPack (no CUDA array interface) is accepted by `step`."""
+    import torch
+
+    n_envs, rows = 32, 3
+    v = gym.VectorEnv(n_envs, rows, 11, 0, 1, 1000, max_orders=256, max_trades=256, max_steps=8)
+    assert v.obs.__dlpack_device__() == (2, 0)            # kDLCUDA, device 0
+    obs_t, ids_t = torch.from_dlpack(v.obs), torch.from_dlpack(v.ids)
+    assert obs_t.data_ptr() == v.obs.ptr and tuple(obs_t.shape) == (n_envs, 45) and obs_t.dtype == torch.uint32
+    assert ids_t.data_ptr() == v.ids.ptr and ids_t.dtype == torch.uint64
+    v.reset()
+    a = gym.pack_actions(np.tile(np.array([abi.OP_NEW, abi.OP_NEW, abi.OP_NOOP], np.uint32), (n_envs, 1)), bid=np.tile([1, 0, 0], (n_envs, 1)),
+                         vol=np.tile([10, 4, 0], (n_envs, 1)), price=np.tile([50, 50, 0], (n_envs, 1)), trader=1)
+
+    class DLPackOnly:   # a producer without __cuda_array_interface__
+        def __init__(self, t): self.t = t
+        def __dlpack__(self, stream=None): return self.t.__dlpack__()
+        def __dlpack_device__(self): return self.t.__dlpack_device__()
+
+    dev = torch.from_numpy(a.view(np.uint8).reshape(n_envs, rows, 32)).cuda()
+    torch.cuda.synchronize()
+    v.step(DLPackOnly(dev))
+    v.env.synchronize()
+    obs = obs_t.cpu().numpy().view(np.uint32)
+    for e in (0, 31):
+        o = oracle.StepEnv(11 + e, 0, 1, 1000)
+        o.place_order(True, 10, 1, 50); o.place_order(False, 4, 1, 50); o.step()
+        assert np.array_equal(obs[e], o.level_2_data_array()), e
+    assert list(ids_t.cpu().numpy().view(np.uint64)[0]) == [0, 1, abi.NO_ID]
+    with pytest.raises(ValueError):   # a host tensor is not a device array
+        gym._dlpack_import(DLPackOnly(torch.zeros(4, dtype=torch.int32)))
+    del obs_t, ids_t
+    v.close()
+
+
 def test_step_device_argument_checks():
     from bourse_b200 import core
     e = core.BatchedEnv(4, 0, 0, 1, 1000, assets=2, max_orders=64, max_trades=64, max_steps=8, max_queue=16)
@@ -226,9 +262,12 @@ def test_step_device_inside_a_cuda_graph(oracle):
     acts = torch.zeros((n_envs, rows, 8), dtype=torch.int32, device="cuda")
     rng = np.random.default_rng(0)
 
+    blocks = []   # every action block the envs executed, for the oracle
+
     def fill():
         blk = gym.pack_actions(np.full((n_envs, rows), abi.OP_NEW, np.uint32), bid=rng.random((n_envs, rows)) < 0.5,
                                vol=rng.integers(1, 20, (n_envs, rows)), price=rng.integers(45, 56, (n_envs, rows)), trader=3)
+        blocks.append(blk)
         acts.copy_(torch.from_numpy(blk.view(np.int32).reshape(n_envs, rows, 8)))
         torch.cuda.synchronize()
 
@@ -250,6 +289,17 @@ def test_step_device_inside_a_cuda_graph(oracle):
     for e in (0, 17, 63):
         assert a.env.get_trades(e) == b.env.get_trades(e) and np.array_equal(a.env.history(e), b.env.history(e))
     assert len(a.env.get_trades(0)) > 0
+    # ... and both equal the oracle: one StepEnv per env fed the same blocks (the captured step was replayed, never re-recorded)
+    assert len(blocks) == k + 1
+    for e in (0, 17, 63):
+        o = oracle.StepEnv(2 + e, 0, 1, 1000)
+        for blk in blocks:
+            for r in range(rows):
+                x = blk[e, r]
+                o.place_order(bool(int(x["op_flags"]) & abi.F_BID), int(x["vol"]), int(x["trader"]), int(x["price"]))
+            o.step()
+        assert np.array_equal(a.obs.numpy()[e], o.level_2_data_array()), e
+        assert a.env.get_trades(e) == o.get_trades() and a.env.get_orders(e) == o.get_orders(), e
     # agent launches stage records without per-step capacity checks and refuse to be captured
     from bourse_b200 import workloads
     c = gym.VectorEnv(4, 2, 0, 0, 1, 1_000_000, agents=workloads.c3_groups(), agent_seed=1, max_orders=1024, max_trades=1024, max_steps=8, max_queue=128)

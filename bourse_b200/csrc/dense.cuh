@@ -270,8 +270,10 @@ __device__ __forceinline__ void d_apply(const G& g, Book& b, u32 kind, u32 id, u
         const u64 kt = ended ? 0ULL : t, end_time = ended ? t : ~0ULL;
         // 52 of the record's 64 bytes are written (the link and padding words are not): L2 therefore reads the two
         // partially written sectors back from DRAM when it evicts them (10 GB per C3 pass).  Writing both sectors
-        // in full removes those reads but was measured 4.6 % SLOWER end to end (wider stores hold their source
-        // registers longer; profiles/r01_s5_summary.md), and DRAM is at 11 % of its bandwidth either way.
+        // in full removes those reads but was measured 4.6 % SLOWER end to end, twice: with zero-filled words
+        // (profiles/r01_s5_summary.md) and with the don't-care words taken from live registers (38.74 vs 37.03 ms,
+        // profiles/r02_summary.md) — the cost is in the store path, not in register pressure — and DRAM is at 11 % of
+        // its bandwidth either way.
         stg64v(ra + OH_PRICE, price, rem);
         stg128(ra + OH_KEYT, (u32)kt, (u32)(kt >> 32), status | (side ? META_BID : 0u), vol);
         stg128(ra + OC_ARR, (u32)t, (u32)(t >> 32), (u32)end_time, (u32)(end_time >> 32));

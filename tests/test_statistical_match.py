@@ -3,8 +3,9 @@
 The reference threads ONE Xoroshiro128** stream through every agent and the shuffle (crates/step_sim/src/runner.rs:46-69);
 the batched path keys Philox per (env, step, agent) instead, so individual runs differ draw for draw and only the
 distributions can agree.  Each test runs the same population both ways over many independent envs and compares the
-across-env means of per-env summary statistics with a two-sample z-test; tolerance: 5 standard errors, stated at the
-assertion.  Seeds are fixed, so the outcome is deterministic."""
+across-env means of per-env summary statistics with a two-sample z-test (tolerance: 5 standard errors, stated at the
+assertion) and the DISTRIBUTIONS of per-step observables with two-sample Kolmogorov-Smirnov tests (one observation per env
+and step, alpha = 0.001; `_assert_ks_match`).  Seeds are fixed, so the outcome is deterministic."""
 import numpy as np
 import pytest
 
@@ -39,6 +40,28 @@ def _assert_match(a, b, n_sigma=5.0):
     assert not np.array_equal(a, b) and (a.std(0) > 0).all()
 
 
+KS_STEPS = (120, 180, 240, 299)   # late, well separated steps: one observation per env and step, independent across envs
+KS_FIELDS = {"trade_vol/step": 0, "bid_price": 1, "ask_price": 2, "ask_vol": 3, "bid_vol": 4, "bid_touch_vol": 5, "ask_touch_vol": 7}
+
+
+def _assert_ks_match(a_hist, b_hist, alpha=1e-3):
+    """Distributional match: two-sample Kolmogorov-Smirnov tests on the per-step traded volume,
+    the touch prices, the spread, the side totals and the touch volumes.  Observations within one env are autocorrelated,
+    so each test takes ONE observation per env (the value at a fixed step) — independent draws, as the test assumes.
+    Tolerance: no test rejects at alpha = 0.001 (seeds are fixed: the outcome is deterministic)."""
+    from scipy.stats import ks_2samp
+
+    worst = (1.0, None)
+    for step in KS_STEPS:
+        cols = {name: (a_hist[:, step, w].astype(np.float64), b_hist[:, step, w].astype(np.float64)) for name, w in KS_FIELDS.items()}
+        cols["spread"] = (a_hist[:, step, 2].astype(np.float64) - a_hist[:, step, 1], b_hist[:, step, 2].astype(np.float64) - b_hist[:, step, 1])
+        for name, (x, y) in cols.items():
+            res = ks_2samp(x, y)
+            assert res.pvalue >= alpha, f"KS rejects {name} at step {step}: D = {res.statistic:.3f}, p = {res.pvalue:.2e}"
+            worst = min(worst, (res.pvalue, f"{name}@{step}"))
+    return worst
+
+
 def _oracle_hist(oracle, groups, n_envs, keyed, seed):
     out = []
     for e in range(n_envs):
@@ -53,9 +76,14 @@ def _oracle_hist(oracle, groups, n_envs, keyed, seed):
 @pytest.mark.parametrize("groups_fn", [workloads.c3_groups, workloads.c4_groups], ids=["random", "random+momentum"])
 def test_philox_contract_matches_reference_stream_statistically(oracle, groups_fn):
     groups = groups_fn()
-    keyed = _env_summaries(_oracle_hist(oracle, groups, 96, True, 11))
-    stream = _env_summaries(_oracle_hist(oracle, groups, 96, False, 1234))
-    _assert_match(keyed, stream)
+    hk, hs = _oracle_hist(oracle, groups, 192, True, 11), _oracle_hist(oracle, groups, 192, False, 1234)
+    _assert_match(_env_summaries(hk[:96]), _env_summaries(hs[:96]))
+    _assert_ks_match(hk, hs)
+    # the KS test has teeth: the same population with a different activity rate is told apart
+    other = [g.copy() for g in groups]
+    other[0]["rate"] = 0.5
+    with pytest.raises(AssertionError, match="KS rejects"):
+        _assert_ks_match(hk, _oracle_hist(oracle, other, 192, False, 99))
 
 
 @pytest.mark.gpu
@@ -68,9 +96,10 @@ def test_gpu_agents_match_reference_stream_statistically(core, oracle):
     env.set_agents(groups)
     env.run_agents(N_STEPS, 11)
     assert not env.env_errors().any()
-    gpu = _env_summaries(env.history_all(N_STEPS))
-    stream = _env_summaries(_oracle_hist(oracle, groups, 128, False, 1234))
-    _assert_match(gpu, stream)
+    hist = env.history_all(N_STEPS)
+    hs = _oracle_hist(oracle, groups, 256, False, 1234)
+    _assert_match(_env_summaries(hist), _env_summaries(hs[:128]))
+    _assert_ks_match(hist, hs)
 
 
 def _oracle_market_hist(oracle, groups, assets, n_assets, n_markets, keyed, seed):

@@ -177,7 +177,8 @@ def run_gpu(args):
     # engine: "dense" = dense tick-indexed ladder + shared-memory order slots (csrc/dense.cuh): C3's resting prices lie
     # in [20, 180) (ticks 10..89 x tick_size 2) and at most 100 orders rest per book (one per RandomAgent), inside the engine's window / slot limits;
     # "paged" = the general engine (any u32 price, any depth).  Both are bit-identical on this workload (tests).
-    eng_kw = dict(price_window=(20, 180), live_cap=128) if args.engine == "dense" else {}
+    # (the window and the slot count follow from the population: core.dense_kwargs_for -> price_window (20, 179), live_cap 100)
+    eng_kw = core.dense_kwargs_for(groups) if args.engine == "dense" else {}
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, device=local, env_id_base=env_base, obs_words=abi.OBS_L1,
                           max_orders=args.max_orders, max_trades=args.max_trades, max_steps=args.sim_steps, max_queue=128, **eng_kw)
     env.set_agents(groups)
@@ -235,6 +236,32 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     checksum = int(hist_host[:, -1, :].astype(np.uint64).sum())
 
+    # ---- the same, plus everything else the reference's sim_runner leaves in HOST memory: every env's trade log and order
+    # table (orderbook.rs:113-115) copied out after the run (bb_trades_all / bb_orders_all, one strided copy each, pinned)
+    e2e_logs = None
+    if not args.no_logs:
+        _, n_tr = env.trades_all(0, out=np.empty((n_envs, 0), dtype=abi.TRADE_REC_DTYPE))
+        _, n_or = env.orders_all(0, out=np.empty((n_envs, 0), dtype=abi.ORDER_REC_DTYPE))
+        cap_t, cap_o = int(n_tr.max()) + 1024, int(n_or.max()) + 1024
+        tr_host = torch.empty((n_envs, cap_t, 32), dtype=torch.uint8, pin_memory=True).numpy().view(abi.TRADE_REC_DTYPE).reshape(n_envs, cap_t)
+        or_host = torch.empty((n_envs, cap_o, 64), dtype=torch.uint8, pin_memory=True).numpy().view(abi.ORDER_REC_DTYPE).reshape(n_envs, cap_o)
+        n_log = 2
+        for i in range(n_log + 1):
+            if i == 1:
+                barrier()
+                t0 = time.perf_counter()
+            env.reset(); env.set_agents(groups); env.run_agents_to_host(n_steps, SEED, hist_host)
+            st = env.stats()
+            _, n_tr = env.trades_all(cap_t, out=tr_host)
+            _, n_or = env.orders_all(cap_o, out=or_host)
+        barrier()
+        logs_s = (time.perf_counter() - t0) / n_log
+        assert int(n_tr.sum()) == stats["trades"] and int(n_or.sum()) == stats["orders_created"]
+        traded = int(sum(int(tr_host[e, :n_tr[e]]["vol"].sum(dtype=np.uint64)) for e in range(0, n_envs, 256)))
+        e2e_logs = {"seconds_per_pass": logs_s, "d2h_bytes_per_step": int(hist_host.nbytes + tr_host.nbytes + or_host.nbytes + 64 + n_envs * 44),
+                    "trade_records": int(n_tr.sum()), "order_records": int(n_or.sum()), "sampled_traded_volume": traded}
+        del tr_host, or_host
+
     # ---- aggregate over ranks: max time, summed work; the ONLY collective of the run is this all-gather (NCCL)
     from bourse_b200.sharding import gather_env_stats
     agg = gather_env_stats(env, total_ms, ctx.comm)
@@ -263,6 +290,11 @@ def run_gpu(args):
             "e2e": {"value": instr_per_pass * args.steps / max_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * max_e2e / args.steps,
                     "api": "BatchedEnv.reset/set_agents/run_agents_to_host/stats (C ABI bb_reset, bb_set_agents, bb_run_agents_to_host, bb_stats)", "obs_checksum": checksum},
+            # everything sim_runner leaves on the host, i.e. the history AND every trade log and order table (PCIe-bound)
+            **({"e2e_with_logs": {"value": instr_per_pass / world / e2e_logs["seconds_per_pass"] * world, "unit": UNIT,
+                                  "ms_per_step": 1e3 * e2e_logs["seconds_per_pass"], "d2h_bytes_per_step": e2e_logs["d2h_bytes_per_step"],
+                                  "trade_records": e2e_logs["trade_records"], "order_records": e2e_logs["order_records"],
+                                  "api": "... + BatchedEnv.trades_all / orders_all (bb_trades_all, bb_orders_all)"}} if e2e_logs else {}),
             "gpu_launches": 2 * args.steps, "clocks": clocks,   # timed region: k_init + k_sim per pass
             # sanity: host wall clock over the timed loop (includes the untimed L2 flushes); must be >= the event total
             "wall_ms_timed_loop": wall_ms, "event_ms_timed_loop": total_ms,
@@ -783,6 +815,7 @@ def main():
                     help="c5 / c2: 32-level price pages per book resident in shared memory (of 192 / 64); the default 10 means 'all of them'")
     ap.add_argument("--bg-agents", action="store_true", help="gym: the C3 background population trades in every env (bb_run_agents_with_rows)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-logs", action="store_true", help="skip the e2e_with_logs leg (full trade log + order table to the host)")
     ap.add_argument("--no-secondary", action="store_true", help="headline run only: skip the C4 / C5 block")
     ap.add_argument("--engine", default=None, choices=["dense", "paged", "deep"],
                     help="default: dense for c3 / market (shallow books inside a known price window), paged for gym")

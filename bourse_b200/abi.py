@@ -30,7 +30,13 @@ GROUP_DTYPE = np.dtype(
     [("kind", "<u4"), ("n_agents", "<u4"), ("tick_lo", "<u4"), ("tick_hi", "<u4"), ("vol_lo", "<u4"),
      ("vol_hi", "<u4"), ("tick_size", "<u4"), ("rate", "<f4"), ("decay", "<f8"), ("demand", "<f8"),
      ("scale", "<f8"), ("order_ratio", "<f8"), ("mu", "<f8"), ("sigma", "<f8")], align=True)
-assert INSTR_DTYPE.itemsize == 32 and GROUP_DTYPE.itemsize == 80
+ORDER_REC_DTYPE = np.dtype(
+    [("price", "<u4"), ("vol", "<u4"), ("link0", "<u4"), ("link1", "<u4"), ("key_time", "<u8"), ("meta", "<u4"), ("start_vol", "<u4"),
+     ("arr_time", "<u8"), ("end_time", "<u8"), ("trader", "<u4"), ("pad", "<u4", (3,))], align=True)
+TRADE_REC_DTYPE = np.dtype(
+    [("t", "<u8"), ("price", "<u4"), ("vol", "<u4"), ("active_id", "<u4"), ("passive_id", "<u4"), ("side_is_bid", "<u4"), ("pad", "<u4")],
+    align=True)
+assert INSTR_DTYPE.itemsize == 32 and GROUP_DTYPE.itemsize == 80 and ORDER_REC_DTYPE.itemsize == 64 and TRADE_REC_DTYPE.itemsize == 32
 
 
 class Config(C.Structure):
@@ -55,7 +61,7 @@ EXPORTS = [
     "bb_n_orders", "bb_n_trades", "bb_orders", "bb_trades", "bb_order_status", "bb_time", "bb_set_time",
     "bb_set_trading", "bb_env_errors", "bb_stats", "bb_history_device", "bb_order_keys", "bb_load_book",
     "bb_set_agents_market", "bb_step_device", "bb_level2_device", "bb_level1_device", "bb_device_alloc", "bb_device_free", "bb_memcpy", "bb_run_agents_with_rows", "bb_reserve", "bb_clear_history", "bb_clear_errors",
-    "bb_comm_unique_id", "bb_comm_init_rank", "bb_comm_init_all", "bb_comm_n_ranks", "bb_comm_destroy", "bb_comm_last_error", "bb_gather_stats",
+    "bb_orders_all", "bb_trades_all", "bb_comm_unique_id", "bb_comm_init_rank", "bb_comm_init_all", "bb_comm_n_ranks", "bb_comm_destroy", "bb_comm_last_error", "bb_gather_stats",
 ]
 
 _lib = None
@@ -129,6 +135,8 @@ def load() -> C.CDLL:
     sig("bb_history_device", i32, vp, P(vp), P(u64), P(u32))
     sig("bb_order_keys", i32, vp, u32, u64, u64, vp)
     sig("bb_load_book", i32, vp, u32, u64, u32, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp)
+    sig("bb_orders_all", i32, vp, u32, vp, vp)
+    sig("bb_trades_all", i32, vp, u32, vp, vp)
     sig("bb_comm_unique_id", i32, vp)
     sig("bb_comm_init_rank", i32, vp, i32, i32, i32, P(vp))
     sig("bb_comm_init_all", i32, i32, vp, P(vp))

@@ -310,6 +310,26 @@ class BatchedEnv:
         self._ck(self._lib.bb_trades(self._h, env, 0, n, *[abi.ptr(c) for c in cols.values()]))
         return cols
 
+    def orders_all(self, cap_per_env: int, out: typing.Optional[np.ndarray] = None):
+        """Every env's order table in one strided copy (bb_orders_all): (records [n_envs, cap_per_env] of abi.ORDER_REC_DTYPE,
+        counts [n_envs]).  `out`: a preallocated (ideally pinned) array to fill."""
+        if out is None:
+            out = np.empty((self.n_envs, cap_per_env), dtype=abi.ORDER_REC_DTYPE)
+        assert out.shape == (self.n_envs, cap_per_env) and out.dtype == abi.ORDER_REC_DTYPE and out.flags.c_contiguous
+        counts = np.empty(self.n_envs, dtype=np.uint32)
+        self._ck(self._lib.bb_orders_all(self._h, cap_per_env, abi.ptr(out), abi.ptr(counts)))
+        return out, counts
+
+    def trades_all(self, cap_per_env: int, out: typing.Optional[np.ndarray] = None):
+        """Every env's trade log in one strided copy (bb_trades_all): (records [n_envs, cap_per_env] of abi.TRADE_REC_DTYPE,
+        counts [n_envs])."""
+        if out is None:
+            out = np.empty((self.n_envs, cap_per_env), dtype=abi.TRADE_REC_DTYPE)
+        assert out.shape == (self.n_envs, cap_per_env) and out.dtype == abi.TRADE_REC_DTYPE and out.flags.c_contiguous
+        counts = np.empty(self.n_envs, dtype=np.uint32)
+        self._ck(self._lib.bb_trades_all(self._h, cap_per_env, abi.ptr(out), abi.ptr(counts)))
+        return out, counts
+
     def get_orders(self, env: int = 0):
         """list[PyOrder] = (side, status, arr, end, vol, start_vol, price, trader, id) — rust/src/types.rs:19-31"""
         c = self.orders_arrays(env)
@@ -361,6 +381,25 @@ def random_group(n_agents, tick_range, vol_range, tick_size, activity_rate):
     g["vol_lo"], g["vol_hi"] = vol_range
     g["tick_size"], g["rate"] = tick_size, activity_rate
     return g
+
+
+def dense_kwargs_for(groups) -> dict:
+    """Engine keywords for `BatchedEnv` derived from an in-kernel agent population: when every group is a RandomAgents
+    group the resting prices are bounded by the groups' tick ranges (`tick * tick_size`, random_agent.rs:96-106) and every
+    agent holds at most one order, so the dense-window engine's window and slot count follow from the parameters:
+    `price_window = [min price, max price + 1)`, `live_cap = number of agents` (<= 254).  MomentumAgent / NoiseAgent quote
+    around the mid price, which is ~2^31 whenever one side of the book is empty (orderbook.rs:272-276): no window holds
+    them, so any such group (or more than 254 agents, or a window beyond 1024 levels) returns {} — the general engine."""
+    lo, hi, n = None, 0, 0
+    for g in groups:
+        if int(g["kind"]) != abi.GROUP_RANDOM:
+            return {}
+        ts = int(g["tick_size"])
+        glo, ghi = int(g["tick_lo"]) * ts, (int(g["tick_hi"]) - 1) * ts + 1
+        lo, hi, n = (glo if lo is None else min(lo, glo)), max(hi, ghi), n + int(g["n_agents"])
+    if lo is None or n > 254 or hi - lo > 1024:
+        return {}
+    return dict(price_window=(lo, hi), live_cap=max(n, 1))
 
 
 def momentum_group(agent_id_start, n_agents, tick_size, p_cancel, trade_vol, decay, demand, scale, order_ratio,

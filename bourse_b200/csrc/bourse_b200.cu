@@ -1249,6 +1249,38 @@ int bb_trades(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* 
     return BB_OK;
 }
 
+static_assert(sizeof(bb_order_rec) == sizeof(OrderRec) && sizeof(bb_trade_rec) == sizeof(TradeRec), "public record layouts");
+
+int bb_orders_all(bb_handle* h, uint32_t cap_per_env, bb_order_rec* out, uint32_t* counts) {
+    CHECK_H(h);
+    if (!out || !counts) return fail(h, BB_EINVAL, "null argument");
+    for (auto& q : h->queue)
+        if (!q.empty()) return fail(h, BB_EINVAL, "host-queued instructions pending: call bb_step first");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const u32 cap = std::min(cap_per_env, h->cfg.max_orders);
+    CUDA_TRY(h, cudaMemcpy2DAsync(counts, 4, h->blobs + offsetof(BookHdr, n_orders), h->blob_stride, 4, h->cfg.n_envs,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    if (cap)
+        CUDA_TRY(h, cudaMemcpy2DAsync(out, (size_t)cap_per_env * sizeof(OrderRec), h->ord, (size_t)h->cfg.max_orders * sizeof(OrderRec),
+                                      (size_t)cap * sizeof(OrderRec), h->cfg.n_envs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+int bb_trades_all(bb_handle* h, uint32_t cap_per_env, bb_trade_rec* out, uint32_t* counts) {
+    CHECK_H(h);
+    if (!out || !counts) return fail(h, BB_EINVAL, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const u32 cap = std::min(cap_per_env, h->cfg.max_trades);
+    CUDA_TRY(h, cudaMemcpy2DAsync(counts, 4, h->blobs + offsetof(BookHdr, n_trades), h->blob_stride, 4, h->cfg.n_envs,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    if (cap)
+        CUDA_TRY(h, cudaMemcpy2DAsync(out, (size_t)cap_per_env * sizeof(TradeRec), h->tr, (size_t)h->cfg.max_trades * sizeof(TradeRec),
+                                      (size_t)cap * sizeof(TradeRec), h->cfg.n_envs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
 int bb_order_keys(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* key_time) {
     CHECK_H(h);
     CHECK_ENV(h, env);

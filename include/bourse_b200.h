@@ -291,6 +291,23 @@ int bb_orders(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint8_t* s
 /* PyTrade columns (rust/src/types.rs:4-17) */
 int bb_trades(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* t, uint8_t* side_is_bid,
               uint32_t* price, uint32_t* vol, uint64_t* active_id, uint64_t* passive_id);
+/* Bulk export of EVERY env's order table / trade log in the device record layout (one strided copy each): what
+ * sim_runner leaves in host memory on the reference (orderbook.rs:113-115).  out[n_envs][cap_per_env] records, row e holds
+ * env e's first min(count, cap_per_env) records; counts[n_envs] = records the env has.  bb_order_rec.meta: bits 0-2 Status
+ * (types.rs:51-75), bit 3 side is bid; `link` words are engine-private. */
+typedef struct {
+    uint32_t price, vol, link0, link1;
+    uint64_t key_time;
+    uint32_t meta, start_vol;
+    uint64_t arr_time, end_time;
+    uint32_t trader, pad[3];
+} bb_order_rec; /* 64 bytes */
+typedef struct {
+    uint64_t t;
+    uint32_t price, vol, active_id, passive_id, side_is_bid, pad;
+} bb_trade_rec; /* 32 bytes */
+int bb_orders_all(bb_handle* h, uint32_t cap_per_env, bb_order_rec* out, uint32_t* counts);
+int bb_trades_all(bb_handle* h, uint32_t cap_per_env, bb_trade_rec* out, uint32_t* counts);
 /* time component of each order's queue key (OrderEntry.key.2, orderbook.rs:36-44); 0 for orders that never rested */
 int bb_order_keys(bb_handle* h, uint32_t env, uint64_t first, uint64_t n, uint64_t* key_time);
 int bb_order_status(bb_handle* h, uint32_t env, uint64_t order_id, uint8_t* status);

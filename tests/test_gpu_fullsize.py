@@ -54,12 +54,15 @@ def _check_book_conservation(env, e, final_obs):
 C3_L1_CHECKSUM = {}
 
 
-@pytest.mark.parametrize("engine_kw", [dict(price_window=(20, 180), live_cap=128), dict()], ids=["dense_bench_config", "paged"])
+@pytest.mark.parametrize("engine_kw", ["bench", dict()], ids=["dense_bench_config", "paged"])
 def test_c3_full_size(core, oracle, engine_kw):
     """Config C3: 4096 envs x (50+50) RandomAgents x 1000 env-steps, level-1 observations.  `dense_bench_config` is
-    exactly the kernel / configuration pair bench.py times (k_sim<DENSE,0,0>, price_window=(20,180), live_cap=128)."""
+    exactly the kernel / configuration pair bench.py times (k_sim<DENSE,0,0> with core.dense_kwargs_for(groups))."""
     n_envs, n_steps, seed = 4096, 1000, 101
     groups = workloads.c3_groups()
+    if engine_kw == "bench":   # what bench.py passes: the window and slot count derived from the population
+        engine_kw = core.dense_kwargs_for(groups)
+        assert engine_kw == dict(price_window=(20, 179), live_cap=100)
     env = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L1, max_orders=65536, max_trades=65536,
                           max_steps=n_steps, max_queue=128, **engine_kw)
     env.set_agents(groups)
@@ -96,6 +99,16 @@ def test_c3_full_size(core, oracle, engine_kw):
         assert v == int(hist[e, :, 0].astype(np.uint64).sum())
         tv_sum += v; tr_sum += n
     assert tr_sum > 20_000 * len(sample)
+    # bulk export (bb_trades_all / bb_orders_all) agrees with the per-env reads
+    rec_t, n_t = env.trades_all(40960)
+    rec_o, n_o = env.orders_all(49152)
+    assert int(n_t.sum()) == st["trades"] and int(n_o.sum()) == st["orders_created"]
+    for e in sample[:4]:
+        gt, go = env.trades_arrays(e), env.orders_arrays(e)
+        assert n_t[e] == len(gt["vol"]) and n_o[e] == len(go["vol"])
+        assert np.array_equal(rec_t[e, :n_t[e]]["vol"], gt["vol"]) and np.array_equal(rec_t[e, :n_t[e]]["passive_id"], gt["passive"].astype(np.uint32))
+        assert np.array_equal(rec_o[e, :n_o[e]]["price"], go["price"]) and np.array_equal(rec_o[e, :n_o[e]]["meta"] & 7, go["status"])
+        assert np.array_equal(rec_o[e, :n_o[e]]["end_time"], go["end_time"])
 
 
 def test_c4_shard_full_size(core, oracle):

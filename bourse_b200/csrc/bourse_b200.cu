@@ -225,16 +225,20 @@ DeepOff deep_layout(u32 W) {
     const u32 nw = W / 32;
     o.bm = DP_OFF_BM;
     o.sm = o.bm + 8u * nw;
-    o.lv = align_up(o.sm + 8u * DP_NS, 16);
-    o.image_bytes = align_up(o.lv + 16u * W, 128);
+    o.lvol = align_up(o.sm + 8u * DP_NS, 16);
+    o.lcnt = o.lvol + 4u * W;
+    o.lht = o.lcnt + 4u * W;
+    o.image_bytes = align_up(o.lht + 8u * W, 128);
     u32 off = o.image_bytes;
     o.ctag = off; off += 4u * DP_NC;
     o.cdat = off; off += DP_CHUNK_BYTES * DP_NC;
     o.ev_ins = off; off += 1024u * DP_RB;
     o.ev_rec = off; off += 1024u * DP_RB;
     o.ev_rf = off; off += 16u;
+    o.cmd = off; off += 32u * DP_CCAP;
     o.ret = off; off += DP_RENT * DP_RCAP;
     o.dirty = off; off += 4u * DP_DIRTY;
+    o.swept = off; off += 4u * DP_SWEPT;
     o.ctl = off; off += 4u * CT_WORDS;
     o.bar = off; off += 8u * (DP_RB + 1u);
     o.total = align_up(off, 128);
@@ -279,7 +283,7 @@ int init_books(bb_handle* h) {
     const bb_config& c = h->cfg;
     if (h->eng == ENG_DEEP) {
         k_init_deep<<<c.n_envs, 128, 0, h->stream>>>(h->blobs, h->blob_stride, c.n_envs, c.start_time, c.trading ? 1u : 0u, h->d_seeds,
-                                                     h->dp.bm, h->dp.lv - h->dp.bm);
+                                                     h->dp.bm, h->dp.lht - h->dp.bm);  // bitmaps, summaries, level volumes and order counts start at zero
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
         h->status_valid = false;
@@ -367,7 +371,7 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
             CUDA_TRY(h, cudaFuncSetAttribute(k_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
             h->deep_attr_set = true;
         }
-        k_deep<<<h->cfg.n_envs, 96, h->dp.total, h->stream>>>(p);
+        k_deep<<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
         CUDA_TRY(h, cudaGetLastError());
         h->recorded_host = -1;
         return BB_OK;

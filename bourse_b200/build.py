@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbourse_b200.so")
 SOURCES = ["bourse_b200.cu", "comm.cu"]
-HEADERS = ["kernels.cuh", "book.cuh", "dense.cuh", "deep.cuh", "philox.cuh", "tma.cuh", os.path.join("..", "..", "include", "bourse_b200.h")]
+HEADERS = ["kernels.cuh", "book.cuh", "dense.cuh", "deep.cuh", "deepw.cuh", "philox.cuh", "tma.cuh", os.path.join("..", "..", "include", "bourse_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-ldl"]
 

@@ -124,11 +124,28 @@ __device__ __forceinline__ void cp_async16(u32 smem_dst, u64 gmem_src) {
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+// Developer profiling (-DDP_PROF): cycles book 0's warps spend in each kind of wait, printed at the end of the launch.
+#ifdef DP_PROF
+__device__ unsigned long long g_dp_prof[64];
+#define DP_T0 const long long dp_t0_ = clock64();
+#define DP_ADD(slot)                                                                  \
+    if (blockIdx.x == 0) {                                                            \
+        atomicAdd(&g_dp_prof[slot], (unsigned long long)(clock64() - dp_t0_));        \
+        atomicAdd(&g_dp_prof[32 + (slot)], 1ull);                                     \
+    }
+#else
+#define DP_T0
+#define DP_ADD(slot)
+#endif
 // bounded spin on a control word; returns false when the wait ran out or another warp aborted
 #define DP_SPIN_MAX (1u << 25)
-template <class F> __device__ __forceinline__ bool dp_wait(u32 ctl, F cond) {
+template <class F> __device__ __forceinline__ bool dp_wait(u32 ctl, F cond, int prof_slot = 0) {
+    DP_T0
     for (u32 spin = 0; spin < DP_SPIN_MAX; ++spin) {
-        if (cond()) return true;
+        if (cond()) {
+            DP_ADD(prof_slot)
+            return true;
+        }
         if ((spin & 255u) == 255u && ld_acq(ctl + CT_ABORT)) return false;
     }
     st_rel(ctl + CT_ABORT, 1u);
@@ -218,7 +235,7 @@ __device__ __forceinline__ bool ld_cmd(const LadReg& r, LadSt& s, uint4 a, uint4
         if (!dp_wait(r.ctl, [&] {
                 s.cmd_room = ld_acq(r.ctl + CT_CMD_DONE) + DP_CCAP;
                 return s.cmd_tail < s.cmd_room;
-            }))
+            }, 4))
             return false;
     }
     const u32 ea = r.cmd + 32u * (s.cmd_tail & (DP_CCAP - 1u));
@@ -237,7 +254,7 @@ __device__ __forceinline__ void ld_publish(const LadReg& r, LadSt& s) {
 __device__ __forceinline__ bool ld_sync_queue(const LadReg& r, LadSt& s) {
     ld_publish(r, s);
     if (ld_acq(r.ctl + CT_CMD_DONE) == s.cmd_tail) return true;
-    return dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_CMD_DONE) == s.cmd_tail; });
+    return dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_CMD_DONE) == s.cmd_tail; }, 5);
 }
 // the volume of level q of `side` just reached zero: is the level empty?  Without zero-volume orders: yes.
 __device__ __forceinline__ bool ld_emptied(const LadReg& r, LadSt& s, u32 q, bool& aborted) {
@@ -301,7 +318,7 @@ __device__ __forceinline__ bool qu_ret_space(const QueReg& r, QueSt& s, u32 n) {
     return dp_wait(r.ctl, [&] {
         s.ret_room = ld_acq(r.ctl + CT_RET_DONE) + DP_RCAP;
         return s.ret_tail + n <= s.ret_room;
-    });
+    }, 8);
 }
 __device__ __forceinline__ void qu_ret_write(const QueReg& r, u32 idx, uint4 a, uint4 b) {
     const u32 ea = r.ret + DP_RENT * (idx & (DP_RCAP - 1u));

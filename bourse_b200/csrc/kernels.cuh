@@ -71,6 +71,7 @@ struct KParams {
     DeepOff dp;
     unsigned char* dp_pool;
     u32 dp_chunks;
+    u32 dp_fast;  // k_deepw: 1 = batch-parallel passes enabled (0: every event through the serial path; debugging)
 };
 
 // Values the optimiser would otherwise rematerialise at every use (S2R for the lane id, cvta + multiply
@@ -1027,14 +1028,15 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
 #define DPF_MARKET (1u << 16)      // the order takes the market path: BB_F_MARKET, or a limit price equal to the sentinel (N3)
 #define DPF_CAP_ORDERS (1u << 17)  // a NEW row whose id would not fit the order table
 
+template <u32 RB>
 __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, const bb_instr* ins, u32 n, u64 oh,
                                               u32 next_id) {
     const u32 ctl = sb + o.ctl;
     const u32 nb = (n + 31u) >> 5;
     for (u32 b = 0; b < nb; ++b) {
-        const u32 slot = b & (DP_RB - 1u);
-        if (b >= DP_RB) {
-            if (!dp_wait(ctl, [&] { return ld_acq(ctl + CT_EV_CONSUMED) + DP_RB > b; })) return;
+        const u32 slot = b & (RB - 1u);
+        if (b >= RB) {
+            if (!dp_wait(ctl, [&] { return ld_acq(ctl + CT_EV_CONSUMED) + RB > b; }, 1)) return;
         }
         const u32 cnt = min(32u, n - 32u * b);
         const u32 ia = sb + o.ev_ins + 1024u * slot, bar = sb + o.bar + 8u + 8u * slot;
@@ -1044,9 +1046,13 @@ __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o
             mbar_expect_tx_a(bar, cnt * 32u);
             bulk_g2s_a(ia, ins + 32u * (size_t)b, cnt * 32u, bar);
         }
-        if (!mbar_wait_a(bar, (b / DP_RB) & 1u)) {
-            st_rel(ctl + CT_ABORT, 1u);
-            return;
+        {
+            DP_T0
+            if (!mbar_wait_a(bar, (b / RB) & 1u)) {
+                st_rel(ctl + CT_ABORT, 1u);
+                return;
+            }
+            if (lane == 0u) { DP_ADD(2) }
         }
         // the record writes of every event below this index are performed and fenced: sampled BEFORE the loads below
         const u32 rf = ld_acq(ctl + CT_EV_RETIRED);
@@ -1087,9 +1093,13 @@ __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o
         }
         next_id += __popc(new_mask);
         if (next_id > p.geo.max_orders) next_id = p.geo.max_orders;  // (later NEW rows fail the same way)
-        cp_async_wait_all();
-        if (new_mask) __threadfence();  // the record halves are in place before anything can name these ids
-        __syncwarp();
+        {
+            DP_T0
+            cp_async_wait_all();
+            if (new_mask) __threadfence();  // the record halves are in place before anything can name these ids
+            __syncwarp();
+            if (lane == 0u) { DP_ADD(3) }
+        }
         if (lane == 0u) {
             sts(sb + o.ev_rf + 4u * slot, rf);
             st_rel(ctl + CT_EV_READY, b + 1u);
@@ -1097,6 +1107,8 @@ __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o
     }
 }
 
+// TRADES: fill entries also append to the trade log in ring order (deep.cuh); k_deepw's book warp writes the log itself
+template <u32 RCAP, bool TRADES>
 __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, u64 oh, u64 tr, u32 n_tr0) {
     const u32 ctl = sb + o.ctl;
     u32 head = 0, n_tr = n_tr0, err = 0, ev_pub = 0;
@@ -1114,13 +1126,13 @@ __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& 
                 st_rel(ctl + CT_EV_RETIRED, q_ev);
             }
             return tail != head || fin;
-        });
+        }, lane == 0u ? 10 : 31);
         if (!ok || (tail == head && fin)) break;
         const u32 n = min(32u, tail - head);
         // entry: a = {kind | side << 8 | status << 12 | filled << 16, order id, ., .}, b = {t lo, t hi, ., .}
         uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
         if (lane < n) {
-            const u32 ea = sb + o.ret + DP_RENT * ((head + lane) & (DP_RCAP - 1u));
+            const u32 ea = sb + o.ret + DP_RENT * ((head + lane) & (RCAP - 1u));
             a = lds128(ea);
             b = lds128(ea + 16u);
         }
@@ -1132,7 +1144,7 @@ __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& 
         const u32 rank = __popc(grp & ((1u << lane) - 1u));
         const u32 rounds = __reduce_max_sync(BB_FULL, rank) + 1u;
         const u64 ra = oh + (u64)a.y * ORD_STRIDE;
-        if (kind == RK_FILL) {  // {., passive id, traded vol, passive vol left} {t, price, active id}
+        if (TRADES && kind == RK_FILL) {  // {., passive id, traded vol, passive vol left} {t, price, active id}
             const u32 ti = n_tr + __popc(fm & ((1u << lane) - 1u));
             if (ti < p.geo.max_trades) {
                 const u64 ta = tr + (u64)ti * 32u;
@@ -1174,8 +1186,15 @@ __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& 
         }
         n_tr += __popc(fm);
         head += n;
-        __threadfence();
-        __syncwarp();
+        {
+            DP_T0
+            __threadfence();
+            __syncwarp();
+            if (lane == 0u) { DP_ADD(11) }
+        }
+#ifdef DP_PROF
+        if (lane == 0u && blockIdx.x == 0) atomicAdd(&g_dp_prof[12], (unsigned long long)n);
+#endif
         if (lane == 0u) {
             st_rel(ctl + CT_RET_DONE, head);
             // every entry up to the tail read above is out: so is everything of the events counted before that tail
@@ -1232,7 +1251,7 @@ __device__ __forceinline__ void dp_queue_warp(const KParams& p, const DeepOff& o
                             fin = ld_acq(r.ctl + CT_FIN_L) != 0u;  // read before the tail: set after the last command
                             tail = ld_acq(r.ctl + CT_CMD_TAIL);
                             return tail != s.cmd_head || fin;
-                        })) {
+                        }, 7)) {
                         aborted = true;
                         break;
                     }
@@ -1290,7 +1309,11 @@ __device__ __forceinline__ void dp_queue_warp(const KParams& p, const DeepOff& o
             const u32 q = __shfl_sync(BB_FULL, w_q, 0), opp = __shfl_sync(BB_FULL, w_opp, 0), take = __shfl_sync(BB_FULL, w_take, 0);
             const u32 exh = __shfl_sync(BB_FULL, w_exh, 0), id = __shfl_sync(BB_FULL, w_id, 0);
             const u32 tlo = __shfl_sync(BB_FULL, w_tlo, 0), thi = __shfl_sync(BB_FULL, w_thi, 0), price = __shfl_sync(BB_FULL, w_price, 0);
-            qu_sweep_warp(r, s, lane, q, opp, take, exh != 0u, id, tlo, thi, price);
+            {
+                DP_T0
+                qu_sweep_warp(r, s, lane, q, opp, take, exh != 0u, id, tlo, thi, price);
+                if (lane == 0u) { DP_ADD(9) }
+            }
             if (lane == 0u) {
                 if (ld_acq(r.ctl + CT_ABORT)) aborted = true;
                 s.cmd_head += 1;
@@ -1340,11 +1363,14 @@ __global__ void __launch_bounds__(128, 2) k_deep(const __grid_constant__ KParams
     }
     __syncthreads();
     const u32 n_tr0 = min((u32)lds64(sb + HDR_NTRADES_TOTAL), p.geo.max_trades);
+#ifdef DP_PROF
+    const long long dp_k0 = clock64();
+#endif
 
     if (warp == 1u) {
-        dp_fetch_warp(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
+        dp_fetch_warp<DP_RB>(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
     } else if (warp == 2u) {
-        dp_retire_warp(p, o, sb, lane, oh, tr, n_tr0);
+        dp_retire_warp<DP_RCAP, true>(p, o, sb, lane, oh, tr, n_tr0);
     } else if (warp == 3u) {
         dp_queue_warp(p, o, sb, lane, env);
     } else {
@@ -1391,7 +1417,7 @@ __global__ void __launch_bounds__(128, 2) k_deep(const __grid_constant__ KParams
                     const u32 bslot = (ev_i >> 5) & (DP_RB - 1u);
                     if ((ev_i & 31u) == 0u) {
                         const u32 b = ev_i >> 5;
-                        if (ld_acq(r.ctl + CT_EV_READY) <= b && !dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_READY) > b; })) {
+                        if (ld_acq(r.ctl + CT_EV_READY) <= b && !dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_READY) > b; }, 6)) {
                             aborted = true;
                             break;
                         }
@@ -1433,11 +1459,11 @@ __global__ void __launch_bounds__(128, 2) k_deep(const __grid_constant__ KParams
                             if (max(dv, sv) > rf) {  // doubtful: let the pipeline drain up to that event, read again
                                 ld_publish(r, s);
                                 const u32 need = dv > rf ? dv : 0u;   // (a stale price makes `sv` meaningless: settle `dv` first)
-                                if (need && !dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_RETIRED) >= need; })) { aborted = true; break; }
+                                if (need && !dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_RETIRED) >= need; }, 13)) { aborted = true; break; }
                                 a = ldg128_cg(r.oh + (u64)id * ORD_STRIDE);
                                 const u32 sv2 = lds(r.swept + 4u * ((a.x - r.win_lo) & (DP_SWEPT - 1u)));
                                 if (sv2 > rf) {
-                                    if (!dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_RETIRED) >= sv2; })) { aborted = true; break; }
+                                    if (!dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_RETIRED) >= sv2; }, 14)) { aborted = true; break; }
                                     a = ldg128_cg(r.oh + (u64)id * ORD_STRIDE);
                                 }
                                 c = ldg128_cg(r.oh + (u64)id * ORD_STRIDE + 16u);
@@ -1625,6 +1651,17 @@ __global__ void __launch_bounds__(128, 2) k_deep(const __grid_constant__ KParams
         }
     }
     __syncthreads();
+#ifdef DP_PROF
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const char* nm[16] = {"-", "F:wait_consumed", "F:tma", "F:cpasync+fence", "L:cmd_room", "L:sync_queue", "L:wait_ev", "Q:wait_cmd",
+                              "Q:ret_room", "Q:warp_sweep", "R:wait", "R:fence", "R:entries", "L:doubt_dirty", "L:doubt_swept", "-"};
+        printf("k_deep prof: n=%u cycles=%lld\n", n, clock64() - dp_k0);
+        for (int i = 1; i < 15; ++i) {
+            printf("  %-16s cycles %12llu  count %10llu\n", nm[i], g_dp_prof[i], g_dp_prof[32 + i]);
+            g_dp_prof[i] = 0; g_dp_prof[32 + i] = 0;
+        }
+    }
+#endif
     if (threadIdx.x == 0) {
         // the trade counters: the queue warp made the fills
         const u32 fills = lds(ctl + CT_QNTR);
@@ -1633,6 +1670,203 @@ __global__ void __launch_bounds__(128, 2) k_deep(const __grid_constant__ KParams
         sts(sb + HDR_NTRADES, (u32)min(tt, (u64)p.geo.max_trades));
         sts64(sb + HDR_NTRANS, lds64(sb + HDR_NTRANS) + fills);  // transitions: one per fill and one per applied event
         u32 err = lds(ctl + CT_RERR) | lds(ctl + CT_QERR) | lds(ctl + CT_LERR);
+        if (ld_acq(ctl + CT_ABORT)) err |= 0x80000000u;
+        sts(sb + HDR_ERR, lds(sb + HDR_ERR) | (err & 0x7FFFFFFFu));
+        if (err) atomicOr(p.err_flag, err);
+        fence_proxy_async();
+        bulk_s2g_a(p.blobs + (size_t)env * p.blob_stride, sb, o.image_bytes);
+        bulk_commit();
+        bulk_wait_all<0>();
+    }
+}
+
+}  // namespace bb
+#include "deepw.cuh"
+namespace bb {
+
+// ---------------------------------------------------------------------------------------------------
+// Deep-book replay kernel, batch-parallel (deepw.cuh): one CTA per book; warp 0 = the book (a batch of 32 events, one lane
+// each), warp 1 = fetch, warp 2 = retire.  Same blob image, chunk pool, order records and trade log as k_deep.
+__global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 sb = smem_u32(smem);
+    const DeepOff& o = p.dp;
+    const u32 ctl = sb + o.ctl;
+    const u32 env = blockIdx.x;
+    if (env >= p.n_envs) return;
+    const u64 oh = (u64)(p.ord + (size_t)env * p.geo.max_orders);
+    const u64 tr = (u64)(p.tr + (size_t)env * p.geo.max_trades);
+    const u64 off = p.offsets[env];
+    const u32 n = (u32)(p.offsets[env + 1] - off);
+    const bb_instr* ins = p.instrs + off;
+    // ---- set-up: barriers, control words, cache tags, filter; then the book image (one bulk copy)
+    if (threadIdx.x == 0) {
+        for (u32 i = 0; i <= DW_RB; ++i) mbar_init_a(sb + o.bar + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (u32 i = threadIdx.x; i < CT_WORDS; i += blockDim.x) sts(ctl + 4u * i, 0u);
+    for (u32 i = threadIdx.x; i < DW_NC; i += blockDim.x) sts(sb + o.ctag + 4u * i, BB_NIL);
+    for (u32 i = threadIdx.x; i < DW_DIRTY; i += blockDim.x) sts(sb + o.dirty + 4u * i, 0u);
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx_a(sb + o.bar, o.image_bytes);
+        bulk_g2s_a(sb, p.blobs + (size_t)env * p.blob_stride, o.image_bytes, sb + o.bar);
+        if (!mbar_wait_a(sb + o.bar, 0u)) st_rel(ctl + CT_ABORT, 1u);
+    }
+    __syncthreads();
+    const u32 n_tr0 = min((u32)lds64(sb + HDR_NTRADES_TOTAL), p.geo.max_trades);
+#ifdef DP_PROF
+    const long long dp_k0 = clock64();
+#endif
+
+    if (warp == 1u) {
+        dp_fetch_warp<DW_RB>(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
+    } else if (warp == 2u) {
+        dp_retire_warp<DW_RCAP, false>(p, o, sb, lane, oh, tr, n_tr0);
+    } else if (warp == 0u) {
+        // ---- the book warp ---------------------------------------------------------------------------------------
+        BkReg r;
+        r.lvol = dp_keep32(sb + o.lvol);
+        r.lcnt = dp_keep32(sb + o.lcnt);
+        r.lht = dp_keep32(sb + o.lht);
+        r.bma = dp_keep32(sb + o.bm);
+        r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
+        r.sma = dp_keep32(sb + o.sm);
+        r.smb = dp_keep32(sb + o.sm + 4u * DP_NS);
+        r.ctag = dp_keep32(sb + o.ctag);
+        r.cdat = dp_keep32(sb + o.cdat);
+        r.ret = dp_keep32(sb + o.ret);
+        r.dirty = dp_keep32(sb + o.dirty);
+        r.ctl = dp_keep32(ctl);
+        r.fs = dp_keep32(sb + DP_OFF_FS);
+        r.win_lo = p.geo.d_win_lo; r.W = p.geo.d_levels; r.max_orders = p.geo.max_orders;
+        r.n_chunks = p.dp_chunks; r.max_trades = p.geo.max_trades;
+        r.oh = dp_keep64(oh);
+        r.chunks = dp_keep64((u64)(p.dp_pool + (size_t)env * p.dp_chunks * DP_CHUNK_BYTES));
+        r.tr = dp_keep64(tr);
+        const u32 ev_ins = dp_keep32(sb + o.ev_ins), ev_rec = dp_keep32(sb + o.ev_rec);
+        BkSt s;
+        s.t = lds64(sb + HDR_T);
+        s.max_key_time = lds64(sb + HDR_MAXKT);
+        s.n_orders = lds(sb + HDR_NORDERS);
+        s.trade_vol = lds(sb + HDR_TRADEVOL);
+        s.vol_ask = lds(sb + HDR_SIDEVOL);
+        s.vol_bid = lds(sb + HDR_SIDEVOL + 4u);
+        s.bq_ask = lds(sb + HDR_BESTQ);
+        s.bq_bid = lds(sb + HDR_BESTQ + 4u);
+        s.flags = (lds(sb + HDR_TRADING) ? FL_TRADING : 0u) | (lds(sb + HDR_HASBEST) ? FL_HAS_ASK : 0u) |
+                  (lds(sb + HDR_HASBEST + 4u) ? FL_HAS_BID : 0u);
+        s.err = 0u;
+        s.d_instr = s.d_applied = 0u;
+        s.zv = lds(sb + HDR_FREETOP);
+        s.bump = lds(sb + DP_OFF_BUMP);
+        s.n_free = lds(sb + DP_OFF_NFREE);
+        s.n_tr = n_tr0;
+        s.ret_tail = s.ret_pub = 0u;
+        s.ret_room = DW_RCAP;
+#ifdef DP_PROF
+        s.pf_pass = s.pf_par = s.pf_ser = 0u;
+        for (int i = 0; i < 8; ++i) s.pf_reason[i] = 0u;
+#endif
+        const u32 n_orders0 = s.n_orders, trade_vol0 = s.trade_vol;
+        const u32 fast = p.dp_fast;
+        u32 lane_err = 0u;
+        bool aborted = false;
+        const u32 nb = (n + 31u) >> 5;
+        for (u32 b = 0; b < nb && !aborted; ++b) {
+            const u32 bslot = b & (DW_RB - 1u);
+            if (!bk_wait(r, lane, [&] { return ld_acq(r.ctl + CT_EV_READY) > b; }, 6)) { aborted = true; break; }
+            const u32 rf = lds(sb + o.ev_rf + 4u * bslot);
+            const u32 cnt = min(32u, n - 32u * b);
+            uint4 x = make_uint4(0, 0, 0, 0), y = x, a = x, c = x;
+            if (lane < cnt) {
+                const u32 eo = 1024u * bslot + 32u * lane;
+                x = lds128(ev_ins + eo);
+                y = lds128(ev_ins + eo + 16u);
+                a = lds128(ev_rec + eo);
+                c = lds128(ev_rec + eo + 16u);
+            }
+            u32 pending = cnt >= 32u ? BB_FULL : ((1u << cnt) - 1u);
+            while (pending) {
+                u32 obs_lane = 32u;
+                if (!bk_batch(r, s, lane, pending, x, y, a, c, 32u * b, rf, fast, lane_err, obs_lane)) { aborted = true; break; }
+                if (obs_lane < 32u) {  // Level2DataRecords::append_record (data.rs:44-56) for a row flagged BB_F_EMIT
+                    const u32 bid = (s.flags & FL_HAS_BID) ? r.win_lo + s.bq_bid : 0u;
+                    const u32 ask = (s.flags & FL_HAS_ASK) ? r.win_lo + s.bq_ask : 0xFFFFFFFFu;
+                    u32 w0, w1;
+                    bk_obs(r, p.geo.tick, lane, s.trade_vol, bid, ask, s.vol_ask, s.vol_bid, &w0, &w1);
+                    // (a level-1 record is the first 9 words of the level-2 one: words 5..8 are the touch level of each side)
+                    const u32 nrec = lds(sb + HDR_NSTEPS);
+                    __syncwarp();
+                    if (nrec < p.max_steps) {
+                        const u64 dst = (u64)(p.hist + (size_t)env * p.hist_env_stride + (size_t)nrec * p.obs_words);
+                        if (lane < p.obs_words) stg32(dst + 4u * lane, w0);
+                        if (lane + 32u < p.obs_words) stg32(dst + 4u * (lane + 32u), w1);
+                        if (lane == 0u) sts(sb + HDR_NSTEPS, nrec + 1u);
+                    } else {
+                        s.err |= ERR_CAP_STEPS;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0u) st_rel(r.ctl + CT_EV_CONSUMED, b + 1u);
+        }
+        // ---- the header goes back into the image; the retire warp drains what is left and exits on FIN
+        lane_err = __reduce_or_sync(BB_FULL, lane_err);
+        __syncwarp();
+        if (lane == 0u) {
+            st_rel(r.ctl + CT_RET_TAIL, s.ret_tail);
+            st_rel(r.ctl + CT_FIN, 1u);
+            sts64(sb + HDR_T, s.t);
+            sts64(sb + HDR_MAXKT, s.max_key_time);
+            sts64(sb + HDR_NCREATED, lds64(sb + HDR_NCREATED) + (s.n_orders - n_orders0));
+            sts(sb + HDR_NORDERS, s.n_orders);
+            sts(sb + HDR_TRADEVOL, s.trade_vol);
+            sts(sb + HDR_SIDEVOL, s.vol_ask);
+            sts(sb + HDR_SIDEVOL + 4u, s.vol_bid);
+            sts(sb + HDR_BESTQ, s.bq_ask);
+            sts(sb + HDR_BESTQ + 4u, s.bq_bid);
+            sts(sb + HDR_TRADING, (s.flags & FL_TRADING) ? 1u : 0u);
+            sts(sb + HDR_HASBEST, (s.flags & FL_HAS_ASK) ? 1u : 0u);
+            sts(sb + HDR_HASBEST + 4u, (s.flags & FL_HAS_BID) ? 1u : 0u);
+            sts(sb + HDR_FREETOP, s.zv);
+            sts(sb + DP_OFF_BUMP, s.bump);
+            sts(sb + DP_OFF_NFREE, s.n_free);
+            sts64(sb + HDR_NINSTR, lds64(sb + HDR_NINSTR) + s.d_instr);
+            // traded volume: trade_vol is never reset in replay mode; transitions: one per applied event and one per fill
+            sts64(sb + HDR_VOLUME, lds64(sb + HDR_VOLUME) + (u32)(s.trade_vol - trade_vol0));
+            sts64(sb + HDR_NTRANS, lds64(sb + HDR_NTRANS) + s.d_applied + (s.n_tr - n_tr0));
+            sts(ctl + CT_LERR, s.err | lane_err);
+            sts(ctl + CT_QNTR, s.n_tr - n_tr0);
+            if (aborted) st_rel(ctl + CT_ABORT, 1u);
+#ifdef DP_PROF
+            if (blockIdx.x == 0)
+                printf("k_deepw book warp: passes %u, events in parallel passes %u, serial events %u (emit %u state %u touch %u doubt %u same-id %u "
+                       "level-empty %u take %u other %u)\n", s.pf_pass, s.pf_par, s.pf_ser, s.pf_reason[0], s.pf_reason[1], s.pf_reason[2],
+                       s.pf_reason[3], s.pf_reason[4], s.pf_reason[5], s.pf_reason[6], s.pf_reason[7]);
+#endif
+        }
+    }
+    __syncthreads();
+#ifdef DP_PROF
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const char* nm[16] = {"-", "F:wait_consumed", "F:tma", "F:cpasync+fence", "-", "-", "B:wait_ev", "-",
+                              "B:ret_room", "-", "R:wait", "R:fence", "R:entries", "B:doubt", "-", "-"};
+        printf("k_deepw prof: n=%u cycles=%lld\n", n, clock64() - dp_k0);
+        for (int i = 1; i < 15; ++i) {
+            if (nm[i][0] != '-') printf("  %-16s cycles %12llu  count %10llu\n", nm[i], g_dp_prof[i], g_dp_prof[32 + i]);
+            g_dp_prof[i] = 0; g_dp_prof[32 + i] = 0;
+        }
+    }
+#endif
+    if (threadIdx.x == 0) {
+        const u32 fills = lds(ctl + CT_QNTR);
+        const u64 tt = lds64(sb + HDR_NTRADES_TOTAL) + fills;
+        sts64(sb + HDR_NTRADES_TOTAL, tt);
+        sts(sb + HDR_NTRADES, (u32)min(tt, (u64)p.geo.max_trades));
+        u32 err = lds(ctl + CT_RERR) | lds(ctl + CT_LERR);
         if (ld_acq(ctl + CT_ABORT)) err |= 0x80000000u;
         sts(sb + HDR_ERR, lds(sb + HDR_ERR) | (err & 0x7FFFFFFFu));
         if (err) atomicOr(p.err_flag, err);

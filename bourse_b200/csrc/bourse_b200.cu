@@ -232,9 +232,9 @@ DeepOff deep_layout(u32 W, bool wide) {
     o.lht = o.lcnt + 4u * W;
     o.image_bytes = align_up(o.lht + 8u * W, 128);
     u32 off = o.image_bytes;
-    const u32 nc = wide ? DW_NC : DP_NC, rb = wide ? DW_RB : DP_RB, rcap = wide ? DW_RCAP : DP_RCAP;
-    o.ctag = off; off += 4u * nc;
-    o.cdat = off; off += DP_CHUNK_BYTES * nc;
+    const u32 rb = wide ? DW_RB : DP_RB, rcap = wide ? DW_RCAP : DP_RCAP;
+    o.ctag = off; off += wide ? 0u : 4u * DP_NC;
+    o.cdat = off; off += wide ? DW_SCRATCH : DP_CHUNK_BYTES * DP_NC;  // (k_deepw: its scratch block)
     o.ev_ins = off; off += 1024u * rb;
     o.ev_rec = off; off += 1024u * rb;
     o.ev_rf = off; off += 16u;

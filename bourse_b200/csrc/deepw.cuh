@@ -4,20 +4,25 @@
 // arrays + per-side bitmaps in shared memory, chunked array queues in HBM, fetch warp in front, retire warp behind.  What
 // changes is how the book itself advances.  deep.cuh runs one event at a time on lane 0 of two warps (ladder, queue):
 // ~200 dependent instructions each per event, 1250 cycles per event on a B200 SM (profiles/r02_summary.md) — a single
-// thread of a GPU is a slow CPU.  Here ONE warp owns the book and takes the events of a batch (32) ONE LANE EACH:
+// thread of a GPU is a slow CPU.  Here ONE warp owns the book and cuts an event's work in two:
 //
-//   classify   every lane decides, under the hypothesis that best bid / best ask stay where they are, what its event does:
-//              rest on a level behind the touch (ADD), leave a level (REM: cancel, or the first half of a replace), shrink in
-//              place (RED), or trade against the touch level of the other side (X) without emptying it.  Anything else —
-//              an event that moves the touch or empties a level, a zero-volume order, a doubtful prefetched record, two
-//              events naming one order, a market-data record, trading switched off — is COMPLEX;
-//   parallel   the events before the first complex one are applied together: level volumes / counts with shared-memory
-//              atomics, queue positions of the ADDs by __match_any_sync over the level index, and the trades of all X
-//              events by a warp prefix sum over the resting volumes of the touch level's head chunk, in FIFO order, one
-//              trade per passive order (orderbook.rs:429-454, 843-870);
-//   serial     the complex event runs through the whole reference algorithm warp-uniformly (all lanes the same values,
-//              lane 0 stores), after which the rest of the batch is classified again against the new touch.
+//   decode    (32 events, one lane each) everything about an event that does not depend on the book: what kind of
+//             instruction it is, whether the order record the fetch warp prefetched can be trusted (not touched by an event
+//             still on its way to HBM, not named twice in the batch), where the order it names rests.  Anything unusual —
+//             a market-data record, a zero-volume order, a doubtful record, trading switched off, time standing still —
+//             makes the event COMPLEX: it runs alone through the whole reference algorithm (bk_serial);
+//   chain     the price ladder, strictly in event order but nothing else: level volumes, bitmaps, best bid / ask.  It
+//             decides how much an aggressive order takes from each level it crosses and where an order rests, and writes
+//             that down as MICRO-OPS, each on ONE price level: T(ake) q volume, A(ppend) q order, R(emove) q position,
+//             D(ecrease) q position volume;
+//   replay    (32 micro-ops, one lane each) the price-time queues.  Levels are independent, so the micro-ops are grouped
+//             by level (__match_any_sync) and the first lane of every group walks its level's FIFO through the group's
+//             micro-ops in order — all levels of the round at the same time.  Fills are staged with their (micro-op, rank)
+//             key; a warp prefix sum over the fill counts then gives every trade its place in the trade log and in the
+//             retire ring in event order, one trade per passive order in queue order (orderbook.rs:429-454, 843-870).
 //
+// Queue entries are read with ordinary (L1-cached) loads: only this CTA ever touches its book's chunk pool, the head
+// chunks of the levels around the touch stay in L1 (latency close to shared memory), and a lane can walk its level alone.
 // Trades go to the trade log straight from the book warp (their order in the log is the event order, which only this
 // warp knows); order-record updates go through the retire ring as before.
 #pragma once
@@ -26,18 +31,31 @@ namespace bb {
 
 #define DW_RB 4u        // event-ring depth in batches of 32
 #define DW_RCAP 256u    // retire-ring entries
-#define DW_NC 32u       // chunk cache entries (direct mapped by chunk id)
 #define DW_DIRTY 4096u  // touched-order filter buckets (by order id)
+#define DW_MOPS 64u     // micro-op list capacity (32 bytes each); a replay round takes 32
+#define DW_FILLS 192u   // fills staged per flush (16 bytes each): also the largest volume one flush may take
+// scratch block (byte offsets from BkReg::scr)
+#define SC_MOP 0u
+#define SC_EVD (SC_MOP + 32u * DW_MOPS)      // decoded events, 48 bytes per lane
+#define SC_FILL (SC_EVD + 48u * 32u)         // staged fills {micro-op | rank << 8, passive id, traded volume, passive volume left}
+#define SC_NFILL (SC_FILL + 16u * DW_FILLS)  // per micro-op: fills made
+#define SC_POS (SC_NFILL + 4u * DW_MOPS)     // per micro-op: position of the appended entry
+#define SC_SPARE (SC_POS + 4u * DW_MOPS)     // per micro-op: a fresh chunk (bit 31: used)
+#define SC_FREED (SC_SPARE + 4u * DW_MOPS)   // per micro-op: up to two chunks it emptied
+#define SC_FCOUNT (SC_FREED + 8u * DW_MOPS)
+#define SC_SWEPT (SC_FCOUNT + 16u)           // per level (hashed): the last event that took volume from it
+#define DW_SWEPT 256u
+#define DW_SCRATCH (SC_SWEPT + 4u * DW_SWEPT)
 
 __device__ __forceinline__ void reds_add(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ u32 atoms_or(u32 a, u32 v) {
+__device__ __forceinline__ u32 atoms_add(u32 a, u32 v) {
     u32 o;
-    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
     return o;
 }
 
 struct BkReg {  // launch-invariant addresses and limits (pinned in registers)
-    u32 lvol, lcnt, lht, bma, bmb, sma, smb, ctag, cdat, ret, dirty, ctl, fs;
+    u32 lvol, lcnt, lht, bma, bmb, sma, smb, scr, ret, dirty, ctl, fs;
     u32 win_lo, W, max_orders, n_chunks, max_trades;
     u64 oh, chunks, tr;
 };
@@ -48,8 +66,9 @@ struct BkSt {  // the book's scalar state: warp-uniform (every lane holds the sa
     u32 bump, n_free;       // chunk allocator
     u32 n_tr;               // next trade-log index
     u32 ret_tail, ret_room, ret_pub;
+    u32 n_mop, flush_take;  // micro-ops waiting for replay, volume they take
 #ifdef DP_PROF
-    u32 pf_pass, pf_par, pf_ser, pf_reason[8];
+    u32 pf_flush, pf_rounds, pf_mops, pf_ser, pf_reason[8];
 #endif
 };
 __device__ __forceinline__ u32 bk_bm(const BkReg& r, u32 side, u32 w) { return (side ? r.bmb : r.bma) + 4u * w; }
@@ -117,11 +136,7 @@ __device__ __forceinline__ void bk_trade(const BkReg& r, BkSt& s, u32 ti, u32 t_
 }
 
 // ---- chunk pool (warp-uniform; lane 0 stores) --------------------------------------------------------------------------
-__device__ __forceinline__ void bk_chunk_st32(const BkReg& r, u32 c, u32 byte_off, u32 v) {  // write-through store, ONE lane
-    stg32(r.chunks + (u64)c * DP_CHUNK_BYTES + byte_off, v);
-    const u32 slot = c & (DW_NC - 1u);
-    if (lds(r.ctag + 4u * slot) == c) sts(r.cdat + DP_CHUNK_BYTES * slot + byte_off, v);
-}
+__device__ __forceinline__ u64 bk_chunk(const BkReg& r, u32 c) { return r.chunks + (u64)c * DP_CHUNK_BYTES; }
 __device__ __forceinline__ u32 bk_alloc(const BkReg& r, BkSt& s, u32 lane) {
     u32 c;
     if (s.n_free) {
@@ -133,14 +148,7 @@ __device__ __forceinline__ u32 bk_alloc(const BkReg& r, BkSt& s, u32 lane) {
         s.err |= ERR_CAP_PAGES;
         return 0u;  // chunk 0 is never handed out: a safe sink
     }
-    // a fresh chunk is born in the cache (write-through): no load when a sweep reaches it while it is still resident
-    if (lane == 0u) {
-        const u32 slot = c & (DW_NC - 1u);
-        sts(r.ctag + 4u * slot, c);
-        sts(r.cdat + DP_CHUNK_BYTES * slot + 8u * DP_CHUNK_ENTRIES, BB_NIL);
-        stg32(r.chunks + (u64)c * DP_CHUNK_BYTES + 8u * DP_CHUNK_ENTRIES, BB_NIL);
-    }
-    __syncwarp();
+    if (lane == 0u) stg32(bk_chunk(r, c) + 8u * DP_CHUNK_ENTRIES, BB_NIL);
     return c;
 }
 __device__ __forceinline__ void bk_free_chunk(const BkReg& r, BkSt& s, u32 lane, u32 c) {
@@ -204,7 +212,7 @@ __device__ __forceinline__ u32 bk_append(const BkReg& r, BkSt& s, u32 lane, u32 
         u32 c = tail >> 5, idx = tail & 31u;
         if (idx == DP_CHUNK_ENTRIES) {  // tail chunk full: link a new one
             const u32 c2 = bk_alloc(r, s, lane);
-            if (lane == 0u) bk_chunk_st32(r, c, 8u * DP_CHUNK_ENTRIES, c2);
+            if (lane == 0u) stg32(bk_chunk(r, c) + 8u * DP_CHUNK_ENTRIES, c2);
             c = c2;
             idx = 0u;
         }
@@ -213,9 +221,7 @@ __device__ __forceinline__ u32 bk_append(const BkReg& r, BkSt& s, u32 lane, u32 
     }
     if (lane == 0u) {
         sts(r.lcnt + 4u * q, cnt + 1u);
-        const u32 c = pos >> 5, idx = pos & 31u, slot = c & (DW_NC - 1u);
-        stg64(r.chunks + (u64)c * DP_CHUNK_BYTES + 8u * idx, ((u64)vol << 32) | id);
-        if (lds(r.ctag + 4u * slot) == c) sts64(r.cdat + DP_CHUNK_BYTES * slot + 8u * idx, ((u64)vol << 32) | id);
+        stg64(bk_chunk(r, pos >> 5) + 8u * (pos & 31u), ((u64)vol << 32) | id);
     }
     __syncwarp();
     return pos;
@@ -226,7 +232,7 @@ __device__ __forceinline__ void bk_remove(const BkReg& r, BkSt& s, u32 lane, u32
     const u64 ht = lds64(r.lht + 8u * q);
     __syncwarp();
     if (lane == 0u) {
-        bk_chunk_st32(r, pos >> 5, 8u * (pos & 31u), BB_NIL);
+        stg32(bk_chunk(r, pos >> 5) + 8u * (pos & 31u), BB_NIL);
         sts(r.lcnt + 4u * q, cnt <= 1u ? 0u : cnt - 1u);
     }
     if (cnt <= 1u && ((u32)ht >> 5) == ((u32)(ht >> 32) >> 5)) bk_free_chunk(r, s, lane, (u32)ht >> 5);  // a longer all-dead chain is left to the pool
@@ -248,17 +254,8 @@ __device__ __forceinline__ bool bk_sweep(const BkReg& r, BkSt& s, u32 lane, u32 
         const u32 head = (u32)ht, tail = (u32)(ht >> 32);
         const u32 c = head >> 5, idx = head & 31u, tc = tail >> 5;
         const u32 end = (c == tc) ? (tail & 31u) : DP_CHUNK_ENTRIES;
-        const u32 slot = c & (DW_NC - 1u);
-        const u32 ca = r.cdat + DP_CHUNK_BYTES * slot;
-        if (lds(r.ctag + 4u * slot) != c) {  // chunk not resident: one coalesced 256-byte load
-            __syncwarp();
-            const u64 v = ldg64_cg(r.chunks + (u64)c * DP_CHUNK_BYTES + 8u * lane);
-            sts64(ca + 8u * lane, v);
-            if (lane == 0u) sts(r.ctag + 4u * slot, c);
-            __syncwarp();
-        }
-        const u64 e = lds64(ca + 8u * lane);
-        const u32 nc = lds(ca + 8u * DP_CHUNK_ENTRIES);
+        const u64 e = ldg64(bk_chunk(r, c) + 8u * lane);  // the head chunk: one coalesced 256-byte load (L1)
+        const u32 nc = __shfl_sync(BB_FULL, (u32)e, 31);   // (its last 8 bytes are the link)
         const u32 pid = (u32)e, pvol = (u32)(e >> 32);
         const bool live = lane >= idx && lane < end && pid != BB_NIL;
         const u32 v = live ? pvol : 0u;
@@ -285,10 +282,7 @@ __device__ __forceinline__ bool bk_sweep(const BkReg& r, BkSt& s, u32 lane, u32 
             bk_ret_write(r, s.ret_tail + k, make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), pid, tv, pv), make_uint4(t_lo, t_hi, price, id));
             bk_trade(r, s, s.n_tr + k, t_lo, t_hi, price, tv, id, pid, opp, lane_err);
             sts(r.dirty + 4u * (pid & (DW_DIRTY - 1u)), mark);
-            if (!full) {  // the partially filled order stays at the head of its level
-                sts(ca + 8u * lane + 4u, pv);
-                stg32(r.chunks + (u64)c * DP_CHUNK_BYTES + 8u * lane + 4u, pv);
-            }
+            if (!full) stg32(bk_chunk(r, c) + 8u * lane + 4u, pv);  // the partially filled order stays at the head of its level
         }
         take -= traded;
         s.ret_tail += nr;
@@ -410,7 +404,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
                     __syncwarp();
                     if (lane == 0u) {
                         sts(la, lv - (a.y - y.y));
-                        bk_chunk_st32(r, a.z >> 5, 8u * (a.z & 31u) + 4u, y.y);
+                        stg32(bk_chunk(r, a.z >> 5) + 8u * (a.z & 31u) + 4u, y.y);
                     }
                     bk_add_side(s, oside, y.y - a.y);
                     if (y.y == 0u) s.zv = 1u;
@@ -530,119 +524,257 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
 }
 
 // =====================================================================================================================
-// The batch-parallel step.  One side's head chunk while the X events of a pass are applied to it:
-struct SweepSide {
-    u32 L, c, idx, end, tc, ca, nc;  // level, head chunk, first live index, end index, tail chunk, cache address, link (uniform)
-    u32 S, total;                // volume consumed from / resting in this chunk (uniform)
-    u32 nfull, taken;            // orders filled completely in chunks already left behind, volume taken in this pass (uniform)
-    u32 pid, pin, pex;           // this lane's entry: order id, inclusive / exclusive prefix of the resting volumes
-    bool live, ok;
-};
-__device__ __forceinline__ void bk_side_load(const BkReg& r, u32 lane, SweepSide& d) {
-    const u64 ht = lds64(r.lht + 8u * d.L);
-    const u32 head = (u32)ht, tail = (u32)(ht >> 32);
-    d.c = head >> 5;
-    d.idx = head & 31u;
-    d.tc = tail >> 5;
-    d.end = (d.c == d.tc) ? (tail & 31u) : DP_CHUNK_ENTRIES;
-    const u32 slot = d.c & (DW_NC - 1u);
-    d.ca = r.cdat + DP_CHUNK_BYTES * slot;
-    if (lds(r.ctag + 4u * slot) != d.c) {  // chunk not resident: one coalesced 256-byte load
-        __syncwarp();
-        const u64 v = ldg64_cg(r.chunks + (u64)d.c * DP_CHUNK_BYTES + 8u * lane);
-        sts64(d.ca + 8u * lane, v);
-        if (lane == 0u) sts(r.ctag + 4u * slot, d.c);
-        __syncwarp();
-    }
-    // (everything the pass needs from the cached copy is taken now: the other side's chunk may claim the same cache slot)
-    const u64 e = lds64(d.ca + 8u * lane);
-    d.nc = lds(d.ca + 8u * DP_CHUNK_ENTRIES);
-    d.pid = (u32)e;
-    const u32 pvol = (u32)(e >> 32);
-    d.live = lane >= d.idx && lane < d.end && d.pid != BB_NIL;
-    const u32 v = d.live ? pvol : 0u;
-    u32 incl = v;
-#pragma unroll
-    for (int k = 1; k < 32; k <<= 1) {
-        const u32 y = __shfl_up_sync(BB_FULL, incl, k);
-        if (lane >= (u32)k) incl += y;
-    }
-    d.pin = incl;
-    d.pex = incl - v;
-    d.total = __shfl_sync(BB_FULL, incl, 31);
-    d.S = 0u;
-}
-// one aggressor (volume `rem`, all of which the level can give) against the head of side d
-__device__ __forceinline__ bool bk_side_take(const BkReg& r, BkSt& s, u32 lane, SweepSide& d, u32 opp, u32 rem, u32 aid, u32 t_lo, u32 t_hi,
-                                             u32 mark, u32& lane_err) {
-    const u32 price = r.win_lo + d.L;
-    d.taken += rem;
-    for (u32 guard = 0; guard < (1u << 22); ++guard) {
-        const u32 hi = d.S + rem;
-        const bool ov = d.live && d.pex < hi && d.pin > d.S;
-        const u32 m = __ballot_sync(BB_FULL, ov);
-        const u32 nf = __popc(m);
-        if (!bk_ret_space(r, s, lane, nf + 1u)) return false;
-        if (ov) {
-            const u32 top = min(d.pin, hi);
-            const u32 tv = top - max(d.pex, d.S), pv = d.pin - top;
-            const u32 k = __popc(m & ((1u << lane) - 1u));
-            bk_ret_write(r, s.ret_tail + k, make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), d.pid, tv, pv),
-                         make_uint4(t_lo, t_hi, price, aid));
-            bk_trade(r, s, s.n_tr + k, t_lo, t_hi, price, tv, aid, d.pid, opp, lane_err);
-            sts(r.dirty + 4u * (d.pid & (DW_DIRTY - 1u)), mark);
-        }
-        s.ret_tail += nf;
-        s.n_tr += nf;
-        if (hi <= d.total) {
-            d.S = hi;
-            return true;
-        }
-        // the chunk is used up and the aggressor wants more: follow the link (the level holds more than this pass takes)
-        rem = hi - d.total;
-        const u32 nc = d.nc;
-        d.nfull += __popc(__ballot_sync(BB_FULL, d.live));
-        if (d.c == d.tc || nc >= r.n_chunks) {  // broken chain: only after an earlier capacity error
-            s.err |= ERR_CAP_PAGES;
-            d.ok = false;
-            return true;
-        }
-        bk_free_chunk(r, s, lane, d.c);
-        __syncwarp();
-        if (lane == 0u) sts(r.lht + 8u * d.L, nc << 5);
-        __syncwarp();
-        bk_side_load(r, lane, d);
-    }
-    return true;
-}
-// the pass is over: head, volumes and counts of the level go back to shared memory
-__device__ __forceinline__ void bk_side_done(const BkReg& r, u32 lane, SweepSide& d) {
-    const u32 fm = __ballot_sync(BB_FULL, d.live && d.pin <= d.S);
-    const u32 rm = __ballot_sync(BB_FULL, d.live && d.pin > d.S);
-    if (d.live && d.pex < d.S && d.S < d.pin) {  // the partially filled order stays at the head of its level
-        bk_chunk_st32(r, d.c, 8u * lane + 4u, d.pin - d.S);
-    }
-    const u32 lc = lds(r.lcnt + 4u * d.L), lv = lds(r.lvol + 4u * d.L);
-    __syncwarp();
+// Micro-ops (32 bytes, in shared memory): w0 = level | kind << 13 | exhaust << 16, w1 = order id (T: the aggressor),
+// w2 / w3 = arguments, w4 / w5 = event time, w6 = the event's order-record entry when this is its last micro-op
+// (retire kind | side << 8 | status << 12; 0 = none), w7 = the event's filter mark (events complete once it is).
+//   MK_T  w2 = volume to take, exhaust: and every order left on the level; w3 = the entry's third word
+//   MK_A  w2 = volume
+//   MK_R  w2 = entry position
+//   MK_D  w2 = entry position, w3 = new volume
+//   MK_N  nothing to do on the book (carries an entry only)
+// The entry's words: RK_NEW {kind, id, volume left, position}, RK_REPLACE {kind, id, volume left, position} + price,
+// RK_CANCEL {kind, id}, RK_REDUCE {kind, id, new volume}; `position` comes from the A micro-op, `volume left` is w2 of an
+// A micro-op and w3 otherwise, a replace's price is the level's (A) or w3's high... see bk_own_entry.
+#define MK_T 0u
+#define MK_A 1u
+#define MK_R 2u
+#define MK_D 3u
+#define MK_N 4u
+
+// decoded event flags (SC_EVD word 0)
+#define EF_REM 1u
+#define EF_RED 2u
+#define EF_PLACE 4u
+#define EF_PSIDE 8u
+#define EF_OSIDE 16u
+#define EF_REPLACE 32u
+#define EF_INSTR 64u
+#define EF_NEW 128u
+#define EF_MARKET 256u
+
+__device__ __forceinline__ void bk_emit(const BkReg& r, BkSt& s, u32 lane, u32 w0, u32 w1, u32 w2, u32 w3, u32 t_lo, u32 t_hi, u32 own, u32 mark) {
     if (lane == 0u) {
-        if (d.ok) {
-            sts(r.lht + 8u * d.L, (d.c << 5) | (rm ? (u32)__ffs(rm) - 1u : d.end));
-            sts(r.lcnt + 4u * d.L, lc - (d.nfull + __popc(fm)));
-        } else {
-            sts(r.lcnt + 4u * d.L, 0u);
-        }
-        sts(r.lvol + 4u * d.L, lv - d.taken);
+        const u32 ma = r.scr + SC_MOP + 32u * s.n_mop;
+        sts128(ma, make_uint4(w0, w1, w2, w3));
+        sts128(ma + 16u, make_uint4(t_lo, t_hi, own, mark));
     }
+    s.n_mop += 1;
+}
+
+// ---- replay: every queued micro-op, 32 per round, one lane each; then `ev_done` events are complete -------------------------
+__device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 ev_done, u32& lane_err) {
+    const u32 lt = (1u << lane) - 1u;
     __syncwarp();
+#ifdef DP_PROF
+    s.pf_flush += 1;
+    s.pf_mops += s.n_mop;
+#endif
+    for (u32 base = 0; base < s.n_mop; base += 32u) {
+#ifdef DP_PROF
+        s.pf_rounds += 1;
+#endif
+        const u32 m = base + lane;
+        const bool valid = m < s.n_mop;
+        const u32 ma = r.scr + SC_MOP + 32u * m;
+        uint4 w = make_uint4(0, 0, 0, 0), v = w;
+        if (valid) {
+            w = lds128(ma);
+            v = lds128(ma + 16u);
+        }
+        const u32 q = w.x & 0x1FFFu, kind = (w.x >> 13) & 7u;
+        // a fresh chunk for every append (it needs at most one); what is not used goes back below
+        const bool is_a = valid && kind == MK_A;
+        const u32 am = __ballot_sync(BB_FULL, is_a);
+        if (am) {
+            const u32 na = __popc(am), rank = __popc(am & lt);
+            const u32 from_stack = min(na, s.n_free);
+            u32 sp = 0u;
+            if (is_a) {
+                if (rank < from_stack) sp = lds(r.fs + 4u * (s.n_free - 1u - rank));
+                else if (s.bump + (rank - from_stack) < r.n_chunks) sp = s.bump + (rank - from_stack);
+                else lane_err |= ERR_CAP_PAGES;  // (chunk 0 is a safe sink)
+                sts(r.scr + SC_SPARE + 4u * lane, sp);
+            }
+            s.n_free -= from_stack;
+            s.bump = min(s.bump + (na - from_stack), r.n_chunks);
+        }
+        if (valid) {
+            sts(r.scr + SC_NFILL + 4u * lane, 0u);
+            sts64(r.scr + SC_FREED + 8u * lane, 0ull);
+        }
+        if (lane == 0u) sts(r.scr + SC_FCOUNT, 0u);
+        __syncwarp();
+        // ---- one lane per level: the level's micro-ops in order --------------------------------------------------------
+        const u32 mg = __match_any_sync(BB_FULL, (valid && kind != MK_N) ? q : (0xFFFFFF00u | lane));
+        if (valid && kind != MK_N && (mg & lt) == 0u) {
+            u32 cnt = lds(r.lcnt + 4u * q);
+            const u64 ht = lds64(r.lht + 8u * q);
+            u32 head = (u32)ht, tail = (u32)(ht >> 32);
+            for (u32 mm = mg; mm; mm &= mm - 1u) {
+                const u32 j = (u32)__ffs(mm) - 1u;
+                const uint4 x = lds128(r.scr + SC_MOP + 32u * (base + j));
+                const u32 kj = (x.x >> 13) & 7u;
+                if (kj == MK_A) {  // insert_order's queue half (side.rs:54-66)
+                    if (cnt == 0u || (tail & 31u) == DP_CHUNK_ENTRIES) {
+                        const u32 sa = r.scr + SC_SPARE + 4u * j;
+                        const u32 c = lds(sa);
+                        sts(sa, c | 0x80000000u);
+                        stg32(bk_chunk(r, c) + 8u * DP_CHUNK_ENTRIES, BB_NIL);
+                        if (cnt == 0u) head = c << 5;
+                        else stg32(bk_chunk(r, tail >> 5) + 8u * DP_CHUNK_ENTRIES, c);
+                        tail = c << 5;
+                    }
+                    stg64(bk_chunk(r, tail >> 5) + 8u * (tail & 31u), ((u64)x.z << 32) | x.y);
+                    sts(r.scr + SC_POS + 4u * j, tail);
+                    tail += 1;
+                    cnt += 1;
+                } else if (kj == MK_R) {  // remove_order's queue half (side.rs:75-84): a tombstone
+                    stg32(bk_chunk(r, x.z >> 5) + 8u * (x.z & 31u), BB_NIL);
+                    if (cnt <= 1u) {
+                        cnt = 0u;
+                        if ((head >> 5) == (tail >> 5)) sts(r.scr + SC_FREED + 8u * j, head >> 5);  // a longer all-dead chain is left to the pool
+                    } else {
+                        cnt -= 1;
+                    }
+                } else if (kj == MK_D) {
+                    stg32(bk_chunk(r, x.z >> 5) + 8u * (x.z & 31u) + 4u, x.w);
+                } else {  // MK_T: match_orders over this level (orderbook.rs:843-870), entry by entry from the head
+                    u32 take = x.z, nf = 0u, nfree = 0u;
+                    const bool exhaust = (x.x >> 16) & 1u;
+                    while ((take > 0u || exhaust) && cnt > 0u) {
+                        const u32 c = head >> 5, idx = head & 31u, tc = tail >> 5;
+                        const u32 end = (c == tc) ? (tail & 31u) : DP_CHUNK_ENTRIES;
+                        if (idx >= end) {  // this chunk is used up: follow the link
+                            const u32 nc = ldg32(bk_chunk(r, c) + 8u * DP_CHUNK_ENTRIES);
+                            if (c == tc || nc >= r.n_chunks) {  // live orders counted but none found: only after an earlier capacity error
+                                lane_err |= ERR_CAP_PAGES;
+                                cnt = 0u;
+                                break;
+                            }
+                            if (nfree < 2u) sts(r.scr + SC_FREED + 8u * j + 4u * nfree, c);
+                            nfree += 1;
+                            head = nc << 5;
+                            continue;
+                        }
+                        const u64 e = ldg64(bk_chunk(r, c) + 8u * idx);
+                        const u32 pid = (u32)e, pvol = (u32)(e >> 32);
+                        if (pid == BB_NIL) {  // tombstone
+                            head += 1;
+                            continue;
+                        }
+                        const u32 tv = min(take, pvol), pv = pvol - tv;
+                        take -= tv;
+                        const u32 f = atoms_add(r.scr + SC_FCOUNT, 1u);
+                        if (f < DW_FILLS) sts128(r.scr + SC_FILL + 16u * f, make_uint4(j | (nf << 8), pid, tv, pv));
+                        else lane_err |= 0x80000000u;  // (cannot happen: a flush takes at most DW_FILLS volume)
+                        nf += 1;
+                        if (pv != 0u) {  // partially filled: stays at the head; the aggressor is done
+                            stg32(bk_chunk(r, c) + 8u * idx + 4u, pv);
+                            break;
+                        }
+                        head += 1;
+                        cnt -= 1;
+                    }
+                    if (cnt == 0u && (head >> 5) == (tail >> 5) && nfree < 2u) sts(r.scr + SC_FREED + 8u * j + 4u * nfree, head >> 5);  // the level is gone
+                    sts(r.scr + SC_NFILL + 4u * j, nf);
+                }
+            }
+            sts(r.lcnt + 4u * q, cnt);
+            sts64(r.lht + 8u * q, ((u64)tail << 32) | head);
+        }
+        __syncwarp();
+        // ---- places in the retire ring and in the trade log: event order, i.e. micro-op order ---------------------------------
+        const u32 nf = valid ? lds(r.scr + SC_NFILL + 4u * lane) : 0u;
+        const u32 own = valid ? v.z : 0u;
+        u32 ci = nf + (own ? 1u : 0u), fi = nf;  // inclusive prefix sums: ring entries, fills
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const u32 a = __shfl_up_sync(BB_FULL, ci, k), b = __shfl_up_sync(BB_FULL, fi, k);
+            if (lane >= (u32)k) { ci += a; fi += b; }
+        }
+        const u32 n_ring = __shfl_sync(BB_FULL, ci, 31), n_fill = __shfl_sync(BB_FULL, fi, 31);
+        if (!bk_ret_space(r, s, lane, n_ring)) return false;
+        const u32 ring0 = s.ret_tail + ci - (nf + (own ? 1u : 0u)), tr0 = s.n_tr + fi - nf;  // this micro-op's first ring slot / trade
+        // the fills, 32 at a time: trade record + the passive order's record update
+        for (u32 f0 = 0; f0 < n_fill; f0 += 32u) {
+            const u32 f = f0 + lane;
+            uint4 g = make_uint4(0, 0, 0, 0);
+            if (f < n_fill) g = lds128(r.scr + SC_FILL + 16u * f);
+            const u32 j = g.x & 31u, k = g.x >> 8;
+            const u32 jr = __shfl_sync(BB_FULL, ring0, j), jt = __shfl_sync(BB_FULL, tr0, j);
+            const u32 jq = __shfl_sync(BB_FULL, q, j), jid = __shfl_sync(BB_FULL, w.y, j);
+            const u32 jlo = __shfl_sync(BB_FULL, v.x, j), jhi = __shfl_sync(BB_FULL, v.y, j), jmark = __shfl_sync(BB_FULL, v.w, j);
+            const u32 jopp = __shfl_sync(BB_FULL, (w.x >> 17) & 1u, j);
+            if (f < n_fill) {
+                const u32 price = r.win_lo + jq;
+                // trade: side / price are the passive order's (orderbook.rs:853-862)
+                bk_ret_write(r, jr + k, make_uint4(RK_FILL | (jopp << 8) | (g.w == 0u ? 0x10000u : 0u), g.y, g.z, g.w), make_uint4(jlo, jhi, price, jid));
+                bk_trade(r, s, jt + k, jlo, jhi, price, g.z, jid, g.y, jopp, lane_err);
+                sts(r.dirty + 4u * (g.y & (DW_DIRTY - 1u)), jmark);
+            }
+        }
+        // the events' own record entries
+        if (own) {
+            const u32 ek = own & 0xFFu;
+            uint4 ea = make_uint4(own, w.y, 0u, 0u), eb = make_uint4(v.x, v.y, 0u, 0u);
+            if (kind == MK_A) {  // the order rests: volume left, queue position; a replace also carries its new price
+                ea.z = w.z;
+                ea.w = lds(r.scr + SC_POS + 4u * lane);
+                eb.z = r.win_lo + q;
+            } else if (ek == RK_REDUCE) {
+                ea.z = w.w;
+            } else if (ek == RK_NEW) {  // ended without resting: volume left (a market order's unfilled rest)
+                ea.z = w.w;
+            } else if (ek == RK_REPLACE) {  // filled: its new price
+                eb.z = w.w;
+            }
+            bk_ret_write(r, ring0 + nf, ea, eb);
+            sts(r.dirty + 4u * (w.y & (DW_DIRTY - 1u)), v.w);
+        }
+        s.ret_tail += n_ring;
+        s.n_tr += n_fill;
+        // ---- chunks: unused spares and emptied chunks go back on the free stack, in lane order ---------------------------------
+        {
+            u32 c0 = 0u, c1 = 0u, c2 = 0u;
+            if (valid) {
+                if (is_a) {
+                    const u32 sp = lds(r.scr + SC_SPARE + 4u * lane);
+                    if (!(sp & 0x80000000u)) c0 = sp;
+                }
+                const u64 fr = lds64(r.scr + SC_FREED + 8u * lane);
+                c1 = (u32)fr;
+                c2 = (u32)(fr >> 32);
+            }
+            u32 n = (c0 ? 1u : 0u) + (c1 ? 1u : 0u) + (c2 ? 1u : 0u), incl = n;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const u32 a = __shfl_up_sync(BB_FULL, incl, k);
+                if (lane >= (u32)k) incl += a;
+            }
+            const u32 tot = __shfl_sync(BB_FULL, incl, 31);
+            if (tot) {
+                u32 at = s.n_free + incl - n;
+                if (c0 && at < DP_FS_CAP) sts(r.fs + 4u * at++, c0);
+                if (c1 && at < DP_FS_CAP) sts(r.fs + 4u * at++, c1);
+                if (c2 && at < DP_FS_CAP) sts(r.fs + 4u * at++, c2);
+                s.n_free = min(s.n_free + tot, DP_FS_CAP);
+            }
+        }
+        __syncwarp();
+    }
+    s.n_mop = 0u;
+    s.flush_take = 0u;
+    bk_publish(r, s, lane, ev_done);
+    return true;
 }
 
 #define CXR_EMIT 0
 #define CXR_STATE 1
-#define CXR_TOUCH 2
+#define CXR_BIG 2
 #define CXR_DOUBT 3
 #define CXR_SAMEID 4
-#define CXR_EMPTY 5
-#define CXR_TAKE 6
+#define CXR_TIME 5
+#define CXR_ZERO 6
 #define CXR_OTHER 7
 
 // The events of one batch still to do (`pending`: a contiguous run of lanes; lane i holds event i: x, y pre-decoded
@@ -658,12 +790,10 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
     while (pending) {
         const u32 first = (u32)__ffs(pending) - 1u;
         const bool valid = (pending >> lane) & 1u;
-        // ---- classify under the hypothesis "the touch does not move" ---------------------------------------------------
+        // ---- decode: everything that does not depend on the book -------------------------------------------------------
         bool cx = false;
         u32 why = CXR_OTHER;
-        bool do_rem = false, do_red = false, do_place = false, is_x = false, is_add = false;
-        u32 q1 = 0u, v1 = 0u, pos1 = 0u, red_vol = 0u, oside = 0u;
-        u32 pside = 0u, pprice = 0u, pvol = 0u, pkind = 0u, q2 = 0u;
+        u32 ef = 0u, q1 = 0u, v1 = 0u, pos1 = 0u, red_vol = 0u, pprice = 0u, pvol = 0u;
         const u32 id = x.w;
         const bool is_new = valid && op == BB_OP_NEW, is_cm = valid && (op == BB_OP_CANCEL || op == BB_OP_MODIFY);
         const u32 newm = __ballot_sync(BB_FULL, is_new);
@@ -672,12 +802,11 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
             if (x.z & BB_F_EMIT) { cx = true; why = CXR_EMIT; }
             if (is_new) {
                 if (x.z & DPF_CAP_ORDERS) cx = true;
-                do_place = true;
-                pkind = RK_NEW;
-                pside = (x.z >> 8) & 1u;
+                ef = EF_PLACE | EF_INSTR | EF_NEW | (((x.z >> 8) & 1u) ? EF_PSIDE : 0u) | ((x.z & DPF_MARKET) ? EF_MARKET : 0u);
                 pprice = y.x;
                 pvol = y.y;
             } else if (is_cm) {
+                ef = EF_INSTR;
                 if (id >= s.n_orders + __popc(newm & lt) || id >= r.max_orders) {
                     cx = true;  // unknown id
                 } else {
@@ -687,258 +816,201 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                     if ((c.z & META_STATUS_MASK) != ST_ACTIVE || (op == BB_OP_MODIFY && !has_p && !has_v) || q1 >= r.W) {
                         // nothing to do (cancel / modify of an order that is not on the book are no-ops)
                     } else {
-                        oside = (c.z & META_BID) ? 1u : 0u;
+                        const u32 oside = (c.z & META_BID) ? 1u : 0u;
+                        ef |= oside ? EF_OSIDE : 0u;
                         v1 = a.y;
                         pos1 = a.z;
                         if (op == BB_OP_MODIFY && !has_p && has_v && y.y < a.y) {
-                            do_red = true;
+                            ef |= EF_RED;
                             red_vol = y.y;
-                            if (red_vol == 0u) cx = true;
                         } else {
-                            do_rem = true;
-                            if (op == BB_OP_MODIFY) {
-                                do_place = true;
-                                pkind = RK_REPLACE;
-                                pside = oside;
+                            ef |= EF_REM;
+                            if (op == BB_OP_MODIFY) {  // replace_order: never a market order (N4)
+                                ef |= EF_PLACE | EF_REPLACE | (oside ? EF_PSIDE : 0u);
                                 pprice = has_p ? y.x : a.x;
                                 pvol = has_v ? y.y : a.y;
                             }
                         }
-                        if (bk_has_best(s, oside) && q1 == bk_best_q(s, oside)) { cx = true; why = CXR_TOUCH; }  // the touch level is being traded
                     }
                 }
             } else {
                 cx = true;  // SET_TRADING, RESTORE, no-ops: the serial path knows
             }
-            if (do_place && !cx) {
-                const u32 opp = pside ^ 1u;
-                if (pvol == 0u) {
-                    cx = true;
-                } else {
-                    bool crosses = false;
-                    if (bk_has_best(s, opp)) {
-                        const u32 bprice = r.win_lo + bk_best_q(s, opp);
-                        crosses = pside ? (pprice >= bprice) : (pprice <= bprice);
-                    }
-                    const bool market = pkind == RK_NEW && (x.z & DPF_MARKET) != 0u;
-                    if (crosses) {
-                        is_x = true;
-                    } else if (market) {
-                        cx = true;  // a market order that finds no other side
-                    } else {
-                        q2 = pprice - r.win_lo;
-                        if (q2 >= r.W) {
-                            cx = true;
-                        } else if (!bk_has_best(s, pside) || (pside ? q2 > s.bq_bid : q2 < s.bq_ask)) {
-                            cx = true;  // a new best price
-                            why = CXR_TOUCH;
-                        } else if ((lds(bk_bm(r, opp, q2 >> 5)) >> (q2 & 31u)) & 1u) {
-                            cx = true;  // the other side rests there (locked level)
-                        } else {
-                            is_add = true;
-                        }
-                    }
-                }
+            if ((ef & EF_RED) && red_vol == 0u) { cx = true; why = CXR_ZERO; }
+            if (ef & EF_PLACE) {
+                if (pvol == 0u) { cx = true; why = CXR_ZERO; }
+                if (pvol > DW_FILLS) { cx = true; why = CXR_BIG; }
+                // a limit price outside the window can only be handled where it never rests; leave it to the serial path
+                if (!(ef & EF_MARKET) && pprice - r.win_lo >= r.W) cx = true;
             }
         }
         {   // time moves strictly forward through the batch and past every resting order's key
             const u32 pl = __shfl_up_sync(BB_FULL, t_lo, 1), ph = __shfl_up_sync(BB_FULL, t_hi, 1);
             const u64 tp = lane == first ? s.max_key_time : (((u64)ph << 32) | pl);
-            if (valid && t <= tp) cx = true;
+            if (valid && t <= tp) { cx = true; why = CXR_TIME; }
         }
-        // two events of the batch naming one order: the later one cannot trust its prefetched record
-        {
+        {   // two events of the batch naming one order: the later one cannot trust its prefetched record
             const u32 key = (is_new || is_cm) ? id : (0xFFFFFF00u | lane);
             const u32 mg = __match_any_sync(BB_FULL, key);
             if ((is_new || is_cm) && (mg & lt)) { cx = true; why = CXR_SAMEID; }
         }
-        // a level must not run empty inside a pass (its chunk chain and bitmap bit would change hands)
-        {
-            const u32 key = (valid && do_rem) ? q1 : (0xFFFFFF00u | lane);
-            const u32 mg = __match_any_sync(BB_FULL, key);
-            if (valid && do_rem && lds(r.lcnt + 4u * q1) <= (u32)__popc(mg & lt) + 1u) { cx = true; why = CXR_EMPTY; }
-        }
-        // the touch level must hold more than the pass takes from it
-        {
-            const u32 ta = (valid && is_x && pside == 1u) ? pvol : 0u, tb = (valid && is_x && pside == 0u) ? pvol : 0u;
-            u32 ca_ = ta, cb_ = tb;
-#pragma unroll
-            for (int k = 1; k < 32; k <<= 1) {
-                const u32 ya = __shfl_up_sync(BB_FULL, ca_, k), yb = __shfl_up_sync(BB_FULL, cb_, k);
-                if (lane >= (u32)k) { ca_ += ya; cb_ += yb; }
-            }
-            if (valid && is_x) {
-                const u32 avail = lds(r.lvol + 4u * bk_best_q(s, pside ^ 1u));
-                if ((pside ? ca_ : cb_) >= avail) { cx = true; why = CXR_TAKE; }
-            }
-        }
         const u32 cm = __ballot_sync(BB_FULL, cx && valid);
-        const u32 clean = cm ? (pending & (((u32)1u << ((u32)__ffs(cm) - 1u)) - 1u)) : pending;
-#ifdef DP_PROF
-        s.pf_pass += 1;
-        s.pf_par += __popc(clean);
-#endif
+        const u32 kcut = cm ? (u32)__ffs(cm) - 1u : 32u;
+        const u32 clean = cm ? (pending & ((1u << kcut) - 1u)) : pending;
         if (clean) {
-            const bool act = (clean >> lane) & 1u;
-            const u32 last = 31u - (u32)__clz(clean);
-            const u32 mark = ev0 + last + 1u;
-            // ---- X: the trades, aggressors in event order, each against the head of its touch level ----------------------
-            u32 xm = __ballot_sync(BB_FULL, act && is_x);
-            if (xm) {
-                SweepSide sa, sb;  // ask side (taken by bids), bid side (taken by asks)
-                sa.L = s.bq_ask; sb.L = s.bq_bid;
-                sa.nfull = sb.nfull = sa.taken = sb.taken = 0u;
-                sa.ok = sb.ok = true;
-                const u32 xa = __ballot_sync(BB_FULL, act && is_x && pside == 1u);
-                if (xa) bk_side_load(r, lane, sa);
-                if (xm & ~xa) bk_side_load(r, lane, sb);
-                while (xm) {
-                    const u32 k = (u32)__ffs(xm) - 1u;
-                    xm &= xm - 1u;
-                    const u32 rem = __shfl_sync(BB_FULL, pvol, k), aid = __shfl_sync(BB_FULL, id, k);
-                    const u32 kl = __shfl_sync(BB_FULL, t_lo, k), kh = __shfl_sync(BB_FULL, t_hi, k);
-                    bool okk;
-                    if ((xa >> k) & 1u) okk = sa.ok ? bk_side_take(r, s, lane, sa, 0u, rem, aid, kl, kh, mark, lane_err) : true;
-                    else okk = sb.ok ? bk_side_take(r, s, lane, sb, 1u, rem, aid, kl, kh, mark, lane_err) : true;
-                    if (!okk || !bk_ret_space(r, s, lane, 1u)) return false;
-                    // the aggressor's own record: Filled
-                    if (lane == k)
-                        bk_ret_write(r, s.ret_tail, make_uint4(pkind | (pside << 8) | (ST_FILLED << 12), id, 0u, 0u), make_uint4(t_lo, t_hi, pprice, 0u));
-                    s.ret_tail += 1;
-                }
-                if (xa) {
-                    bk_side_done(r, lane, sa);
-                    s.trade_vol += sa.taken;
-                    s.vol_ask -= sa.taken;
-                }
-                if (sb.taken || !sb.ok) {
-                    bk_side_done(r, lane, sb);
-                    s.trade_vol += sb.taken;
-                    s.vol_bid -= sb.taken;
-                }
+            // the decoded events go to shared memory: the chain reads them one after the other (broadcast loads)
+            if ((clean >> lane) & 1u) {
+                const u32 ea = r.scr + SC_EVD + 48u * lane;
+                sts128(ea, make_uint4(ef, id, t_lo, t_hi));
+                sts128(ea + 16u, make_uint4(q1, v1, pos1, red_vol));
+                sts128(ea + 32u, make_uint4(pprice, pvol, 0u, 0u));
             }
-            // ---- ADD: queue positions, one group per level ------------------------------------------------------------------
-            const bool addl = act && is_add, reml = act && do_rem, redl = act && do_red;
-            u32 pos2 = 0u;
-            if (__ballot_sync(BB_FULL, addl)) {
-                const u32 mg = __match_any_sync(BB_FULL, addl ? q2 : (0xFFFFFF00u | lane));
-                const u32 leader = (u32)__ffs(mg) - 1u, rank = __popc(mg & lt), gsize = __popc(mg);
-                const bool lead = addl && lane == leader;
-                u32 cnt0 = 1u, tail = 0u;
-                if (addl) {
-                    cnt0 = lds(r.lcnt + 4u * q2);
-                    tail = lds(r.lht + 8u * q2 + 4u);
-                }
-                const bool empty = cnt0 == 0u;
-                const u32 tidx = empty ? 0u : (tail & 31u);
-                const u32 g = tidx + rank, kk = g / DP_CHUNK_ENTRIES, idx = g - DP_CHUNK_ENTRIES * kk;
-                const u32 glast = tidx + gsize - 1u, kmax = glast / DP_CHUNK_ENTRIES;
-                u32 c0 = empty ? 0u : (tail >> 5), c1 = 0u, c2 = 0u;
-                // the leaders' new chunks, handed out one at a time (the allocator is warp-uniform state)
-                const u32 need = lead ? kmax + (empty ? 1u : 0u) : 0u;
-                u32 nm = __ballot_sync(BB_FULL, need > 0u);
-                while (nm) {
-                    const u32 L = (u32)__ffs(nm) - 1u;
-                    nm &= nm - 1u;
-                    const u32 n = __shfl_sync(BB_FULL, need, L);
-                    const u32 o0 = __shfl_sync(BB_FULL, empty ? 0u : 1u, L);
-                    for (u32 j = 0; j < n; ++j) {
-                        const u32 cc = bk_alloc(r, s, lane);
-                        if (lane == L) {
-                            const u32 ord = o0 + j;
-                            if (ord == 0u) c0 = cc; else if (ord == 1u) c1 = cc; else c2 = cc;
+            __syncwarp();
+            const u32 e_end = 32u - (u32)__clz(clean);
+            // ---- chain: the ladder, in event order.  It stops where the micro-op list (or the volume one flush may take) is
+            // full — possibly in the middle of an aggressive order's sweep — and goes on after the flush below.
+            // A cancel / modify trusts the order record the fetch warp prefetched; the decode step above has checked it against
+            // every fill already made, but not against the takes of THIS chain run: an event that names an order on a level
+            // taken from since then stops the run (`late`) and is decoded again once those fills are known.
+            const u32 chain_start = ev0 + first;
+            u32 e = first, rem = 0u, last_t = 0xFFFFFFFFu;
+            bool in_place = false, late = false;
+            for (;;) {
+                while (e < e_end) {
+                    const u32 ea = r.scr + SC_EVD + 48u * e;
+                    const uint4 d0 = lds128(ea);
+                    const u32 f = d0.x, eid = d0.y, mark = ev0 + e + 1u;
+                    if (!in_place) {
+                        if ((f & (EF_REM | EF_RED)) && lds(r.scr + SC_SWEPT + 4u * (lds(ea + 16u) & (DW_SWEPT - 1u))) > chain_start) {
+                            late = true;
+                            break;
+                        }
+                        if (s.n_mop + 3u > DW_MOPS) break;
+                        if (f & EF_PLACE) {
+                            rem = lds(ea + 36u);
+                            if (s.flush_take + rem > DW_FILLS) break;
+                        }
+                        s.t = ((u64)d0.w << 32) | d0.z;
+                        if (f & EF_INSTR) s.d_instr += 1;
+                        if (f & EF_NEW) s.n_orders = eid + 1u;
+                        if (f & (EF_REM | EF_RED)) {
+                            const uint4 d1 = lds128(ea + 16u);
+                            const u32 oside = (f & EF_OSIDE) ? 1u : 0u;
+                            const u32 la = r.lvol + 4u * d1.x;
+                            const u32 lv = lds(la);
+                            if (f & EF_RED) {  // reduce in place: priority kept (orderbook.rs:755-757)
+                                if (lane == 0u) sts(la, lv - (d1.y - d1.w));
+                                bk_add_side(s, oside, d1.w - d1.y);
+                                bk_emit(r, s, lane, d1.x | (MK_D << 13), eid, d1.z, d1.w, d0.z, d0.w, RK_REDUCE, mark);
+                                s.d_applied += 1;
+                            } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
+                                const u32 nv = lv - d1.y;
+                                if (lane == 0u) sts(la, nv);
+                                bk_add_side(s, oside, 0u - d1.y);
+                                bk_emit(r, s, lane, d1.x | (MK_R << 13), eid, d1.z, 0u, d0.z, d0.w, (f & EF_PLACE) ? 0u : (RK_CANCEL | (oside << 8)), mark);
+                                __syncwarp();
+                                if (nv == 0u) bk_level_gone(r, s, lane, oside, d1.x);
+                                if (!(f & EF_PLACE)) s.d_applied += 1;
+                            }
+                            __syncwarp();
+                        }
+                        if (f & EF_PLACE) {
+                            in_place = true;
+                            last_t = 0xFFFFFFFFu;
                         }
                     }
-                }
-                if (lead) {
-                    if (kmax >= 1u) bk_chunk_st32(r, c0, 8u * DP_CHUNK_ENTRIES, c1);
-                    if (kmax >= 2u) bk_chunk_st32(r, c1, 8u * DP_CHUNK_ENTRIES, c2);
-                }
-                const u32 src = addl ? leader : lane;
-                const u32 l0 = __shfl_sync(BB_FULL, c0, src), l1 = __shfl_sync(BB_FULL, c1, src), l2 = __shfl_sync(BB_FULL, c2, src);
-                if (addl) {
-                    const u32 myc = kk == 0u ? l0 : kk == 1u ? l1 : l2;
-                    pos2 = (myc << 5) | idx;
-                    const u64 ent = ((u64)pvol << 32) | id;
-                    stg64(r.chunks + (u64)myc * DP_CHUNK_BYTES + 8u * idx, ent);
-                    const u32 slot = myc & (DW_NC - 1u);
-                    if (lds(r.ctag + 4u * slot) == myc) sts64(r.cdat + DP_CHUNK_BYTES * slot + 8u * idx, ent);
-                }
-                if (lead) {
-                    const u32 il = glast - DP_CHUNK_ENTRIES * kmax;
-                    const u32 cl = kmax == 0u ? c0 : kmax == 1u ? c1 : c2;
-                    const u32 ntail = ((cl << 5) | il) + 1u;
-                    if (empty) {
-                        sts64(r.lht + 8u * q2, ((u64)ntail << 32) | (c0 << 5));
-                        sts(r.lvol + 4u * q2, 0u);
-                        const u32 w = q2 >> 5;
-                        if (atoms_or(bk_bm(r, pside, w), 1u << (q2 & 31u)) == 0u) atoms_or(bk_sm(r, pside, w >> 5), 1u << (w & 31u));
-                    } else {
-                        sts(r.lht + 8u * q2 + 4u, ntail);
+                    if (in_place) {
+                        const u32 side = (f & EF_PSIDE) ? 1u : 0u, opp = side ^ 1u, price = lds(ea + 32u);
+                        const u32 ekind = (f & EF_REPLACE) ? RK_REPLACE : RK_NEW;
+                        // match_bid / match_ask (orderbook.rs:429-487): how much each crossed level gives
+                        bool full = false;
+                        while (rem > 0u && bk_has_best(s, opp)) {
+                            const u32 bq = bk_best_q(s, opp);
+                            const u32 bprice = r.win_lo + bq;
+                            if (side ? (price < bprice) : (price > bprice)) break;
+                            if (s.n_mop + 2u > DW_MOPS) {  // (a sweep through more levels than the list holds)
+                                full = true;
+                                break;
+                            }
+                            const u32 la = r.lvol + 4u * bq;
+                            const u32 lv = lds(la);
+                            const u32 take = min(rem, lv), nv = lv - take;
+                            rem -= take;
+                            if (lane == 0u) sts(la, nv);
+                            s.trade_vol += take;
+                            bk_add_side(s, opp, 0u - take);
+                            last_t = s.n_mop;
+                            if (lane == 0u) sts(r.scr + SC_SWEPT + 4u * (bq & (DW_SWEPT - 1u)), mark);
+                            bk_emit(r, s, lane, bq | (MK_T << 13) | (rem > 0u ? 1u << 16 : 0u) | (opp << 17), eid, take, 0u, d0.z, d0.w, 0u, mark);
+                            s.flush_take += take;
+                            __syncwarp();
+                            if (nv == 0u) bk_level_gone(r, s, lane, opp, bq);
+                        }
+                        if (full) break;
+                        // rest or finish (orderbook.rs:495-531, 699-722)
+                        if (rem == 0u || (f & EF_MARKET)) {
+                            const u32 status = rem == 0u ? ST_FILLED : ST_CANCELLED;  // (trading is enabled on this path)
+                            const u32 own = ekind | (side << 8) | (status << 12);
+                            const u32 w3 = ekind == RK_REPLACE ? price : rem;
+                            if (last_t != 0xFFFFFFFFu) {  // the entry rides on the event's last take
+                                if (lane == 0u) {
+                                    const u32 ma = r.scr + SC_MOP + 32u * last_t;
+                                    sts(ma + 12u, w3);
+                                    sts(ma + 24u, own);
+                                }
+                            } else {  // a market order that found no other side
+                                bk_emit(r, s, lane, MK_N << 13, eid, 0u, w3, d0.z, d0.w, own, mark);
+                            }
+                        } else {  // insert_order (side.rs:54-66), the ladder half
+                            const u32 q = price - r.win_lo;
+                            const u32 ba = bk_bm(r, side, q >> 5), bit = 1u << (q & 31u);
+                            const u32 la = r.lvol + 4u * q;
+                            const u32 bw = lds(ba);
+                            const u32 lv = lds(la);
+                            if (!(bw & bit)) {
+                                if (lds(bk_bm(r, opp, q >> 5)) & bit) {  // (cannot happen while trading is enabled and volumes are > 0)
+                                    s.err |= ERR_LOCKED;
+                                } else {
+                                    const u32 sa = bk_sm(r, side, q >> 10);
+                                    const u32 sv = lds(sa);
+                                    if (lane == 0u) {
+                                        sts(la, rem);
+                                        sts(ba, bw | bit);
+                                        if (bw == 0u) sts(sa, sv | (1u << ((q >> 5) & 31u)));
+                                    }
+                                    const bool better = !bk_has_best(s, side) || (side ? q > s.bq_bid : q < s.bq_ask);
+                                    if (better) {
+                                        if (side) s.bq_bid = q; else s.bq_ask = q;
+                                        s.flags |= FL_HAS_ASK << side;
+                                    }
+                                }
+                            } else {
+                                if (lane == 0u) sts(la, lv + rem);
+                            }
+                            bk_add_side(s, side, rem);
+                            s.max_key_time = s.t;
+                            bk_emit(r, s, lane, q | (MK_A << 13), eid, rem, 0u, d0.z, d0.w, ekind | (side << 8) | (ST_ACTIVE << 12), mark);
+                        }
+                        s.d_applied += 1;
+                        in_place = false;
+                        __syncwarp();
                     }
+                    ++e;
                 }
-                __syncwarp();
+                // the one place micro-ops are replayed from: `e` events of the batch are complete
+                if (!bk_flush(r, s, lane, ev0 + e, lane_err)) return false;
+                last_t = 0xFFFFFFFFu;
+                if (e >= e_end || late) break;
             }
-            // ---- level volumes and counts; tombstones; volume rewrites -------------------------------------------------------
-            if (addl) {
-                reds_add(r.lvol + 4u * q2, pvol);
-                reds_add(r.lcnt + 4u * q2, 1u);
-            }
-            if (reml) {
-                bk_chunk_st32(r, pos1 >> 5, 8u * (pos1 & 31u), BB_NIL);
-                reds_add(r.lvol + 4u * q1, 0u - v1);
-                reds_add(r.lcnt + 4u * q1, 0xFFFFFFFFu);
-            }
-            if (redl) {
-                bk_chunk_st32(r, pos1 >> 5, 8u * (pos1 & 31u) + 4u, red_vol);
-                reds_add(r.lvol + 4u * q1, red_vol - v1);
-            }
-            // ---- order-record updates (X events wrote theirs above) ----------------------------------------------------------
-            const bool ent = addl || (reml && !do_place) || redl;
-            const u32 em = __ballot_sync(BB_FULL, ent);
-            if (em) {
-                if (!bk_ret_space(r, s, lane, __popc(em))) return false;
-                if (ent) {
-                    uint4 ea, eb = make_uint4(t_lo, t_hi, 0u, 0u);
-                    if (addl) {
-                        ea = make_uint4(pkind | (pside << 8) | (ST_ACTIVE << 12), id, pvol, pos2);
-                        eb.z = pprice;
-                    } else if (reml) {
-                        ea = make_uint4(RK_CANCEL | (oside << 8), id, 0u, 0u);
-                    } else {
-                        ea = make_uint4(RK_REDUCE, id, red_vol, 0u);
-                    }
-                    bk_ret_write(r, s.ret_tail + __popc(em & lt), ea, eb);
-                }
-                s.ret_tail += __popc(em);
-            }
-            if (act && (is_new || is_cm)) sts(r.dirty + 4u * (id & (DW_DIRTY - 1u)), mark);
-            // ---- the book's scalars ------------------------------------------------------------------------------------------
-            const u32 nnew = __popc(__ballot_sync(BB_FULL, act && is_new));
-            s.n_orders += nnew;
-            s.d_instr += __popc(__ballot_sync(BB_FULL, act && (is_new || is_cm)));
-            s.d_applied += __popc(__ballot_sync(BB_FULL, act && (do_place || do_rem || do_red)));
-            int da = 0, db = 0;
-            if (addl) { if (pside) db += (int)pvol; else da += (int)pvol; }
-            if (reml) { if (oside) db -= (int)v1; else da -= (int)v1; }
-            if (redl) { if (oside) db -= (int)(v1 - red_vol); else da -= (int)(v1 - red_vol); }
-            s.vol_ask += (u32)__reduce_add_sync(BB_FULL, da);
-            s.vol_bid += (u32)__reduce_add_sync(BB_FULL, db);
-            s.t = ((u64)__shfl_sync(BB_FULL, t_hi, last) << 32) | __shfl_sync(BB_FULL, t_lo, last);
-            const u32 am = __ballot_sync(BB_FULL, addl);
-            if (am) {
-                const u32 la = 31u - (u32)__clz(am);
-                s.max_key_time = ((u64)__shfl_sync(BB_FULL, t_hi, la) << 32) | __shfl_sync(BB_FULL, t_lo, la);
-            }
-            bk_publish(r, s, lane, mark);
-            pending &= ~clean;
+            pending &= ~(clean & (e >= 32u ? BB_FULL : ((1u << e) - 1u)));
+            if (late) continue;  // (decode the rest again: the fills made meanwhile are in the filter now)
         }
         if (cm) {
-            const u32 k = (u32)__ffs(cm) - 1u;
 #ifdef DP_PROF
             s.pf_ser += 1;
-            s.pf_reason[__shfl_sync(BB_FULL, why, k) & 7u] += 1;
+            s.pf_reason[__shfl_sync(BB_FULL, why, kcut) & 7u] += 1;
 #endif
+            const u32 k = kcut;
             uint4 kx, ky, ka, kc;
             kx.x = __shfl_sync(BB_FULL, x.x, k); kx.y = __shfl_sync(BB_FULL, x.y, k); kx.z = __shfl_sync(BB_FULL, x.z, k); kx.w = __shfl_sync(BB_FULL, x.w, k);
             ky.x = __shfl_sync(BB_FULL, y.x, k); ky.y = __shfl_sync(BB_FULL, y.y, k); ky.z = __shfl_sync(BB_FULL, y.z, k); ky.w = __shfl_sync(BB_FULL, y.w, k);

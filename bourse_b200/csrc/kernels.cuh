@@ -1706,8 +1706,8 @@ __global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParam
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (u32 i = threadIdx.x; i < CT_WORDS; i += blockDim.x) sts(ctl + 4u * i, 0u);
-    for (u32 i = threadIdx.x; i < DW_NC; i += blockDim.x) sts(sb + o.ctag + 4u * i, BB_NIL);
     for (u32 i = threadIdx.x; i < DW_DIRTY; i += blockDim.x) sts(sb + o.dirty + 4u * i, 0u);
+    for (u32 i = threadIdx.x; i < DW_SWEPT; i += blockDim.x) sts(sb + o.cdat + SC_SWEPT + 4u * i, 0u);
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1735,8 +1735,7 @@ __global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParam
         r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
         r.sma = dp_keep32(sb + o.sm);
         r.smb = dp_keep32(sb + o.sm + 4u * DP_NS);
-        r.ctag = dp_keep32(sb + o.ctag);
-        r.cdat = dp_keep32(sb + o.cdat);
+        r.scr = dp_keep32(sb + o.cdat);
         r.ret = dp_keep32(sb + o.ret);
         r.dirty = dp_keep32(sb + o.dirty);
         r.ctl = dp_keep32(ctl);
@@ -1766,8 +1765,9 @@ __global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParam
         s.n_tr = n_tr0;
         s.ret_tail = s.ret_pub = 0u;
         s.ret_room = DW_RCAP;
+        s.n_mop = s.flush_take = 0u;
 #ifdef DP_PROF
-        s.pf_pass = s.pf_par = s.pf_ser = 0u;
+        s.pf_flush = s.pf_rounds = s.pf_mops = s.pf_ser = 0u;
         for (int i = 0; i < 8; ++i) s.pf_reason[i] = 0u;
 #endif
         const u32 n_orders0 = s.n_orders, trade_vol0 = s.trade_vol;
@@ -1843,8 +1843,8 @@ __global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParam
             if (aborted) st_rel(ctl + CT_ABORT, 1u);
 #ifdef DP_PROF
             if (blockIdx.x == 0)
-                printf("k_deepw book warp: passes %u, events in parallel passes %u, serial events %u (emit %u state %u touch %u doubt %u same-id %u "
-                       "level-empty %u take %u other %u)\n", s.pf_pass, s.pf_par, s.pf_ser, s.pf_reason[0], s.pf_reason[1], s.pf_reason[2],
+                printf("k_deepw book warp: flushes %u, replay rounds %u, micro-ops %u, serial events %u (emit %u state %u big %u doubt %u same-id %u "
+                       "time %u zero %u other %u)\n", s.pf_flush, s.pf_rounds, s.pf_mops, s.pf_ser, s.pf_reason[0], s.pf_reason[1], s.pf_reason[2],
                        s.pf_reason[3], s.pf_reason[4], s.pf_reason[5], s.pf_reason[6], s.pf_reason[7]);
 #endif
         }

@@ -45,7 +45,8 @@ namespace bb {
 #define SC_FCOUNT (SC_FREED + 8u * DW_MOPS)
 #define SC_SWEPT (SC_FCOUNT + 16u)           // per level (hashed): the last event that took volume from it
 #define DW_SWEPT 256u
-#define DW_SCRATCH (SC_SWEPT + 4u * DW_SWEPT)
+#define SC_COUT (SC_SWEPT + 4u * DW_SWEPT)   // the chain's output: one 16-byte record per micro-op
+#define DW_SCRATCH (SC_COUT + 16u * DW_MOPS)
 
 __device__ __forceinline__ void reds_add(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 atoms_add(u32 a, u32 v) {
@@ -160,18 +161,20 @@ __device__ __forceinline__ void bk_free_chunk(const BkReg& r, BkSt& s, u32 lane,
 }
 
 // level q of `side` just became empty (its bitmap bit is still set): clear it and, if it was the touch, find the next one
+// SOLO: called by lane 0 alone (the chain): plain program order, no warp synchronisation.
+template <bool SOLO = false>
 __device__ __forceinline__ void bk_level_gone(const BkReg& r, BkSt& s, u32 lane, u32 side, u32 q) {
     const u32 w = q >> 5;
     const u32 ba = bk_bm(r, side, w);
     const u32 m = lds(ba) & ~(1u << (q & 31u));
     const u32 sa = bk_sm(r, side, w >> 5);
     const u32 sv = lds(sa);
-    __syncwarp();
-    if (lane == 0u) {
+    if (!SOLO) __syncwarp();
+    if (SOLO || lane == 0u) {
         sts(ba, m);
         if (m == 0u) sts(sa, sv & ~(1u << (w & 31u)));
     }
-    __syncwarp();
+    if (!SOLO) __syncwarp();
     if (!(bk_has_best(s, side) && bk_best_q(s, side) == q)) return;
     // q was the best level: every other level of this side lies on the far side of it
     if (side == 0u) {
@@ -867,140 +870,186 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
             }
             __syncwarp();
             const u32 e_end = 32u - (u32)__clz(clean);
-            // ---- chain: the ladder, in event order.  It stops where the micro-op list (or the volume one flush may take) is
-            // full — possibly in the middle of an aggressive order's sweep — and goes on after the flush below.
+            // ---- chain: the ladder, in event order, on LANE 0 ALONE (plain loads and stores, no warp synchronisation inside).  It
+            // reads the decoded events and writes one 16-byte record per micro-op {level | kind << 13 | exhaust << 16 |
+            // passive side << 17 | event << 18, volume, aux, record entry}; everything that is not part of the recurrence
+            // (counters, side totals, the full micro-op with its ids and times) is worked out by all lanes afterwards.
+            // It stops where its output list (or the volume one flush may take) is full — possibly in the middle of an
+            // aggressive order's sweep — and goes on after the flush below.
             // A cancel / modify trusts the order record the fetch warp prefetched; the decode step above has checked it against
             // every fill already made, but not against the takes of THIS chain run: an event that names an order on a level
             // taken from since then stops the run (`late`) and is decoded again once those fills are known.
             const u32 chain_start = ev0 + first;
-            u32 e = first, rem = 0u, last_t = 0xFFFFFFFFu;
+            u32 e = first, rem = 0u, last_t = 0xFFFFFFFFu;  // (rem, last_t, in_place: lane 0's)
             bool in_place = false, late = false;
             for (;;) {
-                while (e < e_end) {
-                    const u32 ea = r.scr + SC_EVD + 48u * e;
-                    const uint4 d0 = lds128(ea);
-                    const u32 f = d0.x, eid = d0.y, mark = ev0 + e + 1u;
-                    if (!in_place) {
-                        if ((f & (EF_REM | EF_RED)) && lds(r.scr + SC_SWEPT + 4u * (lds(ea + 16u) & (DW_SWEPT - 1u))) > chain_start) {
-                            late = true;
-                            break;
-                        }
-                        if (s.n_mop + 3u > DW_MOPS) break;
-                        if (f & EF_PLACE) {
-                            rem = lds(ea + 36u);
-                            if (s.flush_take + rem > DW_FILLS) break;
-                        }
-                        s.t = ((u64)d0.w << 32) | d0.z;
-                        if (f & EF_INSTR) s.d_instr += 1;
-                        if (f & EF_NEW) s.n_orders = eid + 1u;
-                        if (f & (EF_REM | EF_RED)) {
-                            const uint4 d1 = lds128(ea + 16u);
-                            const u32 oside = (f & EF_OSIDE) ? 1u : 0u;
-                            const u32 la = r.lvol + 4u * d1.x;
-                            const u32 lv = lds(la);
-                            if (f & EF_RED) {  // reduce in place: priority kept (orderbook.rs:755-757)
-                                if (lane == 0u) sts(la, lv - (d1.y - d1.w));
-                                bk_add_side(s, oside, d1.w - d1.y);
-                                bk_emit(r, s, lane, d1.x | (MK_D << 13), eid, d1.z, d1.w, d0.z, d0.w, RK_REDUCE, mark);
-                                s.d_applied += 1;
-                            } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
-                                const u32 nv = lv - d1.y;
-                                if (lane == 0u) sts(la, nv);
-                                bk_add_side(s, oside, 0u - d1.y);
-                                bk_emit(r, s, lane, d1.x | (MK_R << 13), eid, d1.z, 0u, d0.z, d0.w, (f & EF_PLACE) ? 0u : (RK_CANCEL | (oside << 8)), mark);
-                                __syncwarp();
-                                if (nv == 0u) bk_level_gone(r, s, lane, oside, d1.x);
-                                if (!(f & EF_PLACE)) s.d_applied += 1;
-                            }
-                            __syncwarp();
-                        }
-                        if (f & EF_PLACE) {
-                            in_place = true;
-                            last_t = 0xFFFFFFFFu;
-                        }
-                    }
-                    if (in_place) {
-                        const u32 side = (f & EF_PSIDE) ? 1u : 0u, opp = side ^ 1u, price = lds(ea + 32u);
-                        const u32 ekind = (f & EF_REPLACE) ? RK_REPLACE : RK_NEW;
-                        // match_bid / match_ask (orderbook.rs:429-487): how much each crossed level gives
-                        bool full = false;
-                        while (rem > 0u && bk_has_best(s, opp)) {
-                            const u32 bq = bk_best_q(s, opp);
-                            const u32 bprice = r.win_lo + bq;
-                            if (side ? (price < bprice) : (price > bprice)) break;
-                            if (s.n_mop + 2u > DW_MOPS) {  // (a sweep through more levels than the list holds)
-                                full = true;
-                                break;
-                            }
-                            const u32 la = r.lvol + 4u * bq;
-                            const u32 lv = lds(la);
-                            const u32 take = min(rem, lv), nv = lv - take;
-                            rem -= take;
-                            if (lane == 0u) sts(la, nv);
-                            s.trade_vol += take;
-                            bk_add_side(s, opp, 0u - take);
-                            last_t = s.n_mop;
-                            if (lane == 0u) sts(r.scr + SC_SWEPT + 4u * (bq & (DW_SWEPT - 1u)), mark);
-                            bk_emit(r, s, lane, bq | (MK_T << 13) | (rem > 0u ? 1u << 16 : 0u) | (opp << 17), eid, take, 0u, d0.z, d0.w, 0u, mark);
-                            s.flush_take += take;
-                            __syncwarp();
-                            if (nv == 0u) bk_level_gone(r, s, lane, opp, bq);
-                        }
-                        if (full) break;
-                        // rest or finish (orderbook.rs:495-531, 699-722)
-                        if (rem == 0u || (f & EF_MARKET)) {
-                            const u32 status = rem == 0u ? ST_FILLED : ST_CANCELLED;  // (trading is enabled on this path)
-                            const u32 own = ekind | (side << 8) | (status << 12);
-                            const u32 w3 = ekind == RK_REPLACE ? price : rem;
-                            if (last_t != 0xFFFFFFFFu) {  // the entry rides on the event's last take
-                                if (lane == 0u) {
-                                    const u32 ma = r.scr + SC_MOP + 32u * last_t;
-                                    sts(ma + 12u, w3);
-                                    sts(ma + 24u, own);
+                const u32 e_from = e;
+                u32 n_out = 0u, last_a = 32u, stop = 0u;  // stop: 1 = late
+                if (lane == 0u) {
+                    const u32 co = r.scr + SC_COUT;
+                    last_t = 0xFFFFFFFFu;  // (the list is empty again; a sweep under way continues with its next take)
+                    while (e < e_end) {
+                        const u32 ea = r.scr + SC_EVD + 48u * e;
+                        const u32 f = lds(ea);
+                        const u32 ebits = e << 18;
+                        if (!in_place) {
+                            uint4 d1 = make_uint4(0, 0, 0, 0);
+                            if (f & (EF_REM | EF_RED)) {
+                                d1 = lds128(ea + 16u);
+                                if (lds(r.scr + SC_SWEPT + 4u * (d1.x & (DW_SWEPT - 1u))) > chain_start) {
+                                    stop = 1u;
+                                    break;
                                 }
-                            } else {  // a market order that found no other side
-                                bk_emit(r, s, lane, MK_N << 13, eid, 0u, w3, d0.z, d0.w, own, mark);
                             }
-                        } else {  // insert_order (side.rs:54-66), the ladder half
-                            const u32 q = price - r.win_lo;
-                            const u32 ba = bk_bm(r, side, q >> 5), bit = 1u << (q & 31u);
-                            const u32 la = r.lvol + 4u * q;
-                            const u32 bw = lds(ba);
-                            const u32 lv = lds(la);
-                            if (!(bw & bit)) {
-                                if (lds(bk_bm(r, opp, q >> 5)) & bit) {  // (cannot happen while trading is enabled and volumes are > 0)
-                                    s.err |= ERR_LOCKED;
-                                } else {
-                                    const u32 sa = bk_sm(r, side, q >> 10);
-                                    const u32 sv = lds(sa);
-                                    if (lane == 0u) {
+                            if (n_out + 3u > DW_MOPS) break;
+                            if (f & EF_PLACE) {
+                                rem = lds(ea + 36u);
+                                if (s.flush_take + rem > DW_FILLS) break;
+                            }
+                            if (f & (EF_REM | EF_RED)) {
+                                const u32 oside = (f & EF_OSIDE) ? 1u : 0u;
+                                const u32 la = r.lvol + 4u * d1.x;
+                                const u32 lv = lds(la);
+                                if (f & EF_RED) {  // reduce in place: priority kept (orderbook.rs:755-757)
+                                    sts(la, lv - (d1.y - d1.w));
+                                    sts128(co + 16u * n_out++, make_uint4(d1.x | (MK_D << 13) | (oside << 17) | ebits, d1.y - d1.w, 0u, RK_REDUCE));
+                                } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
+                                    const u32 nv = lv - d1.y;
+                                    sts(la, nv);
+                                    sts128(co + 16u * n_out++, make_uint4(d1.x | (MK_R << 13) | (oside << 17) | ebits, d1.y, 0u,
+                                                                          (f & EF_PLACE) ? 0u : (RK_CANCEL | (oside << 8))));
+                                    if (nv == 0u) bk_level_gone<true>(r, s, 0u, oside, d1.x);
+                                }
+                            }
+                            if (f & EF_PLACE) {
+                                in_place = true;
+                                last_t = 0xFFFFFFFFu;
+                            }
+                        }
+                        if (in_place) {
+                            const u32 side = (f & EF_PSIDE) ? 1u : 0u, opp = side ^ 1u, price = lds(ea + 32u);
+                            const u32 ekind = (f & EF_REPLACE) ? RK_REPLACE : RK_NEW;
+                            const u32 mark = ev0 + e + 1u;
+                            // match_bid / match_ask (orderbook.rs:429-487): how much each crossed level gives
+                            bool full = false;
+                            while (rem > 0u && bk_has_best(s, opp)) {
+                                const u32 bq = bk_best_q(s, opp);
+                                const u32 bprice = r.win_lo + bq;
+                                if (side ? (price < bprice) : (price > bprice)) break;
+                                if (n_out + 2u > DW_MOPS) {  // (a sweep through more levels than the list holds)
+                                    full = true;
+                                    break;
+                                }
+                                const u32 la = r.lvol + 4u * bq;
+                                const u32 lv = lds(la);
+                                const u32 take = min(rem, lv), nv = lv - take;
+                                rem -= take;
+                                sts(la, nv);
+                                last_t = n_out;
+                                sts(r.scr + SC_SWEPT + 4u * (bq & (DW_SWEPT - 1u)), mark);
+                                sts128(co + 16u * n_out++, make_uint4(bq | (MK_T << 13) | (rem > 0u ? 1u << 16 : 0u) | (opp << 17) | ebits, take, 0u, 0u));
+                                s.flush_take += take;
+                                if (nv == 0u) bk_level_gone<true>(r, s, 0u, opp, bq);
+                            }
+                            if (full) break;
+                            // rest or finish (orderbook.rs:495-531, 699-722)
+                            if (rem == 0u || (f & EF_MARKET)) {
+                                const u32 status = rem == 0u ? ST_FILLED : ST_CANCELLED;  // (trading is enabled on this path)
+                                const u32 own = ekind | (side << 8) | (status << 12);
+                                const u32 aux = ekind == RK_REPLACE ? price : rem;
+                                if (last_t != 0xFFFFFFFFu) {  // the entry rides on the event's last take
+                                    sts64(co + 16u * last_t + 8u, ((u64)own << 32) | aux);
+                                } else {  // a market order that found no other side
+                                    sts128(co + 16u * n_out++, make_uint4((MK_N << 13) | ebits, 0u, aux, own));
+                                }
+                            } else {  // insert_order (side.rs:54-66), the ladder half
+                                const u32 q = price - r.win_lo;
+                                const u32 ba = bk_bm(r, side, q >> 5), bit = 1u << (q & 31u);
+                                const u32 la = r.lvol + 4u * q;
+                                const u32 bw = lds(ba);
+                                if (!(bw & bit)) {
+                                    if (lds(bk_bm(r, opp, q >> 5)) & bit) {  // (cannot happen while trading is enabled and volumes are > 0)
+                                        s.err |= ERR_LOCKED;
+                                    } else {
                                         sts(la, rem);
                                         sts(ba, bw | bit);
-                                        if (bw == 0u) sts(sa, sv | (1u << ((q >> 5) & 31u)));
+                                        if (bw == 0u) {
+                                            const u32 sa = bk_sm(r, side, q >> 10);
+                                            sts(sa, lds(sa) | (1u << ((q >> 5) & 31u)));
+                                        }
+                                        if (!bk_has_best(s, side) || (side ? q > s.bq_bid : q < s.bq_ask)) {
+                                            if (side) s.bq_bid = q; else s.bq_ask = q;
+                                            s.flags |= FL_HAS_ASK << side;
+                                        }
                                     }
-                                    const bool better = !bk_has_best(s, side) || (side ? q > s.bq_bid : q < s.bq_ask);
-                                    if (better) {
-                                        if (side) s.bq_bid = q; else s.bq_ask = q;
-                                        s.flags |= FL_HAS_ASK << side;
-                                    }
+                                } else {
+                                    sts(la, lds(la) + rem);
                                 }
-                            } else {
-                                if (lane == 0u) sts(la, lv + rem);
+                                last_a = e;
+                                sts128(co + 16u * n_out++, make_uint4(q | (MK_A << 13) | (side << 17) | ebits, rem, 0u, ekind | (side << 8) | (ST_ACTIVE << 12)));
                             }
-                            bk_add_side(s, side, rem);
-                            s.max_key_time = s.t;
-                            bk_emit(r, s, lane, q | (MK_A << 13), eid, rem, 0u, d0.z, d0.w, ekind | (side << 8) | (ST_ACTIVE << 12), mark);
+                            in_place = false;
                         }
-                        s.d_applied += 1;
-                        in_place = false;
-                        __syncwarp();
+                        ++e;
                     }
-                    ++e;
                 }
+                __syncwarp();
+                // ---- back to 32 lanes: lane 0's view of the ladder, then everything that was left off the chain -----------------
+                e = __shfl_sync(BB_FULL, e, 0);
+                n_out = __shfl_sync(BB_FULL, n_out, 0);
+                last_a = __shfl_sync(BB_FULL, last_a, 0);
+                late = __shfl_sync(BB_FULL, stop, 0) == 1u;
+                s.bq_ask = __shfl_sync(BB_FULL, s.bq_ask, 0);
+                s.bq_bid = __shfl_sync(BB_FULL, s.bq_bid, 0);
+                s.flags = __shfl_sync(BB_FULL, s.flags, 0);
+                s.err = __shfl_sync(BB_FULL, s.err, 0);
+                s.flush_take = __shfl_sync(BB_FULL, s.flush_take, 0);
+                // the micro-ops in full: ids, times, positions and marks come from the decoded events
+                s.n_mop = n_out;
+                int d_ask = 0, d_bid = 0;
+                u32 tv = 0u;
+                for (u32 m0 = 0; m0 < n_out; m0 += 32u) {
+                    const u32 m = m0 + lane;
+                    if (m < n_out) {
+                        const uint4 cr = lds128(r.scr + SC_COUT + 16u * m);
+                        const u32 ce = (cr.x >> 18) & 31u, kind = (cr.x >> 13) & 7u, sd = (cr.x >> 17) & 1u;
+                        const u32 ea = r.scr + SC_EVD + 48u * ce;
+                        const uint4 d0 = lds128(ea);
+                        u32 a2 = cr.y, a3 = cr.z;
+                        int dv = 0;
+                        if (kind == MK_T) {
+                            dv = -(int)cr.y;
+                            tv += cr.y;
+                        } else if (kind == MK_A) {
+                            dv = (int)cr.y;
+                        } else if (kind == MK_R) {
+                            dv = -(int)cr.y;
+                            a2 = lds(ea + 24u);
+                        } else if (kind == MK_D) {
+                            dv = -(int)cr.y;
+                            a2 = lds(ea + 24u);
+                            a3 = lds(ea + 28u);
+                        }
+                        if (sd) d_bid += dv; else d_ask += dv;
+                        const u32 ma = r.scr + SC_MOP + 32u * m;
+                        sts128(ma, make_uint4(cr.x & 0x3FFFFu, d0.y, a2, a3));
+                        sts128(ma + 16u, make_uint4(d0.z, d0.w, cr.w, ev0 + ce + 1u));
+                    }
+                }
+                s.vol_ask += (u32)__reduce_add_sync(BB_FULL, d_ask);
+                s.vol_bid += (u32)__reduce_add_sync(BB_FULL, d_bid);
+                s.trade_vol += __reduce_add_sync(BB_FULL, tv);
+                if (last_a < 32u) s.max_key_time = ((u64)lds(r.scr + SC_EVD + 48u * last_a + 12u) << 32) | lds(r.scr + SC_EVD + 48u * last_a + 8u);
                 // the one place micro-ops are replayed from: `e` events of the batch are complete
                 if (!bk_flush(r, s, lane, ev0 + e, lane_err)) return false;
-                last_t = 0xFFFFFFFFu;
                 if (e >= e_end || late) break;
+            }
+            {   // the counters of the events done (a cancel / modify of an order that is not on the book counts as an instruction only)
+                const bool mine = ((clean >> lane) & 1u) && lane < e;
+                s.d_instr += __popc(__ballot_sync(BB_FULL, mine && (ef & EF_INSTR)));
+                s.d_applied += __popc(__ballot_sync(BB_FULL, mine && (ef & (EF_PLACE | EF_REM | EF_RED))));
+                s.n_orders += __popc(__ballot_sync(BB_FULL, mine && (ef & EF_NEW)));
+                if (e > first) s.t = ((u64)__shfl_sync(BB_FULL, t_hi, e - 1u) << 32) | __shfl_sync(BB_FULL, t_lo, e - 1u);
             }
             pending &= ~(clean & (e >= 32u ? BB_FULL : ((1u << e) - 1u)));
             if (late) continue;  // (decode the rest again: the fills made meanwhile are in the filter now)

@@ -53,9 +53,13 @@ def dict_to_columns(d: dict):
     status = np.array([STATUS.index(o["order"]["status"]) for o in orders], dtype=np.uint8).reshape(n)
     col = lambda k, dt: np.array([o["order"][k] for o in orders], dtype=dt).reshape(n)  # noqa: E731
     key_time = np.array([o["key"][2] for o in orders], dtype=np.uint64).reshape(n)
-    for o in orders:  # the key must agree with the order it belongs to, as the reference assumes
+    # The reference's TryFrom (orderbook.rs:898-905) re-inserts every ACTIVE order under its stored key, whatever that key says;
+    # keys of orders that are no longer on the book are carried along unread.  A key that disagrees with its Active order
+    # (other side, other price) would put the order where this engine cannot represent it: refused.  Stale keys of ended
+    # orders (e.g. filled during a replace: the key keeps the price from before the modify) are accepted as the reference does.
+    for o in orders:
         bid = o["order"]["side"] == "Bid"
-        if o["key"][0] != o["order"]["side"] or (o["order"]["status"] == "Active" and
+        if o["order"]["status"] == "Active" and (o["key"][0] != o["order"]["side"] or
                                                   o["key"][1] != (U32_MAX - o["order"]["price"] if bid else o["order"]["price"])):
             raise ValueError("Failed to convert OrderBookState to an OrderBook")
     tcol = lambda k, dt: np.array([x[k] for x in trades], dtype=dt).reshape(m)  # noqa: E731

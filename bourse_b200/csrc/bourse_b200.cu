@@ -231,7 +231,8 @@ DeepOff deep_layout(u32 W, bool wide) {
     o.lcnt = o.lvol + 4u * W;
     o.lht = o.lcnt + 4u * W;
     o.image_bytes = align_up(o.lht + 8u * W, 128);
-    u32 off = o.image_bytes;
+    o.smem_image = wide ? o.lcnt : o.image_bytes;  // (16-byte aligned: the bulk copy stops exactly where the counts begin)
+    u32 off = align_up(o.smem_image, 128);
     const u32 rb = wide ? DW_RB : DP_RB, rcap = wide ? DW_RCAP : DP_RCAP;
     o.ctag = off; off += wide ? 0u : 4u * DP_NC;
     o.cdat = off; off += wide ? DW_SCRATCH : DP_CHUNK_BYTES * DP_NC;  // (k_deepw: its scratch block)

@@ -66,6 +66,7 @@ namespace bb {
 #define DP_SWEPT 256u        // swept-level filter buckets (by level index)
 struct DeepOff {             // byte offsets from the CTA's shared-memory base, filled by the host
     u32 bm, sm, lvol, lcnt, lht, image_bytes;
+    u32 smem_image;  // bytes of the image that live in shared memory during a launch (k_deepw: up to lcnt; its queues' counts / heads / tails stay in the blob)
     u32 ctag, cdat, ev_ins, ev_rec, ev_rf, cmd, ret, dirty, swept, ctl, bar, total;
 };
 // control words (u32 each, at DeepOff::ctl)
@@ -139,13 +140,16 @@ __device__ unsigned long long g_dp_prof[64];
 #endif
 // bounded spin on a control word; returns false when the wait ran out or another warp aborted
 #define DP_SPIN_MAX (1u << 25)
-template <class F> __device__ __forceinline__ bool dp_wait(u32 ctl, F cond, int prof_slot = 0) {
+// NAP: the waiting warp sleeps between polls (producers / consumers that are far ahead: their polling would otherwise take
+// issue slots and shared-memory bandwidth from the book warps of the SM)
+template <bool NAP = false, class F> __device__ __forceinline__ bool dp_wait(u32 ctl, F cond, int prof_slot = 0) {
     DP_T0
     for (u32 spin = 0; spin < DP_SPIN_MAX; ++spin) {
         if (cond()) {
             DP_ADD(prof_slot)
             return true;
         }
+        if (NAP && spin >= 4u) __nanosleep(spin < 64u ? 100u : 400u);
         if ((spin & 255u) == 255u && ld_acq(ctl + CT_ABORT)) return false;
     }
     st_rel(ctl + CT_ABORT, 1u);

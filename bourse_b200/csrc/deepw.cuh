@@ -31,7 +31,7 @@ namespace bb {
 
 #define DW_RB 4u        // event-ring depth in batches of 32
 #define DW_RCAP 256u    // retire-ring entries
-#define DW_DIRTY 4096u  // touched-order filter buckets (by order id)
+#define DW_DIRTY 2048u  // touched-order filter buckets (by order id)
 #define DW_MOPS 64u     // micro-op list capacity (32 bytes each); a replay round takes 32
 #define DW_FILLS 192u   // fills staged per flush (16 bytes each): also the largest volume one flush may take
 // scratch block (byte offsets from BkReg::scr)
@@ -56,9 +56,11 @@ __device__ __forceinline__ u32 atoms_add(u32 a, u32 v) {
 }
 
 struct BkReg {  // launch-invariant addresses and limits (pinned in registers)
-    u32 lvol, lcnt, lht, bma, bmb, sma, smb, scr, ret, dirty, ctl, fs;
+    u32 lvol, bma, bmb, sma, smb, scr, ret, dirty, ctl, fs;
     u32 win_lo, W, max_orders, n_chunks, max_trades;
     u64 oh, chunks, tr;
+    u64 lcnt, lht;  // per level, in the book's blob (global memory, L1-cached: only this CTA touches them): resting orders;
+                    // {head, tail} of the level's queue: chunk id << 5 | entry index (tail: next free entry)
 };
 struct BkSt {  // the book's scalar state: warp-uniform (every lane holds the same values)
     u64 t, max_key_time;
@@ -203,14 +205,14 @@ __device__ __forceinline__ void bk_level_gone(const BkReg& r, BkSt& s, u32 lane,
 
 // insert_order's queue half (side.rs:54-66), one order, warp-uniform: append to the level's chunk chain -> entry position
 __device__ __forceinline__ u32 bk_append(const BkReg& r, BkSt& s, u32 lane, u32 q, u32 id, u32 vol) {
-    const u32 cnt = lds(r.lcnt + 4u * q);
-    const u32 tail = lds(r.lht + 8u * q + 4u);
+    const u32 cnt = ldg32(r.lcnt + 4u * q);
+    const u32 tail = ldg32(r.lht + 8u * q + 4u);
     __syncwarp();
     u32 pos;
     if (cnt == 0u) {
         const u32 c = bk_alloc(r, s, lane);
         pos = c << 5;
-        if (lane == 0u) sts64(r.lht + 8u * q, ((u64)(pos + 1u) << 32) | pos);
+        if (lane == 0u) stg64(r.lht + 8u * q, ((u64)(pos + 1u) << 32) | pos);
     } else {
         u32 c = tail >> 5, idx = tail & 31u;
         if (idx == DP_CHUNK_ENTRIES) {  // tail chunk full: link a new one
@@ -220,10 +222,10 @@ __device__ __forceinline__ u32 bk_append(const BkReg& r, BkSt& s, u32 lane, u32 
             idx = 0u;
         }
         pos = (c << 5) | idx;
-        if (lane == 0u) sts(r.lht + 8u * q + 4u, pos + 1u);
+        if (lane == 0u) stg32(r.lht + 8u * q + 4u, pos + 1u);
     }
     if (lane == 0u) {
-        sts(r.lcnt + 4u * q, cnt + 1u);
+        stg32(r.lcnt + 4u * q, cnt + 1u);
         stg64(bk_chunk(r, pos >> 5) + 8u * (pos & 31u), ((u64)vol << 32) | id);
     }
     __syncwarp();
@@ -231,12 +233,12 @@ __device__ __forceinline__ u32 bk_append(const BkReg& r, BkSt& s, u32 lane, u32 
 }
 // remove_order's queue half (side.rs:75-84): tombstone the entry
 __device__ __forceinline__ void bk_remove(const BkReg& r, BkSt& s, u32 lane, u32 q, u32 pos) {
-    const u32 cnt = lds(r.lcnt + 4u * q);
-    const u64 ht = lds64(r.lht + 8u * q);
+    const u32 cnt = ldg32(r.lcnt + 4u * q);
+    const u64 ht = ldg64(r.lht + 8u * q);
     __syncwarp();
     if (lane == 0u) {
         stg32(bk_chunk(r, pos >> 5) + 8u * (pos & 31u), BB_NIL);
-        sts(r.lcnt + 4u * q, cnt <= 1u ? 0u : cnt - 1u);
+        stg32(r.lcnt + 4u * q, cnt <= 1u ? 0u : cnt - 1u);
     }
     if (cnt <= 1u && ((u32)ht >> 5) == ((u32)(ht >> 32) >> 5)) bk_free_chunk(r, s, lane, (u32)ht >> 5);  // a longer all-dead chain is left to the pool
     __syncwarp();
@@ -251,9 +253,9 @@ __device__ __forceinline__ void bk_remove(const BkReg& r, BkSt& s, u32 lane, u32
 __device__ __forceinline__ bool bk_sweep(const BkReg& r, BkSt& s, u32 lane, u32 q, u32 opp, u32 take, bool exhaust, u32 id, u32 t_lo, u32 t_hi,
                                          u32 price, u32 mark, u32& lane_err) {
     for (u32 guard = 0; guard < (1u << 22); ++guard) {
-        const u32 cnt0 = lds(r.lcnt + 4u * q);
+        const u32 cnt0 = ldg32(r.lcnt + 4u * q);
         if (!((take > 0u || exhaust) && cnt0 > 0u)) break;
-        const u64 ht = lds64(r.lht + 8u * q);
+        const u64 ht = ldg64(r.lht + 8u * q);
         const u32 head = (u32)ht, tail = (u32)(ht >> 32);
         const u32 c = head >> 5, idx = head & 31u, tc = tail >> 5;
         const u32 end = (c == tc) ? (tail & 31u) : DP_CHUNK_ENTRIES;
@@ -295,7 +297,7 @@ __device__ __forceinline__ bool bk_sweep(const BkReg& r, BkSt& s, u32 lane, u32 
         bool done = false;
         if (cnt == 0u) {  // the level is gone
             if (c == tc) bk_free_chunk(r, s, lane, c);
-            if (lane == 0u) sts(r.lcnt + 4u * q, 0u);
+            if (lane == 0u) stg32(r.lcnt + 4u * q, 0u);
         } else {
             u32 nh = 0u;
             bool bad = false;
@@ -313,8 +315,8 @@ __device__ __forceinline__ bool bk_sweep(const BkReg& r, BkSt& s, u32 lane, u32 
             }
             if (bad) s.err |= ERR_CAP_PAGES;
             if (lane == 0u) {
-                sts(r.lcnt + 4u * q, bad ? 0u : cnt);
-                if (!bad) sts(r.lht + 8u * q, nh);
+                stg32(r.lcnt + 4u * q, bad ? 0u : cnt);
+                if (!bad) stg32(r.lht + 8u * q, nh);
             }
         }
         __syncwarp();
@@ -331,7 +333,7 @@ __device__ __forceinline__ void bk_level_at(const BkReg& r, u32 side, u32 price,
     if (q >= r.W) return;
     if (!((lds(bk_bm(r, side, q >> 5)) >> (q & 31u)) & 1u)) return;
     *vol = lds(r.lvol + 4u * q);
-    *cnt = lds(r.lcnt + 4u * q);
+    *cnt = ldg32(r.lcnt + 4u * q);
 }
 // observation words of the book: lane l owns words l and l + 32 (layout: book_obs in book.cuh)
 __device__ __forceinline__ void bk_obs(const BkReg& r, u32 tick, u32 lane, u32 trade_vol, u32 bid, u32 ask, u32 vol_ask, u32 vol_bid, u32* w0,
@@ -423,7 +425,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
                     bk_add_side(s, oside, 0u - a.y);
                     bk_remove(r, s, lane, q, a.z);
                     if (cancel && !bk_ret1(r, s, lane, make_uint4(RK_CANCEL | (oside << 8), id, 0u, 0u), make_uint4(x.x, x.y, 0u, 0u))) return false;
-                    if (nv == 0u && (!s.zv || lds(r.lcnt + 4u * q) == 0u)) bk_level_gone(r, s, lane, oside, q);
+                    if (nv == 0u && (!s.zv || ldg32(r.lcnt + 4u * q) == 0u)) bk_level_gone(r, s, lane, oside, q);
                     if (lane == 0u) sts(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
                     if (cancel) {
                         s.d_applied += 1;
@@ -460,7 +462,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
                 s.trade_vol += take;
                 bk_add_side(s, opp, 0u - take);
                 if (!bk_sweep(r, s, lane, bq, opp, take, exhaust, id, x.x, x.y, bprice, ev_done, lane_err)) return false;
-                if (nv == 0u && (exhaust || !s.zv || lds(r.lcnt + 4u * bq) == 0u)) bk_level_gone(r, s, lane, opp, bq);
+                if (nv == 0u && (exhaust || !s.zv || ldg32(r.lcnt + 4u * bq) == 0u)) bk_level_gone(r, s, lane, opp, bq);
             }
         }
         // ---- rest or finish (orderbook.rs:495-531, 699-722)
@@ -610,8 +612,8 @@ __device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 
         // ---- one lane per level: the level's micro-ops in order --------------------------------------------------------
         const u32 mg = __match_any_sync(BB_FULL, (valid && kind != MK_N) ? q : (0xFFFFFF00u | lane));
         if (valid && kind != MK_N && (mg & lt) == 0u) {
-            u32 cnt = lds(r.lcnt + 4u * q);
-            const u64 ht = lds64(r.lht + 8u * q);
+            u32 cnt = ldg32(r.lcnt + 4u * q);
+            const u64 ht = ldg64(r.lht + 8u * q);
             u32 head = (u32)ht, tail = (u32)(ht >> 32);
             for (u32 mm = mg; mm; mm &= mm - 1u) {
                 const u32 j = (u32)__ffs(mm) - 1u;
@@ -682,8 +684,8 @@ __device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 
                     sts(r.scr + SC_NFILL + 4u * j, nf);
                 }
             }
-            sts(r.lcnt + 4u * q, cnt);
-            sts64(r.lht + 8u * q, ((u64)tail << 32) | head);
+            stg32(r.lcnt + 4u * q, cnt);
+            stg64(r.lht + 8u * q, ((u64)tail << 32) | head);
         }
         __syncwarp();
         // ---- places in the retire ring and in the trade log: event order, i.e. micro-op order ---------------------------------

@@ -1028,7 +1028,7 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
 #define DPF_MARKET (1u << 16)      // the order takes the market path: BB_F_MARKET, or a limit price equal to the sentinel (N3)
 #define DPF_CAP_ORDERS (1u << 17)  // a NEW row whose id would not fit the order table
 
-template <u32 RB>
+template <u32 RB, bool NAP = false>
 __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, const bb_instr* ins, u32 n, u64 oh,
                                               u32 next_id) {
     const u32 ctl = sb + o.ctl;
@@ -1036,7 +1036,7 @@ __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o
     for (u32 b = 0; b < nb; ++b) {
         const u32 slot = b & (RB - 1u);
         if (b >= RB) {
-            if (!dp_wait(ctl, [&] { return ld_acq(ctl + CT_EV_CONSUMED) + RB > b; }, 1)) return;
+            if (!dp_wait<NAP>(ctl, [&] { return ld_acq(ctl + CT_EV_CONSUMED) + RB > b; }, 1)) return;
         }
         const u32 cnt = min(32u, n - 32u * b);
         const u32 ia = sb + o.ev_ins + 1024u * slot, bar = sb + o.bar + 8u + 8u * slot;
@@ -1108,14 +1108,14 @@ __device__ __forceinline__ void dp_fetch_warp(const KParams& p, const DeepOff& o
 }
 
 // TRADES: fill entries also append to the trade log in ring order (deep.cuh); k_deepw's book warp writes the log itself
-template <u32 RCAP, bool TRADES>
+template <u32 RCAP, bool TRADES, bool NAP = false>
 __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, u64 oh, u64 tr, u32 n_tr0) {
     const u32 ctl = sb + o.ctl;
     u32 head = 0, n_tr = n_tr0, err = 0, ev_pub = 0;
     for (;;) {
         u32 tail = 0, q_ev = 0;
         bool fin = false;
-        const bool ok = dp_wait(ctl, [&] {
+        const bool ok = dp_wait<NAP>(ctl, [&] {
             fin = ld_acq(ctl + CT_FIN) != 0u;  // read before the tail: FIN is set after the last tail update
             q_ev = ld_acq(ctl + CT_Q_EV);      // ... and the event count before the tail it is covered by
             tail = ld_acq(ctl + CT_RET_TAIL);
@@ -1687,7 +1687,7 @@ namespace bb {
 // ---------------------------------------------------------------------------------------------------
 // Deep-book replay kernel, batch-parallel (deepw.cuh): one CTA per book; warp 0 = the book (a batch of 32 events, one lane
 // each), warp 1 = fetch, warp 2 = retire.  Same blob image, chunk pool, order records and trade log as k_deep.
-__global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(96, 4) k_deepw(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const u32 sb = smem_u32(smem);
@@ -1711,8 +1711,8 @@ __global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParam
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx_a(sb + o.bar, o.image_bytes);
-        bulk_g2s_a(sb, p.blobs + (size_t)env * p.blob_stride, o.image_bytes, sb + o.bar);
+        mbar_expect_tx_a(sb + o.bar, o.smem_image);
+        bulk_g2s_a(sb, p.blobs + (size_t)env * p.blob_stride, o.smem_image, sb + o.bar);
         if (!mbar_wait_a(sb + o.bar, 0u)) st_rel(ctl + CT_ABORT, 1u);
     }
     __syncthreads();
@@ -1722,15 +1722,15 @@ __global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParam
 #endif
 
     if (warp == 1u) {
-        dp_fetch_warp<DW_RB>(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
+        dp_fetch_warp<DW_RB, true>(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
     } else if (warp == 2u) {
-        dp_retire_warp<DW_RCAP, false>(p, o, sb, lane, oh, tr, n_tr0);
+        dp_retire_warp<DW_RCAP, false, true>(p, o, sb, lane, oh, tr, n_tr0);
     } else if (warp == 0u) {
         // ---- the book warp ---------------------------------------------------------------------------------------
         BkReg r;
         r.lvol = dp_keep32(sb + o.lvol);
-        r.lcnt = dp_keep32(sb + o.lcnt);
-        r.lht = dp_keep32(sb + o.lht);
+        r.lcnt = dp_keep64((u64)(p.blobs + (size_t)env * p.blob_stride + o.lcnt));  // (the queues' counts / heads / tails stay in the blob)
+        r.lht = dp_keep64((u64)(p.blobs + (size_t)env * p.blob_stride + o.lht));
         r.bma = dp_keep32(sb + o.bm);
         r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
         r.sma = dp_keep32(sb + o.sm);
@@ -1871,7 +1871,7 @@ __global__ void __launch_bounds__(128, 2) k_deepw(const __grid_constant__ KParam
         sts(sb + HDR_ERR, lds(sb + HDR_ERR) | (err & 0x7FFFFFFFu));
         if (err) atomicOr(p.err_flag, err);
         fence_proxy_async();
-        bulk_s2g_a(p.blobs + (size_t)env * p.blob_stride, sb, o.image_bytes);
+        bulk_s2g_a(p.blobs + (size_t)env * p.blob_stride, sb, o.smem_image);
         bulk_commit();
         bulk_wait_all<0>();
     }

@@ -378,7 +378,7 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
         }
         p.dp_fast = h->deep_mode == 2 ? 1u : 0u;
         if (h->deep_mode == 0) k_deep<<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
-        else k_deepw<<<h->cfg.n_envs, 96, h->dp.total, h->stream>>>(p);
+        else k_deepw<<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
         CUDA_TRY(h, cudaGetLastError());
         h->recorded_host = -1;
         return BB_OK;

@@ -85,7 +85,17 @@ struct DeepOff {             // byte offsets from the CTA's shared-memory base, 
 #define CT_QERR 48u         // queue warp's error bits
 #define CT_LERR 52u         // ladder warp's error bits
 #define CT_QNTR 56u         // queue warp: trades made in this launch
-#define CT_WORDS 16u
+// k_deepw (deepw.cuh): chain warp <-> replay warp
+#define CT_MOP_TAIL 64u     // chain: micro-ops published
+#define CT_MOP_DONE 68u     // replay: micro-ops replayed
+#define CT_DRAIN 72u        // chain: odd = "finish what is published, then park" (even: run)
+#define CT_PARKED 76u       // replay: the CT_DRAIN value it has parked for
+#define RS_BUMP 80u         // the replay warp's scalars, at rest here between rounds (the chain warp borrows them while the
+#define RS_NFREE 84u        // replay warp is parked: complex events run on the chain warp)
+#define RS_NTR 88u
+#define RS_RET_TAIL 92u
+#define RS_ERR 96u
+#define CT_WORDS 32u
 
 // ladder -> queue commands: a = {op | side << 8 | kind-or-flag << 12 | last << 16 | status << 20, order id, level / position, volume},
 //                            b = {t lo, t hi, price / level, events completed once this command is done}

@@ -32,23 +32,25 @@ namespace bb {
 #define DW_RB 4u        // event-ring depth in batches of 32
 #define DW_RCAP 256u    // retire-ring entries
 #define DW_DIRTY 2048u  // touched-order filter buckets (by order id)
-#define DW_MOPS 64u     // micro-op list capacity (32 bytes each); a replay round takes 32
+#define DW_MOPS 128u    // micro-op ring (32 bytes each) between the chain warp and the replay warp; a replay round takes up to 32
+#define DW_COUT 64u     // the chain's output list per run (16 bytes each)
 #define DW_FILLS 192u   // fills staged per flush (16 bytes each): also the largest volume one flush may take
 // scratch block (byte offsets from BkReg::scr)
 #define SC_MOP 0u
 #define SC_EVD (SC_MOP + 32u * DW_MOPS)      // decoded events, 48 bytes per lane
 #define SC_FILL (SC_EVD + 48u * 32u)         // staged fills {micro-op | rank << 8, passive id, traded volume, passive volume left}
-#define SC_NFILL (SC_FILL + 16u * DW_FILLS)  // per micro-op: fills made
-#define SC_POS (SC_NFILL + 4u * DW_MOPS)     // per micro-op: position of the appended entry
-#define SC_SPARE (SC_POS + 4u * DW_MOPS)     // per micro-op: a fresh chunk (bit 31: used)
-#define SC_FREED (SC_SPARE + 4u * DW_MOPS)   // per micro-op: up to two chunks it emptied
-#define SC_FCOUNT (SC_FREED + 8u * DW_MOPS)
+#define SC_NFILL (SC_FILL + 16u * DW_FILLS)  // per micro-op of the round: fills made
+#define SC_POS (SC_NFILL + 4u * 32u)         // ... position of the appended entry
+#define SC_SPARE (SC_POS + 4u * 32u)         // ... a fresh chunk (bit 31: used)
+#define SC_FREED (SC_SPARE + 4u * 32u)       // ... up to two chunks it emptied
+#define SC_FCOUNT (SC_FREED + 8u * 32u)
 #define SC_SWEPT (SC_FCOUNT + 16u)           // per level (hashed): the last event that took volume from it
 #define DW_SWEPT 256u
 #define SC_COUT (SC_SWEPT + 4u * DW_SWEPT)   // the chain's output: one 16-byte record per micro-op
-#define DW_SCRATCH (SC_COUT + 16u * DW_MOPS)
+#define DW_SCRATCH (SC_COUT + 16u * DW_COUT)
 
 __device__ __forceinline__ void reds_add(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_max(u32 a, u32 v) { asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 atoms_add(u32 a, u32 v) {
     u32 o;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
@@ -69,7 +71,8 @@ struct BkSt {  // the book's scalar state: warp-uniform (every lane holds the sa
     u32 bump, n_free;       // chunk allocator
     u32 n_tr;               // next trade-log index
     u32 ret_tail, ret_room, ret_pub;
-    u32 n_mop, flush_take;  // micro-ops waiting for replay, volume they take
+    u32 n_emit, done_seen;  // chain warp: micro-ops written to the ring, (a lower bound of) those the replay warp has finished
+    u32 drain_seq;          // chain warp: the CT_DRAIN value last written
 #ifdef DP_PROF
     u32 pf_flush, pf_rounds, pf_mops, pf_ser, pf_reason[8];
 #endif
@@ -286,7 +289,7 @@ __device__ __forceinline__ bool bk_sweep(const BkReg& r, BkSt& s, u32 lane, u32 
             // trade: side / price are the passive order's (orderbook.rs:853-862)
             bk_ret_write(r, s.ret_tail + k, make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), pid, tv, pv), make_uint4(t_lo, t_hi, price, id));
             bk_trade(r, s, s.n_tr + k, t_lo, t_hi, price, tv, id, pid, opp, lane_err);
-            sts(r.dirty + 4u * (pid & (DW_DIRTY - 1u)), mark);
+            reds_max(r.dirty + 4u * (pid & (DW_DIRTY - 1u)), mark);
             if (!full) stg32(bk_chunk(r, c) + 8u * lane + 4u, pv);  // the partially filled order stays at the head of its level
         }
         take -= traded;
@@ -414,7 +417,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
                     bk_add_side(s, oside, y.y - a.y);
                     if (y.y == 0u) s.zv = 1u;
                     if (!bk_ret1(r, s, lane, make_uint4(RK_REDUCE, id, y.y, 0u), make_uint4(x.x, x.y, 0u, 0u))) return false;
-                    if (lane == 0u) sts(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
+                    if (lane == 0u) reds_max(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
                     s.d_applied += 1;
                 } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
                     const bool cancel = op == BB_OP_CANCEL;
@@ -426,7 +429,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
                     bk_remove(r, s, lane, q, a.z);
                     if (cancel && !bk_ret1(r, s, lane, make_uint4(RK_CANCEL | (oside << 8), id, 0u, 0u), make_uint4(x.x, x.y, 0u, 0u))) return false;
                     if (nv == 0u && (!s.zv || ldg32(r.lcnt + 4u * q) == 0u)) bk_level_gone(r, s, lane, oside, q);
-                    if (lane == 0u) sts(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
+                    if (lane == 0u) reds_max(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
                     if (cancel) {
                         s.d_applied += 1;
                     } else {  // never a market order (N4)
@@ -521,7 +524,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
         // rest — flagged above — keeps status Active in its record and is not on the book)
         if (!bk_ret1(r, s, lane, make_uint4(kind | (side << 8) | (status << 12), id, rem, rests ? pos : 0u), make_uint4(x.x, x.y, price, 0u)))
             return false;
-        if (lane == 0u) sts(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
+        if (lane == 0u) reds_max(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
         s.d_applied += 1;
     }
     bk_publish(r, s, lane, ev_done);
@@ -557,35 +560,31 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
 #define EF_NEW 128u
 #define EF_MARKET 256u
 
-__device__ __forceinline__ void bk_emit(const BkReg& r, BkSt& s, u32 lane, u32 w0, u32 w1, u32 w2, u32 w3, u32 t_lo, u32 t_hi, u32 own, u32 mark) {
-    if (lane == 0u) {
-        const u32 ma = r.scr + SC_MOP + 32u * s.n_mop;
-        sts128(ma, make_uint4(w0, w1, w2, w3));
-        sts128(ma + 16u, make_uint4(t_lo, t_hi, own, mark));
-    }
-    s.n_mop += 1;
-}
-
-// ---- replay: every queued micro-op, 32 per round, one lane each; then `ev_done` events are complete -------------------------
-__device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 ev_done, u32& lane_err) {
+// ---- replay: one round = up to 32 micro-ops from the ring (starting at `head`), one lane each -------------------------------
+// (`rhead`: ring index of its first micro-op.)  Returns the number of micro-ops done (0 when a bounded wait ran out).  `s` is the REPLAY warp's state: chunk allocator, trade
+// count, retire ring.  A round stops short of 32 where the volume its takes may fill would overflow the fill staging area.
+__device__ __forceinline__ u32 bk_replay_round(const BkReg& r, BkSt& s, u32 lane, u32 rhead, u32 avail, u32& lane_err) {
     const u32 lt = (1u << lane) - 1u;
-    __syncwarp();
-#ifdef DP_PROF
-    s.pf_flush += 1;
-    s.pf_mops += s.n_mop;
-#endif
-    for (u32 base = 0; base < s.n_mop; base += 32u) {
-#ifdef DP_PROF
-        s.pf_rounds += 1;
-#endif
-        const u32 m = base + lane;
-        const bool valid = m < s.n_mop;
-        const u32 ma = r.scr + SC_MOP + 32u * m;
+    {
+        const u32 ma = r.scr + SC_MOP + 32u * ((rhead + lane) & (DW_MOPS - 1u));
         uint4 w = make_uint4(0, 0, 0, 0), v = w;
-        if (valid) {
+        if (lane < avail) {
             w = lds128(ma);
             v = lds128(ma + 16u);
         }
+        // the round: the longest prefix whose takes fit the staging area (each take alone does)
+        u32 cum = (lane < avail && ((w.x >> 13) & 7u) == MK_T) ? w.z : 0u;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const u32 a = __shfl_up_sync(BB_FULL, cum, k);
+            if (lane >= (u32)k) cum += a;
+        }
+        const u32 n_round = __popc(__ballot_sync(BB_FULL, lane < avail && cum <= DW_FILLS));
+        const bool valid = lane < n_round;
+#ifdef DP_PROF
+        s.pf_rounds += 1;
+        s.pf_mops += n_round;
+#endif
         const u32 q = w.x & 0x1FFFu, kind = (w.x >> 13) & 7u;
         // a fresh chunk for every append (it needs at most one); what is not used goes back below
         const bool is_a = valid && kind == MK_A;
@@ -617,7 +616,7 @@ __device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 
             u32 head = (u32)ht, tail = (u32)(ht >> 32);
             for (u32 mm = mg; mm; mm &= mm - 1u) {
                 const u32 j = (u32)__ffs(mm) - 1u;
-                const uint4 x = lds128(r.scr + SC_MOP + 32u * (base + j));
+                const uint4 x = lds128(r.scr + SC_MOP + 32u * ((rhead + j) & (DW_MOPS - 1u)));
                 const u32 kj = (x.x >> 13) & 7u;
                 if (kj == MK_A) {  // insert_order's queue half (side.rs:54-66)
                     if (cnt == 0u || (tail & 31u) == DP_CHUNK_ENTRIES) {
@@ -698,7 +697,7 @@ __device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 
             if (lane >= (u32)k) { ci += a; fi += b; }
         }
         const u32 n_ring = __shfl_sync(BB_FULL, ci, 31), n_fill = __shfl_sync(BB_FULL, fi, 31);
-        if (!bk_ret_space(r, s, lane, n_ring)) return false;
+        if (!bk_ret_space(r, s, lane, n_ring)) return 0u;
         const u32 ring0 = s.ret_tail + ci - (nf + (own ? 1u : 0u)), tr0 = s.n_tr + fi - nf;  // this micro-op's first ring slot / trade
         // the fills, 32 at a time: trade record + the passive order's record update
         for (u32 f0 = 0; f0 < n_fill; f0 += 32u) {
@@ -715,7 +714,7 @@ __device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 
                 // trade: side / price are the passive order's (orderbook.rs:853-862)
                 bk_ret_write(r, jr + k, make_uint4(RK_FILL | (jopp << 8) | (g.w == 0u ? 0x10000u : 0u), g.y, g.z, g.w), make_uint4(jlo, jhi, price, jid));
                 bk_trade(r, s, jt + k, jlo, jhi, price, g.z, jid, g.y, jopp, lane_err);
-                sts(r.dirty + 4u * (g.y & (DW_DIRTY - 1u)), jmark);
+                reds_max(r.dirty + 4u * (g.y & (DW_DIRTY - 1u)), jmark);
             }
         }
         // the events' own record entries
@@ -734,7 +733,7 @@ __device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 
                 eb.z = w.w;
             }
             bk_ret_write(r, ring0 + nf, ea, eb);
-            sts(r.dirty + 4u * (w.y & (DW_DIRTY - 1u)), v.w);
+            reds_max(r.dirty + 4u * (w.y & (DW_DIRTY - 1u)), v.w);
         }
         s.ret_tail += n_ring;
         s.n_tr += n_fill;
@@ -766,12 +765,113 @@ __device__ __forceinline__ bool bk_flush(const BkReg& r, BkSt& s, u32 lane, u32 
             }
         }
         __syncwarp();
+        // what is complete now: the events whose last micro-op (the one that carries the record entry) was in this round
+        const u32 om = __ballot_sync(BB_FULL, own != 0u);
+        if (om) {
+            const u32 ev_done = __shfl_sync(BB_FULL, v.w, 31u - (u32)__clz(om));
+            bk_publish(r, s, lane, ev_done);
+        }
+        return n_round;
     }
-    s.n_mop = 0u;
-    s.flush_take = 0u;
-    bk_publish(r, s, lane, ev_done);
+}
+
+// ---- the replay warp: rounds while micro-ops are published; parks when the chain warp asks for it ---------------------------------
+__device__ __forceinline__ void bk_replay_warp(const BkReg& r, u32 lane, u32 n_tr0) {
+    BkSt s;
+    s.err = 0u;
+    s.ret_room = 0u;  // (first use reads the retire warp's counter)
+#ifdef DP_PROF
+    s.pf_rounds = s.pf_mops = 0u;
+#endif
+    u32 head = 0u, lane_err = 0u, parked = 0u, ok_final = 1u;
+    (void)n_tr0;
+    for (;;) {
+        u32 tail = 0u, drain = 0u, fin = 0u, ok = 1u;
+        if (lane == 0u) {
+            ok = dp_wait(r.ctl, [&] {
+                fin = ld_acq(r.ctl + CT_FIN_L);   // read before the tail: set after the last publication
+                drain = ld_acq(r.ctl + CT_DRAIN);  // (likewise)
+                tail = ld_acq(r.ctl + CT_MOP_TAIL);
+                return tail != head || fin != 0u || ((drain & 1u) && drain != parked);
+            }, 7) ? 1u : 0u;
+        }
+        ok = __shfl_sync(BB_FULL, ok, 0);
+        tail = __shfl_sync(BB_FULL, tail, 0);
+        drain = __shfl_sync(BB_FULL, drain, 0);
+        fin = __shfl_sync(BB_FULL, fin, 0);
+        if (!ok) { ok_final = 0u; break; }
+        if (tail != head) {
+            s.bump = lds(r.ctl + RS_BUMP);
+            s.n_free = lds(r.ctl + RS_NFREE);
+            s.n_tr = lds(r.ctl + RS_NTR);
+            s.ret_tail = s.ret_pub = lds(r.ctl + RS_RET_TAIL);
+            if (s.ret_room < s.ret_tail) s.ret_room = s.ret_tail;
+            while (tail != head) {
+                const u32 n = bk_replay_round(r, s, lane, head, min(32u, tail - head), lane_err);
+                if (n == 0u) { ok = 0u; break; }
+                head += n;
+                if (lane == 0u) st_rel(r.ctl + CT_MOP_DONE, head);
+            }
+            __syncwarp();
+            if (lane == 0u) {
+                if (s.ret_pub != s.ret_tail) st_rel(r.ctl + CT_RET_TAIL, s.ret_tail);
+                sts(r.ctl + RS_BUMP, s.bump);
+                sts(r.ctl + RS_NFREE, s.n_free);
+                sts(r.ctl + RS_NTR, s.n_tr);
+                sts(r.ctl + RS_RET_TAIL, s.ret_tail);
+            }
+            s.ret_pub = s.ret_tail;
+            if (!ok) { ok_final = 0u; break; }
+            continue;
+        }
+        if ((drain & 1u) && drain != parked) {  // everything published is done: the chain warp may borrow the queues
+            parked = drain;
+            if (lane == 0u) st_rel(r.ctl + CT_PARKED, parked);
+            continue;
+        }
+        if (fin) break;
+    }
+    lane_err = __reduce_or_sync(BB_FULL, lane_err | s.err);
+    if (lane == 0u) {
+        sts(r.ctl + RS_ERR, lane_err);
+        if (!ok_final) st_rel(r.ctl + CT_ABORT, 1u);
+    }
+#ifdef DP_PROF
+    if (lane == 0u && blockIdx.x == 0) printf("k_deepw replay warp: rounds %u, micro-ops %u\n", s.pf_rounds, s.pf_mops);
+#endif
+}
+
+// ---- chain warp: the replay warp finishes what is published and parks; its scalars come over (complex events, market-data
+// records and the end of the launch work on the queues from the chain warp) -----------------------------------------------------------
+__device__ __forceinline__ bool bk_borrow(const BkReg& r, BkSt& s, u32 lane) {
+    s.drain_seq += 1;  // odd
+    const u32 seq = s.drain_seq;
+    __syncwarp();
+    if (lane == 0u) st_rel(r.ctl + CT_DRAIN, seq);
+    if (!bk_wait(r, lane, [&] { return ld_acq(r.ctl + CT_PARKED) == seq; }, 5)) return false;
+    s.bump = lds(r.ctl + RS_BUMP);
+    s.n_free = lds(r.ctl + RS_NFREE);
+    s.n_tr = lds(r.ctl + RS_NTR);
+    s.ret_tail = s.ret_pub = lds(r.ctl + RS_RET_TAIL);
+    s.ret_room = s.ret_tail;  // (re-read the retire warp's counter on first use)
+    s.done_seen = s.n_emit;
     return true;
 }
+__device__ __forceinline__ void bk_give_back(const BkReg& r, BkSt& s, u32 lane) {
+    __syncwarp();
+    if (lane == 0u) {
+        if (s.ret_pub != s.ret_tail) st_rel(r.ctl + CT_RET_TAIL, s.ret_tail);
+        sts(r.ctl + RS_BUMP, s.bump);
+        sts(r.ctl + RS_NFREE, s.n_free);
+        sts(r.ctl + RS_NTR, s.n_tr);
+        sts(r.ctl + RS_RET_TAIL, s.ret_tail);
+    }
+    s.ret_pub = s.ret_tail;
+    s.drain_seq += 1;  // even: run
+    __syncwarp();
+    if (lane == 0u) st_rel(r.ctl + CT_DRAIN, s.drain_seq);
+}
+
 
 #define CXR_EMIT 0
 #define CXR_STATE 1
@@ -795,6 +895,10 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
     while (pending) {
         const u32 first = (u32)__ffs(pending) - 1u;
         const bool valid = (pending >> lane) & 1u;
+        // events whose fills are all in the touched-order filter (sampled BEFORE the filter is read below)
+        u32 qev = 0u;
+        if (lane == 0u) qev = ld_acq(r.ctl + CT_Q_EV);
+        qev = __shfl_sync(BB_FULL, qev, 0);
         // ---- decode: everything that does not depend on the book -------------------------------------------------------
         bool cx = false;
         u32 why = CXR_OTHER;
@@ -879,14 +983,14 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
             // It stops where its output list (or the volume one flush may take) is full — possibly in the middle of an
             // aggressive order's sweep — and goes on after the flush below.
             // A cancel / modify trusts the order record the fetch warp prefetched; the decode step above has checked it against
-            // every fill already made, but not against the takes of THIS chain run: an event that names an order on a level
-            // taken from since then stops the run (`late`) and is decoded again once those fills are known.
-            const u32 chain_start = ev0 + first;
+            // every fill the replay warp had made by then (`qev`), but not against takes that are still on their way through
+            // the ring: an event that names an order on a level taken from since then stops the run (`late`), waits for the
+            // replay warp to get there and is decoded again.
             u32 e = first, rem = 0u, last_t = 0xFFFFFFFFu;  // (rem, last_t, in_place: lane 0's)
             bool in_place = false, late = false;
             for (;;) {
                 const u32 e_from = e;
-                u32 n_out = 0u, last_a = 32u, stop = 0u;  // stop: 1 = late
+                u32 n_out = 0u, last_a = 32u, stop = 0u;  // stop: the mark to wait for (late)
                 if (lane == 0u) {
                     const u32 co = r.scr + SC_COUT;
                     last_t = 0xFFFFFFFFu;  // (the list is empty again; a sweep under way continues with its next take)
@@ -898,16 +1002,14 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                             uint4 d1 = make_uint4(0, 0, 0, 0);
                             if (f & (EF_REM | EF_RED)) {
                                 d1 = lds128(ea + 16u);
-                                if (lds(r.scr + SC_SWEPT + 4u * (d1.x & (DW_SWEPT - 1u))) > chain_start) {
-                                    stop = 1u;
+                                const u32 sw = lds(r.scr + SC_SWEPT + 4u * (d1.x & (DW_SWEPT - 1u)));
+                                if (sw > qev) {
+                                    stop = sw;
                                     break;
                                 }
                             }
-                            if (n_out + 3u > DW_MOPS) break;
-                            if (f & EF_PLACE) {
-                                rem = lds(ea + 36u);
-                                if (s.flush_take + rem > DW_FILLS) break;
-                            }
+                            if (n_out + 3u > DW_COUT) break;
+                            if (f & EF_PLACE) rem = lds(ea + 36u);
                             if (f & (EF_REM | EF_RED)) {
                                 const u32 oside = (f & EF_OSIDE) ? 1u : 0u;
                                 const u32 la = r.lvol + 4u * d1.x;
@@ -938,7 +1040,7 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                                 const u32 bq = bk_best_q(s, opp);
                                 const u32 bprice = r.win_lo + bq;
                                 if (side ? (price < bprice) : (price > bprice)) break;
-                                if (n_out + 2u > DW_MOPS) {  // (a sweep through more levels than the list holds)
+                                if (n_out + 2u > DW_COUT) {  // (a sweep through more levels than the list holds)
                                     full = true;
                                     break;
                                 }
@@ -950,7 +1052,6 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                                 last_t = n_out;
                                 sts(r.scr + SC_SWEPT + 4u * (bq & (DW_SWEPT - 1u)), mark);
                                 sts128(co + 16u * n_out++, make_uint4(bq | (MK_T << 13) | (rem > 0u ? 1u << 16 : 0u) | (opp << 17) | ebits, take, 0u, 0u));
-                                s.flush_take += take;
                                 if (nv == 0u) bk_level_gone<true>(r, s, 0u, opp, bq);
                             }
                             if (full) break;
@@ -1000,14 +1101,23 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                 e = __shfl_sync(BB_FULL, e, 0);
                 n_out = __shfl_sync(BB_FULL, n_out, 0);
                 last_a = __shfl_sync(BB_FULL, last_a, 0);
-                late = __shfl_sync(BB_FULL, stop, 0) == 1u;
+                stop = __shfl_sync(BB_FULL, stop, 0);
+                late = stop != 0u;
                 s.bq_ask = __shfl_sync(BB_FULL, s.bq_ask, 0);
                 s.bq_bid = __shfl_sync(BB_FULL, s.bq_bid, 0);
                 s.flags = __shfl_sync(BB_FULL, s.flags, 0);
                 s.err = __shfl_sync(BB_FULL, s.err, 0);
-                s.flush_take = __shfl_sync(BB_FULL, s.flush_take, 0);
-                // the micro-ops in full: ids, times, positions and marks come from the decoded events
-                s.n_mop = n_out;
+                // the micro-ops in full — ids, times, positions and marks come from the decoded events — go into the ring
+                if (s.n_emit + n_out - s.done_seen > DW_MOPS) {
+                    u32 done = 0u;
+                    const u32 need = s.n_emit + n_out - DW_MOPS;
+                    if (!bk_wait(r, lane, [&] {
+                            done = ld_acq(r.ctl + CT_MOP_DONE);
+                            return (int)(done - need) >= 0;
+                        }, 4))
+                        return false;
+                    s.done_seen = __shfl_sync(BB_FULL, done, 0);
+                }
                 int d_ask = 0, d_bid = 0;
                 u32 tv = 0u;
                 for (u32 m0 = 0; m0 < n_out; m0 += 32u) {
@@ -1033,17 +1143,28 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                             a3 = lds(ea + 28u);
                         }
                         if (sd) d_bid += dv; else d_ask += dv;
-                        const u32 ma = r.scr + SC_MOP + 32u * m;
+                        const u32 ma = r.scr + SC_MOP + 32u * ((s.n_emit + m) & (DW_MOPS - 1u));
+                        const u32 mark = ev0 + ce + 1u;
                         sts128(ma, make_uint4(cr.x & 0x3FFFFu, d0.y, a2, a3));
-                        sts128(ma + 16u, make_uint4(d0.z, d0.w, cr.w, ev0 + ce + 1u));
+                        sts128(ma + 16u, make_uint4(d0.z, d0.w, cr.w, mark));
+                        // the order this event names is in flight from now on: its prefetched record is not to be trusted
+                        if (cr.w) reds_max(r.dirty + 4u * (d0.y & (DW_DIRTY - 1u)), mark);
                     }
                 }
+                s.n_emit += n_out;
+                __syncwarp();
+                if (lane == 0u && n_out) st_rel(r.ctl + CT_MOP_TAIL, s.n_emit);
+#ifdef DP_PROF
+                s.pf_flush += 1;
+#endif
                 s.vol_ask += (u32)__reduce_add_sync(BB_FULL, d_ask);
                 s.vol_bid += (u32)__reduce_add_sync(BB_FULL, d_bid);
                 s.trade_vol += __reduce_add_sync(BB_FULL, tv);
                 if (last_a < 32u) s.max_key_time = ((u64)lds(r.scr + SC_EVD + 48u * last_a + 12u) << 32) | lds(r.scr + SC_EVD + 48u * last_a + 8u);
-                // the one place micro-ops are replayed from: `e` events of the batch are complete
-                if (!bk_flush(r, s, lane, ev0 + e, lane_err)) return false;
+                if (late) {  // the replay warp has to get past the take that may have filled the order this event names
+                    const u32 need = stop;
+                    if (!bk_wait(r, lane, [&] { return ld_acq(r.ctl + CT_Q_EV) >= need; }, 14)) return false;
+                }
                 if (e >= e_end || late) break;
             }
             {   // the counters of the events done (a cancel / modify of an order that is not on the book counts as an instruction only)
@@ -1067,12 +1188,16 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
             ky.x = __shfl_sync(BB_FULL, y.x, k); ky.y = __shfl_sync(BB_FULL, y.y, k); ky.z = __shfl_sync(BB_FULL, y.z, k); ky.w = __shfl_sync(BB_FULL, y.w, k);
             ka.x = __shfl_sync(BB_FULL, a.x, k); ka.y = __shfl_sync(BB_FULL, a.y, k); ka.z = __shfl_sync(BB_FULL, a.z, k); ka.w = __shfl_sync(BB_FULL, a.w, k);
             kc.x = __shfl_sync(BB_FULL, c.x, k); kc.y = __shfl_sync(BB_FULL, c.y, k); kc.z = __shfl_sync(BB_FULL, c.z, k); kc.w = __shfl_sync(BB_FULL, c.w, k);
-            if (!bk_serial(r, s, lane, kx, ky, ka, kc, ev0 + k + 1u, rf, lane_err)) return false;
+            // the replay warp parks; the whole reference algorithm for this event runs here, on the queues as they are
+            if (!bk_borrow(r, s, lane)) return false;
+            const bool sok = bk_serial(r, s, lane, kx, ky, ka, kc, ev0 + k + 1u, rf, lane_err);
             pending &= ~(1u << k);
-            if (kx.z & BB_F_EMIT) {  // the caller writes the market-data record and comes back for the rest of the batch
+            if (sok && (kx.z & BB_F_EMIT)) {  // the caller writes the market-data record, gives the queues back and returns for the rest
                 obs_lane = k;
                 return true;
             }
+            bk_give_back(r, s, lane);
+            if (!sok) return false;
         }
         (void)why;
     }

@@ -1687,7 +1687,7 @@ namespace bb {
 // ---------------------------------------------------------------------------------------------------
 // Deep-book replay kernel, batch-parallel (deepw.cuh): one CTA per book; warp 0 = the book (a batch of 32 events, one lane
 // each), warp 1 = fetch, warp 2 = retire.  Same blob image, chunk pool, order records and trade log as k_deep.
-__global__ void __launch_bounds__(96, 4) k_deepw(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const u32 sb = smem_u32(smem);
@@ -1721,30 +1721,39 @@ __global__ void __launch_bounds__(96, 4) k_deepw(const __grid_constant__ KParams
     const long long dp_k0 = clock64();
 #endif
 
+    BkReg r;
+    r.lvol = dp_keep32(sb + o.lvol);
+    r.lcnt = dp_keep64((u64)(p.blobs + (size_t)env * p.blob_stride + o.lcnt));  // (the queues' counts / heads / tails stay in the blob)
+    r.lht = dp_keep64((u64)(p.blobs + (size_t)env * p.blob_stride + o.lht));
+    r.bma = dp_keep32(sb + o.bm);
+    r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
+    r.sma = dp_keep32(sb + o.sm);
+    r.smb = dp_keep32(sb + o.sm + 4u * DP_NS);
+    r.scr = dp_keep32(sb + o.cdat);
+    r.ret = dp_keep32(sb + o.ret);
+    r.dirty = dp_keep32(sb + o.dirty);
+    r.ctl = dp_keep32(ctl);
+    r.fs = dp_keep32(sb + DP_OFF_FS);
+    r.win_lo = p.geo.d_win_lo; r.W = p.geo.d_levels; r.max_orders = p.geo.max_orders;
+    r.n_chunks = p.dp_chunks; r.max_trades = p.geo.max_trades;
+    r.oh = dp_keep64(oh);
+    r.chunks = dp_keep64((u64)(p.dp_pool + (size_t)env * p.dp_chunks * DP_CHUNK_BYTES));
+    r.tr = dp_keep64(tr);
+    if (threadIdx.x == 0) {  // the replay warp's scalars, at rest
+        sts(ctl + RS_BUMP, lds(sb + DP_OFF_BUMP));
+        sts(ctl + RS_NFREE, lds(sb + DP_OFF_NFREE));
+        sts(ctl + RS_NTR, n_tr0);
+        sts(ctl + RS_RET_TAIL, 0u);
+    }
+    __syncthreads();
     if (warp == 1u) {
         dp_fetch_warp<DW_RB, true>(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
     } else if (warp == 2u) {
         dp_retire_warp<DW_RCAP, false, true>(p, o, sb, lane, oh, tr, n_tr0);
+    } else if (warp == 3u) {
+        bk_replay_warp(r, lane, n_tr0);
     } else if (warp == 0u) {
-        // ---- the book warp ---------------------------------------------------------------------------------------
-        BkReg r;
-        r.lvol = dp_keep32(sb + o.lvol);
-        r.lcnt = dp_keep64((u64)(p.blobs + (size_t)env * p.blob_stride + o.lcnt));  // (the queues' counts / heads / tails stay in the blob)
-        r.lht = dp_keep64((u64)(p.blobs + (size_t)env * p.blob_stride + o.lht));
-        r.bma = dp_keep32(sb + o.bm);
-        r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
-        r.sma = dp_keep32(sb + o.sm);
-        r.smb = dp_keep32(sb + o.sm + 4u * DP_NS);
-        r.scr = dp_keep32(sb + o.cdat);
-        r.ret = dp_keep32(sb + o.ret);
-        r.dirty = dp_keep32(sb + o.dirty);
-        r.ctl = dp_keep32(ctl);
-        r.fs = dp_keep32(sb + DP_OFF_FS);
-        r.win_lo = p.geo.d_win_lo; r.W = p.geo.d_levels; r.max_orders = p.geo.max_orders;
-        r.n_chunks = p.dp_chunks; r.max_trades = p.geo.max_trades;
-        r.oh = dp_keep64(oh);
-        r.chunks = dp_keep64((u64)(p.dp_pool + (size_t)env * p.dp_chunks * DP_CHUNK_BYTES));
-        r.tr = dp_keep64(tr);
+        // ---- the chain warp ---------------------------------------------------------------------------------------
         const u32 ev_ins = dp_keep32(sb + o.ev_ins), ev_rec = dp_keep32(sb + o.ev_rec);
         BkSt s;
         s.t = lds64(sb + HDR_T);
@@ -1760,12 +1769,10 @@ __global__ void __launch_bounds__(96, 4) k_deepw(const __grid_constant__ KParams
         s.err = 0u;
         s.d_instr = s.d_applied = 0u;
         s.zv = lds(sb + HDR_FREETOP);
-        s.bump = lds(sb + DP_OFF_BUMP);
-        s.n_free = lds(sb + DP_OFF_NFREE);
+        s.bump = s.n_free = 0u;  // (the queues' scalars are the replay warp's; bk_borrow brings them over)
         s.n_tr = n_tr0;
-        s.ret_tail = s.ret_pub = 0u;
-        s.ret_room = DW_RCAP;
-        s.n_mop = s.flush_take = 0u;
+        s.ret_tail = s.ret_pub = s.ret_room = 0u;
+        s.n_emit = s.done_seen = s.drain_seq = 0u;
 #ifdef DP_PROF
         s.pf_flush = s.pf_rounds = s.pf_mops = s.pf_ser = 0u;
         for (int i = 0; i < 8; ++i) s.pf_reason[i] = 0u;
@@ -1809,16 +1816,20 @@ __global__ void __launch_bounds__(96, 4) k_deepw(const __grid_constant__ KParams
                         s.err |= ERR_CAP_STEPS;
                     }
                     __syncwarp();
+                    bk_give_back(r, s, lane);  // (bk_batch came back with the queues still borrowed)
                 }
             }
             if (lane == 0u) st_rel(r.ctl + CT_EV_CONSUMED, b + 1u);
         }
-        // ---- the header goes back into the image; the retire warp drains what is left and exits on FIN
+        // ---- the replay warp finishes and parks; the header goes back into the image; the retire warp drains what is left and
+        // exits on FIN, the replay warp on FIN_L
+        if (!aborted && !bk_borrow(r, s, lane)) aborted = true;
         lane_err = __reduce_or_sync(BB_FULL, lane_err);
         __syncwarp();
         if (lane == 0u) {
-            st_rel(r.ctl + CT_RET_TAIL, s.ret_tail);
+            if (!aborted) st_rel(r.ctl + CT_RET_TAIL, s.ret_tail);
             st_rel(r.ctl + CT_FIN, 1u);
+            st_rel(r.ctl + CT_FIN_L, 1u);
             sts64(sb + HDR_T, s.t);
             sts64(sb + HDR_MAXKT, s.max_key_time);
             sts64(sb + HDR_NCREATED, lds64(sb + HDR_NCREATED) + (s.n_orders - n_orders0));
@@ -1843,8 +1854,8 @@ __global__ void __launch_bounds__(96, 4) k_deepw(const __grid_constant__ KParams
             if (aborted) st_rel(ctl + CT_ABORT, 1u);
 #ifdef DP_PROF
             if (blockIdx.x == 0)
-                printf("k_deepw book warp: flushes %u, replay rounds %u, micro-ops %u, serial events %u (emit %u state %u big %u doubt %u same-id %u "
-                       "time %u zero %u other %u)\n", s.pf_flush, s.pf_rounds, s.pf_mops, s.pf_ser, s.pf_reason[0], s.pf_reason[1], s.pf_reason[2],
+                printf("k_deepw chain warp: runs %u, serial events %u (emit %u state %u big %u doubt %u same-id %u "
+                       "time %u zero %u other %u)\n", s.pf_flush, s.pf_ser, s.pf_reason[0], s.pf_reason[1], s.pf_reason[2],
                        s.pf_reason[3], s.pf_reason[4], s.pf_reason[5], s.pf_reason[6], s.pf_reason[7]);
 #endif
         }
@@ -1866,7 +1877,7 @@ __global__ void __launch_bounds__(96, 4) k_deepw(const __grid_constant__ KParams
         const u64 tt = lds64(sb + HDR_NTRADES_TOTAL) + fills;
         sts64(sb + HDR_NTRADES_TOTAL, tt);
         sts(sb + HDR_NTRADES, (u32)min(tt, (u64)p.geo.max_trades));
-        u32 err = lds(ctl + CT_RERR) | lds(ctl + CT_LERR);
+        u32 err = lds(ctl + CT_RERR) | lds(ctl + CT_LERR) | lds(ctl + RS_ERR);
         if (ld_acq(ctl + CT_ABORT)) err |= 0x80000000u;
         sts(sb + HDR_ERR, lds(sb + HDR_ERR) | (err & 0x7FFFFFFFu));
         if (err) atomicOr(p.err_flag, err);

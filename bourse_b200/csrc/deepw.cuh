@@ -873,6 +873,71 @@ __device__ __forceinline__ void bk_give_back(const BkReg& r, BkSt& s, u32 lane) 
 }
 
 
+// The placement half of an event on the chain (lane 0 alone): match_bid / match_ask (orderbook.rs:429-487) level by level —
+// how much each crossed level gives — then rest or finish (orderbook.rs:495-531, 699-722).  SIDE is the order's side, a
+// compile-time constant so that "the other side's touch" is a register, not a select.  Returns true when the output list is
+// full in the middle of a sweep (the caller flushes and calls again: rem and the ladder carry the state).
+template <u32 SIDE>
+__device__ __forceinline__ bool bk_chain_place(const BkReg& r, BkSt& s, u32 co, u32& n_out, u32 ea, u32 f, u32 e, u32 mark, u32& rem, u32& last_t,
+                                               u32& last_a) {
+    constexpr u32 OPP = SIDE ^ 1u;
+    constexpr u32 HAS_OPP = FL_HAS_ASK << OPP, HAS_OWN = FL_HAS_ASK << SIDE;
+    const u32 price = lds(ea + 32u);
+    const u32 ebits = e << 18;
+    while (rem > 0u && (s.flags & HAS_OPP)) {
+        const u32 bq = SIDE ? s.bq_ask : s.bq_bid;
+        const u32 bprice = r.win_lo + bq;
+        if (SIDE ? (price < bprice) : (price > bprice)) break;
+        if (n_out + 2u > DW_COUT) return true;  // (a sweep through more levels than the list holds)
+        const u32 la = r.lvol + 4u * bq;
+        const u32 lv = lds(la);
+        const u32 take = min(rem, lv), nv = lv - take;
+        rem -= take;
+        sts(la, nv);
+        last_t = n_out;
+        sts(r.scr + SC_SWEPT + 4u * (bq & (DW_SWEPT - 1u)), mark);
+        sts128(co + 16u * n_out++, make_uint4(bq | (MK_T << 13) | (rem > 0u ? 1u << 16 : 0u) | (OPP << 17) | ebits, take, 0u, 0u));
+        if (nv == 0u) bk_level_gone<true>(r, s, 0u, OPP, bq);
+    }
+    const u32 ekind = (f & EF_REPLACE) ? RK_REPLACE : RK_NEW;
+    if (rem == 0u || (f & EF_MARKET)) {
+        const u32 status = rem == 0u ? ST_FILLED : ST_CANCELLED;  // (trading is enabled on this path)
+        const u32 own = ekind | (SIDE << 8) | (status << 12);
+        const u32 aux = ekind == RK_REPLACE ? price : rem;
+        if (last_t != 0xFFFFFFFFu) {  // the entry rides on the event's last take
+            sts64(co + 16u * last_t + 8u, ((u64)own << 32) | aux);
+        } else {  // a market order that found no other side
+            sts128(co + 16u * n_out++, make_uint4((MK_N << 13) | ebits, 0u, aux, own));
+        }
+    } else {  // insert_order (side.rs:54-66), the ladder half
+        const u32 q = price - r.win_lo;
+        const u32 ba = (SIDE ? r.bmb : r.bma) + 4u * (q >> 5), bit = 1u << (q & 31u);
+        const u32 la = r.lvol + 4u * q;
+        const u32 bw = lds(ba);
+        if (!(bw & bit)) {
+            if (lds((SIDE ? r.bma : r.bmb) + 4u * (q >> 5)) & bit) {  // (cannot happen while trading is enabled and volumes are > 0)
+                s.err |= ERR_LOCKED;
+            } else {
+                sts(la, rem);
+                sts(ba, bw | bit);
+                if (bw == 0u) {
+                    const u32 sa = (SIDE ? r.smb : r.sma) + 4u * (q >> 10);
+                    sts(sa, lds(sa) | (1u << ((q >> 5) & 31u)));
+                }
+                if (!(s.flags & HAS_OWN) || (SIDE ? q > s.bq_bid : q < s.bq_ask)) {
+                    if (SIDE) s.bq_bid = q; else s.bq_ask = q;
+                    s.flags |= HAS_OWN;
+                }
+            }
+        } else {
+            sts(la, lds(la) + rem);
+        }
+        last_a = e;
+        sts128(co + 16u * n_out++, make_uint4(q | (MK_A << 13) | (SIDE << 17) | ebits, rem, 0u, ekind | (SIDE << 8) | (ST_ACTIVE << 12)));
+    }
+    return false;
+}
+
 #define CXR_EMIT 0
 #define CXR_STATE 1
 #define CXR_BIG 2
@@ -891,6 +956,7 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
     const u32 op = x.z & BB_OP_MASK;
     const u32 t_lo = x.x, t_hi = x.y;
     const u64 t = ((u64)t_hi << 32) | t_lo;
+    u32 rfl = rf;  // per lane: events whose record writes were in HBM when THIS lane's record (a, c) was read
     obs_lane = 32u;
     while (pending) {
         const u32 first = (u32)__ffs(pending) - 1u;
@@ -919,7 +985,7 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                 if (id >= s.n_orders + __popc(newm & lt) || id >= r.max_orders) {
                     cx = true;  // unknown id
                 } else {
-                    if (lds(r.dirty + 4u * (id & (DW_DIRTY - 1u))) > rf) { cx = true; why = CXR_DOUBT; }
+                    if (lds(r.dirty + 4u * (id & (DW_DIRTY - 1u))) > rfl) { cx = true; why = CXR_DOUBT; }
                     const bool has_p = (x.z & BB_F_HAS_PRICE) != 0u, has_v = (x.z & BB_F_HAS_VOL) != 0u;
                     q1 = a.x - r.win_lo;
                     if ((c.z & META_STATUS_MASK) != ST_ACTIVE || (op == BB_OP_MODIFY && !has_p && !has_v) || q1 >= r.W) {
@@ -994,104 +1060,44 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                 if (lane == 0u) {
                     const u32 co = r.scr + SC_COUT;
                     last_t = 0xFFFFFFFFu;  // (the list is empty again; a sweep under way continues with its next take)
-                    while (e < e_end) {
+                    if (in_place) {  // the sweep the last run had to leave
                         const u32 ea = r.scr + SC_EVD + 48u * e;
                         const u32 f = lds(ea);
-                        const u32 ebits = e << 18;
-                        if (!in_place) {
-                            uint4 d1 = make_uint4(0, 0, 0, 0);
-                            if (f & (EF_REM | EF_RED)) {
-                                d1 = lds128(ea + 16u);
-                                const u32 sw = lds(r.scr + SC_SWEPT + 4u * (d1.x & (DW_SWEPT - 1u)));
-                                if (sw > qev) {
-                                    stop = sw;
-                                    break;
-                                }
+                        in_place = (f & EF_PSIDE) ? bk_chain_place<1u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
+                                                  : bk_chain_place<0u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a);
+                        if (!in_place) ++e;
+                    }
+                    while (!in_place && e < e_end) {
+                        const u32 ea = r.scr + SC_EVD + 48u * e;
+                        const u32 f = lds(ea);
+                        if (n_out + 4u > DW_COUT) break;
+                        if (f & (EF_REM | EF_RED)) {
+                            const uint4 d1 = lds128(ea + 16u);
+                            const u32 sw = lds(r.scr + SC_SWEPT + 4u * (d1.x & (DW_SWEPT - 1u)));
+                            if (sw > qev) {
+                                stop = sw;
+                                break;
                             }
-                            if (n_out + 3u > DW_COUT) break;
-                            if (f & EF_PLACE) rem = lds(ea + 36u);
-                            if (f & (EF_REM | EF_RED)) {
-                                const u32 oside = (f & EF_OSIDE) ? 1u : 0u;
-                                const u32 la = r.lvol + 4u * d1.x;
-                                const u32 lv = lds(la);
-                                if (f & EF_RED) {  // reduce in place: priority kept (orderbook.rs:755-757)
-                                    sts(la, lv - (d1.y - d1.w));
-                                    sts128(co + 16u * n_out++, make_uint4(d1.x | (MK_D << 13) | (oside << 17) | ebits, d1.y - d1.w, 0u, RK_REDUCE));
-                                } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
-                                    const u32 nv = lv - d1.y;
-                                    sts(la, nv);
-                                    sts128(co + 16u * n_out++, make_uint4(d1.x | (MK_R << 13) | (oside << 17) | ebits, d1.y, 0u,
-                                                                          (f & EF_PLACE) ? 0u : (RK_CANCEL | (oside << 8))));
-                                    if (nv == 0u) bk_level_gone<true>(r, s, 0u, oside, d1.x);
-                                }
-                            }
-                            if (f & EF_PLACE) {
-                                in_place = true;
-                                last_t = 0xFFFFFFFFu;
+                            const u32 oside = (f & EF_OSIDE) ? 1u : 0u;
+                            const u32 la = r.lvol + 4u * d1.x;
+                            const u32 lv = lds(la);
+                            if (f & EF_RED) {  // reduce in place: priority kept (orderbook.rs:755-757)
+                                sts(la, lv - (d1.y - d1.w));
+                                sts128(co + 16u * n_out++, make_uint4(d1.x | (MK_D << 13) | (oside << 17) | (e << 18), d1.y - d1.w, 0u, RK_REDUCE));
+                            } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
+                                const u32 nv = lv - d1.y;
+                                sts(la, nv);
+                                sts128(co + 16u * n_out++, make_uint4(d1.x | (MK_R << 13) | (oside << 17) | (e << 18), d1.y, 0u,
+                                                                      (f & EF_PLACE) ? 0u : (RK_CANCEL | (oside << 8))));
+                                if (nv == 0u) bk_level_gone<true>(r, s, 0u, oside, d1.x);
                             }
                         }
-                        if (in_place) {
-                            const u32 side = (f & EF_PSIDE) ? 1u : 0u, opp = side ^ 1u, price = lds(ea + 32u);
-                            const u32 ekind = (f & EF_REPLACE) ? RK_REPLACE : RK_NEW;
-                            const u32 mark = ev0 + e + 1u;
-                            // match_bid / match_ask (orderbook.rs:429-487): how much each crossed level gives
-                            bool full = false;
-                            while (rem > 0u && bk_has_best(s, opp)) {
-                                const u32 bq = bk_best_q(s, opp);
-                                const u32 bprice = r.win_lo + bq;
-                                if (side ? (price < bprice) : (price > bprice)) break;
-                                if (n_out + 2u > DW_COUT) {  // (a sweep through more levels than the list holds)
-                                    full = true;
-                                    break;
-                                }
-                                const u32 la = r.lvol + 4u * bq;
-                                const u32 lv = lds(la);
-                                const u32 take = min(rem, lv), nv = lv - take;
-                                rem -= take;
-                                sts(la, nv);
-                                last_t = n_out;
-                                sts(r.scr + SC_SWEPT + 4u * (bq & (DW_SWEPT - 1u)), mark);
-                                sts128(co + 16u * n_out++, make_uint4(bq | (MK_T << 13) | (rem > 0u ? 1u << 16 : 0u) | (opp << 17) | ebits, take, 0u, 0u));
-                                if (nv == 0u) bk_level_gone<true>(r, s, 0u, opp, bq);
-                            }
-                            if (full) break;
-                            // rest or finish (orderbook.rs:495-531, 699-722)
-                            if (rem == 0u || (f & EF_MARKET)) {
-                                const u32 status = rem == 0u ? ST_FILLED : ST_CANCELLED;  // (trading is enabled on this path)
-                                const u32 own = ekind | (side << 8) | (status << 12);
-                                const u32 aux = ekind == RK_REPLACE ? price : rem;
-                                if (last_t != 0xFFFFFFFFu) {  // the entry rides on the event's last take
-                                    sts64(co + 16u * last_t + 8u, ((u64)own << 32) | aux);
-                                } else {  // a market order that found no other side
-                                    sts128(co + 16u * n_out++, make_uint4((MK_N << 13) | ebits, 0u, aux, own));
-                                }
-                            } else {  // insert_order (side.rs:54-66), the ladder half
-                                const u32 q = price - r.win_lo;
-                                const u32 ba = bk_bm(r, side, q >> 5), bit = 1u << (q & 31u);
-                                const u32 la = r.lvol + 4u * q;
-                                const u32 bw = lds(ba);
-                                if (!(bw & bit)) {
-                                    if (lds(bk_bm(r, opp, q >> 5)) & bit) {  // (cannot happen while trading is enabled and volumes are > 0)
-                                        s.err |= ERR_LOCKED;
-                                    } else {
-                                        sts(la, rem);
-                                        sts(ba, bw | bit);
-                                        if (bw == 0u) {
-                                            const u32 sa = bk_sm(r, side, q >> 10);
-                                            sts(sa, lds(sa) | (1u << ((q >> 5) & 31u)));
-                                        }
-                                        if (!bk_has_best(s, side) || (side ? q > s.bq_bid : q < s.bq_ask)) {
-                                            if (side) s.bq_bid = q; else s.bq_ask = q;
-                                            s.flags |= FL_HAS_ASK << side;
-                                        }
-                                    }
-                                } else {
-                                    sts(la, lds(la) + rem);
-                                }
-                                last_a = e;
-                                sts128(co + 16u * n_out++, make_uint4(q | (MK_A << 13) | (side << 17) | ebits, rem, 0u, ekind | (side << 8) | (ST_ACTIVE << 12)));
-                            }
-                            in_place = false;
+                        if (f & EF_PLACE) {
+                            rem = lds(ea + 36u);
+                            last_t = 0xFFFFFFFFu;
+                            in_place = (f & EF_PSIDE) ? bk_chain_place<1u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
+                                                      : bk_chain_place<0u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a);
+                            if (in_place) break;
                         }
                         ++e;
                     }
@@ -1183,6 +1189,24 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
             s.pf_reason[__shfl_sync(BB_FULL, why, kcut) & 7u] += 1;
 #endif
             const u32 k = kcut;
+            if (__shfl_sync(BB_FULL, why, k) == CXR_DOUBT) {
+                // A doubtful record is no reason for the serial path: everything that is on its way drains (the micro-ops are all
+                // published), the record is read again, and the event is decoded again — with a record it can trust now.
+                const u32 need = __shfl_sync(BB_FULL, lds(r.dirty + 4u * (id & (DW_DIRTY - 1u))), k);
+                u32 seen = 0u;
+                if (!bk_wait(r, lane, [&] {
+                        seen = ld_acq(r.ctl + CT_EV_RETIRED);
+                        return seen >= need;
+                    }, 13))
+                    return false;
+                seen = __shfl_sync(BB_FULL, seen, 0);
+                if (lane == k) {
+                    a = ldg128_cg(r.oh + (u64)id * ORD_STRIDE);
+                    c = ldg128_cg(r.oh + (u64)id * ORD_STRIDE + 16u);
+                    rfl = seen;
+                }
+                continue;
+            }
             uint4 kx, ky, ka, kc;
             kx.x = __shfl_sync(BB_FULL, x.x, k); kx.y = __shfl_sync(BB_FULL, x.y, k); kx.z = __shfl_sync(BB_FULL, x.z, k); kx.w = __shfl_sync(BB_FULL, x.w, k);
             ky.x = __shfl_sync(BB_FULL, y.x, k); ky.y = __shfl_sync(BB_FULL, y.y, k); ky.z = __shfl_sync(BB_FULL, y.z, k); ky.w = __shfl_sync(BB_FULL, y.w, k);

@@ -1689,7 +1689,9 @@ namespace bb {
 // each), warp 1 = fetch, warp 2 = retire.  Same blob image, chunk pool, order records and trade log as k_deep.
 __global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // The four roles rotate with the wave a CTA belongs to (CTAs go round the 148 SMs of a B200, so the up-to-four CTAs that
+    // share an SM are 148 apart): the four busy chain warps of an SM then sit on four different schedulers, not on one.
+    const u32 lane = threadIdx.x & 31u, warp = ((threadIdx.x >> 5) + blockIdx.x / 148u) & 3u;
     const u32 sb = smem_u32(smem);
     const DeepOff& o = p.dp;
     const u32 ctl = sb + o.ctl;

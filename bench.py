@@ -570,10 +570,11 @@ def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pag
     o1 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * n_rest
     o2 = torch.arange(0, n_envs + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
     if engine == "deep":
-        # deep-book engine (csrc/deep.cuh): one CTA per book; window = every price the stream can rest at (10000 +- 2048,
+        # deep-book engine (csrc/deepw.cuh): one CTA per book; window = every price the stream can rest at (10000 +- 2048,
         # rounded out to 32-level words), 98304 queue chunks of 31 entries per book
         eng_kw = dict(price_window=C5_WINDOW, deep_chunks=C5_CHUNKS)
-        eng_name = "deep-book engine (one CTA per book: fetch / match / retire warps, chunked array queues in HBM, prefix-sum sweeps)"
+        eng_name = ("deep-book engine (one CTA per book: fetch / chain / replay / retire warps — the ladder chain in event order, the queues "
+                    "replayed one lane per price level, trades placed by a warp prefix sum; chunked array queues in HBM)")
     else:
         # Price pages resident in shared memory: as many as let the whole shard stay resident in ONE wave (a book's image is
         # ~0.5 KB per page; 148 SMs x 227 KB).  128-296 books per GPU: all 192 pages (2 books per CTA); 512: ~100 pages.
@@ -619,12 +620,12 @@ def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pag
                        "book (15% cancel, 15% modify, 60% limit within +-32 ticks, 10% market), level-2 record per step, replayed from "
                        "device memory; " + eng_name,
            "value": agg["instructions"] * steps / (agg["elapsed_ms_max"] * 1e-3), "unit": UNIT, "ms_per_step": agg["elapsed_ms_max"] / steps,
-           # (one CTA per book, two resident per SM: up to 296 books run in one wave and the pass time IS a book's time)
-           **({"us_per_event_per_book": 1e3 * k_ms / (n_steps * per_step)} if n_envs <= 296 and engine == "deep" else {}),
+           # (one CTA per book, up to four resident per SM: with at most one book per SM the pass time IS a book's time)
+           **({"us_per_event_per_book": 1e3 * k_ms / (n_steps * per_step)} if n_envs <= 148 and engine == "deep" else {}),
            "env_steps_per_sec": agg["env_steps"] * steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
            "trades_per_pass": agg["trades"], "n_books_total": per_gpu * ctx.world, "l1_checksums": agg["l1_checksums"][:1],
            "roofline": roofline_block(workloads.algorithmic_bytes(stats, obs, n_envs * n_steps * per_step), k_ms,
-                                      "k_deep" if engine == "deep" else "k_apply<REPLAY,PAGED_RES>", profile_traffic("c5_" + engine))}
+                                      "k_deepw" if engine == "deep" else "k_apply<REPLAY,PAGED_RES>", profile_traffic("c5_" + engine))}
     if with_cpu and ctx.rank == 0:
         from oracle import oracle as orc
         orc.build()
@@ -735,7 +736,7 @@ def run_gpu_other(args):
                                    f"{'deep-book engine (one CTA per book)' if deep else 'paged engine'}"},
             "orders_per_pass": stats["instructions"], "trades_per_pass": stats["trades"],
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
-                         "traffic": None, "kernel": "k_deep" if deep else "k_apply", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+                         "traffic": None, "kernel": "k_deepw" if deep else "k_apply", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             "cpu_baseline": {"value": r["instructions"] / r["seconds"], "unit": UNIT, "cores": min(n_books, cores), "kind": "port",
                              "sample": f"the same stream into {min(n_books, cores)} book(s), one per core ({r['seconds']:.2f} s; counts every row incl. no-ops)"}}))
         return 0

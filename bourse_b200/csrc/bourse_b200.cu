@@ -80,7 +80,7 @@ struct bb_handle {
     unsigned char* dp_pool = nullptr;
     u32 dp_chunks = 0;
     bool deep_attr_set = false;
-    int deep_mode = 2;  // 0 = k_deep (event-serial pipeline), 1 = k_deepw with every event on its serial path, 2 = k_deepw
+    bool deep_serial = false;  // developer switch (BOURSE_B200_DEEP=serial): every event through k_deepw's serial path
     // agents
     std::vector<bb_agent_group> groups;
     std::vector<u32> group_asset;  // bb_set_agents_market: asset each group trades (empty: single-asset agents)
@@ -221,8 +221,8 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.dp_chunks = h->dp_chunks;
 }
 
-// shared-memory map of k_deep (deep.cuh) / k_deepw (deepw.cuh, `wide`) for a window of W levels
-DeepOff deep_layout(u32 W, bool wide) {
+// shared-memory map of k_deepw (deep.cuh, deepw.cuh) for a window of W levels
+DeepOff deep_layout(u32 W) {
     DeepOff o{};
     const u32 nw = W / 32;
     o.bm = DP_OFF_BM;
@@ -231,20 +231,16 @@ DeepOff deep_layout(u32 W, bool wide) {
     o.lcnt = o.lvol + 4u * W;
     o.lht = o.lcnt + 4u * W;
     o.image_bytes = align_up(o.lht + 8u * W, 128);
-    o.smem_image = wide ? o.lcnt : o.image_bytes;  // (16-byte aligned: the bulk copy stops exactly where the counts begin)
+    o.smem_image = o.lcnt;  // (16-byte aligned: the bulk copy stops exactly where the counts begin; they stay in the blob)
     u32 off = align_up(o.smem_image, 128);
-    const u32 rb = wide ? DW_RB : DP_RB, rcap = wide ? DW_RCAP : DP_RCAP;
-    o.ctag = off; off += wide ? 0u : 4u * DP_NC;
-    o.cdat = off; off += wide ? DW_SCRATCH : DP_CHUNK_BYTES * DP_NC;  // (k_deepw: its scratch block)
-    o.ev_ins = off; off += 1024u * rb;
-    o.ev_rec = off; off += 1024u * rb;
+    o.scratch = off; off += DW_SCRATCH;
+    o.ev_ins = off; off += 1024u * DW_RB;
+    o.ev_rec = off; off += 1024u * DW_RB;
     o.ev_rf = off; off += 16u;
-    o.cmd = off; off += wide ? 0u : 32u * DP_CCAP;
-    o.ret = off; off += DP_RENT * rcap;
-    o.dirty = off; off += 4u * (wide ? DW_DIRTY : DP_DIRTY);
-    o.swept = off; off += wide ? 0u : 4u * DP_SWEPT;
+    o.ret = off; off += DP_RENT * DW_RCAP;
+    o.dirty = off; off += 4u * DW_DIRTY;
     o.ctl = off; off += 4u * CT_WORDS;
-    o.bar = off; off += 8u * (rb + 1u);
+    o.bar = off; off += 8u * (DW_RB + 1u);
     o.total = align_up(off, 128);
     return o;
 }
@@ -372,13 +368,11 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     if (h->eng == ENG_DEEP) {
         if (mode != MODE_REPLAY || d_out_ids || d_obs_out) return fail(h, BB_EINVAL, "the deep-book engine replays instruction streams only");
         if (!h->deep_attr_set) {
-            CUDA_TRY(h, cudaFuncSetAttribute(k_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
             CUDA_TRY(h, cudaFuncSetAttribute(k_deepw, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
             h->deep_attr_set = true;
         }
-        p.dp_fast = h->deep_mode == 2 ? 1u : 0u;
-        if (h->deep_mode == 0) k_deep<<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
-        else k_deepw<<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
+        p.dp_fast = h->deep_serial ? 0u : 1u;
+        k_deepw<<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
         CUDA_TRY(h, cudaGetLastError());
         h->recorded_host = -1;
         return BB_OK;
@@ -514,9 +508,8 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
         h->eng = ENG_DEEP;
         h->dgeo.d_win_lo = cfg->win_lo; h->dgeo.d_levels = W; h->dgeo.d_live = 0;
         h->dense_lp = h->dense_nwmax = 0;
-        if (const char* m = getenv("BOURSE_B200_DEEP"))  // developer switch: "pipe" | "serial" | "wide" (default)
-            h->deep_mode = !strcmp(m, "pipe") ? 0 : !strcmp(m, "serial") ? 1 : 2;
-        h->dp = deep_layout(W, h->deep_mode != 0);
+        if (const char* m = getenv("BOURSE_B200_DEEP")) h->deep_serial = !strcmp(m, "serial");
+        h->dp = deep_layout(W);
         h->dp_chunks = cfg->deep_chunks;
         if (h->dp.total > 232448u - 1024u) {
             delete h;

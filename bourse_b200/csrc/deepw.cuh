@@ -1,10 +1,10 @@
 // Deep-book engine, batch-parallel book warp (included by kernels.cuh after deep.cuh; kernel k_deepw).
 //
-// Same data structures and reference semantics as deep.cuh (side.rs:36-143, orderbook.rs:429-772): dense tick-indexed level
-// arrays + per-side bitmaps in shared memory, chunked array queues in HBM, fetch warp in front, retire warp behind.  What
-// changes is how the book itself advances.  deep.cuh runs one event at a time on lane 0 of two warps (ladder, queue):
-// ~200 dependent instructions each per event, 1250 cycles per event on a B200 SM (profiles/r02_summary.md) — a single
-// thread of a GPU is a slow CPU.  Here ONE warp owns the book and cuts an event's work in two:
+// Reference semantics: side.rs:36-143, orderbook.rs:429-772.  Data structures (deep.cuh): dense tick-indexed level volumes +
+// per-side bitmaps in shared memory, chunked array queues in HBM, fetch warp in front, retire warp behind.  The first version of
+// this engine ran one event at a time on lane 0 of two warps (ladder, queue): ~200 dependent instructions each per event, 1250
+// cycles per event on a B200 SM (profiles/r02_summary.md) — a single thread of a GPU is a slow CPU.  Here an event's work is
+// cut along its data, and only the true recurrence stays serial:
 //
 //   decode    (32 events, one lane each) everything about an event that does not depend on the book: what kind of
 //             instruction it is, whether the order record the fetch warp prefetched can be trusted (not touched by an event
@@ -1055,7 +1055,6 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
             u32 e = first, rem = 0u, last_t = 0xFFFFFFFFu;  // (rem, last_t, in_place: lane 0's)
             bool in_place = false, late = false;
             for (;;) {
-                const u32 e_from = e;
                 u32 n_out = 0u, last_a = 32u, stop = 0u;  // stop: the mark to wait for (late)
                 if (lane == 0u) {
                     const u32 co = r.scr + SC_COUT;

@@ -1019,11 +1019,8 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Deep-book replay kernel (deep.cuh): one CTA per book; warp 0 = ladder, warp 1 = fetch, warp 2 = retire, warp 3 = queue.
+// Deep-book replay (deep.cuh, deepw.cuh): the fetch warp and the retire warp of k_deepw.
 // Immediate-mode instruction streams (OrderBook API at explicit times, orderbook.rs:411-792), configs C5 / C2.
-#define DT_EXIT 1u
-#define DT_SWEEP 2u
-#define DT_OBS 3u
 // pre-decoded flag bits the fetch warp adds to op_flags (above the public BB_F_* bits)
 #define DPF_MARKET (1u << 16)      // the order takes the market path: BB_F_MARKET, or a limit price equal to the sentinel (N3)
 #define DPF_CAP_ORDERS (1u << 17)  // a NEW row whose id would not fit the order table
@@ -1208,478 +1205,6 @@ __device__ __forceinline__ void dp_retire_warp(const KParams& p, const DeepOff& 
     if (lane == 0u) sts(ctl + CT_RERR, err);
 }
 
-// the queue warp: consumes the ladder warp's commands in order
-__device__ __forceinline__ void dp_queue_warp(const KParams& p, const DeepOff& o, u32 sb, u32 lane, u32 env) {
-    QueReg r;
-    r.lcnt = dp_keep32(sb + o.lcnt);
-    r.lht = dp_keep32(sb + o.lht);
-    r.ctag = dp_keep32(sb + o.ctag);
-    r.cdat = dp_keep32(sb + o.cdat);
-    r.cmd = dp_keep32(sb + o.cmd);
-    r.ret = dp_keep32(sb + o.ret);
-    r.ctl = dp_keep32(sb + o.ctl);
-    r.fs = dp_keep32(sb + DP_OFF_FS);
-    r.n_chunks = p.dp_chunks;
-    r.win_lo = p.geo.d_win_lo;
-    r.chunks = dp_keep64((u64)(p.dp_pool + (size_t)env * p.dp_chunks * DP_CHUNK_BYTES));
-    QueSt s;
-    s.bump = lds(sb + DP_OFF_BUMP);
-    s.n_free = lds(sb + DP_OFF_NFREE);
-    s.err = 0u;
-    s.n_trades = 0u;
-    s.ret_tail = s.ret_pub = 0u;
-    s.ret_room = DP_RCAP;
-    s.cmd_head = 0u;
-    // a sweep handed to the whole warp (lane 0's registers)
-    u32 w_q = 0u, w_opp = 0u, w_take = 0u, w_exh = 0u, w_id = 0u, w_tlo = 0u, w_thi = 0u, w_price = 0u;
-    bool aborted = false;
-    for (;;) {
-        u32 trap = 0u;
-        if (lane == 0u) {
-            trap = DT_EXIT;
-            for (;;) {
-                if (aborted) break;
-                // next command
-                u32 tail = ld_acq(r.ctl + CT_CMD_TAIL);
-                if (tail == s.cmd_head) {
-                    if (s.ret_pub != s.ret_tail) {
-                        s.ret_pub = s.ret_tail;
-                        st_rel(r.ctl + CT_RET_TAIL, s.ret_pub);
-                    }
-                    bool fin = false;
-                    if (!dp_wait(r.ctl, [&] {
-                            fin = ld_acq(r.ctl + CT_FIN_L) != 0u;  // read before the tail: set after the last command
-                            tail = ld_acq(r.ctl + CT_CMD_TAIL);
-                            return tail != s.cmd_head || fin;
-                        }, 7)) {
-                        aborted = true;
-                        break;
-                    }
-                    if (tail == s.cmd_head) break;  // the stream is over
-                }
-                const u32 ea = r.cmd + 32u * (s.cmd_head & (DP_CCAP - 1u));
-                const uint4 a = lds128(ea), b = lds128(ea + 16u);
-                const u32 op = a.x & 0xFFu, side = (a.x >> 8) & 1u, flag = (a.x >> 12) & 0xFu;
-                if (op == QC_SWEEP) {
-                    u32 take = a.w;
-                    const bool exhaust = flag != 0u;
-                    if (qu_sweep_serial(r, s, a.z, side, take, exhaust, a.y, b.x, b.y, b.z, aborted)) {
-                        w_q = a.z; w_opp = side; w_take = take; w_exh = exhaust ? 1u : 0u; w_id = a.y; w_tlo = b.x; w_thi = b.y; w_price = b.z;
-                        trap = DT_SWEEP;  // the rest of this sweep is the warp's
-                        break;
-                    }
-                    if (aborted) break;
-                } else if (op == QC_APPEND || op == QC_END) {
-                    u32 pos = 0u, status = (a.x >> 20) & 7u;
-                    if (op == QC_APPEND) {
-                        pos = qu_append(r, s, a.z, a.y, a.w);
-                        status = ST_ACTIVE;
-                    }
-                    if (!qu_ret_space(r, s, 1u)) { aborted = true; break; }
-                    qu_ret_write(r, s.ret_tail, make_uint4(flag | (side << 8) | (status << 12), a.y, a.w, pos), make_uint4(b.x, b.y, b.z, 0u));
-                    s.ret_tail += 1;
-                } else if (op == QC_REMOVE) {
-                    qu_remove(r, s, b.z, a.z);
-                    if (flag) {  // a cancel (the first half of a replace queues no record write of its own)
-                        if (!qu_ret_space(r, s, 1u)) { aborted = true; break; }
-                        qu_ret_write(r, s.ret_tail, make_uint4(RK_CANCEL | (side << 8), a.y, 0u, 0u), make_uint4(b.x, b.y, 0u, 0u));
-                        s.ret_tail += 1;
-                    }
-                } else if (op == QC_REDUCE) {
-                    qu_chunk_st32(r, a.z >> 5, 8u * (a.z & 31u) + 4u, a.w);
-                    if (!qu_ret_space(r, s, 1u)) { aborted = true; break; }
-                    qu_ret_write(r, s.ret_tail, make_uint4(RK_REDUCE, a.y, a.w, 0u), make_uint4(b.x, b.y, 0u, 0u));
-                    s.ret_tail += 1;
-                }
-                // the command is done
-                s.cmd_head += 1;
-                if (a.x & QCF_LAST) {  // ... and with it its event: record writes first, then the event count
-                    if (s.ret_pub != s.ret_tail) {
-                        s.ret_pub = s.ret_tail;
-                        st_rel(r.ctl + CT_RET_TAIL, s.ret_pub);
-                    }
-                    st_rel(r.ctl + CT_Q_EV, b.w);
-                }
-                st_rel(r.ctl + CT_CMD_DONE, s.cmd_head);
-            }
-        }
-        trap = __shfl_sync(BB_FULL, trap, 0);
-        if (trap == DT_EXIT) break;
-        {   // DT_SWEEP: the warp finishes the sweep lane 0 handed over (a sweep is never the last command of its event)
-            const u32 q = __shfl_sync(BB_FULL, w_q, 0), opp = __shfl_sync(BB_FULL, w_opp, 0), take = __shfl_sync(BB_FULL, w_take, 0);
-            const u32 exh = __shfl_sync(BB_FULL, w_exh, 0), id = __shfl_sync(BB_FULL, w_id, 0);
-            const u32 tlo = __shfl_sync(BB_FULL, w_tlo, 0), thi = __shfl_sync(BB_FULL, w_thi, 0), price = __shfl_sync(BB_FULL, w_price, 0);
-            {
-                DP_T0
-                qu_sweep_warp(r, s, lane, q, opp, take, exh != 0u, id, tlo, thi, price);
-                if (lane == 0u) { DP_ADD(9) }
-            }
-            if (lane == 0u) {
-                if (ld_acq(r.ctl + CT_ABORT)) aborted = true;
-                s.cmd_head += 1;
-                st_rel(r.ctl + CT_CMD_DONE, s.cmd_head);
-            }
-        }
-    }
-    if (lane == 0u) {
-        st_rel(r.ctl + CT_RET_TAIL, s.ret_tail);
-        st_rel(r.ctl + CT_FIN, 1u);
-        sts(sb + DP_OFF_BUMP, s.bump);
-        sts(sb + DP_OFF_NFREE, s.n_free);
-        sts(r.ctl + CT_QERR, s.err);
-        sts(r.ctl + CT_QNTR, s.n_trades);
-        if (aborted) st_rel(r.ctl + CT_ABORT, 1u);
-    }
-}
-
-__global__ void __launch_bounds__(128, 2) k_deep(const __grid_constant__ KParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const u32 sb = smem_u32(smem);
-    const DeepOff& o = p.dp;
-    const u32 ctl = sb + o.ctl;
-    const u32 env = blockIdx.x;
-    if (env >= p.n_envs) return;
-    const u64 oh = (u64)(p.ord + (size_t)env * p.geo.max_orders);
-    const u64 tr = (u64)(p.tr + (size_t)env * p.geo.max_trades);
-    const u64 off = p.offsets[env];
-    const u32 n = (u32)(p.offsets[env + 1] - off);
-    const bb_instr* ins = p.instrs + off;
-    // ---- set-up: barriers, control words, cache tags, filters; then the book image (one bulk copy)
-    if (threadIdx.x == 0) {
-        for (u32 i = 0; i <= DP_RB; ++i) mbar_init_a(sb + o.bar + 8u * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (u32 i = threadIdx.x; i < CT_WORDS; i += blockDim.x) sts(ctl + 4u * i, 0u);
-    for (u32 i = threadIdx.x; i < DP_NC; i += blockDim.x) sts(sb + o.ctag + 4u * i, BB_NIL);
-    for (u32 i = threadIdx.x; i < DP_DIRTY; i += blockDim.x) sts(sb + o.dirty + 4u * i, 0u);
-    for (u32 i = threadIdx.x; i < DP_SWEPT; i += blockDim.x) sts(sb + o.swept + 4u * i, 0u);
-    fence_proxy_async();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx_a(sb + o.bar, o.image_bytes);
-        bulk_g2s_a(sb, p.blobs + (size_t)env * p.blob_stride, o.image_bytes, sb + o.bar);
-        if (!mbar_wait_a(sb + o.bar, 0u)) st_rel(ctl + CT_ABORT, 1u);
-    }
-    __syncthreads();
-    const u32 n_tr0 = min((u32)lds64(sb + HDR_NTRADES_TOTAL), p.geo.max_trades);
-#ifdef DP_PROF
-    const long long dp_k0 = clock64();
-#endif
-
-    if (warp == 1u) {
-        dp_fetch_warp<DP_RB>(p, o, sb, lane, ins, n, oh, lds(sb + HDR_NORDERS));
-    } else if (warp == 2u) {
-        dp_retire_warp<DP_RCAP, true>(p, o, sb, lane, oh, tr, n_tr0);
-    } else if (warp == 3u) {
-        dp_queue_warp(p, o, sb, lane, env);
-    } else {
-        // ---- ladder warp ---------------------------------------------------------------------------------------
-        LadReg r;
-        r.lvol = dp_keep32(sb + o.lvol);
-        r.lcnt = dp_keep32(sb + o.lcnt);
-        r.bma = dp_keep32(sb + o.bm);
-        r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
-        r.sma = dp_keep32(sb + o.sm);
-        r.smb = dp_keep32(sb + o.sm + 4u * DP_NS);
-        r.cmd = dp_keep32(sb + o.cmd);
-        r.dirty = dp_keep32(sb + o.dirty);
-        r.swept = dp_keep32(sb + o.swept);
-        r.ctl = dp_keep32(ctl);
-        r.win_lo = p.geo.d_win_lo; r.W = p.geo.d_levels; r.max_orders = p.geo.max_orders;
-        r.oh = dp_keep64(oh);
-        const u32 ev_ins = dp_keep32(sb + o.ev_ins), ev_rec = dp_keep32(sb + o.ev_rec);
-        LadSt s;
-        s.t = lds64(sb + HDR_T);
-        s.max_key_time = lds64(sb + HDR_MAXKT);
-        s.n_orders = lds(sb + HDR_NORDERS);
-        s.trade_vol = lds(sb + HDR_TRADEVOL);
-        s.vol_ask = lds(sb + HDR_SIDEVOL);
-        s.vol_bid = lds(sb + HDR_SIDEVOL + 4u);
-        s.bq_ask = lds(sb + HDR_BESTQ);
-        s.bq_bid = lds(sb + HDR_BESTQ + 4u);
-        s.flags = (lds(sb + HDR_TRADING) ? FL_TRADING : 0u) | (lds(sb + HDR_HASBEST) ? FL_HAS_ASK : 0u) |
-                  (lds(sb + HDR_HASBEST + 4u) ? FL_HAS_BID : 0u);
-        s.err = 0u;
-        s.d_instr = s.d_applied = 0u;
-        s.zv = lds(sb + HDR_FREETOP);
-        s.cmd_tail = s.cmd_pub = 0u;
-        s.cmd_room = DP_CCAP;
-        const u32 n_orders0 = s.n_orders, trade_vol0 = s.trade_vol;
-        u32 ev_i = 0u, rf = 0u;
-        bool aborted = false;
-        for (;;) {
-            u32 trap = 0u;
-            if (lane == 0u) {
-                trap = DT_EXIT;
-                while (ev_i < n && !aborted) {
-                    // ---- next event
-                    const u32 bslot = (ev_i >> 5) & (DP_RB - 1u);
-                    if ((ev_i & 31u) == 0u) {
-                        const u32 b = ev_i >> 5;
-                        if (ld_acq(r.ctl + CT_EV_READY) <= b && !dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_READY) > b; }, 6)) {
-                            aborted = true;
-                            break;
-                        }
-                        rf = lds(sb + o.ev_rf + 4u * bslot);
-                    }
-                    const u32 eo = 1024u * bslot + 32u * (ev_i & 31u);
-                    const uint4 x = lds128(ev_ins + eo), y = lds128(ev_ins + eo + 16u);
-                    ev_i += 1;  // (from here on: the number of events completed once this one is)
-                    s.t = ((u64)x.y << 32) | x.x;
-                    const u32 op = x.z & BB_OP_MASK;
-                    const u32 emit = x.z & BB_F_EMIT;
-                    // the order that goes through matching (NEW, or the second half of a replace)
-                    u32 kind = 0u, side = 0u, price = 0u, vol = 0u, id = 0u;
-                    bool market = false;
-                    if (op == BB_OP_NEW) {  // (id, sentinel price and the market flag were settled by the fetch warp)
-                        s.d_instr += 1;
-                        if (x.z & DPF_CAP_ORDERS) {
-                            s.err |= ERR_CAP_ORDERS;
-                        } else {
-                            id = x.w;
-                            s.n_orders = id + 1u;
-                            kind = RK_NEW;
-                            side = (x.z >> 8) & 1u;  // BB_F_BID
-                            price = y.x;
-                            market = (x.z & DPF_MARKET) != 0u;
-                            vol = y.y;
-                        }
-                    } else if (op == BB_OP_CANCEL || op == BB_OP_MODIFY) {
-                        s.d_instr += 1;
-                        id = x.w;
-                        if (id >= s.n_orders || id >= r.max_orders) {
-                            s.err |= ERR_BAD_ID;  // the reference panics (orderbook.rs:642, :749)
-                        } else {
-                            // The order's record as the fetch warp saw it.  Usable iff every write to it was in HBM by
-                            // then: no event naming the order, and no sweep of its price level, was still in the pipeline.
-                            uint4 a = lds128(ev_rec + eo), c = lds128(ev_rec + eo + 16u);
-                            const u32 dv = lds(r.dirty + 4u * (id & (DP_DIRTY - 1u)));
-                            const u32 sv = lds(r.swept + 4u * ((a.x - r.win_lo) & (DP_SWEPT - 1u)));
-                            if (max(dv, sv) > rf) {  // doubtful: let the pipeline drain up to that event, read again
-                                ld_publish(r, s);
-                                const u32 need = dv > rf ? dv : 0u;   // (a stale price makes `sv` meaningless: settle `dv` first)
-                                if (need && !dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_RETIRED) >= need; }, 13)) { aborted = true; break; }
-                                a = ldg128_cg(r.oh + (u64)id * ORD_STRIDE);
-                                const u32 sv2 = lds(r.swept + 4u * ((a.x - r.win_lo) & (DP_SWEPT - 1u)));
-                                if (sv2 > rf) {
-                                    if (!dp_wait(r.ctl, [&] { return ld_acq(r.ctl + CT_EV_RETIRED) >= sv2; }, 14)) { aborted = true; break; }
-                                    a = ldg128_cg(r.oh + (u64)id * ORD_STRIDE);
-                                }
-                                c = ldg128_cg(r.oh + (u64)id * ORD_STRIDE + 16u);
-                            }
-                            if ((c.z & META_STATUS_MASK) == ST_ACTIVE) {
-                                const u32 oside = (c.z & META_BID) ? 1u : 0u;
-                                const bool has_p = (x.z & BB_F_HAS_PRICE) != 0u, has_v = (x.z & BB_F_HAS_VOL) != 0u;
-                                const u32 q = a.x - r.win_lo;
-                                const bool reduce = op == BB_OP_MODIFY && !has_p && has_v && y.y < a.y;
-                                if (op == BB_OP_MODIFY && !has_p && !has_v) {
-                                } else if (q >= r.W) {  // never rested (flagged when it was placed)
-                                } else if (reduce) {  // reduce in place: priority kept (orderbook.rs:755-757)
-                                    const u32 la = r.lvol + 4u * q;
-                                    sts(la, lds(la) - (a.y - y.y));
-                                    ld_add_side(s, oside, y.y - a.y);
-                                    if (y.y == 0u) s.zv = 1u;
-                                    if (!ld_cmd(r, s, make_uint4(QC_REDUCE | QCF_LAST, id, a.z, y.y), make_uint4(x.x, x.y, 0u, ev_i))) { aborted = true; break; }
-                                    sts(r.dirty + 4u * (id & (DP_DIRTY - 1u)), ev_i);
-                                    s.d_applied += 1;
-                                } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
-                                    const bool cancel = op == BB_OP_CANCEL;
-                                    const u32 la = r.lvol + 4u * q;
-                                    const u32 nv = lds(la) - a.y;
-                                    sts(la, nv);
-                                    ld_add_side(s, oside, 0u - a.y);
-                                    if (!ld_cmd(r, s, make_uint4(QC_REMOVE | (oside << 8) | (cancel ? (1u << 12) | QCF_LAST : 0u), id, a.z, 0u),
-                                                make_uint4(x.x, x.y, q, ev_i))) { aborted = true; break; }
-                                    if (nv == 0u && ld_emptied(r, s, q, aborted)) ld_level_gone(r, s, oside, q);
-                                    if (aborted) break;
-                                    sts(r.dirty + 4u * (id & (DP_DIRTY - 1u)), ev_i);
-                                    if (cancel) {
-                                        s.d_applied += 1;
-                                    } else {  // never a market order (N4)
-                                        kind = RK_REPLACE;
-                                        side = oside;
-                                        price = has_p ? y.x : a.x;
-                                        vol = has_v ? y.y : a.y;
-                                    }
-                                }
-                            }
-                        }
-                    } else if (op == BB_OP_SET_TRADING) {
-                        s.flags = y.y ? (s.flags | FL_TRADING) : (s.flags & ~FL_TRADING);
-                    } else if (op == BB_OP_RESTORE) {
-                        s.err |= ERR_ROW_OP;  // bb_load_book is not available on the deep engine
-                    }
-                    if (kind) {
-                        // ---- match_bid / match_ask (orderbook.rs:429-487) on the ladder: how much each crossed level gives
-                        u32 rem = vol;
-                        const u32 opp = side ^ 1u;
-                        if (s.flags & FL_TRADING) {
-                            while (rem > 0u && ld_has_best(s, opp)) {
-                                const u32 bq = ld_best_q(s, opp);
-                                const u32 bprice = r.win_lo + bq;
-                                if (side ? (price < bprice) : (price > bprice)) break;
-                                const u32 la = r.lvol + 4u * bq;
-                                const u32 lv = lds(la);
-                                const u32 take = min(rem, lv), nv = lv - take;
-                                rem -= take;
-                                const bool exhaust = rem > 0u;  // the aggressor goes on: it takes every order left on this level
-                                sts(la, nv);
-                                s.trade_vol += take;
-                                ld_add_side(s, opp, 0u - take);
-                                sts(r.swept + 4u * (bq & (DP_SWEPT - 1u)), ev_i);
-                                if (!ld_cmd(r, s, make_uint4(QC_SWEEP | (opp << 8) | (exhaust ? 1u << 12 : 0u), id, bq, take), make_uint4(x.x, x.y, bprice, ev_i))) {
-                                    aborted = true;
-                                    break;
-                                }
-                                if (nv == 0u && (exhaust || ld_emptied(r, s, bq, aborted))) ld_level_gone(r, s, opp, bq);
-                                if (aborted) break;
-                            }
-                            if (aborted) break;
-                        }
-                        // ---- rest or finish (orderbook.rs:495-531, 699-722)
-                        const bool filled = vol != 0u && rem == 0u;
-                        const u32 status = filled ? ST_FILLED : market ? ((s.flags & FL_TRADING) ? ST_CANCELLED : ST_REJECTED) : ST_ACTIVE;
-                        u32 cmd = QC_END;
-                        if (status == ST_ACTIVE) {  // insert_order (side.rs:54-66), the ladder half
-                            const u32 q = price - r.win_lo;
-                            if (q >= r.W) {
-                                s.err |= ERR_CAP_PAGES;
-                            } else {
-                                const u32 ba = ld_bm(r, side, q >> 5), bit = 1u << (q & 31u);
-                                const u32 la = r.lvol + 4u * q;
-                                const u32 bw = lds(ba);
-                                const u32 lv = lds(la);
-                                bool ok = true;
-                                if (!(bw & bit)) {
-                                    // the level array is shared by the two sides.  While trading is enabled an order only rests
-                                    // where the other side is empty, with one exception the reference allows: a ZERO-volume
-                                    // order never matches (orderbook.rs:436) and rests wherever its price says
-                                    if (lds(ld_bm(r, opp, q >> 5)) & bit) {
-                                        s.err |= ERR_LOCKED;
-                                        ok = false;
-                                    } else {
-                                        sts(la, rem);
-                                        sts(ba, bw | bit);
-                                        if (bw == 0u) {
-                                            const u32 sa = ld_sm(r, side, q >> 10);
-                                            sts(sa, lds(sa) | (1u << ((q >> 5) & 31u)));
-                                        }
-                                        const bool better = !ld_has_best(s, side) || (side ? q > s.bq_bid : q < s.bq_ask);
-                                        if (better) {
-                                            if (side) s.bq_bid = q; else s.bq_ask = q;
-                                            s.flags |= FL_HAS_ASK << side;
-                                        }
-                                    }
-                                } else {
-                                    if (s.t <= s.max_key_time) s.err |= ERR_TIME_ORDER;
-                                    sts(la, lv + rem);
-                                }
-                                if (ok) {
-                                    ld_add_side(s, side, rem);
-                                    if (s.t > s.max_key_time) s.max_key_time = s.t;
-                                    if (rem == 0u) s.zv = 1u;
-                                    cmd = QC_APPEND;
-                                }
-                            }
-                        }
-                        // QC_APPEND: level index in a.z; QC_END: the order's record gets its final status (an order that
-                        // could not rest — flagged above — keeps status Active in its record and is not on the book)
-                        const u32 q = price - r.win_lo;
-                        if (!ld_cmd(r, s, make_uint4(cmd | (side << 8) | (kind << 12) | QCF_LAST | (status << 20), id, cmd == QC_APPEND ? q : 0u, rem),
-                                    make_uint4(x.x, x.y, price, ev_i))) { aborted = true; break; }
-                        sts(r.dirty + 4u * (id & (DP_DIRTY - 1u)), ev_i);
-                        s.d_applied += 1;
-                    }
-                    // ---- the event is done: commands out, finished batches back to the fetch warp
-                    ld_publish(r, s);
-                    if ((ev_i & 31u) == 0u || ev_i == n) st_rel(r.ctl + CT_EV_CONSUMED, (ev_i + 31u) >> 5);
-                    if (emit) {
-                        if (!ld_sync_queue(r, s)) aborted = true;  // the record needs the queue warp's order counts
-                        trap = DT_OBS;
-                        break;
-                    }
-                }
-            }
-            trap = __shfl_sync(BB_FULL, trap, 0);
-            if (trap == DT_EXIT) break;
-            {   // Level2DataRecords::append_record (data.rs:44-56) for a row flagged BB_F_EMIT
-                const u32 bid_has = __shfl_sync(BB_FULL, s.flags & FL_HAS_BID, 0), ask_has = __shfl_sync(BB_FULL, s.flags & FL_HAS_ASK, 0);
-                const u32 bid = bid_has ? r.win_lo + __shfl_sync(BB_FULL, s.bq_bid, 0) : 0u;
-                const u32 ask = ask_has ? r.win_lo + __shfl_sync(BB_FULL, s.bq_ask, 0) : 0xFFFFFFFFu;
-                u32 w0, w1;
-                dp_obs(r, p.geo.tick, lane, __shfl_sync(BB_FULL, s.trade_vol, 0), bid, ask, __shfl_sync(BB_FULL, s.vol_ask, 0),
-                       __shfl_sync(BB_FULL, s.vol_bid, 0), &w0, &w1);
-                // (a level-1 record is the first 9 words of the level-2 one: words 5..8 are the touch level of each side)
-                const u32 nrec = lds(sb + HDR_NSTEPS);
-                __syncwarp();
-                if (nrec < p.max_steps) {
-                    const u64 dst = (u64)(p.hist + (size_t)env * p.hist_env_stride + (size_t)nrec * p.obs_words);
-                    if (lane < p.obs_words) stg32(dst + 4u * lane, w0);
-                    if (lane + 32u < p.obs_words) stg32(dst + 4u * (lane + 32u), w1);
-                    if (lane == 0u) sts(sb + HDR_NSTEPS, nrec + 1u);
-                } else if (lane == 0u) {
-                    s.err |= ERR_CAP_STEPS;
-                }
-                __syncwarp();
-            }
-        }
-        // ---- the ladder's part of the header goes back into the image; the queue warp drains what is left and exits on FIN_L
-        if (lane == 0u) {
-            ld_publish(r, s);
-            st_rel(r.ctl + CT_FIN_L, 1u);
-            sts64(sb + HDR_T, s.t);
-            sts64(sb + HDR_MAXKT, s.max_key_time);
-            sts64(sb + HDR_NCREATED, lds64(sb + HDR_NCREATED) + (s.n_orders - n_orders0));
-            sts(sb + HDR_NORDERS, s.n_orders);
-            sts(sb + HDR_TRADEVOL, s.trade_vol);
-            sts(sb + HDR_SIDEVOL, s.vol_ask);
-            sts(sb + HDR_SIDEVOL + 4u, s.vol_bid);
-            sts(sb + HDR_BESTQ, s.bq_ask);
-            sts(sb + HDR_BESTQ + 4u, s.bq_bid);
-            sts(sb + HDR_TRADING, (s.flags & FL_TRADING) ? 1u : 0u);
-            sts(sb + HDR_HASBEST, (s.flags & FL_HAS_ASK) ? 1u : 0u);
-            sts(sb + HDR_HASBEST + 4u, (s.flags & FL_HAS_BID) ? 1u : 0u);
-            sts(sb + HDR_FREETOP, s.zv);
-            sts64(sb + HDR_NINSTR, lds64(sb + HDR_NINSTR) + s.d_instr);
-            // traded volume: trade_vol is never reset in replay mode; transitions: see below (needs the queue warp's fill count)
-            sts64(sb + HDR_VOLUME, lds64(sb + HDR_VOLUME) + (u32)(s.trade_vol - trade_vol0));
-            sts64(sb + HDR_NTRANS, lds64(sb + HDR_NTRANS) + s.d_applied);
-            sts(ctl + CT_LERR, s.err);
-            // the other warps may still be waiting for each other when the ladder warp gave up early
-            if (aborted) st_rel(ctl + CT_ABORT, 1u);
-        }
-    }
-    __syncthreads();
-#ifdef DP_PROF
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const char* nm[16] = {"-", "F:wait_consumed", "F:tma", "F:cpasync+fence", "L:cmd_room", "L:sync_queue", "L:wait_ev", "Q:wait_cmd",
-                              "Q:ret_room", "Q:warp_sweep", "R:wait", "R:fence", "R:entries", "L:doubt_dirty", "L:doubt_swept", "-"};
-        printf("k_deep prof: n=%u cycles=%lld\n", n, clock64() - dp_k0);
-        for (int i = 1; i < 15; ++i) {
-            printf("  %-16s cycles %12llu  count %10llu\n", nm[i], g_dp_prof[i], g_dp_prof[32 + i]);
-            g_dp_prof[i] = 0; g_dp_prof[32 + i] = 0;
-        }
-    }
-#endif
-    if (threadIdx.x == 0) {
-        // the trade counters: the queue warp made the fills
-        const u32 fills = lds(ctl + CT_QNTR);
-        const u64 tt = lds64(sb + HDR_NTRADES_TOTAL) + fills;
-        sts64(sb + HDR_NTRADES_TOTAL, tt);
-        sts(sb + HDR_NTRADES, (u32)min(tt, (u64)p.geo.max_trades));
-        sts64(sb + HDR_NTRANS, lds64(sb + HDR_NTRANS) + fills);  // transitions: one per fill and one per applied event
-        u32 err = lds(ctl + CT_RERR) | lds(ctl + CT_QERR) | lds(ctl + CT_LERR);
-        if (ld_acq(ctl + CT_ABORT)) err |= 0x80000000u;
-        sts(sb + HDR_ERR, lds(sb + HDR_ERR) | (err & 0x7FFFFFFFu));
-        if (err) atomicOr(p.err_flag, err);
-        fence_proxy_async();
-        bulk_s2g_a(p.blobs + (size_t)env * p.blob_stride, sb, o.image_bytes);
-        bulk_commit();
-        bulk_wait_all<0>();
-    }
-}
-
 }  // namespace bb
 #include "deepw.cuh"
 namespace bb {
@@ -1709,7 +1234,7 @@ __global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParam
     }
     for (u32 i = threadIdx.x; i < CT_WORDS; i += blockDim.x) sts(ctl + 4u * i, 0u);
     for (u32 i = threadIdx.x; i < DW_DIRTY; i += blockDim.x) sts(sb + o.dirty + 4u * i, 0u);
-    for (u32 i = threadIdx.x; i < DW_SWEPT; i += blockDim.x) sts(sb + o.cdat + SC_SWEPT + 4u * i, 0u);
+    for (u32 i = threadIdx.x; i < DW_SWEPT; i += blockDim.x) sts(sb + o.scratch + SC_SWEPT + 4u * i, 0u);
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1731,7 +1256,7 @@ __global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParam
     r.bmb = dp_keep32(sb + o.bm + 4u * (p.geo.d_levels >> 5));
     r.sma = dp_keep32(sb + o.sm);
     r.smb = dp_keep32(sb + o.sm + 4u * DP_NS);
-    r.scr = dp_keep32(sb + o.cdat);
+    r.scr = dp_keep32(sb + o.scratch);
     r.ret = dp_keep32(sb + o.ret);
     r.dirty = dp_keep32(sb + o.dirty);
     r.ctl = dp_keep32(ctl);

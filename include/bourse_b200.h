@@ -95,10 +95,11 @@ typedef struct {
      * multiple of assets; market m shuffles with Xoroshiro128**(seed + env_id_base / assets + m).  0 or 1 => every
      * book is its own Env.  In-kernel agents on a multi-asset handle are defined with bb_set_agents_market. */
     uint32_t assets;
-    /* Deep-book engine (csrc/deep.cuh) for books with up to millions of resting orders, replayed instruction streams
-     * (bb_replay / bb_replay_device; BASELINE config C5): one CTA per book — a fetch warp that prefetches the records
-     * cancels / modifies name, a match warp working out of shared memory, a retire warp that streams the order-record and
-     * trade-log writes out — with array (chunked) price-time queues in HBM swept by a warp prefix sum.  Selected when
+    /* Deep-book engine (csrc/deep.cuh, csrc/deepw.cuh) for books with up to millions of resting orders, replayed instruction
+     * streams (bb_replay / bb_replay_device; BASELINE config C5): one CTA per book — a fetch warp that prefetches the records
+     * cancels / modifies name, a chain warp that keeps the price ladder (shared memory) in event order and writes per-level
+     * micro-ops, a replay warp that applies them to the array (chunked) price-time queues in HBM one lane per price level and
+     * places the trades with a warp prefix sum, a retire warp that streams the order-record updates out.  Selected when
      * deep_chunks > 0, together with the window fields above: win_levels <= 8192 price levels starting at win_lo,
      * price_granule == 1; deep_chunks = 256-byte queue chunks per book (31 entries each; one per resting order in the
      * worst case, ~ resting orders / 31 + win_levels + entries appended during a launch / 31 in practice).  Preconditions

@@ -625,7 +625,7 @@ def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pag
            "env_steps_per_sec": agg["env_steps"] * steps / (agg["elapsed_ms_max"] * 1e-3), "orders_per_pass": agg["instructions"],
            "trades_per_pass": agg["trades"], "n_books_total": per_gpu * ctx.world, "l1_checksums": agg["l1_checksums"][:1],
            "roofline": roofline_block(workloads.algorithmic_bytes(stats, obs, n_envs * n_steps * per_step), k_ms,
-                                      "k_deepw" if engine == "deep" else "k_apply<REPLAY,PAGED_RES>", profile_traffic("c5_" + engine))}
+                                      "k_deepw" if engine == "deep" else "k_apply<REPLAY,PAGED_RES>", profile_traffic("c5_" + engine, per_book=n_envs))}
     if with_cpu and ctx.rank == 0:
         from oracle import oracle as orc
         orc.build()
@@ -641,12 +641,14 @@ def measure_c5(ctx: Ctx, per_gpu: int, steps: int, warmup: int, engine: str, pag
     return out
 
 
-def profile_traffic(key: str):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full` capture per kernel, committed
-    under profiles/): ncu cannot run inside a timed bench, so the figure comes from profiles/kernel_traffic.json."""
+def profile_traffic(key: str, per_book: int = 0):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one ncu capture per kernel, committed under
+    profiles/): ncu cannot run inside a timed bench, so the figure comes from profiles/kernel_traffic.json.  per_book: the
+    launch's book count when it may differ from the profiled one (books are independent: the traffic scales with them)."""
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     try:
-        return json.load(open(tp))[key]["dram_bytes_per_launch"]
+        e = json.load(open(tp))[key]
+        return e["dram_bytes_per_book"] * per_book if per_book else e["dram_bytes_per_launch"]
     except Exception:
         return None
 

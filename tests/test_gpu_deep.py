@@ -204,3 +204,50 @@ def test_recently_written_orders_are_not_read_stale(core, oracle):
     env.replay(s)
     assert not env.env_errors().any()
     compare_book(env, 0, ob, env.history(0), obs_cpu)
+
+
+def test_one_order_sweeping_more_levels_than_the_chain_list_holds(core, oracle):
+    """An aggressive order whose volume the fast path takes (<= 192) but which crosses ~150 one-lot levels: the chain's output
+    list fills up in the middle of the sweep, is flushed and the sweep goes on (deepw.cuh, `in_place`); the same for a market
+    order, for a modify that crosses, and with cancels of the levels' orders in between."""
+    rows, t = [], 0
+    def add(of, oid, price, vol):
+        nonlocal t
+        t += 1
+        rows.append((t, of, oid, price, vol))
+    for rep in range(3):
+        base = len([r for r in rows if (r[1] & 0xFF) == abi.OP_NEW])
+        for k in range(150):
+            add(abi.OP_NEW, 0, 5001 + k, 1)                      # asks, one lot per level
+        for k in range(150):
+            add(abi.OP_NEW | abi.F_BID, 0, 4999 - k, 1)          # bids
+        for k in range(0, 150, 7):
+            add(abi.OP_CANCEL, base + k, 0, 0)                   # holes in the ask ladder
+        add(abi.OP_NEW | abi.F_BID, 0, 5150, 140)                # sweeps ~128 ask levels, fills completely or rests
+        add(abi.OP_NEW | abi.F_MARKET, 0, 0, 150)                # market sell through the bid ladder
+        add(abi.OP_NEW | abi.F_BID, 0, 4000, 30)                 # a deep resting bid ...
+        add(abi.OP_MODIFY | abi.F_HAS_PRICE | abi.F_HAS_VOL, len([r for r in rows if (r[1] & 0xFF) == abi.OP_NEW]) - 1, 5150, 100)  # ... re-priced through what is left
+        add(abi.OP_NEW | abi.F_MARKET | abi.F_BID, 0, 0, 190)    # and a market buy that exhausts the side
+    s = np.zeros(len(rows), dtype=abi.INSTR_DTYPE)
+    for i, (tt, of, oid, price, vol) in enumerate(rows):
+        s[i] = (tt, of | (abi.F_EMIT if i % 97 == 96 else 0), oid, price, vol, i % 5, 0)
+    ob = oracle.OrderBook(0, 1)
+    obs_cpu = ob.replay(s, obs_cap=len(s))
+    env = deep_env(core, 1, (3968, 5184), len(s))
+    env.replay(s)
+    assert not env.env_errors().any()
+    compare_book(env, 0, ob, env.history(0), obs_cpu)
+    tr = ob.trades_arrays()
+    assert np.bincount(tr["active"].astype(np.int64)).max() > 100   # one aggressor, more than a hundred one-lot levels
+
+
+def test_chunk_pool_exhaustion_is_flagged(core):
+    """Fewer queue chunks than the stream needs: BB_ERR_CAP_PAGES, never a silent difference or an out-of-bounds access."""
+    n = 4000
+    s = np.zeros(n, dtype=abi.INSTR_DTYPE)
+    for i in range(n):
+        s[i] = (i + 1, abi.OP_NEW | abi.F_BID, 0, 4000 + (i % 64), 3, 0, 0)   # 64 levels x 62 orders: 2 chunks a level, plus one at birth
+    env = deep_env(core, 1, (3968, 4096), n, chunks=40)
+    with pytest.raises(MemoryError):
+        env.replay(s)
+    assert int(env.env_errors()[0]) & 0x04

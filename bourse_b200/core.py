@@ -53,9 +53,10 @@ class BatchedEnv:
     fastest for shallow books whose resting prices stay in [lo, hi) with at most `live_cap` (default 128, max 254)
     resting orders per book; leaving those limits flags an env error rather than producing different results.
 
-    `deep_chunks=N` (with `price_window`, up to 8192 levels) selects the deep-book engine: one CTA per book with fetch /
-    match / retire warps and chunked array queues in HBM (N 256-byte chunks of 31 queue entries per book) — for books with
-    ~10^6 resting orders driven by replayed streams (`replay`, `replay_device`); Env mode and in-kernel agents raise.
+    `deep_chunks=N` (with `price_window`, up to 8192 levels) selects the deep-book engine: one CTA per book (fetch / chain /
+    replay / retire warps, csrc/deepw.cuh) and chunked array queues in HBM (N 256-byte chunks of 31 queue entries per book)
+    — for books with ~10^6 resting orders driven by replayed streams (`replay`, `replay_device`); Env mode and in-kernel
+    agents raise.
 
     `assets=A` (> 1) groups consecutive books into multi-asset markets with MarketEnv semantics
     (crates/step_sim/src/market_env.rs:108-121); see `bourse_b200.market`."""
@@ -507,54 +508,113 @@ class _StepEnvBase:
         kw.setdefault("pages_total", 256)
         self._env = BatchedEnv(1, seed, start_time, tick_size, step_size, trading, obs_words=abi.OBS_L2,
                                max_orders=max_orders, max_trades=max_trades, max_steps=max_steps, max_queue=max_queue, **kw)
-        # single-row submissions (the per-agent calls of the reference's Python agents) go through preallocated
-        # one-element columns: wrapping eight fresh numpy arrays per call cost more than the call itself
-        self._row = {k: np.zeros(1, dt) for k, dt in (("action", np.uint32), ("side", np.uint8), ("vol", np.uint32), ("trader", np.uint32),
-                                                       ("price", np.uint32), ("order_id", np.uint64), ("flags", np.uint32), ("out", np.uint64))}
-        self._row_ptr = {k: abi.ptr(v) for k, v in self._row.items()}
-        self._done = C.c_uint64()
+        # Single-row submissions (the per-agent calls of the reference's Python agents: Env::place_order / cancel_order /
+        # modify_order, env.rs:173-219) only QUEUE a transaction until the next step, and the id a new order gets is the next
+        # one in sequence (orderbook.rs:356-396).  They are therefore collected here — ids handed out from a host counter, the
+        # tick check of create_order done at the call so that its ValueError is raised where the reference raises it — and
+        # reach the library as ONE bb_submit per step (or before anything that reads the book's tables): a ctypes call per
+        # order cost more than everything else in examples/random_trades.py.
+        self._pend: typing.List[tuple] = []
+        self._pend_new = 0   # new orders among them
+        # host copy of the order table's status column: [0, _status_n) known, everything below _first_live final
+        self._status, self._status_n, self._first_live, self._status_stale = np.zeros(1024, np.uint8), 0, 0, False
+        self._tick = tick_size
+        self._next_id = 0    # the id the next new order gets (None: unknown, ask the library)
         self._n_issued = 0   # upper bound of the order ids handed out (exact unless a submission raised)
 
-    def _submit1(self, action, side=0, vol=0, trader=0, price=0, order_id=0, flags=abi.F_HAS_PRICE | abi.F_HAS_VOL) -> int:
-        r, p, e = self._row, self._row_ptr, self._env
-        if action == abi.ACT_NEW:
-            self._ensure_orders(1)
-        r["action"][0], r["side"][0], r["vol"][0], r["trader"][0] = action, side, vol, trader
-        r["price"][0], r["order_id"][0], r["flags"][0] = price, order_id, flags
-        e._ck(e._lib.bb_submit(e._h, 1, None, p["action"], p["side"], p["vol"], p["trader"], p["price"], p["order_id"], p["flags"],
-                               p["out"], C.byref(self._done)))
-        return int(r["out"][0])
+    def _sync_ids(self):
+        if self._next_id is None:
+            self._next_id = self._env.n_orders(0)
 
-    def enable_trading(self): self._env.set_trading(True, 0)
-    def disable_trading(self): self._env.set_trading(False, 0)
+    def _submit1(self, action, side=0, vol=0, trader=0, price=0, order_id=0, flags=abi.F_HAS_PRICE | abi.F_HAS_VOL) -> int:
+        oid = abi.NO_ID
+        if action == abi.ACT_NEW:
+            if not (flags & abi.F_MARKET) and price % self._tick:   # create_order's tick check, orderbook.rs:367-383
+                raise ValueError(f"Price {price} was not a multiple of tick-size {self._tick}")
+            self._sync_ids()
+            self._ensure_orders(1)
+            oid = self._next_id
+            self._next_id += 1
+            self._pend_new += 1
+        self._pend.append((action, side, vol, trader, price, order_id, flags))
+        return oid
+
+    def _flush(self):
+        """Hand the collected transactions to the library (in submission order)."""
+        if not self._pend:
+            return
+        a = np.array(self._pend, dtype=np.uint64)
+        self._pend, self._pend_new = [], 0
+        try:
+            out = self._env.submit(a[:, 0].astype(np.uint32), a[:, 1].astype(np.uint8), a[:, 2].astype(np.uint32), a[:, 3].astype(np.uint32),
+                                   a[:, 4].astype(np.uint32), a[:, 5], flags=a[:, 6].astype(np.uint32))
+        except Exception:
+            self._next_id = None   # (whatever was accepted before the failing row keeps its id)
+            raise
+        new = out[a[:, 0] == abi.ACT_NEW]
+        if len(new) and int(new[-1]) + 1 != self._next_id:   # ids are handed out in sequence: cannot happen
+            raise RuntimeError("order ids out of step with the library")
+
+    def enable_trading(self): self._flush(); self._env.set_trading(True, 0)
+    def disable_trading(self): self._flush(); self._env.set_trading(False, 0)
     # The reference's order table, trade log and per-step records are Vecs that grow without bound (orderbook.rs:113-115,
     # data.rs:9-57); the tables here are preallocated, so the single-env classes reserve ahead (bb_reserve):
     # orders at submission (ids are handed out on the host), history and trade log before every step.
     def _ensure_orders(self, n_more: int):
         e = self._env
-        need = self._n_issued + n_more         # ids handed out so far (tracked from the ids the submissions return)
+        self._sync_ids()                      # ids handed out so far, the transactions still collected here included
+        need = self._next_id + n_more
         if need > e.max_orders:
-            need = e.n_orders(0) + n_more      # exact count from the library before paying for a reallocation
-            if need > e.max_orders:
-                e.reserve(max_orders=max(2 * e.max_orders, 2 * need))
-        self._n_issued += n_more
+            e.reserve(max_orders=max(2 * e.max_orders, 2 * need))
+        self._n_issued = need
 
     def step(self):
         e = self._env
+        self._flush()
+        self._sync_ids()
         self._n_steps = getattr(self, "_n_steps", 0) + 1
         if self._n_steps > e.max_steps:
             e.reserve(max_steps=2 * e.max_steps)
         if e.max_trades:
-            # a trade either fills a passive order completely or is the last fill of its aggressor, so one step adds
-            # at most (orders in existence) trades
-            need = e.n_trades(0) + e.n_orders(0) + 64
-            if need > e.max_trades:
-                e.reserve(max_trades=max(2 * e.max_trades, 2 * need))
+            # a trade either fills a passive order completely or is the last fill of its aggressor, so one step adds at most
+            # (orders in existence) trades; the exact count is only asked for when that bound runs into the capacity
+            self._trades_ub = getattr(self, "_trades_ub", 0) + self._next_id + 64
+            if self._trades_ub > e.max_trades:
+                self._trades_ub = e.n_trades(0) + self._next_id + 64
+                if self._trades_ub > e.max_trades:
+                    e.reserve(max_trades=max(2 * e.max_trades, 2 * self._trades_ub))
+        self._status_stale = True
         e.step(1)
 
-    def get_orders(self): return self._env.get_orders(0)
+    def get_orders(self): self._flush(); return self._env.get_orders(0)
     def get_trades(self): return self._env.get_trades(0)
-    def order_status(self, order_id: int) -> int: return self._env.order_status(order_id, 0)
+
+    def order_status(self, order_id: int) -> int:
+        # an order submitted since the last step is New (0) until the step places it; transactions still collected here do not
+        # change any status before the step either
+        if self._next_id is None:
+            self._flush()
+            self._sync_ids()
+        if order_id >= self._next_id:
+            self._flush()
+            return self._env.order_status(order_id, 0)   # (raises like the reference: unknown id)
+        n_done = self._next_id - self._pend_new           # orders the library knows
+        if order_id >= n_done:
+            return 0
+        # Statuses only change in a step, and Filled / Cancelled / Rejected are final: the first query after a step brings the
+        # statuses from the oldest order that could still change (New / Active at the last look) to the newest one over in ONE
+        # copy, and the queries of the step are served from the host column — not one library call per query.
+        if self._status_n < n_done or self._status_stale:
+            st, lo = self._status, self._first_live
+            if len(st) < n_done:
+                st = np.concatenate([st, np.zeros(max(n_done, 2 * len(st)) - len(st), np.uint8)])
+            e = self._env
+            e._ck(e._lib.bb_orders(e._h, 0, lo, n_done - lo, None, abi.ptr(st[lo:]), None, None, None, None, None, None))
+            open_ = np.flatnonzero(st[lo:n_done] <= 1)
+            self._first_live = lo + int(open_[0]) if len(open_) else n_done
+            self._status, self._status_n, self._status_stale = st, n_done, False
+        st = self._status
+        return int(st[order_id])
 
     def _l2(self) -> np.ndarray:
         return self._env.level_2_data()[0]
@@ -621,11 +681,14 @@ class StepEnvNumpy(_StepEnvBase):
     def submit_limit_orders(self, orders):
         sides, vols, traders, prices = orders
         n = len(sides)
+        self._flush()
         self._ensure_orders(n)
+        self._next_id = None
         return self._env.submit(np.full(n, abi.ACT_NEW, np.uint32), np.asarray(sides), vols, traders, prices)
 
     def submit_cancellations(self, order_ids):
         order_ids = np.asarray(order_ids, dtype=np.uint64)
+        self._flush()
         self._env.submit(np.full(len(order_ids), abi.ACT_CANCEL, np.uint32), order_id=order_ids)
 
     def submit_instructions(self, instructions):
@@ -633,7 +696,9 @@ class StepEnvNumpy(_StepEnvBase):
         action = np.asarray(action, dtype=np.uint32)
         # the reference treats every code other than 1 / 2 as a no-op (step_sim_numpy.rs:254-268)
         action = np.where((action == 1) | (action == 2), action, 0).astype(np.uint32)
+        self._flush()
         self._ensure_orders(int((action == 1).sum()))
+        self._next_id = None
         return self._env.submit(action, np.asarray(sides), vols, traders, prices, order_ids)
 
     def level_1_data(self): return self._l2()[:9].copy()

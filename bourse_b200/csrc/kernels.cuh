@@ -1390,8 +1390,8 @@ __global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParam
     __syncthreads();
 #ifdef DP_PROF
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const char* nm[16] = {"-", "F:wait_consumed", "F:tma", "F:cpasync+fence", "-", "-", "B:wait_ev", "-",
-                              "B:ret_room", "-", "R:wait", "R:fence", "R:entries", "B:doubt", "-", "-"};
+        const char* nm[16] = {"-", "F:wait_consumed", "F:tma", "F:cpasync+fence", "C:ring_room", "C:borrow", "C:wait_ev", "P:wait_work",
+                              "P:ret_room", "-", "R:wait", "R:fence", "R:entries", "C:doubt", "C:late", "-"};
         printf("k_deepw prof: n=%u cycles=%lld\n", n, clock64() - dp_k0);
         for (int i = 1; i < 15; ++i) {
             if (nm[i][0] != '-') printf("  %-16s cycles %12llu  count %10llu\n", nm[i], g_dp_prof[i], g_dp_prof[32 + i]);

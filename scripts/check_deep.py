@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Developer check: one C5-shaped book on the deep engine against the oracle; prints the first differences.
-    python scripts/dbg_deep.py [n_rest] [n_steps] [per_step] [depth_ticks]"""
+    python scripts/check_deep.py [n_rest] [n_steps] [per_step] [depth_ticks]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

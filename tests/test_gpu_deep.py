@@ -251,3 +251,27 @@ def test_chunk_pool_exhaustion_is_flagged(core):
     with pytest.raises(MemoryError):
         env.replay(s)
     assert int(env.env_errors()[0]) & 0x04
+
+
+def test_trade_log_overflow_is_flagged(core, oracle):
+    """More trades than max_trades: BB_ERR_CAP_TRADES; the book and the order table are still the reference's (only the log is
+    cut), and nothing is written past the log's end (the next env's log stays intact)."""
+    n = 3000
+    s = workloads.replay_stream(n, 4, tick_size=1, trading_windows=False)
+    env = core.BatchedEnv(2, 5, 0, 1, 1000, obs_words=abi.OBS_L2, max_orders=n + 64, max_trades=64, max_steps=n // 32 + 64, max_queue=32,
+                          price_window=(896, 1152), deep_chunks=4096)
+    short = s[:40]   # env 1 gets a short stream: its log must not be touched by env 0's overflow
+    with pytest.raises(MemoryError):
+        env.replay(np.concatenate([s, short]), np.array([0, n, n + len(short)], dtype=np.uint64))
+    errs = env.env_errors()
+    assert int(errs[0]) & 0x02 and not int(errs[1])
+    ob = oracle.OrderBook(0, 1)
+    ob.replay(s, obs_cap=n)
+    go, co = env.orders_arrays(0), ob.orders_arrays()
+    for k in co:
+        assert np.array_equal(co[k], go[k]), k
+    ct, gt = ob.trades_arrays(), env.trades_arrays(0)
+    assert len(gt["t"]) == 64 and all(np.array_equal(ct[k][:64], gt[k]) for k in ct)
+    ob1 = oracle.OrderBook(0, 1)
+    ob1.replay(short, obs_cap=len(short))
+    assert env.get_trades(1) == ob1.get_trades() and env.get_orders(1) == ob1.get_orders()

@@ -21,7 +21,8 @@ def main():
         import torch
         n_books = int(sys.argv[2]) if len(sys.argv) > 2 else 16
         eng = sys.argv[3] if len(sys.argv) > 3 else "deep"
-        n_rest, n_steps, per_step = 1_000_000, 100, 10_000
+        # (a lighter variant for ncu captures with many books: PROF_REST=200000 PROF_STEPS=30 keeps the save / restore small)
+        n_rest, n_steps, per_step = int(os.environ.get("PROF_REST", 1_000_000)), int(os.environ.get("PROF_STEPS", 100)), 10_000
         s = workloads.c5_stream(n_rest, n_steps, per_step, seed=100)
         dev = torch.device("cuda", 0)
         d1 = torch.from_numpy(s[:n_rest].view(np.uint8)).to(dev).repeat(n_books)
@@ -29,8 +30,8 @@ def main():
         o1 = torch.arange(0, n_books + 1, dtype=torch.int64, device=dev) * n_rest
         o2 = torch.arange(0, n_books + 1, dtype=torch.int64, device=dev) * (n_steps * per_step)
         kw = dict(price_window=(7936, 12160), deep_chunks=98304) if eng == "deep" else dict(pages_smem=192, pages_total=192)
-        env = core.BatchedEnv(n_books, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=1_800_000, max_trades=1 << 20,
-                              max_steps=n_steps, max_queue=32, **kw)
+        env = core.BatchedEnv(n_books, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=n_rest + n_steps * per_step * 8 // 10 + 1024,
+                              max_trades=n_steps * per_step + 1024, max_steps=n_steps, max_queue=32, **kw)
         torch.cuda.synchronize()
         env.replay_device(d1.data_ptr(), o1.data_ptr())
         env.replay_device(d2.data_ptr(), o2.data_ptr())

@@ -275,3 +275,30 @@ def test_trade_log_overflow_is_flagged(core, oracle):
     ob1 = oracle.OrderBook(0, 1)
     ob1.replay(short, obs_cap=len(short))
     assert env.get_trades(1) == ob1.get_trades() and env.get_orders(1) == ob1.get_orders()
+
+
+# ---- the reference's OrderBook known answers through core.OrderBook on the deep-book engine ---------------------------------
+# A scenario outside the engine's stated domain must be REFUSED with a flagged error, not mis-simulated: equal-(price, time)
+# key collisions (N1: several orders at one price without advancing time).
+from . import scenarios  # noqa: E402
+
+DEEP_REFUSED = {"book_level_data": "0x100"}
+
+
+@pytest.fixture(scope="module")
+def deep_core(core):
+    import types
+
+    def book(*a, **k):
+        return core.OrderBook(*a, **{**dict(price_window=(0, 512), deep_chunks=1024), **k})
+
+    return types.SimpleNamespace(OrderBook=book, PanicException=core.PanicException)
+
+
+@pytest.mark.parametrize("scenario", scenarios.ALL_BOOK, ids=lambda f: f.__name__)
+def test_reference_known_answers_deep(deep_core, scenario):
+    if scenario.__name__ in DEEP_REFUSED:
+        with pytest.raises(MemoryError, match=DEEP_REFUSED[scenario.__name__]):
+            scenario(deep_core)
+    else:
+        scenario(deep_core)

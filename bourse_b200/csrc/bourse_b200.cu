@@ -1316,7 +1316,6 @@ int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int
     CHECK_ENV(h, env);
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->queue[env].empty()) return fail(h, BB_EINVAL, "env has queued instructions");
-    if (h->eng == ENG_DEEP) return fail(h, BB_EINVAL, "bb_load_book is not available on the deep-book engine");
     if (n_orders > h->cfg.max_orders || n_trades > h->cfg.max_trades) return fail(h, BB_ECAP, "snapshot exceeds max_orders / max_trades");
     if (n_orders && !(side_is_bid && status && arr_time && end_time && vol && start_vol && price && trader && key_time))
         return fail(h, BB_EINVAL, "null order column");
@@ -1339,7 +1338,10 @@ int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int
     hdr.n_trades = (u32)n_trades;
     hdr.n_trades_total = n_trades;
     std::vector<u32> dir;
-    if (h->eng >= ENG_DENSE) {  // empty bitmaps, every slot free (same image k_init writes)
+    if (h->eng == ENG_DEEP) {  // the image k_init_deep writes: empty bitmaps, zero level volumes / counts, chunk 0 reserved
+        dir.assign((h->dp.lht - 128) / 4, 0u);
+        dir[(DP_OFF_BUMP - 128) / 4] = 1u;
+    } else if (h->eng >= ENG_DENSE) {  // empty bitmaps, every slot free (same image k_init writes)
         const Geo& d = h->dgeo;
         hdr.free_top = d.d_live;
         dir.assign((h->blob_smem_bytes - 128) / 4, 0u);
@@ -1383,7 +1385,7 @@ int bb_load_book(bb_handle* h, uint32_t env, uint64_t t, uint32_t trade_vol, int
     std::vector<bb_instr> ins(n_orders);
     std::vector<u32> order(n_orders);
     for (u64 i = 0; i < n_orders; ++i) order[i] = (u32)i;
-    // the dense engine only appends to its queues: feed it the orders by key time (ties keep id order)
+    // the dense and deep engines only append to their queues: feed them the orders by key time (ties keep id order)
     if (h->eng >= ENG_DENSE)
         std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return key_time[a] < key_time[b]; });
     for (u64 i = 0; i < n_orders; ++i) {

@@ -444,7 +444,54 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
     } else if (op == BB_OP_SET_TRADING) {
         s.flags = y.y ? (s.flags | FL_TRADING) : (s.flags & ~FL_TRADING);
     } else if (op == BB_OP_RESTORE) {
-        s.err |= ERR_ROW_OP;  // bb_load_book is not available on the deep engine
+        // bb_load_book: put an Active order read from its HBM record back on its side (orderbook.rs:898-905).  The host feeds
+        // the orders by key time, so appending rebuilds every level's FIFO; equal keys on one level are the N1 collision.
+        id = x.w;
+        if (id < r.max_orders) {
+            const uint4 ra = ldg128_cg(r.oh + (u64)id * ORD_STRIDE), rc = ldg128_cg(r.oh + (u64)id * ORD_STRIDE + 16u);
+            if (id + 1u > s.n_orders) s.n_orders = id + 1u;
+            if ((rc.z & META_STATUS_MASK) == ST_ACTIVE) {
+                const u32 rside = (rc.z & META_BID) ? 1u : 0u, q = ra.x - r.win_lo, rvol = ra.y;
+                const u64 kt = ((u64)rc.y << 32) | rc.x;
+                if (q >= r.W) {
+                    s.err |= ERR_CAP_PAGES;
+                } else {
+                    const u32 ba = bk_bm(r, rside, q >> 5), bit = 1u << (q & 31u);
+                    const u32 la = r.lvol + 4u * q;
+                    const u32 bw = lds(ba), lv = lds(la);
+                    const u32 sa = bk_sm(r, rside, q >> 10);
+                    const u32 sv = lds(sa);
+                    const bool locked = !(bw & bit) && ((lds(bk_bm(r, rside ^ 1u, q >> 5)) & bit) != 0u);
+                    __syncwarp();
+                    if (locked) {
+                        s.err |= ERR_LOCKED;
+                    } else {
+                        if (!(bw & bit)) {
+                            if (lane == 0u) {
+                                sts(la, rvol);
+                                sts(ba, bw | bit);
+                                if (bw == 0u) sts(sa, sv | (1u << ((q >> 5) & 31u)));
+                            }
+                            if (!bk_has_best(s, rside) || (rside ? q > s.bq_bid : q < s.bq_ask)) {
+                                if (rside) s.bq_bid = q; else s.bq_ask = q;
+                                s.flags |= FL_HAS_ASK << rside;
+                            }
+                        } else {
+                            if (kt <= s.max_key_time) s.err |= ERR_TIME_ORDER;
+                            if (lane == 0u) sts(la, lv + rvol);
+                        }
+                        __syncwarp();
+                        bk_add_side(s, rside, rvol);
+                        if (kt > s.max_key_time) s.max_key_time = kt;
+                        if (rvol == 0u) s.zv = 1u;
+                        const u32 pos = bk_append(r, s, lane, q, id, rvol);
+                        if (lane == 0u) stg32(r.oh + (u64)id * ORD_STRIDE + OH_NEXT, pos);  // (the rest of the record is the snapshot's)
+                    }
+                }
+            }
+        } else {
+            s.err |= ERR_CAP_ORDERS;
+        }
     }
     if (kind) {
         // ---- match_bid / match_ask (orderbook.rs:429-487): level by level from the touch

@@ -104,7 +104,7 @@ typedef struct {
      * price_granule == 1; deep_chunks = 256-byte queue chunks per book (31 entries each; one per resting order in the
      * worst case, ~ resting orders / 31 + win_levels + entries appended during a launch / 31 in practice).  Preconditions
      * beyond the window: strictly increasing time between resting inserts (BB_ERR_TIME_ORDER) and one side per price
-     * level (BB_ERR_LOCKED: only reachable while trading is disabled).  Env mode, in-kernel agents and bb_load_book are
+     * level (BB_ERR_LOCKED: only reachable while trading is disabled).  Env mode and in-kernel agents are
      * not available on a deep handle (BB_EINVAL). */
     uint32_t deep_chunks;
 } bb_config;

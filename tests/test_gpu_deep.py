@@ -302,3 +302,27 @@ def test_reference_known_answers_deep(deep_core, scenario):
             scenario(deep_core)
     else:
         scenario(deep_core)
+
+
+def test_snapshot_midstream_on_the_deep_engine(core, oracle, tmp_path):
+    """save_json_snapshot / order_book_from_json (f1, orderbook.rs:898-905) with the book restored onto the deep-book engine:
+    save after half of a C2 stream (paged engine), reload into a deep book, apply the second half to both: identical to the
+    oracle that never saved — order table, trade log, level data, records."""
+    s = workloads.replay_stream(6000, 21, tick_size=1, time_mode="strict", half_width=24, trading_windows=False)
+    a = core.OrderBook(0, 1)
+    a.replay(s[:3000])
+    path = str(tmp_path / "mid.json")
+    a.save_json_snapshot(path)
+    b = core.order_book_from_json(path, price_window=(896, 1152), deep_chunks=4096)
+    assert a.get_orders() == b.get_orders() and a.get_trades() == b.get_trades()
+    assert np.array_equal(a.level_2_data(), b.level_2_data()) and a._l1() == b._l1()
+    oa, ob_ = a.replay(s[3000:]), b.replay(s[3000:])
+    assert np.array_equal(oa, ob_)
+    ref = oracle.OrderBook(0, 1)
+    ref.replay(s)
+    assert b.get_trades() == ref.get_trades() and b.get_orders() == ref.get_orders()
+    assert np.array_equal(b.level_2_data(), ref.level_2_data())
+    # and a deep book saves a snapshot the general engine continues from
+    b.save_json_snapshot(str(tmp_path / "deep.json"))
+    c = core.order_book_from_json(str(tmp_path / "deep.json"))
+    assert c.get_orders() == ref.get_orders() and c.get_trades() == ref.get_trades() and np.array_equal(c.level_2_data(), ref.level_2_data())

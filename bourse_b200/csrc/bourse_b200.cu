@@ -221,8 +221,9 @@ void fill_params(const bb_handle* h, const SmemLayout& l, KParams& p) {
     p.dp_chunks = h->dp_chunks;
 }
 
-// shared-memory map of k_deepw (deep.cuh, deepw.cuh) for a window of W levels
-DeepOff deep_layout(u32 W) {
+// shared-memory map of k_deepw (deep.cuh, deepw.cuh) for a window of W levels; `roomy`: at most two books per SM, so the
+// two staleness filters can be four times larger (fewer false doubts: events that wait for the pipeline to drain)
+DeepOff deep_layout(u32 W, u32 roomy /* filter size multiplier: 1, 4, 8 */) {
     DeepOff o{};
     const u32 nw = W / 32;
     o.bm = DP_OFF_BM;
@@ -238,7 +239,10 @@ DeepOff deep_layout(u32 W) {
     o.ev_rec = off; off += 1024u * DW_RB;
     o.ev_rf = off; off += 16u;
     o.ret = off; off += DP_RENT * DW_RCAP;
-    o.dirty = off; off += 4u * DW_DIRTY;
+    o.dirty_n = roomy * DW_DIRTY;
+    o.swept_n = roomy * DW_SWEPT;
+    o.dirty = off; off += 4u * o.dirty_n;
+    o.swept = off; off += roomy > 1u ? 4u * o.swept_n : 0u;  // (the compact filter sits inside the scratch block)
     o.ctl = off; off += 4u * CT_WORDS;
     o.bar = off; off += 8u * (DW_RB + 1u);
     o.total = align_up(off, 128);
@@ -368,11 +372,13 @@ int launch_apply(bb_handle* h, int mode, const bb_instr* d_instrs, const u64* d_
     if (h->eng == ENG_DEEP) {
         if (mode != MODE_REPLAY || d_out_ids || d_obs_out) return fail(h, BB_EINVAL, "the deep-book engine replays instruction streams only");
         if (!h->deep_attr_set) {
-            CUDA_TRY(h, cudaFuncSetAttribute(k_deepw, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+            CUDA_TRY(h, cudaFuncSetAttribute(k_deepw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+            CUDA_TRY(h, cudaFuncSetAttribute(k_deepw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
             h->deep_attr_set = true;
         }
         p.dp_fast = h->deep_serial ? 0u : 1u;
-        k_deepw<<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
+        if (h->dp.dirty_n > DW_DIRTY) k_deepw<true><<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
+        else k_deepw<false><<<h->cfg.n_envs, 128, h->dp.total, h->stream>>>(p);
         CUDA_TRY(h, cudaGetLastError());
         h->recorded_host = -1;
         return BB_OK;
@@ -509,7 +515,9 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
         h->dgeo.d_win_lo = cfg->win_lo; h->dgeo.d_levels = W; h->dgeo.d_live = 0;
         h->dense_lp = h->dense_nwmax = 0;
         if (const char* m = getenv("BOURSE_B200_DEEP")) h->deep_serial = !strcmp(m, "serial");
-        h->dp = deep_layout(W);
+        // one book per SM: filters x8; two: x4 (while two CTAs still fit an SM); more: the compact sizes
+        h->dp = deep_layout(W, cfg->n_envs <= 148u ? 8u : cfg->n_envs <= 2u * 148u ? 4u : 1u);
+        if (cfg->n_envs > 148u && h->dp.total > 113u * 1024u) h->dp = deep_layout(W, 1u);  // (a wide window: keep two CTAs per SM possible)
         h->dp_chunks = cfg->deep_chunks;
         if (h->dp.total > 232448u - 1024u) {
             delete h;

@@ -47,7 +47,8 @@ namespace bb {
 struct DeepOff {             // byte offsets from the CTA's shared-memory base, filled by the host
     u32 bm, sm, lvol, lcnt, lht, image_bytes;
     u32 smem_image;  // bytes of the image that live in shared memory during a launch (k_deepw: up to lcnt; its queues' counts / heads / tails stay in the blob)
-    u32 scratch, ev_ins, ev_rec, ev_rf, ret, dirty, ctl, bar, total;
+    u32 scratch, ev_ins, ev_rec, ev_rf, ret, dirty, swept, ctl, bar, total;
+    u32 dirty_n, swept_n;  // filter sizes (powers of two): larger when few books share an SM (fewer false doubts)
 };
 // control words (u32 each, at DeepOff::ctl)
 #define CT_EV_READY 0u      // fetch: batches published

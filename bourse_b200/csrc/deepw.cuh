@@ -31,7 +31,8 @@ namespace bb {
 
 #define DW_RB 4u        // event-ring depth in batches of 32
 #define DW_RCAP 256u    // retire-ring entries
-#define DW_DIRTY 2048u  // touched-order filter buckets (by order id)
+#define DW_DIRTY 2048u  // touched-order filter buckets (by order id) / DW_SWEPT swept-level filter buckets (by level): the sizes
+#define DW_SWEPT 256u   // for launches with more than two books per SM; 8192 / 1024 otherwise (DeepOff::dirty_n, swept_n)
 #define DW_MOPS 128u    // micro-op ring (32 bytes each) between the chain warp and the replay warp; a replay round takes up to 32
 #define DW_COUT 64u     // the chain's output list per run (16 bytes each)
 #define DW_FILLS 192u   // fills staged per flush (16 bytes each): also the largest volume one flush may take
@@ -44,8 +45,7 @@ namespace bb {
 #define SC_SPARE (SC_POS + 4u * 32u)         // ... a fresh chunk (bit 31: used)
 #define SC_FREED (SC_SPARE + 4u * 32u)       // ... up to two chunks it emptied
 #define SC_FCOUNT (SC_FREED + 8u * 32u)
-#define SC_SWEPT (SC_FCOUNT + 16u)           // per level (hashed): the last event that took volume from it
-#define DW_SWEPT 256u
+#define SC_SWEPT (SC_FCOUNT + 16u)           // the swept-level filter at its compact size (DW_SWEPT buckets; larger ones live elsewhere)
 #define SC_COUT (SC_SWEPT + 4u * DW_SWEPT)   // the chain's output: one 16-byte record per micro-op
 #define DW_SCRATCH (SC_COUT + 16u * DW_COUT)
 
@@ -58,7 +58,8 @@ __device__ __forceinline__ u32 atoms_add(u32 a, u32 v) {
 }
 
 struct BkReg {  // launch-invariant addresses and limits (pinned in registers)
-    u32 lvol, bma, bmb, sma, smb, scr, ret, dirty, ctl, fs;
+    u32 lvol, bma, bmb, sma, smb, scr, ret, dirty, swept, ctl, fs;
+    u32 dirty_mask, swept_mask;
     u32 win_lo, W, max_orders, n_chunks, max_trades;
     u64 oh, chunks, tr;
     u64 lcnt, lht;  // per level, in the book's blob (global memory, L1-cached: only this CTA touches them): resting orders;
@@ -289,7 +290,7 @@ __device__ __forceinline__ bool bk_sweep(const BkReg& r, BkSt& s, u32 lane, u32 
             // trade: side / price are the passive order's (orderbook.rs:853-862)
             bk_ret_write(r, s.ret_tail + k, make_uint4(RK_FILL | (opp << 8) | (pv == 0u ? 0x10000u : 0u), pid, tv, pv), make_uint4(t_lo, t_hi, price, id));
             bk_trade(r, s, s.n_tr + k, t_lo, t_hi, price, tv, id, pid, opp, lane_err);
-            reds_max(r.dirty + 4u * (pid & (DW_DIRTY - 1u)), mark);
+            reds_max(r.dirty + 4u * (pid & r.dirty_mask), mark);
             if (!full) stg32(bk_chunk(r, c) + 8u * lane + 4u, pv);  // the partially filled order stays at the head of its level
         }
         take -= traded;
@@ -392,7 +393,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
         } else {
             // The order's record as the fetch warp saw it: usable iff every write to it was in HBM by then, i.e. no event that
             // touched the order (its own, or a sweep that filled it) was still in the pipeline.
-            const u32 dv = lds(r.dirty + 4u * (id & (DW_DIRTY - 1u)));
+            const u32 dv = lds(r.dirty + 4u * (id & r.dirty_mask));
             if (dv > rf) {  // doubtful: let the pipeline drain up to that event, read again
                 bk_publish(r, s, lane, ev_done - 1u);
                 if (!bk_wait(r, lane, [&] { return ld_acq(r.ctl + CT_EV_RETIRED) >= dv; }, 13)) return false;
@@ -417,7 +418,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
                     bk_add_side(s, oside, y.y - a.y);
                     if (y.y == 0u) s.zv = 1u;
                     if (!bk_ret1(r, s, lane, make_uint4(RK_REDUCE, id, y.y, 0u), make_uint4(x.x, x.y, 0u, 0u))) return false;
-                    if (lane == 0u) reds_max(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
+                    if (lane == 0u) reds_max(r.dirty + 4u * (id & r.dirty_mask), ev_done);
                     s.d_applied += 1;
                 } else {  // cancel_order (orderbook.rs:622-644), or the remove half of replace_order (:679-723)
                     const bool cancel = op == BB_OP_CANCEL;
@@ -429,7 +430,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
                     bk_remove(r, s, lane, q, a.z);
                     if (cancel && !bk_ret1(r, s, lane, make_uint4(RK_CANCEL | (oside << 8), id, 0u, 0u), make_uint4(x.x, x.y, 0u, 0u))) return false;
                     if (nv == 0u && (!s.zv || ldg32(r.lcnt + 4u * q) == 0u)) bk_level_gone(r, s, lane, oside, q);
-                    if (lane == 0u) reds_max(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
+                    if (lane == 0u) reds_max(r.dirty + 4u * (id & r.dirty_mask), ev_done);
                     if (cancel) {
                         s.d_applied += 1;
                     } else {  // never a market order (N4)
@@ -571,7 +572,7 @@ __device__ __forceinline__ bool bk_serial(const BkReg& r, BkSt& s, u32 lane, uin
         // rest — flagged above — keeps status Active in its record and is not on the book)
         if (!bk_ret1(r, s, lane, make_uint4(kind | (side << 8) | (status << 12), id, rem, rests ? pos : 0u), make_uint4(x.x, x.y, price, 0u)))
             return false;
-        if (lane == 0u) reds_max(r.dirty + 4u * (id & (DW_DIRTY - 1u)), ev_done);
+        if (lane == 0u) reds_max(r.dirty + 4u * (id & r.dirty_mask), ev_done);
         s.d_applied += 1;
     }
     bk_publish(r, s, lane, ev_done);
@@ -761,7 +762,7 @@ __device__ __forceinline__ u32 bk_replay_round(const BkReg& r, BkSt& s, u32 lane
                 // trade: side / price are the passive order's (orderbook.rs:853-862)
                 bk_ret_write(r, jr + k, make_uint4(RK_FILL | (jopp << 8) | (g.w == 0u ? 0x10000u : 0u), g.y, g.z, g.w), make_uint4(jlo, jhi, price, jid));
                 bk_trade(r, s, jt + k, jlo, jhi, price, g.z, jid, g.y, jopp, lane_err);
-                reds_max(r.dirty + 4u * (g.y & (DW_DIRTY - 1u)), jmark);
+                reds_max(r.dirty + 4u * (g.y & r.dirty_mask), jmark);
             }
         }
         // the events' own record entries
@@ -780,7 +781,7 @@ __device__ __forceinline__ u32 bk_replay_round(const BkReg& r, BkSt& s, u32 lane
                 eb.z = w.w;
             }
             bk_ret_write(r, ring0 + nf, ea, eb);
-            reds_max(r.dirty + 4u * (w.y & (DW_DIRTY - 1u)), v.w);
+            reds_max(r.dirty + 4u * (w.y & r.dirty_mask), v.w);
         }
         s.ret_tail += n_ring;
         s.n_tr += n_fill;
@@ -942,7 +943,7 @@ __device__ __forceinline__ bool bk_chain_place(const BkReg& r, BkSt& s, u32 co, 
         rem -= take;
         sts(la, nv);
         last_t = n_out;
-        sts(r.scr + SC_SWEPT + 4u * (bq & (DW_SWEPT - 1u)), mark);
+        sts(r.swept + 4u * (bq & r.swept_mask), mark);
         sts128(co + 16u * n_out++, make_uint4(bq | (MK_T << 13) | (rem > 0u ? 1u << 16 : 0u) | (OPP << 17) | ebits, take, 0u, 0u));
         if (nv == 0u) bk_level_gone<true>(r, s, 0u, OPP, bq);
     }
@@ -1032,7 +1033,7 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                 if (id >= s.n_orders + __popc(newm & lt) || id >= r.max_orders) {
                     cx = true;  // unknown id
                 } else {
-                    if (lds(r.dirty + 4u * (id & (DW_DIRTY - 1u))) > rfl) { cx = true; why = CXR_DOUBT; }
+                    if (lds(r.dirty + 4u * (id & r.dirty_mask)) > rfl) { cx = true; why = CXR_DOUBT; }
                     const bool has_p = (x.z & BB_F_HAS_PRICE) != 0u, has_v = (x.z & BB_F_HAS_VOL) != 0u;
                     q1 = a.x - r.win_lo;
                     if ((c.z & META_STATUS_MASK) != ST_ACTIVE || (op == BB_OP_MODIFY && !has_p && !has_v) || q1 >= r.W) {
@@ -1119,7 +1120,7 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                         if (n_out + 4u > DW_COUT) break;
                         if (f & (EF_REM | EF_RED)) {
                             const uint4 d1 = lds128(ea + 16u);
-                            const u32 sw = lds(r.scr + SC_SWEPT + 4u * (d1.x & (DW_SWEPT - 1u)));
+                            const u32 sw = lds(r.swept + 4u * (d1.x & r.swept_mask));
                             if (sw > qev) {
                                 stop = sw;
                                 break;
@@ -1200,7 +1201,7 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                         sts128(ma, make_uint4(cr.x & 0x3FFFFu, d0.y, a2, a3));
                         sts128(ma + 16u, make_uint4(d0.z, d0.w, cr.w, mark));
                         // the order this event names is in flight from now on: its prefetched record is not to be trusted
-                        if (cr.w) reds_max(r.dirty + 4u * (d0.y & (DW_DIRTY - 1u)), mark);
+                        if (cr.w) reds_max(r.dirty + 4u * (d0.y & r.dirty_mask), mark);
                     }
                 }
                 s.n_emit += n_out;
@@ -1238,7 +1239,7 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
             if (__shfl_sync(BB_FULL, why, k) == CXR_DOUBT) {
                 // A doubtful record is no reason for the serial path: everything that is on its way drains (the micro-ops are all
                 // published), the record is read again, and the event is decoded again — with a record it can trust now.
-                const u32 need = __shfl_sync(BB_FULL, lds(r.dirty + 4u * (id & (DW_DIRTY - 1u))), k);
+                const u32 need = __shfl_sync(BB_FULL, lds(r.dirty + 4u * (id & r.dirty_mask)), k);
                 u32 seen = 0u;
                 if (!bk_wait(r, lane, [&] {
                         seen = ld_acq(r.ctl + CT_EV_RETIRED);

@@ -1212,7 +1212,10 @@ namespace bb {
 // ---------------------------------------------------------------------------------------------------
 // Deep-book replay kernel, batch-parallel (deepw.cuh): one CTA per book; warp 0 = the book (a batch of 32 events, one lane
 // each), warp 1 = fetch, warp 2 = retire.  Same blob image, chunk pool, order records and trade log as k_deep.
-__global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParams p) {
+// ROOMY: at most two books per SM — the staleness filters take their (larger) sizes from the launch; otherwise they are
+// compile-time constants and the kernel is the compact one the four-books-per-SM case needs (its instruction cache is the limiter).
+template <bool ROOMY>
+__global__ void __launch_bounds__(128, ROOMY ? 2 : 4) k_deepw(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     // The four roles rotate with the wave a CTA belongs to (CTAs go round the 148 SMs of a B200, so the up-to-four CTAs that
     // share an SM are 148 apart): the four busy chain warps of an SM then sit on four different schedulers, not on one.
@@ -1233,8 +1236,8 @@ __global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParam
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (u32 i = threadIdx.x; i < CT_WORDS; i += blockDim.x) sts(ctl + 4u * i, 0u);
-    for (u32 i = threadIdx.x; i < DW_DIRTY; i += blockDim.x) sts(sb + o.dirty + 4u * i, 0u);
-    for (u32 i = threadIdx.x; i < DW_SWEPT; i += blockDim.x) sts(sb + o.scratch + SC_SWEPT + 4u * i, 0u);
+    for (u32 i = threadIdx.x; i < (ROOMY ? o.dirty_n : DW_DIRTY); i += blockDim.x) sts(sb + o.dirty + 4u * i, 0u);
+    for (u32 i = threadIdx.x; i < (ROOMY ? o.swept_n : DW_SWEPT); i += blockDim.x) sts(sb + (ROOMY ? o.swept : o.scratch + SC_SWEPT) + 4u * i, 0u);
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1259,6 +1262,9 @@ __global__ void __launch_bounds__(128, 4) k_deepw(const __grid_constant__ KParam
     r.scr = dp_keep32(sb + o.scratch);
     r.ret = dp_keep32(sb + o.ret);
     r.dirty = dp_keep32(sb + o.dirty);
+    r.swept = ROOMY ? dp_keep32(sb + o.swept) : r.scr + SC_SWEPT;  // (compact: a constant offset from the scratch base, no register)
+    r.dirty_mask = ROOMY ? o.dirty_n - 1u : DW_DIRTY - 1u;
+    r.swept_mask = ROOMY ? o.swept_n - 1u : DW_SWEPT - 1u;
     r.ctl = dp_keep32(ctl);
     r.fs = dp_keep32(sb + DP_OFF_FS);
     r.win_lo = p.geo.d_win_lo; r.W = p.geo.d_levels; r.max_orders = p.geo.max_orders;

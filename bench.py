@@ -826,7 +826,9 @@ def main():
                     help="c3 = the headline line; the others are the secondary configs (market = the multi-asset example)")
     args = ap.parse_args()
     if args.engine is None:
-        args.engine = "paged" if args.workload == "gym" and not args.bg_agents else "deep" if args.workload == "c5" else "dense"
+        # c2: one CTA per book (k_deepw) while at most two books share an SM, the paged engine (one warp per book) beyond
+        c2_deep = args.workload == "c2" and (args.envs == N_ENVS_PER_GPU or args.envs <= 296)
+        args.engine = ("paged" if args.workload == "gym" and not args.bg_agents else "deep" if args.workload == "c5" or c2_deep else "dense")
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

@@ -1,10 +1,12 @@
-// Deep-book engine, batch-parallel book warp (included by kernels.cuh after deep.cuh; kernel k_deepw).
+// Deep-book engine, the book side: chain warp and replay warp (included by kernels.cuh after deep.cuh; kernel k_deepw).
 //
 // Reference semantics: side.rs:36-143, orderbook.rs:429-772.  Data structures (deep.cuh): dense tick-indexed level volumes +
 // per-side bitmaps in shared memory, chunked array queues in HBM, fetch warp in front, retire warp behind.  The first version of
 // this engine ran one event at a time on lane 0 of two warps (ladder, queue): ~200 dependent instructions each per event, 1250
 // cycles per event on a B200 SM (profiles/r02_summary.md) — a single thread of a GPU is a slow CPU.  Here an event's work is
-// cut along its data, and only the true recurrence stays serial:
+// cut along its data, and only the true recurrence stays serial.  Two warps, a ring of micro-ops between them:
+//
+// CHAIN WARP
 //
 //   decode    (32 events, one lane each) everything about an event that does not depend on the book: what kind of
 //             instruction it is, whether the order record the fetch warp prefetched can be trusted (not touched by an event
@@ -14,7 +16,9 @@
 //   chain     the price ladder, strictly in event order but nothing else: level volumes, bitmaps, best bid / ask.  It
 //             decides how much an aggressive order takes from each level it crosses and where an order rests, and writes
 //             that down as MICRO-OPS, each on ONE price level: T(ake) q volume, A(ppend) q order, R(emove) q position,
-//             D(ecrease) q position volume;
+//             D(ecrease) q position volume.  Lane 0 runs it alone (plain loads / stores, side-specialised code) and writes
+//             16-byte records; all lanes then turn them into self-contained 32-byte micro-ops in the ring.
+// REPLAY WARP
 //   replay    (32 micro-ops, one lane each) the price-time queues.  Levels are independent, so the micro-ops are grouped
 //             by level (__match_any_sync) and the first lane of every group walks its level's FIFO through the group's
 //             micro-ops in order — all levels of the round at the same time.  Fills are staged with their (micro-op, rank)
@@ -23,8 +27,9 @@
 //
 // Queue entries are read with ordinary (L1-cached) loads: only this CTA ever touches its book's chunk pool, the head
 // chunks of the levels around the touch stay in L1 (latency close to shared memory), and a lane can walk its level alone.
-// Trades go to the trade log straight from the book warp (their order in the log is the event order, which only this
-// warp knows); order-record updates go through the retire ring as before.
+// Trades go to the trade log straight from the replay warp (their order in the log is the event order = the ring order);
+// order-record updates go through the retire ring to the retire warp.  Complex events run on the chain warp while the replay
+// warp is parked (bk_borrow / bk_give_back: the queues' scalars change hands through the control block).
 #pragma once
 
 namespace bb {
@@ -49,7 +54,6 @@ namespace bb {
 #define SC_COUT (SC_SWEPT + 4u * DW_SWEPT)   // the chain's output: one 16-byte record per micro-op
 #define DW_SCRATCH (SC_COUT + 16u * DW_COUT)
 
-__device__ __forceinline__ void reds_add(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_max(u32 a, u32 v) { asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 atoms_add(u32 a, u32 v) {
     u32 o;

@@ -929,11 +929,14 @@ __device__ __forceinline__ void bk_give_back(const BkReg& r, BkSt& s, u32 lane) 
 // how much each crossed level gives — then rest or finish (orderbook.rs:495-531, 699-722).  SIDE is the order's side, a
 // compile-time constant so that "the other side's touch" is a register, not a select.  Returns true when the output list is
 // full in the middle of a sweep (the caller flushes and calls again: rem and the ladder carry the state).
-template <u32 SIDE>
+template <u32 SIDE_T>
 __device__ __forceinline__ bool bk_chain_place(const BkReg& r, BkSt& s, u32 co, u32& n_out, u32 ea, u32 f, u32 e, u32 mark, u32& rem, u32& last_t,
                                                u32& last_a) {
-    constexpr u32 OPP = SIDE ^ 1u;
-    constexpr u32 HAS_OPP = FL_HAS_ASK << OPP, HAS_OWN = FL_HAS_ASK << SIDE;
+    // SIDE_T 0 / 1: the side as a compile-time constant; 2: one generic copy — the compact kernel (several books per SM) is bound by
+    // instruction-cache refills and wins with the smaller hot loop, the roomy one with the shorter chain (profiles/r02_summary.md)
+    const u32 SIDE = SIDE_T < 2u ? SIDE_T : ((f & EF_PSIDE) ? 1u : 0u);
+    const u32 OPP = SIDE ^ 1u;
+    const u32 HAS_OPP = FL_HAS_ASK << OPP, HAS_OWN = FL_HAS_ASK << SIDE;
     const u32 price = lds(ea + 32u);
     const u32 ebits = e << 18;
     while (rem > 0u && (s.flags & HAS_OPP)) {
@@ -1002,8 +1005,10 @@ __device__ __forceinline__ bool bk_chain_place(const BkReg& r, BkSt& s, u32 co, 
 // The events of one batch still to do (`pending`: a contiguous run of lanes; lane i holds event i: x, y pre-decoded
 // instruction, a, c prefetched record).  `ev0`: events complete before this batch.  Comes back early (obs_lane < 32) after an
 // event that asks for a market-data record.  Returns false when a bounded wait ran out.
+template <bool COMPACT>
 __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32& pending, uint4 x, uint4 y, uint4 a, uint4 c, u32 ev0, u32 rf,
                                          u32 fast, u32& lane_err, u32& obs_lane) {
+    constexpr bool compact = COMPACT;
     const u32 lt = (1u << lane) - 1u;
     const u32 op = x.z & BB_OP_MASK;
     const u32 t_lo = x.x, t_hi = x.y;
@@ -1114,8 +1119,9 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                     if (in_place) {  // the sweep the last run had to leave
                         const u32 ea = r.scr + SC_EVD + 48u * e;
                         const u32 f = lds(ea);
-                        in_place = (f & EF_PSIDE) ? bk_chain_place<1u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
-                                                  : bk_chain_place<0u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a);
+                        in_place = compact              ? bk_chain_place<2u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
+                                   : (f & EF_PSIDE) ? bk_chain_place<1u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
+                                                    : bk_chain_place<0u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a);
                         if (!in_place) ++e;
                     }
                     while (!in_place && e < e_end) {
@@ -1146,8 +1152,9 @@ __device__ __forceinline__ bool bk_batch(const BkReg& r, BkSt& s, u32 lane, u32&
                         if (f & EF_PLACE) {
                             rem = lds(ea + 36u);
                             last_t = 0xFFFFFFFFu;
-                            in_place = (f & EF_PSIDE) ? bk_chain_place<1u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
-                                                      : bk_chain_place<0u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a);
+                            in_place = compact              ? bk_chain_place<2u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
+                                       : (f & EF_PSIDE) ? bk_chain_place<1u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a)
+                                                        : bk_chain_place<0u>(r, s, co, n_out, ea, f, e, ev0 + e + 1u, rem, last_t, last_a);
                             if (in_place) break;
                         }
                         ++e;

@@ -1331,7 +1331,7 @@ __global__ void __launch_bounds__(128, ROOMY ? 2 : 4) k_deepw(const __grid_const
             u32 pending = cnt >= 32u ? BB_FULL : ((1u << cnt) - 1u);
             while (pending) {
                 u32 obs_lane = 32u;
-                if (!bk_batch(r, s, lane, pending, x, y, a, c, 32u * b, rf, fast, lane_err, obs_lane)) { aborted = true; break; }
+                if (!bk_batch<!ROOMY>(r, s, lane, pending, x, y, a, c, 32u * b, rf, fast, lane_err, obs_lane)) { aborted = true; break; }
                 if (obs_lane < 32u) {  // Level2DataRecords::append_record (data.rs:44-56) for a row flagged BB_F_EMIT
                     const u32 bid = (s.flags & FL_HAS_BID) ? r.win_lo + s.bq_bid : 0u;
                     const u32 ask = (s.flags & FL_HAS_ASK) ? r.win_lo + s.bq_ask : 0xFFFFFFFFu;

@@ -326,3 +326,33 @@ def test_snapshot_midstream_on_the_deep_engine(core, oracle, tmp_path):
     b.save_json_snapshot(str(tmp_path / "deep.json"))
     c = core.order_book_from_json(str(tmp_path / "deep.json"))
     assert c.get_orders() == ref.get_orders() and c.get_trades() == ref.get_trades() and np.array_equal(c.level_2_data(), ref.level_2_data())
+
+
+@pytest.mark.parametrize("n_books", [150, 300, 600])
+def test_every_kernel_variant_against_the_oracle(core, oracle, n_books):
+    """k_deepw comes in two instantiations and three filter sizes, chosen by how many books share an SM (one, two, more):
+    150 books run the roomy kernel with x4 filters, 300 and 600 the compact one (generic placement code, compact filters;
+    600 also goes beyond one wave of 4 x 148 CTAs).  C5-shaped books, 8 distinct streams, the books that share a stream must be
+    identical and the distinct ones equal the oracle bit for bit."""
+    n_rest, n_steps, per_step, n_distinct = 6000, 4, 900, 8
+    streams = [workloads.c5_stream(n_rest, n_steps, per_step, seed=70 + i, mid_ticks=3000, depth_ticks=96) for i in range(n_distinct)]
+    n = len(streams[0])
+    allb = np.concatenate([streams[b % n_distinct] for b in range(n_books)])
+    env = core.BatchedEnv(n_books, 5, 0, 1, 1000, obs_words=abi.OBS_L2, max_orders=n + 64, max_trades=2 * n + 64, max_steps=n_steps + 8,
+                          max_queue=32, price_window=(2880, 3136), deep_chunks=n // 8 + 1024)
+    cut = n_rest + per_step + 333
+    off = np.arange(n_books + 1, dtype=np.uint64)
+    env.replay(np.concatenate([streams[b % n_distinct][:cut] for b in range(n_books)]), off * cut)
+    env.replay(np.concatenate([streams[b % n_distinct][cut:] for b in range(n_books)]), off * (n - cut))
+    del allb
+    assert not env.env_errors().any()
+    hist = env.history_all(n_steps)
+    l2 = env.level_2_data()
+    for b in range(n_distinct, n_books):
+        assert np.array_equal(hist[b], hist[b % n_distinct]) and np.array_equal(l2[b], l2[b % n_distinct]), b
+        assert env.n_orders(b) == env.n_orders(b % n_distinct) and env.n_trades(b) == env.n_trades(b % n_distinct), b
+    for i in list(range(n_distinct)) + [n_books - 1]:
+        ob = oracle.OrderBook(0, 1)
+        obs = ob.replay(streams[i % n_distinct], obs_cap=n_steps)
+        compare_book(env, i, ob, hist[i], obs)
+        assert len(ob.get_trades()) > 500

@@ -60,7 +60,7 @@ EXPORTS = [
     "bb_level2", "bb_book_level1", "bb_book_level2", "bb_n_steps", "bb_history", "bb_history_all",
     "bb_n_orders", "bb_n_trades", "bb_orders", "bb_trades", "bb_order_status", "bb_time", "bb_set_time",
     "bb_set_trading", "bb_env_errors", "bb_stats", "bb_history_device", "bb_order_keys", "bb_load_book",
-    "bb_set_agents_market", "bb_step_device", "bb_level2_device", "bb_level1_device", "bb_device_alloc", "bb_device_free", "bb_memcpy", "bb_run_agents_with_rows", "bb_reserve", "bb_clear_history", "bb_clear_errors",
+    "bb_set_agents_market", "bb_step_device", "bb_level2_device", "bb_level1_device", "bb_device_alloc", "bb_device_free", "bb_memcpy", "bb_run_agents_with_rows", "bb_reserve", "bb_reserve_queue", "bb_clear_history", "bb_clear_errors",
     "bb_orders_all", "bb_trades_all", "bb_comm_unique_id", "bb_comm_init_rank", "bb_comm_init_all", "bb_comm_n_ranks", "bb_comm_destroy", "bb_comm_last_error", "bb_gather_stats",
 ]
 
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     sig("bb_destroy", i32, vp)
     sig("bb_reset", i32, vp)
     sig("bb_reserve", i32, vp, u32, u32, u32)
+    sig("bb_reserve_queue", i32, vp, u32)
     sig("bb_clear_history", i32, vp)
     sig("bb_clear_errors", i32, vp)
     sig("bb_last_error", C.c_char_p, vp)

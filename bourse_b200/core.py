@@ -88,7 +88,7 @@ class BatchedEnv:
         cfg.deep_chunks = deep_chunks
         self._h = C.c_void_p()
         self.n_envs, self.obs_words, self.tick_size, self.device = n_envs, obs_words, tick_size, device
-        self.max_orders, self.max_trades, self.max_steps = max_orders, max_trades, max_steps
+        self.max_orders, self.max_trades, self.max_steps, self.max_queue = max_orders, max_trades, max_steps, max_queue
         rc = self._lib.bb_create(C.byref(cfg), C.byref(self._h))
         if rc != abi.BB_OK:
             msg = self._lib.bb_last_error(None)
@@ -116,6 +116,12 @@ class BatchedEnv:
         self.max_orders, self.max_steps = max(self.max_orders, max_orders), max(self.max_steps, max_steps)
         if self.max_trades:
             self.max_trades = max(self.max_trades, max_trades)
+
+    def reserve_queue(self, max_queue: int):
+        """Grow the number of transactions one env may queue for one step (bb_reserve_queue); MemoryError when the step's
+        shuffle would no longer fit in shared memory."""
+        self._ck(self._lib.bb_reserve_queue(self._h, max_queue))
+        self.max_queue = max(self.max_queue, max_queue)
 
     def grow_if_needed(self, env: int = 0, headroom_orders: int = 0, headroom_steps: int = 0, headroom_trades: int = 0):
         """Single-env convenience used by OrderBook / StepEnv: double a table once it is more than half full (plus the
@@ -521,6 +527,12 @@ class _StepEnvBase:
         self._tick = tick_size
         self._next_id = 0    # the id the next new order gets (None: unknown, ask the library)
         self._n_issued = 0   # upper bound of the order ids handed out (exact unless a submission raised)
+        self._queued = 0     # rows handed to the library since the last step
+
+    def _submit_rows(self, action, *a, **kw):
+        out = self._env.submit(action, *a, **kw)
+        self._queued += len(action)   # transactions waiting for the next step (the reference's Env::transactions, env.rs:93-96)
+        return out
 
     def _sync_ids(self):
         if self._next_id is None:
@@ -546,7 +558,7 @@ class _StepEnvBase:
         a = np.array(self._pend, dtype=np.uint64)
         self._pend, self._pend_new = [], 0
         try:
-            out = self._env.submit(a[:, 0].astype(np.uint32), a[:, 1].astype(np.uint8), a[:, 2].astype(np.uint32), a[:, 3].astype(np.uint32),
+            out = self._submit_rows(a[:, 0].astype(np.uint32), a[:, 1].astype(np.uint8), a[:, 2].astype(np.uint32), a[:, 3].astype(np.uint32),
                                    a[:, 4].astype(np.uint32), a[:, 5], flags=a[:, 6].astype(np.uint32))
         except Exception:
             self._next_id = None   # (whatever was accepted before the failing row keeps its id)
@@ -584,7 +596,21 @@ class _StepEnvBase:
                 if self._trades_ub > e.max_trades:
                     e.reserve(max_trades=max(2 * e.max_trades, 2 * self._trades_ub))
         self._status_stale = True
-        e.step(1)
+        # the reference's transaction queue is an unbounded Vec; the step's shuffle here happens in shared memory, so the queue
+        # capacity is reserved ahead of need (and once more if a submission that raised half-way left the count short)
+        if self._queued > e.max_queue:
+            try:
+                e.reserve_queue(min(65535, max(2 * e.max_queue, self._queued)))
+            except MemoryError:
+                pass   # (the count includes rows that queue nothing; bb_step knows the exact one and refuses cleanly)
+        try:
+            e.step(1)
+        except MemoryError as err:
+            if "max_queue" not in str(err) or e.max_queue >= 65535:
+                raise
+            e.reserve_queue(min(65535, 4 * max(e.max_queue, self._queued)))
+            e.step(1)
+        self._queued = 0
 
     def get_orders(self): self._flush(); return self._env.get_orders(0)
     def get_trades(self): return self._env.get_trades(0)
@@ -684,12 +710,12 @@ class StepEnvNumpy(_StepEnvBase):
         self._flush()
         self._ensure_orders(n)
         self._next_id = None
-        return self._env.submit(np.full(n, abi.ACT_NEW, np.uint32), np.asarray(sides), vols, traders, prices)
+        return self._submit_rows(np.full(n, abi.ACT_NEW, np.uint32), np.asarray(sides), vols, traders, prices)
 
     def submit_cancellations(self, order_ids):
         order_ids = np.asarray(order_ids, dtype=np.uint64)
         self._flush()
-        self._env.submit(np.full(len(order_ids), abi.ACT_CANCEL, np.uint32), order_id=order_ids)
+        self._submit_rows(np.full(len(order_ids), abi.ACT_CANCEL, np.uint32), order_id=order_ids)
 
     def submit_instructions(self, instructions):
         action, sides, vols, traders, prices, order_ids = instructions
@@ -699,7 +725,7 @@ class StepEnvNumpy(_StepEnvBase):
         self._flush()
         self._ensure_orders(int((action == 1).sum()))
         self._next_id = None
-        return self._env.submit(action, np.asarray(sides), vols, traders, prices, order_ids)
+        return self._submit_rows(action, np.asarray(sides), vols, traders, prices, order_ids)
 
     def level_1_data(self): return self._l2()[:9].copy()
     def level_2_data(self): return self._l2().copy()

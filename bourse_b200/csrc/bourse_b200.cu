@@ -677,6 +677,14 @@ int bb_step(bb_handle* h, uint32_t n_steps) {
         total += h->queue[e].size();
     }
     h->h_offsets[ne] = total;
+    // A step's queue is shuffled in shared memory: a queue beyond max_queue is refused BEFORE anything is applied (the
+    // transactions stay queued; bb_reserve_queue makes room) instead of being cut short on the device.
+    if (h->assets <= 1)
+        for (u32 e = 0; e < ne; ++e)
+            if (h->queue[e].size() > h->cfg.max_queue)
+                return fail(h, BB_ECAP, "env " + std::to_string(e) + " has " + std::to_string(h->queue[e].size()) +
+                                            " transactions queued for this step, max_queue is " + std::to_string(h->cfg.max_queue) +
+                                            " (bb_reserve_queue grows it)");
     int rc = ensure_instr_capacity(h, total + 1);
     if (rc) return rc;
     if (h->assets > 1) {
@@ -926,6 +934,33 @@ int bb_reserve(bb_handle* h, uint32_t max_orders, uint32_t max_trades, uint32_t 
         h->max_steps_padded = padded;
         h->hist_env_stride = stride;
     }
+    return BB_OK;
+}
+
+int bb_reserve_queue(bb_handle* h, uint32_t max_queue) {
+    CHECK_H(h);
+    if (max_queue <= h->cfg.max_queue || h->eng == ENG_DEEP) return BB_OK;  // (the deep-book engine has no Env-step queue)
+    if (max_queue > 65535 || (h->assets > 1 && (u64)h->assets * max_queue > 65535))
+        return fail(h, BB_EINVAL, "max_queue (times assets, for markets) must stay below 65536");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    // the step's permutation (and, for the dense engine's in-kernel agents, the queue itself) lives in shared memory: the
+    // layouts are rebuilt for the new capacity, and the request is refused while the Env-step kernel could not run one book
+    // per CTA with it (k_sim's fit is checked at its launch, like at creation)
+    const u32 old = h->cfg.max_queue;
+    h->cfg.max_queue = max_queue;
+    const SmemLayout la = make_layout(h, false, true);
+    if (la.warp_bytes > 232448u - 1024u) {
+        h->cfg.max_queue = old;
+        return fail(h, BB_ECAP, "max_queue does not fit in shared memory next to the book image");
+    }
+    h->lay_apply = la;
+    h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE, !h->group_asset.empty());
+    h->lay_snap = make_layout(h, false, false);
+    cudaFree(h->scratch);  // k_sim's global-memory queues are sized by max_queue: reallocated at the next agent launch
+    h->scratch = nullptr;
+    h->scratch_warps = 0;
     return BB_OK;
 }
 

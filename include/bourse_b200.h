@@ -186,6 +186,12 @@ int bb_reset(bb_handle* h); /* back to the freshly created state (same config, s
  * a host that cannot size a run up front calls this when usage nears a capacity (the Python OrderBook / StepEnv /
  * StepEnvNumpy classes do).  Synchronous; costs one device-to-device copy of the slab that grows. */
 int bb_reserve(bb_handle* h, uint32_t max_orders, uint32_t max_trades, uint32_t max_steps);
+/* Grow (never shrink) max_queue, the number of transactions one env may queue for ONE step.  The reference's
+ * Env::transactions is an unbounded Vec (crates/step_sim/src/env.rs:93-96, 121); here a step's queue is shuffled in shared
+ * memory, so it is bounded by what fits there next to the book image (BB_ECAP beyond that, nothing changed).  bb_step refuses
+ * a step whose queue exceeds max_queue with BB_ECAP BEFORE applying anything (the transactions stay queued), so a host can
+ * call this and step again; the Python StepEnv / StepEnvNumpy classes reserve ahead of need.  Synchronous. */
+int bb_reserve_queue(bb_handle* h, uint32_t max_queue);
 /* Forget the per-step records (Level2DataRecords, data.rs:9-57) of every env: the history restarts at record 0, the books,
  * order tables and trade logs are untouched.  For open-ended loops that consume each step's observation as it is produced
  * (bb_step_device / bb_run_agents_with_rows) and would otherwise run into max_steps.  Asynchronous. */

@@ -410,11 +410,12 @@ def dense_kwargs_for(groups) -> dict:
 
 
 def momentum_group(agent_id_start, n_agents, tick_size, p_cancel, trade_vol, decay, demand, scale, order_ratio,
-                   price_dist_mu, price_dist_sigma):
-    """MomentumAgent::new + MomentumParams (crates/step_sim/src/agents/momentum_agent.rs:16-35, 118-134)."""
+                   price_dist_mu, price_dist_sigma, live_cap: int = 0):
+    """MomentumAgent::new + MomentumParams (crates/step_sim/src/agents/momentum_agent.rs:16-35, 118-134).
+    `live_cap`: room for the agent's list of resting limit orders (the reference's Vec, momentum_agent.rs:99-102); 0 = 254."""
     g = np.zeros(1, dtype=abi.GROUP_DTYPE)[0]
     g["kind"], g["n_agents"] = abi.GROUP_MOMENTUM, n_agents
-    g["tick_lo"], g["vol_lo"] = agent_id_start, trade_vol
+    g["tick_lo"], g["vol_lo"], g["vol_hi"] = agent_id_start, trade_vol, live_cap
     g["tick_size"], g["rate"] = tick_size, p_cancel
     g["decay"], g["demand"], g["scale"], g["order_ratio"] = decay, demand, scale, order_ratio
     g["mu"], g["sigma"] = price_dist_mu, price_dist_sigma
@@ -422,11 +423,11 @@ def momentum_group(agent_id_start, n_agents, tick_size, p_cancel, trade_vol, dec
 
 
 def noise_group(agent_id_start, n_agents, tick_size, p_limit, p_market, p_cancel, trade_vol, price_dist_mu,
-                price_dist_sigma):
-    """NoiseAgent::new + NoiseAgentParams (crates/step_sim/src/agents/noise_agent.rs:14-44, 98-114)."""
+                price_dist_sigma, live_cap: int = 0):
+    """NoiseAgent::new + NoiseAgentParams (crates/step_sim/src/agents/noise_agent.rs:14-44, 98-114); `live_cap` as above."""
     g = np.zeros(1, dtype=abi.GROUP_DTYPE)[0]
     g["kind"], g["n_agents"] = abi.GROUP_NOISE, n_agents
-    g["tick_lo"], g["vol_lo"] = agent_id_start, trade_vol
+    g["tick_lo"], g["vol_lo"], g["vol_hi"] = agent_id_start, trade_vol, live_cap
     g["tick_size"], g["rate"] = tick_size, p_cancel
     g["decay"], g["demand"] = p_limit, p_market
     g["mu"], g["sigma"] = price_dist_mu, price_dist_sigma

@@ -57,6 +57,7 @@ struct bb_handle {
     unsigned long long* d_stats = nullptr;
     u32* rslot = nullptr;
     MomState* mom = nullptr;
+    u32 mom_cap = LIVE_CAP, mom_stride = MOM_HDR_BYTES + 4u * LIVE_CAP;  // live-list entries / bytes per MomState record
     uint4* scratch = nullptr;
     size_t scratch_warps = 0;
     u64* d_ids = nullptr;  // bb_step_device: ids assigned on the device when the caller does not ask for them
@@ -298,7 +299,7 @@ int init_books(bb_handle* h) {
         return BB_OK;
     }
     k_init<<<c.n_envs, 64, 0, h->stream>>>(h->blobs, h->blob_stride, c.n_envs, h->p_total, c.start_time, c.trading ? 1u : 0u,
-                                           h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups, h->dgeo, h->dense_lp, h->dense_nwmax);
+                                           h->d_seeds, h->rslot, h->agents_per_env, h->mom, h->mom_groups, h->mom_stride, h->dgeo, h->dense_lp, h->dense_nwmax);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, 4, h->stream));
     h->status_valid = false;
@@ -777,7 +778,7 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
             if (asset[i] >= h->assets) return fail(h, BB_EINVAL, "agent group asset index out of range");
     }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    u32 total = 0, mom = 0;
+    u32 total = 0, mom = 0, mom_cap = LIVE_CAP;
     for (u32 i = 0; i < n_groups; ++i) {
         const bb_agent_group& g = groups[i];
         if (g.kind == BB_GROUP_RANDOM) {
@@ -786,6 +787,8 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
         } else if (g.kind == BB_GROUP_MOMENTUM || g.kind == BB_GROUP_NOISE) {
             if ((u64)g.tick_lo + g.n_agents >= (1u << 19)) return fail(h, BB_EINVAL, "momentum trader ids must stay below 2^19");
             if (g.tick_size == 0 || g.n_agents == 0) return fail(h, BB_EINVAL, "momentum group needs tick_size and n_agents > 0");
+            if (g.vol_hi > (1u << 20)) return fail(h, BB_EINVAL, "live-order list capacity (vol_hi of a momentum / noise group) above 2^20");
+            mom_cap = std::max(mom_cap, g.vol_hi);  // 0 = the default
             ++mom;
         } else {
             return fail(h, BB_EINVAL, "unknown agent group kind");
@@ -797,7 +800,8 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
     // agent state is (re)allocated only when the population's shape changes: cudaFree / cudaMalloc synchronise the
     // whole device and cost ~100 ms next to tens of GB of slabs, which used to dominate the end-to-end pass
     const size_t ne = h->cfg.n_envs;
-    if (total != h->agents_per_env || mom != h->mom_groups || (total && !h->rslot) || (mom && !h->mom)) {
+    mom_cap = (mom_cap + 1u) & ~1u;  // (records stay 8-byte aligned)
+    if (total != h->agents_per_env || mom != h->mom_groups || mom_cap != h->mom_cap || (total && !h->rslot) || (mom && !h->mom)) {
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(h->rslot); h->rslot = nullptr;
         cudaFree(h->mom); h->mom = nullptr;
@@ -806,7 +810,9 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
         h->groups.clear(); h->group_asset.clear();
         h->agents_per_env = h->mom_groups = h->chip_agents = 0;
         if (total) CUDA_TRY(h, cudaMalloc(&h->rslot, ne * total * 4));
-        if (mom) CUDA_TRY(h, cudaMalloc(&h->mom, ne * mom * sizeof(MomState)));
+        h->mom_cap = mom_cap;
+        h->mom_stride = MOM_HDR_BYTES + 4u * mom_cap;
+        if (mom) CUDA_TRY(h, cudaMalloc(&h->mom, ne * mom * (size_t)h->mom_stride));
     }
     h->groups.assign(groups, groups + n_groups);
     h->group_asset.clear();
@@ -825,7 +831,7 @@ static int set_agents_impl(bb_handle* h, const bb_agent_group* groups, const uin
     h->mom_groups = mom;
     h->lay_sim = make_layout(h, true, false, h->eng >= ENG_DENSE, asset != nullptr);  // the on-chip agent state depends on the population
     if (total) CUDA_TRY(h, cudaMemsetAsync(h->rslot, 0xFF, ne * total * 4, h->stream));
-    if (mom) CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * sizeof(MomState), h->stream));
+    if (mom) CUDA_TRY(h, cudaMemsetAsync(h->mom, 0, ne * mom * (size_t)h->mom_stride, h->stream));
     return BB_OK;
 }
 
@@ -1027,6 +1033,8 @@ int run_agents_impl(bb_handle* h, uint64_t seed, uint32_t n_steps, const ExtRows
     p.agents_per_env = h->agents_per_env;
     p.chip_agents = h->chip_agents;
     p.mom_groups_per_env = h->mom_groups;
+    p.mom_stride = h->mom_stride;
+    p.mom_live_cap = h->mom_cap;
     p.rslot = h->rslot;
     p.mom = h->mom;
     p.seed_lo = (u32)seed;

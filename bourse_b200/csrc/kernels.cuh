@@ -19,17 +19,21 @@ namespace bb {
 #define MODE_REPLAY 0
 #define MODE_ENV 1
 #define MAX_GROUPS 8
-#define LIVE_CAP 254  // MomentumAgent live-order list capacity per group per env
+#define LIVE_CAP 254  // default capacity of a MomentumAgent / NoiseAgent live-order list (per group per env)
 // env-steps of observation records staged in shared memory per bulk store: 8 level-1 records (288 B) or 4 level-2
 // records (720 B); both are multiples of 16 bytes and keep the staging area under 1.5 KB per book
 #define OBS_STAGE_STEPS(obs_words) ((obs_words) > 9u ? 4u : 8u)
 
-struct MomState {  // 1040 bytes per (env, momentum group)
+// The reference keeps the ids of a MomentumAgent's resting limit orders in a Vec (momentum_agent.rs:99-102, common.rs:56-75).
+// Here the list is an array of KParams::mom_live_cap entries (the largest capacity any group of the population asked for,
+// bb_agent_group::vol_hi; 254 by default) behind a 24-byte header; records are KParams::mom_stride bytes apart.
+struct MomState {
     double momentum, last_price;
     u32 has_last, n_live;
-    u32 live[LIVE_CAP];
+    u32 live[2];  // [mom_live_cap]
 };
-static_assert(sizeof(MomState) == 16 + 8 + 4 * LIVE_CAP, "MomState layout");
+#define MOM_HDR_BYTES 24u
+static_assert(sizeof(MomState) == MOM_HDR_BYTES + 8, "MomState layout");
 
 struct KParams {
     unsigned char* blobs;
@@ -57,6 +61,7 @@ struct KParams {
     u32* obs_out;    // [n_envs][obs_words] or null: the step's observation record, also written here (bb_step_device)
     // k_sim
     u32 n_groups, agents_per_env, mom_groups_per_env;
+    u32 mom_stride, mom_live_cap;  // bytes between MomState records; entries in each live list
     u32 chip_agents;  // dense engine: capacity of the on-chip agent tables (agents_per_env; markets: the largest per-asset count)
     u32* rslot;
     MomState* mom;
@@ -559,7 +564,7 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
             const u32 pos = e.n + before;
             if (pos < p.max_queue) q[pos] = make_uint4(1u | (limit_bid ? 2u : 0u) | (trader << 13), id_l, price, ag.vol_lo);
             const u32 lpos = n_keep + __popc(lm & ((1u << lane) - 1u));
-            if (lpos < LIVE_CAP) ms->live[lpos] = id_l; else err |= ERR_CAP_LIVE;
+            if (lpos < p.mom_live_cap) ms->live[lpos] = id_l; else err |= ERR_CAP_LIVE;
         }
         if (do_market) {
             const u32 pos = e.n + before + (do_limit ? 1u : 0u);
@@ -567,7 +572,7 @@ __device__ __noinline__ MomOut momentum_agent_update(const KParams& p, const bb_
             if (pos < p.max_queue)
                 q[pos] = make_uint4(1u | (market_bid ? 2u : 0u) | (trader << 13), id_m, market_bid ? 0xFFFFFFFFu : 0u, ag.vol_lo);
         }
-        n_keep = min(n_keep + __popc(lm), (u32)LIVE_CAP);
+        n_keep = min(n_keep + __popc(lm), p.mom_live_cap);
         e.n += total;
         e.next_id += total;
     }
@@ -708,7 +713,7 @@ __global__ void __launch_bounds__(128, ENG == ENG_PAGED ? 5 : 7) k_sim(const __g
                 } else {
                     if (mine) {
                         const MomOut mo = momentum_agent_update(p, ag, b.oh, lane, best_price(g, b, 1), best_price(g, b, 0), q, e.n,
-                                                                e.next_id, p.mom + (size_t)env * p.mom_groups_per_env + mi, env_g,
+                                                                e.next_id, (MomState*)((char*)p.mom + ((size_t)env * p.mom_groups_per_env + mi) * p.mom_stride), env_g,
                                                                 step, gi, slot_base);
                         e.n = mo.n;
                         e.next_id = mo.next_id;
@@ -1466,7 +1471,7 @@ template <int ENG> __global__ void __launch_bounds__(128) k_snapshot(const __gri
 
 // fresh-book initialisation (OrderBook::new orderbook.rs:158-171 + Env::new env.rs:84-95)
 __global__ void k_init(unsigned char* blobs, u64 blob_stride, u32 n_envs, u32 p_total, u64 start_time, u32 trading,
-                       const u64* rng_seeds, u32* rslot, u32 agents_per_env, MomState* mom, u32 mom_per_env, Geo dense,
+                       const u64* rng_seeds, u32* rslot, u32 agents_per_env, MomState* mom, u32 mom_per_env, u32 mom_stride, Geo dense,
                        u32 dense_lp, u32 dense_nwmax) {
     const u32 env = blockIdx.x;
     if (env >= n_envs) return;
@@ -1502,7 +1507,7 @@ __global__ void k_init(unsigned char* blobs, u64 blob_stride, u32 n_envs, u32 p_
         for (u32 i = threadIdx.x; i < agents_per_env; i += blockDim.x) rslot[(size_t)env * agents_per_env + i] = BB_NIL;
     if (mom)
         for (u32 i = threadIdx.x; i < mom_per_env; i += blockDim.x) {
-            MomState* m = mom + (size_t)env * mom_per_env + i;
+            MomState* m = (MomState*)((char*)mom + ((size_t)env * mom_per_env + i) * mom_stride);
             m->momentum = 0.0; m->last_price = 0.0; m->has_last = 0; m->n_live = 0;
         }
 }

@@ -150,7 +150,10 @@ typedef struct {
  *         crates/step_sim/src/agents/momentum_agent.rs:16-35, 118-134
  *  kind 2 NoiseAgent::new(agent_id_start = tick_lo, n_agents, NoiseAgentParams{tick_size, p_limit = decay,
  *         p_market = demand, p_cancel = rate, trade_vol = vol_lo, mu, sigma})
- *         crates/step_sim/src/agents/noise_agent.rs:14-44, 98-114 */
+ *         crates/step_sim/src/agents/noise_agent.rs:14-44, 98-114
+ *  kinds 1 and 2: vol_hi = capacity of the agent's list of resting limit orders (the reference's Vec<OrderId>,
+ *         momentum_agent.rs:99-102; common.rs:56-75 prunes it every step); 0 => 254.  A list that would outgrow it flags
+ *         BB_ERR_CAP_LIVE.  The population's largest request sizes every group's list (4 bytes per entry per env). */
 typedef struct {
     uint32_t kind;
     uint32_t n_agents;

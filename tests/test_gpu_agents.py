@@ -159,3 +159,31 @@ def test_live_list_overflow_is_flagged_on_every_env(core, oracle):
         assert same or (err[env] & 0x80), env       # differs => flagged
         n_bad += not same
     assert n_bad > 0 and (err & 0x80).any()
+
+
+def test_live_list_capacity_is_a_parameter_of_the_group(core, oracle):
+    """The reference's live-order list is a Vec (momentum_agent.rs:99-102).  The population of the overflow test above, with
+    room for 4096 entries asked for on one group (it sizes every group's list), runs the same 60 steps without a flag and equals
+    the oracle on every env; a second population on the same handle falls back to the default size and still overflows."""
+    M = (1000, 17, 1, 0.02, 10, 0.41, 6.35, 0.75, 1.82, 0.0, 0.98)
+    N = (2000, 15, 1, 0.385, 0.198, 0.315, 7, 0.66, 1.07)
+    n_envs, n_steps = 8, 60
+    e = core.BatchedEnv(n_envs, 0, 0, 1, 1_000_000, obs_words=abi.OBS_L2, max_orders=16384, max_trades=32768, max_steps=64,
+                        max_queue=2048, pages_smem=64, pages_total=64)
+    e.set_agents([core.momentum_group(*M, live_cap=4096), core.noise_group(*N)])
+    e.run_agents(n_steps, 5)
+    assert not e.env_errors().any()
+    longest = 0
+    for env in range(n_envs):
+        o = oracle.StepEnvNumpy(0, 0, 1, 1_000_000)
+        o.set_groups([oracle.momentum_group(*M), oracle.noise_group(*N)])
+        o.run_agents(n_steps, 5, env_id=env, keyed=True)
+        assert np.array_equal(e.history(env)[:n_steps], o._history()), env
+        assert e.get_orders(env) == o.get_orders() and e.get_trades(env) == o.get_trades(), env
+        longest = max(longest, sum(1 for x in o.get_orders() if x[1] == 1 and 1000 <= x[7] < 1017))
+    assert longest > 254    # (Active orders of the momentum traders at the end: the list did outgrow the default)
+    e.reset()
+    e.set_agents([core.momentum_group(*M), core.noise_group(*N)])
+    e.run_agents(n_steps, 5, sync=False)
+    with pytest.raises(MemoryError, match="0x80"):
+        e.synchronize(); e.stats(); e.level_2_data(); e.step(1)

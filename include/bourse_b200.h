@@ -75,7 +75,7 @@ typedef struct {
     uint32_t max_orders;    /* per env */
     uint32_t max_trades;    /* per env; 0 disables the trade log (trade_vol is still tracked) */
     uint32_t max_steps;     /* per env history records (steps, or emitted snapshots in replay mode) */
-    uint32_t max_queue;     /* per env instructions per step */
+    uint32_t max_queue;     /* per env instructions per step (bb_reserve_queue grows it) */
     uint32_t pages_smem;    /* 32-level price pages per book resident in shared memory; 0 => default */
     uint32_t pages_total;   /* total pages per book (the rest live in HBM); 0 => default */
     /* Dense-window engine for shallow books (the layout BASELINE.json's north_star names: a dense tick-indexed

@@ -59,6 +59,16 @@ def test_market_agent_constructors_follow_the_rust_argument_order():
     assert n.group.tobytes() == same.tobytes()
 
 
+def test_live_list_capacity_travels_in_vol_hi():
+    """bb_agent_group::vol_hi of a Momentum / Noise group is the capacity of its live-order list (include/bourse_b200.h);
+    0, the default of the constructors, keeps the library's 254."""
+    assert core.momentum_group(0, 5, 1, 0.1, 10, 1.0, 5.0, 0.5, 1.0, 0.0, 1.0)["vol_hi"] == 0
+    assert core.momentum_group(0, 5, 1, 0.1, 10, 1.0, 5.0, 0.5, 1.0, 0.0, 1.0, live_cap=4096)["vol_hi"] == 4096
+    assert core.noise_group(10, 4, 2, 0.5, 0.25, 0.1, 100, 0.0, 1.0, live_cap=777)["vol_hi"] == 777
+    # C4's population asks for nothing beyond the default: the benched configuration is unchanged
+    assert all(int(g["vol_hi"]) == 0 for g in workloads.c4_groups() if int(g["kind"]) != abi.GROUP_RANDOM)
+
+
 def test_market_example_population():
     groups, assets = workloads.market_example_groups()        # crates/step_sim/examples/multi_asset/main.rs:15-20
     assert assets == [0, 0, 1, 1] and len(groups) == 4

@@ -52,6 +52,7 @@ def _check_book_conservation(env, e, final_obs):
 # bench.py's headline line prints this checksum (`l1_checksums`) for the same config and seed: FNV-1a over every env's final
 # level-1 record.  The test below checks the run that produces it against the oracle, on BOTH engines.
 C3_L1_CHECKSUM = {}
+C3_BENCH_L1_CHECKSUM = 154729883691269768   # rank 0's entry of `l1_checksums` in the BENCH line (4096 envs, seed 101, env ids 0..4095)
 
 
 @pytest.mark.parametrize("engine_kw", ["bench", dict()], ids=["dense_bench_config", "paged"])
@@ -73,6 +74,7 @@ def test_c3_full_size(core, oracle, engine_kw):
     if len(C3_L1_CHECKSUM) == 2:   # both engines end every one of the 4096 books in the same state
         assert C3_L1_CHECKSUM[True] == C3_L1_CHECKSUM[False]
     print("C3 l1_checksum", st["l1_checksum"])
+    assert st["l1_checksum"] == C3_BENCH_L1_CHECKSUM   # the run checked here IS the run the bench line reports
     hist = env.history_all(n_steps)
     assert st["env_steps"] == n_envs * n_steps and st["error_envs"] == 0
     # checksum of checksums: three independent read-back paths agree

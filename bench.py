@@ -135,8 +135,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args.gpus, sample=f"each step = all {N_ENVS_PER_GPU} envs x {N_SIM_STEPS} env-steps of one GPU's shard, on the host cores; "
-                                                     "the CPU arm is the oracle's C++ restatement (std::map where the reference uses BTreeMap), not the Rust build"),
+        # the SAME config object as the b200 arm prints (the driver compares them); what a reference step is goes below
+        "config": workload_config(args.gpus),
+        "note": f"each step = all {N_ENVS_PER_GPU} envs x {N_SIM_STEPS} env-steps of one GPU's shard, on the host cores; the CPU arm is the "
+                "oracle's C++ restatement (std::map where the reference uses BTreeMap), not the Rust build",
         "env_steps_per_sec": sum(r["env_steps_per_sec"] * r["seconds"] for r in vals) / tot_s,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": vals[-1]["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -281,7 +283,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic", "config": dict(workload_config(world), engine=args.engine),
+            "dtype": "u32", "data": "synthetic", "config": workload_config(world), "engine": args.engine,
             "env_steps_per_sec": env_steps_per_pass * args.steps / (max_ms * 1e-3),
             "orders_per_pass": instr_per_pass, "trades_per_pass": agg["trades"], "l1_checksums": agg["l1_checksums"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
